@@ -1,0 +1,331 @@
+"""bench.py — the plan-step benchmark (BASELINE.json metric: rollouts/sec per control step; plan latency p50).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cartpole_mppi|cylinder_push_cem|leap_cube_mppi]
+  python bench.py --impl reference ...        # the reference's CPU path (oracle port; MuJoCo is not installable here)
+  torchrun --nproc-per-node N bench.py --gpus N ...   # one rank per GPU, weak scaling: every rank owns n_rollouts
+
+A "step" is one plan step over one batch of candidates: spline -> N x H dynamics rollout -> per-step cost ->
+MPPI/CEM/PS update.  `value` times it with candidates already resident in HBM (CUDA events, L2 flushed between
+iterations); `e2e` times the public API call with HOST buffers (pinned staging, H2D + D2H inside).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on at N=1
+    "cartpole_mppi": dict(task="cartpole", optimizer="mppi", n_rollouts=4096, H=64, K=4, order="zero", horizon=2.56,
+                          algo_bytes_per_rollout=276),
+    "cylinder_push_cem": dict(task="cylinder_push", optimizer="cem", n_rollouts=2048, H=50, K=4, order="zero", horizon=1.0,
+                              algo_bytes_per_rollout=236),
+    "leap_cube_mppi": dict(task="leap_cube", optimizer="mppi", n_rollouts=1024, H=40, K=4, order="cubic", horizon=0.4,
+                           algo_bytes_per_rollout=420),
+}
+
+
+def problem(w: dict, n_total: int, seed: int = 42):
+    """Synthetic inputs exactly as SURVEY.md §8(d): seed 42, the task's own reset distribution, nominal warm start 0."""
+    from judo_b200.optimizers import get_registered_optimizers
+    from judo_b200.spline import spline_basis
+    from judo_b200.tasks import get_registered_tasks
+
+    np.random.seed(seed)
+    task_cls, _ = get_registered_tasks()[w["task"]]
+    task = task_cls()                       # reset() draws x0 from the task's distribution
+    x0 = np.concatenate([task.data.qpos, task.data.qvel])
+    opt_cls, cfg_cls = get_registered_optimizers()[w["optimizer"]]
+    cfg = cfg_cls()
+    cfg.set_override(w["task"])
+    cfg.num_rollouts, cfg.num_nodes = n_total, w["K"]
+    opt = opt_cls(cfg, task.nu)
+    nominal = np.tile(task.optimizer_warm_start(), (w["K"], 1))
+    lo, hi = task.actuator_ctrlrange[:, 0], task.actuator_ctrlrange[:, 1]
+    knots = np.clip(opt.sample_control_knots(nominal), lo, hi)
+    times = np.linspace(0, w["horizon"], w["K"], endpoint=True)
+    basis = spline_basis(times, task.dt * np.arange(w["H"]), w["order"])
+    meta = task.get_sim_metadata() if hasattr(task, "get_sim_metadata") else {}
+    params = task.cost_params(meta)
+    return task, opt, x0, knots, basis, params
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int) -> None:
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self) -> None:
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a) -> None:  # noqa: ANN002
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_port_plan_step(w: dict, x0, knots, basis, params, opt, nthread: int = 0) -> np.ndarray:
+    """The reference's plan step on the CPU with the oracle physics: spline eval (the same linear map scipy's interp1d
+    applies), oracle rollouts (all host cores), NumPy reward and optimizer update — what Controller.update_action does
+    after sampling (controller.py:261-288)."""
+    from oracle import plan as op
+
+    om = cpu_port_plan_step.models.setdefault(w["task"], _oracle_model(w["task"]))
+    controls = np.einsum("hk,nkj->nhj", basis, knots)
+    states, _ = om.rollout(x0, controls, nthread=nthread)
+    if w["task"] == "cartpole":
+        r = op.cartpole_reward(states, controls, *params)
+    elif w["task"] == "cylinder_push":
+        r = op.cylinder_push_reward(states, controls, params[0], params[1], params[2], params[3], params[4:6])
+    else:
+        r = op.leap_cube_reward(states, params[2:6], params[0], params[1])
+    if w["optimizer"] == "mppi":
+        return op.mppi_update(knots, r, opt.temperature)
+    if w["optimizer"] == "cem":
+        return op.cem_update(knots, r, opt.num_elites, opt.sigma_min, opt.sigma_max)[0]
+    return op.ps_update(knots, r)
+
+
+cpu_port_plan_step.models = {}
+
+
+def _oracle_model(task: str):
+    from oracle.mjc import OracleModel, load_table
+
+    if task == "leap_cube":
+        from judo_b200.tasks.leap_cube import reduced_collision_model
+
+        tb = load_table(task)
+        geoms, pairs = reduced_collision_model(tb)
+        return OracleModel(tb, pairs=pairs, geoms=geoms)
+    return OracleModel(task)
+
+
+def time_cpu(w: dict, x0, knots, basis, params, opt, budget_s: float, n_sample: int) -> dict:
+    ks = knots[:n_sample]
+    cpu_port_plan_step(w, x0, ks[: min(64, n_sample)], basis, params, opt)  # warm-up (thread pool, page-in)
+    t0, reps, times = time.perf_counter(), 0, []
+    while True:
+        t1 = time.perf_counter()
+        cpu_port_plan_step(w, x0, ks, basis, params, opt)
+        times.append(time.perf_counter() - t1)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 50:
+            break
+    med = statistics.median(times)
+    return {"value": n_sample / med, "unit": "rollouts/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{reps} plan steps of {n_sample} rollouts x H={w['H']} ({w['task']}), oracle C port with OpenMP on all host cores + NumPy "
+                      f"reward/update; median {med * 1e3:.2f} ms/step", "ms_per_step": med * 1e3}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cartpole_mppi", choices=list(WORKLOADS))
+    ap.add_argument("--n-rollouts", type=int, default=0, help="per-GPU rollouts (default: the workload's)")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.n_rollouts:
+        w["n_rollouts"] = args.n_rollouts
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    n_local = w["n_rollouts"]
+    n_total = n_local * world
+    config = {"workload": f"{w['task']}+{w['optimizer']} N={n_local}/GPU H={w['H']} K={w['K']} spline={w['order']} (BASELINE config "
+                          f"{'C2' if args.workload == 'cartpole_mppi' else 'C3' if args.workload == 'cylinder_push_cem' else 'C4'})",
+              "n_rollouts_per_gpu": n_local, "n_rollouts_total": n_total, "horizon_steps": w["H"], "num_nodes": w["K"],
+              "parallelism": f"rollout-sharded x{world}", "l2": "flushed (256 MiB memset) between timed iterations",
+              "contract": "B (fused: knots in, cost matrix f32 + reward out)"}
+
+    # ------------------------------------------------------------------ reference arm: CPU path on the host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        task, opt, x0, knots, basis, params = problem(w, n_local)
+        # bounded sample per step so that steps+warmup finish within minutes
+        n_sample = min(n_local, 4096 if w["task"] != "leap_cube" else 256)
+        for _ in range(min(args.warmup, 3)):
+            cpu_port_plan_step(w, x0, knots[:n_sample], basis, params, opt)
+        steps = max(1, min(args.steps, 30))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_port_plan_step(w, x0, knots[:n_sample], basis, params, opt)
+        dt = (time.perf_counter() - t0) / steps
+        val = n_sample / dt
+        cb = {"value": val, "unit": "rollouts/s", "cores": os.cpu_count(), "kind": "port",
+              "sample": f"{steps} plan steps of {n_sample} rollouts x H={w['H']}; oracle C port (OpenMP, all host cores) + NumPy"}
+        print(json.dumps({"impl": "reference", "metric": "rollouts/sec per control step", "value": val, "unit": "rollouts/s", "n_gpus": args.gpus,
+                          "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": val, "unit": "rollouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "note": "reference CPU path = mujoco 3.5.0 (not installable offline); timed here: restated CPU oracle"}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+        torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    from judo_b200.dist import ShardedPlanner, shard_range
+
+    task, opt, x0, knots_all, basis, params = problem(w, n_total)
+    lo, hi = shard_range(n_total, world, rank)
+    knots = np.ascontiguousarray(knots_all[lo:hi])
+    opt_params = opt.fused_params()
+    planner = ShardedPlanner(w["task"], n_local, device=local_rank, rank=rank, world_size=world)
+    planner.set_problem(x0, basis, params, want_cost_matrix=True)
+    planner.set_knots(knots)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier() -> None:
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        planner.step(w["optimizer"], opt_params, index_offset=lo)
+    barrier()
+    launches0 = planner.engine.launch_count
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k_ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    import ctypes
+
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()                                  # evict L2 between timed iterations (outside the events)
+            starts[i].record()
+            # dominant kernel alone (for the roofline) is bracketed inside the step by a second event
+            planner.step(w["optimizer"], opt_params, index_offset=lo)
+            ends[i].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = sum(step_ms)
+    launches = planner.engine.launch_count - launches0
+
+    # dominant kernel alone: rollout+cost, timed live with events on the launching stream, L2 flushed
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
+    kms = []
+    for i in range(min(args.steps, 50)):
+        flush.zero_()
+        starts[i].record()
+        planner._check(planner.lib.b200mpc_plan_costs_dev(planner.engine.handle, P(planner.d_x0), P(planner.d_knots), n_local, w["K"],
+                                                          P(planner.d_basis), w["H"], P(planner.d_params), P(planner.d_cost), P(planner.d_reward), st))
+        k_ends[i].record()
+    torch.cuda.synchronize(dev)
+    kms = [starts[i].elapsed_time(k_ends[i]) for i in range(min(args.steps, 50))]
+    kernel_ms = statistics.mean(kms)
+
+    # max over ranks
+    tt = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = float(tt[0]), float(tt[1])
+    ms_per_step = total_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # ---- e2e: the public API call with HOST buffers (one pinned H2D + kernels + one D2H inside every call)
+    eng = planner.engine
+    e2e_times = []
+    for i in range(max(args.warmup, 3) + args.steps):
+        if dist is not None and i == max(args.warmup, 3):
+            barrier()
+        t1 = time.perf_counter()
+        res = eng.plan_step(x0, knots, basis, params, w["optimizer"], opt_params, want_rewards=True, n_elite=5)
+        e2e_times.append(time.perf_counter() - t1)
+    e2e_times = e2e_times[max(args.warmup, 3):]
+    e2e_tt = torch.tensor([sum(e2e_times), statistics.median(e2e_times)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_tt, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_tt[0]) / args.steps * 1e3
+    h2d = x0.nbytes + basis.nbytes + params.nbytes + knots.nbytes
+    d2h = 2 * res["nominal"].nbytes + 5 * 8 + n_local * 8
+    e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": "rollouts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "plan_latency_p50_ms": float(e2e_tt[1]) * 1e3,
+           "note": "Engine.plan_step per rank with host buffers; multi-GPU e2e = independent per-rank plans (no exchange on the host path)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    algo_bytes = w["algo_bytes_per_rollout"] * n_local
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
+                "kernel": "rollout_kernel<Task, COST> (fused spline+dynamics+cost)", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "note": "N independent serial recurrences: latency/issue-bound by construction, HBM fraction is expected to be <<1% "
+                        "(SURVEY.md §8d); see profiles/ for occupancy and stall reasons"}
+    cpu = time_cpu(w, x0, knots, basis, params, opt, args.cpu_budget, min(n_local, 4096 if w["task"] != "leap_cube" else 256))
+    out = {"metric": "rollouts/sec per control step", "value": value, "unit": "rollouts/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": config, "state_steps_per_s": value * w["H"],
+           "plan_latency_p50_ms": statistics.median(step_ms), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+           "gpu_launches": int(launches), "clocks": clocks.summary(), "wall_s_timed_region": t_wall}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+/* b200mpc.h — C ABI of the B200 rollout engine (libb200mpc.so).
+ *
+ * Drop-in boundary for judo's sampling-MPC plan step.  Plain pointers and sizes only; no
+ * torch / numpy / MuJoCo types.  All host arrays are C-contiguous float64 unless stated.  Every function
+ * returns 0 on success, non-zero on failure; b200mpc_last_error() gives the message.  Not re-entrant per
+ * handle (the reference calls the backend under ControllerNode.lock, judo/app/dora/controller.py:131-140);
+ * several handles per process are fine (one per GPU).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to /root/reference).
+ */
+#ifndef B200MPC_H
+#define B200MPC_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200mpc_handle b200mpc_handle;
+
+enum { B200MPC_TASK_CARTPOLE = 0, B200MPC_TASK_CYLINDER_PUSH = 1, B200MPC_TASK_LEAP_CUBE = 2 };
+enum { B200MPC_OPT_MPPI = 0, B200MPC_OPT_CEM = 1, B200MPC_OPT_PS = 2 };
+
+/* Task dimensions as the reference's MjModel reports them (nq, nv, nu, nsensordata). */
+typedef struct { int nq, nv, nu, nsensordata, n_cost_params; } b200mpc_dims;
+
+/* ---- lifetime -------------------------------------------------------------------------------------------
+ * Replaces: MJRolloutBackend.__init__ (judo/utils/mj_rollout_backend.py:21-36), which deep-copies an MjModel
+ * per thread.  Here the model is a flat constant table (task_consts: doubles, layout per task documented in
+ * judo_b200/consts.py) baked from the task's MJCF; num_rollouts sizes the device buffers. */
+int b200mpc_create(b200mpc_handle** out, int task_id, const double* task_consts, size_t n_consts, int device,
+                   int num_rollouts);
+void b200mpc_destroy(b200mpc_handle* h);
+const char* b200mpc_last_error(const b200mpc_handle* h); /* h may be NULL: error of the last failed create */
+int b200mpc_get_dims(const b200mpc_handle* h, b200mpc_dims* out);
+
+/* Replaces: RolloutBackend.update(num_threads) (judo/utils/rollout_backend.py:40-46; called from
+ * judo/controller/controller.py:225-226 when num_rollouts changes). */
+int b200mpc_update(b200mpc_handle* h, int num_rollouts);
+int b200mpc_num_rollouts(const b200mpc_handle* h);
+
+/* ---- contract A: drop-in rollout ---------------------------------------------------------------------------
+ * Replaces: RolloutBackend.rollout / MJRolloutBackend.rollout (judo/utils/rollout_backend.py:20-38,
+ * judo/utils/mj_rollout_backend.py:45-88).
+ *   x0        (nq+nv) if !x0_batched else (N, nq+nv)
+ *   controls  (N, H, nu)
+ *   states    (N, H, nq+nv)  OUT: state after applying controls[:, t]
+ *   sensors   (N, H, nsensordata) OUT, may be NULL
+ * N must equal the handle's num_rollouts (the reference asserts the same, mj_rollout_backend.py:82). */
+int b200mpc_rollout(b200mpc_handle* h, const double* x0, int x0_batched, const double* controls, int N, int H,
+                    double* states, double* sensors);
+
+/* ---- contract B: fused spline -> rollout -> per-step cost -----------------------------------------------------
+ * Replaces the Python sequence make_spline + spline eval + rollout + Task.reward
+ * (judo/controller/controller.py:261-285; rewards judo/tasks/{cartpole.py:42-78,cylinder_push.py:50-93,
+ * leap_cube.py:63-88}).
+ *   knots        (N, K, nu)   candidate knots, already clipped/denormalised (controller.py:253-258)
+ *   basis        (H, K)       spline basis: controls[n,t,:] = sum_k basis[t,k] * knots[n,k,:] (interp1d is linear
+ *                             in the knots; judo_b200/spline.py builds it)
+ *   cost_params  task-specific weights (b200mpc_dims.n_cost_params doubles; see judo_b200/consts.py)
+ *   cost_NH      (N, H) float32 OUT per-step cost, may be NULL
+ *   reward_N     (N) OUT reward as Task.reward returns it (negative total / mean cost) */
+int b200mpc_plan_costs(b200mpc_handle* h, const double* x0, const double* knots, int N, int K, const double* basis,
+                       int H, const double* cost_params, float* cost_NH, double* reward_N);
+
+/* Reward only, from given trajectories: replaces Task.reward(states, sensors, controls, metadata)
+ * (judo/tasks/base.py:55-76) for the built-in tasks when the caller used contract A.
+ *   states (N,H,nq+nv), controls (N,H,nu) -> reward_N (N) */
+int b200mpc_reward(b200mpc_handle* h, const double* states, const double* controls, int N, int H, const double* cost_params,
+                   double* reward_N);
+
+/* ---- optimizer updates ----------------------------------------------------------------------------------------
+ * Replace: MPPI.update_nominal_knots (judo/optimizers/mppi.py:61-82),
+ *          CrossEntropyMethod.update_nominal_knots (judo/optimizers/cem.py:76-92; ties: higher index first),
+ *          PredictiveSampling.update_nominal_knots (judo/optimizers/ps.py:52-65; first maximum).
+ *   knots (N,K,nu), rewards (N) -> nominal (K,nu); CEM also writes sigma (K,nu) = clip(std(elites), min, max). */
+int b200mpc_update_mppi(b200mpc_handle* h, const double* knots, const double* rewards, int N, int K, double temperature,
+                        double* nominal);
+int b200mpc_update_cem(b200mpc_handle* h, const double* knots, const double* rewards, int N, int K, int num_elites,
+                       double sigma_min, double sigma_max, double* nominal, double* sigma);
+int b200mpc_update_ps(b200mpc_handle* h, const double* knots, const double* rewards, int N, int K, double* nominal);
+
+/* ---- fused plan step (one H2D, three kernels, one D2H) ------------------------------------------------------------
+ * Replaces one iteration of the while-loop body in Controller.update_action (controller.py:261-288) after
+ * sampling/clipping.  opt_params: MPPI {temperature}; CEM {num_elites, sigma_min, sigma_max}; PS {}.
+ *   nominal (K,nu) OUT; sigma (K,nu) OUT (CEM only, else may be NULL); reward_N (N) OUT, may be NULL;
+ *   elite_idx (n_elite) OUT indices of the best rollouts in descending reward order, may be NULL (n_elite=0) */
+int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const double* knots, int N, int K, const double* basis, int H,
+                      const double* cost_params, int optimizer, const double* opt_params, double* nominal, double* sigma,
+                      double* reward_N, int* elite_idx, int n_elite);
+
+/* ---- resident (device-pointer) API: inputs/outputs already in HBM, asynchronous on `stream` ------------------------
+ * Used by bench.py's device-resident measurement and by the multi-GPU sharded plan step (judo_b200/dist.py), where
+ * torch owns the allocations and NCCL moves the partials.  All pointers are device pointers; stream is a
+ * cudaStream_t passed as void*.  Partials layout (doubles): MPPI  [beta, S, V[K*nu]];
+ * top-k  k x [reward, global_index, knots[K*nu]]. */
+int b200mpc_plan_costs_dev(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K,
+                           const double* d_basis, int H, const double* d_cost_params, float* d_cost_NH,
+                           double* d_reward_N, void* stream);
+int b200mpc_rollout_dev(b200mpc_handle* h, const double* d_x0, int x0_batched, const double* d_controls, int N, int H,
+                        double* d_states, double* d_sensors, void* stream);
+int b200mpc_mppi_partial_dev(b200mpc_handle* h, const double* d_knots, const double* d_rewards, int N, int KNU,
+                             double temperature, double* d_partial, void* stream);
+int b200mpc_mppi_combine_dev(b200mpc_handle* h, const double* d_partials, int n_partials, int KNU, double temperature,
+                             double* d_nominal, void* stream);
+int b200mpc_topk_partial_dev(b200mpc_handle* h, const double* d_knots, const double* d_rewards, int N, int KNU, int k,
+                             int index_offset, int prefer_high_index, double* d_partial, void* stream);
+int b200mpc_topk_combine_dev(b200mpc_handle* h, const double* d_partials, int n_partials, int KNU, int k,
+                             int prefer_high_index, double sigma_min, double sigma_max, double* d_nominal,
+                             double* d_sigma, double* d_elite_idx, void* stream);
+
+/* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
+long long b200mpc_launch_count(const b200mpc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

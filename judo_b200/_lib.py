@@ -1,0 +1,66 @@
+"""ctypes binding of libb200mpc.so (include/b200mpc.h).  Fails loudly when the CUDA library is missing:
+there is NO CPU fallback on the product path."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200mpc.so")
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_fp = ctypes.POINTER(ctypes.c_float)
+_ip = ctypes.POINTER(ctypes.c_int)
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_d = ctypes.c_double
+
+
+class Dims(ctypes.Structure):
+    _fields_ = [("nq", _i), ("nv", _i), ("nu", _i), ("nsensordata", _i), ("n_cost_params", _i)]
+
+
+# symbol -> (restype, argtypes); mirrors include/b200mpc.h one to one
+SIGNATURES = {
+    "b200mpc_create": (_i, [ctypes.POINTER(_vp), _i, _dp, ctypes.c_size_t, _i, _i]),
+    "b200mpc_destroy": (None, [_vp]),
+    "b200mpc_last_error": (ctypes.c_char_p, [_vp]),
+    "b200mpc_get_dims": (_i, [_vp, ctypes.POINTER(Dims)]),
+    "b200mpc_update": (_i, [_vp, _i]),
+    "b200mpc_num_rollouts": (_i, [_vp]),
+    "b200mpc_rollout": (_i, [_vp, _dp, _i, _dp, _i, _i, _dp, _dp]),
+    "b200mpc_plan_costs": (_i, [_vp, _dp, _dp, _i, _i, _dp, _i, _dp, _fp, _dp]),
+    "b200mpc_reward": (_i, [_vp, _dp, _dp, _i, _i, _dp, _dp]),
+    "b200mpc_update_mppi": (_i, [_vp, _dp, _dp, _i, _i, _d, _dp]),
+    "b200mpc_update_cem": (_i, [_vp, _dp, _dp, _i, _i, _i, _d, _d, _dp, _dp]),
+    "b200mpc_update_ps": (_i, [_vp, _dp, _dp, _i, _i, _dp]),
+    "b200mpc_plan_step": (_i, [_vp, _dp, _dp, _i, _i, _dp, _i, _dp, _i, _dp, _dp, _dp, _dp, _ip, _i]),
+    "b200mpc_plan_costs_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "b200mpc_rollout_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "b200mpc_mppi_partial_dev": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp]),
+    "b200mpc_mppi_combine_dev": (_i, [_vp, _vp, _i, _i, _d, _vp, _vp]),
+    "b200mpc_topk_partial_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "b200mpc_topk_combine_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp]),
+    "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m judo_b200.build` (nvcc, sm_100a). "
+                "judo_b200 has no CPU fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library ever diverge
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

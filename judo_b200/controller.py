@@ -1,0 +1,283 @@
+"""Controller — mirror of judo/controller/controller.py:34-442 around the B200 engine.
+
+``update_action`` keeps the reference's sequence (controller.py:210-299): time-shift the nominal spline,
+pre_optimization, then per iteration  sample -> clip -> (spline -> rollout -> reward -> update)  and finally the
+spline / trace refresh.  The bracketed part is ONE fused call (Engine.plan_step: one H2D copy, the fused rollout+cost
+kernel, the optimizer-update reduction, one D2H copy) whenever the task has a fused kernel; a user Task with its own
+NumPy ``reward`` goes through the drop-in RolloutBackend contract instead (still GPU rollouts).
+"""
+
+from __future__ import annotations
+
+import warnings
+from dataclasses import dataclass
+from typing import Literal
+
+import numpy as np
+
+from judo_b200.config import OverridableConfig, set_config_overrides
+from judo_b200.normalization import IdentityNormalizer, Normalizer, make_normalizer, normalizer_registry
+from judo_b200.optimizers import Optimizer, OptimizerConfig, get_registered_optimizers
+from judo_b200.rollout_backend import B200RolloutBackend, RolloutBackend
+from judo_b200.spline import spline_basis
+from judo_b200.tasks import Task, TaskConfig, get_registered_tasks
+
+
+@dataclass
+class ControllerConfig(OverridableConfig):
+    """judo/controller/controller.py:34-42."""
+
+    horizon: float = 1.0
+    spline_order: Literal["zero", "linear", "cubic"] = "linear"
+    control_freq: float = 20.0
+    max_opt_iters: int = 1
+    max_num_traces: int = 5
+    action_normalizer: Literal["none", "min_max", "running"] = "none"
+
+
+# judo/controller/overrides.py:7-44
+set_config_overrides("cylinder_push", ControllerConfig, {"horizon": 1.0, "spline_order": "zero"})
+set_config_overrides("cartpole", ControllerConfig, {"horizon": 1.0, "spline_order": "zero"})
+set_config_overrides("leap_cube", ControllerConfig, {"horizon": 1.0, "spline_order": "cubic", "max_num_traces": 1})
+
+
+class Spline:
+    """Callable nominal spline: what make_spline(times, knots, order) returns in the reference (controller.py:382-401)."""
+
+    def __init__(self, times: np.ndarray, knots: np.ndarray, order: str) -> None:
+        self.times, self.knots, self.order = np.asarray(times, dtype=np.float64), np.asarray(knots, dtype=np.float64), order
+
+    def __call__(self, query: np.ndarray | float) -> np.ndarray:
+        q = np.atleast_1d(np.asarray(query, dtype=np.float64))
+        out = np.einsum("hk,...kj->...hj", spline_basis(self.times, q, self.order), self.knots)
+        return out[..., 0, :] if np.ndim(query) == 0 else out
+
+
+def make_spline(times: np.ndarray, controls: np.ndarray, spline_order: str) -> Spline:
+    return Spline(times, controls, spline_order)
+
+
+class Controller:
+    """The controller object (judo/controller/controller.py:45-380)."""
+
+    def __init__(self, controller_config: ControllerConfig, task: Task, optimizer: Optimizer,
+                 rollout_backend: Literal["b200"] = "b200", device: int = 0) -> None:
+        self._controller_cfg = controller_config
+        self.task = task
+        self.optimizer = optimizer
+        self.available_optimizers = get_registered_optimizers()
+        self.available_tasks = get_registered_tasks()
+        self.model = self.task.model
+        self.rollout_backend: RolloutBackend = B200RolloutBackend(self.task, self.optimizer_cfg.num_rollouts, device=device)
+        self.engine = self.rollout_backend.engine
+        self.task.engine = self.engine
+        self.optimizer.bind(self.engine)
+        self._last_policy_output = None
+        self.action_normalizer = self._init_action_normalizer()
+        self.system_metadata: dict = {}
+        N, H = self.optimizer_cfg.num_rollouts, self.num_timesteps
+        self.states = np.zeros((N, H, self.model.nq + self.model.nv))
+        self.current_state = np.concatenate([self.task.data.qpos, self.task.data.qvel])
+        self.sensors = np.zeros((N, H, self.model.nsensordata))
+        self.rollout_controls = np.zeros((N, H, self.task.nu))
+        self.rewards = np.zeros((N,))
+        self.reset()
+        self.traces = None
+        self.trace_sensors = [i for i, (tp, nm) in enumerate(zip(self.model.sensor_types, self.model.sensor_names)) if tp == "framepos" and "trace" in nm]
+        self.num_trace_elites = min(self.max_num_traces, len(self.rewards))
+        self.num_trace_sensors = len(self.trace_sensors)
+        self.sensor_rollout_size = self.num_timesteps - 1
+        self.all_traces_rollout_size = self.sensor_rollout_size * self.num_trace_sensors
+        self.fused = True  # set False to force the contract-A path (rollout + Task.reward + optimizer update)
+
+    # ---- config views (controller.py:109-208) ----------------------------------------------------------------
+    horizon = property(lambda self: self.controller_cfg.horizon)
+    nu = property(lambda self: self.task.nu)
+    max_num_traces = property(lambda self: self.controller_cfg.max_num_traces)
+    max_opt_iters = property(lambda self: self.controller_cfg.max_opt_iters)
+    spline_order = property(lambda self: self.controller_cfg.spline_order)
+    action_normalizer_type = property(lambda self: self.controller_cfg.action_normalizer)
+
+    @property
+    def num_timesteps(self) -> int:
+        return int(np.ceil(self.horizon / self.task.dt))
+
+    @property
+    def rollout_times(self) -> np.ndarray:
+        return self.task.dt * np.arange(self.num_timesteps)
+
+    @property
+    def spline_timesteps(self) -> np.ndarray:
+        return np.linspace(0, self.horizon, self.optimizer_cfg.num_nodes, endpoint=True)
+
+    @property
+    def optimizer_cfg(self) -> OptimizerConfig:
+        return self.optimizer.config
+
+    @optimizer_cfg.setter
+    def optimizer_cfg(self, cfg: OptimizerConfig) -> None:
+        self.optimizer.config = cfg
+
+    @property
+    def task_config(self) -> TaskConfig:
+        return self.task.config
+
+    @task_config.setter
+    def task_config(self, cfg: TaskConfig) -> None:
+        self.task.config = cfg
+
+    @property
+    def time(self) -> float:
+        return self.task.time
+
+    @time.setter
+    def time(self, value: float) -> None:
+        self.task.time = value
+
+    @property
+    def controller_cfg(self) -> ControllerConfig:
+        return self._controller_cfg
+
+    @controller_cfg.setter
+    def controller_cfg(self, cfg: ControllerConfig) -> None:
+        self._controller_cfg = cfg
+        self.action_normalizer = self._init_action_normalizer()
+
+    # ---- the plan step (controller.py:210-299) -----------------------------------------------------------------
+    def _can_fuse(self) -> bool:
+        return self.fused and self.task.cost_params(self.system_metadata) is not None and self.optimizer.name in ("mppi", "cem", "ps") \
+            and type(self.optimizer).update_nominal_knots is get_registered_optimizers()[self.optimizer.name][0].update_nominal_knots
+
+    def update_action(self) -> None:
+        assert self.current_state.shape == (self.model.nq + self.model.nv,), "Current state must be of shape (nq + nv,)"
+        assert self.optimizer_cfg.num_rollouts > 0, "Need at least one rollout!"
+        if self.optimizer_cfg.num_nodes < 4 and self.spline_order == "cubic":
+            warnings.warn("Cubic splines require at least 4 nodes. Setting num_nodes=4.", stacklevel=2)
+            self.optimizer_cfg.num_nodes = 4
+
+        # time-shift the previous plan onto the new knot times
+        new_times = self.time + self.spline_timesteps
+        nominal_knots = self.spline(new_times)
+        nominal_knots_normalized = self.action_normalizer.normalize(nominal_knots)
+
+        if self.rollout_backend.num_threads != self.optimizer_cfg.num_rollouts:
+            self.rollout_backend.update(self.optimizer_cfg.num_rollouts)
+
+        normalizer_cls = normalizer_registry.get(self.action_normalizer_type)
+        if normalizer_cls is None:
+            warnings.warn(f"Invalid action normalizer type '{self.action_normalizer_type}'. Falling back to 'none'.", stacklevel=2)
+            normalizer_cls = IdentityNormalizer
+        if not isinstance(self.action_normalizer, normalizer_cls):
+            self.action_normalizer = self._init_action_normalizer()
+
+        self.optimizer.pre_optimization(self.times, new_times)
+
+        query = self.time + self.rollout_times
+        basis = spline_basis(new_times, query, self.spline_order)  # (H, K): controls = basis @ knots
+        lo = self.action_normalizer.normalize(self.task.actuator_ctrlrange[:, 0])
+        hi = self.action_normalizer.normalize(self.task.actuator_ctrlrange[:, 1])
+        self._rollout_cache_valid = False
+        i = 0
+        while i < self.max_opt_iters and not self.optimizer.stop_cond():
+            cand_norm = np.clip(self.optimizer.sample_control_knots(nominal_knots_normalized), lo, hi)
+            self.candidate_knots = self.action_normalizer.denormalize(cand_norm)
+            self.task.pre_rollout(self.current_state)
+            if self._can_fuse() and isinstance(self.action_normalizer, IdentityNormalizer):
+                res = self.engine.plan_step(self.current_state, self.candidate_knots, basis, self.task.cost_params(self.system_metadata),
+                                            self.optimizer.name, self.optimizer.fused_params(), want_rewards=True,
+                                            n_elite=min(self.max_num_traces, self.optimizer_cfg.num_rollouts))
+                self.rewards = res["rewards"]
+                self._elite = res["elite"]
+                nominal_knots_normalized = self.optimizer.accept_fused(res)
+                self._basis = basis
+                self._rollout_cache_valid = False
+            else:
+                self.rollout_controls = np.einsum("hk,nkj->nhj", basis, self.candidate_knots)
+                sim_controls = self.task.task_to_sim_ctrl(self.rollout_controls)
+                self.states, self.sensors, _ = self.rollout_backend.rollout(self.current_state, sim_controls, self._last_policy_output)
+                self.task.post_rollout(self.states, self.sensors, self.rollout_controls, self.system_metadata)
+                self.rewards = self.task.reward(self.states, self.sensors, self.rollout_controls, self.system_metadata)
+                nominal_knots_normalized = self.optimizer.update_nominal_knots(cand_norm, self.rewards)
+                self._elite = None
+                self._rollout_cache_valid = True
+            self.action_normalizer.update(self.candidate_knots)
+            i += 1
+
+        self.nominal_knots = self.action_normalizer.denormalize(nominal_knots_normalized)
+        self.times = new_times
+        self.update_spline(self.times, self.nominal_knots)
+        self.update_traces()
+
+    def action(self, time: float) -> np.ndarray:
+        return self.spline(time)
+
+    def update_spline(self, times: np.ndarray, controls: np.ndarray) -> None:
+        self.spline = make_spline(times, controls, self.spline_order)
+
+    def reset(self) -> None:
+        """controller.py:309-321."""
+        self.task.reset()
+        if self.optimizer_cfg.num_nodes < 4 and self.spline_order == "cubic":
+            warnings.warn("Cubic splines require at least 4 nodes. Setting num_nodes=4.", stacklevel=2)
+            self.optimizer_cfg.num_nodes = 4
+        self.nominal_knots = np.tile(self.task.optimizer_warm_start(), (self.optimizer_cfg.num_nodes, 1))
+        self.candidate_knots = np.tile(self.nominal_knots, (self.optimizer_cfg.num_rollouts, 1, 1))
+        self.times = self.task.data.time + self.spline_timesteps
+        self.update_spline(self.times, self.nominal_knots)
+
+    def update_traces(self) -> None:
+        """Elite rollouts' trace sensors as line segments (controller.py:323-363).
+
+        In fused mode the sensors of the <= max_num_traces elite rollouts are recomputed by a tiny contract-A rollout
+        of just those candidates instead of materialising (N, H, nsensordata) for everybody."""
+        self.sensor_rollout_size = self.num_timesteps - 1
+        self.all_traces_rollout_size = self.sensor_rollout_size * self.num_trace_sensors
+        self.num_trace_elites = min(self.max_num_traces, self.optimizer_cfg.num_rollouts)
+        ne, nts, size = self.num_trace_elites, self.num_trace_sensors, self.sensor_rollout_size
+        if getattr(self, "_rollout_cache_valid", False) or getattr(self, "_elite", None) is None:
+            elite = np.argsort(self.rewards)[-ne:][::-1]
+            elite_sensors = self.sensors[elite]
+        else:
+            elite = np.asarray(self._elite[:ne])
+            ctrl = np.einsum("hk,nkj->nhj", self._basis, self.candidate_knots[elite])
+            N = self.engine.num_rollouts
+            self.engine.update(len(elite))
+            _, elite_sensors = self.engine.rollout(self.current_state, self.task.task_to_sim_ctrl(ctrl), want_sensors=True)
+            self.engine.update(N)
+        self.elite_indices = elite
+        inds = [int(self.model.sensor_adr[s]) + p for s in self.trace_sensors for p in range(3)]
+        rep = np.repeat(elite_sensors, 2, axis=1)[:, 1:-1, :][:, :, inds]
+        out = np.zeros((nts * ne, size, 2, 3))
+        for s in range(nts):
+            out[s::nts] = np.reshape(rep[:, :, 3 * s:3 * s + 3], (ne, size, 2, 3))
+        self.traces = np.reshape(out, (ne * nts * size, 2, 3))
+
+    def update_states(self, state_msg) -> None:  # noqa: ANN001
+        """state_msg: any object with qpos, qvel, time, sim_metadata (judo/app/structs.py:30-41)."""
+        self.current_state = np.concatenate([state_msg.qpos, state_msg.qvel])
+        self.time = state_msg.time
+        self.system_metadata = state_msg.sim_metadata
+
+    def _init_action_normalizer(self) -> Normalizer:
+        kwargs = {}
+        if self.action_normalizer_type == "min_max":
+            kwargs = dict(min=self.task.actuator_ctrlrange[:, 0], max=self.task.actuator_ctrlrange[:, 1])
+        elif self.action_normalizer_type == "running":
+            kwargs = dict(init_std=1.0)
+        return make_normalizer(self.action_normalizer_type, self.model.nu, **kwargs)
+
+
+def make_controller(init_task: str, init_optimizer: str, rollout_backend: Literal["b200"] = "b200", device: int = 0) -> Controller:
+    """judo/controller/controller.py:404-442."""
+    task_entry = get_registered_tasks().get(init_task)
+    optimizer_entry = get_registered_optimizers().get(init_optimizer)
+    assert task_entry is not None, f"Task {init_task} not found in task registry."
+    assert optimizer_entry is not None, f"Optimizer {init_optimizer} not found in optimizer registry."
+    task = task_entry[0]()
+    optimizer_cls, optimizer_config_cls = optimizer_entry
+    optimizer_cfg = optimizer_config_cls()
+    optimizer_cfg.set_override(init_task)
+    optimizer = optimizer_cls(optimizer_cfg, task.nu)
+    controller_cfg = ControllerConfig()
+    controller_cfg.set_override(init_task)
+    return Controller(controller_config=controller_cfg, task=task, optimizer=optimizer, rollout_backend=rollout_backend, device=device)

@@ -1,0 +1,468 @@
+// b200mpc.cu — C-ABI implementation (include/b200mpc.h): handle, device buffers, pinned staging, kernel dispatch.
+// Built with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC  (judo_b200/build.py)
+#include "../../include/b200mpc.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#ifdef B200MPC_WITH_LEAP
+#include "leap.cuh"
+#endif
+
+using namespace b2;
+
+static thread_local std::string g_create_error;
+
+struct b200mpc_handle {
+  int task = -1, device = 0, N = 0;
+  b200mpc_dims dims{};
+  std::string err;
+  long long launches = 0;
+  cudaStream_t stream = nullptr;
+  CartpoleConsts cartpole{};
+  CylinderPushConsts cyl{};
+#ifdef B200MPC_WITH_LEAP
+  LeapModel* leap = nullptr;  // device-resident constant table
+#endif
+  // device buffers (grown on demand)
+  void* d_in = nullptr; size_t d_in_bytes = 0;      // packed inputs [x0 | basis | params | knots/controls]
+  void* d_out = nullptr; size_t d_out_bytes = 0;    // packed small outputs [nominal | sigma | elite | reward_N]
+  void* d_big = nullptr; size_t d_big_bytes = 0;    // states / sensors / cost matrix
+  void* d_part = nullptr; size_t d_part_bytes = 0;  // reduction partials
+  void* d_work = nullptr; size_t d_work_bytes = 0;  // per-rollout scratch (leap)
+  void* h_in = nullptr; size_t h_in_bytes = 0;      // pinned staging
+  void* h_out = nullptr; size_t h_out_bytes = 0;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+      return 1;                                                                                    \
+    }                                                                                              \
+  } while (0)
+
+static int fail(b200mpc_handle* h, const std::string& msg) { h->err = msg; return 1; }
+
+static int grow(b200mpc_handle* h, void** p, size_t* cur, size_t need, bool pinned) {
+  if (need <= *cur) return 0;
+  size_t cap = std::max(need, *cur * 2);
+  if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cur = 0; }
+  cudaError_t e = pinned ? cudaMallocHost(p, cap) : cudaMalloc(p, cap);
+  if (e != cudaSuccess) { h->err = std::string("allocation failed: ") + cudaGetErrorString(e); return 1; }
+  *cur = cap;
+  return 0;
+}
+
+static size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+extern "C" const char* b200mpc_last_error(const b200mpc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int b200mpc_create(b200mpc_handle** out, int task_id, const double* consts, size_t n_consts, int device, int num_rollouts) {
+  if (!out) { g_create_error = "out is NULL"; return 1; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e); return 1; }
+  if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return 1; }
+  if (num_rollouts <= 0) { g_create_error = "num_rollouts must be positive"; return 1; }
+  b200mpc_handle* h = new b200mpc_handle();
+  h->task = task_id; h->device = device; h->N = num_rollouts;
+  auto bad = [&](const std::string& m) { g_create_error = m; delete h; return 1; };
+  if (cudaSetDevice(device) != cudaSuccess) return bad("cudaSetDevice failed");
+  if (task_id == B200MPC_TASK_CARTPOLE) {
+    if (n_consts != sizeof(CartpoleConsts) / sizeof(double)) return bad("cartpole: wrong number of task constants");
+    memcpy(&h->cartpole, consts, sizeof(CartpoleConsts));
+    h->dims = {CartpoleTask::NQ, CartpoleTask::NV, CartpoleTask::NU, CartpoleTask::NS, CartpoleTask::NCOST};
+  } else if (task_id == B200MPC_TASK_CYLINDER_PUSH) {
+    if (n_consts != sizeof(CylinderPushConsts) / sizeof(double)) return bad("cylinder_push: wrong number of task constants");
+    memcpy(&h->cyl, consts, sizeof(CylinderPushConsts));
+    h->dims = {CylinderPushTask::NQ, CylinderPushTask::NV, CylinderPushTask::NU, CylinderPushTask::NS, CylinderPushTask::NCOST};
+  } else if (task_id == B200MPC_TASK_LEAP_CUBE) {
+#ifdef B200MPC_WITH_LEAP
+    std::string msg;
+    if (leap_create(&h->leap, consts, n_consts, &msg)) return bad("leap_cube: " + msg);
+    h->dims = {LEAP_NQ, LEAP_NV, LEAP_NU, LEAP_NS, LEAP_NCOST};
+#else
+    return bad("leap_cube kernel not built into this library");
+#endif
+  } else return bad("unknown task id");
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bad("cudaStreamCreate failed");
+  *out = h;
+  return 0;
+}
+
+extern "C" void b200mpc_destroy(b200mpc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work);
+  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
+#ifdef B200MPC_WITH_LEAP
+  if (h->leap) leap_destroy(h->leap);
+#endif
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int b200mpc_get_dims(const b200mpc_handle* h, b200mpc_dims* out) { if (!h || !out) return 1; *out = h->dims; return 0; }
+extern "C" int b200mpc_update(b200mpc_handle* h, int n) { if (!h) return 1; if (n <= 0) return fail(h, "num_rollouts must be positive"); h->N = n; return 0; }
+extern "C" int b200mpc_num_rollouts(const b200mpc_handle* h) { return h ? h->N : -1; }
+extern "C" long long b200mpc_launch_count(const b200mpc_handle* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------ launch helpers
+static int pick_threads(int N) {
+  // latency-bound serial recurrences: spread warps over the 148 SMs first, then fill each SM
+  if (N <= 148 * 32) return 32;
+  if (N <= 148 * 64 * 4) return 64;
+  return 128;
+}
+
+template <class Task>
+static int launch_rollout(b200mpc_handle* h, const typename Task::Consts& c, const double* d_x0, int batched, const double* d_ctrl,
+                          int N, int H, double* d_states, double* d_sensors, cudaStream_t st) {
+  int thr = pick_threads(N), grid = (N + thr - 1) / thr;
+  rollout_kernel<Task, false, 1><<<grid, thr, 0, st>>>(c, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <class Task, int MAXK>
+static int launch_costs_k(b200mpc_handle* h, const typename Task::Consts& c, const double* d_x0, const double* d_knots, int N, int K,
+                          const double* d_basis, int H, const double* d_params, float* d_cost, double* d_reward, cudaStream_t st) {
+  int thr = pick_threads(N), grid = (N + thr - 1) / thr;
+  size_t smem = rollout_cost_smem<Task>(thr, H, K, d_cost != nullptr);
+  auto kern = rollout_kernel<Task, true, MAXK>;
+  if (smem > 48 * 1024) {
+    if (smem > 227 * 1024) return fail(h, "horizon/knots too large for the shared-memory tile");
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  kern<<<grid, thr, smem, st>>>(c, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+template <class Task>
+static int launch_costs(b200mpc_handle* h, const typename Task::Consts& c, const double* d_x0, const double* d_knots, int N, int K,
+                        const double* d_basis, int H, const double* d_params, float* d_cost, double* d_reward, cudaStream_t st) {
+  if (K <= 4) return launch_costs_k<Task, 4>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, st);
+  if (K <= 8) return launch_costs_k<Task, 8>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, st);
+  if (K <= 12) return launch_costs_k<Task, 12>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, st);
+  return fail(h, "num_nodes > 12 not supported (reference slider range is 3..12, optimizers/base.py:13)");
+}
+
+extern "C" int b200mpc_rollout_dev(b200mpc_handle* h, const double* d_x0, int batched, const double* d_ctrl, int N, int H,
+                                   double* d_states, double* d_sensors, void* stream) {
+  if (!h) return 1;
+  if (N <= 0 || H <= 0) return fail(h, "N and H must be positive");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (h->task) {
+    case B200MPC_TASK_CARTPOLE: return launch_rollout<CartpoleTask>(h, h->cartpole, d_x0, batched, d_ctrl, N, H, d_states, d_sensors, st);
+    case B200MPC_TASK_CYLINDER_PUSH: return launch_rollout<CylinderPushTask>(h, h->cyl, d_x0, batched, d_ctrl, N, H, d_states, d_sensors, st);
+#ifdef B200MPC_WITH_LEAP
+    case B200MPC_TASK_LEAP_CUBE: {
+      if (leap_launch(h->leap, /*cost_mode=*/0, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, st, &h->err)) return 1;
+      h->launches++;
+      return 0;
+    }
+#endif
+  }
+  return fail(h, "task not supported");
+}
+
+extern "C" int b200mpc_plan_costs_dev(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis,
+                                      int H, const double* d_params, float* d_cost, double* d_reward, void* stream) {
+  if (!h) return 1;
+  if (N <= 0 || H <= 0 || K <= 0) return fail(h, "N, H and K must be positive");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (h->task) {
+    case B200MPC_TASK_CARTPOLE: return launch_costs<CartpoleTask>(h, h->cartpole, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, st);
+    case B200MPC_TASK_CYLINDER_PUSH: return launch_costs<CylinderPushTask>(h, h->cyl, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, st);
+#ifdef B200MPC_WITH_LEAP
+    case B200MPC_TASK_LEAP_CUBE: {
+      if (leap_launch(h->leap, /*cost_mode=*/1, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, st, &h->err)) return 1;
+      h->launches++;
+      return 0;
+    }
+#endif
+  }
+  return fail(h, "task not supported");
+}
+
+// ------------------------------------------------------------------ reductions (device-pointer API)
+static int n_partials_for(int N) { return std::max(1, std::min(64, (N + 511) / 512)); }
+
+extern "C" int b200mpc_mppi_partial_dev(b200mpc_handle* h, const double* d_knots, const double* d_rewards, int N, int KNU,
+                                        double temperature, double* d_partial, void* stream) {
+  if (!h) return 1;
+  if (KNU > 256 * 8) return fail(h, "K*nu too large");
+  CK(cudaSetDevice(h->device));
+  // a single partial over all N rollouts of this call (grid=1) is what the multi-GPU path gathers
+  int chunk = N;
+  size_t smem = ((size_t)chunk + 256) * sizeof(double);
+  if (smem > 200 * 1024) return fail(h, "mppi_partial_dev: N too large for one partial; split the call");
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(mppi_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mppi_partial_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(d_knots, d_rewards, N, KNU, temperature, d_partial);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int mppi_blocks(b200mpc_handle* h, const double* d_knots, const double* d_rewards, int N, int KNU, double temperature,
+                       double* d_partial, int nb, cudaStream_t st) {
+  int chunk = (N + nb - 1) / nb;
+  size_t smem = ((size_t)chunk + 256) * sizeof(double);
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(mppi_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mppi_partial_kernel<<<nb, 256, smem, st>>>(d_knots, d_rewards, N, KNU, temperature, d_partial);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200mpc_mppi_combine_dev(b200mpc_handle* h, const double* d_partials, int np, int KNU, double temperature,
+                                        double* d_nominal, void* stream) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->device));
+  mppi_combine_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(d_partials, np, KNU, temperature, d_nominal);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200mpc_topk_partial_dev(b200mpc_handle* h, const double* d_knots, const double* d_rewards, int N, int KNU, int k,
+                                        int index_offset, int prefer_high, double* d_partial, void* stream) {
+  if (!h) return 1;
+  if (k <= 0 || k > 64) return fail(h, "num_elites must be in 1..64");
+  CK(cudaSetDevice(h->device));
+  topk_partial_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_knots, d_rewards, N, KNU, k, index_offset, prefer_high, d_partial);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200mpc_topk_combine_dev(b200mpc_handle* h, const double* d_partials, int np, int KNU, int k, int prefer_high,
+                                        double sigma_min, double sigma_max, double* d_nominal, double* d_sigma, double* d_elite,
+                                        void* stream) {
+  if (!h) return 1;
+  if (k <= 0 || k > 64) return fail(h, "num_elites must be in 1..64");
+  if ((long long)np * k >= (1 << 20)) return fail(h, "too many candidates");
+  CK(cudaSetDevice(h->device));
+  topk_combine_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_partials, np, KNU, k, prefer_high, sigma_min, sigma_max, d_nominal, d_sigma, d_elite);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// multi-block partials + combine on the handle's own scratch
+static int run_update(b200mpc_handle* h, int optimizer, const double* opt_params, const double* d_knots, const double* d_rewards, int N,
+                      int KNU, double* d_nominal, double* d_sigma, double* d_elite, int n_elite, cudaStream_t st) {
+  int nb = n_partials_for(N);
+  if (optimizer == B200MPC_OPT_MPPI) {
+    if (grow(h, &h->d_part, &h->d_part_bytes, (size_t)nb * (2 + KNU) * 8, false)) return 1;
+    if (mppi_blocks(h, d_knots, d_rewards, N, KNU, opt_params[0], (double*)h->d_part, nb, st)) return 1;
+    if (b200mpc_mppi_combine_dev(h, (double*)h->d_part, nb, KNU, opt_params[0], d_nominal, st)) return 1;
+    return 0;
+  }
+  int k = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
+  int prefer_high = optimizer == B200MPC_OPT_CEM ? 1 : 0;
+  if (k <= 0 || k > 64) return fail(h, "num_elites must be in 1..64");
+  if (grow(h, &h->d_part, &h->d_part_bytes, (size_t)nb * k * (2 + KNU) * 8, false)) return 1;
+  topk_partial_kernel<<<nb, 256, 0, st>>>(d_knots, d_rewards, N, KNU, k, 0, prefer_high, (double*)h->d_part);
+  h->launches++;
+  CK(cudaGetLastError());
+  double smin = optimizer == B200MPC_OPT_CEM ? opt_params[1] : 0, smax = optimizer == B200MPC_OPT_CEM ? opt_params[2] : 0;
+  return b200mpc_topk_combine_dev(h, (double*)h->d_part, nb, KNU, k, prefer_high, smin, smax, d_nominal,
+                                  optimizer == B200MPC_OPT_CEM ? d_sigma : nullptr, d_elite, st);
+}
+
+// ------------------------------------------------------------------ host-buffer API
+extern "C" int b200mpc_rollout(b200mpc_handle* h, const double* x0, int batched, const double* controls, int N, int H, double* states,
+                               double* sensors) {
+  if (!h) return 1;
+  if (!x0 || !controls || !states) return fail(h, "NULL argument");
+  if (N != h->N) return fail(h, "controls batch size does not match num_rollouts (call update first)");
+  if (H <= 0) return fail(h, "H must be positive");
+  CK(cudaSetDevice(h->device));
+  const int nx = h->dims.nq + h->dims.nv, nu = h->dims.nu, ns = h->dims.nsensordata;
+  size_t bx = al16((size_t)(batched ? N : 1) * nx * 8), bc = (size_t)N * H * nu * 8;
+  size_t bs = al16((size_t)N * H * nx * 8), be = sensors ? (size_t)N * H * ns * 8 : 0;
+  if (grow(h, &h->d_in, &h->d_in_bytes, bx + bc, false) || grow(h, &h->d_big, &h->d_big_bytes, bs + be, false)) return 1;
+  char* din = (char*)h->d_in; char* dbig = (char*)h->d_big;
+  CK(cudaMemcpyAsync(din, x0, (size_t)(batched ? N : 1) * nx * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(din + bx, controls, bc, cudaMemcpyHostToDevice, h->stream));
+  if (b200mpc_rollout_dev(h, (double*)din, batched, (double*)(din + bx), N, H, (double*)dbig, sensors ? (double*)(dbig + bs) : nullptr, h->stream)) return 1;
+  CK(cudaMemcpyAsync(states, dbig, (size_t)N * H * nx * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (sensors) CK(cudaMemcpyAsync(sensors, dbig + bs, be, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// stage [x0 | basis | params | knots] through pinned memory with ONE host-to-device copy
+static int stage_inputs(b200mpc_handle* h, const double* x0, const double* basis, int H, int K, const double* params, const double* knots,
+                        int N, size_t* ox0, size_t* obasis, size_t* oparams, size_t* oknots) {
+  const int nx = h->dims.nq + h->dims.nv, nu = h->dims.nu, np = h->dims.n_cost_params;
+  size_t o = 0;
+  *ox0 = o; o += al16((size_t)nx * 8);
+  *obasis = o; o += al16((size_t)H * K * 8);
+  *oparams = o; o += al16((size_t)np * 8);
+  *oknots = o; o += (size_t)N * K * nu * 8;
+  if (grow(h, &h->h_in, &h->h_in_bytes, o, true) || grow(h, &h->d_in, &h->d_in_bytes, o, false)) return 1;
+  char* hp = (char*)h->h_in;
+  memcpy(hp + *ox0, x0, (size_t)nx * 8);
+  memcpy(hp + *obasis, basis, (size_t)H * K * 8);
+  memcpy(hp + *oparams, params, (size_t)np * 8);
+  memcpy(hp + *oknots, knots, (size_t)N * K * nu * 8);
+  CK(cudaMemcpyAsync(h->d_in, h->h_in, o, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+extern "C" int b200mpc_plan_costs(b200mpc_handle* h, const double* x0, const double* knots, int N, int K, const double* basis, int H,
+                                  const double* params, float* cost_NH, double* reward_N) {
+  if (!h) return 1;
+  if (!x0 || !knots || !basis || !params || !reward_N) return fail(h, "NULL argument");
+  if (N <= 0 || H <= 0 || K <= 0) return fail(h, "N, H and K must be positive");
+  CK(cudaSetDevice(h->device));
+  size_t ox0, ob, op, ok;
+  if (stage_inputs(h, x0, basis, H, K, params, knots, N, &ox0, &ob, &op, &ok)) return 1;
+  size_t br = al16((size_t)N * 8), bc = cost_NH ? (size_t)N * H * 4 : 0;
+  if (grow(h, &h->d_big, &h->d_big_bytes, br + bc, false)) return 1;
+  char* din = (char*)h->d_in; char* dbig = (char*)h->d_big;
+  if (b200mpc_plan_costs_dev(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op),
+                             cost_NH ? (float*)(dbig + br) : nullptr, (double*)dbig, h->stream)) return 1;
+  CK(cudaMemcpyAsync(reward_N, dbig, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (cost_NH) CK(cudaMemcpyAsync(cost_NH, dbig + br, bc, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int b200mpc_reward(b200mpc_handle* h, const double* states, const double* controls, int N, int H, const double* params,
+                              double* reward_N) {
+  if (!h) return 1;
+  if (!states || !controls || !params || !reward_N) return fail(h, "NULL argument");
+  if (N <= 0 || H <= 0) return fail(h, "N and H must be positive");
+  CK(cudaSetDevice(h->device));
+  const int nx = h->dims.nq + h->dims.nv, nu = h->dims.nu, np = h->dims.n_cost_params;
+  size_t bs = al16((size_t)N * H * nx * 8), bc = al16((size_t)N * H * nu * 8), bp = al16((size_t)np * 8);
+  if (grow(h, &h->d_in, &h->d_in_bytes, bs + bc + bp, false) || grow(h, &h->d_out, &h->d_out_bytes, (size_t)N * 8, false)) return 1;
+  char* din = (char*)h->d_in;
+  CK(cudaMemcpyAsync(din, states, (size_t)N * H * nx * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(din + bs, controls, (size_t)N * H * nu * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(din + bs + bc, params, (size_t)np * 8, cudaMemcpyHostToDevice, h->stream));
+  int thr = 128, grid = (N + thr - 1) / thr;
+  switch (h->task) {
+    case B200MPC_TASK_CARTPOLE:
+      reward_kernel<CartpoleTask><<<grid, thr, 0, h->stream>>>((double*)din, (double*)(din + bs), N, H, (double*)(din + bs + bc), (double*)h->d_out);
+      break;
+    case B200MPC_TASK_CYLINDER_PUSH:
+      reward_kernel<CylinderPushTask><<<grid, thr, 0, h->stream>>>((double*)din, (double*)(din + bs), N, H, (double*)(din + bs + bc), (double*)h->d_out);
+      break;
+#ifdef B200MPC_WITH_LEAP
+    case B200MPC_TASK_LEAP_CUBE:
+      if (leap_reward_launch(h->leap, (double*)din, N, H, (double*)(din + bs + bc), (double*)h->d_out, h->stream, &h->err)) return 1;
+      break;
+#endif
+    default: return fail(h, "task not supported");
+  }
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(reward_N, h->d_out, (size_t)N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int host_update(b200mpc_handle* h, int optimizer, const double* opt_params, const double* knots, const double* rewards, int N, int K,
+                       double* nominal, double* sigma) {
+  if (!h) return 1;
+  if (!knots || !rewards || !nominal) return fail(h, "NULL argument");
+  if (N <= 0 || K <= 0) return fail(h, "N and K must be positive");
+  CK(cudaSetDevice(h->device));
+  const int KNU = K * h->dims.nu;
+  size_t bk = al16((size_t)N * KNU * 8), br = al16((size_t)N * 8), bo = al16((size_t)KNU * 8);
+  if (grow(h, &h->d_in, &h->d_in_bytes, bk + br, false) || grow(h, &h->d_out, &h->d_out_bytes, 2 * bo, false)) return 1;
+  char* din = (char*)h->d_in; char* dout = (char*)h->d_out;
+  CK(cudaMemcpyAsync(din, knots, (size_t)N * KNU * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(din + bk, rewards, (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
+  if (run_update(h, optimizer, opt_params, (double*)din, (double*)(din + bk), N, KNU, (double*)dout, (double*)(dout + bo), nullptr, 0, h->stream)) return 1;
+  CK(cudaMemcpyAsync(nominal, dout, (size_t)KNU * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (sigma) CK(cudaMemcpyAsync(sigma, dout + bo, (size_t)KNU * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int b200mpc_update_mppi(b200mpc_handle* h, const double* knots, const double* rewards, int N, int K, double temperature, double* nominal) {
+  if (h && !(temperature > 0)) return fail(h, "temperature must be positive");
+  double p[1] = {temperature};
+  return host_update(h, B200MPC_OPT_MPPI, p, knots, rewards, N, K, nominal, nullptr);
+}
+extern "C" int b200mpc_update_cem(b200mpc_handle* h, const double* knots, const double* rewards, int N, int K, int num_elites, double sigma_min,
+                                  double sigma_max, double* nominal, double* sigma) {
+  double p[3] = {(double)num_elites, sigma_min, sigma_max};
+  return host_update(h, B200MPC_OPT_CEM, p, knots, rewards, N, K, nominal, sigma);
+}
+extern "C" int b200mpc_update_ps(b200mpc_handle* h, const double* knots, const double* rewards, int N, int K, double* nominal) {
+  return host_update(h, B200MPC_OPT_PS, nullptr, knots, rewards, N, K, nominal, nullptr);
+}
+
+extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const double* knots, int N, int K, const double* basis, int H,
+                                 const double* params, int optimizer, const double* opt_params, double* nominal, double* sigma,
+                                 double* reward_N, int* elite_idx, int n_elite) {
+  if (!h) return 1;
+  if (!x0 || !knots || !basis || !params || !nominal) return fail(h, "NULL argument");
+  if (N <= 0 || H <= 0 || K <= 0) return fail(h, "N, H and K must be positive");
+  if (optimizer == B200MPC_OPT_MPPI && !(opt_params && opt_params[0] > 0)) return fail(h, "temperature must be positive");
+  if (optimizer == B200MPC_OPT_CEM && !opt_params) return fail(h, "CEM needs {num_elites, sigma_min, sigma_max}");
+  if (n_elite < 0 || n_elite > 64) return fail(h, "n_elite must be in 0..64");
+  CK(cudaSetDevice(h->device));
+  const int KNU = K * h->dims.nu;
+  size_t ox0, ob, op, ok;
+  if (stage_inputs(h, x0, basis, H, K, params, knots, N, &ox0, &ob, &op, &ok)) return 1;
+  // packed outputs: [nominal KNU | sigma KNU | elite n_elite | reward N]
+  size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_rw = o_el + al16((size_t)std::max(n_elite, 1) * 8);
+  size_t out_bytes = o_rw + (size_t)N * 8;
+  if (grow(h, &h->d_out, &h->d_out_bytes, out_bytes, false) || grow(h, &h->h_out, &h->h_out_bytes, out_bytes, true)) return 1;
+  char* din = (char*)h->d_in; char* dout = (char*)h->d_out;
+  double* d_reward = (double*)(dout + o_rw);
+  if (b200mpc_plan_costs_dev(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), nullptr,
+                             d_reward, h->stream)) return 1;
+  bool elite_from_update = optimizer != B200MPC_OPT_MPPI;
+  int k_upd = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
+  if (run_update(h, optimizer, opt_params, (double*)(din + ok), d_reward, N, KNU, (double*)(dout + o_nom), (double*)(dout + o_sig),
+                 (elite_from_update && n_elite > 0 && n_elite <= k_upd) ? (double*)(dout + o_el) : nullptr, n_elite, h->stream)) return 1;
+  bool need_elite_pass = n_elite > 0 && !(elite_from_update && n_elite <= k_upd);
+  if (need_elite_pass) {
+    // best-first indices for the trace gather (controller.py:341: argsort(rewards)[-E:][::-1] -> ties: higher index first)
+    int nb = n_partials_for(N);
+    size_t scratch = (size_t)nb * n_elite * (2 + KNU) * 8 + al16((size_t)KNU * 8);
+    size_t base = al16((size_t)nb * std::max(k_upd, 1) * (2 + KNU) * 8);
+    if (base + scratch > h->d_part_bytes) {
+      // keep the update's partials intact: allocate a larger buffer only when nothing is in flight that needs the old one
+      CK(cudaStreamSynchronize(h->stream));
+      if (grow(h, &h->d_part, &h->d_part_bytes, base + scratch, false)) return 1;
+    }
+    double* part = (double*)((char*)h->d_part + base);
+    double* dummy_nom = part + (size_t)nb * n_elite * (2 + KNU);
+    topk_partial_kernel<<<nb, 256, 0, h->stream>>>((double*)(din + ok), d_reward, N, KNU, n_elite, 0, 1, part);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (b200mpc_topk_combine_dev(h, part, nb, KNU, n_elite, 1, 0, 0, dummy_nom, nullptr, (double*)(dout + o_el), h->stream)) return 1;
+  }
+  size_t copy_bytes = reward_N ? out_bytes : o_rw;
+  CK(cudaMemcpyAsync(h->h_out, h->d_out, copy_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const char* ho = (const char*)h->h_out;
+  memcpy(nominal, ho + o_nom, (size_t)KNU * 8);
+  if (sigma && optimizer == B200MPC_OPT_CEM) memcpy(sigma, ho + o_sig, (size_t)KNU * 8);
+  if (elite_idx) for (int i = 0; i < n_elite; i++) elite_idx[i] = (int)((const double*)(ho + o_el))[i];
+  if (reward_N) memcpy(reward_N, ho + o_rw, (size_t)N * 8);
+  return 0;
+}

@@ -1,0 +1,254 @@
+// common.cuh — device helpers shared by the task kernels (sm_100a).
+//
+// The constraint model follows MuJoCo 3.5.0's soft-constraint pipeline (the reference's physics lives in that
+// third-party wheel: judo/utils/mj_rollout_backend.py:36,84).  The per-thread Newton solver below is the
+// thread-per-rollout form used by the two small tasks (cartpole, cylinder_push: <=4 dofs, <=4 rows).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B2_MINVAL 1e-15
+#define B2_MINIMP 0.0001
+#define B2_MAXIMP 0.9999
+#define B2_MINMU 1e-5
+
+namespace b2 {
+
+// ------------------------------------------------------------------ 1-D TMA bulk copy (global -> shared) + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+// bytes must be a multiple of 16; src and dst 16-byte aligned. SASS: UBLKCP.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ------------------------------------------------------------------ soft-constraint parameters
+// getimpedance: sigmoid d(r) from solimp = (d0, dwidth, width, midpoint, power)
+__device__ inline double impedance(const double* solimp, double pos, double margin) {
+  double d0 = fmin(fmax(solimp[0], B2_MINIMP), B2_MAXIMP), dw = fmin(fmax(solimp[1], B2_MINIMP), B2_MAXIMP);
+  double width = solimp[2], mid = fmin(fmax(solimp[3], B2_MINIMP), B2_MAXIMP), power = fmax(solimp[4], 1.0);
+  if (d0 == dw || width <= B2_MINVAL) return 0.5 * (d0 + dw);
+  double x = fabs((pos - margin) / width);
+  if (x >= 1) return dw;
+  if (x <= 0) return d0;
+  double y;
+  if (power == 1) y = x;
+  else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
+  else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
+  return d0 + y * (dw - d0);
+}
+// mj_makeImpedance for one non-friction row: returns R and aref (before the per-contact cone adjustment)
+__device__ inline void row_reference(const double* solref, const double* solimp, double timestep, double pos, double margin,
+                                     double vel, double diagApprox, double* R, double* aref) {
+  double ref0 = solref[0], ref1 = solref[1];
+  double dmax = fmin(fmax(solimp[1], B2_MINIMP), B2_MAXIMP);
+  double imp = impedance(solimp, pos, margin);
+  double K, B;
+  if (ref0 > 0) {
+    if (ref0 < 2 * timestep) ref0 = 2 * timestep;  // refsafe
+    K = 1 / fmax(B2_MINVAL, dmax * dmax * ref0 * ref0 * ref1 * ref1);
+    B = 2 / fmax(B2_MINVAL, dmax * ref0);
+  } else {
+    K = -ref0 / fmax(B2_MINVAL, dmax * dmax);
+    B = -ref1 / fmax(B2_MINVAL, dmax);
+  }
+  *R = fmax(B2_MINVAL, (1 - imp) * diagApprox / imp);
+  *aref = -B * vel - K * imp * (pos - margin);
+}
+
+// ------------------------------------------------------------------ small dense linear algebra (registers)
+template <int N>
+__device__ inline void chol(double (&L)[N][N], const double (&A)[N][N]) {
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      double s = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+      if (i == j) { if (s < B2_MINVAL) s = B2_MINVAL; L[i][i] = sqrt(s); }
+      else L[i][j] = s / L[j][j];
+    }
+}
+template <int N>
+__device__ inline void chol_solve(const double (&L)[N][N], double (&x)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; i++) { double s = x[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s -= L[i][k] * x[k];
+    x[i] = s / L[i][i]; }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) { double s = x[i];
+#pragma unroll
+    for (int k = i + 1; k < N; k++) s -= L[k][i] * x[k];
+    x[i] = s / L[i][i]; }
+}
+
+struct SolverOpt { double meaninertia, tolerance, ls_tolerance; int iterations, ls_iterations; };
+
+// ------------------------------------------------------------------ per-thread primal Newton (inequality rows only)
+// Rows are limit / pyramidal-contact rows: s(x) = 0.5 D x^2 for x < 0, 0 otherwise (x = J qacc - aref).
+template <int NV, int NE>
+struct RowSolver {
+  double Ma[NV], jar[NE], grad[NV], search[NV], Mv[NV], jv[NE], H[NV][NV], force[NE];
+  double cost;
+
+  __device__ inline void mulM(const double (&M)[NV][NV], const double (&x)[NV], double (&y)[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) { double s = 0;
+#pragma unroll
+      for (int j = 0; j < NV; j++) s += M[i][j] * x[j];
+      y[i] = s; }
+  }
+  __device__ inline void set_point(const double (&M)[NV][NV], const double (&J)[NE][NV], const double (&aref)[NE], int nefc,
+                                   const double (&qacc)[NV]) {
+    mulM(M, qacc, Ma);
+#pragma unroll
+    for (int r = 0; r < NE; r++) { double v = 0;
+#pragma unroll
+      for (int i = 0; i < NV; i++) v += J[r][i] * qacc[i];
+      jar[r] = r < nefc ? v - aref[r] : 0.0; }
+  }
+  __device__ inline void update(const double (&M)[NV][NV], const double (&J)[NE][NV], const double (&D)[NE], int nefc,
+                                const double (&qfrc_smooth)[NV], const double (&qacc_smooth)[NV], const double (&qacc)[NV],
+                                double (&qfrc_c)[NV], bool want_h) {
+    double c = 0;
+    if (want_h) {
+#pragma unroll
+      for (int i = 0; i < NV; i++)
+#pragma unroll
+        for (int j = 0; j < NV; j++) H[i][j] = M[i][j];
+    }
+#pragma unroll
+    for (int r = 0; r < NE; r++) {
+      bool active = r < nefc && jar[r] < 0;
+      force[r] = active ? -D[r] * jar[r] : 0.0;
+      if (active) {
+        c += 0.5 * D[r] * jar[r] * jar[r];
+        if (want_h) {
+#pragma unroll
+          for (int i = 0; i < NV; i++) { double a = D[r] * J[r][i];
+#pragma unroll
+            for (int j = 0; j < NV; j++) H[i][j] += a * J[r][j]; }
+        }
+      }
+    }
+    double g = 0;
+#pragma unroll
+    for (int i = 0; i < NV; i++) g += (Ma[i] - qfrc_smooth[i]) * (qacc[i] - qacc_smooth[i]);
+    cost = 0.5 * g + c;
+#pragma unroll
+    for (int i = 0; i < NV; i++) { double f = 0;
+#pragma unroll
+      for (int r = 0; r < NE; r++) f += J[r][i] * force[r];
+      qfrc_c[i] = f;
+      grad[i] = Ma[i] - qfrc_smooth[i] - f; }
+  }
+  __device__ inline void ls_eval(const double (&D)[NE], int nefc, double alpha, double g1, double g2, double* d1, double* d2) {
+    double p1 = g1 + alpha * g2, p2 = g2;
+#pragma unroll
+    for (int r = 0; r < NE; r++) {
+      double x = jar[r] + alpha * jv[r];
+      if (r < nefc && x < 0) { p1 -= (-D[r] * x) * jv[r]; p2 += D[r] * jv[r] * jv[r]; }
+    }
+    *d1 = p1; *d2 = p2;
+  }
+  __device__ inline double line_search(const double (&D)[NE], int nefc, const double (&qfrc_smooth)[NV], const SolverOpt& o) {
+    double g1 = 0, g2 = 0, snorm = 0;
+#pragma unroll
+    for (int i = 0; i < NV; i++) { g1 += search[i] * (Ma[i] - qfrc_smooth[i]); g2 += search[i] * Mv[i]; snorm += search[i] * search[i]; }
+    snorm = sqrt(snorm);
+    if (snorm < B2_MINVAL) return 0;
+    double gtol = o.tolerance * o.ls_tolerance * snorm * o.meaninertia * (NV > 1 ? NV : 1);
+    double d1, d2, lo = 0, hi = -1, dlo, dhi = 0, alpha;
+    ls_eval(D, nefc, 0, g1, g2, &d1, &d2);
+    if (d1 >= 0 || d2 <= 0) return 0;
+    dlo = d1;
+    alpha = -d1 / d2;
+    for (int it = 0; it < o.ls_iterations; it++) {
+      ls_eval(D, nefc, alpha, g1, g2, &d1, &d2);
+      if (fabs(d1) < gtol) return alpha;
+      if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
+      double next = d2 > 0 ? alpha - d1 / d2 : -1;
+      if (hi < 0) { if (!(next > lo)) next = 2 * alpha + B2_MINVAL; }
+      else if (!(next > lo && next < hi)) {
+        next = lo + (hi - lo) * (-dlo) / (dhi - dlo);
+        if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);
+      }
+      if (next == alpha) return alpha;
+      alpha = next;
+    }
+    return alpha;
+  }
+
+  // mj_fwdConstraint: warm-start choice + Newton iterations.  qacc (out), qfrc_c (out).
+  __device__ inline void solve(const double (&M)[NV][NV], const double (&qfrc_smooth)[NV], const double (&qacc_smooth)[NV],
+                               const double (&J)[NE][NV], const double (&D)[NE], const double (&aref)[NE], int nefc,
+                               const double (&warm)[NV], const SolverOpt& o, double (&qacc)[NV], double (&qfrc_c)[NV]) {
+    if (nefc == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) { qacc[i] = qacc_smooth[i]; qfrc_c[i] = 0; }
+      return;
+    }
+    set_point(M, J, aref, nefc, warm);
+    update(M, J, D, nefc, qfrc_smooth, qacc_smooth, warm, qfrc_c, false);
+    double cw = cost;
+    set_point(M, J, aref, nefc, qacc_smooth);
+    update(M, J, D, nefc, qfrc_smooth, qacc_smooth, qacc_smooth, qfrc_c, false);
+    double cs = cost;
+#pragma unroll
+    for (int i = 0; i < NV; i++) qacc[i] = cw > cs ? qacc_smooth[i] : warm[i];
+    set_point(M, J, aref, nefc, qacc);
+    update(M, J, D, nefc, qfrc_smooth, qacc_smooth, qacc, qfrc_c, true);
+    double scale = 1.0 / (o.meaninertia * (NV > 1 ? NV : 1));
+    for (int it = 0; it < o.iterations; it++) {
+      double gn = 0;
+#pragma unroll
+      for (int i = 0; i < NV; i++) gn += grad[i] * grad[i];
+      if (scale * sqrt(gn) < o.tolerance) break;
+      double L[NV][NV];
+      chol<NV>(L, H);
+#pragma unroll
+      for (int i = 0; i < NV; i++) search[i] = -grad[i];
+      chol_solve<NV>(L, search);
+      mulM(M, search, Mv);
+#pragma unroll
+      for (int r = 0; r < NE; r++) { double v = 0;
+#pragma unroll
+        for (int i = 0; i < NV; i++) v += J[r][i] * search[i];
+        jv[r] = r < nefc ? v : 0.0; }
+      double alpha = line_search(D, nefc, qfrc_smooth, o);
+      if (alpha == 0) break;
+      double oldcost = cost;
+#pragma unroll
+      for (int i = 0; i < NV; i++) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+#pragma unroll
+      for (int r = 0; r < NE; r++) jar[r] += alpha * jv[r];
+      update(M, J, D, nefc, qfrc_smooth, qacc_smooth, qacc, qfrc_c, true);
+      if (scale * (oldcost - cost) < o.tolerance) break;
+    }
+  }
+};
+
+}  // namespace b2

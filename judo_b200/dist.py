@@ -1,0 +1,110 @@
+"""Sharded, device-resident plan step: one process per GPU, rollouts split along N.
+
+Every rank rolls out its own slice with the fused kernel, reduces it to ONE partial
+(MPPI: [beta, S, V[K*nu]]; CEM/PS: k x [reward, global index, knots[K*nu]]), the partials are exchanged with a single
+``all_gather`` (NCCL over NVLink; a few hundred bytes per rank — latency-bound) and every rank runs the same tiny
+combine kernel, so all ranks hold the identical nominal knots.  world_size == 1 skips the collective.
+
+torch is plumbing here: it owns the device allocations, the stream and the process group; all compute goes through
+the C ABI's resident (``*_dev``) entry points.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+
+def shard_range(n_total: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous slice [lo, hi) of the global rollout axis owned by ``rank`` (rollout 0, the un-noised nominal,
+    lives on rank 0).  Remainders go to the lowest ranks."""
+    base, rem = divmod(n_total, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def partial_width(optimizer: str, knu: int, k: int = 1) -> int:
+    """Doubles per rank in the exchanged partial."""
+    return 2 + knu if optimizer == "mppi" else k * (2 + knu)
+
+
+def gather_partials(local, world_size: int, group=None):  # noqa: ANN001
+    """all_gather of one fixed-size partial per rank -> (world_size, width) tensor.  Works for NCCL (cuda tensors)
+    and gloo (cpu tensors); used as is by the CPU tests of the N>1 path."""
+    import torch
+    import torch.distributed as dist
+
+    if world_size == 1:
+        return local.reshape(1, -1)
+    out = torch.empty((world_size, local.numel()), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.reshape(-1).contiguous(), group=group)
+    return out
+
+
+class ShardedPlanner:
+    """Resident plan step for one rank.  Inputs are uploaded once (``set_problem`` / ``set_knots``); ``step`` launches
+    rollout+cost -> partial -> [all_gather] -> combine on the current torch stream and returns device tensors."""
+
+    def __init__(self, task: str, n_local: int, device: int = 0, rank: int = 0, world_size: int = 1, group=None) -> None:  # noqa: ANN001
+        import torch
+
+        from judo_b200 import _lib
+        from judo_b200.engine import Engine
+
+        self.torch = torch
+        self.lib = _lib.load()
+        self.engine = Engine(task, n_local, device=device)
+        self.dev = torch.device("cuda", device)
+        self.rank, self.world_size, self.group = rank, world_size, group
+        self.n_local = n_local
+        self.nu = self.engine.nu
+        self.nx = self.engine.nq + self.engine.nv
+
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise RuntimeError(self.lib.b200mpc_last_error(self.engine.handle).decode())
+
+    def set_problem(self, x0: np.ndarray, basis: np.ndarray, cost_params: np.ndarray, want_cost_matrix: bool = True) -> None:
+        t = self.torch
+        self.H, self.K = basis.shape
+        self.knu = self.K * self.nu
+        self.d_x0 = t.as_tensor(np.ascontiguousarray(x0, dtype=np.float64), device=self.dev)
+        self.d_basis = t.as_tensor(np.ascontiguousarray(basis, dtype=np.float64), device=self.dev)
+        self.d_params = t.as_tensor(np.ascontiguousarray(cost_params, dtype=np.float64), device=self.dev)
+        self.d_reward = t.empty(self.n_local, dtype=t.float64, device=self.dev)
+        self.d_cost = t.empty((self.n_local, self.H), dtype=t.float32, device=self.dev) if want_cost_matrix else None
+        self.d_nominal = t.empty(self.knu, dtype=t.float64, device=self.dev)
+        self.d_sigma = t.empty(self.knu, dtype=t.float64, device=self.dev)
+        self.d_elite = t.empty(64, dtype=t.float64, device=self.dev)
+
+    def set_knots(self, knots_local: np.ndarray) -> None:
+        assert knots_local.shape == (self.n_local, self.K, self.nu)
+        self.d_knots = self.torch.as_tensor(np.ascontiguousarray(knots_local, dtype=np.float64), device=self.dev)
+
+    def step(self, optimizer: str, opt_params: np.ndarray, index_offset: int = 0):  # noqa: ANN201
+        """One resident plan step; returns the (K*nu,) nominal device tensor (identical on every rank)."""
+        t = self.torch
+        st = ctypes.c_void_p(t.cuda.current_stream(self.dev).cuda_stream)
+        h = self.engine.handle
+        P = lambda x: ctypes.c_void_p(0 if x is None else x.data_ptr())  # noqa: E731
+        self._check(self.lib.b200mpc_plan_costs_dev(h, P(self.d_x0), P(self.d_knots), self.n_local, self.K, P(self.d_basis), self.H,
+                                                    P(self.d_params), P(self.d_cost), P(self.d_reward), st))
+        if optimizer == "mppi":
+            part = t.empty(2 + self.knu, dtype=t.float64, device=self.dev)
+            self._check(self.lib.b200mpc_mppi_partial_dev(h, P(self.d_knots), P(self.d_reward), self.n_local, self.knu, float(opt_params[0]), P(part), st))
+            allp = gather_partials(part, self.world_size, self.group)
+            self._check(self.lib.b200mpc_mppi_combine_dev(h, P(allp), self.world_size, self.knu, float(opt_params[0]), P(self.d_nominal), st))
+        else:
+            k = int(opt_params[0]) if optimizer == "cem" else 1
+            hi = 1 if optimizer == "cem" else 0
+            part = t.empty(k * (2 + self.knu), dtype=t.float64, device=self.dev)
+            self._check(self.lib.b200mpc_topk_partial_dev(h, P(self.d_knots), P(self.d_reward), self.n_local, self.knu, k, int(index_offset), hi, P(part), st))
+            allp = gather_partials(part, self.world_size, self.group)
+            smin, smax = (float(opt_params[1]), float(opt_params[2])) if optimizer == "cem" else (0.0, 0.0)
+            self._check(self.lib.b200mpc_topk_combine_dev(h, P(allp), self.world_size, self.knu, k, hi, smin, smax, P(self.d_nominal),
+                                                          P(self.d_sigma) if optimizer == "cem" else ctypes.c_void_p(0), P(self.d_elite), st))
+        self._keep = (part, allp)  # keep the buffers alive until the stream has consumed them
+        return self.d_nominal
+
+    KERNELS_PER_STEP = 3  # rollout+cost, partial, combine

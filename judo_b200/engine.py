@@ -1,0 +1,136 @@
+"""Engine: a thin numpy-facing wrapper over one b200mpc handle (one GPU).  All compute happens in libb200mpc.so."""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from judo_b200 import _lib
+from judo_b200.consts import TASK_IDS, task_consts
+
+OPT_IDS = {"mppi": 0, "cem": 1, "ps": 2}
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a: np.ndarray | None):  # noqa: ANN202
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _c(a: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    """Owns a b200mpc_handle.  Raises RuntimeError with the library's message on any failure."""
+
+    def __init__(self, task: str, num_rollouts: int, device: int = 0, consts: np.ndarray | None = None) -> None:
+        self._lib = _lib.load()
+        self.task = task
+        c = _c(task_consts(task) if consts is None else consts)
+        h = ctypes.c_void_p()
+        rc = self._lib.b200mpc_create(ctypes.byref(h), TASK_IDS[task], _p(c), c.size, device, int(num_rollouts))
+        if rc:
+            raise RuntimeError("b200mpc_create: " + self._lib.b200mpc_last_error(None).decode())
+        self._h = h
+        d = _lib.Dims()
+        self._check(self._lib.b200mpc_get_dims(self._h, ctypes.byref(d)))
+        self.nq, self.nv, self.nu, self.nsensordata, self.n_cost_params = d.nq, d.nv, d.nu, d.nsensordata, d.n_cost_params
+        self.device = device
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.b200mpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise RuntimeError(self._lib.b200mpc_last_error(self._h).decode())
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._h
+
+    @property
+    def num_rollouts(self) -> int:
+        return self._lib.b200mpc_num_rollouts(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.b200mpc_launch_count(self._h))
+
+    def update(self, num_rollouts: int) -> None:
+        self._check(self._lib.b200mpc_update(self._h, int(num_rollouts)))
+
+    # ---- contract A
+    def rollout(self, x0: np.ndarray, controls: np.ndarray, want_sensors: bool = True) -> tuple[np.ndarray, np.ndarray | None]:
+        x0, controls = _c(x0), _c(controls)
+        N, H, _ = controls.shape
+        states = np.empty((N, H, self.nq + self.nv))
+        sensors = np.empty((N, H, self.nsensordata)) if want_sensors else None
+        self._check(self._lib.b200mpc_rollout(self._h, _p(x0), int(x0.ndim == 2), _p(controls), N, H, _p(states), _p(sensors)))
+        return states, sensors
+
+    # ---- contract B
+    def plan_costs(self, x0: np.ndarray, knots: np.ndarray, basis: np.ndarray, cost_params: np.ndarray,
+                   want_cost_matrix: bool = False) -> tuple[np.ndarray, np.ndarray | None]:
+        x0, knots, basis, cost_params = _c(x0), _c(knots), _c(basis), _c(cost_params)
+        N, K, _ = knots.shape
+        H = basis.shape[0]
+        assert basis.shape == (H, K) and cost_params.size == self.n_cost_params and x0.shape == (self.nq + self.nv,)
+        reward = np.empty(N)
+        cost = np.empty((N, H), dtype=np.float32) if want_cost_matrix else None
+        cp = None if cost is None else cost.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        self._check(self._lib.b200mpc_plan_costs(self._h, _p(x0), _p(knots), N, K, _p(basis), H, _p(cost_params), cp, _p(reward)))
+        return reward, cost
+
+    def reward(self, states: np.ndarray, controls: np.ndarray, cost_params: np.ndarray) -> np.ndarray:
+        states, controls, cost_params = _c(states), _c(controls), _c(cost_params)
+        N, H, _ = states.shape
+        out = np.empty(N)
+        self._check(self._lib.b200mpc_reward(self._h, _p(states), _p(controls), N, H, _p(cost_params), _p(out)))
+        return out
+
+    # ---- optimizer updates
+    def update_mppi(self, knots: np.ndarray, rewards: np.ndarray, temperature: float) -> np.ndarray:
+        knots, rewards = _c(knots), _c(rewards)
+        N, K, nu = knots.shape
+        out = np.empty((K, nu))
+        self._check(self._lib.b200mpc_update_mppi(self._h, _p(knots), _p(rewards), N, K, float(temperature), _p(out)))
+        return out
+
+    def update_cem(self, knots: np.ndarray, rewards: np.ndarray, num_elites: int, sigma_min: float, sigma_max: float) -> tuple[np.ndarray, np.ndarray]:
+        knots, rewards = _c(knots), _c(rewards)
+        N, K, nu = knots.shape
+        nom, sig = np.empty((K, nu)), np.empty((K, nu))
+        self._check(self._lib.b200mpc_update_cem(self._h, _p(knots), _p(rewards), N, K, int(num_elites), float(sigma_min), float(sigma_max), _p(nom), _p(sig)))
+        return nom, sig
+
+    def update_ps(self, knots: np.ndarray, rewards: np.ndarray) -> np.ndarray:
+        knots, rewards = _c(knots), _c(rewards)
+        N, K, nu = knots.shape
+        out = np.empty((K, nu))
+        self._check(self._lib.b200mpc_update_ps(self._h, _p(knots), _p(rewards), N, K, _p(out)))
+        return out
+
+    # ---- fused plan step
+    def plan_step(self, x0: np.ndarray, knots: np.ndarray, basis: np.ndarray, cost_params: np.ndarray, optimizer: str,
+                  opt_params: np.ndarray, want_rewards: bool = True, n_elite: int = 0) -> dict:
+        x0, knots, basis, cost_params = _c(x0), _c(knots), _c(basis), _c(cost_params)
+        op = _c(np.atleast_1d(opt_params)) if opt_params is not None and np.size(opt_params) else np.zeros(1)
+        N, K, nu = knots.shape
+        H = basis.shape[0]
+        assert basis.shape == (H, K) and cost_params.size == self.n_cost_params and x0.shape == (self.nq + self.nv,) and nu == self.nu
+        nominal = np.empty((K, nu))
+        sigma = np.empty((K, nu)) if optimizer == "cem" else None
+        rewards = np.empty(N) if want_rewards else None
+        elite = np.empty(max(n_elite, 1), dtype=np.int32)
+        self._check(self._lib.b200mpc_plan_step(self._h, _p(x0), _p(knots), N, K, _p(basis), H, _p(cost_params), OPT_IDS[optimizer], _p(op),
+                                                _p(nominal), _p(sigma), _p(rewards), elite.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(n_elite)))
+        return dict(nominal=nominal, sigma=sigma, rewards=rewards, elite=elite[:n_elite])

@@ -1,0 +1,147 @@
+"""CPU: host-side logic of the product (no GPU compute) and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from judo_b200 import _lib
+from judo_b200.config import OverridableConfig, set_config_overrides
+from judo_b200.consts import task_consts
+from judo_b200.normalization import make_normalizer
+from judo_b200.optimizers import (MPPI, CrossEntropyMethod, CrossEntropyMethodConfig, MPPIConfig, PredictiveSamplingConfig,
+                                  get_registered_optimizers, register_optimizer)
+from judo_b200.spline import spline_basis
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_spline_basis_matches_reference_golden(golden):
+    g = golden("spline")
+    for i in range(int(g["ncases"])):
+        kind = str(g[f"s{i}_kind"])
+        for q, o in (("query", "out"), ("query_shift", "out_shift")):
+            B = spline_basis(g[f"s{i}_times"], g[f"s{i}_{q}"], kind)
+            np.testing.assert_allclose(np.einsum("hk,nkj->nhj", B, g[f"s{i}_knots"]), g[f"s{i}_{o}"], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("kind", ["zero", "linear", "cubic"])
+def test_spline_basis_matches_scipy_on_coincident_and_outside_queries(kind):
+    from scipy.interpolate import interp1d
+
+    rng = np.random.default_rng(1)
+    for K in (4, 5, 9):
+        t = 2.0 + np.linspace(0, 1.3, K)
+        y = rng.normal(size=(K, 2))
+        q = np.concatenate([t, t - 1e-12, t + 1e-12, [t[0] - 1, t[-1] + 1], rng.uniform(t[0], t[-1], 20)])
+        ref = interp1d(t, y, kind=kind, axis=0, fill_value=(y[0], y[-1]), bounds_error=False)(q)
+        np.testing.assert_allclose(spline_basis(t, q, kind) @ y, ref, rtol=0, atol=1e-10)
+    with pytest.raises(ValueError):
+        spline_basis(np.arange(3.0), np.arange(3.0), "cubic")
+    with pytest.raises(ValueError):
+        spline_basis(np.arange(4.0), np.arange(3.0), "quintic")
+
+
+def test_sampling_is_bit_exact_with_reference(golden, temp_np_seed):
+    g = golden("optimizers")
+    reg = get_registered_optimizers()
+    for ci in range(int(g["ncases"])):
+        name, task, nu, N = g[f"c{ci}_meta"][:4]
+        cls, cfg_cls = reg[str(name)]
+        cfg = cfg_cls()
+        if task != "default":
+            cfg.set_override(str(task))
+        cfg.num_rollouts = int(N)
+        opt = cls(cfg, int(nu))
+        with temp_np_seed(7 + ci):
+            for it in range(2):
+                if name == "cem":
+                    np.testing.assert_array_equal(opt.sigma, g[f"c{ci}_sigma_in{it}"])
+                knots = opt.sample_control_knots(g[f"c{ci}_nominal_in{it}"])
+                np.testing.assert_array_equal(knots, g[f"c{ci}_knots{it}"])
+                np.testing.assert_array_equal(knots[0], g[f"c{ci}_nominal_in{it}"])  # row 0 is the un-noised nominal
+                if name == "cem":
+                    opt.sigma = g[f"c{ci}_sigma_out{it}"]
+
+
+def test_update_without_engine_fails_loudly():
+    opt = MPPI(MPPIConfig(), 2)
+    with pytest.raises(RuntimeError, match="GPU"):
+        opt.update_nominal_knots(np.zeros((16, 4, 2)), np.zeros(16))
+
+
+def test_cem_pre_optimization_reinterpolates_sigma():
+    cfg = CrossEntropyMethodConfig()
+    opt = CrossEntropyMethod(cfg, 2)
+    opt.sigma = np.arange(8.0).reshape(4, 2)
+    cfg.num_nodes = 6
+    opt.pre_optimization(np.linspace(0, 1, 4), np.linspace(0.1, 1.1, 6))
+    from scipy.interpolate import interp1d
+
+    ref = interp1d(np.linspace(0, 1, 4), np.arange(8.0).reshape(4, 2), axis=0, fill_value="extrapolate", kind="linear")(np.linspace(0.1, 1.1, 6))
+    np.testing.assert_allclose(opt.sigma, ref, atol=1e-13)
+
+
+def test_config_overrides_and_registry():
+    cfg = MPPIConfig()
+    cfg.set_override("leap_cube")
+    assert (cfg.sigma, cfg.temperature, cfg.noise_ramp, cfg.num_rollouts, cfg.use_noise_ramp) == (0.2, 0.0025, 4.0, 32, True)
+    cfg.set_override("nonexistent")
+    assert (cfg.sigma, cfg.temperature, cfg.noise_ramp, cfg.num_rollouts, cfg.use_noise_ramp) == (0.1, 0.05, 2.5, 16, False)
+    ps = PredictiveSamplingConfig()
+    ps.set_override("cartpole")
+    assert ps.num_rollouts == 32 and ps.sigma == 0.05
+    with pytest.warns(UserWarning):
+        set_config_overrides("x", MPPIConfig, {"not_a_field": 1})
+    with pytest.raises(TypeError):
+        set_config_overrides("x", int, {})
+
+    class MyOpt(MPPI):
+        pass
+
+    register_optimizer("mine", MyOpt, MPPIConfig)
+    assert get_registered_optimizers()["mine"] == (MyOpt, MPPIConfig)
+    assert issubclass(MPPIConfig, OverridableConfig)
+
+
+def test_normalizers_closed_form():
+    mm = make_normalizer("min_max", 2, min=np.array([-2.0, 0.0]), max=np.array([2.0, 4.0]))
+    x = np.array([[0.0, 1.0], [2.0, 4.0]])
+    np.testing.assert_allclose(mm.normalize(x), [[0, -0.5], [1, 1]])
+    np.testing.assert_allclose(mm.denormalize(mm.normalize(x)), x)
+    with pytest.warns(UserWarning):
+        inf = make_normalizer("min_max", 2, min=np.array([-np.inf, 0.0]), max=np.array([np.inf, 1.0]))
+    np.testing.assert_allclose(inf.normalize(np.array([3.0, 0.5])), [3.0, 0.0])
+    rn = make_normalizer("running", 3, init_std=1.0)
+    data = np.random.default_rng(0).normal(size=(5, 7, 3)) * 3 + 1
+    for chunk in data:
+        rn.update(chunk)
+    np.testing.assert_allclose(rn.mean, data.reshape(-1, 3).mean(0), rtol=1e-12)
+    np.testing.assert_allclose(rn.std, data.reshape(-1, 3).std(0), rtol=1e-12)
+    np.testing.assert_allclose(rn.denormalize(rn.normalize(data)), data, rtol=1e-4, atol=1e-5)  # eps only on the way in
+    assert make_normalizer("none", 2).normalize(x) is x
+    with pytest.raises(ValueError):
+        make_normalizer("bogus", 2)
+
+
+def test_task_constant_tables_have_the_struct_sizes():
+    # sizes of the all-double structs in csrc/small_tasks.cuh
+    assert task_consts("cartpole").size == 38
+    assert task_consts("cylinder_push").size == 39
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """include/b200mpc.h, judo_b200/_lib.py and the built library agree (loading needs no GPU)."""
+    header = open(os.path.join(ROOT, "include", "b200mpc.h")).read()
+    declared = set(re.findall(r"\b(b200mpc_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    # no device here: create must fail cleanly with a message, never crash or fall back
+    if not os.path.exists("/dev/nvidia0"):
+        h = ctypes.c_void_p()
+        c = task_consts("cartpole")
+        rc = lib.b200mpc_create(ctypes.byref(h), 0, c.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), c.size, 0, 8)
+        assert rc != 0 and b"CUDA" in lib.b200mpc_last_error(None)
