@@ -98,6 +98,15 @@ int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const double* knots, 
 int b200mpc_plan_costs_dev(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K,
                            const double* d_basis, int H, const double* d_cost_params, float* d_cost_NH,
                            double* d_reward_N, void* stream);
+/* One-launch resident plan step: rollout + cost + optimizer update fused (judo_b200/csrc/epilogue.cuh).
+ *   finalize=1: writes d_nominal (K*nu), d_sigma (CEM), d_elite (n_elite indices as doubles, best first).
+ *   finalize=0: writes this rank's partial to d_rank_partial for the all_gather: MPPI [beta, S, V[K*nu]];
+ *               CEM num_elites x [reward, global index, knots]; PS 1 x [reward, global index, knots]; indices are
+ *               offset by index_offset.  opt_params is a HOST pointer (see b200mpc_plan_step). */
+int b200mpc_plan_step_dev(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis,
+                          int H, const double* d_cost_params, int optimizer, const double* opt_params, int finalize,
+                          int index_offset, int n_elite, float* d_cost_NH, double* d_reward_N, double* d_nominal,
+                          double* d_sigma, double* d_elite, double* d_rank_partial, void* stream);
 int b200mpc_rollout_dev(b200mpc_handle* h, const double* d_x0, int x0_batched, const double* d_controls, int N, int H,
                         double* d_states, double* d_sensors, void* stream);
 int b200mpc_mppi_partial_dev(b200mpc_handle* h, const double* d_knots, const double* d_rewards, int N, int KNU,

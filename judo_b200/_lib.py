@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200mpc_update_ps": (_i, [_vp, _dp, _dp, _i, _i, _dp]),
     "b200mpc_plan_step": (_i, [_vp, _dp, _dp, _i, _i, _dp, _i, _dp, _i, _dp, _dp, _dp, _dp, _ip, _i]),
     "b200mpc_plan_costs_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "b200mpc_plan_step_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _dp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200mpc_rollout_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "b200mpc_mppi_partial_dev": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp]),
     "b200mpc_mppi_combine_dev": (_i, [_vp, _vp, _i, _i, _d, _vp, _vp]),

@@ -129,7 +129,9 @@ template <class Task>
 static int launch_rollout(b200mpc_handle* h, const typename Task::Consts& c, const double* d_x0, int batched, const double* d_ctrl,
                           int N, int H, double* d_states, double* d_sensors, cudaStream_t st) {
   int thr = pick_threads(N), grid = (N + thr - 1) / thr;
-  rollout_kernel<Task, false, 1><<<grid, thr, 0, st>>>(c, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr);
+  PlanEpilogue ep{};
+  ep.optimizer = EP_NONE;
+  rollout_kernel<Task, false, 1><<<grid, thr, 0, st>>>(c, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, ep);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -137,7 +139,8 @@ static int launch_rollout(b200mpc_handle* h, const typename Task::Consts& c, con
 
 template <class Task, int MAXK>
 static int launch_costs_k(b200mpc_handle* h, const typename Task::Consts& c, const double* d_x0, const double* d_knots, int N, int K,
-                          const double* d_basis, int H, const double* d_params, float* d_cost, double* d_reward, cudaStream_t st) {
+                          const double* d_basis, int H, const double* d_params, float* d_cost, double* d_reward, const PlanEpilogue& ep,
+                          cudaStream_t st) {
   int thr = pick_threads(N), grid = (N + thr - 1) / thr;
   size_t smem = rollout_cost_smem<Task>(thr, H, K, d_cost != nullptr);
   auto kern = rollout_kernel<Task, true, MAXK>;
@@ -145,17 +148,18 @@ static int launch_costs_k(b200mpc_handle* h, const typename Task::Consts& c, con
     if (smem > 227 * 1024) return fail(h, "horizon/knots too large for the shared-memory tile");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  kern<<<grid, thr, smem, st>>>(c, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward);
+  kern<<<grid, thr, smem, st>>>(c, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
 }
 template <class Task>
 static int launch_costs(b200mpc_handle* h, const typename Task::Consts& c, const double* d_x0, const double* d_knots, int N, int K,
-                        const double* d_basis, int H, const double* d_params, float* d_cost, double* d_reward, cudaStream_t st) {
-  if (K <= 4) return launch_costs_k<Task, 4>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, st);
-  if (K <= 8) return launch_costs_k<Task, 8>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, st);
-  if (K <= 12) return launch_costs_k<Task, 12>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, st);
+                        const double* d_basis, int H, const double* d_params, float* d_cost, double* d_reward, const PlanEpilogue& ep,
+                        cudaStream_t st) {
+  if (K <= 4) return launch_costs_k<Task, 4>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
+  if (K <= 8) return launch_costs_k<Task, 8>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
+  if (K <= 12) return launch_costs_k<Task, 12>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
   return fail(h, "num_nodes > 12 not supported (reference slider range is 3..12, optimizers/base.py:13)");
 }
 
@@ -179,24 +183,88 @@ extern "C" int b200mpc_rollout_dev(b200mpc_handle* h, const double* d_x0, int ba
   return fail(h, "task not supported");
 }
 
-extern "C" int b200mpc_plan_costs_dev(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis,
-                                      int H, const double* d_params, float* d_cost, double* d_reward, void* stream) {
-  if (!h) return 1;
+static int plan_costs_ep(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis, int H,
+                         const double* d_params, float* d_cost, double* d_reward, const PlanEpilogue& ep, cudaStream_t st) {
   if (N <= 0 || H <= 0 || K <= 0) return fail(h, "N, H and K must be positive");
   CK(cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)stream;
   switch (h->task) {
-    case B200MPC_TASK_CARTPOLE: return launch_costs<CartpoleTask>(h, h->cartpole, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, st);
-    case B200MPC_TASK_CYLINDER_PUSH: return launch_costs<CylinderPushTask>(h, h->cyl, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, st);
+    case B200MPC_TASK_CARTPOLE: return launch_costs<CartpoleTask>(h, h->cartpole, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
+    case B200MPC_TASK_CYLINDER_PUSH: return launch_costs<CylinderPushTask>(h, h->cyl, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
 #ifdef B200MPC_WITH_LEAP
     case B200MPC_TASK_LEAP_CUBE: {
-      if (leap_launch(h->leap, /*cost_mode=*/1, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, st, &h->err)) return 1;
+      if (leap_launch(h->leap, /*cost_mode=*/1, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep, st, &h->err)) return 1;
       h->launches++;
       return 0;
     }
 #endif
   }
   return fail(h, "task not supported");
+}
+
+// number of warp partials the fused kernel of this task produces for N rollouts
+static int n_warp_partials(const b200mpc_handle* h, int N) {
+#ifdef B200MPC_WITH_LEAP
+  if (h->task == B200MPC_TASK_LEAP_CUBE) return leap_num_partials(N);
+#endif
+  int thr = pick_threads(N);
+  return ((N + thr - 1) / thr) * (thr / 32);
+}
+
+// Fill a PlanEpilogue and make sure its scratch (ticket + warp partials) exists.  Output pointers are the caller's.
+static int make_epilogue(b200mpc_handle* h, int optimizer, const double* opt_params, int n_elite, int N, int KNU, int finalize,
+                         int index_offset, double* d_nominal, double* d_sigma, double* d_elite, double* d_rank_partial,
+                         cudaStream_t st, PlanEpilogue* ep) {
+  memset(ep, 0, sizeof(*ep));
+  ep->optimizer = optimizer;
+  int k_cem = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 0;
+  if (optimizer == B200MPC_OPT_CEM && k_cem <= 0) return fail(h, "num_elites must be positive");
+  ep->k = std::max(n_elite, k_cem);
+  ep->k_cem = k_cem;
+  if (ep->k > EP_MAXK) return fail(h, "fused epilogue supports at most 8 elites");
+  ep->finalize = finalize;
+  ep->index_offset = index_offset;
+  if (optimizer == B200MPC_OPT_MPPI) ep->temperature = opt_params[0];
+  if (optimizer == B200MPC_OPT_CEM) { ep->sigma_min = opt_params[1]; ep->sigma_max = opt_params[2]; }
+  const int nw = n_warp_partials(h, N);
+  size_t off_m = 16, bytes_m = optimizer == B200MPC_OPT_MPPI ? (size_t)nw * (2 + KNU) * 8 : 0;
+  size_t off_t = off_m + bytes_m, bytes_t = (size_t)nw * (ep->k + 1) * 2 * 8;
+  size_t need = off_t + bytes_t;
+  if (need > h->d_part_bytes) {
+    CK(cudaStreamSynchronize(st));
+    if (grow(h, &h->d_part, &h->d_part_bytes, need, false)) return 1;
+    CK(cudaMemsetAsync(h->d_part, 0, 16, st));  // the ticket
+  }
+  char* base = (char*)h->d_part;
+  ep->ticket = (unsigned int*)base;
+  ep->warp_mppi = (double*)(base + off_m);
+  ep->warp_topk = (double*)(base + off_t);
+  ep->nominal = d_nominal; ep->sigma = d_sigma; ep->elite = d_elite;
+  ep->rank_mppi = d_rank_partial; ep->rank_topk = d_rank_partial;
+  return 0;
+}
+
+extern "C" int b200mpc_plan_costs_dev(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis,
+                                      int H, const double* d_params, float* d_cost, double* d_reward, void* stream) {
+  if (!h) return 1;
+  PlanEpilogue ep{};
+  ep.optimizer = EP_NONE;
+  return plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, (cudaStream_t)stream);
+}
+
+extern "C" int b200mpc_plan_step_dev(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis,
+                                     int H, const double* d_params, int optimizer, const double* opt_params, int finalize,
+                                     int index_offset, int n_elite, float* d_cost, double* d_reward, double* d_nominal, double* d_sigma,
+                                     double* d_elite, double* d_rank_partial, void* stream) {
+  if (!h) return 1;
+  if (optimizer < 0 || optimizer > 2) return fail(h, "unknown optimizer");
+  if (optimizer == B200MPC_OPT_MPPI && !(opt_params && opt_params[0] > 0)) return fail(h, "temperature must be positive");
+  if (optimizer == B200MPC_OPT_CEM && !opt_params) return fail(h, "CEM needs {num_elites, sigma_min, sigma_max}");
+  if (n_elite < 0 || n_elite > EP_MAXK) return fail(h, "n_elite must be in 0..8");
+  CK(cudaSetDevice(h->device));
+  PlanEpilogue ep;
+  if (make_epilogue(h, optimizer, opt_params, n_elite, N, K * h->dims.nu, finalize, index_offset, d_nominal, d_sigma, d_elite,
+                    d_rank_partial, (cudaStream_t)stream, &ep)) return 1;
+  return plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ reductions (device-pointer API)
@@ -267,21 +335,22 @@ extern "C" int b200mpc_topk_combine_dev(b200mpc_handle* h, const double* d_parti
 static int run_update(b200mpc_handle* h, int optimizer, const double* opt_params, const double* d_knots, const double* d_rewards, int N,
                       int KNU, double* d_nominal, double* d_sigma, double* d_elite, int n_elite, cudaStream_t st) {
   int nb = n_partials_for(N);
+  // these kernels use their own scratch (d_work) so that the fused path's ticket in d_part is never clobbered
   if (optimizer == B200MPC_OPT_MPPI) {
-    if (grow(h, &h->d_part, &h->d_part_bytes, (size_t)nb * (2 + KNU) * 8, false)) return 1;
-    if (mppi_blocks(h, d_knots, d_rewards, N, KNU, opt_params[0], (double*)h->d_part, nb, st)) return 1;
-    if (b200mpc_mppi_combine_dev(h, (double*)h->d_part, nb, KNU, opt_params[0], d_nominal, st)) return 1;
+    if (grow(h, &h->d_work, &h->d_work_bytes, (size_t)nb * (2 + KNU) * 8, false)) return 1;
+    if (mppi_blocks(h, d_knots, d_rewards, N, KNU, opt_params[0], (double*)h->d_work, nb, st)) return 1;
+    if (b200mpc_mppi_combine_dev(h, (double*)h->d_work, nb, KNU, opt_params[0], d_nominal, st)) return 1;
     return 0;
   }
   int k = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
   int prefer_high = optimizer == B200MPC_OPT_CEM ? 1 : 0;
   if (k <= 0 || k > 64) return fail(h, "num_elites must be in 1..64");
-  if (grow(h, &h->d_part, &h->d_part_bytes, (size_t)nb * k * (2 + KNU) * 8, false)) return 1;
-  topk_partial_kernel<<<nb, 256, 0, st>>>(d_knots, d_rewards, N, KNU, k, 0, prefer_high, (double*)h->d_part);
+  if (grow(h, &h->d_work, &h->d_work_bytes, (size_t)nb * k * (2 + KNU) * 8, false)) return 1;
+  topk_partial_kernel<<<nb, 256, 0, st>>>(d_knots, d_rewards, N, KNU, k, 0, prefer_high, (double*)h->d_work);
   h->launches++;
   CK(cudaGetLastError());
   double smin = optimizer == B200MPC_OPT_CEM ? opt_params[1] : 0, smax = optimizer == B200MPC_OPT_CEM ? opt_params[2] : 0;
-  return b200mpc_topk_combine_dev(h, (double*)h->d_part, nb, KNU, k, prefer_high, smin, smax, d_nominal,
+  return b200mpc_topk_combine_dev(h, (double*)h->d_work, nb, KNU, k, prefer_high, smin, smax, d_nominal,
                                   optimizer == B200MPC_OPT_CEM ? d_sigma : nullptr, d_elite, st);
 }
 
@@ -422,6 +491,7 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
   if (optimizer == B200MPC_OPT_MPPI && !(opt_params && opt_params[0] > 0)) return fail(h, "temperature must be positive");
   if (optimizer == B200MPC_OPT_CEM && !opt_params) return fail(h, "CEM needs {num_elites, sigma_min, sigma_max}");
   if (n_elite < 0 || n_elite > 64) return fail(h, "n_elite must be in 0..64");
+  if (optimizer < 0 || optimizer > 2) return fail(h, "unknown optimizer");
   CK(cudaSetDevice(h->device));
   const int KNU = K * h->dims.nu;
   size_t ox0, ob, op, ok;
@@ -432,29 +502,34 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
   if (grow(h, &h->d_out, &h->d_out_bytes, out_bytes, false) || grow(h, &h->h_out, &h->h_out_bytes, out_bytes, true)) return 1;
   char* din = (char*)h->d_in; char* dout = (char*)h->d_out;
   double* d_reward = (double*)(dout + o_rw);
-  if (b200mpc_plan_costs_dev(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), nullptr,
-                             d_reward, h->stream)) return 1;
-  bool elite_from_update = optimizer != B200MPC_OPT_MPPI;
-  int k_upd = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
-  if (run_update(h, optimizer, opt_params, (double*)(din + ok), d_reward, N, KNU, (double*)(dout + o_nom), (double*)(dout + o_sig),
-                 (elite_from_update && n_elite > 0 && n_elite <= k_upd) ? (double*)(dout + o_el) : nullptr, n_elite, h->stream)) return 1;
-  bool need_elite_pass = n_elite > 0 && !(elite_from_update && n_elite <= k_upd);
-  if (need_elite_pass) {
-    // best-first indices for the trace gather (controller.py:341: argsort(rewards)[-E:][::-1] -> ties: higher index first)
-    int nb = n_partials_for(N);
-    size_t scratch = (size_t)nb * n_elite * (2 + KNU) * 8 + al16((size_t)KNU * 8);
-    size_t base = al16((size_t)nb * std::max(k_upd, 1) * (2 + KNU) * 8);
-    if (base + scratch > h->d_part_bytes) {
-      // keep the update's partials intact: allocate a larger buffer only when nothing is in flight that needs the old one
+  int k_cem = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 0;
+  if (std::max(n_elite, k_cem) <= EP_MAXK) {
+    // one launch: rollout + cost + optimizer update + elite list
+    if (b200mpc_plan_step_dev(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), optimizer,
+                              opt_params, /*finalize=*/1, 0, n_elite, nullptr, d_reward, (double*)(dout + o_nom), (double*)(dout + o_sig),
+                              (double*)(dout + o_el), nullptr, h->stream)) return 1;
+  } else {
+    // more than 8 elites: separate reduction kernels
+    if (b200mpc_plan_costs_dev(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), nullptr,
+                               d_reward, h->stream)) return 1;
+    CK(cudaStreamSynchronize(h->stream));  // run_update may re-allocate the partial scratch the fused path uses
+    if (run_update(h, optimizer, opt_params, (double*)(din + ok), d_reward, N, KNU, (double*)(dout + o_nom), (double*)(dout + o_sig),
+                   nullptr, 0, h->stream)) return 1;
+    if (n_elite > 0) {
+      int nb = n_partials_for(N);
+      size_t scratch = (size_t)nb * n_elite * (2 + KNU) * 8 + al16((size_t)KNU * 8);
+      void* tmp = nullptr;
       CK(cudaStreamSynchronize(h->stream));
-      if (grow(h, &h->d_part, &h->d_part_bytes, base + scratch, false)) return 1;
+      CK(cudaMalloc(&tmp, scratch));
+      double* part = (double*)tmp;
+      double* dummy_nom = part + (size_t)nb * n_elite * (2 + KNU);
+      topk_partial_kernel<<<nb, 256, 0, h->stream>>>((double*)(din + ok), d_reward, N, KNU, n_elite, 0, 1, part);
+      h->launches++;
+      int rc = b200mpc_topk_combine_dev(h, part, nb, KNU, n_elite, 1, 0, 0, dummy_nom, nullptr, (double*)(dout + o_el), h->stream);
+      cudaStreamSynchronize(h->stream);
+      cudaFree(tmp);
+      if (rc) return 1;
     }
-    double* part = (double*)((char*)h->d_part + base);
-    double* dummy_nom = part + (size_t)nb * n_elite * (2 + KNU);
-    topk_partial_kernel<<<nb, 256, 0, h->stream>>>((double*)(din + ok), d_reward, N, KNU, n_elite, 0, 1, part);
-    h->launches++;
-    CK(cudaGetLastError());
-    if (b200mpc_topk_combine_dev(h, part, nb, KNU, n_elite, 1, 0, 0, dummy_nom, nullptr, (double*)(dout + o_el), h->stream)) return 1;
   }
   size_t copy_bytes = reward_N ? out_bytes : o_rw;
   CK(cudaMemcpyAsync(h->h_out, h->d_out, copy_bytes, cudaMemcpyDeviceToHost, h->stream));

@@ -1,0 +1,214 @@
+// epilogue.cuh — optimizer update fused into the tail of the rollout kernel.
+//
+// Every warp reduces the rollouts it owns to a small partial while rewards and knots are still in registers
+// (warp shuffles only), publishes it, and takes a ticket; the LAST warp to arrive combines all partials in index
+// order (deterministic) and writes either the final nominal knots (single GPU) or this rank's partial for the
+// all_gather (multi-GPU).  One kernel launch per plan step.
+//
+//   MPPI  (judo/optimizers/mppi.py:61-82):  partial = [beta, S, V[KNU]],  beta = min cost,
+//         S = sum exp(-(c-beta)/T),  V = sum exp(-(c-beta)/T) * knots;  combine rescales to the global beta.
+//   CEM   (judo/optimizers/cem.py:76-92) / PS (ps.py:52-65) / trace elites (controller.py:341):
+//         partial = top-k (reward, index) pairs; the final stage picks the global top-k and reads those knots.
+#pragma once
+#include "common.cuh"
+
+namespace b2 {
+
+enum { EP_NONE = -1, EP_MPPI = 0, EP_CEM = 1, EP_PS = 2 };
+constexpr int EP_MAXK = 8;  // max(num_elites, trace elites) the fused path supports; larger -> separate kernels
+
+struct PlanEpilogue {
+  int optimizer;          // EP_*
+  int k;                  // best rollouts to list (descending, ties: higher index first), 0..EP_MAXK
+  int k_cem;              // elites entering CEM's mean/var (<= k)
+  int finalize;           // 1: write nominal/sigma/elite;  0: write rank partials for the exchange
+  int index_offset;       // global index of this launch's rollout 0
+  double temperature, sigma_min, sigma_max;
+  double* warp_mppi;      // scratch [nwarps][2+KNU]
+  double* warp_topk;      // scratch [nwarps][k+1][2]   (slot k: PS argmax, ties -> lower index)
+  unsigned int* ticket;   // zero-initialised; reset by the last warp
+  double* nominal;        // [KNU]  (finalize)
+  double* sigma;          // [KNU]  (finalize, CEM)
+  double* elite;          // [k] global indices as doubles, -1 padded (finalize)
+  double* rank_mppi;      // [2+KNU]            (!finalize)
+  double* rank_topk;      // CEM: [k][2+KNU]; PS: [1][2+KNU]   (!finalize)
+};
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
+  return v;
+}
+__device__ __forceinline__ double wmin(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, shfl_xor_d(v, o));
+  return v;
+}
+__device__ __forceinline__ bool better(double ra, long long ia, double rb, long long ib, bool prefer_high) {
+  if (ia < 0) return false;
+  if (ib < 0) return true;
+  if (ra != rb) return ra > rb;
+  return prefer_high ? ia > ib : ia < ib;
+}
+// warp arg-best of (r, i) under `better`; every lane gets the winner
+__device__ __forceinline__ void warp_best(double& r, long long& i, bool prefer_high) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double r2 = shfl_xor_d(r, o);
+    long long i2 = __shfl_xor_sync(0xffffffffu, i, o);
+    if (better(r2, i2, r, i, prefer_high)) { r = r2; i = i2; }
+  }
+}
+
+// Final stage, run by one full warp after all partials are visible.  knots: this launch's (N, KNU) candidates.
+// Loads are issued in batches of independent __ldcg's (the stage is one warp deep: L2 latency, not bandwidth, is the cost).
+template <int MAXKNU>
+__device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KNU, const double* __restrict__ knots) {
+  const int lane = threadIdx.x & 31;
+  if (ep.optimizer == EP_MPPI) {
+    const int stride = 2 + KNU;
+    double b = INFINITY;
+    for (int p = lane; p < nparts; p += 32) b = fmin(b, __ldcg(ep.warp_mppi + (size_t)p * stride));
+    const double beta = wmin(b);
+    double s = 0, v[MAXKNU];
+#pragma unroll
+    for (int j = 0; j < MAXKNU; j++) v[j] = 0;
+    for (int p = lane; p < nparts; p += 32) {
+      const double* q = ep.warp_mppi + (size_t)p * stride;
+      const double bp = __ldcg(q), sp = __ldcg(q + 1);
+      double x[MAXKNU];
+#pragma unroll
+      for (int j = 0; j < MAXKNU; j++) x[j] = j < KNU ? __ldcg(q + 2 + j) : 0.0;
+      const double sc = sp > 0 ? exp(-(bp - beta) / ep.temperature) : 0.0;
+      s += sp * sc;
+#pragma unroll
+      for (int j = 0; j < MAXKNU; j++) v[j] += x[j] * sc;
+    }
+    const double S = wsum(s);
+    double* out = ep.finalize ? ep.nominal : ep.rank_mppi + 2;
+#pragma unroll
+    for (int j = 0; j < MAXKNU; j++) {
+      if (j < KNU) {
+        const double t = wsum(v[j]);
+        if (lane == 0) out[j] = ep.finalize ? t / S : t;
+      }
+    }
+    if (!ep.finalize && lane == 0) { ep.rank_mppi[0] = beta; ep.rank_mppi[1] = S; }
+  }
+  if (ep.k > 0 || ep.optimizer == EP_PS) {
+    const int k = ep.k, slots = k + 1;
+    // global top-k (descending; ties: higher index first) over nparts*k candidates
+    double prev_r = INFINITY; long long prev_i = -1; bool have_prev = false;
+    double er[EP_MAXK]; long long ei[EP_MAXK];
+    int ne = 0;
+    for (int e = 0; e < k; e++) {
+      double br = -INFINITY; long long bi = -1;
+      for (int cnd = lane; cnd < nparts * k; cnd += 32) {
+        const double* q = ep.warp_topk + ((size_t)(cnd / k) * slots + (cnd % k)) * 2;
+        double r = __ldcg(q); long long i = (long long)__ldcg(q + 1);
+        if (i < 0) continue;
+        if (have_prev && !better(prev_r, prev_i, r, i, true)) continue;
+        if (better(r, i, br, bi, true)) { br = r; bi = i; }
+      }
+      warp_best(br, bi, true);
+      if (bi < 0) break;
+      er[e] = br; ei[e] = bi; ne = e + 1;
+      prev_r = br; prev_i = bi; have_prev = true;
+    }
+    // PS: first maximum (ties -> lower index)
+    double pr = -INFINITY; long long pi = -1;
+    if (ep.optimizer == EP_PS) {
+      for (int p = lane; p < nparts; p += 32) {
+        const double* q = ep.warp_topk + ((size_t)p * slots + k) * 2;
+        double r = __ldcg(q); long long i = (long long)__ldcg(q + 1);
+        if (better(r, i, pr, pi, false)) { pr = r; pi = i; }
+      }
+      warp_best(pr, pi, false);
+    }
+    if (ep.finalize) {
+      if (ep.elite) for (int e = lane; e < k; e += 32) ep.elite[e] = e < ne ? (double)(ei[e] + ep.index_offset) : -1.0;
+      if (ep.optimizer == EP_CEM) {
+        const int nc = min(ne, ep.k_cem);
+        for (int j = lane; j < KNU; j += 32) {
+          double mean = 0;
+          for (int e = 0; e < nc; e++) mean += knots[(size_t)ei[e] * KNU + j];
+          mean = nc ? mean / nc : 0.0;
+          double var = 0;
+          for (int e = 0; e < nc; e++) { double d = knots[(size_t)ei[e] * KNU + j] - mean; var += d * d; }
+          var = nc ? var / nc : 0.0;
+          ep.nominal[j] = mean;
+          ep.sigma[j] = fmin(fmax(sqrt(var), ep.sigma_min), ep.sigma_max);
+        }
+      } else if (ep.optimizer == EP_PS) {
+        for (int j = lane; j < KNU; j += 32) ep.nominal[j] = pi >= 0 ? knots[(size_t)pi * KNU + j] : 0.0;
+      }
+    } else if (ep.optimizer == EP_PS) {  // rank partial: 1 x [reward, global index, knots]
+      double* o = ep.rank_topk;
+      if (lane == 0) { o[0] = pi >= 0 ? pr : -INFINITY; o[1] = pi >= 0 ? (double)(pi + ep.index_offset) : -1.0; }
+      for (int j = lane; j < KNU; j += 32) o[2 + j] = pi >= 0 ? knots[(size_t)pi * KNU + j] : 0.0;
+    } else {  // rank partial: k x [reward, global index, knots]
+      const int stride = 2 + KNU;
+      for (int e = 0; e < k; e++) {
+        double* o = ep.rank_topk + (size_t)e * stride;
+        if (lane == 0) { o[0] = e < ne ? er[e] : -INFINITY; o[1] = e < ne ? (double)(ei[e] + ep.index_offset) : -1.0; }
+        for (int j = lane; j < KNU; j += 32) o[2 + j] = e < ne ? knots[(size_t)ei[e] * KNU + j] : 0.0;
+      }
+    }
+  }
+}
+
+// Publish this warp's partial (already written by the caller), take a ticket, and run the final stage in the last warp.
+template <int MAXKNU>
+__device__ inline void epilogue_commit(const PlanEpilogue& ep, int nparts, int KNU, const double* __restrict__ knots) {
+  __threadfence();
+  __syncwarp();
+  unsigned t = 0;
+  if ((threadIdx.x & 31) == 0) t = atomicAdd(ep.ticket, 1u);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t == (unsigned)nparts - 1) {
+    __threadfence();
+    epilogue_final<MAXKNU>(ep, nparts, KNU, knots);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) *ep.ticket = 0;
+  }
+}
+
+// Thread-per-rollout flavour: lane owns rollout `n` (valid or not) with reward r and knots kn[0..KNU).
+template <int MAXKNU>
+__device__ inline void epilogue_thread_per_rollout(const PlanEpilogue& ep, bool valid, int n_local, double r, const double (&kn)[MAXKNU],
+                                                   int KNU, int warp_global, int nwarps, const double* __restrict__ knots) {
+  const int lane = threadIdx.x & 31;
+  if (ep.optimizer == EP_MPPI) {
+    const double c = valid ? -r : INFINITY;
+    const double beta = wmin(c);
+    const double w = valid ? exp(-(c - beta) / ep.temperature) : 0.0;
+    const double S = wsum(w);
+    double* out = ep.warp_mppi + (size_t)warp_global * (2 + KNU);
+    if (lane == 0) { out[0] = beta; out[1] = S; }
+#pragma unroll
+    for (int j = 0; j < MAXKNU; j++) {
+      if (j < KNU) {
+        double v = wsum(w * kn[j]);
+        if (lane == 0) out[2 + j] = v;
+      }
+    }
+  }
+  if (ep.k > 0 || ep.optimizer == EP_PS) {
+    const int slots = ep.k + 1;
+    double* out = ep.warp_topk + (size_t)warp_global * slots * 2;
+    bool taken = !valid;
+    for (int e = 0; e < ep.k; e++) {
+      double br = taken ? -INFINITY : r; long long bi = taken ? -1 : n_local;
+      warp_best(br, bi, true);
+      if (bi == n_local && !taken) taken = true;
+      if (lane == 0) { out[2 * e] = bi >= 0 ? br : -INFINITY; out[2 * e + 1] = (double)bi; }
+    }
+    double br = valid ? r : -INFINITY; long long bi = valid ? n_local : -1;
+    warp_best(br, bi, false);
+    if (lane == 0) { out[2 * ep.k] = bi >= 0 ? br : -INFINITY; out[2 * ep.k + 1] = (double)bi; }
+  }
+  epilogue_commit<MAXKNU>(ep, nwarps, KNU, knots);
+}
+
+}  // namespace b2

@@ -1,5 +1,6 @@
 // kernels.cuh — the fused rollout kernel for the thread-per-rollout tasks and the optimizer-update reductions.
 #pragma once
+#include "epilogue.cuh"
 #include "small_tasks.cuh"
 
 namespace b2 {
@@ -16,7 +17,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
                                                       const double* __restrict__ in, int N, int H, int K,
                                                       const double* __restrict__ basis, const double* __restrict__ cost_params,
                                                       double* __restrict__ states, double* __restrict__ sensors,
-                                                      float* __restrict__ cost_NH, double* __restrict__ reward_N) {
+                                                      float* __restrict__ cost_NH, double* __restrict__ reward_N,
+                                                      const PlanEpilogue ep) {
   constexpr int NU = Task::NU, NX = Task::NX, NS = Task::NS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -53,6 +55,9 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
 #pragma unroll
     for (int i = 0; i < Task::NCOST; i++) cp[i] = cost_params[i];
     double kn[MAXK * NU];
+    double reward = 0;
+#pragma unroll
+    for (int i = 0; i < MAXK * NU; i++) kn[i] = 0;
     if (n < N) {
 #pragma unroll
       for (int k = 0; k < MAXK; k++)
@@ -77,8 +82,11 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
         total += ct;
         if (cost_NH) sC[(size_t)tid * (H + 1) + t] = (float)ct;
       }
-      reward_N[n] = Task::finish(total, H);
+      reward = Task::finish(total, H);
+      reward_N[n] = reward;
     }
+    if (ep.optimizer != EP_NONE || ep.k > 0)
+      epilogue_thread_per_rollout<MAXK * NU>(ep, n < N, n, reward, kn, K * NU, blockIdx.x * (nthr >> 5) + (tid >> 5), gridDim.x * (nthr >> 5), in);
     if (cost_NH) {
       __syncthreads();
       // coalesced write-back of the block's (nblk, H) tile: consecutive threads write consecutive floats

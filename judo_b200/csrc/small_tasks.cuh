@@ -22,17 +22,21 @@ struct CartpoleConsts {
 struct CartpoleTask {
   static constexpr int NQ = 2, NV = 2, NU = 1, NS = 6, NX = 4, NCOST = 6;
   using Consts = CartpoleConsts;
-  struct State { double q[2], v[2], warm[2]; };
+  // sn/cs cache sincos(q[1]) (shared by this step's kinematics and the previous step's cost); the warm start
+  // qacc_{t-1} = M_{t-1}^-1 qfrc_smooth_{t-1} of an unconstrained step is kept in factored form (wm01, wq) and only
+  // evaluated if a constraint row turns up.
+  struct State { double q[2], v[2], warm[2], sn, cs, wm01, wq[2]; bool lazy; };
 
   __device__ static inline void load(State& s, const double* x) {
-    s.q[0] = x[0]; s.q[1] = x[1]; s.v[0] = x[2]; s.v[1] = x[3]; s.warm[0] = s.warm[1] = 0;
+    s.q[0] = x[0]; s.q[1] = x[1]; s.v[0] = x[2]; s.v[1] = x[3]; s.warm[0] = s.warm[1] = 0; s.lazy = false;
+    s.wm01 = 0; s.wq[0] = s.wq[1] = 0;
+    sincos(s.q[1], &s.sn, &s.cs);
   }
   __device__ static inline void store(const State& s, double* x) { x[0] = s.q[0]; x[1] = s.q[1]; x[2] = s.v[0]; x[3] = s.v[1]; }
 
   // cart: slide along x; pole: hinge about +y at the cart origin, COM at (0,0,l) in the pole frame.
   __device__ static inline void step(const Consts& c, State& s, const double* u, double* sens) {
-    double sn, cs;
-    sincos(s.q[1], &sn, &cs);
+    const double sn = s.sn, cs = s.cs;
     if (sens) {  // framepos sensors are evaluated in mj_forward, i.e. at the pre-step state
       sens[0] = s.q[0] + c.site_cart[0]; sens[1] = c.site_cart[1]; sens[2] = c.site_cart[2];
       sens[3] = s.q[0] + cs * c.site_pole[0] + sn * c.site_pole[2];
@@ -40,55 +44,66 @@ struct CartpoleTask {
       sens[5] = -sn * c.site_pole[0] + cs * c.site_pole[2];
     }
     const double h = c.dt, mp = c.m_pole, l = c.l_pole;
-    double M[2][2];
-    M[0][0] = c.m_cart + mp; M[0][1] = M[1][0] = mp * l * cs; M[1][1] = c.iyy_pole + mp * l * l;
-    // joint-limit rows (mj_instantiateLimit): active when dist < margin
-    double J[2][2], D[2], aref[2];
-    int nefc = 0;
-    if (c.limited != 0) {
-#pragma unroll
-      for (int side = -1; side <= 1; side += 2) {
-        double dist = side * ((side < 0 ? c.lim_lo : c.lim_hi) - s.q[0]);
-        if (dist < c.lim_margin) {
-          double R, ar, jx = -side;
-          row_reference(c.solref, c.solimp, h, dist, c.lim_margin, jx * s.v[0], c.invweight_cart, &R, &ar);
-          J[nefc][0] = jx; J[nefc][1] = 0; D[nefc] = 1 / R; aref[nefc] = ar; nefc++;
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 2; r++) if (r >= nefc) { J[r][0] = J[r][1] = 0; D[r] = 0; aref[r] = 0; }
+    const double m00 = c.m_cart + mp, m01 = mp * l * cs, m11 = c.iyy_pole + mp * l * l;
     // passive (joint damping), bias (Coriolis + gravity), actuation (position servo with ctrl/force clamps)
     double uc = u[0];
     if (c.ctrllimited != 0) uc = fmin(fmax(uc, c.ctrl_lo), c.ctrl_hi);
     double fa = c.kp * uc - c.kp * s.q[0];
     if (c.forcelimited != 0) fa = fmin(fmax(fa, c.frc_lo), c.frc_hi);
-    double bias0 = -mp * l * sn * s.v[1] * s.v[1];
-    double bias1 = -mp * c.gravity * l * sn;
-    double qfs[2] = {-c.damp_cart * s.v[0] - bias0 + fa, -c.damp_pole * s.v[1] - bias1};
-    double L[2][2], qas[2] = {qfs[0], qfs[1]};
-    chol<2>(L, M);
-    chol_solve<2>(L, qas);
-    double qacc[2], qfc[2];
-    SolverOpt o{c.meaninertia, c.tolerance, c.ls_tolerance, (int)c.iterations, (int)c.ls_iterations};
-    RowSolver<2, 2> sol;
-    sol.solve(M, qfs, qas, J, D, aref, nefc, s.warm, o, qacc, qfc);
-    // mj_Euler: implicit joint damping, then semi-implicit advance
-    double qa[2];
-    if (c.damp_cart > 0 || c.damp_pole > 0) {
-      double A[2][2] = {{M[0][0] + h * c.damp_cart, M[0][1]}, {M[1][0], M[1][1] + h * c.damp_pole}};
-      qa[0] = qfs[0] + qfc[0]; qa[1] = qfs[1] + qfc[1];
-      chol<2>(L, A);
-      chol_solve<2>(L, qa);
-    } else { qa[0] = qacc[0]; qa[1] = qacc[1]; }
-    s.v[0] += h * qa[0]; s.v[1] += h * qa[1];
+    const double bias0 = -mp * l * sn * s.v[1] * s.v[1];
+    const double bias1 = -mp * c.gravity * l * sn;
+    const double qfs0 = -c.damp_cart * s.v[0] - bias0 + fa, qfs1 = -c.damp_pole * s.v[1] - bias1;
+    // joint-limit rows (mj_instantiateLimit): active when dist < margin
+    const double dlo = s.q[0] - c.lim_lo, dhi = c.lim_hi - s.q[0];
+    const bool constrained = c.limited != 0 && (dlo < c.lim_margin || dhi < c.lim_margin);
+    double qfc0 = 0, qfc1 = 0;
+    if (!constrained) {
+      // nefc == 0: qacc = qacc_smooth; keep it factored for a possible later warm start
+      s.wm01 = m01; s.wq[0] = qfs0; s.wq[1] = qfs1; s.lazy = true;
+    } else {
+      double M[2][2] = {{m00, m01}, {m01, m11}};
+      double J[2][2] = {{0, 0}, {0, 0}}, D[2] = {0, 0}, aref[2] = {0, 0};
+      int nefc = 0;
+      if (dlo < c.lim_margin) {
+        double R;
+        row_reference(c.solref, c.solimp, h, dlo, c.lim_margin, s.v[0], c.invweight_cart, &R, &aref[0]);
+        J[0][0] = 1; D[0] = 1 / R; nefc = 1;
+      }
+      if (dhi < c.lim_margin) {
+        double R, ar;
+        row_reference(c.solref, c.solimp, h, dhi, c.lim_margin, -s.v[0], c.invweight_cart, &R, &ar);
+        if (nefc == 0) { J[0][0] = -1; D[0] = 1 / R; aref[0] = ar; } else { J[1][0] = -1; D[1] = 1 / R; aref[1] = ar; }
+        nefc++;
+      }
+      if (s.lazy) {  // materialise the previous step's unconstrained acceleration
+        double Mp[2][2] = {{m00, s.wm01}, {s.wm01, m11}}, Lp[2][2];
+        chol<2>(Lp, Mp);
+        s.warm[0] = s.wq[0]; s.warm[1] = s.wq[1];
+        chol_solve<2>(Lp, s.warm);
+        s.lazy = false;
+      }
+      double qfs[2] = {qfs0, qfs1}, qas[2] = {qfs0, qfs1}, L[2][2], qacc[2], qfc[2];
+      chol<2>(L, M);
+      chol_solve<2>(L, qas);
+      SolverOpt o{c.meaninertia, c.tolerance, c.ls_tolerance, (int)c.iterations, (int)c.ls_iterations};
+      RowSolver<2, 2> sol;
+      sol.solve(M, qfs, qas, J, D, aref, nefc, s.warm, o, qacc, qfc);
+      qfc0 = qfc[0]; qfc1 = qfc[1];
+      s.warm[0] = qacc[0]; s.warm[1] = qacc[1];
+    }
+    // mj_Euler: (M + h diag(damping)) qacc = qfrc_smooth + qfrc_constraint — closed-form 2x2 solve — then advance
+    const double a00 = m00 + h * c.damp_cart, a11 = m11 + h * c.damp_pole;
+    const double r0 = qfs0 + qfc0, r1 = qfs1 + qfc1;
+    const double idet = 1.0 / (a00 * a11 - m01 * m01);
+    const double qa0 = (a11 * r0 - m01 * r1) * idet, qa1 = (a00 * r1 - m01 * r0) * idet;
+    s.v[0] += h * qa0; s.v[1] += h * qa1;
     s.q[0] += h * s.v[0]; s.q[1] += h * s.v[1];
-    s.warm[0] = qacc[0]; s.warm[1] = qacc[1];
+    sincos(s.q[1], &s.sn, &s.cs);
   }
 
   // cost params: [w_vertical, w_centered, w_velocity, w_control, p_vertical, p_centered]
   __device__ static inline double cost(const double* p, const State& s, const double* u) {
-    double cz = cos(s.q[1]) - 1;
+    double cz = s.cs - 1;
     double vertical = sqrt(cz * cz + p[4] * p[4]) - p[4];
     double centered = sqrt(s.q[0] * s.q[0] + p[5] * p[5]) - p[5];
     double vel = 0.5 * (s.v[0] * s.v[0] + s.v[1] * s.v[1]);
@@ -128,60 +143,8 @@ struct CylinderPushTask {
       sens[3] = s.q[2] + c.site_cart[0]; sens[4] = s.q[3] + c.site_cart[1]; sens[5] = c.site_cart[2];
     }
     const double h = c.dt;
-    double M[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) M[i][j] = (i == j) ? (i < 2 ? c.mass_pusher : c.mass_cart) : 0.0;
-    // collision: two upright discs; normal from geom1 (pusher) to geom2 (cart)
-    double J[4][4], D[4], aref[4];
-    int nefc = 0;
-    double dx = s.q[2] - s.q[0], dy = s.q[3] - s.q[1];
-    double dxy = sqrt(dx * dx + dy * dy);
-    double dist = dxy - (c.r_pusher + c.r_cart);
-    double includemargin = c.margin - c.gap;
-    if (dist < c.margin && dxy >= B2_MINVAL && dist < includemargin) {
-      double nx = dx / dxy, ny = dy / dxy;
-      // mju_makeFrame: second axis from (0,1,0) if |n_y| < 0.5 else (0,0,1); third = n x second.  Only the xy parts
-      // of the tangents reach the 4 translational dofs.
-      double t1x, t1y, t2x, t2y;
-      if (fabs(ny) < 0.5) {
-        double yx = -ny * nx, yy = 1 - ny * ny;  // (0,1,0) - n (n.y)
-        double yn = sqrt(yx * yx + yy * yy);
-        t1x = yx / yn; t1y = yy / yn; t2x = 0; t2y = 0;
-      } else { t1x = 0; t1y = 0; t2x = ny; t2y = -nx; }
-      double Jn[4] = {-nx, -ny, nx, ny};
-      double Jt[2][4] = {{-t1x, -t1y, t1x, t1y}, {-t2x, -t2y, t2x, t2y}};
-      double mu = c.mu;
-      // rows: (t1,+) (t1,-) (t2,+) (t2,-); R0 from the first row, then the pyramidal adjustment
-      double diagA = c.tran + mu * mu * c.tran;
-#pragma unroll
-      for (int a = 0; a < 2; a++)
-#pragma unroll
-        for (int sg = 0; sg < 2; sg++) {
-          int r = 2 * a + sg;
-          double sgn = sg == 0 ? 1.0 : -1.0, vel = 0;
-#pragma unroll
-          for (int i = 0; i < 4; i++) { J[r][i] = Jn[i] + sgn * mu * Jt[a][i]; vel += J[r][i] * s.v[i]; }
-          double R;
-          row_reference(c.solref, c.solimp, h, dist, includemargin, vel, diagA, &R, &aref[r]);
-          D[r] = R;  // holds R until the cone adjustment below
-        }
-      double R0 = D[0];
-      double R1 = R0 / fmax(B2_MINVAL, c.impratio);
-      double mureg = mu * sqrt(R1 / R0);
-      double Rpy = 2 * mureg * mureg * R1;
-#pragma unroll
-      for (int r = 0; r < 4; r++) D[r] = 1 / Rpy;
-      nefc = 4;
-    } else {
-#pragma unroll
-      for (int r = 0; r < 4; r++) { D[r] = 0; aref[r] = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) J[r][i] = 0; }
-    }
-    // smooth forces: damping + position servos on the pusher; gravity does no work on the slides
-    double qfs[4], qas[4];
+    // smooth forces: damping + position servos on the pusher; gravity does no work on the slides; M is diagonal
+    double qfs[4], mass[4] = {c.mass_pusher, c.mass_pusher, c.mass_cart, c.mass_cart};
 #pragma unroll
     for (int i = 0; i < 4; i++) qfs[i] = -c.damp[i] * s.v[i];
 #pragma unroll
@@ -192,36 +155,76 @@ struct CylinderPushTask {
       if (c.forcelimited != 0) f = fmin(fmax(f, c.frc_lo), c.frc_hi);
       qfs[a] += f;
     }
-    double L[4][4];
-    chol<4>(L, M);
+    double qas[4], qfc[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < 4; i++) qas[i] = qfs[i];
-    chol_solve<4>(L, qas);
-    double qacc[4], qfc[4];
-    SolverOpt o{c.meaninertia, c.tolerance, c.ls_tolerance, (int)c.iterations, (int)c.ls_iterations};
-    RowSolver<4, 4> sol;
-    sol.solve(M, qfs, qas, J, D, aref, nefc, s.warm, o, qacc, qfc);
-    double qa[4];
-    bool any = false;
+    for (int i = 0; i < 4; i++) qas[i] = qfs[i] / mass[i];  // constant divisors: folded to reciprocal constants' cost
+    // collision: two upright discs; normal from geom1 (pusher) to geom2 (cart).  Squared test first: no sqrt off-contact
+    const double dx = s.q[2] - s.q[0], dy = s.q[3] - s.q[1];
+    const double includemargin = c.margin - c.gap, rsum = c.r_pusher + c.r_cart;
+    const double reach = rsum + fmin(c.margin, includemargin);
+    const double d2 = dx * dx + dy * dy;
+    bool contact = false;
+    if (reach > 0 && d2 < reach * reach) {
+      const double dxy = sqrt(d2), dist = dxy - rsum;
+      if (dist < c.margin && dxy >= B2_MINVAL && dist < includemargin) {
+        contact = true;
+        double M[4][4], J[4][4], D[4], aref[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) any = any || c.damp[i] > 0;
-    if (any) {
-      double A[4][4];
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
+          for (int j = 0; j < 4; j++) M[i][j] = (i == j) ? mass[i] : 0.0;
+        const double nx = dx / dxy, ny = dy / dxy;
+        // mju_makeFrame: second axis from (0,1,0) if |n_y| < 0.5 else (0,0,1); third = n x second.  Only the xy parts
+        // of the tangents reach the 4 translational dofs.
+        double t1x, t1y, t2x, t2y;
+        if (fabs(ny) < 0.5) {
+          double yx = -ny * nx, yy = 1 - ny * ny;  // (0,1,0) - n (n.y)
+          double yn = sqrt(yx * yx + yy * yy);
+          t1x = yx / yn; t1y = yy / yn; t2x = 0; t2y = 0;
+        } else { t1x = 0; t1y = 0; t2x = ny; t2y = -nx; }
+        const double Jn[4] = {-nx, -ny, nx, ny};
+        const double Jt[2][4] = {{-t1x, -t1y, t1x, t1y}, {-t2x, -t2y, t2x, t2y}};
+        const double mu = c.mu;
+        // rows: (t1,+) (t1,-) (t2,+) (t2,-); R0 from the first row, then the pyramidal adjustment
+        const double diagA = c.tran + mu * mu * c.tran;
 #pragma unroll
-        for (int j = 0; j < 4; j++) A[i][j] = M[i][j];
-        A[i][i] += h * c.damp[i];
-        qa[i] = qfs[i] + qfc[i];
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+          for (int sg = 0; sg < 2; sg++) {
+            const int r = 2 * a + sg;
+            const double sgn = sg == 0 ? 1.0 : -1.0;
+            double vel = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { J[r][i] = Jn[i] + sgn * mu * Jt[a][i]; vel += J[r][i] * s.v[i]; }
+            double R;
+            row_reference(c.solref, c.solimp, h, dist, includemargin, vel, diagA, &R, &aref[r]);
+            D[r] = R;  // holds R until the cone adjustment below
+          }
+        const double R0 = D[0];
+        const double R1 = R0 / fmax(B2_MINVAL, c.impratio);
+        const double mureg = mu * sqrt(R1 / R0);
+        const double Rpy = 2 * mureg * mureg * R1;
+#pragma unroll
+        for (int r = 0; r < 4; r++) D[r] = 1 / Rpy;
+        double qacc[4];
+        SolverOpt o{c.meaninertia, c.tolerance, c.ls_tolerance, (int)c.iterations, (int)c.ls_iterations};
+        RowSolver<4, 4> sol;
+        sol.solve(M, qfs, qas, J, D, aref, 4, s.warm, o, qacc, qfc);
+#pragma unroll
+        for (int i = 0; i < 4; i++) s.warm[i] = qacc[i];
       }
-      chol<4>(L, A);
-      chol_solve<4>(L, qa);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; i++) qa[i] = qacc[i];
     }
+    if (!contact) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) { s.v[i] += h * qa[i]; s.q[i] += h * s.v[i]; s.warm[i] = qacc[i]; }
+      for (int i = 0; i < 4; i++) s.warm[i] = qas[i];  // qacc = qacc_smooth
+    }
+    // mj_Euler with implicit joint damping (diagonal system), then semi-implicit advance
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const double qa = (qfs[i] + qfc[i]) / (mass[i] + h * c.damp[i]);
+      s.v[i] += h * qa;
+      s.q[i] += h * s.v[i];
+    }
   }
 
   // cost params: [w_pusher_proximity, w_pusher_velocity, w_cart_position, pusher_goal_offset, goal_x, goal_y]

@@ -1,6 +1,6 @@
 """Sharded, device-resident plan step: one process per GPU, rollouts split along N.
 
-Every rank rolls out its own slice with the fused kernel, reduces it to ONE partial
+Every rank rolls out its own slice with the fused kernel, whose epilogue reduces it to ONE partial
 (MPPI: [beta, S, V[K*nu]]; CEM/PS: k x [reward, global index, knots[K*nu]]), the partials are exchanged with a single
 ``all_gather`` (NCCL over NVLink; a few hundred bytes per rank — latency-bound) and every rank runs the same tiny
 combine kernel, so all ranks hold the identical nominal knots.  world_size == 1 skips the collective.
@@ -82,29 +82,36 @@ class ShardedPlanner:
         assert knots_local.shape == (self.n_local, self.K, self.nu)
         self.d_knots = self.torch.as_tensor(np.ascontiguousarray(knots_local, dtype=np.float64), device=self.dev)
 
-    def step(self, optimizer: str, opt_params: np.ndarray, index_offset: int = 0):  # noqa: ANN201
-        """One resident plan step; returns the (K*nu,) nominal device tensor (identical on every rank)."""
+    def step(self, optimizer: str, opt_params: np.ndarray, index_offset: int = 0, n_elite: int = 0):  # noqa: ANN201
+        """One resident plan step; returns the (K*nu,) nominal device tensor (identical on every rank).
+
+        world_size == 1: ONE launch (rollout + cost + update fused).  world_size > 1: the fused kernel leaves this rank's
+        partial, one all_gather moves world_size partials, one tiny combine kernel finishes."""
         t = self.torch
+        from judo_b200.engine import OPT_IDS
+
         st = ctypes.c_void_p(t.cuda.current_stream(self.dev).cuda_stream)
         h = self.engine.handle
         P = lambda x: ctypes.c_void_p(0 if x is None else x.data_ptr())  # noqa: E731
-        self._check(self.lib.b200mpc_plan_costs_dev(h, P(self.d_x0), P(self.d_knots), self.n_local, self.K, P(self.d_basis), self.H,
-                                                    P(self.d_params), P(self.d_cost), P(self.d_reward), st))
-        if optimizer == "mppi":
-            part = t.empty(2 + self.knu, dtype=t.float64, device=self.dev)
-            self._check(self.lib.b200mpc_mppi_partial_dev(h, P(self.d_knots), P(self.d_reward), self.n_local, self.knu, float(opt_params[0]), P(part), st))
+        op = np.ascontiguousarray(np.atleast_1d(opt_params), dtype=np.float64) if np.size(opt_params) else np.zeros(1)
+        opp = op.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        single = self.world_size == 1
+        k = int(op[0]) if optimizer == "cem" else 1
+        width = 2 + self.knu if optimizer == "mppi" else k * (2 + self.knu)
+        part = None if single else t.empty(width, dtype=t.float64, device=self.dev)
+        self._check(self.lib.b200mpc_plan_step_dev(h, P(self.d_x0), P(self.d_knots), self.n_local, self.K, P(self.d_basis), self.H,
+                                                   P(self.d_params), OPT_IDS[optimizer], opp, int(single), int(index_offset),
+                                                   int(n_elite) if single else 0, P(self.d_cost), P(self.d_reward), P(self.d_nominal),
+                                                   P(self.d_sigma), P(self.d_elite), P(part), st))
+        if not single:
             allp = gather_partials(part, self.world_size, self.group)
-            self._check(self.lib.b200mpc_mppi_combine_dev(h, P(allp), self.world_size, self.knu, float(opt_params[0]), P(self.d_nominal), st))
-        else:
-            k = int(opt_params[0]) if optimizer == "cem" else 1
-            hi = 1 if optimizer == "cem" else 0
-            part = t.empty(k * (2 + self.knu), dtype=t.float64, device=self.dev)
-            self._check(self.lib.b200mpc_topk_partial_dev(h, P(self.d_knots), P(self.d_reward), self.n_local, self.knu, k, int(index_offset), hi, P(part), st))
-            allp = gather_partials(part, self.world_size, self.group)
-            smin, smax = (float(opt_params[1]), float(opt_params[2])) if optimizer == "cem" else (0.0, 0.0)
-            self._check(self.lib.b200mpc_topk_combine_dev(h, P(allp), self.world_size, self.knu, k, hi, smin, smax, P(self.d_nominal),
-                                                          P(self.d_sigma) if optimizer == "cem" else ctypes.c_void_p(0), P(self.d_elite), st))
-        self._keep = (part, allp)  # keep the buffers alive until the stream has consumed them
+            if optimizer == "mppi":
+                self._check(self.lib.b200mpc_mppi_combine_dev(h, P(allp), self.world_size, self.knu, float(op[0]), P(self.d_nominal), st))
+            else:
+                hi = 1 if optimizer == "cem" else 0
+                smin, smax = (float(op[1]), float(op[2])) if optimizer == "cem" else (0.0, 0.0)
+                self._check(self.lib.b200mpc_topk_combine_dev(h, P(allp), self.world_size, self.knu, k, hi, smin, smax, P(self.d_nominal),
+                                                              P(self.d_sigma) if optimizer == "cem" else ctypes.c_void_p(0), P(self.d_elite), st))
+            self._keep = (part, allp)  # keep the buffers alive until the stream has consumed them
         return self.d_nominal
 
-    KERNELS_PER_STEP = 3  # rollout+cost, partial, combine

@@ -258,3 +258,68 @@ def test_full_size_properties_cartpole_c2(engines):
     idx = rng.choice(N, 16, replace=False)
     ctrl = np.einsum("hk,nkj->nhj", basis, knots[idx])
     np.testing.assert_allclose(r[idx], op.cartpole_reward(om.rollout(x0, ctrl)[0], ctrl), rtol=1e-9)
+
+
+@pytest.mark.parametrize("optimizer,params", [("mppi", [0.05]), ("cem", [3, 0.1, 1.0]), ("ps", [])])
+def test_resident_sharded_step_equals_unsharded(optimizer, params):
+    """Multi-GPU algebra on one device: two 'ranks' (two handles, disjoint halves of the candidates) leave rank partials;
+    combining them equals the single fused launch over all candidates and the oracle update."""
+    import ctypes
+
+    import torch
+
+    from judo_b200.dist import ShardedPlanner, shard_range
+    from judo_b200.spline import spline_basis
+
+    rng = np.random.default_rng(3)
+    N, H, K = 600, 50, 4
+    x0 = _x0("cylinder_push", rng)
+    knots = rng.normal(size=(N, K, 2)) * 2
+    basis = spline_basis(np.linspace(0, 1.0, K), 0.02 * np.arange(H), "zero")
+    cp = np.array([0.5, 0.0, 0.1, 0.25, 0.0, 0.0])
+    op_params = np.array(params, dtype=np.float64)
+    whole = ShardedPlanner("cylinder_push", N)
+    whole.set_problem(x0, basis, cp)
+    whole.set_knots(knots)
+    nominal = whole.step(optimizer, op_params, n_elite=5).cpu().numpy().reshape(K, 2)
+    rewards = whole.d_reward.cpu().numpy()
+    if optimizer == "mppi":
+        ref = op.mppi_update(knots, rewards, 0.05)
+    elif optimizer == "cem":
+        ref, ref_sigma = op.cem_update(knots, rewards, 3, 0.1, 1.0)
+        np.testing.assert_allclose(whole.d_sigma.cpu().numpy().reshape(K, 2), ref_sigma, rtol=1e-12)
+    else:
+        ref = op.ps_update(knots, rewards)
+    np.testing.assert_allclose(nominal, ref, rtol=1e-11, atol=1e-13)
+    np.testing.assert_array_equal(whole.d_elite.cpu().numpy()[:5].astype(int), np.argsort(rewards)[-5:][::-1])
+    # two ranks
+    parts = []
+    planners = []
+    for rank in range(2):
+        lo, hi = shard_range(N, 2, rank)
+        pl = ShardedPlanner("cylinder_push", hi - lo, rank=rank, world_size=2)
+        pl.set_problem(x0, basis, cp)
+        pl.set_knots(knots[lo:hi])
+        import judo_b200.dist as D
+
+        captured = {}
+        orig = D.gather_partials
+        D.gather_partials = lambda local, ws, group=None: (captured.setdefault("p", local.clone()), torch.stack([local, local]))[1]
+        try:
+            pl.step(optimizer, op_params, index_offset=lo)
+        finally:
+            D.gather_partials = orig
+        parts.append(captured["p"])
+        planners.append(pl)
+    allp = torch.stack(parts).contiguous()
+    pl = planners[0]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
+    if optimizer == "mppi":
+        pl._check(pl.lib.b200mpc_mppi_combine_dev(pl.engine.handle, P(allp), 2, K * 2, 0.05, P(pl.d_nominal), st))
+    else:
+        k = 3 if optimizer == "cem" else 1
+        pl._check(pl.lib.b200mpc_topk_combine_dev(pl.engine.handle, P(allp), 2, K * 2, k, int(optimizer == "cem"), 0.1, 1.0, P(pl.d_nominal),
+                                                  P(pl.d_sigma) if optimizer == "cem" else ctypes.c_void_p(0), P(pl.d_elite), st))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(pl.d_nominal.cpu().numpy().reshape(K, 2), ref, rtol=1e-11, atol=1e-13)
