@@ -174,7 +174,9 @@ extern "C" int b200mpc_rollout_dev(b200mpc_handle* h, const double* d_x0, int ba
     case B200MPC_TASK_CYLINDER_PUSH: return launch_rollout<CylinderPushTask>(h, h->cyl, d_x0, batched, d_ctrl, N, H, d_states, d_sensors, st);
 #ifdef B200MPC_WITH_LEAP
     case B200MPC_TASK_LEAP_CUBE: {
-      if (leap_launch(h->leap, /*cost_mode=*/0, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, st, &h->err)) return 1;
+      PlanEpilogue none{};
+      none.optimizer = EP_NONE;
+      if (leap_launch(h->leap, /*cost_mode=*/0, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, none, st, &h->err)) return 1;
       h->launches++;
       return 0;
     }
@@ -200,6 +202,10 @@ static int plan_costs_ep(b200mpc_handle* h, const double* d_x0, const double* d_
   }
   return fail(h, "task not supported");
 }
+
+static int run_update(b200mpc_handle* h, int optimizer, const double* opt_params, const double* d_knots, const double* d_rewards, int N,
+                      int KNU, double* d_nominal, double* d_sigma, double* d_elite, int n_elite, cudaStream_t st);
+static int n_partials_for(int N);
 
 // number of warp partials the fused kernel of this task produces for N rollouts
 static int n_warp_partials(const b200mpc_handle* h, int N) {
@@ -261,10 +267,35 @@ extern "C" int b200mpc_plan_step_dev(b200mpc_handle* h, const double* d_x0, cons
   if (optimizer == B200MPC_OPT_CEM && !opt_params) return fail(h, "CEM needs {num_elites, sigma_min, sigma_max}");
   if (n_elite < 0 || n_elite > EP_MAXK) return fail(h, "n_elite must be in 0..8");
   CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int KNU = K * h->dims.nu;
+  if (h->task == B200MPC_TASK_LEAP_CUBE) {
+    // warp-per-rollout kernel (ms-scale): the update runs as separate reduction kernels (2% of the step)
+    PlanEpilogue none{};
+    none.optimizer = EP_NONE;
+    if (plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, none, st)) return 1;
+    if (finalize) {
+      if (run_update(h, optimizer, opt_params, d_knots, d_reward, N, KNU, d_nominal, d_sigma, nullptr, 0, st)) return 1;
+      if (n_elite > 0 && d_elite) {
+        int nb = n_partials_for(N);
+        size_t need = (size_t)nb * n_elite * (2 + KNU) * 8 + al16((size_t)KNU * 8);
+        if (need > h->d_part_bytes) { CK(cudaStreamSynchronize(st)); if (grow(h, &h->d_part, &h->d_part_bytes, need, false)) return 1; CK(cudaMemsetAsync(h->d_part, 0, 16, st)); }
+        double* part = (double*)h->d_part + 2;
+        double* dummy = part + (size_t)nb * n_elite * (2 + KNU);
+        topk_partial_kernel<<<nb, 256, 0, st>>>(d_knots, d_reward, N, KNU, n_elite, index_offset, 1, part);
+        h->launches++;
+        CK(cudaGetLastError());
+        if (b200mpc_topk_combine_dev(h, part, nb, KNU, n_elite, 1, 0, 0, dummy, nullptr, d_elite, st)) return 1;
+      }
+      return 0;
+    }
+    if (optimizer == B200MPC_OPT_MPPI) return b200mpc_mppi_partial_dev(h, d_knots, d_reward, N, KNU, opt_params[0], d_rank_partial, st);
+    int k = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
+    return b200mpc_topk_partial_dev(h, d_knots, d_reward, N, KNU, k, index_offset, optimizer == B200MPC_OPT_CEM, d_rank_partial, st);
+  }
   PlanEpilogue ep;
-  if (make_epilogue(h, optimizer, opt_params, n_elite, N, K * h->dims.nu, finalize, index_offset, d_nominal, d_sigma, d_elite,
-                    d_rank_partial, (cudaStream_t)stream, &ep)) return 1;
-  return plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, (cudaStream_t)stream);
+  if (make_epilogue(h, optimizer, opt_params, n_elite, N, KNU, finalize, index_offset, d_nominal, d_sigma, d_elite, d_rank_partial, st, &ep)) return 1;
+  return plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
 }
 
 // ------------------------------------------------------------------ reductions (device-pointer API)

@@ -186,20 +186,20 @@ struct RowSolver {
     if (d1 >= 0 || d2 <= 0) return 0;
     dlo = d1;
     alpha = -d1 / d2;
+    double prev_step = 1e300;
     for (int it = 0; it < o.ls_iterations; it++) {
       ls_eval(D, nefc, alpha, g1, g2, &d1, &d2);
       if (fabs(d1) < gtol) return alpha;
       if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
       double next = d2 > 0 ? alpha - d1 / d2 : -1;
       if (hi < 0) { if (!(next > lo)) next = 2 * alpha + B2_MINVAL; }
-      else if (!(next > lo && next < hi)) {
-        next = lo + (hi - lo) * (-dlo) / (dhi - dlo);
-        if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);
-      }
+      else if (!(next > lo && next < hi && fabs(next - alpha) < 0.5 * prev_step)) next = 0.5 * (lo + hi);
       if (next == alpha) return alpha;
+      prev_step = fabs(next - alpha);
       alpha = next;
     }
-    return alpha;
+    (void)dlo; (void)dhi;
+    return lo > 0 ? lo : alpha;
   }
 
   // mj_fwdConstraint: warm-start choice + Newton iterations.  qacc (out), qfrc_c (out).

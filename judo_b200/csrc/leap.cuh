@@ -1,0 +1,1164 @@
+// leap.cuh — leap_cube: warp-per-rollout reduced articulated-body integrator + cost.
+//
+// One warp owns one rollout: 23 qpos / 22 dofs (free cube + 4 fingers x 4 hinges), state and all per-step work
+// arrays live in shared memory (~29 KB per warp -> 7 resident rollouts per SM, one wave at N = 1024).
+// Every stage of MuJoCo's mj_step that judo/models/xml/leap_cube.xml switches on is restated and spread over the
+// 32 lanes: kinematics (lane per chain), mass matrix + RNE (lane per finger), collision of the cube against the hand
+// geoms (lane per geom / per candidate pair), constraint rows (lane per row), the primal Newton solver with elliptic
+// cones (lane per row / per contact / per Hessian entry, warp Cholesky), implicitfast integration.
+// The collision GEOMETRY is reduced; the constraint/solver pipeline is the full one.
+#pragma once
+#include "epilogue.cuh"
+
+#include <string>
+
+namespace b2 {
+
+constexpr int LEAP_NQ = 23, LEAP_NV = 22, LEAP_NU = 16, LEAP_NS = 31, LEAP_NX = 45, LEAP_NCOST = 9;
+constexpr int LB = 17;         // moving bodies: 0 = cube, 1 + 4f + d = link d of finger f
+constexpr int LMAXG = 80;      // hand collision geoms
+constexpr int LMAXCON = 24;    // contacts kept per step (3 rows each)
+constexpr int LMAXEFC = 32 + 3 * LMAXCON;
+constexpr unsigned FULL = 0xffffffffu;
+#define LH(i, j) Hp[(i) * ((i) + 1) / 2 + (j)]  // j <= i
+
+// All-double POD; field order == judo_b200/tasks/leap_cube.py:leap_consts.
+struct LeapModel {
+  double dt, gravity[3], impratio, tolerance, ls_tolerance, meaninertia, iterations, ls_iterations;
+  double base_pos[5][3], base_quat[5][4];
+  double body_pos[LB][3], body_quat[LB][4], body_ipos[LB][3], body_imat[LB][9], body_mass[LB], body_inertia[LB][3], body_invw[LB];
+  double jnt_axis[LB][3], jnt_pos[LB][3], qpos0[LEAP_NQ];
+  double cube_Irot[9];
+  double dof_damping[LEAP_NV], dof_frictionloss[LEAP_NV], dof_invw[LEAP_NV];
+  double nfr, fr_dof[LEAP_NV], fr_solref[2], fr_solimp[5];
+  double limited[16], lim_lo[16], lim_hi[16], lim_margin, lim_solref[2], lim_solimp[5];
+  double kp[16], kv[16], ctrllimited[16], ctrl_lo[16], ctrl_hi[16];
+  double ngeom, geom_type[LMAXG], geom_body[LMAXG], geom_pos[LMAXG][3], geom_mat[LMAXG][9], geom_size[LMAXG][3], geom_rbound[LMAXG], geom_mu[LMAXG];
+  double cube_size[3], cube_rbound, con_solref[2], con_solimp[5];
+  double site_body[5], site_pos[5][3];
+};
+
+// per-warp shared-memory work area
+struct LeapWork {
+  double qpos[LEAP_NQ], qvel[LEAP_NV], warm[LEAP_NV], ctrl[LEAP_NU];
+  double xpos[LB][3], xquat[LB][4], xmat[LB][9], xipos[LB][3], Iw[LB][6], xanchor[LB][3], xaxis[LB][3];
+  double Mc[6];          // cube block: 3 translational masses are Mc[0..2]; rotational block is model.cube_Irot
+  double Mf[4][4][4];    // finger blocks
+  double Hp[LEAP_NV * (LEAP_NV + 1) / 2];  // packed lower triangle of the Newton Hessian / its Cholesky factor
+  double qfrc_bias[LEAP_NV], qfrc_smooth[LEAP_NV], qacc_smooth[LEAP_NV], qacc[LEAP_NV], qfrc_constraint[LEAP_NV];
+  double Ma[LEAP_NV], grad[LEAP_NV], search[LEAP_NV], Mv[LEAP_NV], tmp[LEAP_NV];
+  double cdist[LMAXCON], cpos[LMAXCON][3], cframe[LMAXCON][9], cmu[LMAXCON], cfri[LMAXCON], cHc[LMAXCON][9];
+  double Jc[3 * LMAXCON][10];  // compressed contact rows: 6 cube dofs + 4 dofs of the touched finger
+  double eD[LMAXEFC], eR[LMAXEFC], earef[LMAXEFC], ejar[LMAXEFC], ejv[LMAXEFC], eforce[LMAXEFC], efloss[LMAXEFC], esign[LMAXEFC];
+  int estate[LMAXEFC], edof[LMAXEFC];
+  int cbody[LMAXCON], cfinger[LMAXCON], cdepth[LMAXCON], cswap[LMAXCON];
+  int cand[LMAXG];
+  int ncon, nefc, nfl, ncand, solver_iter;
+  double cost, gauss;
+};
+
+enum { LST_SATISFIED = 0, LST_QUADRATIC = 1, LST_LINEARNEG = 2, LST_LINEARPOS = 3, LST_CONE = 4 };
+
+// ------------------------------------------------------------------ small vector helpers (same op order as the oracle)
+__device__ __forceinline__ double ldot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void lcross3(double* r, const double* a, const double* b) {
+  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ double lnorm3(const double* a) { return sqrt(ldot3(a, a)); }
+__device__ __forceinline__ double lnormalize3(double* a) {
+  double n = lnorm3(a);
+  if (n < B2_MINVAL) { a[0] = 1; a[1] = 0; a[2] = 0; return 0; }
+  a[0] /= n; a[1] /= n; a[2] /= n;
+  return n;
+}
+__device__ __forceinline__ void lquat_mul(double* r, const double* a, const double* b) {
+  double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+__device__ __forceinline__ void lquat_normalize(double* q) {
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < B2_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+__device__ __forceinline__ void lquat2mat(double* m, const double* q) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+__device__ __forceinline__ void lmat_vec(double* r, const double* m, const double* v) {
+  double x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2], z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ void lmatT_vec(double* r, const double* m, const double* v) {
+  double x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2], z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+__device__ __forceinline__ void lmat_mul(double* r, const double* a, const double* b) {
+  double t[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) t[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+#pragma unroll
+  for (int i = 0; i < 9; i++) r[i] = t[i];
+}
+
+// ------------------------------------------------------------------ kinematics (mj_kinematics + mj_comPos)
+__device__ inline void leap_kinematics(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  if (lane == 0) {  // chain 0: the free cube
+    lquat_normalize(W->qpos + 3);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { W->xpos[0][k] = W->qpos[k]; W->xanchor[0][k] = W->qpos[k]; W->xaxis[0][k] = (k == 2); }
+#pragma unroll
+    for (int k = 0; k < 4; k++) W->xquat[0][k] = W->qpos[3 + k];
+    lquat2mat(W->xmat[0], W->xquat[0]);
+  } else if (lane <= 4) {  // chains 1..4: fingers hanging off the static palm
+    const int f = lane - 1;
+    double ppos[3], pquat[4], pmat[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) ppos[k] = m->base_pos[lane][k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) pquat[k] = m->base_quat[lane][k];
+    lquat2mat(pmat, pquat);
+    for (int d = 0; d < 4; d++) {
+      const int b = 1 + 4 * f + d;
+      double pos[3], quat[4], t[3], mat[9], axis[3], off[3], anchor[3], dq[4], nq[4];
+      lmat_vec(t, pmat, m->body_pos[b]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) pos[k] = ppos[k] + t[k];
+      lquat_mul(quat, pquat, m->body_quat[b]);
+      lquat2mat(mat, quat);
+      lmat_vec(axis, mat, m->jnt_axis[b]);
+      lmat_vec(off, mat, m->jnt_pos[b]);
+      const double q = W->qpos[7 + 4 * f + d] - m->qpos0[7 + 4 * f + d];
+      double sn, cs;
+      sincos(0.5 * q, &sn, &cs);
+#pragma unroll
+      for (int k = 0; k < 3; k++) anchor[k] = pos[k] + off[k];
+      dq[0] = cs; dq[1] = sn * m->jnt_axis[b][0]; dq[2] = sn * m->jnt_axis[b][1]; dq[3] = sn * m->jnt_axis[b][2];
+      lquat_mul(nq, quat, dq);
+      lquat2mat(mat, nq);
+      lmat_vec(off, mat, m->jnt_pos[b]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { pos[k] = anchor[k] - off[k]; W->xanchor[b][k] = anchor[k]; W->xaxis[b][k] = axis[k]; }
+      lquat_normalize(nq);
+      lquat2mat(mat, nq);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { W->xpos[b][k] = pos[k]; ppos[k] = pos[k]; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { W->xquat[b][k] = nq[k]; pquat[k] = nq[k]; }
+#pragma unroll
+      for (int k = 0; k < 9; k++) { W->xmat[b][k] = mat[k]; pmat[k] = mat[k]; }
+    }
+  }
+  __syncwarp();
+  if (lane < LB) {  // inertial frames and world inertia tensors
+    const int b = lane;
+    double t[3], im[9];
+    lmat_vec(t, W->xmat[b], m->body_ipos[b]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) W->xipos[b][k] = W->xpos[b][k] + t[k];
+    lmat_mul(im, W->xmat[b], m->body_imat[b]);
+    int e = 0;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = r; c < 3; c++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) s += im[3 * r + k] * m->body_inertia[b][k] * im[3 * c + k];
+        W->Iw[b][e++] = s;  // xx xy xz yy yz zz
+      }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void Iw_mul(double* r, const double* I6, const double* v) {
+  r[0] = I6[0] * v[0] + I6[1] * v[1] + I6[2] * v[2];
+  r[1] = I6[1] * v[0] + I6[3] * v[1] + I6[4] * v[2];
+  r[2] = I6[2] * v[0] + I6[4] * v[1] + I6[5] * v[2];
+}
+
+// ------------------------------------------------------------------ mass matrix (mj_crb) and bias forces (mj_rne), lane per chain
+__device__ inline void leap_mass_and_bias(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) W->Mc[k] = m->body_mass[0];
+    // cube bias: gravity on the translational dofs; gyroscopic torque in the body frame
+    double wl[3] = {W->qvel[3], W->qvel[4], W->qvel[5]}, Iwl[3], g[3];
+    lmat_vec(Iwl, m->cube_Irot, wl);
+    lcross3(g, wl, Iwl);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { W->qfrc_bias[k] = -m->body_mass[0] * m->gravity[k]; W->qfrc_bias[3 + k] = g[k]; }
+  } else if (lane <= 4) {
+    const int f = lane - 1, b0 = 1 + 4 * f;
+    // M_ij = sum_{b >= j} m_b (a_i x r_ib).(a_j x r_jb) + a_j . Iw_b a_i     (i <= j, r_ib = com_b - anchor_i)
+    double c[4][4][3], Ia[4][4][3];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int b = i; b < 4; b++) {
+        double r[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) r[k] = W->xipos[b0 + b][k] - W->xanchor[b0 + i][k];
+        lcross3(c[i][b], W->xaxis[b0 + i], r);
+        Iw_mul(Ia[i][b], W->Iw[b0 + b], W->xaxis[b0 + i]);
+      }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = i; j < 4; j++) {
+        double s = 0;
+#pragma unroll
+        for (int b = j; b < 4; b++) s += m->body_mass[b0 + b] * ldot3(c[i][b], c[j][b]) + ldot3(W->xaxis[b0 + j], Ia[i][b]);
+        W->Mf[f][i][j] = s; W->Mf[f][j][i] = s;
+      }
+    // RNE with zero acceleration, classical Newton-Euler in world coordinates (base: w = 0, a = -g)
+    double Wv[3] = {0, 0, 0}, A[3] = {0, 0, 0}, P[3], V[3] = {0, 0, 0}, Ac[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { P[k] = m->base_pos[lane][k]; Ac[k] = -m->gravity[k]; }
+    double F[4][3], N0[4][3];
+    for (int d = 0; d < 4; d++) {
+      const int b = b0 + d;
+      double r[3], t[3], t2[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) r[k] = W->xanchor[b][k] - P[k];
+      lcross3(t, Wv, r);
+#pragma unroll
+      for (int k = 0; k < 3; k++) V[k] += t[k];
+      lcross3(t2, Wv, t);
+      lcross3(t, A, r);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { Ac[k] += t[k] + t2[k]; P[k] = W->xanchor[b][k]; }
+      const double qd = W->qvel[6 + 4 * f + d];
+      double u[3] = {W->xaxis[b][0] * qd, W->xaxis[b][1] * qd, W->xaxis[b][2] * qd};
+      lcross3(t, Wv, u);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { A[k] += t[k]; Wv[k] += u[k]; }
+      // move the reference point to the body origin (kept as P for the next link), then evaluate at the COM
+#pragma unroll
+      for (int k = 0; k < 3; k++) r[k] = W->xpos[b][k] - P[k];
+      lcross3(t, Wv, r);
+      lcross3(t2, Wv, t);
+#pragma unroll
+      for (int k = 0; k < 3; k++) V[k] += t[k];
+      lcross3(t, A, r);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { Ac[k] += t[k] + t2[k]; P[k] = W->xpos[b][k]; }
+      double ac[3], Iwa[3], Iww[3], n[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) r[k] = W->xipos[b][k] - W->xpos[b][k];
+      lcross3(t, Wv, r); lcross3(t2, Wv, t); lcross3(t, A, r);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { ac[k] = Ac[k] + t[k] + t2[k]; F[d][k] = m->body_mass[b] * ac[k]; }
+      Iw_mul(Iwa, W->Iw[b], A);
+      Iw_mul(Iww, W->Iw[b], Wv);
+      lcross3(t, Wv, Iww);
+      lcross3(n, W->xipos[b], F[d]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) N0[d][k] = Iwa[k] + t[k] + n[k];
+    }
+    for (int d = 3; d >= 0; d--) {
+      const int b = b0 + d;
+      double t[3], nn[3];
+      lcross3(t, W->xanchor[b], F[d]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) nn[k] = N0[d][k] - t[k];
+      W->qfrc_bias[6 + 4 * f + d] = ldot3(W->xaxis[b], nn);
+      if (d > 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { F[d - 1][k] += F[d][k]; N0[d - 1][k] += N0[d][k]; }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// y = M x (block diagonal), lane per dof
+__device__ __forceinline__ double leap_mulM_row(const LeapModel* __restrict__ m, const LeapWork* W, const double* x, int i) {
+  if (i < 3) return W->Mc[i] * x[i];
+  if (i < 6) { const double* R = m->cube_Irot + 3 * (i - 3); return R[0] * x[3] + R[1] * x[4] + R[2] * x[5]; }
+  const int f = (i - 6) >> 2, r = (i - 6) & 3;
+  const double* row = W->Mf[f][r];
+  const double* xx = x + 6 + 4 * f;
+  return row[0] * xx[0] + row[1] * xx[1] + row[2] * xx[2] + row[3] * xx[3];
+}
+
+// x <- (M + diag(add))^-1 x, exploiting the block structure: cube (lane 0) and one finger per lane (1..4).
+// Small dense Cholesky per block, same recurrences as the oracle's dense factorisation restricted to the block.
+template <int N>
+__device__ __forceinline__ void small_chol_solve(double (&A)[N][N], double* x) {
+  double L[N][N];
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      double s = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+      if (i == j) { if (s < B2_MINVAL) s = B2_MINVAL; L[i][i] = sqrt(s); } else L[i][j] = s / L[j][j];
+    }
+#pragma unroll
+  for (int i = 0; i < N; i++) { double s = x[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s -= L[i][k] * x[k];
+    x[i] = s / L[i][i]; }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) { double s = x[i];
+#pragma unroll
+    for (int k = i + 1; k < N; k++) s -= L[k][i] * x[k];
+    x[i] = s / L[i][i]; }
+}
+__device__ inline void leap_block_solve(const LeapModel* __restrict__ m, LeapWork* W, const double* add, double* x, int lane) {
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) x[k] = x[k] / (W->Mc[k] + (add ? add[k] : 0.0));
+    double A[3][3], v[3] = {x[3], x[4], x[5]};
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) A[i][j] = m->cube_Irot[3 * i + j] + ((i == j && add) ? add[3 + i] : 0.0);
+    small_chol_solve<3>(A, v);
+    x[3] = v[0]; x[4] = v[1]; x[5] = v[2];
+  } else if (lane <= 4) {
+    const int f = lane - 1;
+    double A[4][4], v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { v[i] = x[6 + 4 * f + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) A[i][j] = W->Mf[f][i][j] + ((i == j && add) ? add[6 + 4 * f + i] : 0.0); }
+    small_chol_solve<4>(A, v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) x[6 + 4 * f + i] = v[i];
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ collision (reduced geometry; same routines as the oracle)
+struct LRaw { double dist, pos[3], normal[3]; };
+
+__device__ inline int l_clip_poly(double (*poly)[2], int n, int axis, double sign, double lim) {
+  double out[16][2];
+  int no = 0;
+  for (int i = 0; i < n; i++) {
+    const double* a = poly[i];
+    const double* b = poly[(i + 1) % n];
+    double da = sign * a[axis] - lim, db = sign * b[axis] - lim;
+    if (da <= 0) { out[no][0] = a[0]; out[no][1] = a[1]; no++; }
+    if ((da < 0 && db > 0) || (da > 0 && db < 0)) {
+      double t = da / (da - db);
+      out[no][0] = a[0] + t * (b[0] - a[0]); out[no][1] = a[1] + t * (b[1] - a[1]); no++;
+    }
+    if (no >= 15) break;
+  }
+  for (int i = 0; i < no; i++) { poly[i][0] = out[i][0]; poly[i][1] = out[i][1]; }
+  return no;
+}
+
+__device__ inline int l_sphere_box(const double* ps, double rs, const double* pb, const double* mb, const double* sb, double margin, LRaw* out) {
+  double rel[3], loc[3], cl[3];
+  for (int k = 0; k < 3; k++) rel[k] = ps[k] - pb[k];
+  lmatT_vec(loc, mb, rel);
+  int inside = 1;
+  for (int k = 0; k < 3; k++) {
+    cl[k] = fmin(fmax(loc[k], -sb[k]), sb[k]);
+    if (cl[k] != loc[k]) inside = 0;
+  }
+  double nl[3], dist;
+  if (!inside) {
+    double dv[3] = {loc[0] - cl[0], loc[1] - cl[1], loc[2] - cl[2]};
+    double dn = lnorm3(dv);
+    if (dn - rs >= margin) return 0;
+    for (int k = 0; k < 3; k++) nl[k] = -dv[k] / dn;
+    dist = dn - rs;
+  } else {
+    int ax = 0; double best = 1e300;
+    for (int k = 0; k < 3; k++) { double g = sb[k] - fabs(loc[k]); if (g < best) { best = g; ax = k; } }
+    nl[0] = nl[1] = nl[2] = 0; nl[ax] = loc[ax] >= 0 ? -1 : 1;
+    cl[ax] = loc[ax] >= 0 ? sb[ax] : -sb[ax];
+    dist = -best - rs;
+  }
+  lmat_vec(out->normal, mb, nl);
+  double clw[3];
+  lmat_vec(clw, mb, cl);
+  for (int k = 0; k < 3; k++) out->pos[k] = pb[k] + clw[k] - out->normal[k] * (-0.5 * dist);
+  out->dist = dist;
+  return 1;
+}
+
+__device__ inline int l_box_box(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2, const double* s2,
+                                double margin, LRaw* out, int maxout) {
+  double R[3][3], AR[3][3], t[3], d12[3];
+  for (int k = 0; k < 3; k++) d12[k] = p2[k] - p1[k];
+  lmatT_vec(t, m1, d12);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      R[i][j] = m1[i] * m2[j] + m1[3 + i] * m2[3 + j] + m1[6 + i] * m2[6 + j];
+      AR[i][j] = fabs(R[i][j]) + 1e-12;
+    }
+  double best = -1e300; int code = -1; double bsign = 1;
+  for (int i = 0; i < 3; i++) {
+    double sep = fabs(t[i]) - (s1[i] + s2[0] * AR[i][0] + s2[1] * AR[i][1] + s2[2] * AR[i][2]);
+    if (sep >= margin) return 0;
+    if (sep > best) { best = sep; code = i; bsign = t[i] >= 0 ? 1 : -1; }
+  }
+  for (int j = 0; j < 3; j++) {
+    double tj = t[0] * R[0][j] + t[1] * R[1][j] + t[2] * R[2][j];
+    double sep = fabs(tj) - (s2[j] + s1[0] * AR[0][j] + s1[1] * AR[1][j] + s1[2] * AR[2][j]);
+    if (sep >= margin) return 0;
+    if (sep > best) { best = sep; code = 3 + j; bsign = tj >= 0 ? 1 : -1; }
+  }
+  double ebest = -1e300; int ecode = -1; double esign = 1, eaxis[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double a1[3] = {m1[i], m1[3 + i], m1[6 + i]}, a2[3] = {m2[j], m2[3 + j], m2[6 + j]}, ax[3];
+      lcross3(ax, a1, a2);
+      double len = lnorm3(ax);
+      if (len < 1e-8) continue;
+      for (int k = 0; k < 3; k++) ax[k] /= len;
+      double td = ldot3(ax, d12), ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) {
+        double c1[3] = {m1[k], m1[3 + k], m1[6 + k]}, c2[3] = {m2[k], m2[3 + k], m2[6 + k]};
+        ra += s1[k] * fabs(ldot3(ax, c1)); rb += s2[k] * fabs(ldot3(ax, c2));
+      }
+      double sep = fabs(td) - (ra + rb);
+      if (sep >= margin) return 0;
+      if (sep > ebest) { ebest = sep; ecode = 6 + 3 * i + j; esign = td >= 0 ? 1 : -1; eaxis[0] = ax[0]; eaxis[1] = ax[1]; eaxis[2] = ax[2]; }
+    }
+  if (ecode >= 0 && ebest > best + 1e-6 + 0.05 * fabs(best)) {
+    int i = (ecode - 6) / 3, j = (ecode - 6) % 3;
+    double n[3] = {eaxis[0] * esign, eaxis[1] * esign, eaxis[2] * esign};
+    double c1[3] = {p1[0], p1[1], p1[2]}, c2[3] = {p2[0], p2[1], p2[2]};
+    for (int k = 0; k < 3; k++) {
+      if (k != i) { double a[3] = {m1[k], m1[3 + k], m1[6 + k]}; double sg = ldot3(a, n) > 0 ? 1 : -1; for (int q = 0; q < 3; q++) c1[q] += sg * s1[k] * a[q]; }
+      if (k != j) { double a[3] = {m2[k], m2[3 + k], m2[6 + k]}; double sg = ldot3(a, n) > 0 ? -1 : 1; for (int q = 0; q < 3; q++) c2[q] += sg * s2[k] * a[q]; }
+    }
+    double u1[3] = {m1[i], m1[3 + i], m1[6 + i]}, u2[3] = {m2[j], m2[3 + j], m2[6 + j]}, w0[3];
+    for (int k = 0; k < 3; k++) w0[k] = c1[k] - c2[k];
+    double b = ldot3(u1, u2), dd = ldot3(u1, w0), e = ldot3(u2, w0), den = 1 - b * b;
+    double sc = den > 1e-12 ? (b * e - dd) / den : 0, tc = den > 1e-12 ? (e - b * dd) / den : 0;
+    sc = fmin(fmax(sc, -s1[i]), s1[i]); tc = fmin(fmax(tc, -s2[j]), s2[j]);
+    out[0].dist = ebest;
+    for (int k = 0; k < 3; k++) { out[0].normal[k] = n[k]; out[0].pos[k] = 0.5 * ((c1[k] + sc * u1[k]) + (c2[k] + tc * u2[k])); }
+    return 1;
+  }
+  const double *pr, *mr, *sr, *pi, *mi, *si;
+  int raxis; double nsign;
+  const int ref_is_1 = code < 3;
+  if (ref_is_1) { pr = p1; mr = m1; sr = s1; pi = p2; mi = m2; si = s2; raxis = code; nsign = bsign; }
+  else { pr = p2; mr = m2; sr = s2; pi = p1; mi = m1; si = s1; raxis = code - 3; nsign = -bsign; }
+  double nref[3] = {mr[raxis] * nsign, mr[3 + raxis] * nsign, mr[6 + raxis] * nsign};
+  int iaxis = 0; double imin = 1e300, isign = 1;
+  for (int k = 0; k < 3; k++) {
+    double a[3] = {mi[k], mi[3 + k], mi[6 + k]}, dd = ldot3(a, nref);
+    if (-fabs(dd) < imin) { imin = -fabs(dd); iaxis = k; isign = dd > 0 ? -1 : 1; }
+  }
+  const int iu = (iaxis + 1) % 3, iv = (iaxis + 2) % 3, ru = (raxis + 1) % 3, rv = (raxis + 2) % 3;
+  double fc[3];
+  for (int k = 0; k < 3; k++) fc[k] = pi[k] + isign * si[iaxis] * mi[3 * k + iaxis];
+  double poly[16][2];
+  int n = 4;
+  const double sg[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
+  double verts[4][3];
+  for (int c = 0; c < 4; c++) {
+    for (int k = 0; k < 3; k++) verts[c][k] = fc[k] + sg[c][0] * si[iu] * mi[3 * k + iu] + sg[c][1] * si[iv] * mi[3 * k + iv] - pr[k];
+    double loc[3];
+    lmatT_vec(loc, mr, verts[c]);
+    poly[c][0] = loc[ru]; poly[c][1] = loc[rv];
+  }
+  double l0[3], l1[3], l2[3];
+  lmatT_vec(l0, mr, verts[0]); lmatT_vec(l1, mr, verts[1]); lmatT_vec(l2, mr, verts[3]);
+  const double e1u = l1[ru] - l0[ru], e1v = l1[rv] - l0[rv], e1h = l1[raxis] - l0[raxis];
+  const double e2u = l2[ru] - l0[ru], e2v = l2[rv] - l0[rv], e2h = l2[raxis] - l0[raxis];
+  const double det = e1u * e2v - e1v * e2u;
+  n = l_clip_poly(poly, n, 0, 1, sr[ru]);
+  if (n) n = l_clip_poly(poly, n, 0, -1, sr[ru]);
+  if (n) n = l_clip_poly(poly, n, 1, 1, sr[rv]);
+  if (n) n = l_clip_poly(poly, n, 1, -1, sr[rv]);
+  int nc = 0;
+  for (int c = 0; c < n && nc < maxout; c++) {
+    double du = poly[c][0] - l0[ru], dv = poly[c][1] - l0[rv], h;
+    if (fabs(det) > 1e-14) {
+      double a = (du * e2v - dv * e2u) / det, b = (e1u * dv - e1v * du) / det;
+      h = l0[raxis] + a * e1h + b * e2h;
+    } else h = l0[raxis];
+    double dist = nsign * h - sr[raxis];
+    if (dist >= margin) continue;
+    double loc[3], wpt[3];
+    loc[ru] = poly[c][0]; loc[rv] = poly[c][1]; loc[raxis] = h - 0.5 * dist * nsign;
+    lmat_vec(wpt, mr, loc);
+    out[nc].dist = dist;
+    for (int k = 0; k < 3; k++) { out[nc].pos[k] = pr[k] + wpt[k]; out[nc].normal[k] = ref_is_1 ? nref[k] : -nref[k]; }
+    nc++;
+  }
+  return nc;
+}
+
+__device__ inline void l_make_frame(double* frame) {
+  double* x = frame; double* y = frame + 3; double* z = frame + 6;
+  lnormalize3(x);
+  if (fabs(x[1]) < 0.5) { y[0] = 0; y[1] = 1; y[2] = 0; } else { y[0] = 0; y[1] = 0; y[2] = 1; }
+  double dd = ldot3(x, y);
+  for (int k = 0; k < 3; k++) y[k] -= dd * x[k];
+  lnormalize3(y);
+  lcross3(z, x, y);
+}
+
+__device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  const int ng = (int)m->ngeom;
+  const double* cp = W->xpos[0];
+  // broad phase: bounding spheres against the cube's; ordered compaction keeps the geom order of the pair list
+  int base = 0;
+  for (int g0 = 0; g0 < ng; g0 += 32) {
+    const int g = g0 + lane;
+    bool keep = false;
+    if (g < ng) {
+      const int b = (int)m->geom_body[g];
+      double gp[3];
+      if (b < 0) { gp[0] = m->geom_pos[g][0]; gp[1] = m->geom_pos[g][1]; gp[2] = m->geom_pos[g][2]; }
+      else { double t[3]; lmat_vec(t, W->xmat[b], m->geom_pos[g]); gp[0] = W->xpos[b][0] + t[0]; gp[1] = W->xpos[b][1] + t[1]; gp[2] = W->xpos[b][2] + t[2]; }
+      double dc[3] = {gp[0] - cp[0], gp[1] - cp[1], gp[2] - cp[2]};
+      keep = !(lnorm3(dc) > m->geom_rbound[g] + m->cube_rbound);
+    }
+    const unsigned mask = __ballot_sync(FULL, keep);
+    if (keep) W->cand[base + __popc(mask & ((1u << lane) - 1))] = g;
+    base += __popc(mask);
+  }
+  __syncwarp();
+  const int ncand = base;
+  int ncon = 0;
+  for (int c0 = 0; c0 < ncand; c0 += 32) {
+    const int ci = c0 + lane;
+    LRaw raw[8];
+    int n = 0, g = -1, b = -1, swap = 0;
+    if (ci < ncand) {
+      g = W->cand[ci];
+      b = (int)m->geom_body[g];
+      double gp[3], gm[9];
+      if (b < 0) {
+        for (int k = 0; k < 3; k++) gp[k] = m->geom_pos[g][k];
+        for (int k = 0; k < 9; k++) gm[k] = m->geom_mat[g][k];
+      } else {
+        double t[3];
+        lmat_vec(t, W->xmat[b], m->geom_pos[g]);
+        for (int k = 0; k < 3; k++) gp[k] = W->xpos[b][k] + t[k];
+        lmat_mul(gm, W->xmat[b], m->geom_mat[g]);
+      }
+      if ((int)m->geom_type[g] == 6) n = l_box_box(cp, W->xmat[0], m->cube_size, gp, gm, m->geom_size[g], 0.0, raw, 8);  // geom1 = cube
+      else { n = l_sphere_box(gp, m->geom_size[g][0], cp, W->xmat[0], m->cube_size, 0.0, raw); swap = 1; }          // geom1 = sphere
+    }
+    // ordered slot allocation: exclusive prefix of n over the lanes
+    int pre = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += v; }
+    const int total = __shfl_sync(FULL, pre, 31);
+    pre -= n;
+    for (int i = 0; i < n; i++) {
+      const int slot = ncon + pre + i;
+      if (slot < LMAXCON) {
+        W->cdist[slot] = raw[i].dist;
+        for (int k = 0; k < 3; k++) { W->cpos[slot][k] = raw[i].pos[k]; W->cframe[slot][k] = raw[i].normal[k]; }
+        l_make_frame(W->cframe[slot]);
+        W->cbody[slot] = b; W->cswap[slot] = swap;
+        W->cfinger[slot] = b >= 1 ? (b - 1) >> 2 : -1;
+        W->cdepth[slot] = b >= 1 ? (b - 1) & 3 : -1;
+        W->cfri[slot] = m->geom_mu[g];
+      }
+    }
+    ncon += total;
+  }
+  __syncwarp();
+  if (lane == 0) W->ncon = ncon < LMAXCON ? ncon : LMAXCON;
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ constraint rows (mj_makeConstraint + mj_makeImpedance)
+__device__ __forceinline__ double leap_Jrow_dot(const LeapWork* W, int crow, const double* x) {
+  const double* J = W->Jc[crow];
+  const int f = W->cfinger[crow / 3];
+  double s = J[0] * x[0] + J[1] * x[1] + J[2] * x[2] + J[3] * x[3] + J[4] * x[4] + J[5] * x[5];
+  if (f >= 0) { const double* xx = x + 6 + 4 * f; s += J[6] * xx[0] + J[7] * xx[1] + J[8] * xx[2] + J[9] * xx[3]; }
+  return s;
+}
+
+__device__ inline void leap_make_constraint(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  const int nfr = (int)m->nfr;
+  // friction-loss rows
+  if (lane < nfr) {
+    const int dof = (int)m->fr_dof[lane];
+    W->edof[lane] = dof; W->esign[lane] = 1; W->efloss[lane] = m->dof_frictionloss[dof];
+  }
+  // joint-limit rows: joint-major, lower side before upper side
+  bool lo_act = false, hi_act = false;
+  double dlo = 0, dhi = 0;
+  if (lane < 16 && m->limited[lane] != 0) {
+    const double q = W->qpos[7 + lane];
+    dlo = q - m->lim_lo[lane]; dhi = m->lim_hi[lane] - q;
+    lo_act = dlo < m->lim_margin; hi_act = dhi < m->lim_margin;
+  }
+  const unsigned mlo = __ballot_sync(FULL, lo_act), mhi = __ballot_sync(FULL, hi_act);
+  const unsigned below = (1u << lane) - 1;
+  const int rbase = nfr + __popc(mlo & below) + __popc(mhi & below);
+  if (lo_act) { W->edof[rbase] = 6 + lane; W->esign[rbase] = 1; W->efloss[rbase] = 0; W->ejar[rbase] = dlo; }
+  if (hi_act) { const int r = rbase + (lo_act ? 1 : 0); W->edof[r] = 6 + lane; W->esign[r] = -1; W->efloss[r] = 0; W->ejar[r] = dhi; }
+  const int nfl = nfr + __popc(mlo) + __popc(mhi);
+  const int ncon = W->ncon;
+  __syncwarp();
+  // contact Jacobians: lane per (contact, frame axis): 6 cube entries + up to 4 finger entries
+  for (int e = lane; e < 3 * ncon; e += 32) {
+    const int c = e / 3, a = e - 3 * c;
+    const double* fr = W->cframe[c] + 3 * a;
+    const double* p = W->cpos[c];
+    const double sgn_cube = W->cswap[c] ? 1.0 : -1.0;  // J = frame^T (Jp(body2) - Jp(body1)); cube is body2 when swapped
+    double* J = W->Jc[e];
+    // cube: translation columns are the identity, rotation columns are (body axis) x (p - xpos)
+    double r[3] = {p[0] - W->xpos[0][0], p[1] - W->xpos[0][1], p[2] - W->xpos[0][2]};
+#pragma unroll
+    for (int k = 0; k < 3; k++) J[k] = sgn_cube * fr[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      double ax[3] = {W->xmat[0][k], W->xmat[0][3 + k], W->xmat[0][6 + k]}, cr[3];
+      lcross3(cr, ax, r);
+      J[3 + k] = sgn_cube * ldot3(fr, cr);
+    }
+    const int f = W->cfinger[c], dep = W->cdepth[c];
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      double v = 0;
+      if (f >= 0 && d <= dep) {
+        const int b = 1 + 4 * f + d;
+        double rr[3] = {p[0] - W->xanchor[b][0], p[1] - W->xanchor[b][1], p[2] - W->xanchor[b][2]}, cr[3];
+        lcross3(cr, W->xaxis[b], rr);
+        v = -sgn_cube * ldot3(fr, cr);
+      }
+      J[6 + d] = v;
+    }
+  }
+  if (lane == 0) { W->nfl = nfl; W->nefc = nfl + 3 * ncon; }
+  __syncwarp();
+  // R, aref per row (mj_makeImpedance); contact rows get their cone adjustment afterwards
+  const int nefc = nfl + 3 * ncon;
+  for (int r = lane; r < nefc; r += 32) {
+    const double *solref, *solimp;
+    double pos, margin = 0, vel, diagA;
+    bool friction_row = false;
+    if (r < nfr) { solref = m->fr_solref; solimp = m->fr_solimp; pos = 0; vel = W->qvel[W->edof[r]]; diagA = m->dof_invw[W->edof[r]]; friction_row = true; }
+    else if (r < nfl) { solref = m->lim_solref; solimp = m->lim_solimp; pos = W->ejar[r]; margin = m->lim_margin; vel = W->esign[r] * W->qvel[W->edof[r]]; diagA = m->dof_invw[W->edof[r]]; }
+    else {
+      const int e = r - nfl, c = e / 3;
+      solref = m->con_solref; solimp = m->con_solimp; pos = W->cdist[c];
+      vel = leap_Jrow_dot(W, e, W->qvel);
+      const int b = W->cbody[c];
+      diagA = m->body_invw[0] + (b >= 0 ? m->body_invw[b] : 0.0);
+      friction_row = (e - 3 * c) > 0;
+      W->efloss[r] = 0;
+    }
+    double ref0 = solref[0], ref1 = solref[1];
+    const double dmax = fmin(fmax(solimp[1], B2_MINIMP), B2_MAXIMP);
+    const double imp = impedance(solimp, pos, margin);
+    double K, B;
+    if (ref0 > 0) {
+      if (ref0 < 2 * m->dt) ref0 = 2 * m->dt;
+      K = 1 / fmax(B2_MINVAL, dmax * dmax * ref0 * ref0 * ref1 * ref1);
+      B = 2 / fmax(B2_MINVAL, dmax * ref0);
+    } else { K = -ref0 / fmax(B2_MINVAL, dmax * dmax); B = -ref1 / fmax(B2_MINVAL, dmax); }
+    if (friction_row) K = 0;
+    W->eR[r] = fmax(B2_MINVAL, (1 - imp) * diagA / imp);
+    W->earef[r] = -B * vel - K * imp * (pos - margin);
+  }
+  __syncwarp();
+  for (int c = lane; c < ncon; c += 32) {
+    const int i = nfl + 3 * c;
+    const double R0 = W->eR[i];
+    const double R1 = R0 / fmax(B2_MINVAL, m->impratio);
+    W->eR[i + 1] = R1;
+    W->cmu[c] = W->cfri[c] * sqrt(R1 / R0);
+    W->eR[i + 2] = R1 * W->cfri[c] * W->cfri[c] / (W->cfri[c] * W->cfri[c]);
+  }
+  __syncwarp();
+  for (int r = lane; r < nefc; r += 32) W->eD[r] = 1 / W->eR[r];
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ Newton solver (mj_solNewton, primal, elliptic cones)
+// one elliptic contact at x[3]: returns cost, writes force[3], state, optional 3x3 cone Hessian
+__device__ __forceinline__ double leap_cone_eval(const LeapWork* W, int c, int row0, const double* x, double* force, int* state, double* Hc) {
+  const double mu = W->cmu[c], f1 = W->cfri[c], f2 = W->cfri[c];
+  const double D0 = W->eD[row0];
+  const double U0 = x[0] * mu, U1 = x[1] * f1, U2 = x[2] * f2;
+  const double N = U0, T = sqrt(U1 * U1 + U2 * U2);
+  double cost = 0;
+  if (N >= mu * T) { force[0] = force[1] = force[2] = 0; *state = LST_SATISFIED; }
+  else if (mu * N + T <= 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { force[k] = -W->eD[row0 + k] * x[k]; cost += 0.5 * W->eD[row0 + k] * x[k] * x[k]; }
+    *state = LST_QUADRATIC;
+  } else {
+    const double Dm = D0 / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+    cost = 0.5 * Dm * NmT * NmT;
+    force[0] = -Dm * NmT * mu;
+    force[1] = T > B2_MINVAL ? -force[0] / T * U1 * f1 : 0;
+    force[2] = T > B2_MINVAL ? -force[0] / T * U2 * f2 : 0;
+    *state = LST_CONE;
+    if (Hc) {
+      const double S[3] = {mu, f1, f2}, U[3] = {U0, U1, U2};
+      double HU[9];
+      const double Ti = T > B2_MINVAL ? 1 / T : 0;
+      HU[0] = Dm;
+#pragma unroll
+      for (int j = 1; j < 3; j++) HU[j] = HU[3 * j] = -Dm * mu * U[j] * Ti;
+#pragma unroll
+      for (int j = 1; j < 3; j++)
+#pragma unroll
+        for (int k = 1; k < 3; k++)
+          HU[3 * j + k] = Dm * mu * mu * U[j] * U[k] * Ti * Ti - Dm * mu * NmT * ((j == k ? Ti : 0) - U[j] * U[k] * Ti * Ti * Ti);
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) Hc[3 * j + k] = S[j] * HU[3 * j + k] * S[k];
+    }
+  }
+  return cost;
+}
+
+// friction-loss / limit row at x: returns cost, writes force and state
+__device__ __forceinline__ double leap_row_eval(const LeapWork* W, int r, int nfr, double x, double* force, int* state) {
+  const double D = W->eD[r];
+  if (r < nfr) {
+    const double f = W->efloss[r], R = W->eR[r];
+    if (x <= -R * f) { *force = f; *state = LST_LINEARNEG; return -0.5 * R * f * f - f * x; }
+    if (x >= R * f) { *force = -f; *state = LST_LINEARPOS; return -0.5 * R * f * f + f * x; }
+    *force = -D * x; *state = LST_QUADRATIC; return 0.5 * D * x * x;
+  }
+  if (x < 0) { *force = -D * x; *state = LST_QUADRATIC; return 0.5 * D * x * x; }
+  *force = 0; *state = LST_SATISFIED; return 0;
+}
+
+__device__ __forceinline__ double lwsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// jar = J qacc - aref for every row; Ma = M qacc
+__device__ inline void leap_set_point(const LeapModel* __restrict__ m, LeapWork* W, const double* qacc, int lane) {
+  if (lane < LEAP_NV) W->Ma[lane] = leap_mulM_row(m, W, qacc, lane);
+  const int nfl = W->nfl, nefc = W->nefc;
+  for (int r = lane; r < nefc; r += 32) {
+    const double v = r < nfl ? W->esign[r] * qacc[W->edof[r]] : leap_Jrow_dot(W, r - nfl, qacc);
+    W->ejar[r] = v - W->earef[r];
+  }
+  __syncwarp();
+}
+
+// cost / forces / states at the current jar (+ gradient and, optionally, the Newton Hessian)
+__device__ inline void leap_constraint_update(const LeapModel* __restrict__ m, LeapWork* W, const double* qacc, bool want_h, int lane) {
+  const int nfr = (int)m->nfr, nfl = W->nfl, ncon = W->ncon;
+  double cost = 0;
+  for (int r = lane; r < nfl; r += 32) cost += leap_row_eval(W, r, nfr, W->ejar[r], &W->eforce[r], &W->estate[r]);
+  for (int c = lane; c < ncon; c += 32) {
+    const int r0 = nfl + 3 * c;
+    int st;
+    cost += leap_cone_eval(W, c, r0, W->ejar + r0, W->eforce + r0, &st, want_h ? W->cHc[c] : nullptr);
+    W->estate[r0] = W->estate[r0 + 1] = W->estate[r0 + 2] = st;
+  }
+  cost = lwsum(cost);
+  __syncwarp();
+  // qfrc_constraint = J^T force, gradient, Gauss term — lane per dof
+  double g = 0;
+  if (lane < LEAP_NV) {
+    const int i = lane;
+    double f = 0;
+    for (int r = 0; r < nfl; r++) if (W->edof[r] == i) f += W->esign[r] * W->eforce[r];
+    const int fi = i >= 6 ? (i - 6) >> 2 : -1, ki = i < 6 ? i : 6 + ((i - 6) & 3);
+    for (int c = 0; c < ncon; c++) {
+      if (i >= 6 && W->cfinger[c] != fi) continue;
+#pragma unroll
+      for (int a = 0; a < 3; a++) f += W->Jc[3 * c + a][ki] * W->eforce[nfl + 3 * c + a];
+    }
+    W->qfrc_constraint[i] = f;
+    W->grad[i] = W->Ma[i] - W->qfrc_smooth[i] - f;
+    g = (W->Ma[i] - W->qfrc_smooth[i]) * (qacc[i] - W->qacc_smooth[i]);
+  }
+  g = lwsum(g);
+  if (lane == 0) { W->gauss = 0.5 * g; W->cost = 0.5 * g + cost; }
+  if (want_h) {
+    // H = M + sum_rows D J^T J (+ cone blocks): lane per lower-triangle entry
+    for (int e = lane; e < LEAP_NV * (LEAP_NV + 1) / 2; e += 32) {
+      int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((i + 1) * (i + 2) / 2 <= e) i++;
+      while (i * (i + 1) / 2 > e) i--;
+      const int j = e - i * (i + 1) / 2;  // j <= i
+      double h = 0;
+      // mass matrix entry
+      if (i < 3) h = (i == j) ? W->Mc[i] : 0.0;
+      else if (i < 6) h = j >= 3 ? m->cube_Irot[3 * (i - 3) + (j - 3)] : 0.0;
+      else { const int f = (i - 6) >> 2; if (j >= 6 + 4 * f) h = W->Mf[f][(i - 6) & 3][(j - 6) & 3]; }
+      if (i == j)
+        for (int r = 0; r < nfl; r++) if (W->edof[r] == i && W->estate[r] == LST_QUADRATIC) h += W->eD[r];
+      const int fi = i >= 6 ? (i - 6) >> 2 : -1, fj = j >= 6 ? (j - 6) >> 2 : -1;
+      const int ki = i < 6 ? i : 6 + ((i - 6) & 3), kj = j < 6 ? j : 6 + ((j - 6) & 3);
+      if (fi < 0 || fj < 0 || fi == fj) {
+        for (int c = 0; c < ncon; c++) {
+          const int fc = W->cfinger[c];
+          if ((fi >= 0 && fi != fc) || (fj >= 0 && fj != fc)) continue;
+          const int r0 = 3 * c, st = W->estate[nfl + r0];
+          if (st == LST_QUADRATIC) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) h += W->eD[nfl + r0 + a] * W->Jc[r0 + a][ki] * W->Jc[r0 + a][kj];
+          } else if (st == LST_CONE) {
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+              for (int b = 0; b < 3; b++) h += W->cHc[c][3 * a + b] * W->Jc[r0 + a][ki] * W->Jc[r0 + b][kj];
+          }
+        }
+      }
+      W->LH(i, j) = h;
+    }
+  }
+  __syncwarp();
+}
+
+// in-place dense Cholesky of the lower triangle of H (warp cooperative), then x <- H^-1 x
+__device__ inline void leap_chol_solve_H(LeapWork* W, double* x, int lane) {
+  constexpr int n = LEAP_NV;
+  for (int k = 0; k < n; k++) {
+    double d = W->LH(k, k);
+    if (d < B2_MINVAL) d = B2_MINVAL;
+    const double lkk = sqrt(d);
+    __syncwarp();
+    if (lane == 0) W->LH(k, k) = lkk;
+    for (int i = k + 1 + lane; i < n; i += 32) W->LH(i, k) = W->LH(i, k) / lkk;
+    __syncwarp();
+    // trailing update of the lower triangle
+    const int rem = n - k - 1;
+    for (int e = lane; e < rem * (rem + 1) / 2; e += 32) {
+      int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((a + 1) * (a + 2) / 2 <= e) a++;
+      while (a * (a + 1) / 2 > e) a--;
+      const int b = e - a * (a + 1) / 2;
+      const int i = k + 1 + a, j = k + 1 + b;
+      W->LH(i, j) -= W->LH(i, k) * W->LH(j, k);
+    }
+    __syncwarp();
+  }
+  // forward substitution L y = x
+  for (int k = 0; k < n; k++) {
+    const double xk = x[k] / W->LH(k, k);
+    __syncwarp();
+    if (lane == 0) x[k] = xk;
+    for (int i = k + 1 + lane; i < n; i += 32) x[i] -= W->LH(i, k) * xk;
+    __syncwarp();
+  }
+  // back substitution L^T z = y
+  for (int k = n - 1; k >= 0; k--) {
+    const double xk = x[k] / W->LH(k, k);
+    __syncwarp();
+    if (lane == 0) x[k] = xk;
+    for (int i = lane; i < k; i += 32) x[i] -= W->LH(k, i) * xk;
+    __syncwarp();
+  }
+}
+
+// 1-D derivatives of the cost along the search direction at step alpha (all lanes get the result)
+__device__ inline void leap_ls_eval(const LeapModel* __restrict__ m, const LeapWork* W, double alpha, double g1, double g2, double* d1, double* d2, int lane) {
+  const int nfr = (int)m->nfr, nfl = W->nfl, ncon = W->ncon;
+  double p1 = 0, p2 = 0;
+  for (int r = lane; r < nfl; r += 32) {
+    double f; int st;
+    leap_row_eval(W, r, nfr, W->ejar[r] + alpha * W->ejv[r], &f, &st);
+    p1 -= f * W->ejv[r];
+    if (st == LST_QUADRATIC) p2 += W->eD[r] * W->ejv[r] * W->ejv[r];
+  }
+  for (int c = lane; c < ncon; c += 32) {
+    const int r0 = nfl + 3 * c;
+    double x[3], f[3], Hc[9]; int st;
+#pragma unroll
+    for (int k = 0; k < 3; k++) x[k] = W->ejar[r0 + k] + alpha * W->ejv[r0 + k];
+    leap_cone_eval(W, c, r0, x, f, &st, Hc);
+#pragma unroll
+    for (int k = 0; k < 3; k++) p1 -= f[k] * W->ejv[r0 + k];
+    if (st == LST_CONE) {
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) p2 += W->ejv[r0 + a] * Hc[3 * a + b] * W->ejv[r0 + b];
+    } else if (st == LST_QUADRATIC) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) p2 += W->eD[r0 + k] * W->ejv[r0 + k] * W->ejv[r0 + k];
+    }
+  }
+  *d1 = g1 + alpha * g2 + lwsum(p1);
+  *d2 = g2 + lwsum(p2);
+}
+
+__device__ inline double leap_line_search(const LeapModel* __restrict__ m, const LeapWork* W, int lane) {
+  double g1 = 0, g2 = 0, sn = 0;
+  if (lane < LEAP_NV) { g1 = W->search[lane] * (W->Ma[lane] - W->qfrc_smooth[lane]); g2 = W->search[lane] * W->Mv[lane]; sn = W->search[lane] * W->search[lane]; }
+  g1 = lwsum(g1); g2 = lwsum(g2);
+  const double snorm = sqrt(lwsum(sn));
+  if (snorm < B2_MINVAL) return 0;
+  const double gtol = m->tolerance * m->ls_tolerance * snorm * m->meaninertia * LEAP_NV;
+  double d1, d2, lo = 0, hi = -1, dlo, dhi = 0, alpha;
+  leap_ls_eval(m, W, 0, g1, g2, &d1, &d2, lane);
+  if (d1 >= 0 || d2 <= 0) return 0;
+  dlo = d1;
+  alpha = -d1 / d2;
+  double prev_step = 1e300;
+  const int iters = (int)m->ls_iterations;
+  for (int it = 0; it < iters; it++) {
+    leap_ls_eval(m, W, alpha, g1, g2, &d1, &d2, lane);
+    if (fabs(d1) < gtol) return alpha;
+    if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
+    double next = d2 > 0 ? alpha - d1 / d2 : -1;
+    if (hi < 0) { if (!(next > lo)) next = 2 * alpha + B2_MINVAL; }
+    else if (!(next > lo && next < hi && fabs(next - alpha) < 0.5 * prev_step)) next = 0.5 * (lo + hi);
+    if (next == alpha) return alpha;
+    prev_step = fabs(next - alpha);
+    alpha = next;
+  }
+  (void)dlo; (void)dhi;
+  return lo > 0 ? lo : alpha;
+}
+
+__device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  const int nefc = W->nefc;
+  if (nefc == 0) {
+    if (lane < LEAP_NV) { W->qacc[lane] = W->qacc_smooth[lane]; W->qfrc_constraint[lane] = 0; }
+    __syncwarp();
+    return;
+  }
+  // warm start: keep qacc_warmstart unless qacc_smooth has lower cost
+  leap_set_point(m, W, W->warm, lane);
+  leap_constraint_update(m, W, W->warm, false, lane);
+  const double cw = W->cost;
+  __syncwarp();
+  leap_set_point(m, W, W->qacc_smooth, lane);
+  leap_constraint_update(m, W, W->qacc_smooth, false, lane);
+  const double cs = W->cost;
+  __syncwarp();
+  if (lane < LEAP_NV) W->qacc[lane] = cw > cs ? W->qacc_smooth[lane] : W->warm[lane];
+  __syncwarp();
+  leap_set_point(m, W, W->qacc, lane);
+  leap_constraint_update(m, W, W->qacc, true, lane);
+  const double scale = 1.0 / (m->meaninertia * LEAP_NV);
+  const int iters = (int)m->iterations, nfl = W->nfl;
+  for (int it = 0; it < iters; it++) {
+    double gn = lane < LEAP_NV ? W->grad[lane] * W->grad[lane] : 0.0;
+    gn = lwsum(gn);
+    if (scale * sqrt(gn) < m->tolerance) break;
+    if (lane < LEAP_NV) W->search[lane] = -W->grad[lane];
+    __syncwarp();
+    leap_chol_solve_H(W, W->search, lane);
+    if (lane < LEAP_NV) W->Mv[lane] = leap_mulM_row(m, W, W->search, lane);
+    for (int r = lane; r < nefc; r += 32) W->ejv[r] = r < nfl ? W->esign[r] * W->search[W->edof[r]] : leap_Jrow_dot(W, r - nfl, W->search);
+    __syncwarp();
+    const double alpha = leap_line_search(m, W, lane);
+    if (alpha == 0) break;
+    const double oldcost = W->cost;
+    __syncwarp();
+    if (lane < LEAP_NV) { W->qacc[lane] += alpha * W->search[lane]; W->Ma[lane] += alpha * W->Mv[lane]; }
+    for (int r = lane; r < nefc; r += 32) W->ejar[r] += alpha * W->ejv[r];
+    __syncwarp();
+    leap_constraint_update(m, W, W->qacc, true, lane);
+    const double newcost = W->cost;
+    __syncwarp();
+    if (scale * (oldcost - newcost) < m->tolerance) break;
+  }
+}
+
+// ------------------------------------------------------------------ one mj_step
+__device__ inline void leap_step(const LeapModel* __restrict__ m, LeapWork* W, int lane, double* sens /* global, may be null */) {
+  leap_kinematics(m, W, lane);
+  leap_mass_and_bias(m, W, lane);
+  leap_collision(m, W, lane);
+  leap_make_constraint(m, W, lane);
+  if (sens) {  // position-stage sensors: 16 jointpos then 5 framepos sites (pre-step state)
+    if (lane < 16) sens[lane] = W->qpos[7 + lane];
+    if (lane < 5) {
+      const int b = (int)m->site_body[lane];
+      double t[3];
+      lmat_vec(t, W->xmat[b], m->site_pos[lane]);
+      for (int k = 0; k < 3; k++) sens[16 + 3 * lane + k] = W->xpos[b][k] + t[k];
+    }
+  }
+  // passive + actuation -> qfrc_smooth; qacc_smooth = M^-1 qfrc_smooth
+  if (lane < LEAP_NV) {
+    const int i = lane;
+    double f = -m->dof_damping[i] * W->qvel[i] - W->qfrc_bias[i];
+    if (i >= 6) {
+      const int a = i - 6;
+      double u = W->ctrl[a];
+      if (m->ctrllimited[a] != 0) u = fmin(fmax(u, m->ctrl_lo[a]), m->ctrl_hi[a]);
+      f += m->kp[a] * u - m->kp[a] * W->qpos[7 + a] - m->kv[a] * W->qvel[i];
+    }
+    W->qfrc_smooth[i] = f; W->qacc_smooth[i] = f;
+  }
+  __syncwarp();
+  leap_block_solve(m, W, nullptr, W->qacc_smooth, lane);
+  leap_fwd_constraint(m, W, lane);
+  __syncwarp();
+  // implicitfast: (M + h (damping + kv)) qacc = qfrc_smooth + qfrc_constraint, then semi-implicit advance
+  const double h = m->dt;
+  if (lane < LEAP_NV) {
+    W->tmp[lane] = h * (m->dof_damping[lane] + (lane >= 6 ? m->kv[lane - 6] : 0.0));
+    W->Mv[lane] = W->qfrc_smooth[lane] + W->qfrc_constraint[lane];
+  }
+  __syncwarp();
+  leap_block_solve(m, W, W->tmp, W->Mv, lane);
+  if (lane < LEAP_NV) { W->qvel[lane] += h * W->Mv[lane]; W->warm[lane] = W->qacc[lane]; }
+  __syncwarp();
+  if (lane < 3) W->qpos[lane] += h * W->qvel[lane];
+  else if (lane == 3) {
+    double w[3] = {W->qvel[3], W->qvel[4], W->qvel[5]};
+    const double ang = h * lnormalize3(w);
+    double sn, cs, dq[4], nq[4];
+    sincos(0.5 * ang, &sn, &cs);
+    dq[0] = cs; dq[1] = sn * w[0]; dq[2] = sn * w[1]; dq[3] = sn * w[2];
+    lquat_mul(nq, W->qpos + 3, dq);
+    lquat_normalize(nq);
+    for (int k = 0; k < 4; k++) W->qpos[3 + k] = nq[k];
+  } else if (lane >= 6 && lane < LEAP_NV) W->qpos[lane + 1] += h * W->qvel[lane];
+  __syncwarp();
+}
+
+// per-step cost (leap_cube.py:76-86): 0.5 w_pos |p - goal|^2 + 0.5 w_rot |log(q* (x) q_goal)|^2 ; params [w_pos, w_rot, goal_quat4, goal_pos3]
+__device__ inline double leap_cost(const double* p, const double* qpos) {
+  const double dx = qpos[0] - p[6], dy = qpos[1] - p[7], dz = qpos[2] - p[8];
+  const double u0 = qpos[3], u1 = -qpos[4], u2 = -qpos[5], u3 = -qpos[6];
+  const double v0 = p[2], v1 = p[3], v2 = p[4], v3 = p[5];
+  const double w = u0 * v0 - u1 * v1 - u2 * v2 - u3 * v3;
+  const double x = u0 * v1 + u1 * v0 + u2 * v3 - u3 * v2;
+  const double y = u0 * v2 - u1 * v3 + u2 * v0 + u3 * v1;
+  const double z = u0 * v3 + u1 * v2 - u2 * v1 + u3 * v0;
+  const double s = sqrt(x * x + y * y + z * z);
+  double ax = 1, ay = 0, az = 0;
+  if (!(s < 1e-6)) { ax = x / s; ay = y / s; az = z / s; }
+  double speed = 2.0 * atan2(s, w);
+  if (speed > 3.14159265358979323846) speed -= 2 * 3.14159265358979323846;
+  const double rx = ax * speed, ry = ay * speed, rz = az * speed;
+  return p[0] * 0.5 * (dx * dx + dy * dy + dz * dz) + p[1] * 0.5 * (rx * rx + ry * ry + rz * rz);
+}
+
+// ------------------------------------------------------------------ kernels
+// COST: in = knots (N,K,16), basis (H,K) -> reward (N) [+ cost (N,H) f32];  !COST: in = controls (N,H,16) -> states, sensors
+template <bool COST>
+__global__ void __launch_bounds__(32) leap_rollout_kernel(const LeapModel* __restrict__ m, const double* __restrict__ x0, int x0_batched,
+                                                          const double* __restrict__ in, int N, int H, int K, const double* __restrict__ basis,
+                                                          const double* __restrict__ cost_params, double* __restrict__ states,
+                                                          double* __restrict__ sensors, float* __restrict__ cost_NH, double* __restrict__ reward_N) {
+  extern __shared__ __align__(16) unsigned char lsm[];
+  LeapWork* W = reinterpret_cast<LeapWork*>(lsm);
+  const int lane = threadIdx.x, n = blockIdx.x;
+  if (n >= N) return;
+  const double* xs = x0 + (x0_batched ? (size_t)n * LEAP_NX : 0);
+  if (lane < LEAP_NQ) W->qpos[lane] = xs[lane];
+  if (lane < LEAP_NV) { W->qvel[lane] = xs[LEAP_NQ + lane]; W->warm[lane] = 0; }
+  __syncwarp();
+  if constexpr (COST) {
+    // stage this rollout's knots (K*16 doubles) and the basis behind the work area with TMA bulk copies
+    uint64_t* bar = reinterpret_cast<uint64_t*>(lsm + ((sizeof(LeapWork) + 15) & ~(size_t)15));
+    double* sK = reinterpret_cast<double*>(bar + 2);
+    double* sB = sK + K * LEAP_NU;
+    const unsigned bytesK = (unsigned)(K * LEAP_NU * sizeof(double)), bytesB = (unsigned)(H * K * sizeof(double));
+    const double* gK = in + (size_t)n * K * LEAP_NU;
+    const bool tma_ok = (bytesB % 16 == 0) && ((reinterpret_cast<uintptr_t>(basis) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gK) & 15) == 0);
+    if (tma_ok) {
+      if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+      __syncwarp();
+      if (lane == 0) { mbar_expect_tx(bar, bytesK + bytesB); tma_bulk_g2s(sK, gK, bytesK, bar); tma_bulk_g2s(sB, basis, bytesB, bar); }
+      mbar_wait(bar, 0);
+    } else {
+      for (int i = lane; i < K * LEAP_NU; i += 32) sK[i] = gK[i];
+      for (int i = lane; i < H * K; i += 32) sB[i] = basis[i];
+      __syncwarp();
+    }
+    double total = 0;
+    for (int t = 0; t < H; t++) {
+      if (lane < LEAP_NU) {
+        double u = 0;
+        for (int k = 0; k < K; k++) u += sB[t * K + k] * sK[k * LEAP_NU + lane];
+        W->ctrl[lane] = u;
+      }
+      __syncwarp();
+      leap_step(m, W, lane, nullptr);
+      if (lane == 0) {
+        double cp[LEAP_NCOST];
+#pragma unroll
+        for (int i = 0; i < LEAP_NCOST; i++) cp[i] = cost_params[i];
+        const double ct = leap_cost(cp, W->qpos);
+        total += ct;
+        if (cost_NH) cost_NH[(size_t)n * H + t] = (float)ct;
+      }
+    }
+    if (lane == 0) reward_N[n] = -(total / H);
+  } else {
+    for (int t = 0; t < H; t++) {
+      if (lane < LEAP_NU) W->ctrl[lane] = in[((size_t)n * H + t) * LEAP_NU + lane];
+      __syncwarp();
+      leap_step(m, W, lane, sensors ? sensors + ((size_t)n * H + t) * LEAP_NS : nullptr);
+      double* so = states + ((size_t)n * H + t) * LEAP_NX;
+      if (lane < LEAP_NQ) so[lane] = W->qpos[lane];
+      if (lane < LEAP_NV) so[LEAP_NQ + lane] = W->qvel[lane];
+    }
+  }
+}
+
+__global__ void leap_reward_kernel(const double* __restrict__ states, int N, int H, const double* __restrict__ cost_params, double* __restrict__ reward_N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double cp[LEAP_NCOST];
+#pragma unroll
+  for (int i = 0; i < LEAP_NCOST; i++) cp[i] = cost_params[i];
+  double total = 0;
+  for (int t = 0; t < H; t++) total += leap_cost(cp, states + ((size_t)n * H + t) * LEAP_NX);
+  reward_N[n] = -(total / H);
+}
+
+// ------------------------------------------------------------------ host side
+inline int leap_create(LeapModel** out, const double* consts, size_t n, std::string* err) {
+  if (n != sizeof(LeapModel) / sizeof(double)) { *err = "wrong number of task constants"; return 1; }
+  LeapModel* d = nullptr;
+  if (cudaMalloc(&d, sizeof(LeapModel)) != cudaSuccess) { *err = "cudaMalloc failed"; return 1; }
+  if (cudaMemcpy(d, consts, sizeof(LeapModel), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); *err = "cudaMemcpy failed"; return 1; }
+  *out = d;
+  return 0;
+}
+inline void leap_destroy(LeapModel* m) { cudaFree(m); }
+inline int leap_num_partials(int N) { return N; }
+
+inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, int batched, const double* d_in, int N, int H, int K,
+                       const double* d_basis, const double* d_params, double* d_states, double* d_sensors, float* d_cost, double* d_reward,
+                       const PlanEpilogue& ep, cudaStream_t st, std::string* err) {
+  (void)ep;  // the leap path runs the optimizer update as separate reduction kernels (b200mpc.cu)
+  size_t smem = ((sizeof(LeapWork) + 15) & ~(size_t)15) + 16 + (cost_mode ? ((size_t)K * LEAP_NU + (size_t)H * K) * sizeof(double) : 0);
+  if (smem > 227 * 1024) { *err = "horizon/knots too large for the shared-memory tile"; return 1; }
+  cudaError_t e;
+  if (cost_mode) {
+    e = cudaFuncSetAttribute(leap_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) leap_rollout_kernel<true><<<N, 32, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward);
+  } else {
+    e = cudaFuncSetAttribute(leap_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) leap_rollout_kernel<false><<<N, 32, smem, st>>>(m, d_x0, batched, d_in, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("leap launch: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+inline int leap_reward_launch(const LeapModel* m, const double* d_states, int N, int H, const double* d_params, double* d_reward, cudaStream_t st,
+                              std::string* err) {
+  (void)m;
+  leap_reward_kernel<<<(N + 127) / 128, 128, 0, st>>>(d_states, N, H, d_params, d_reward);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("leap reward launch: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+}  // namespace b2

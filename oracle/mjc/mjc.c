@@ -7,6 +7,7 @@
 #include "mjc.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -17,6 +18,9 @@
 #define MINIMP 0.0001
 #define MAXIMP 0.9999
 #define MINMU 1e-5
+
+static int g_debug = 0;
+void mjc_set_debug(int v) { g_debug = v; }
 
 /* constraint row types, in MuJoCo's row order */
 enum { CT_FRICTION_DOF = 1, CT_LIMIT_JOINT = 3, CT_CONTACT_PYRAMIDAL = 6, CT_CONTACT_ELLIPTIC = 7 };
@@ -63,6 +67,7 @@ typedef struct {
   double qacc_smooth[MJC_MAXNV], qfrc_constraint[MJC_MAXNV], actuator_force[MJC_MAXNU];
   double sensordata[MJC_MAXSENSOR * 3];
   int ncon, nefc, solver_iter;
+  double solver_grad, solver_cost;
   mjcContact contact[MJC_MAXCON];
   double efc_J[MJC_MAXEFC][MJC_MAXNV];
   double efc_pos[MJC_MAXEFC], efc_margin[MJC_MAXEFC], efc_frictionloss[MJC_MAXEFC], efc_diagApprox[MJC_MAXEFC];
@@ -954,25 +959,29 @@ static double line_search(const mjcModel* m, const mjcData* d, const Solver* s) 
   double gtol = m->tolerance * m->ls_tolerance * snorm * scale;
   double c0, d1, d2, lo = 0, hi = -1, dlo, dhi = 0, alpha = 0, c;
   ls_eval(m, d, s, 0, g1, g2, &c0, &d1, &d2);
+  if (g_debug) fprintf(stderr, "    ls: d1(0) %.6e d2(0) %.6e gtol %.3e\n", d1, d2, gtol);
   if (d1 >= 0 || d2 <= 0) return 0;
   dlo = d1;
   alpha = -d1 / d2;
+  double prev_step = 1e300;
   for (int it = 0; it < m->ls_iterations; it++) {
     ls_eval(m, d, s, alpha, g1, g2, &c, &d1, &d2);
+    if (g_debug > 1) fprintf(stderr, "      ls it %d alpha %.9e cost-c0 %.6e d1 %.6e d2 %.6e lo %.6e hi %.6e\n", it, alpha, c - c0, d1, d2, lo, hi);
     if (fabs(d1) < gtol) return alpha;
     if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
     double next = d2 > 0 ? alpha - d1 / d2 : -1;
     if (hi < 0) { /* no upper bracket yet: accept Newton if it moves right, else expand */
       if (!(next > lo)) next = 2 * alpha + MINVAL;
-    } else if (!(next > lo && next < hi)) {
-      /* Newton left the bracket: secant/bisection fallback */
-      next = lo + (hi - lo) * (-dlo) / (dhi - dlo);
-      if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);
+    } else if (!(next > lo && next < hi && fabs(next - alpha) < 0.5 * prev_step)) {
+      /* Newton left the bracket or is not contracting (kinks of the piecewise-quadratic cost): bisect */
+      next = 0.5 * (lo + hi);
     }
     if (next == alpha) return alpha;
+    prev_step = fabs(next - alpha);
     alpha = next;
   }
-  return alpha;
+  (void)dlo; (void)dhi;
+  return lo > 0 ? lo : alpha; /* not converged: the last point with negative slope still lowers the convex cost */
 }
 
 static void mul_M(const mjcData* d, int nv, const double* x, double* y) {
@@ -1020,6 +1029,8 @@ static void fwd_constraint(const mjcModel* m, mjcData* d, Solver* s) {
   for (int it = 0; it < m->iterations; it++) {
     double gn = 0;
     for (int i = 0; i < nv; i++) gn += s->grad[i] * s->grad[i];
+    d->solver_grad = scale * sqrt(gn);
+    d->solver_cost = s->cost;
     if (scale * sqrt(gn) < m->tolerance) break;
     cholesky(s->Lh, s->H, nv);
     for (int i = 0; i < nv; i++) s->search[i] = -s->grad[i];
@@ -1032,11 +1043,16 @@ static void fwd_constraint(const mjcModel* m, mjcData* d, Solver* s) {
     }
     double alpha = line_search(m, d, s);
     d->solver_iter = it + 1;
+    if (g_debug) {
+      double sg = 0; for (int i = 0; i < nv; i++) sg += s->search[i] * s->grad[i];
+      fprintf(stderr, "  newton it %d cost %.12e |g| %.3e search.grad %.3e alpha %.6e\n", it, s->cost, scale * sqrt(gn), sg, alpha);
+    }
     if (alpha == 0) break;
     double oldcost = s->cost;
     for (int i = 0; i < nv; i++) { d->qacc[i] += alpha * s->search[i]; s->Ma[i] += alpha * s->Mv[i]; }
     for (int r = 0; r < s->nefc; r++) s->jar[r] += alpha * s->jv[r];
     constraint_update(m, d, s, 1);
+    if (g_debug) fprintf(stderr, "      -> new cost %.12e improvement %.3e\n", s->cost, scale * (oldcost - s->cost));
     if (scale * (oldcost - s->cost) < m->tolerance) break;
   }
 }
@@ -1124,6 +1140,9 @@ static void integrate(const mjcModel* m, mjcData* d) {
   memcpy(d->qacc_warmstart, d->qacc, sizeof(double) * nv);
 }
 
+static double* g_stats = 0; /* debug hook: (N,H,4) = iterations, nefc, last checked scaled |grad|, cost */
+void mjc_set_stats_buffer(double* p) { g_stats = p; }
+
 int mjc_rollout(const mjcModel* m, const double* x0, int x0_batched, const double* controls, int N, int H,
                 double* states, double* sensors_out, int nthread) {
   int nq = m->nq, nv = m->nv, nu = m->nu, ns = m->nsensordata, nx = nq + nv;
@@ -1150,6 +1169,12 @@ int mjc_rollout(const mjcModel* m, const double* x0, int x0_batched, const doubl
         for (int t = 0; t < H; t++) {
           memcpy(d->ctrl, controls + ((size_t)n * H + t) * nu, sizeof(double) * nu);
           forward(m, d, s);
+          if (g_stats) {
+            double* st = g_stats + ((size_t)n * H + t) * 4;
+            double gn = 0;
+            for (int i = 0; i < nv; i++) gn += s->grad[i] * s->grad[i];
+            st[0] = d->solver_iter; st[1] = d->nefc; st[2] = d->nefc ? sqrt(gn) / (m->meaninertia * nv) : 0; st[3] = d->ncon;
+          }
           integrate(m, d);
           double* so = states + ((size_t)n * H + t) * nx;
           memcpy(so, d->qpos, sizeof(double) * nq);

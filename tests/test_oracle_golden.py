@@ -44,14 +44,20 @@ def test_optimizers_oracle_matches_reference(golden, temp_np_seed):
                 np.testing.assert_array_equal(nom, g[f"c{ci}_nominal_out{it}"])
 
 
-@pytest.mark.parametrize("tag", ["cartpole_ps", "cartpole_mppi", "cylinder_push_cem"])
+@pytest.mark.parametrize("tag", ["cartpole_ps", "cartpole_mppi", "cylinder_push_cem", "leap_cube_mppi"])
 def test_plan_golden_is_self_consistent(golden, tag):
     """The stored reference plan steps: oracle physics reproduces the stored states; oracle.plan reproduces
     controls -> rewards -> nominal -> traces from the stored candidates."""
     g = golden("plan_" + tag)
     task, opt, N, horizon, seed, order, max_traces = g["meta"]
     table = load_table(task)
-    om = OracleModel(table)
+    if task == "leap_cube":
+        from judo_b200.tasks.leap_cube import reduced_collision_model
+
+        geoms, pairs = reduced_collision_model(table)
+        om = OracleModel(table, pairs=pairs, geoms=geoms)
+    else:
+        om = OracleModel(table)
     trace_adrs = [s["adr"] for s in table["sensors"] if s["type"] == "framepos" and "trace" in s["name"]]
     dt = table["opt"]["timestep"]
     for p in range(3):
@@ -63,7 +69,12 @@ def test_plan_golden_is_self_consistent(golden, tag):
         states, sensors = om.rollout(g[f"p{p}_x0"], ctrl)
         np.testing.assert_allclose(states, g[f"p{p}_states"], rtol=0, atol=1e-12)
         np.testing.assert_allclose(sensors, g[f"p{p}_sensors"], rtol=0, atol=1e-12)
-        rew = op.cartpole_reward(states, ctrl) if task == "cartpole" else op.cylinder_push_reward(states, ctrl)
+        if task == "cartpole":
+            rew = op.cartpole_reward(states, ctrl)
+        elif task == "cylinder_push":
+            rew = op.cylinder_push_reward(states, ctrl)
+        else:
+            rew = op.leap_cube_reward(states, g["goal_quat"])
         np.testing.assert_allclose(rew, g[f"p{p}_rewards"], rtol=1e-13)
         tr = op.update_traces(g[f"p{p}_sensors"], g[f"p{p}_rewards"], trace_adrs, int(max_traces))
         np.testing.assert_array_equal(tr, g[f"p{p}_traces"])
