@@ -106,7 +106,7 @@ extern "C" void b200mpc_destroy(b200mpc_handle* h) {
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
 #ifdef B200MPC_WITH_LEAP
-  if (h->leap) leap_destroy(h->leap);
+  if (h->leap) { if (getenv("B200MPC_LEAP_PROF")) leap_prof_dump(); leap_destroy(h->leap); }
 #endif
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

@@ -10,6 +10,10 @@
 #pragma once
 #include "epilogue.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include <string>
 
 namespace b2 {
@@ -20,7 +24,6 @@ constexpr int LMAXG = 80;      // hand collision geoms
 constexpr int LMAXCON = 24;    // contacts kept per step (3 rows each)
 constexpr int LMAXEFC = 32 + 3 * LMAXCON;
 constexpr unsigned FULL = 0xffffffffu;
-#define LH(i, j) Hp[(i) * ((i) + 1) / 2 + (j)]  // j <= i
 
 // All-double POD; field order == judo_b200/tasks/leap_cube.py:leap_consts.
 struct LeapModel {
@@ -44,7 +47,8 @@ struct LeapWork {
   double xpos[LB][3], xquat[LB][4], xmat[LB][9], xipos[LB][3], Iw[LB][6], xanchor[LB][3], xaxis[LB][3];
   double Mc[6];          // cube block: 3 translational masses are Mc[0..2]; rotational block is model.cube_Irot
   double Mf[4][4][4];    // finger blocks
-  double Hp[LEAP_NV * (LEAP_NV + 1) / 2];  // packed lower triangle of the Newton Hessian / its Cholesky factor
+  // Newton Hessian in arrow form (dof order: 6 cube dofs, then 4 fingers x 4): cube block, finger blocks, coupling
+  double Hcc[6][6], Hcf[4][4][6], Hff[4][4][4], xc[6], yf[4][4];
   double qfrc_bias[LEAP_NV], qfrc_smooth[LEAP_NV], qacc_smooth[LEAP_NV], qacc[LEAP_NV], qfrc_constraint[LEAP_NV];
   double Ma[LEAP_NV], grad[LEAP_NV], search[LEAP_NV], Mv[LEAP_NV], tmp[LEAP_NV];
   double cdist[LMAXCON], cpos[LMAXCON][3], cframe[LMAXCON][9], cmu[LMAXCON], cfri[LMAXCON], cHc[LMAXCON][9];
@@ -56,6 +60,12 @@ struct LeapWork {
   int ncon, nefc, nfl, ncand, solver_iter;
   double cost, gauss;
 };
+
+// optional phase timers (clock64 deltas accumulated by lane 0): kin, mass+bias, collision, constraints, smooth, solver, integrate,
+// and inside the solver: update, direction (H + Cholesky + solve), line search, #newton iterations
+__device__ unsigned long long g_leap_prof[16];
+#define LPROF_T() (prof ? clock64() : 0)
+#define LPROF_ADD(slot, t0) do { if (prof && lane == 0) atomicAdd(&g_leap_prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
 
 enum { LST_SATISFIED = 0, LST_QUADRATIC = 1, LST_LINEARNEG = 2, LST_LINEARPOS = 3, LST_CONE = 4 };
 
@@ -342,7 +352,7 @@ __device__ inline void leap_block_solve(const LeapModel* __restrict__ m, LeapWor
 // ------------------------------------------------------------------ collision (reduced geometry; same routines as the oracle)
 struct LRaw { double dist, pos[3], normal[3]; };
 
-__device__ inline int l_clip_poly(double (*poly)[2], int n, int axis, double sign, double lim) {
+__device__ __noinline__ int l_clip_poly(double (*poly)[2], int n, int axis, double sign, double lim) {
   double out[16][2];
   int no = 0;
   for (int i = 0; i < n; i++) {
@@ -360,7 +370,7 @@ __device__ inline int l_clip_poly(double (*poly)[2], int n, int axis, double sig
   return no;
 }
 
-__device__ inline int l_sphere_box(const double* ps, double rs, const double* pb, const double* mb, const double* sb, double margin, LRaw* out) {
+__device__ __noinline__ int l_sphere_box(const double* ps, double rs, const double* pb, const double* mb, const double* sb, double margin, LRaw* out) {
   double rel[3], loc[3], cl[3];
   for (int k = 0; k < 3; k++) rel[k] = ps[k] - pb[k];
   lmatT_vec(loc, mb, rel);
@@ -391,7 +401,7 @@ __device__ inline int l_sphere_box(const double* ps, double rs, const double* pb
   return 1;
 }
 
-__device__ inline int l_box_box(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2, const double* s2,
+__device__ __noinline__ int l_box_box(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2, const double* s2,
                                 double margin, LRaw* out, int maxout) {
   double R[3][3], AR[3][3], t[3], d12[3];
   for (int k = 0; k < 3; k++) d12[k] = p2[k] - p1[k];
@@ -523,7 +533,34 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
       if (b < 0) { gp[0] = m->geom_pos[g][0]; gp[1] = m->geom_pos[g][1]; gp[2] = m->geom_pos[g][2]; }
       else { double t[3]; lmat_vec(t, W->xmat[b], m->geom_pos[g]); gp[0] = W->xpos[b][0] + t[0]; gp[1] = W->xpos[b][1] + t[1]; gp[2] = W->xpos[b][2] + t[2]; }
       double dc[3] = {gp[0] - cp[0], gp[1] - cp[1], gp[2] - cp[2]};
-      keep = !(lnorm3(dc) > m->geom_rbound[g] + m->cube_rbound);
+      keep = !(lnorm3(dc) > m->geom_rbound[g] + m->cube_rbound);  // the oracle's bounding-sphere test
+      if (keep) {
+        // conservative pre-filter (never rejects a touching pair): the 6 face axes of the SAT / exact sphere-box distance,
+        // so that only a handful of pairs reach the divergent contact-generation pass
+        double t[3];
+        lmatT_vec(t, W->xmat[0], dc);  // geom centre in the cube frame
+        if ((int)m->geom_type[g] == 6) {
+          double gm[9], R[3][3];
+          if (b < 0) { for (int k = 0; k < 9; k++) gm[k] = m->geom_mat[g][k]; } else lmat_mul(gm, W->xmat[b], m->geom_mat[g]);
+          const double* m1 = W->xmat[0];
+          for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) R[i][j] = fabs(m1[i] * gm[j] + m1[3 + i] * gm[3 + j] + m1[6 + i] * gm[6 + j]) + 1e-12;
+          const double* s2 = m->geom_size[g];
+          for (int i = 0; i < 3 && keep; i++)
+            if (fabs(t[i]) - (m->cube_size[i] + s2[0] * R[i][0] + s2[1] * R[i][1] + s2[2] * R[i][2]) >= 1e-9) keep = false;
+          if (keep) {
+            double t2[3];
+            lmatT_vec(t2, gm, dc);
+            for (int j = 0; j < 3 && keep; j++)
+              if (fabs(t2[j]) - (s2[j] + m->cube_size[0] * R[0][j] + m->cube_size[1] * R[1][j] + m->cube_size[2] * R[2][j]) >= 1e-9) keep = false;
+          }
+        } else {
+          double d2 = 0;
+          for (int k = 0; k < 3; k++) { const double ex = fabs(t[k]) - m->cube_size[k]; if (ex > 0) d2 += ex * ex; }
+          const double rr = m->geom_size[g][0] + 1e-9;
+          if (d2 >= rr * rr) keep = false;
+        }
+      }
     }
     const unsigned mask = __ballot_sync(FULL, keep);
     if (keep) W->cand[base + __popc(mask & ((1u << lane) - 1))] = g;
@@ -687,7 +724,7 @@ __device__ inline void leap_make_constraint(const LeapModel* __restrict__ m, Lea
 
 // ------------------------------------------------------------------ Newton solver (mj_solNewton, primal, elliptic cones)
 // one elliptic contact at x[3]: returns cost, writes force[3], state, optional 3x3 cone Hessian
-__device__ __forceinline__ double leap_cone_eval(const LeapWork* W, int c, int row0, const double* x, double* force, int* state, double* Hc) {
+__device__ __noinline__ double leap_cone_eval(const LeapWork* W, int c, int row0, const double* x, double* force, int* state, double* Hc) {
   const double mu = W->cmu[c], f1 = W->cfri[c], f2 = W->cfri[c];
   const double D0 = W->eD[row0];
   const double U0 = x[0] * mu, U1 = x[1] * f1, U2 = x[2] * f2;
@@ -746,7 +783,7 @@ __device__ __forceinline__ double lwsum(double v) {
 }
 
 // jar = J qacc - aref for every row; Ma = M qacc
-__device__ inline void leap_set_point(const LeapModel* __restrict__ m, LeapWork* W, const double* qacc, int lane) {
+__device__ __noinline__ void leap_set_point(const LeapModel* __restrict__ m, LeapWork* W, const double* qacc, int lane) {
   if (lane < LEAP_NV) W->Ma[lane] = leap_mulM_row(m, W, qacc, lane);
   const int nfl = W->nfl, nefc = W->nefc;
   for (int r = lane; r < nefc; r += 32) {
@@ -757,7 +794,7 @@ __device__ inline void leap_set_point(const LeapModel* __restrict__ m, LeapWork*
 }
 
 // cost / forces / states at the current jar (+ gradient and, optionally, the Newton Hessian)
-__device__ inline void leap_constraint_update(const LeapModel* __restrict__ m, LeapWork* W, const double* qacc, bool want_h, int lane) {
+__device__ __noinline__ void leap_constraint_update(const LeapModel* __restrict__ m, LeapWork* W, const double* qacc, bool want_h, int lane) {
   const int nfr = (int)m->nfr, nfl = W->nfl, ncon = W->ncon;
   double cost = 0;
   for (int r = lane; r < nfl; r += 32) cost += leap_row_eval(W, r, nfr, W->ejar[r], &W->eforce[r], &W->estate[r]);
@@ -787,111 +824,236 @@ __device__ inline void leap_constraint_update(const LeapModel* __restrict__ m, L
   }
   g = lwsum(g);
   if (lane == 0) { W->gauss = 0.5 * g; W->cost = 0.5 * g + cost; }
-  if (want_h) {
-    // H = M + sum_rows D J^T J (+ cone blocks): lane per lower-triangle entry
-    for (int e = lane; e < LEAP_NV * (LEAP_NV + 1) / 2; e += 32) {
-      int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while ((i + 1) * (i + 2) / 2 <= e) i++;
-      while (i * (i + 1) / 2 > e) i--;
-      const int j = e - i * (i + 1) / 2;  // j <= i
-      double h = 0;
-      // mass matrix entry
-      if (i < 3) h = (i == j) ? W->Mc[i] : 0.0;
-      else if (i < 6) h = j >= 3 ? m->cube_Irot[3 * (i - 3) + (j - 3)] : 0.0;
-      else { const int f = (i - 6) >> 2; if (j >= 6 + 4 * f) h = W->Mf[f][(i - 6) & 3][(j - 6) & 3]; }
-      if (i == j)
-        for (int r = 0; r < nfl; r++) if (W->edof[r] == i && W->estate[r] == LST_QUADRATIC) h += W->eD[r];
-      const int fi = i >= 6 ? (i - 6) >> 2 : -1, fj = j >= 6 ? (j - 6) >> 2 : -1;
-      const int ki = i < 6 ? i : 6 + ((i - 6) & 3), kj = j < 6 ? j : 6 + ((j - 6) & 3);
-      if (fi < 0 || fj < 0 || fi == fj) {
-        for (int c = 0; c < ncon; c++) {
-          const int fc = W->cfinger[c];
-          if ((fi >= 0 && fi != fc) || (fj >= 0 && fj != fc)) continue;
-          const int r0 = 3 * c, st = W->estate[nfl + r0];
-          if (st == LST_QUADRATIC) {
-#pragma unroll
-            for (int a = 0; a < 3; a++) h += W->eD[nfl + r0 + a] * W->Jc[r0 + a][ki] * W->Jc[r0 + a][kj];
-          } else if (st == LST_CONE) {
-#pragma unroll
-            for (int a = 0; a < 3; a++)
-#pragma unroll
-              for (int b = 0; b < 3; b++) h += W->cHc[c][3 * a + b] * W->Jc[r0 + a][ki] * W->Jc[r0 + b][kj];
-          }
-        }
-      }
-      W->LH(i, j) = h;
+  __syncwarp();
+}
+
+// lower-triangle index tables packed 3 bits per entry: 6x6 (21 entries) and 4x4 (10 entries)
+#define TRI6_I 0x5b6db2491b6d2448ull  /* 0,1,1,2,2,2,3,3,3,3,4,4,4,4,4,5,5,5,5,5,5 */
+#define TRI6_J 0x58d111a21a211040ull /* 0,0,1,0,1,2,0,1,2,3,0,1,2,3,4,0,1,2,3,4,5 */
+#define TRI4_I 0x1b6d2448ull         /* 0,1,1,2,2,2,3,3,3,3 */
+#define TRI4_J 0x1a211040ull         /* 0,0,1,0,1,2,0,1,2,3 */
+__device__ __forceinline__ int tri_get(unsigned long long tab, int e) { return (int)((tab >> (3 * e)) & 7ull); }
+
+// Newton direction: search = -H^-1 grad, H = M + sum_rows D J^T J (+ elliptic cone blocks).
+// Contacts only involve the cube, so H is an ARROW matrix: cube block C (6x6), four independent finger blocks F_f (4x4)
+// and couplings B_f (4x6).  Eliminating the fingers first:  L_f = chol(F_f),  X_f = L_f^-1 B_f,
+// S = C - sum_f X_f^T X_f,  L_S = chol(S)  — sequential depth 4 + 6 instead of 22, compact code, tiny shared footprint.
+__device__ inline void leap_newton_direction(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  const int nfr = (int)m->nfr, nfl = W->nfl, ncon = W->ncon;
+  // ---- assemble: mass matrix
+  for (int e = lane; e < 36; e += 32) {
+    const int i = e / 6, j = e - 6 * i;
+    W->Hcc[i][j] = (i < 3) ? (i == j ? W->Mc[i] : 0.0) : (j >= 3 ? m->cube_Irot[3 * (i - 3) + (j - 3)] : 0.0);
+  }
+  for (int e = lane; e < 96; e += 32) (&W->Hcf[0][0][0])[e] = 0.0;
+  for (int e = lane; e < 64; e += 32) (&W->Hff[0][0][0])[e] = (&W->Mf[0][0][0])[e];
+  __syncwarp();
+  // friction-loss rows, then limit rows, in their quadratic zone: D on the diagonal (two passes: a dof can own both kinds)
+  for (int pass = 0; pass < 2; pass++) {
+    const int r = lane;
+    const bool mine = pass == 0 ? r < nfr : (r >= nfr && r < nfl);
+    if (mine && W->estate[r] == LST_QUADRATIC) {
+      const int dof = W->edof[r];
+      if (dof < 6) W->Hcc[dof][dof] += W->eD[r]; else W->Hff[(dof - 6) >> 2][(dof - 6) & 3][(dof - 6) & 3] += W->eD[r];
     }
+    __syncwarp();
+  }
+  // contacts: J^T Wc J with Wc = diag(D) (quadratic zone) or the 3x3 cone Hessian
+  for (int c = 0; c < ncon; c++) {
+    const int st = W->estate[nfl + 3 * c];
+    if (st == LST_SATISFIED) continue;
+    const int fc = W->cfinger[c];
+    double Wm[9];
+    if (st == LST_QUADRATIC) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) Wm[k] = 0;
+      Wm[0] = W->eD[nfl + 3 * c]; Wm[4] = W->eD[nfl + 3 * c + 1]; Wm[8] = W->eD[nfl + 3 * c + 2];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; k++) Wm[k] = W->cHc[c][k];
+    }
+    const double(*J)[10] = &W->Jc[3 * c];
+    // pass A: cube-cube (lanes 0..20) and finger-finger (lanes 21..30)
+    int ia = -1, ja = -1;
+    double* dst = nullptr;
+    if (lane < 21) { ia = tri_get(TRI6_I, lane); ja = tri_get(TRI6_J, lane); dst = &W->Hcc[ia][ja]; }
+    else if (lane < 31 && fc >= 0) { const int e = lane - 21; ia = 6 + tri_get(TRI4_I, e); ja = 6 + tri_get(TRI4_J, e); dst = &W->Hff[fc][ia - 6][ja - 6]; }
+    if (dst) {
+      double h = 0;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) h += Wm[3 * a + b] * J[a][ia] * J[b][ja];
+      *dst += h;
+    }
+    // pass B: finger-cube coupling (lanes 0..23)
+    if (fc >= 0 && lane < 24) {
+      const int r = lane / 6, cc = lane - 6 * r;
+      double h = 0;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) h += Wm[3 * a + b] * J[a][6 + r] * J[b][cc];
+      W->Hcf[fc][r][cc] += h;
+    }
+    __syncwarp();
+  }
+  // ---- factorise the finger blocks (lane f), keep 1/L_kk on the diagonal slot for the substitutions
+  if (lane < 4) {
+    const int f = lane;
+    double L[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        double sacc = W->Hff[f][i][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
+        // pivots are kept as RECIPROCALS (one rsqrt per pivot, every later division becomes a multiplication)
+        if (i == j) { if (sacc < B2_MINVAL) sacc = B2_MINVAL; L[i][i] = rsqrt(sacc); } else L[i][j] = sacc * L[j][j];
+      }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) W->Hff[f][i][j] = L[i][j];
+    // y_f = L_f^-1 (-grad_f)
+    double y[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { double sacc = -W->grad[6 + 4 * f + i];
+#pragma unroll
+      for (int k = 0; k < i; k++) sacc -= L[i][k] * y[k];
+      y[i] = sacc * L[i][i]; W->yf[f][i] = y[i]; }
+  }
+  __syncwarp();
+  // X_f = L_f^-1 B_f, one (finger, cube column) per lane
+  if (lane < 24) {
+    const int f = lane / 6, cc = lane - 6 * f;
+    double x[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { double sacc = W->Hcf[f][i][cc];
+#pragma unroll
+      for (int k = 0; k < i; k++) sacc -= W->Hff[f][i][k] * x[k];
+      x[i] = sacc * W->Hff[f][i][i]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) W->Hcf[f][i][cc] = x[i];
+  }
+  __syncwarp();
+  // Schur complement S = C - sum_f X_f^T X_f (lanes 0..20) and reduced right-hand side (lanes 21..26)
+  if (lane < 21) {
+    const int i = tri_get(TRI6_I, lane), j = tri_get(TRI6_J, lane);
+    double sacc = W->Hcc[i][j];
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) sacc -= W->Hcf[f][r][i] * W->Hcf[f][r][j];
+    W->Hcc[i][j] = sacc;
+  } else if (lane < 27) {
+    const int cc = lane - 21;
+    double sacc = -W->grad[cc];
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) sacc -= W->Hcf[f][r][cc] * W->yf[f][r];
+    W->xc[cc] = sacc;
+  }
+  __syncwarp();
+  // cube block: Cholesky + both substitutions in one lane (6x6)
+  if (lane == 0) {
+    double L[6][6], x[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        double sacc = W->Hcc[i][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
+        if (i == j) { if (sacc < B2_MINVAL) sacc = B2_MINVAL; L[i][i] = rsqrt(sacc); } else L[i][j] = sacc * L[j][j];
+      }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { double sacc = W->xc[i];
+#pragma unroll
+      for (int k = 0; k < i; k++) sacc -= L[i][k] * x[k];
+      x[i] = sacc * L[i][i]; }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) { double sacc = x[i];
+#pragma unroll
+      for (int k = i + 1; k < 6; k++) sacc -= L[k][i] * x[k];
+      x[i] = sacc * L[i][i]; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { W->xc[i] = x[i]; W->search[i] = x[i]; }
+  }
+  __syncwarp();
+  // fingers: x_f = L_f^-T (y_f - X_f x_C)
+  if (lane < 4) {
+    const int f = lane;
+    double t[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) { double sacc = W->yf[f][r];
+#pragma unroll
+      for (int cc = 0; cc < 6; cc++) sacc -= W->Hcf[f][r][cc] * W->xc[cc];
+      t[r] = sacc; }
+#pragma unroll
+    for (int i = 3; i >= 0; i--) { double sacc = t[i];
+#pragma unroll
+      for (int k = i + 1; k < 4; k++) sacc -= W->Hff[f][k][i] * t[k];
+      t[i] = sacc * W->Hff[f][i][i]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) W->search[6 + 4 * f + i] = t[i];
   }
   __syncwarp();
 }
 
-// in-place dense Cholesky of the lower triangle of H (warp cooperative), then x <- H^-1 x
-__device__ inline void leap_chol_solve_H(LeapWork* W, double* x, int lane) {
-  constexpr int n = LEAP_NV;
-  for (int k = 0; k < n; k++) {
-    double d = W->LH(k, k);
-    if (d < B2_MINVAL) d = B2_MINVAL;
-    const double lkk = sqrt(d);
-    __syncwarp();
-    if (lane == 0) W->LH(k, k) = lkk;
-    for (int i = k + 1 + lane; i < n; i += 32) W->LH(i, k) = W->LH(i, k) / lkk;
-    __syncwarp();
-    // trailing update of the lower triangle
-    const int rem = n - k - 1;
-    for (int e = lane; e < rem * (rem + 1) / 2; e += 32) {
-      int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while ((a + 1) * (a + 2) / 2 <= e) a++;
-      while (a * (a + 1) / 2 > e) a--;
-      const int b = e - a * (a + 1) / 2;
-      const int i = k + 1 + a, j = k + 1 + b;
-      W->LH(i, j) -= W->LH(i, k) * W->LH(j, k);
-    }
-    __syncwarp();
-  }
-  // forward substitution L y = x
-  for (int k = 0; k < n; k++) {
-    const double xk = x[k] / W->LH(k, k);
-    __syncwarp();
-    if (lane == 0) x[k] = xk;
-    for (int i = k + 1 + lane; i < n; i += 32) x[i] -= W->LH(i, k) * xk;
-    __syncwarp();
-  }
-  // back substitution L^T z = y
-  for (int k = n - 1; k >= 0; k--) {
-    const double xk = x[k] / W->LH(k, k);
-    __syncwarp();
-    if (lane == 0) x[k] = xk;
-    for (int i = lane; i < k; i += 32) x[i] -= W->LH(k, i) * xk;
-    __syncwarp();
+// Line search state held in REGISTERS: lane r owns friction/limit row r (nfl <= 32) and lane c owns contact c (ncon <= 24),
+// so one evaluation of the 1-D cost derivatives is register math plus two warp reductions.
+struct LeapLS {
+  double rjar, rjv, rD, rR, rfl;           // my friction/limit row
+  double cjar[3], cjv[3], cD[3], cmu, cfr;  // my contact
+  bool has_row, row_is_friction, has_con;
+};
+
+__device__ __forceinline__ void leap_ls_load(const LeapModel* __restrict__ m, const LeapWork* W, int lane, LeapLS& L) {
+  const int nfr = (int)m->nfr, nfl = W->nfl;
+  L.has_row = lane < nfl; L.row_is_friction = lane < nfr; L.has_con = lane < W->ncon;
+  if (L.has_row) { L.rjar = W->ejar[lane]; L.rjv = W->ejv[lane]; L.rD = W->eD[lane]; L.rR = W->eR[lane]; L.rfl = W->efloss[lane]; }
+  if (L.has_con) {
+    const int r0 = nfl + 3 * lane;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { L.cjar[k] = W->ejar[r0 + k]; L.cjv[k] = W->ejv[r0 + k]; L.cD[k] = W->eD[r0 + k]; }
+    L.cmu = W->cmu[lane]; L.cfr = W->cfri[lane];
   }
 }
 
-// 1-D derivatives of the cost along the search direction at step alpha (all lanes get the result)
-__device__ inline void leap_ls_eval(const LeapModel* __restrict__ m, const LeapWork* W, double alpha, double g1, double g2, double* d1, double* d2, int lane) {
-  const int nfr = (int)m->nfr, nfl = W->nfl, ncon = W->ncon;
+// first and second derivative of the cost along the search direction at step alpha (all lanes get the result)
+__device__ __forceinline__ void leap_ls_eval(const LeapLS& L, double alpha, double g1, double g2, double* d1, double* d2) {
   double p1 = 0, p2 = 0;
-  for (int r = lane; r < nfl; r += 32) {
-    double f; int st;
-    leap_row_eval(W, r, nfr, W->ejar[r] + alpha * W->ejv[r], &f, &st);
-    p1 -= f * W->ejv[r];
-    if (st == LST_QUADRATIC) p2 += W->eD[r] * W->ejv[r] * W->ejv[r];
+  if (L.has_row) {
+    const double x = L.rjar + alpha * L.rjv;
+    if (L.row_is_friction) {
+      const double lim = L.rR * L.rfl;
+      if (x <= -lim) p1 -= L.rfl * L.rjv;
+      else if (x >= lim) p1 += L.rfl * L.rjv;
+      else { p1 += L.rD * x * L.rjv; p2 += L.rD * L.rjv * L.rjv; }
+    } else if (x < 0) { p1 += L.rD * x * L.rjv; p2 += L.rD * L.rjv * L.rjv; }
   }
-  for (int c = lane; c < ncon; c += 32) {
-    const int r0 = nfl + 3 * c;
-    double x[3], f[3], Hc[9]; int st;
-#pragma unroll
-    for (int k = 0; k < 3; k++) x[k] = W->ejar[r0 + k] + alpha * W->ejv[r0 + k];
-    leap_cone_eval(W, c, r0, x, f, &st, Hc);
-#pragma unroll
-    for (int k = 0; k < 3; k++) p1 -= f[k] * W->ejv[r0 + k];
-    if (st == LST_CONE) {
-#pragma unroll
-      for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b = 0; b < 3; b++) p2 += W->ejv[r0 + a] * Hc[3 * a + b] * W->ejv[r0 + b];
-    } else if (st == LST_QUADRATIC) {
-#pragma unroll
-      for (int k = 0; k < 3; k++) p2 += W->eD[r0 + k] * W->ejv[r0 + k] * W->ejv[r0 + k];
+  if (L.has_con) {
+    const double mu = L.cmu, f = L.cfr;
+    const double x0 = L.cjar[0] + alpha * L.cjv[0], x1 = L.cjar[1] + alpha * L.cjv[1], x2 = L.cjar[2] + alpha * L.cjv[2];
+    const double U1 = x1 * f, U2 = x2 * f;
+    const double N = x0 * mu, T = sqrt(U1 * U1 + U2 * U2);
+    if (N >= mu * T) { /* separating: no force */ }
+    else if (mu * N + T <= 0) {
+      p1 += L.cD[0] * x0 * L.cjv[0] + L.cD[1] * x1 * L.cjv[1] + L.cD[2] * x2 * L.cjv[2];
+      p2 += L.cD[0] * L.cjv[0] * L.cjv[0] + L.cD[1] * L.cjv[1] * L.cjv[1] + L.cD[2] * L.cjv[2] * L.cjv[2];
+    } else {
+      // s = 0.5 Dm (N - mu T)^2 in the scaled space U = S x; chain rule with dU/dalpha = S jv
+      const double Dm = L.cD[0] / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+      const double Ti = T > B2_MINVAL ? 1 / T : 0;
+      const double v0 = mu * L.cjv[0], v1 = f * L.cjv[1], v2 = f * L.cjv[2];
+      const double dT = (U1 * v1 + U2 * v2) * Ti;
+      const double dNmT = v0 - mu * dT;
+      const double d2T = (v1 * v1 + v2 * v2 - dT * dT) * Ti;  // curvature of |U_T| along a line
+      p1 += Dm * NmT * dNmT;
+      p2 += Dm * (dNmT * dNmT - NmT * mu * d2T);
     }
   }
   *d1 = g1 + alpha * g2 + lwsum(p1);
@@ -905,17 +1067,19 @@ __device__ inline double leap_line_search(const LeapModel* __restrict__ m, const
   const double snorm = sqrt(lwsum(sn));
   if (snorm < B2_MINVAL) return 0;
   const double gtol = m->tolerance * m->ls_tolerance * snorm * m->meaninertia * LEAP_NV;
-  double d1, d2, lo = 0, hi = -1, dlo, dhi = 0, alpha;
-  leap_ls_eval(m, W, 0, g1, g2, &d1, &d2, lane);
+  LeapLS L;
+  leap_ls_load(m, W, lane, L);
+  double d1, d2, lo = 0, hi = -1, alpha;
+  leap_ls_eval(L, 0, g1, g2, &d1, &d2);
   if (d1 >= 0 || d2 <= 0) return 0;
-  dlo = d1;
   alpha = -d1 / d2;
   double prev_step = 1e300;
   const int iters = (int)m->ls_iterations;
+#pragma unroll 1
   for (int it = 0; it < iters; it++) {
-    leap_ls_eval(m, W, alpha, g1, g2, &d1, &d2, lane);
+    leap_ls_eval(L, alpha, g1, g2, &d1, &d2);
     if (fabs(d1) < gtol) return alpha;
-    if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
+    if (d1 < 0) lo = alpha; else hi = alpha;
     double next = d2 > 0 ? alpha - d1 / d2 : -1;
     if (hi < 0) { if (!(next > lo)) next = 2 * alpha + B2_MINVAL; }
     else if (!(next > lo && next < hi && fabs(next - alpha) < 0.5 * prev_step)) next = 0.5 * (lo + hi);
@@ -923,11 +1087,10 @@ __device__ inline double leap_line_search(const LeapModel* __restrict__ m, const
     prev_step = fabs(next - alpha);
     alpha = next;
   }
-  (void)dlo; (void)dhi;
   return lo > 0 ? lo : alpha;
 }
 
-__device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+__device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, LeapWork* W, int lane, int prof) {
   const int nefc = W->nefc;
   if (nefc == 0) {
     if (lane < LEAP_NV) { W->qacc[lane] = W->qacc_smooth[lane]; W->qfrc_constraint[lane] = 0; }
@@ -953,13 +1116,15 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
     double gn = lane < LEAP_NV ? W->grad[lane] * W->grad[lane] : 0.0;
     gn = lwsum(gn);
     if (scale * sqrt(gn) < m->tolerance) break;
-    if (lane < LEAP_NV) W->search[lane] = -W->grad[lane];
-    __syncwarp();
-    leap_chol_solve_H(W, W->search, lane);
+    long long t1 = LPROF_T();
+    leap_newton_direction(m, W, lane);
+    LPROF_ADD(8, t1); t1 = LPROF_T();
     if (lane < LEAP_NV) W->Mv[lane] = leap_mulM_row(m, W, W->search, lane);
     for (int r = lane; r < nefc; r += 32) W->ejv[r] = r < nfl ? W->esign[r] * W->search[W->edof[r]] : leap_Jrow_dot(W, r - nfl, W->search);
     __syncwarp();
     const double alpha = leap_line_search(m, W, lane);
+    LPROF_ADD(9, t1); t1 = LPROF_T();
+    if (lane == 0 && prof) atomicAdd(&g_leap_prof[10], 1ull);
     if (alpha == 0) break;
     const double oldcost = W->cost;
     __syncwarp();
@@ -967,6 +1132,7 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
     for (int r = lane; r < nefc; r += 32) W->ejar[r] += alpha * W->ejv[r];
     __syncwarp();
     leap_constraint_update(m, W, W->qacc, true, lane);
+    LPROF_ADD(7, t1);
     const double newcost = W->cost;
     __syncwarp();
     if (scale * (oldcost - newcost) < m->tolerance) break;
@@ -974,36 +1140,55 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
 }
 
 // ------------------------------------------------------------------ one mj_step
-__device__ inline void leap_step(const LeapModel* __restrict__ m, LeapWork* W, int lane, double* sens /* global, may be null */) {
-  leap_kinematics(m, W, lane);
-  leap_mass_and_bias(m, W, lane);
-  leap_collision(m, W, lane);
-  leap_make_constraint(m, W, lane);
-  if (sens) {  // position-stage sensors: 16 jointpos then 5 framepos sites (pre-step state)
-    if (lane < 16) sens[lane] = W->qpos[7 + lane];
-    if (lane < 5) {
-      const int b = (int)m->site_body[lane];
-      double t[3];
-      lmat_vec(t, W->xmat[b], m->site_pos[lane]);
-      for (int k = 0; k < 3; k++) sens[16 + 3 * lane + k] = W->xpos[b][k] + t[k];
-    }
+// All warps of the block call this together; `active` masks the tail warps.  The two block barriers keep the warps in
+// the same code region (see the kernel comment) — they are NOT data dependencies.
+__device__ inline void leap_step(const LeapModel* __restrict__ m, LeapWork* W, int lane, double* sens /* global, may be null */, int prof,
+                                 bool active) {
+  long long t0 = LPROF_T();
+  if (active) {
+    leap_kinematics(m, W, lane);
+    LPROF_ADD(0, t0); t0 = LPROF_T();
+    leap_mass_and_bias(m, W, lane);
+    LPROF_ADD(1, t0);
   }
-  // passive + actuation -> qfrc_smooth; qacc_smooth = M^-1 qfrc_smooth
-  if (lane < LEAP_NV) {
-    const int i = lane;
-    double f = -m->dof_damping[i] * W->qvel[i] - W->qfrc_bias[i];
-    if (i >= 6) {
-      const int a = i - 6;
-      double u = W->ctrl[a];
-      if (m->ctrllimited[a] != 0) u = fmin(fmax(u, m->ctrl_lo[a]), m->ctrl_hi[a]);
-      f += m->kp[a] * u - m->kp[a] * W->qpos[7 + a] - m->kv[a] * W->qvel[i];
+  __syncthreads();
+  t0 = LPROF_T();
+  if (active) {
+    leap_collision(m, W, lane);
+    LPROF_ADD(2, t0); t0 = LPROF_T();
+    leap_make_constraint(m, W, lane);
+    LPROF_ADD(3, t0); t0 = LPROF_T();
+    if (sens) {  // position-stage sensors: 16 jointpos then 5 framepos sites (pre-step state)
+      if (lane < 16) sens[lane] = W->qpos[7 + lane];
+      if (lane < 5) {
+        const int b = (int)m->site_body[lane];
+        double t[3];
+        lmat_vec(t, W->xmat[b], m->site_pos[lane]);
+        for (int k = 0; k < 3; k++) sens[16 + 3 * lane + k] = W->xpos[b][k] + t[k];
+      }
     }
-    W->qfrc_smooth[i] = f; W->qacc_smooth[i] = f;
+    // passive + actuation -> qfrc_smooth; qacc_smooth = M^-1 qfrc_smooth
+    if (lane < LEAP_NV) {
+      const int i = lane;
+      double f = -m->dof_damping[i] * W->qvel[i] - W->qfrc_bias[i];
+      if (i >= 6) {
+        const int a = i - 6;
+        double u = W->ctrl[a];
+        if (m->ctrllimited[a] != 0) u = fmin(fmax(u, m->ctrl_lo[a]), m->ctrl_hi[a]);
+        f += m->kp[a] * u - m->kp[a] * W->qpos[7 + a] - m->kv[a] * W->qvel[i];
+      }
+      W->qfrc_smooth[i] = f; W->qacc_smooth[i] = f;
+    }
+    __syncwarp();
+    leap_block_solve(m, W, nullptr, W->qacc_smooth, lane);
+    LPROF_ADD(4, t0);
   }
+  __syncthreads();
+  if (!active) return;
+  t0 = LPROF_T();
+  leap_fwd_constraint(m, W, lane, prof);
   __syncwarp();
-  leap_block_solve(m, W, nullptr, W->qacc_smooth, lane);
-  leap_fwd_constraint(m, W, lane);
-  __syncwarp();
+  LPROF_ADD(5, t0); t0 = LPROF_T();
   // implicitfast: (M + h (damping + kv)) qacc = qfrc_smooth + qfrc_constraint, then semi-implicit advance
   const double h = m->dt;
   if (lane < LEAP_NV) {
@@ -1026,6 +1211,7 @@ __device__ inline void leap_step(const LeapModel* __restrict__ m, LeapWork* W, i
     for (int k = 0; k < 4; k++) W->qpos[3 + k] = nq[k];
   } else if (lane >= 6 && lane < LEAP_NV) W->qpos[lane + 1] += h * W->qvel[lane];
   __syncwarp();
+  LPROF_ADD(6, t0);
 }
 
 // per-step cost (leap_cube.py:76-86): 0.5 w_pos |p - goal|^2 + 0.5 w_rot |log(q* (x) q_goal)|^2 ; params [w_pos, w_rot, goal_quat4, goal_pos3]
@@ -1048,47 +1234,59 @@ __device__ inline double leap_cost(const double* p, const double* qpos) {
 
 // ------------------------------------------------------------------ kernels
 // COST: in = knots (N,K,16), basis (H,K) -> reward (N) [+ cost (N,H) f32];  !COST: in = controls (N,H,16) -> states, sensors
+// Block = up to 7 warps (7 rollouts, one SM's worth of shared memory).  The warps of a block are re-aligned with a
+// __syncthreads() at every time step so that they walk through the same code region together: the kernel's instruction
+// footprint far exceeds the SM's instruction caches, and warps drifting apart would each stream it from L2 on their own.
 template <bool COST>
-__global__ void __launch_bounds__(32) leap_rollout_kernel(const LeapModel* __restrict__ m, const double* __restrict__ x0, int x0_batched,
-                                                          const double* __restrict__ in, int N, int H, int K, const double* __restrict__ basis,
-                                                          const double* __restrict__ cost_params, double* __restrict__ states,
-                                                          double* __restrict__ sensors, float* __restrict__ cost_NH, double* __restrict__ reward_N) {
-  extern __shared__ __align__(16) unsigned char lsm[];
+__global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __restrict__ m, const double* __restrict__ x0, int x0_batched,
+                                                           const double* __restrict__ in, int N, int H, int K, const double* __restrict__ basis,
+                                                           const double* __restrict__ cost_params, double* __restrict__ states,
+                                                           double* __restrict__ sensors, float* __restrict__ cost_NH, double* __restrict__ reward_N,
+                                                           int wstride, int prof) {
+  extern __shared__ __align__(16) unsigned char lsm_all[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int n = blockIdx.x * wpb + wib;
+  const bool active = n < N;
+  unsigned char* lsm = lsm_all + (size_t)wib * wstride;
   LeapWork* W = reinterpret_cast<LeapWork*>(lsm);
-  const int lane = threadIdx.x, n = blockIdx.x;
-  if (n >= N) return;
-  const double* xs = x0 + (x0_batched ? (size_t)n * LEAP_NX : 0);
-  if (lane < LEAP_NQ) W->qpos[lane] = xs[lane];
-  if (lane < LEAP_NV) { W->qvel[lane] = xs[LEAP_NQ + lane]; W->warm[lane] = 0; }
+  if (active) {
+    const double* xs = x0 + (x0_batched ? (size_t)n * LEAP_NX : 0);
+    if (lane < LEAP_NQ) W->qpos[lane] = xs[lane];
+    if (lane < LEAP_NV) { W->qvel[lane] = xs[LEAP_NQ + lane]; W->warm[lane] = 0; }
+  }
   __syncwarp();
   if constexpr (COST) {
     // stage this rollout's knots (K*16 doubles) and the basis behind the work area with TMA bulk copies
     uint64_t* bar = reinterpret_cast<uint64_t*>(lsm + ((sizeof(LeapWork) + 15) & ~(size_t)15));
     double* sK = reinterpret_cast<double*>(bar + 2);
     double* sB = sK + K * LEAP_NU;
-    const unsigned bytesK = (unsigned)(K * LEAP_NU * sizeof(double)), bytesB = (unsigned)(H * K * sizeof(double));
-    const double* gK = in + (size_t)n * K * LEAP_NU;
-    const bool tma_ok = (bytesB % 16 == 0) && ((reinterpret_cast<uintptr_t>(basis) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gK) & 15) == 0);
-    if (tma_ok) {
-      if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-      __syncwarp();
-      if (lane == 0) { mbar_expect_tx(bar, bytesK + bytesB); tma_bulk_g2s(sK, gK, bytesK, bar); tma_bulk_g2s(sB, basis, bytesB, bar); }
-      mbar_wait(bar, 0);
-    } else {
-      for (int i = lane; i < K * LEAP_NU; i += 32) sK[i] = gK[i];
-      for (int i = lane; i < H * K; i += 32) sB[i] = basis[i];
-      __syncwarp();
+    if (active) {
+      const unsigned bytesK = (unsigned)(K * LEAP_NU * sizeof(double)), bytesB = (unsigned)(H * K * sizeof(double));
+      const double* gK = in + (size_t)n * K * LEAP_NU;
+      const bool tma_ok = (bytesB % 16 == 0) && ((reinterpret_cast<uintptr_t>(basis) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gK) & 15) == 0);
+      if (tma_ok) {
+        if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+        __syncwarp();
+        if (lane == 0) { mbar_expect_tx(bar, bytesK + bytesB); tma_bulk_g2s(sK, gK, bytesK, bar); tma_bulk_g2s(sB, basis, bytesB, bar); }
+        mbar_wait(bar, 0);
+      } else {
+        for (int i = lane; i < K * LEAP_NU; i += 32) sK[i] = gK[i];
+        for (int i = lane; i < H * K; i += 32) sB[i] = basis[i];
+        __syncwarp();
+      }
     }
     double total = 0;
+#pragma unroll 1
     for (int t = 0; t < H; t++) {
-      if (lane < LEAP_NU) {
+      __syncthreads();
+      if (active && lane < LEAP_NU) {
         double u = 0;
         for (int k = 0; k < K; k++) u += sB[t * K + k] * sK[k * LEAP_NU + lane];
         W->ctrl[lane] = u;
       }
       __syncwarp();
-      leap_step(m, W, lane, nullptr);
-      if (lane == 0) {
+      leap_step(m, W, lane, nullptr, prof, active);
+      if (active && lane == 0) {
         double cp[LEAP_NCOST];
 #pragma unroll
         for (int i = 0; i < LEAP_NCOST; i++) cp[i] = cost_params[i];
@@ -1097,12 +1295,15 @@ __global__ void __launch_bounds__(32) leap_rollout_kernel(const LeapModel* __res
         if (cost_NH) cost_NH[(size_t)n * H + t] = (float)ct;
       }
     }
-    if (lane == 0) reward_N[n] = -(total / H);
+    if (active && lane == 0) reward_N[n] = -(total / H);
   } else {
+#pragma unroll 1
     for (int t = 0; t < H; t++) {
-      if (lane < LEAP_NU) W->ctrl[lane] = in[((size_t)n * H + t) * LEAP_NU + lane];
+      __syncthreads();
+      if (active && lane < LEAP_NU) W->ctrl[lane] = in[((size_t)n * H + t) * LEAP_NU + lane];
       __syncwarp();
-      leap_step(m, W, lane, sensors ? sensors + ((size_t)n * H + t) * LEAP_NS : nullptr);
+      leap_step(m, W, lane, (sensors && active) ? sensors + ((size_t)n * H + t) * LEAP_NS : nullptr, prof, active);
+      if (!active) continue;
       double* so = states + ((size_t)n * H + t) * LEAP_NX;
       if (lane < LEAP_NQ) so[lane] = W->qpos[lane];
       if (lane < LEAP_NV) so[LEAP_NQ + lane] = W->qvel[lane];
@@ -1131,21 +1332,39 @@ inline int leap_create(LeapModel** out, const double* consts, size_t n, std::str
   return 0;
 }
 inline void leap_destroy(LeapModel* m) { cudaFree(m); }
+inline void leap_prof_dump() {
+  unsigned long long h[16];
+  if (cudaMemcpyFromSymbol(h, g_leap_prof, sizeof(h)) != cudaSuccess) return;
+  const char* names[11] = {"kinematics", "mass+bias", "collision", "constraints", "smooth", "solver(total)", "integrate", "  update", "  direction", "  linesearch", "newton iters"};
+  for (int i = 0; i < 11; i++) fprintf(stderr, "leap_prof %-14s %llu\n", names[i], h[i]);
+  memset(h, 0, sizeof(h));
+  cudaMemcpyToSymbol(g_leap_prof, h, sizeof(h));
+}
 inline int leap_num_partials(int N) { return N; }
 
 inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, int batched, const double* d_in, int N, int H, int K,
                        const double* d_basis, const double* d_params, double* d_states, double* d_sensors, float* d_cost, double* d_reward,
                        const PlanEpilogue& ep, cudaStream_t st, std::string* err) {
+  const int prof = getenv("B200MPC_LEAP_PROF") ? 1 : 0;
   (void)ep;  // the leap path runs the optimizer update as separate reduction kernels (b200mpc.cu)
-  size_t smem = ((sizeof(LeapWork) + 15) & ~(size_t)15) + 16 + (cost_mode ? ((size_t)K * LEAP_NU + (size_t)H * K) * sizeof(double) : 0);
+  size_t wstride = ((sizeof(LeapWork) + 15) & ~(size_t)15) + 16 + (cost_mode ? ((size_t)K * LEAP_NU + (size_t)H * K) * sizeof(double) : 0);
+  wstride = (wstride + 15) & ~(size_t)15;
+  int wpb = (N + 147) / 148;  // spread the rollouts over the 148 SMs first, then stack up to 7 warps per SM
+  if (wpb < 1) wpb = 1;
+  if (wpb > 7) wpb = 7;
+  while (wpb > 1 && wpb * wstride > 226 * 1024) wpb--;
+  const size_t smem = wpb * wstride;
   if (smem > 227 * 1024) { *err = "horizon/knots too large for the shared-memory tile"; return 1; }
+  const int grid = (N + wpb - 1) / wpb;
   cudaError_t e;
   if (cost_mode) {
     e = cudaFuncSetAttribute(leap_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) leap_rollout_kernel<true><<<N, 32, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward);
+    if (e == cudaSuccess)
+      leap_rollout_kernel<true><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, (int)wstride, prof);
   } else {
     e = cudaFuncSetAttribute(leap_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) leap_rollout_kernel<false><<<N, 32, smem, st>>>(m, d_x0, batched, d_in, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr);
+    if (e == cudaSuccess)
+      leap_rollout_kernel<false><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, (int)wstride, prof);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("leap launch: ") + cudaGetErrorString(e); return 1; }

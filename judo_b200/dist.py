@@ -37,9 +37,10 @@ def gather_partials(local, world_size: int, group=None):  # noqa: ANN001
 
     if world_size == 1:
         return local.reshape(1, -1)
-    out = torch.empty((world_size, local.numel()), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local.reshape(-1).contiguous(), group=group)
-    return out
+    flat = local.reshape(-1).contiguous()
+    out = torch.empty(world_size * flat.numel(), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    return out.view(world_size, flat.numel())
 
 
 class ShardedPlanner:

@@ -20,6 +20,8 @@
 #define MINMU 1e-5
 
 static int g_debug = 0;
+static long g_ls_evals = 0, g_newton_iters = 0, g_steps = 0;
+void mjc_get_counters(long* out) { out[0] = g_ls_evals; out[1] = g_newton_iters; out[2] = g_steps; g_ls_evals = g_newton_iters = g_steps = 0; }
 void mjc_set_debug(int v) { g_debug = v; }
 
 /* constraint row types, in MuJoCo's row order */
@@ -926,6 +928,7 @@ static void constraint_update(const mjcModel* m, mjcData* d, Solver* s, int want
 /* derivative information of the 1-D cost along the search direction at step alpha */
 static void ls_eval(const mjcModel* m, const mjcData* d, const Solver* s, double alpha, double g1, double g2,
                     double* cost, double* d1, double* d2) {
+  if (g_debug < 0) g_ls_evals++;
   double c = alpha * g1 + 0.5 * alpha * alpha * g2, p1 = g1 + alpha * g2, p2 = g2;
   for (int r = 0; r < s->nefc;) {
     int span = row_span(m, d, r), st[3];
@@ -959,7 +962,7 @@ static double line_search(const mjcModel* m, const mjcData* d, const Solver* s) 
   double gtol = m->tolerance * m->ls_tolerance * snorm * scale;
   double c0, d1, d2, lo = 0, hi = -1, dlo, dhi = 0, alpha = 0, c;
   ls_eval(m, d, s, 0, g1, g2, &c0, &d1, &d2);
-  if (g_debug) fprintf(stderr, "    ls: d1(0) %.6e d2(0) %.6e gtol %.3e\n", d1, d2, gtol);
+  if (g_debug > 0) fprintf(stderr, "    ls: d1(0) %.6e d2(0) %.6e gtol %.3e\n", d1, d2, gtol);
   if (d1 >= 0 || d2 <= 0) return 0;
   dlo = d1;
   alpha = -d1 / d2;
@@ -1043,7 +1046,8 @@ static void fwd_constraint(const mjcModel* m, mjcData* d, Solver* s) {
     }
     double alpha = line_search(m, d, s);
     d->solver_iter = it + 1;
-    if (g_debug) {
+    if (g_debug < 0) g_newton_iters++;
+    if (g_debug > 0) {
       double sg = 0; for (int i = 0; i < nv; i++) sg += s->search[i] * s->grad[i];
       fprintf(stderr, "  newton it %d cost %.12e |g| %.3e search.grad %.3e alpha %.6e\n", it, s->cost, scale * sqrt(gn), sg, alpha);
     }
@@ -1052,7 +1056,7 @@ static void fwd_constraint(const mjcModel* m, mjcData* d, Solver* s) {
     for (int i = 0; i < nv; i++) { d->qacc[i] += alpha * s->search[i]; s->Ma[i] += alpha * s->Mv[i]; }
     for (int r = 0; r < s->nefc; r++) s->jar[r] += alpha * s->jv[r];
     constraint_update(m, d, s, 1);
-    if (g_debug) fprintf(stderr, "      -> new cost %.12e improvement %.3e\n", s->cost, scale * (oldcost - s->cost));
+    if (g_debug > 0) fprintf(stderr, "      -> new cost %.12e improvement %.3e\n", s->cost, scale * (oldcost - s->cost));
     if (scale * (oldcost - s->cost) < m->tolerance) break;
   }
 }
@@ -1169,6 +1173,7 @@ int mjc_rollout(const mjcModel* m, const double* x0, int x0_batched, const doubl
         for (int t = 0; t < H; t++) {
           memcpy(d->ctrl, controls + ((size_t)n * H + t) * nu, sizeof(double) * nu);
           forward(m, d, s);
+          if (g_debug < 0) g_steps++;
           if (g_stats) {
             double* st = g_stats + ((size_t)n * H + t) * 4;
             double gn = 0;
