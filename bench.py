@@ -202,12 +202,18 @@ def main() -> None:
         return
 
     # ------------------------------------------------------------------ B200 arm
+    # libraries (NCCL's version banner, ...) may write to fd 1: park stdout on stderr until the single JSON line is printed
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
 
     if world > 1:
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
@@ -316,13 +322,17 @@ def main() -> None:
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "N independent serial recurrences: latency/issue-bound by construction, HBM fraction is expected to be <<1% "
                         "(SURVEY.md §8d); see profiles/ for occupancy and stall reasons"}
-    cpu = time_cpu(w, x0, knots, basis, params, opt, args.cpu_budget, min(n_local, 4096 if w["task"] != "leap_cube" else 256))
+    # the CPU baseline is timed on rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host cores)
+    cpu = time_cpu(w, x0, knots, basis, params, opt, args.cpu_budget, min(n_local, 4096 if w["task"] != "leap_cube" else 256)) if world == 1 else None
     out = {"metric": "rollouts/sec per control step", "value": value, "unit": "rollouts/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": config, "state_steps_per_s": value * w["H"],
            "plan_latency_p50_ms": statistics.median(step_ms), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
            "gpu_launches": int(launches), "clocks": clocks.summary(), "wall_s_timed_region": t_wall}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(_saved_stdout, 1)
+    print(json.dumps(out), flush=True)
+    os.dup2(2, 1)
     if dist is not None:
         dist.destroy_process_group()
 

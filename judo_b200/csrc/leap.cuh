@@ -1090,32 +1090,44 @@ __device__ inline double leap_line_search(const LeapModel* __restrict__ m, const
   return lo > 0 ? lo : alpha;
 }
 
-__device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, LeapWork* W, int lane, int prof) {
-  const int nefc = W->nefc;
-  if (nefc == 0) {
+// mj_fwdConstraint.  Called by ALL warps of the block; with sync_mode >= 3 the Newton iterations of the block's warps run in
+// lock-step (block barrier per iteration, finished warps idle) so that the iteration body is fetched once for all of them.
+__device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, LeapWork* W, int lane, int prof, bool active, int sync_mode) {
+  const int nefc = active ? W->nefc : 0;
+  bool done = !active;
+  if (active && nefc == 0) {
     if (lane < LEAP_NV) { W->qacc[lane] = W->qacc_smooth[lane]; W->qfrc_constraint[lane] = 0; }
     __syncwarp();
-    return;
+    done = true;
   }
-  // warm start: keep qacc_warmstart unless qacc_smooth has lower cost
-  leap_set_point(m, W, W->warm, lane);
-  leap_constraint_update(m, W, W->warm, false, lane);
-  const double cw = W->cost;
-  __syncwarp();
-  leap_set_point(m, W, W->qacc_smooth, lane);
-  leap_constraint_update(m, W, W->qacc_smooth, false, lane);
-  const double cs = W->cost;
-  __syncwarp();
-  if (lane < LEAP_NV) W->qacc[lane] = cw > cs ? W->qacc_smooth[lane] : W->warm[lane];
-  __syncwarp();
-  leap_set_point(m, W, W->qacc, lane);
-  leap_constraint_update(m, W, W->qacc, true, lane);
-  const double scale = 1.0 / (m->meaninertia * LEAP_NV);
-  const int iters = (int)m->iterations, nfl = W->nfl;
+  double scale = 0;
+  int nfl = 0;
+  if (!done) {
+    // warm start: keep qacc_warmstart unless qacc_smooth has lower cost
+    leap_set_point(m, W, W->warm, lane);
+    leap_constraint_update(m, W, W->warm, false, lane);
+    const double cw = W->cost;
+    __syncwarp();
+    leap_set_point(m, W, W->qacc_smooth, lane);
+    leap_constraint_update(m, W, W->qacc_smooth, false, lane);
+    const double cs = W->cost;
+    __syncwarp();
+    if (lane < LEAP_NV) W->qacc[lane] = cw > cs ? W->qacc_smooth[lane] : W->warm[lane];
+    __syncwarp();
+    leap_set_point(m, W, W->qacc, lane);
+    leap_constraint_update(m, W, W->qacc, true, lane);
+    scale = 1.0 / (m->meaninertia * LEAP_NV);
+    nfl = W->nfl;
+  }
+  const int iters = (int)m->iterations;
+#pragma unroll 1
   for (int it = 0; it < iters; it++) {
+    if (sync_mode >= 3) { if (!__syncthreads_or(done ? 0 : 1)) break; }
+    else if (done) break;
+    if (done) continue;
     double gn = lane < LEAP_NV ? W->grad[lane] * W->grad[lane] : 0.0;
     gn = lwsum(gn);
-    if (scale * sqrt(gn) < m->tolerance) break;
+    if (scale * sqrt(gn) < m->tolerance) { done = true; continue; }
     long long t1 = LPROF_T();
     leap_newton_direction(m, W, lane);
     LPROF_ADD(8, t1); t1 = LPROF_T();
@@ -1125,7 +1137,7 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
     const double alpha = leap_line_search(m, W, lane);
     LPROF_ADD(9, t1); t1 = LPROF_T();
     if (lane == 0 && prof) atomicAdd(&g_leap_prof[10], 1ull);
-    if (alpha == 0) break;
+    if (alpha == 0) { done = true; continue; }
     const double oldcost = W->cost;
     __syncwarp();
     if (lane < LEAP_NV) { W->qacc[lane] += alpha * W->search[lane]; W->Ma[lane] += alpha * W->Mv[lane]; }
@@ -1135,7 +1147,7 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
     LPROF_ADD(7, t1);
     const double newcost = W->cost;
     __syncwarp();
-    if (scale * (oldcost - newcost) < m->tolerance) break;
+    if (scale * (oldcost - newcost) < m->tolerance) done = true;
   }
 }
 
@@ -1143,7 +1155,7 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
 // All warps of the block call this together; `active` masks the tail warps.  The two block barriers keep the warps in
 // the same code region (see the kernel comment) — they are NOT data dependencies.
 __device__ inline void leap_step(const LeapModel* __restrict__ m, LeapWork* W, int lane, double* sens /* global, may be null */, int prof,
-                                 bool active) {
+                                 bool active, int sync_mode) {
   long long t0 = LPROF_T();
   if (active) {
     leap_kinematics(m, W, lane);
@@ -1151,7 +1163,7 @@ __device__ inline void leap_step(const LeapModel* __restrict__ m, LeapWork* W, i
     leap_mass_and_bias(m, W, lane);
     LPROF_ADD(1, t0);
   }
-  __syncthreads();
+  if (sync_mode >= 2) __syncthreads();
   t0 = LPROF_T();
   if (active) {
     leap_collision(m, W, lane);
@@ -1183,11 +1195,11 @@ __device__ inline void leap_step(const LeapModel* __restrict__ m, LeapWork* W, i
     leap_block_solve(m, W, nullptr, W->qacc_smooth, lane);
     LPROF_ADD(4, t0);
   }
-  __syncthreads();
-  if (!active) return;
+  if (sync_mode >= 2) __syncthreads();
   t0 = LPROF_T();
-  leap_fwd_constraint(m, W, lane, prof);
+  leap_fwd_constraint(m, W, lane, prof, active, sync_mode);
   __syncwarp();
+  if (!active) return;
   LPROF_ADD(5, t0); t0 = LPROF_T();
   // implicitfast: (M + h (damping + kv)) qacc = qfrc_smooth + qfrc_constraint, then semi-implicit advance
   const double h = m->dt;
@@ -1243,6 +1255,8 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
                                                            const double* __restrict__ cost_params, double* __restrict__ states,
                                                            double* __restrict__ sensors, float* __restrict__ cost_NH, double* __restrict__ reward_N,
                                                            int wstride, int prof) {
+  const int sync_mode = prof >> 8;
+  prof &= 255;
   extern __shared__ __align__(16) unsigned char lsm_all[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int n = blockIdx.x * wpb + wib;
@@ -1278,14 +1292,14 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
     double total = 0;
 #pragma unroll 1
     for (int t = 0; t < H; t++) {
-      __syncthreads();
+      if (sync_mode >= 1) __syncthreads();
       if (active && lane < LEAP_NU) {
         double u = 0;
         for (int k = 0; k < K; k++) u += sB[t * K + k] * sK[k * LEAP_NU + lane];
         W->ctrl[lane] = u;
       }
       __syncwarp();
-      leap_step(m, W, lane, nullptr, prof, active);
+      leap_step(m, W, lane, nullptr, prof, active, sync_mode);
       if (active && lane == 0) {
         double cp[LEAP_NCOST];
 #pragma unroll
@@ -1299,10 +1313,10 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
   } else {
 #pragma unroll 1
     for (int t = 0; t < H; t++) {
-      __syncthreads();
+      if (sync_mode >= 1) __syncthreads();
       if (active && lane < LEAP_NU) W->ctrl[lane] = in[((size_t)n * H + t) * LEAP_NU + lane];
       __syncwarp();
-      leap_step(m, W, lane, (sensors && active) ? sensors + ((size_t)n * H + t) * LEAP_NS : nullptr, prof, active);
+      leap_step(m, W, lane, (sensors && active) ? sensors + ((size_t)n * H + t) * LEAP_NS : nullptr, prof, active, sync_mode);
       if (!active) continue;
       double* so = states + ((size_t)n * H + t) * LEAP_NX;
       if (lane < LEAP_NQ) so[lane] = W->qpos[lane];
@@ -1345,7 +1359,8 @@ inline int leap_num_partials(int N) { return N; }
 inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, int batched, const double* d_in, int N, int H, int K,
                        const double* d_basis, const double* d_params, double* d_states, double* d_sensors, float* d_cost, double* d_reward,
                        const PlanEpilogue& ep, cudaStream_t st, std::string* err) {
-  const int prof = getenv("B200MPC_LEAP_PROF") ? 1 : 0;
+  const char* sm_env = getenv("B200MPC_LEAP_SYNC");
+  const int prof = (getenv("B200MPC_LEAP_PROF") ? 1 : 0) | ((sm_env ? atoi(sm_env) : 3) << 8);
   (void)ep;  // the leap path runs the optimizer update as separate reduction kernels (b200mpc.cu)
   size_t wstride = ((sizeof(LeapWork) + 15) & ~(size_t)15) + 16 + (cost_mode ? ((size_t)K * LEAP_NU + (size_t)H * K) * sizeof(double) : 0);
   wstride = (wstride + 15) & ~(size_t)15;
