@@ -107,7 +107,7 @@ def cpu_port_plan_step(w: dict, x0, knots, basis, params, opt, nthread: int = 0)
 
     om = cpu_port_plan_step.models.setdefault(w["task"], _oracle_model(w["task"]))
     controls = np.einsum("hk,nkj->nhj", basis, knots)
-    states, _ = om.rollout(x0, controls, nthread=nthread)
+    states, _ = om.rollout(x0, controls, nthread=nthread or (os.cpu_count() or 1))  # all host threads, explicitly
     if w["task"] == "cartpole":
         r = op.cartpole_reward(states, controls, *params)
     elif w["task"] == "cylinder_push":
