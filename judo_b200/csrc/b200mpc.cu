@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,9 @@ struct b200mpc_handle {
   void* d_work = nullptr; size_t d_work_bytes = 0;  // per-rollout scratch (leap)
   void* h_in = nullptr; size_t h_in_bytes = 0;      // pinned staging
   void* h_out = nullptr; size_t h_out_bytes = 0;
+  int zero_copy = 2;           // plan_step: bit0 = kernel READS the pinned staging buffer, bit1 = kernel WRITES results to pinned memory
+  bool zero_copy_now = false;  // set for the duration of a zero-copy plan_step
+  double t_stage = 0, t_launch = 0, t_sync = 0, t_out = 0; long long t_calls = 0; bool timing = false;  // B200MPC_TIMING=1
 };
 
 #define CK(call)                                                                                   \
@@ -95,12 +99,17 @@ extern "C" int b200mpc_create(b200mpc_handle** out, int task_id, const double* c
 #endif
   } else return bad("unknown task id");
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bad("cudaStreamCreate failed");
+  if (const char* z = getenv("B200MPC_ZEROCOPY")) h->zero_copy = atoi(z);
+  h->timing = getenv("B200MPC_TIMING") != nullptr;
   *out = h;
   return 0;
 }
 
 extern "C" void b200mpc_destroy(b200mpc_handle* h) {
   if (!h) return;
+  if (h->timing && h->t_calls)
+    fprintf(stderr, "b200mpc plan_step host timing over %lld calls (us): stage %.1f launch %.1f sync(wait for GPU) %.1f copy-out %.1f\n", h->t_calls,
+            h->t_stage / h->t_calls, h->t_launch / h->t_calls, h->t_sync / h->t_calls, h->t_out / h->t_calls);
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work);
@@ -422,7 +431,7 @@ static int stage_inputs(b200mpc_handle* h, const double* x0, const double* basis
   memcpy(hp + *obasis, basis, (size_t)H * K * 8);
   memcpy(hp + *oparams, params, (size_t)np * 8);
   memcpy(hp + *oknots, knots, (size_t)N * K * nu * 8);
-  CK(cudaMemcpyAsync(h->d_in, h->h_in, o, cudaMemcpyHostToDevice, h->stream));
+  if (!h->zero_copy_now) CK(cudaMemcpyAsync(h->d_in, h->h_in, o, cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
 
@@ -525,15 +534,26 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
   if (optimizer < 0 || optimizer > 2) return fail(h, "unknown optimizer");
   CK(cudaSetDevice(h->device));
   const int KNU = K * h->dims.nu;
+  int k_cem = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 0;
+  // Zero-copy outputs (default): the fused kernel writes nominal/sigma/elite/rewards straight into pinned host memory, so the
+  // step is ONE H2D copy + ONE launch.  Zero-copy inputs (bit0) make the kernel pull the candidates over PCIe itself (slower).
+  const bool fusable = std::max(n_elite, k_cem) <= EP_MAXK;
+  const bool zc_in = (h->zero_copy & 1) && fusable, zc = (h->zero_copy & 2) && fusable;  // zc: outputs
+  h->zero_copy_now = zc_in;
+  auto T0 = std::chrono::steady_clock::now();
   size_t ox0, ob, op, ok;
-  if (stage_inputs(h, x0, basis, H, K, params, knots, N, &ox0, &ob, &op, &ok)) return 1;
+  int rc_stage = stage_inputs(h, x0, basis, H, K, params, knots, N, &ox0, &ob, &op, &ok);
+  h->zero_copy_now = false;
+  if (rc_stage) return 1;
   // packed outputs: [nominal KNU | sigma KNU | elite n_elite | reward N]
   size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_rw = o_el + al16((size_t)std::max(n_elite, 1) * 8);
   size_t out_bytes = o_rw + (size_t)N * 8;
   if (grow(h, &h->d_out, &h->d_out_bytes, out_bytes, false) || grow(h, &h->h_out, &h->h_out_bytes, out_bytes, true)) return 1;
   char* din = (char*)h->d_in; char* dout = (char*)h->d_out;
+  if (zc_in) { void* p = nullptr; CK(cudaHostGetDevicePointer(&p, h->h_in, 0)); din = (char*)p; }
+  if (zc) { void* p = nullptr; CK(cudaHostGetDevicePointer(&p, h->h_out, 0)); dout = (char*)p; }
   double* d_reward = (double*)(dout + o_rw);
-  int k_cem = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 0;
+  auto T1 = std::chrono::steady_clock::now();
   if (std::max(n_elite, k_cem) <= EP_MAXK) {
     // one launch: rollout + cost + optimizer update + elite list
     if (b200mpc_plan_step_dev(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), optimizer,
@@ -563,12 +583,19 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
     }
   }
   size_t copy_bytes = reward_N ? out_bytes : o_rw;
-  CK(cudaMemcpyAsync(h->h_out, h->d_out, copy_bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (!zc) CK(cudaMemcpyAsync(h->h_out, h->d_out, copy_bytes, cudaMemcpyDeviceToHost, h->stream));
+  auto T2 = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(h->stream));
+  auto T3 = std::chrono::steady_clock::now();
   const char* ho = (const char*)h->h_out;
   memcpy(nominal, ho + o_nom, (size_t)KNU * 8);
   if (sigma && optimizer == B200MPC_OPT_CEM) memcpy(sigma, ho + o_sig, (size_t)KNU * 8);
   if (elite_idx) for (int i = 0; i < n_elite; i++) elite_idx[i] = (int)((const double*)(ho + o_el))[i];
   if (reward_N) memcpy(reward_N, ho + o_rw, (size_t)N * 8);
+  if (h->timing) {
+    auto T4 = std::chrono::steady_clock::now();
+    auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    h->t_stage += us(T0, T1); h->t_launch += us(T1, T2); h->t_sync += us(T2, T3); h->t_out += us(T3, T4); h->t_calls++;
+  }
   return 0;
 }

@@ -98,23 +98,40 @@ __device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KN
   }
   if (ep.k > 0 || ep.optimizer == EP_PS) {
     const int k = ep.k, slots = k + 1;
-    // global top-k (descending; ties: higher index first) over nparts*k candidates
-    double prev_r = INFINITY; long long prev_i = -1; bool have_prev = false;
-    double er[EP_MAXK]; long long ei[EP_MAXK];
-    int ne = 0;
-    for (int e = 0; e < k; e++) {
-      double br = -INFINITY; long long bi = -1;
-      for (int cnd = lane; cnd < nparts * k; cnd += 32) {
-        const double* q = ep.warp_topk + ((size_t)(cnd / k) * slots + (cnd % k)) * 2;
-        double r = __ldcg(q); long long i = (long long)__ldcg(q + 1);
-        if (i < 0) continue;
-        if (have_prev && !better(prev_r, prev_i, r, i, true)) continue;
-        if (better(r, i, br, bi, true)) { br = r; bi = i; }
+    // global top-k (descending; ties: higher index first) over nparts*k candidates.  Each lane streams its share of the
+    // candidates (independent L2 loads) through a register-resident sorted list, then k warp-wide pops merge the 32 lists.
+    double lr[EP_MAXK]; long long li[EP_MAXK];
+#pragma unroll
+    for (int e = 0; e < EP_MAXK; e++) { lr[e] = -INFINITY; li[e] = -1; }
+    const int ncand = nparts * k;
+    for (int cnd = lane; cnd < ncand; cnd += 32) {
+      const int pidx = cnd / k, slot = cnd - pidx * k;
+      const double* q = ep.warp_topk + ((size_t)pidx * slots + slot) * 2;
+      double r = __ldcg(q); long long i = (long long)__ldcg(q + 1);
+      if (i < 0) continue;
+#pragma unroll
+      for (int e = 0; e < EP_MAXK; e++) {  // insertion: carry the displaced entry down the list
+        if (better(r, i, lr[e], li[e], true)) { const double tr = lr[e]; const long long ti = li[e]; lr[e] = r; li[e] = i; r = tr; i = ti; }
       }
-      warp_best(br, bi, true);
-      if (bi < 0) break;
-      er[e] = br; ei[e] = bi; ne = e + 1;
-      prev_r = br; prev_i = bi; have_prev = true;
+    }
+    double er[EP_MAXK]; long long ei[EP_MAXK];
+#pragma unroll
+    for (int e = 0; e < EP_MAXK; e++) { er[e] = -INFINITY; ei[e] = -1; }
+    int ne = 0;
+#pragma unroll
+    for (int e = 0; e < EP_MAXK; e++) {
+      if (e < k) {
+        double br = lr[0]; long long bi = li[0];
+        warp_best(br, bi, true);
+        if (bi >= 0) {
+          er[e] = br; ei[e] = bi; ne = e + 1;
+          if (li[0] == bi) {  // my head won: pop it
+#pragma unroll
+            for (int t = 0; t + 1 < EP_MAXK; t++) { lr[t] = lr[t + 1]; li[t] = li[t + 1]; }
+            lr[EP_MAXK - 1] = -INFINITY; li[EP_MAXK - 1] = -1;
+          }
+        }
+      }
     }
     // PS: first maximum (ties -> lower index)
     double pr = -INFINITY; long long pi = -1;
