@@ -287,7 +287,7 @@ extern "C" int b200mpc_plan_step_dev(b200mpc_handle* h, const double* d_x0, cons
       if (run_update(h, optimizer, opt_params, d_knots, d_reward, N, KNU, d_nominal, d_sigma, nullptr, 0, st)) return 1;
       if (n_elite > 0 && d_elite) {
         int nb = n_partials_for(N);
-        size_t need = (size_t)nb * n_elite * (2 + KNU) * 8 + al16((size_t)KNU * 8);
+        size_t need = 16 + (size_t)nb * n_elite * (2 + KNU) * 8 + al16((size_t)KNU * 8);  // 16: the ticket slot in front
         if (need > h->d_part_bytes) { CK(cudaStreamSynchronize(st)); if (grow(h, &h->d_part, &h->d_part_bytes, need, false)) return 1; CK(cudaMemsetAsync(h->d_part, 0, 16, st)); }
         double* part = (double*)h->d_part + 2;
         double* dummy = part + (size_t)nb * n_elite * (2 + KNU);
