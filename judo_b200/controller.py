@@ -39,6 +39,7 @@ class ControllerConfig(OverridableConfig):
 set_config_overrides("cylinder_push", ControllerConfig, {"horizon": 1.0, "spline_order": "zero"})
 set_config_overrides("cartpole", ControllerConfig, {"horizon": 1.0, "spline_order": "zero"})
 set_config_overrides("leap_cube", ControllerConfig, {"horizon": 1.0, "spline_order": "cubic", "max_num_traces": 1})
+set_config_overrides("leap_cube_down", ControllerConfig, {"horizon": 1.0, "spline_order": "cubic", "max_num_traces": 1})
 
 
 class Spline:

@@ -21,6 +21,11 @@ set_config_overrides("leap_cube", PredictiveSamplingConfig, dict(_COMMON, noise_
 set_config_overrides("leap_cube", CrossEntropyMethodConfig, dict(_COMMON, num_elites=3, noise_ramp=4.0))
 set_config_overrides("leap_cube", MPPIConfig, dict(_COMMON, noise_ramp=4.0, sigma=0.2, temperature=0.0025))
 
+# overrides.py:112-146
+set_config_overrides("leap_cube_down", PredictiveSamplingConfig, dict(_COMMON, noise_ramp=4.0, sigma=0.2))
+set_config_overrides("leap_cube_down", CrossEntropyMethodConfig, dict(_COMMON, num_rollouts=64, num_elites=3, noise_ramp=4.0))
+set_config_overrides("leap_cube_down", MPPIConfig, dict(_COMMON, num_rollouts=64, noise_ramp=4.0, sigma=0.2, temperature=0.0025))
+
 _registered_optimizers: dict[str, tuple[Type[Optimizer], Type[OptimizerConfig]]] = {
     "cem": (CrossEntropyMethod, CrossEntropyMethodConfig),
     "mppi": (MPPI, MPPIConfig),

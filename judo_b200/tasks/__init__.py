@@ -14,9 +14,10 @@ _registered_tasks: Dict[str, Tuple[Type[Task], Type[TaskConfig]]] = {
 }
 
 try:  # the leap task registers itself once its kernel is in the library
-    from judo_b200.tasks.leap_cube import LeapCube, LeapCubeConfig
+    from judo_b200.tasks.leap_cube import LeapCube, LeapCubeConfig, LeapCubeDown, LeapCubeDownConfig
 
     _registered_tasks[LeapCube.name] = (LeapCube, LeapCubeConfig)
+    _registered_tasks[LeapCubeDown.name] = (LeapCubeDown, LeapCubeDownConfig)
 except ImportError:
     pass
 

@@ -57,12 +57,16 @@ class LeapCube(Task[LeapCubeConfig]):
     name = "leap_cube"
     config_t = LeapCubeConfig
 
+    model_table = "leap_cube"
+    home = QPOS_HOME
+    default_goal_pos = (0.0, 0.03, 0.1)
+
     def __init__(self) -> None:
-        super().__init__("leap_cube")
-        self.goal_pos = np.array([0.0, 0.03, 0.1])
+        super().__init__(self.model_table)
+        self.goal_pos = np.array(self.default_goal_pos)
         self.goal_quat = np.array([1.0, 0.0, 0.0, 0.0])
-        self.qpos_home = QPOS_HOME
-        self.reset_command = QPOS_HOME[7:].copy()
+        self.qpos_home = self.home
+        self.reset_command = self.home[7:].copy()
         self.reset()
 
     def cost_params(self, system_metadata: dict[str, Any] | None = None) -> np.ndarray:
@@ -104,6 +108,34 @@ class LeapCube(Task[LeapCubeConfig]):
 
     def get_sim_metadata(self) -> dict[str, Any]:
         return {"goal_quat": self.goal_quat}
+
+
+
+QPOS_HOME_DOWN = np.array([
+    -0.04, -0.035, -0.065, 1.0, 0.0, 0.0, 0.0,  # cube
+    1.0, 0.0, 0.8, 0.8,  # index
+    1.0, 0.0, 0.8, 0.8,  # middle
+    1.0, 0.0, 0.8, 0.8,  # ring
+    1.0, 1.0, 0.4, 0.9,  # thumb
+])  # judo/tasks/leap_cube_down.py:13-21
+
+
+@dataclass
+class LeapCubeDownConfig(LeapCubeConfig):
+    """judo/tasks/leap_cube_down.py:24-30."""
+
+    w_rot: float = 0.05
+
+
+class LeapCubeDown(LeapCube):
+    """LEAP cube rotation with the palm facing down — mirror of judo/tasks/leap_cube_down.py:33-53.  Same kernel and reduced
+    collision model, constants from leap_cube_palm_down.xml (hand frame un-tilted), its own home pose / goal position."""
+
+    name = "leap_cube_down"
+    config_t = LeapCubeDownConfig
+    model_table = "leap_cube_down"
+    home = QPOS_HOME_DOWN
+    default_goal_pos = (-0.04, -0.035, -0.065)
 
 
 # ------------------------------------------------------------------------------------------ constant table

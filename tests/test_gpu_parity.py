@@ -411,3 +411,24 @@ def test_leap_rewards_match_reference_golden(engines, golden):
     t.engine = engines("leap_cube", 6)
     np.testing.assert_allclose(t.reward(g["leap_states"], None, None, {}), g["leap_rewards_default_goal"], rtol=1e-12)
     np.testing.assert_allclose(t.reward(g["leap_states"], None, None, {"goal_quat": g["leap_goal_quat"]}), g["leap_rewards"], rtol=1e-12)
+
+
+def test_leap_cube_down_variant_matches_oracle(engines):
+    """the palm-down variant is the same kernel with the constant table of leap_cube_palm_down.xml."""
+    from judo_b200.tasks.leap_cube import QPOS_HOME_DOWN, LeapCubeDown, reduced_collision_model
+    from oracle.mjc import load_table
+
+    tb = load_table("leap_cube_down")
+    geoms, pairs = reduced_collision_model(tb)
+    om = OracleModel(tb, pairs=pairs, geoms=geoms)
+    rng = np.random.default_rng(9)
+    N, H = 16, 20
+    eng = engines("leap_cube_down", N)
+    x0 = np.concatenate([QPOS_HOME_DOWN, np.zeros(22)])
+    controls = QPOS_HOME_DOWN[7:] + 0.4 * rng.normal(size=(N, 1, 16)) * np.linspace(0.3, 1, H)[None, :, None]
+    s, e = eng.rollout(x0, controls)
+    s_ref, e_ref = om.rollout(x0, controls)
+    np.testing.assert_allclose(s, s_ref, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(e, e_ref, rtol=0, atol=1e-7)
+    t = LeapCubeDown()
+    assert t.config.w_rot == 0.05 and t.name == "leap_cube_down" and np.allclose(t.goal_pos, [-0.04, -0.035, -0.065])
