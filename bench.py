@@ -315,10 +315,15 @@ def main() -> None:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     algo_bytes = w["algo_bytes_per_rollout"] * n_local
+    traffic = None
+    try:  # measured once per round with `ncu --set full` (a number taken under the profiler is never a bench value; this is bytes, not time)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+    except Exception:  # noqa: BLE001
+        pass
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
-                "kernel": "rollout_kernel<Task, COST> (fused spline+dynamics+cost)", "kernel_ms": kernel_ms,
+                "kernel": ("leap_rollout_kernel<COST>" if w["task"].startswith("leap") else "rollout_kernel<Task, COST, MAXK>") + " (fused spline+dynamics+cost)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "N independent serial recurrences: latency/issue-bound by construction, HBM fraction is expected to be <<1% "
                         "(SURVEY.md §8d); see profiles/ for occupancy and stall reasons"}
