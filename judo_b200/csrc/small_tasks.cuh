@@ -126,11 +126,13 @@ struct CylinderPushConsts {
 struct CylinderPushTask {
   static constexpr int NQ = 4, NV = 4, NU = 2, NS = 6, NX = 8, NCOST = 6;
   using Consts = CylinderPushConsts;
-  struct State { double q[4], v[4], warm[4]; };
+  // im / ia: reciprocals of the (diagonal) mass matrix and of M + h*damping, computed once per rollout (ready < 0: not yet)
+  struct State { double q[4], v[4], warm[4], im[4], ia[4]; bool ready; };
 
   __device__ static inline void load(State& s, const double* x) {
 #pragma unroll
     for (int i = 0; i < 4; i++) { s.q[i] = x[i]; s.v[i] = x[4 + i]; s.warm[i] = 0; }
+    s.ready = false;
   }
   __device__ static inline void store(const State& s, double* x) {
 #pragma unroll
@@ -143,6 +145,11 @@ struct CylinderPushTask {
       sens[3] = s.q[2] + c.site_cart[0]; sens[4] = s.q[3] + c.site_cart[1]; sens[5] = c.site_cart[2];
     }
     const double h = c.dt;
+    if (!s.ready) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) { const double mi = i < 2 ? c.mass_pusher : c.mass_cart; s.im[i] = 1.0 / mi; s.ia[i] = 1.0 / (mi + h * c.damp[i]); }
+      s.ready = true;
+    }
     // smooth forces: damping + position servos on the pusher; gravity does no work on the slides; M is diagonal
     double qfs[4], mass[4] = {c.mass_pusher, c.mass_pusher, c.mass_cart, c.mass_cart};
 #pragma unroll
@@ -157,7 +164,7 @@ struct CylinderPushTask {
     }
     double qas[4], qfc[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < 4; i++) qas[i] = qfs[i] / mass[i];  // constant divisors: folded to reciprocal constants' cost
+    for (int i = 0; i < 4; i++) qas[i] = qfs[i] * s.im[i];
     // collision: two upright discs; normal from geom1 (pusher) to geom2 (cart).  Squared test first: no sqrt off-contact
     const double dx = s.q[2] - s.q[0], dy = s.q[3] - s.q[1];
     const double includemargin = c.margin - c.gap, rsum = c.r_pusher + c.r_cart;
@@ -221,7 +228,7 @@ struct CylinderPushTask {
     // mj_Euler with implicit joint damping (diagonal system), then semi-implicit advance
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const double qa = (qfs[i] + qfc[i]) / (mass[i] + h * c.damp[i]);
+      const double qa = (qfs[i] + qfc[i]) * s.ia[i];
       s.v[i] += h * qa;
       s.q[i] += h * s.v[i];
     }
@@ -230,8 +237,8 @@ struct CylinderPushTask {
   // cost params: [w_pusher_proximity, w_pusher_velocity, w_cart_position, pusher_goal_offset, goal_x, goal_y]
   __device__ static inline double cost(const double* p, const State& s, const double* u) {
     double gx = p[4] - s.q[2], gy = p[5] - s.q[3];
-    double gn = sqrt(gx * gx + gy * gy);  // no epsilon (cylinder_push.py:76-77)
-    double pgx = s.q[2] - p[3] * (gx / gn), pgy = s.q[3] - p[3] * (gy / gn);
+    const double ign = 1.0 / sqrt(gx * gx + gy * gy);  // no epsilon (cylinder_push.py:76-77): inf/nan at the goal, as numpy
+    double pgx = s.q[2] - p[3] * (gx * ign), pgy = s.q[3] - p[3] * (gy * ign);
     double ex = s.q[0] - pgx, ey = s.q[1] - pgy;
     double prox = 0.5 * (ex * ex + ey * ey);
     double vel = 0.5 * (s.v[0] * s.v[0] + s.v[1] * s.v[1]);

@@ -1,0 +1,103 @@
+"""CPU: physical sanity of the restated dynamics (oracle/mjc).  The oracle cannot be pinned to MuJoCo binaries (absent), so
+these tests pin it to closed-form physics instead: free fall, energy conservation, Newton's third law in contacts, static
+equilibrium on the palm, soft joint limits, actuator clamps."""
+import copy
+
+import numpy as np
+
+from oracle.mjc import OracleModel, load_table
+
+
+def _leap():
+    from judo_b200.tasks.leap_cube import QPOS_HOME, reduced_collision_model
+
+    tb = load_table("leap_cube")
+    geoms, pairs = reduced_collision_model(tb)
+    return OracleModel(tb, pairs=pairs, geoms=geoms), tb, QPOS_HOME
+
+
+def test_free_fall_is_the_semi_implicit_euler_parabola():
+    om, tb, home = _leap()
+    q = home.copy()
+    q[:3] = [0.5, 0.5, 1.0]  # far from the hand: no contacts
+    H, h, g = 30, tb["opt"]["timestep"], 9.81
+    s, _ = om.rollout(np.concatenate([q, np.zeros(22)]), np.tile(home[7:], (1, H, 1)))
+    k = np.arange(1, H + 1)
+    np.testing.assert_allclose(s[0, :, 2], 1.0 - g * h * h * k * (k + 1) / 2, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(s[0, :, 23 + 2], -g * h * k, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(s[0, :, 3:7], np.tile([1, 0, 0, 0], (H, 1)), atol=1e-15)  # no spurious rotation
+
+
+def test_spinning_free_cube_keeps_angular_momentum():
+    om, tb, home = _leap()
+    q = home.copy()
+    q[:3] = [0.5, 0.5, 1.0]
+    v = np.zeros(22)
+    v[3:6] = [3.0, -2.0, 1.0]  # isotropic inertia: body angular velocity stays constant
+    s, _ = om.rollout(np.concatenate([q, v]), np.tile(home[7:], (1, 50, 1)))
+    np.testing.assert_allclose(s[0, :, 23 + 3:23 + 6], np.tile(v[3:6], (50, 1)), atol=1e-12)
+    np.testing.assert_allclose(np.linalg.norm(s[0, :, 3:7], axis=1), 1.0, atol=1e-14)
+    # rotation angle after 50 steps = |w| * t
+    ang = 2 * np.arccos(np.clip(abs(s[0, -1, 3]), 0, 1))
+    expected = np.linalg.norm(v[3:6]) * 50 * tb["opt"]["timestep"]
+    assert abs(ang - (expected % (2 * np.pi))) < 1e-9 or abs(2 * np.pi - ang - (expected % (2 * np.pi))) < 1e-9
+
+
+def test_cartpole_energy_is_conserved_without_damping_and_actuation():
+    tb = copy.deepcopy(load_table("cartpole"))
+    tb["opt"]["timestep"] = 0.001
+    for d in tb["dofs"]:
+        d["damping"] = 0.0
+    tb["joints"][0]["damping"] = 0.0
+    tb["actuators"][0]["kp"] = 0.0
+    tb["joints"][0]["limited"] = False
+    om = OracleModel(tb)
+    x0 = np.array([0.0, 2.5, 0.3, -0.5])
+    s, _ = om.rollout(x0, np.zeros((1, 2000, 1)))
+    mc, mp, l, I = tb["bodies"][1]["mass"], tb["bodies"][2]["mass"], tb["bodies"][2]["ipos"][2], tb["bodies"][2]["inertia"][1]
+
+    def energy(x):
+        q0, th, v0, w = x[..., 0], x[..., 1], x[..., 2], x[..., 3]
+        T = 0.5 * (mc + mp) * v0**2 + mp * l * np.cos(th) * v0 * w + 0.5 * (I + mp * l * l) * w**2
+        return T + mp * 9.81 * l * np.cos(th)
+
+    e = energy(np.vstack([x0, s[0]]))
+    assert np.abs(e - e[0]).max() < 2e-3 * abs(e[0])  # first-order integrator, h = 1 ms: small bounded drift
+
+
+def test_contact_forces_obey_newtons_third_law():
+    om = OracleModel("cylinder_push")
+    f = om.forward(np.array([-0.45, 0.02, 0.0, 0.0]), np.array([1.0, 0.0, 0.0, 0.0]), np.zeros(2))
+    fc = f["qfrc_constraint"]
+    assert f["ncon"] == 1 and f["contact_dist"][0] < 0
+    np.testing.assert_allclose(fc[0:2] + fc[2:4], 0, atol=1e-9)      # equal and opposite
+    n = np.array([0.45, -0.02]) / np.hypot(0.45, 0.02)                 # pusher -> cart
+    assert fc[2:4] @ n > 0 and abs(fc[2] * n[1] - fc[3] * n[0]) < 1e-3 * (fc[2:4] @ n)  # repulsive, along the normal (mu = 1e-5)
+
+
+def test_cube_rests_on_the_hand_in_static_equilibrium():
+    om, tb, home = _leap()
+    H = 300
+    s, _ = om.rollout(np.concatenate([home, np.zeros(22)]), np.tile(home[7:], (1, H, 1)))
+    assert np.abs(s[0, -1, 23:29]).max() < 0.05 and 0.03 < s[0, -1, 2] < 0.1   # settled on the palm/fingers
+    f = om.forward(s[0, -1, :23], s[0, -1, 23:], home[7:])
+    assert f["ncon"] >= 3
+    mg = tb["bodies"][2]["mass"] * 9.81
+    assert abs(f["qfrc_constraint"][2] - mg) < 0.1 * mg                         # contacts carry the weight
+    assert np.all(f["contact_dist"] < 0) and np.all(f["contact_dist"] > -2e-3)  # soft contact: sub-2-mm penetration
+
+
+def test_joint_limit_and_clamps():
+    tb = load_table("leap_cube")
+    om, _, home = _leap()
+    lo = np.array([a["ctrlrange"][0] for a in tb["actuators"]])
+    hi = np.array([a["ctrlrange"][1] for a in tb["actuators"]])
+    q = home.copy()
+    q[:3] = [0.5, 0.5, 1.0]
+    x0 = np.concatenate([q, np.zeros(22)])
+    far = np.tile(hi + 5.0, (1, 150, 1))      # commands far beyond ctrlrange are clamped (mj_fwdActuation)
+    edge = np.tile(hi, (1, 150, 1))
+    np.testing.assert_array_equal(om.rollout(x0, far)[0], om.rollout(x0, edge)[0])
+    s = om.rollout(x0, edge)[0]
+    jr = np.array([j["range"] for j in tb["joints"][1:]])
+    assert np.all(s[0, -1, 7:23] < jr[:, 1] + 0.02) and np.all(s[0, -1, 7:23] > lo - 0.3)   # soft limits hold the joints
