@@ -303,6 +303,27 @@ def main() -> None:
            "plan_latency_p50_ms": float(e2e_tt[1]) * 1e3,
            "note": "Engine.plan_step per rank with host buffers; multi-GPU e2e = independent per-rank plans (no exchange on the host path)"}
 
+    # ---- e2e in perf mode: candidates drawn on the device (Philox), only the nominal crosses PCIe on the way in
+    sig = opt.device_sigma()
+    lo_c, hi_c = task.actuator_ctrlrange[:, 0], task.actuator_ctrlrange[:, 1]
+    nominal0 = np.tile(task.optimizer_warm_start(), (w["K"], 1))
+    ds_times = []
+    for i in range(max(args.warmup, 3) + args.steps):
+        t1 = time.perf_counter()
+        res_ds = eng.plan_step_sampled(x0, nominal0, sig, lo_c, hi_c, n_local, basis, params, w["optimizer"], opt_params, seed=42, counter=i,
+                                       index_offset=lo, want_rewards=True, n_elite=5)
+        ds_times.append(time.perf_counter() - t1)
+    ds_times = ds_times[max(args.warmup, 3):]
+    ds_tt = torch.tensor([sum(ds_times), statistics.median(ds_times)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(ds_tt, op=dist.ReduceOp.MAX)
+    ds_ms = float(ds_tt[0]) / args.steps * 1e3
+    e2e["device_sampling"] = {"value": n_total / (ds_ms * 1e-3), "unit": "rollouts/s", "plan_latency_p50_ms": float(ds_tt[1]) * 1e3,
+                              "h2d_bytes_per_step": int(x0.nbytes + basis.nbytes + params.nbytes + 2 * nominal0.nbytes + 2 * lo_c.nbytes),
+                              "d2h_bytes_per_step": int(2 * nominal0.nbytes + 5 * 8 + 5 * nominal0.nbytes + n_local * 8),
+                              "note": "Engine.plan_step_sampled: Philox sampling + clip inside the rollout kernel (same distribution as the "
+                                      "reference's np.random.randn, different stream)"}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -90,6 +90,20 @@ int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const double* knots, 
                       const double* cost_params, int optimizer, const double* opt_params, double* nominal, double* sigma,
                       double* reward_N, int* elite_idx, int n_elite);
 
+/* ---- fused plan step with ON-DEVICE sampling (perf mode) -------------------------------------------------------------
+ * Replaces sample_control_knots + clip + the loop body (judo/optimizers/{mppi.py:38-59,cem.py:55-74,ps.py:29-50},
+ * judo/controller/controller.py:252-288): candidates = clip(nominal + sigma * N(0,1), lo, hi), row 0 = the nominal, drawn inside
+ * the rollout kernel with a counter-based Philox4x32-10 keyed by (seed, counter, global rollout index) — same distribution as the
+ * reference, NOT NumPy's MT19937 stream (use b200mpc_plan_step with host-sampled knots for seed parity).
+ *   nominal_in, sigma_in (K,nu); lo, hi (nu) clip range (+-inf allowed); index_offset: global index of rollout 0 of this call.
+ *   OUT: nominal (K,nu), sigma (CEM), reward_N (N, may be NULL), elite_idx / elite_knots (n_elite best candidates, may be NULL),
+ *        knots_out (N,K,nu) all generated candidates (may be NULL: they then never leave the GPU). */
+int b200mpc_plan_step_sampled(b200mpc_handle* h, const double* x0, const double* nominal_in, const double* sigma_in,
+                              const double* lo, const double* hi, int N, int K, const double* basis, int H,
+                              const double* cost_params, int optimizer, const double* opt_params, unsigned long long seed,
+                              unsigned long long counter, int index_offset, double* nominal, double* sigma, double* reward_N,
+                              int* elite_idx, int n_elite, double* elite_knots, double* knots_out);
+
 /* ---- resident (device-pointer) API: inputs/outputs already in HBM, asynchronous on `stream` ------------------------
  * Used by bench.py's device-resident measurement and by the multi-GPU sharded plan step (judo_b200/dist.py), where
  * torch owns the allocations and NCCL moves the partials.  All pointers are device pointers; stream is a

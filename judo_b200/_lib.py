@@ -36,6 +36,8 @@ SIGNATURES = {
     "b200mpc_update_cem": (_i, [_vp, _dp, _dp, _i, _i, _i, _d, _d, _dp, _dp]),
     "b200mpc_update_ps": (_i, [_vp, _dp, _dp, _i, _i, _dp]),
     "b200mpc_plan_step": (_i, [_vp, _dp, _dp, _i, _i, _dp, _i, _dp, _i, _dp, _dp, _dp, _dp, _ip, _i]),
+    "b200mpc_plan_step_sampled": (_i, [_vp, _dp, _dp, _dp, _dp, _dp, _i, _i, _dp, _i, _dp, _i, _dp, ctypes.c_ulonglong, ctypes.c_ulonglong, _i,
+                                       _dp, _dp, _dp, _ip, _i, _dp, _dp]),
     "b200mpc_plan_costs_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "b200mpc_plan_step_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _dp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200mpc_rollout_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),

@@ -90,6 +90,11 @@ class Controller:
         self.sensor_rollout_size = self.num_timesteps - 1
         self.all_traces_rollout_size = self.sensor_rollout_size * self.num_trace_sensors
         self.fused = True  # set False to force the contract-A path (rollout + Task.reward + optimizer update)
+        # "host": np.random.randn exactly as the reference (seed parity).  "device": Philox inside the rollout kernel (perf mode:
+        # same distribution, nothing but the nominal crosses PCIe; candidate_knots then holds only the elite candidates).
+        self.sampling: Literal["host", "device"] = "host"
+        self.device_seed = 0
+        self._plan_counter = 0
 
     # ---- config views (controller.py:109-208) ----------------------------------------------------------------
     horizon = property(lambda self: self.controller_cfg.horizon)
@@ -180,6 +185,23 @@ class Controller:
         self._rollout_cache_valid = False
         i = 0
         while i < self.max_opt_iters and not self.optimizer.stop_cond():
+            if self.sampling == "device" and self._can_fuse() and isinstance(self.action_normalizer, IdentityNormalizer):
+                self.task.pre_rollout(self.current_state)
+                ne = min(self.max_num_traces, self.optimizer_cfg.num_rollouts)
+                res = self.engine.plan_step_sampled(self.current_state, nominal_knots_normalized, self.optimizer.device_sigma(), lo, hi,
+                                                    self.optimizer_cfg.num_rollouts, basis, self.task.cost_params(self.system_metadata),
+                                                    self.optimizer.name, self.optimizer.fused_params(), self.device_seed, self._plan_counter,
+                                                    want_rewards=True, n_elite=ne)
+                self._plan_counter += 1
+                self.rewards = res["rewards"]
+                self.candidate_knots = res["elite_knots"]       # only the elite candidates leave the GPU
+                self._elite = np.arange(len(res["elite"]))       # ... so they are rows 0..ne-1 of candidate_knots
+                self.elite_indices_global = res["elite"]
+                nominal_knots_normalized = self.optimizer.accept_fused(res)
+                self._basis = basis
+                self._rollout_cache_valid = False
+                i += 1
+                continue
             cand_norm = np.clip(self.optimizer.sample_control_knots(nominal_knots_normalized), lo, hi)
             self.candidate_knots = self.action_normalizer.denormalize(cand_norm)
             self.task.pre_rollout(self.current_state)

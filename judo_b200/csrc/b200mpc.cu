@@ -140,7 +140,8 @@ static int launch_rollout(b200mpc_handle* h, const typename Task::Consts& c, con
   int thr = pick_threads(N), grid = (N + thr - 1) / thr;
   PlanEpilogue ep{};
   ep.optimizer = EP_NONE;
-  rollout_kernel<Task, false, 1><<<grid, thr, 0, st>>>(c, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, ep);
+  SampleSpec nos{};
+  rollout_kernel<Task, false, 1><<<grid, thr, 0, st>>>(c, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, ep, nos);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -149,7 +150,7 @@ static int launch_rollout(b200mpc_handle* h, const typename Task::Consts& c, con
 template <class Task, int MAXK>
 static int launch_costs_k(b200mpc_handle* h, const typename Task::Consts& c, const double* d_x0, const double* d_knots, int N, int K,
                           const double* d_basis, int H, const double* d_params, float* d_cost, double* d_reward, const PlanEpilogue& ep,
-                          cudaStream_t st) {
+                          const SampleSpec& smp, cudaStream_t st) {
   int thr = pick_threads(N), grid = (N + thr - 1) / thr;
   size_t smem = rollout_cost_smem<Task>(thr, H, K, d_cost != nullptr);
   auto kern = rollout_kernel<Task, true, MAXK>;
@@ -157,7 +158,7 @@ static int launch_costs_k(b200mpc_handle* h, const typename Task::Consts& c, con
     if (smem > 227 * 1024) return fail(h, "horizon/knots too large for the shared-memory tile");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  kern<<<grid, thr, smem, st>>>(c, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep);
+  kern<<<grid, thr, smem, st>>>(c, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep, smp);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -165,10 +166,10 @@ static int launch_costs_k(b200mpc_handle* h, const typename Task::Consts& c, con
 template <class Task>
 static int launch_costs(b200mpc_handle* h, const typename Task::Consts& c, const double* d_x0, const double* d_knots, int N, int K,
                         const double* d_basis, int H, const double* d_params, float* d_cost, double* d_reward, const PlanEpilogue& ep,
-                        cudaStream_t st) {
-  if (K <= 4) return launch_costs_k<Task, 4>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
-  if (K <= 8) return launch_costs_k<Task, 8>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
-  if (K <= 12) return launch_costs_k<Task, 12>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
+                        const SampleSpec& smp, cudaStream_t st) {
+  if (K <= 4) return launch_costs_k<Task, 4>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, smp, st);
+  if (K <= 8) return launch_costs_k<Task, 8>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, smp, st);
+  if (K <= 12) return launch_costs_k<Task, 12>(h, c, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, smp, st);
   return fail(h, "num_nodes > 12 not supported (reference slider range is 3..12, optimizers/base.py:13)");
 }
 
@@ -185,7 +186,7 @@ extern "C" int b200mpc_rollout_dev(b200mpc_handle* h, const double* d_x0, int ba
     case B200MPC_TASK_LEAP_CUBE: {
       PlanEpilogue none{};
       none.optimizer = EP_NONE;
-      if (leap_launch(h->leap, /*cost_mode=*/0, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, none, st, &h->err)) return 1;
+      if (leap_launch(h->leap, /*cost_mode=*/0, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, none, SampleSpec{}, st, &h->err)) return 1;
       h->launches++;
       return 0;
     }
@@ -195,15 +196,16 @@ extern "C" int b200mpc_rollout_dev(b200mpc_handle* h, const double* d_x0, int ba
 }
 
 static int plan_costs_ep(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis, int H,
-                         const double* d_params, float* d_cost, double* d_reward, const PlanEpilogue& ep, cudaStream_t st) {
+                         const double* d_params, float* d_cost, double* d_reward, const PlanEpilogue& ep, cudaStream_t st,
+                         const SampleSpec& smp = SampleSpec{}) {
   if (N <= 0 || H <= 0 || K <= 0) return fail(h, "N, H and K must be positive");
   CK(cudaSetDevice(h->device));
   switch (h->task) {
-    case B200MPC_TASK_CARTPOLE: return launch_costs<CartpoleTask>(h, h->cartpole, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
-    case B200MPC_TASK_CYLINDER_PUSH: return launch_costs<CylinderPushTask>(h, h->cyl, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
+    case B200MPC_TASK_CARTPOLE: return launch_costs<CartpoleTask>(h, h->cartpole, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, smp, st);
+    case B200MPC_TASK_CYLINDER_PUSH: return launch_costs<CylinderPushTask>(h, h->cyl, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, smp, st);
 #ifdef B200MPC_WITH_LEAP
     case B200MPC_TASK_LEAP_CUBE: {
-      if (leap_launch(h->leap, /*cost_mode=*/1, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep, st, &h->err)) return 1;
+      if (leap_launch(h->leap, /*cost_mode=*/1, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep, smp, st, &h->err)) return 1;
       h->launches++;
       return 0;
     }
@@ -266,10 +268,10 @@ extern "C" int b200mpc_plan_costs_dev(b200mpc_handle* h, const double* d_x0, con
   return plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, (cudaStream_t)stream);
 }
 
-extern "C" int b200mpc_plan_step_dev(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis,
-                                     int H, const double* d_params, int optimizer, const double* opt_params, int finalize,
-                                     int index_offset, int n_elite, float* d_cost, double* d_reward, double* d_nominal, double* d_sigma,
-                                     double* d_elite, double* d_rank_partial, void* stream) {
+static int plan_step_impl(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis,
+                          int H, const double* d_params, int optimizer, const double* opt_params, int finalize,
+                          int index_offset, int n_elite, float* d_cost, double* d_reward, double* d_nominal, double* d_sigma,
+                          double* d_elite, double* d_elite_knots, double* d_rank_partial, const SampleSpec& smp, void* stream) {
   if (!h) return 1;
   if (optimizer < 0 || optimizer > 2) return fail(h, "unknown optimizer");
   if (optimizer == B200MPC_OPT_MPPI && !(opt_params && opt_params[0] > 0)) return fail(h, "temperature must be positive");
@@ -282,7 +284,9 @@ extern "C" int b200mpc_plan_step_dev(b200mpc_handle* h, const double* d_x0, cons
     // warp-per-rollout kernel (ms-scale): the update runs as separate reduction kernels (2% of the step)
     PlanEpilogue none{};
     none.optimizer = EP_NONE;
-    if (plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, none, st)) return 1;
+    none.index_offset = index_offset;
+    if (plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, none, st, smp)) return 1;
+    if (smp.enabled) d_knots = smp.knots_out;
     if (finalize) {
       if (run_update(h, optimizer, opt_params, d_knots, d_reward, N, KNU, d_nominal, d_sigma, nullptr, 0, st)) return 1;
       if (n_elite > 0 && d_elite) {
@@ -295,6 +299,11 @@ extern "C" int b200mpc_plan_step_dev(b200mpc_handle* h, const double* d_x0, cons
         h->launches++;
         CK(cudaGetLastError());
         if (b200mpc_topk_combine_dev(h, part, nb, KNU, n_elite, 1, 0, 0, dummy, nullptr, d_elite, st)) return 1;
+        if (d_elite_knots) {
+          gather_rows_kernel<<<n_elite, 64, 0, st>>>(d_knots, d_elite, index_offset, KNU, d_elite_knots);
+          h->launches++;
+          CK(cudaGetLastError());
+        }
       }
       return 0;
     }
@@ -304,7 +313,72 @@ extern "C" int b200mpc_plan_step_dev(b200mpc_handle* h, const double* d_x0, cons
   }
   PlanEpilogue ep;
   if (make_epilogue(h, optimizer, opt_params, n_elite, N, KNU, finalize, index_offset, d_nominal, d_sigma, d_elite, d_rank_partial, st, &ep)) return 1;
-  return plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st);
+  ep.elite_knots = d_elite_knots;
+  return plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st, smp);
+}
+
+extern "C" int b200mpc_plan_step_dev(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis,
+                                     int H, const double* d_params, int optimizer, const double* opt_params, int finalize,
+                                     int index_offset, int n_elite, float* d_cost, double* d_reward, double* d_nominal, double* d_sigma,
+                                     double* d_elite, double* d_rank_partial, void* stream) {
+  return plan_step_impl(h, d_x0, d_knots, N, K, d_basis, H, d_params, optimizer, opt_params, finalize, index_offset, n_elite, d_cost,
+                        d_reward, d_nominal, d_sigma, d_elite, nullptr, d_rank_partial, SampleSpec{}, stream);
+}
+
+// On-device sampling (judo_b200/csrc/sampling.cuh): candidates = clip(nominal + sigma * N(0,1)) generated inside the rollout kernel.
+extern "C" int b200mpc_plan_step_sampled(b200mpc_handle* h, const double* x0, const double* nominal_in, const double* sigma_in,
+                                         const double* lo, const double* hi, int N, int K, const double* basis, int H,
+                                         const double* params, int optimizer, const double* opt_params, unsigned long long seed,
+                                         unsigned long long counter, int index_offset, double* nominal, double* sigma,
+                                         double* reward_N, int* elite_idx, int n_elite, double* elite_knots, double* knots_out) {
+  if (!h) return 1;
+  if (!x0 || !nominal_in || !sigma_in || !lo || !hi || !basis || !params || !nominal) return fail(h, "NULL argument");
+  if (N <= 0 || H <= 0 || K <= 0) return fail(h, "N, H and K must be positive");
+  if (optimizer < 0 || optimizer > 2) return fail(h, "unknown optimizer");
+  if (optimizer == B200MPC_OPT_MPPI && !(opt_params && opt_params[0] > 0)) return fail(h, "temperature must be positive");
+  if (optimizer == B200MPC_OPT_CEM && !opt_params) return fail(h, "CEM needs {num_elites, sigma_min, sigma_max}");
+  if (n_elite < 0 || n_elite > EP_MAXK) return fail(h, "n_elite must be in 0..8");
+  if (optimizer == B200MPC_OPT_CEM && (int)opt_params[0] > EP_MAXK) return fail(h, "device sampling supports at most 8 elites");
+  CK(cudaSetDevice(h->device));
+  const int nx = h->dims.nq + h->dims.nv, nu = h->dims.nu, np = h->dims.n_cost_params, KNU = K * nu;
+  // staged inputs: [x0 | basis | params | nominal | sigma | lo | hi]  (~1-3 KB: the only bytes that cross PCIe on the way in)
+  size_t o = 0, ox0 = o; o += al16((size_t)nx * 8);
+  size_t ob = o; o += al16((size_t)H * K * 8);
+  size_t op = o; o += al16((size_t)np * 8);
+  size_t on = o; o += al16((size_t)KNU * 8);
+  size_t os = o; o += al16((size_t)KNU * 8);
+  size_t ol = o; o += al16((size_t)nu * 8);
+  size_t oh = o; o += al16((size_t)nu * 8);
+  if (grow(h, &h->h_in, &h->h_in_bytes, o, true) || grow(h, &h->d_in, &h->d_in_bytes, o, false)) return 1;
+  if (grow(h, &h->d_big, &h->d_big_bytes, (size_t)N * KNU * 8, false)) return 1;
+  char* hp = (char*)h->h_in;
+  memcpy(hp + ox0, x0, (size_t)nx * 8); memcpy(hp + ob, basis, (size_t)H * K * 8); memcpy(hp + op, params, (size_t)np * 8);
+  memcpy(hp + on, nominal_in, (size_t)KNU * 8); memcpy(hp + os, sigma_in, (size_t)KNU * 8);
+  memcpy(hp + ol, lo, (size_t)nu * 8); memcpy(hp + oh, hi, (size_t)nu * 8);
+  CK(cudaMemcpyAsync(h->d_in, h->h_in, o, cudaMemcpyHostToDevice, h->stream));
+  // outputs (pinned, written by the kernel): [nominal | sigma | elite idx | elite knots | reward]
+  size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_ek = o_el + al16((size_t)std::max(n_elite, 1) * 8);
+  size_t o_rw = o_ek + al16((size_t)std::max(n_elite, 1) * KNU * 8), out_bytes = o_rw + (size_t)N * 8;
+  if (grow(h, &h->h_out, &h->h_out_bytes, out_bytes, true)) return 1;
+  void* dout_v = nullptr;
+  CK(cudaHostGetDevicePointer(&dout_v, h->h_out, 0));
+  char* din = (char*)h->d_in; char* dout = (char*)dout_v;
+  SampleSpec smp{};
+  smp.enabled = 1; smp.seed = seed; smp.counter = counter;
+  smp.nominal = (double*)(din + on); smp.sigma = (double*)(din + os); smp.lo = (double*)(din + ol); smp.hi = (double*)(din + oh);
+  smp.knots_out = (double*)h->d_big;
+  if (plan_step_impl(h, (double*)(din + ox0), nullptr, N, K, (double*)(din + ob), H, (double*)(din + op), optimizer, opt_params, 1, index_offset,
+                     n_elite, nullptr, (double*)(dout + o_rw), (double*)(dout + o_nom), (double*)(dout + o_sig), (double*)(dout + o_el),
+                     (elite_knots && n_elite > 0) ? (double*)(dout + o_ek) : nullptr, nullptr, smp, h->stream)) return 1;
+  if (knots_out) CK(cudaMemcpyAsync(knots_out, h->d_big, (size_t)N * KNU * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const char* ho = (const char*)h->h_out;
+  memcpy(nominal, ho + o_nom, (size_t)KNU * 8);
+  if (sigma && optimizer == B200MPC_OPT_CEM) memcpy(sigma, ho + o_sig, (size_t)KNU * 8);
+  if (elite_idx) for (int i = 0; i < n_elite; i++) elite_idx[i] = (int)((const double*)(ho + o_el))[i];
+  if (elite_knots && n_elite > 0) memcpy(elite_knots, ho + o_ek, (size_t)n_elite * KNU * 8);
+  if (reward_N) memcpy(reward_N, ho + o_rw, (size_t)N * 8);
+  return 0;
 }
 
 // ------------------------------------------------------------------ reductions (device-pointer API)

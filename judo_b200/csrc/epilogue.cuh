@@ -30,6 +30,7 @@ struct PlanEpilogue {
   double* nominal;        // [KNU]  (finalize)
   double* sigma;          // [KNU]  (finalize, CEM)
   double* elite;          // [k] global indices as doubles, -1 padded (finalize)
+  double* elite_knots;    // [k][KNU] the elite candidates themselves, or NULL (finalize)
   double* rank_mppi;      // [2+KNU]            (!finalize)
   double* rank_topk;      // CEM: [k][2+KNU]; PS: [1][2+KNU]   (!finalize)
 };
@@ -145,31 +146,34 @@ __device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KN
     }
     if (ep.finalize) {
       if (ep.elite) for (int e = lane; e < k; e += 32) ep.elite[e] = e < ne ? (double)(ei[e] + ep.index_offset) : -1.0;
+      if (ep.elite_knots)
+        for (int e = 0; e < ne; e++)
+          for (int j = lane; j < KNU; j += 32) ep.elite_knots[(size_t)e * KNU + j] = __ldcg(knots + (size_t)ei[e] * KNU + j);
       if (ep.optimizer == EP_CEM) {
         const int nc = min(ne, ep.k_cem);
         for (int j = lane; j < KNU; j += 32) {
           double mean = 0;
-          for (int e = 0; e < nc; e++) mean += knots[(size_t)ei[e] * KNU + j];
+          for (int e = 0; e < nc; e++) mean += __ldcg(knots + (size_t)ei[e] * KNU + j);
           mean = nc ? mean / nc : 0.0;
           double var = 0;
-          for (int e = 0; e < nc; e++) { double d = knots[(size_t)ei[e] * KNU + j] - mean; var += d * d; }
+          for (int e = 0; e < nc; e++) { double d = __ldcg(knots + (size_t)ei[e] * KNU + j) - mean; var += d * d; }
           var = nc ? var / nc : 0.0;
           ep.nominal[j] = mean;
           ep.sigma[j] = fmin(fmax(sqrt(var), ep.sigma_min), ep.sigma_max);
         }
       } else if (ep.optimizer == EP_PS) {
-        for (int j = lane; j < KNU; j += 32) ep.nominal[j] = pi >= 0 ? knots[(size_t)pi * KNU + j] : 0.0;
+        for (int j = lane; j < KNU; j += 32) ep.nominal[j] = pi >= 0 ? __ldcg(knots + (size_t)pi * KNU + j) : 0.0;
       }
     } else if (ep.optimizer == EP_PS) {  // rank partial: 1 x [reward, global index, knots]
       double* o = ep.rank_topk;
       if (lane == 0) { o[0] = pi >= 0 ? pr : -INFINITY; o[1] = pi >= 0 ? (double)(pi + ep.index_offset) : -1.0; }
-      for (int j = lane; j < KNU; j += 32) o[2 + j] = pi >= 0 ? knots[(size_t)pi * KNU + j] : 0.0;
+      for (int j = lane; j < KNU; j += 32) o[2 + j] = pi >= 0 ? __ldcg(knots + (size_t)pi * KNU + j) : 0.0;
     } else {  // rank partial: k x [reward, global index, knots]
       const int stride = 2 + KNU;
       for (int e = 0; e < k; e++) {
         double* o = ep.rank_topk + (size_t)e * stride;
         if (lane == 0) { o[0] = e < ne ? er[e] : -INFINITY; o[1] = e < ne ? (double)(ei[e] + ep.index_offset) : -1.0; }
-        for (int j = lane; j < KNU; j += 32) o[2 + j] = e < ne ? knots[(size_t)ei[e] * KNU + j] : 0.0;
+        for (int j = lane; j < KNU; j += 32) o[2 + j] = e < ne ? __ldcg(knots + (size_t)ei[e] * KNU + j) : 0.0;
       }
     }
   }

@@ -1,6 +1,7 @@
 // kernels.cuh — the fused rollout kernel for the thread-per-rollout tasks and the optimizer-update reductions.
 #pragma once
 #include "epilogue.cuh"
+#include "sampling.cuh"
 #include "small_tasks.cuh"
 
 namespace b2 {
@@ -18,7 +19,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
                                                       const double* __restrict__ basis, const double* __restrict__ cost_params,
                                                       double* __restrict__ states, double* __restrict__ sensors,
                                                       float* __restrict__ cost_NH, double* __restrict__ reward_N,
-                                                      const PlanEpilogue ep) {
+                                                      const PlanEpilogue ep, const SampleSpec smp) {
   constexpr int NU = Task::NU, NX = Task::NX, NS = Task::NS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -35,20 +36,21 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
     float* sC = reinterpret_cast<float*>(sK + (size_t)nthr * K * NU);
     const unsigned bytesB = (unsigned)(nB * sizeof(double)), bytesK = (unsigned)((size_t)nblk * K * NU * sizeof(double));
     const double* gK = in + (size_t)n0 * K * NU;
-    const bool tma_ok = (bytesB % 16 == 0) && (bytesK % 16 == 0) && ((reinterpret_cast<uintptr_t>(basis) & 15) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(gK) & 15) == 0);
+    const bool want_knots = !smp.enabled;  // sampled candidates are generated in registers below
+    const bool tma_ok = (bytesB % 16 == 0) && (!want_knots || bytesK % 16 == 0) && ((reinterpret_cast<uintptr_t>(basis) & 15) == 0) &&
+                        (!want_knots || (reinterpret_cast<uintptr_t>(gK) & 15) == 0);
     if (tma_ok) {
       if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
       __syncthreads();
       if (tid == 0) {
-        mbar_expect_tx(bar, bytesB + bytesK);
+        mbar_expect_tx(bar, bytesB + (want_knots ? bytesK : 0u));
         tma_bulk_g2s(sB, basis, bytesB, bar);
-        tma_bulk_g2s(sK, gK, bytesK, bar);
+        if (want_knots) tma_bulk_g2s(sK, gK, bytesK, bar);
       }
       mbar_wait(bar, 0);
     } else {
       for (int i = tid; i < nB; i += nthr) sB[i] = basis[i];
-      for (int i = tid; i < nblk * K * NU; i += nthr) sK[i] = gK[i];
+      if (want_knots) for (int i = tid; i < nblk * K * NU; i += nthr) sK[i] = gK[i];
       __syncthreads();
     }
     double cp[Task::NCOST];
@@ -59,10 +61,27 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
 #pragma unroll
     for (int i = 0; i < MAXK * NU; i++) kn[i] = 0;
     if (n < N) {
+      if (smp.enabled) {
+        // on-device sampling: Philox keyed by the GLOBAL rollout index -> identical candidates however N is sharded
+        const long long gn = (long long)n + ep.index_offset;
+        const int KNU = K * NU;
 #pragma unroll
-      for (int k = 0; k < MAXK; k++)
+        for (int p2 = 0; p2 < (MAXK * NU + 1) / 2; p2++) {
+          if (2 * p2 < KNU) {
+            double z0, z1;
+            normal_pair(smp, gn, p2, &z0, &z1);
+            kn[2 * p2] = sample_element(smp, gn, 2 * p2, NU, z0);
+            if (2 * p2 + 1 < MAXK * NU && 2 * p2 + 1 < KNU) kn[2 * p2 + 1] = sample_element(smp, gn, 2 * p2 + 1, NU, z1);
+          }
+        }
 #pragma unroll
-        for (int j = 0; j < NU; j++) kn[k * NU + j] = k < K ? sK[(size_t)tid * K * NU + k * NU + j] : 0.0;
+        for (int e = 0; e < MAXK * NU; e++) if (e < KNU) smp.knots_out[(size_t)n * KNU + e] = kn[e];
+      } else {
+#pragma unroll
+        for (int k = 0; k < MAXK; k++)
+#pragma unroll
+          for (int j = 0; j < NU; j++) kn[k * NU + j] = k < K ? sK[(size_t)tid * K * NU + k * NU + j] : 0.0;
+      }
       Task::load(s, x0 + (x0_batched ? (size_t)n * NX : 0));
       double total = 0;
       for (int t = 0; t < H; t++) {
@@ -86,7 +105,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
       reward_N[n] = reward;
     }
     if (ep.optimizer != EP_NONE || ep.k > 0)
-      epilogue_thread_per_rollout<MAXK * NU>(ep, n < N, n, reward, kn, K * NU, blockIdx.x * (nthr >> 5) + (tid >> 5), gridDim.x * (nthr >> 5), in);
+      epilogue_thread_per_rollout<MAXK * NU>(ep, n < N, n, reward, kn, K * NU, blockIdx.x * (nthr >> 5) + (tid >> 5), gridDim.x * (nthr >> 5),
+                                             smp.enabled ? smp.knots_out : in);
     if (cost_NH) {
       __syncthreads();
       // coalesced write-back of the block's (nblk, H) tile: consecutive threads write consecutive floats
@@ -251,6 +271,13 @@ __global__ void mppi_combine_kernel(const double* __restrict__ partials, int np,
     }
     nominal[j] = v / S;
   }
+}
+
+// rows[e] = knots[idx[e] - index_offset] for the elite list (leap path; the fused kernels do this in their epilogue)
+__global__ void gather_rows_kernel(const double* __restrict__ knots, const double* __restrict__ idx, int index_offset, int KNU,
+                                   double* __restrict__ rows) {
+  const long long i = (long long)idx[blockIdx.x] - index_offset;
+  for (int j = threadIdx.x; j < KNU; j += blockDim.x) rows[(size_t)blockIdx.x * KNU + j] = i >= 0 ? knots[(size_t)i * KNU + j] : 0.0;
 }
 
 // total order for elite selection: larger reward first; ties by index (higher first for CEM's flipped argsort,

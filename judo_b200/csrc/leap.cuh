@@ -9,6 +9,7 @@
 // The collision GEOMETRY is reduced; the constraint/solver pipeline is the full one.
 #pragma once
 #include "epilogue.cuh"
+#include "sampling.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -1254,7 +1255,7 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
                                                            const double* __restrict__ in, int N, int H, int K, const double* __restrict__ basis,
                                                            const double* __restrict__ cost_params, double* __restrict__ states,
                                                            double* __restrict__ sensors, float* __restrict__ cost_NH, double* __restrict__ reward_N,
-                                                           int wstride, int prof) {
+                                                           int wstride, int prof, const SampleSpec smp, int index_offset) {
   const int sync_mode = prof >> 8;
   prof &= 255;
   extern __shared__ __align__(16) unsigned char lsm_all[];
@@ -1277,15 +1278,32 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
     if (active) {
       const unsigned bytesK = (unsigned)(K * LEAP_NU * sizeof(double)), bytesB = (unsigned)(H * K * sizeof(double));
       const double* gK = in + (size_t)n * K * LEAP_NU;
-      const bool tma_ok = (bytesB % 16 == 0) && ((reinterpret_cast<uintptr_t>(basis) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gK) & 15) == 0);
+      const bool want_knots = !smp.enabled;
+      const bool tma_ok = (bytesB % 16 == 0) && ((reinterpret_cast<uintptr_t>(basis) & 15) == 0) && (!want_knots || (reinterpret_cast<uintptr_t>(gK) & 15) == 0);
       if (tma_ok) {
         if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
         __syncwarp();
-        if (lane == 0) { mbar_expect_tx(bar, bytesK + bytesB); tma_bulk_g2s(sK, gK, bytesK, bar); tma_bulk_g2s(sB, basis, bytesB, bar); }
+        if (lane == 0) {
+          mbar_expect_tx(bar, (want_knots ? bytesK : 0u) + bytesB);
+          if (want_knots) tma_bulk_g2s(sK, gK, bytesK, bar);
+          tma_bulk_g2s(sB, basis, bytesB, bar);
+        }
         mbar_wait(bar, 0);
       } else {
-        for (int i = lane; i < K * LEAP_NU; i += 32) sK[i] = gK[i];
+        if (want_knots) for (int i = lane; i < K * LEAP_NU; i += 32) sK[i] = gK[i];
         for (int i = lane; i < H * K; i += 32) sB[i] = basis[i];
+        __syncwarp();
+      }
+      if (smp.enabled) {  // on-device sampling: lane p draws the normal pair for elements 2p, 2p+1 (Philox keyed by the global index)
+        const long long gn = (long long)n + index_offset;
+        const int KNU = K * LEAP_NU;
+        for (int p2 = lane; 2 * p2 < KNU; p2 += 32) {
+          double z0, z1;
+          normal_pair(smp, gn, p2, &z0, &z1);
+          const double a = sample_element(smp, gn, 2 * p2, LEAP_NU, z0);
+          sK[2 * p2] = a; smp.knots_out[(size_t)n * KNU + 2 * p2] = a;
+          if (2 * p2 + 1 < KNU) { const double b = sample_element(smp, gn, 2 * p2 + 1, LEAP_NU, z1); sK[2 * p2 + 1] = b; smp.knots_out[(size_t)n * KNU + 2 * p2 + 1] = b; }
+        }
         __syncwarp();
       }
     }
@@ -1358,7 +1376,7 @@ inline int leap_num_partials(int N) { return N; }
 
 inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, int batched, const double* d_in, int N, int H, int K,
                        const double* d_basis, const double* d_params, double* d_states, double* d_sensors, float* d_cost, double* d_reward,
-                       const PlanEpilogue& ep, cudaStream_t st, std::string* err) {
+                       const PlanEpilogue& ep, const SampleSpec& smp, cudaStream_t st, std::string* err) {
   const char* sm_env = getenv("B200MPC_LEAP_SYNC");
   const int prof = (getenv("B200MPC_LEAP_PROF") ? 1 : 0) | ((sm_env ? atoi(sm_env) : 3) << 8);
   (void)ep;  // the leap path runs the optimizer update as separate reduction kernels (b200mpc.cu)
@@ -1375,11 +1393,11 @@ inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, in
   if (cost_mode) {
     e = cudaFuncSetAttribute(leap_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      leap_rollout_kernel<true><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, (int)wstride, prof);
+      leap_rollout_kernel<true><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, (int)wstride, prof, smp, ep.index_offset);
   } else {
     e = cudaFuncSetAttribute(leap_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      leap_rollout_kernel<false><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, (int)wstride, prof);
+      leap_rollout_kernel<false><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, (int)wstride, prof, smp, 0);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("leap launch: ") + cudaGetErrorString(e); return 1; }

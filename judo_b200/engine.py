@@ -134,3 +134,26 @@ class Engine:
         self._check(self._lib.b200mpc_plan_step(self._h, _p(x0), _p(knots), N, K, _p(basis), H, _p(cost_params), OPT_IDS[optimizer], _p(op),
                                                 _p(nominal), _p(sigma), _p(rewards), elite.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(n_elite)))
         return dict(nominal=nominal, sigma=sigma, rewards=rewards, elite=elite[:n_elite])
+
+    # ---- fused plan step with on-device sampling (perf mode; see include/b200mpc.h)
+    def plan_step_sampled(self, x0: np.ndarray, nominal: np.ndarray, sigma: np.ndarray, lo: np.ndarray, hi: np.ndarray, num_rollouts: int,
+                          basis: np.ndarray, cost_params: np.ndarray, optimizer: str, opt_params: np.ndarray, seed: int, counter: int,
+                          index_offset: int = 0, want_rewards: bool = True, n_elite: int = 0, want_knots: bool = False) -> dict:
+        x0, nominal, basis, cost_params = _c(x0), _c(nominal), _c(basis), _c(cost_params)
+        K, nu = nominal.shape
+        sigma = _c(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (K, nu)))
+        lo, hi = _c(np.broadcast_to(lo, (nu,))), _c(np.broadcast_to(hi, (nu,)))
+        op = _c(np.atleast_1d(opt_params)) if opt_params is not None and np.size(opt_params) else np.zeros(1)
+        H, N = basis.shape[0], int(num_rollouts)
+        assert basis.shape == (H, K) and cost_params.size == self.n_cost_params and x0.shape == (self.nq + self.nv,) and nu == self.nu
+        nom_out = np.empty((K, nu))
+        sig_out = np.empty((K, nu)) if optimizer == "cem" else None
+        rewards = np.empty(N) if want_rewards else None
+        elite = np.empty(max(n_elite, 1), dtype=np.int32)
+        elite_knots = np.empty((max(n_elite, 1), K, nu))
+        knots = np.empty((N, K, nu)) if want_knots else None
+        self._check(self._lib.b200mpc_plan_step_sampled(
+            self._h, _p(x0), _p(nominal), _p(sigma), _p(lo), _p(hi), N, K, _p(basis), H, _p(cost_params), OPT_IDS[optimizer], _p(op),
+            ctypes.c_ulonglong(int(seed) & (2**64 - 1)), ctypes.c_ulonglong(int(counter) & (2**64 - 1)), int(index_offset), _p(nom_out),
+            _p(sig_out), _p(rewards), elite.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(n_elite), _p(elite_knots), _p(knots)))
+        return dict(nominal=nom_out, sigma=sig_out, rewards=rewards, elite=elite[:n_elite], elite_knots=elite_knots[:n_elite], knots=knots)

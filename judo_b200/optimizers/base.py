@@ -84,6 +84,11 @@ class Optimizer(ABC, Generic[ConfigT]):
     def update_nominal_knots(self, sampled_knots: np.ndarray, rewards: np.ndarray) -> np.ndarray:
         """(num_rollouts, num_nodes, nu), (num_rollouts,) -> (num_nodes, nu)."""
 
+    def device_sigma(self) -> np.ndarray:
+        """(num_nodes, nu) standard deviation of the next draw, for on-device sampling (Engine.plan_step_sampled).  Applies the
+        same state changes sample_control_knots would (CEM's ramp mutates sigma)."""
+        raise NotImplementedError(f"{type(self).__name__} does not support on-device sampling")
+
     def fused_params(self) -> np.ndarray:
         """opt_params vector for b200mpc_plan_step."""
         return np.zeros(0)

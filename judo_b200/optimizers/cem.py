@@ -46,6 +46,11 @@ class CrossEntropyMethod(Optimizer[CrossEntropyMethodConfig]):
             self.sigma = np.clip(self.sigma * self._ramp(), self.sigma_min, self.sigma_max)
         return self._noised(nominal_knots, self.sigma[None])
 
+    def device_sigma(self) -> np.ndarray:
+        if self.use_noise_ramp:
+            self.sigma = np.clip(self.sigma * self._ramp(), self.sigma_min, self.sigma_max)  # same mutation as sample_control_knots
+        return self.sigma.copy()
+
     def update_nominal_knots(self, sampled_knots: np.ndarray, rewards: np.ndarray) -> np.ndarray:
         nominal, self.sigma = self._engine().update_cem(sampled_knots, rewards, self.num_elites, self.sigma_min, self.sigma_max)
         return nominal

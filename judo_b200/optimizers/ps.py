@@ -26,5 +26,9 @@ class PredictiveSampling(Optimizer[PredictiveSamplingConfig]):
         sigma = self._ramp() * self.sigma if self.use_noise_ramp else self.sigma
         return self._noised(nominal_knots, sigma)
 
+    def device_sigma(self) -> np.ndarray:
+        sigma = self._ramp() * self.sigma if self.use_noise_ramp else np.full((self.num_nodes, 1), self.sigma)
+        return np.broadcast_to(sigma, (self.num_nodes, self.nu)).copy()
+
     def update_nominal_knots(self, sampled_knots: np.ndarray, rewards: np.ndarray) -> np.ndarray:
         return self._engine().update_ps(sampled_knots, rewards)
