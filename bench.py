@@ -107,7 +107,7 @@ def cpu_port_plan_step(w: dict, x0, knots, basis, params, opt, nthread: int = 0)
 
     om = cpu_port_plan_step.models.setdefault(w["task"], _oracle_model(w["task"]))
     controls = np.einsum("hk,nkj->nhj", basis, knots)
-    states, _ = om.rollout(x0, controls, nthread=nthread or (os.cpu_count() or 1))  # all host threads, explicitly
+    states, _ = om.rollout(x0, controls, nthread=nthread or host_threads())  # every host thread this process may run on
     if w["task"] == "cartpole":
         r = op.cartpole_reward(states, controls, *params)
     elif w["task"] == "cylinder_push":
@@ -124,6 +124,14 @@ def cpu_port_plan_step(w: dict, x0, knots, basis, params, opt, nthread: int = 0)
 cpu_port_plan_step.models = {}
 
 
+def host_threads() -> int:
+    """CPUs this process can actually run on (cgroup / affinity aware): oversubscribing the OpenMP pool is far slower."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
 def _oracle_model(task: str):
     from oracle.mjc import OracleModel, load_table
 
@@ -136,20 +144,36 @@ def _oracle_model(task: str):
     return OracleModel(task)
 
 
+def best_thread_count(w: dict, x0, ks, basis, params, opt) -> int:
+    """The OpenMP thread count that runs the CPU path fastest on this host (SMT / cgroup limits make 'all logical CPUs' a bad
+    default): one plan step per candidate, keep the quickest."""
+    ht = host_threads()
+    best, best_t = ht, float("inf")
+    for nt in sorted({ht, max(1, ht // 2), max(1, ht // 4), min(ht, 16)}, reverse=True):
+        cpu_port_plan_step(w, x0, ks, basis, params, opt, nthread=nt)
+        t1 = time.perf_counter()
+        cpu_port_plan_step(w, x0, ks, basis, params, opt, nthread=nt)
+        dt = time.perf_counter() - t1
+        if dt < best_t:
+            best, best_t = nt, dt
+    return best
+
+
 def time_cpu(w: dict, x0, knots, basis, params, opt, budget_s: float, n_sample: int) -> dict:
     ks = knots[:n_sample]
     cpu_port_plan_step(w, x0, ks[: min(64, n_sample)], basis, params, opt)  # warm-up (thread pool, page-in)
+    nt = best_thread_count(w, x0, ks, basis, params, opt)
     t0, reps, times = time.perf_counter(), 0, []
     while True:
         t1 = time.perf_counter()
-        cpu_port_plan_step(w, x0, ks, basis, params, opt)
+        cpu_port_plan_step(w, x0, ks, basis, params, opt, nthread=nt)
         times.append(time.perf_counter() - t1)
         reps += 1
         if time.perf_counter() - t0 > budget_s or reps >= 50:
             break
     med = statistics.median(times)
-    return {"value": n_sample / med, "unit": "rollouts/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{reps} plan steps of {n_sample} rollouts x H={w['H']} ({w['task']}), oracle C port with OpenMP on all host cores + NumPy "
+    return {"value": n_sample / med, "unit": "rollouts/s", "cores": nt, "host_logical_cpus": host_threads(), "kind": "port",
+            "sample": f"{reps} plan steps of {n_sample} rollouts x H={w['H']} ({w['task']}), oracle C port with OpenMP ({nt} threads = fastest of the tried counts) + NumPy "
                       f"reward/update; median {med * 1e3:.2f} ms/step", "ms_per_step": med * 1e3}
 
 
@@ -184,16 +208,17 @@ def main() -> None:
         task, opt, x0, knots, basis, params = problem(w, n_local)
         # bounded sample per step so that steps+warmup finish within minutes
         n_sample = min(n_local, 4096 if w["task"] != "leap_cube" else 256)
+        nt = best_thread_count(w, x0, knots[:n_sample], basis, params, opt)
         for _ in range(min(args.warmup, 3)):
-            cpu_port_plan_step(w, x0, knots[:n_sample], basis, params, opt)
+            cpu_port_plan_step(w, x0, knots[:n_sample], basis, params, opt, nthread=nt)
         steps = max(1, min(args.steps, 30))
         t0 = time.perf_counter()
         for _ in range(steps):
-            cpu_port_plan_step(w, x0, knots[:n_sample], basis, params, opt)
+            cpu_port_plan_step(w, x0, knots[:n_sample], basis, params, opt, nthread=nt)
         dt = (time.perf_counter() - t0) / steps
         val = n_sample / dt
-        cb = {"value": val, "unit": "rollouts/s", "cores": os.cpu_count(), "kind": "port",
-              "sample": f"{steps} plan steps of {n_sample} rollouts x H={w['H']}; oracle C port (OpenMP, all host cores) + NumPy"}
+        cb = {"value": val, "unit": "rollouts/s", "cores": nt, "host_logical_cpus": host_threads(), "kind": "port",
+              "sample": f"{steps} plan steps of {n_sample} rollouts x H={w['H']}; oracle C port (OpenMP, {nt} threads = fastest tried) + NumPy"}
         print(json.dumps({"impl": "reference", "metric": "rollouts/sec per control step", "value": val, "unit": "rollouts/s", "n_gpus": args.gpus,
                           "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,

@@ -95,7 +95,7 @@ class ShardedPlanner:
         h = self.engine.handle
         P = lambda x: ctypes.c_void_p(0 if x is None else x.data_ptr())  # noqa: E731
         op = np.ascontiguousarray(np.atleast_1d(opt_params), dtype=np.float64) if np.size(opt_params) else np.zeros(1)
-        opp = op.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        opp = op.ctypes.data
         single = self.world_size == 1
         k = int(op[0]) if optimizer == "cem" else 1
         width = 2 + self.knu if optimizer == "mppi" else k * (2 + self.knu)

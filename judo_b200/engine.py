@@ -14,7 +14,7 @@ _dp = ctypes.POINTER(ctypes.c_double)
 
 
 def _p(a: np.ndarray | None):  # noqa: ANN202
-    return None if a is None else a.ctypes.data_as(_dp)
+    return None if a is None else a.ctypes.data
 
 
 def _c(a: np.ndarray) -> np.ndarray:
@@ -86,7 +86,7 @@ class Engine:
         assert basis.shape == (H, K) and cost_params.size == self.n_cost_params and x0.shape == (self.nq + self.nv,)
         reward = np.empty(N)
         cost = np.empty((N, H), dtype=np.float32) if want_cost_matrix else None
-        cp = None if cost is None else cost.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        cp = None if cost is None else cost.ctypes.data
         self._check(self._lib.b200mpc_plan_costs(self._h, _p(x0), _p(knots), N, K, _p(basis), H, _p(cost_params), cp, _p(reward)))
         return reward, cost
 
@@ -132,7 +132,7 @@ class Engine:
         rewards = np.empty(N) if want_rewards else None
         elite = np.empty(max(n_elite, 1), dtype=np.int32)
         self._check(self._lib.b200mpc_plan_step(self._h, _p(x0), _p(knots), N, K, _p(basis), H, _p(cost_params), OPT_IDS[optimizer], _p(op),
-                                                _p(nominal), _p(sigma), _p(rewards), elite.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(n_elite)))
+                                                _p(nominal), _p(sigma), _p(rewards), elite.ctypes.data, int(n_elite)))
         return dict(nominal=nominal, sigma=sigma, rewards=rewards, elite=elite[:n_elite])
 
     # ---- fused plan step with on-device sampling (perf mode; see include/b200mpc.h)
@@ -155,5 +155,5 @@ class Engine:
         self._check(self._lib.b200mpc_plan_step_sampled(
             self._h, _p(x0), _p(nominal), _p(sigma), _p(lo), _p(hi), N, K, _p(basis), H, _p(cost_params), OPT_IDS[optimizer], _p(op),
             ctypes.c_ulonglong(int(seed) & (2**64 - 1)), ctypes.c_ulonglong(int(counter) & (2**64 - 1)), int(index_offset), _p(nom_out),
-            _p(sig_out), _p(rewards), elite.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(n_elite), _p(elite_knots), _p(knots)))
+            _p(sig_out), _p(rewards), elite.ctypes.data, int(n_elite), _p(elite_knots), _p(knots)))
         return dict(nominal=nom_out, sigma=sig_out, rewards=rewards, elite=elite[:n_elite], elite_knots=elite_knots[:n_elite], knots=knots)

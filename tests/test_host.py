@@ -143,5 +143,5 @@ def test_c_abi_library_exports_every_declared_symbol():
     if not os.path.exists("/dev/nvidia0"):
         h = ctypes.c_void_p()
         c = task_consts("cartpole")
-        rc = lib.b200mpc_create(ctypes.byref(h), 0, c.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), c.size, 0, 8)
+        rc = lib.b200mpc_create(ctypes.byref(h), 0, c.ctypes.data, c.size, 0, 8)
         assert rc != 0 and b"CUDA" in lib.b200mpc_last_error(None)
