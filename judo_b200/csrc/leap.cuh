@@ -1070,10 +1070,11 @@ __device__ inline double leap_line_search(const LeapModel* __restrict__ m, const
   const double gtol = m->tolerance * m->ls_tolerance * snorm * m->meaninertia * LEAP_NV;
   LeapLS L;
   leap_ls_load(m, W, lane, L);
-  double d1, d2, lo = 0, hi = -1, alpha;
-  leap_ls_eval(L, 0, g1, g2, &d1, &d2);
+  // derivatives at alpha = 0 without evaluating the rows: d1(0) = grad . search, and for the Newton direction H search = -grad
+  // gives d2(0) = search^T H search = -d1(0), i.e. the first trial step is the full Newton step
+  double d1 = lwsum(lane < LEAP_NV ? W->grad[lane] * W->search[lane] : 0.0), d2 = -d1, lo = 0, hi = -1, alpha;
   if (d1 >= 0 || d2 <= 0) return 0;
-  alpha = -d1 / d2;
+  alpha = 1.0;
   double prev_step = 1e300;
   const int iters = (int)m->ls_iterations;
 #pragma unroll 1

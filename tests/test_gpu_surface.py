@@ -191,3 +191,47 @@ def test_engine_argument_errors():
     with pytest.raises(RuntimeError):  # K > 12
         eng.plan_costs(np.zeros(4), np.zeros((4, 13, 1)), np.zeros((3, 13)), np.ones(6))
     eng.close()
+
+
+def test_closed_loop_sim_plan_act_matches_cpu_loop(temp_np_seed):
+    """sim -> plan -> act without MuJoCo: B200Simulation plant + Controller, 15 control steps of cartpole+mppi,
+    against the same loop driven by the CPU oracle (oracle plant, oracle rollouts, NumPy reward/update) on the same seed."""
+    from judo_b200.controller import make_controller
+    from judo_b200.simulation import B200Simulation
+    from judo_b200.spline import spline_basis
+
+    n_ctrl, substeps = 15, 2
+    with temp_np_seed(11):
+        sim = B200Simulation("cartpole")
+        ctrl = make_controller("cartpole", "mppi")
+        ctrl.task.data.qpos, ctrl.task.data.qvel = sim.task.data.qpos.copy(), sim.task.data.qvel.copy()
+        x_init = np.concatenate([sim.task.data.qpos, sim.task.data.qvel])
+        rng_state = np.random.get_state()
+        gpu_traj = []
+        for _ in range(n_ctrl):
+            ctrl.update_states(sim.sim_state)
+            ctrl.update_action()
+            for _ in range(substeps):
+                sim.step(ctrl.action(sim.task.data.time))
+            gpu_traj.append(np.concatenate([sim.task.data.qpos, sim.task.data.qvel]))
+        # CPU replica of the loop
+        np.random.set_state(rng_state)
+        om = OracleModel("cartpole")
+        x, t, dt = x_init.copy(), 0.0, 0.04
+        K, N, H = 4, 32, 25
+        times = np.linspace(0, 1.0, K)
+        nominal = np.zeros((K, 1))
+        cpu_traj = []
+        for _ in range(n_ctrl):
+            new_times = t + np.linspace(0, 1.0, K)
+            nominal = op.make_spline(times, nominal, "zero")(new_times)
+            cand = np.clip(op.sample_fixed_sigma(nominal, N, 0.1, True, 2.5), -1.8, 1.8)
+            u = op.make_spline(new_times, cand, "zero")(t + dt * np.arange(H))
+            r = op.cartpole_reward(om.rollout(x, u)[0], u)
+            nominal, times = op.mppi_update(cand, r, 0.05), new_times
+            for _ in range(substeps):
+                a = op.make_spline(times, nominal, "zero")(np.array([t]))
+                x = om.rollout(x, a.reshape(1, 1, 1))[0][0, 0]
+                t += dt
+            cpu_traj.append(x.copy())
+    np.testing.assert_allclose(np.array(gpu_traj), np.array(cpu_traj), rtol=0, atol=1e-7)
