@@ -520,8 +520,9 @@ __device__ inline void l_make_frame(double* frame) {
   lcross3(z, x, y);
 }
 
-__device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+__device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork* W, int lane, int prof = 0) {
   const int ng = (int)m->ngeom;
+  long long tc0 = LPROF_T();
   const double* cp = W->xpos[0];
   // broad phase: bounding spheres against the cube's; ordered compaction keeps the geom order of the pair list
   int base = 0;
@@ -569,6 +570,8 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
   }
   __syncwarp();
   const int ncand = base;
+  LPROF_ADD(11, tc0); tc0 = LPROF_T();
+  if (prof && lane == 0) atomicAdd(&g_leap_prof[13], (unsigned long long)ncand);
   int ncon = 0;
   for (int c0 = 0; c0 < ncand; c0 += 32) {
     const int ci = c0 + lane;
@@ -613,6 +616,8 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
   __syncwarp();
   if (lane == 0) W->ncon = ncon < LMAXCON ? ncon : LMAXCON;
   __syncwarp();
+  LPROF_ADD(12, tc0);
+  if (prof && lane == 0) atomicAdd(&g_leap_prof[14], (unsigned long long)ncon);
 }
 
 // ------------------------------------------------------------------ constraint rows (mj_makeConstraint + mj_makeImpedance)
@@ -1168,7 +1173,7 @@ __device__ inline void leap_step(const LeapModel* __restrict__ m, LeapWork* W, i
   if (sync_mode >= 2) __syncthreads();
   t0 = LPROF_T();
   if (active) {
-    leap_collision(m, W, lane);
+    leap_collision(m, W, lane, prof);
     LPROF_ADD(2, t0); t0 = LPROF_T();
     leap_make_constraint(m, W, lane);
     LPROF_ADD(3, t0); t0 = LPROF_T();
@@ -1368,8 +1373,8 @@ inline void leap_destroy(LeapModel* m) { cudaFree(m); }
 inline void leap_prof_dump() {
   unsigned long long h[16];
   if (cudaMemcpyFromSymbol(h, g_leap_prof, sizeof(h)) != cudaSuccess) return;
-  const char* names[11] = {"kinematics", "mass+bias", "collision", "constraints", "smooth", "solver(total)", "integrate", "  update", "  direction", "  linesearch", "newton iters"};
-  for (int i = 0; i < 11; i++) fprintf(stderr, "leap_prof %-14s %llu\n", names[i], h[i]);
+  const char* names[15] = {"kinematics", "mass+bias", "collision", "constraints", "smooth", "solver(total)", "integrate", "  update", "  direction", "  linesearch", "newton iters", "  coll:broad", "  coll:narrow", "candidates", "contacts"};
+  for (int i = 0; i < 15; i++) fprintf(stderr, "leap_prof %-14s %llu\n", names[i], h[i]);
   memset(h, 0, sizeof(h));
   cudaMemcpyToSymbol(g_leap_prof, h, sizeof(h));
 }
