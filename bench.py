@@ -276,6 +276,9 @@ def main() -> None:
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
             flush.zero_()                                  # evict L2 between timed iterations (outside the events)
+            if dist is not None:
+                dist.barrier()                             # line the ranks up again (the flush skews them): the timed region must
+                                                           # not contain time spent waiting for a late peer to START its step
             starts[i].record()
             # dominant kernel alone (for the roofline) is bracketed inside the step by a second event
             planner.step(w["optimizer"], opt_params, index_offset=lo)
