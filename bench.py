@@ -198,7 +198,7 @@ def main() -> None:
     config = {"workload": f"{w['task']}+{w['optimizer']} N={n_local}/GPU H={w['H']} K={w['K']} spline={w['order']} (BASELINE config "
                           f"{'C2' if args.workload == 'cartpole_mppi' else 'C3' if args.workload == 'cylinder_push_cem' else 'C4'})",
               "n_rollouts_per_gpu": n_local, "n_rollouts_total": n_total, "horizon_steps": w["H"], "num_nodes": w["K"],
-              "parallelism": f"rollout-sharded x{world}", "l2": "flushed (256 MiB memset) between timed iterations",
+              "parallelism": f"rollout-sharded x{world}", "exchange": ("in-kernel P2P over NVLink (CUDA IPC)" if world > 1 and os.environ.get("B200MPC_PEER_EXCHANGE", "1") != "0" and w["optimizer"] == "mppi" and w["task"] != "leap_cube" else ("nccl all_gather" if world > 1 else "none")), "l2": "flushed (256 MiB memset) between timed iterations",
               "contract": "B (fused: knots in, cost matrix f32 + reward out)"}
 
     # ------------------------------------------------------------------ reference arm: CPU path on the host cores
@@ -253,6 +253,8 @@ def main() -> None:
     knots = np.ascontiguousarray(knots_all[lo:hi])
     opt_params = opt.fused_params()
     planner = ShardedPlanner(w["task"], n_local, device=local_rank, rank=rank, world_size=world)
+    if world > 1 and os.environ.get("B200MPC_PEER_EXCHANGE", "1") != "0":
+        planner.enable_peer_exchange()   # MPPI partials cross NVLink inside the rollout kernel (falls back to all_gather for CEM/PS/leap)
     planner.set_problem(x0, basis, params, want_cost_matrix=True)
     planner.set_knots(knots)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)

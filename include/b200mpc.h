@@ -114,6 +114,7 @@ int b200mpc_plan_costs_dev(b200mpc_handle* h, const double* d_x0, const double* 
                            double* d_reward_N, void* stream);
 /* One-launch resident plan step: rollout + cost + optimizer update fused (judo_b200/csrc/epilogue.cuh).
  *   finalize=1: writes d_nominal (K*nu), d_sigma (CEM), d_elite (n_elite indices as doubles, best first).
+ *   finalize=2: MPPI over the peer exchange (see b200mpc_exchange_*): writes d_nominal, identical on every rank.
  *   finalize=0: writes this rank's partial to d_rank_partial for the all_gather: MPPI [beta, S, V[K*nu]];
  *               CEM num_elites x [reward, global index, knots]; PS 1 x [reward, global index, knots]; indices are
  *               offset by index_offset.  opt_params is a HOST pointer (see b200mpc_plan_step). */
@@ -132,6 +133,13 @@ int b200mpc_topk_partial_dev(b200mpc_handle* h, const double* d_knots, const dou
 int b200mpc_topk_combine_dev(b200mpc_handle* h, const double* d_partials, int n_partials, int KNU, int k,
                              int prefer_high_index, double sigma_min, double sigma_max, double* d_nominal,
                              double* d_sigma, double* d_elite_idx, void* stream);
+
+/* Peer exchange for the multi-GPU fused MPPI step: every rank allocates a small exchange buffer, the 64-byte CUDA IPC handles are
+ * exchanged out of band (torch.distributed), and with finalize=2 in b200mpc_plan_step_dev the LAST WARP of the rollout kernel writes
+ * the rank's [beta, S, V] partial into every peer's buffer over NVLink, waits for the peers' flags and writes the final nominal
+ * knots — the collective of SURVEY.md §8e happens inside the rollout kernel (no NCCL call, no extra launch on the data path). */
+int b200mpc_exchange_create(b200mpc_handle* h, int world_size, int rank, unsigned char* ipc_handle_out_64B);
+int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all_handles_world_x_64B);
 
 /* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
 long long b200mpc_launch_count(const b200mpc_handle* h);

@@ -47,6 +47,8 @@ SIGNATURES = {
     "b200mpc_mppi_combine_dev": (_i, [_vp, _vp, _i, _i, _d, _vp, _vp]),
     "b200mpc_topk_partial_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200mpc_topk_combine_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp]),
+    "b200mpc_exchange_create": (_i, [_vp, _i, _i, _vp]),
+    "b200mpc_exchange_open": (_i, [_vp, _vp]),
     "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),
 }
 

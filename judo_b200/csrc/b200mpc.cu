@@ -41,6 +41,8 @@ struct b200mpc_handle {
   void* h_out = nullptr; size_t h_out_bytes = 0;
   int zero_copy = 2;           // plan_step: bit0 = kernel READS the pinned staging buffer, bit1 = kernel WRITES results to pinned memory
   bool zero_copy_now = false;  // set for the duration of a zero-copy plan_step
+  // peer exchange (multi-GPU fused MPPI): local buffer + peers' buffers opened through CUDA IPC
+  void* xchg = nullptr; void* xchg_peer[8] = {nullptr}; int xchg_world = 0, xchg_rank = 0; unsigned long long xchg_epoch = 0;
   double t_stage = 0, t_launch = 0, t_sync = 0, t_out = 0; long long t_calls = 0; bool timing = false;  // B200MPC_TIMING=1
 };
 
@@ -112,6 +114,8 @@ extern "C" void b200mpc_destroy(b200mpc_handle* h) {
             h->t_stage / h->t_calls, h->t_launch / h->t_calls, h->t_sync / h->t_calls, h->t_out / h->t_calls);
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int g = 0; g < h->xchg_world; g++) if (h->xchg_peer[g] && g != h->xchg_rank) cudaIpcCloseMemHandle(h->xchg_peer[g]);
+  cudaFree(h->xchg);
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
 #ifdef B200MPC_WITH_LEAP
@@ -119,6 +123,35 @@ extern "C" void b200mpc_destroy(b200mpc_handle* h) {
 #endif
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+// ---- peer exchange set-up -------------------------------------------------------------------------------------------------
+extern "C" int b200mpc_exchange_create(b200mpc_handle* h, int world, int rank, unsigned char* ipc_handle_out /* 64 bytes */) {
+  if (!h) return 1;
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(h, "exchange: world must be 1..8 and 0 <= rank < world");
+  CK(cudaSetDevice(h->device));
+  if (!h->xchg) {
+    CK(cudaMalloc(&h->xchg, EP_XCHG_BYTES));
+    CK(cudaMemset(h->xchg, 0, EP_XCHG_BYTES));
+  }
+  h->xchg_world = world; h->xchg_rank = rank; h->xchg_epoch = 0;
+  cudaIpcMemHandle_t ih;
+  CK(cudaIpcGetMemHandle(&ih, h->xchg));
+  static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(ipc_handle_out, &ih, 64);
+  return 0;
+}
+
+extern "C" int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all_handles /* world x 64 bytes */) {
+  if (!h || !h->xchg) return 1;
+  CK(cudaSetDevice(h->device));
+  for (int g = 0; g < h->xchg_world; g++) {
+    if (g == h->xchg_rank) { h->xchg_peer[g] = h->xchg; continue; }
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, all_handles + 64 * g, 64);
+    CK(cudaIpcOpenMemHandle(&h->xchg_peer[g], ih, cudaIpcMemLazyEnablePeerAccess));
+  }
+  return 0;
 }
 
 extern "C" int b200mpc_get_dims(const b200mpc_handle* h, b200mpc_dims* out) { if (!h || !out) return 1; *out = h->dims; return 0; }
@@ -314,6 +347,13 @@ static int plan_step_impl(b200mpc_handle* h, const double* d_x0, const double* d
   PlanEpilogue ep;
   if (make_epilogue(h, optimizer, opt_params, n_elite, N, KNU, finalize, index_offset, d_nominal, d_sigma, d_elite, d_rank_partial, st, &ep)) return 1;
   ep.elite_knots = d_elite_knots;
+  if (finalize == 2) {
+    if (optimizer != B200MPC_OPT_MPPI) return fail(h, "peer exchange is implemented for MPPI; use the gather path for CEM/PS");
+    if (!h->xchg || !h->xchg_peer[h->xchg_world - 1] || !h->xchg_peer[0]) return fail(h, "peer exchange not set up (exchange_create/open)");
+    if (KNU > EP_XCHG_STRIDE - 2) return fail(h, "K*nu too large for the exchange slot");
+    ep.world = h->xchg_world; ep.rank = h->xchg_rank; ep.epoch = ++h->xchg_epoch;
+    for (int g = 0; g < h->xchg_world; g++) ep.peer[g] = (double*)h->xchg_peer[g];
+  }
   return plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st, smp);
 }
 

@@ -33,7 +33,25 @@ struct PlanEpilogue {
   double* elite_knots;    // [k][KNU] the elite candidates themselves, or NULL (finalize)
   double* rank_mppi;      // [2+KNU]            (!finalize)
   double* rank_topk;      // CEM: [k][2+KNU]; PS: [1][2+KNU]   (!finalize)
+  // peer exchange (finalize == 2, MPPI): the last warp writes this rank's partial straight into every peer's exchange buffer
+  // over NVLink (P2P stores + system-scope release flag), waits for the world_size flags of the current epoch in its OWN buffer
+  // and finishes the update — the collective is part of the rollout kernel, no NCCL call and no extra launch on the data path.
+  int world, rank;
+  unsigned long long epoch;
+  double* peer[8];        // peer[g]: exchange buffer of rank g mapped into this process (peer[rank] is local)
 };
+constexpr int EP_XCHG_FLAGS = 8;                   // u64 flags in front of the partial slots
+constexpr int EP_XCHG_STRIDE = 2 + 96;             // doubles per rank slot (beta, S, V[<=96])
+constexpr size_t EP_XCHG_BYTES = 8 * EP_XCHG_FLAGS + 2 * 8 * (size_t)EP_XCHG_STRIDE * 8;  // slots double-buffered by epoch parity
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ double wsum(double v) {
@@ -87,15 +105,51 @@ __device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KN
       for (int j = 0; j < MAXKNU; j++) v[j] += x[j] * sc;
     }
     const double S = wsum(s);
-    double* out = ep.finalize ? ep.nominal : ep.rank_mppi + 2;
+    if (ep.finalize == 2) {
+      // ---- fused exchange: publish [beta, S, V] into every peer's slot for this rank, then raise the epoch flag there
+      double vj[MAXKNU];
 #pragma unroll
-    for (int j = 0; j < MAXKNU; j++) {
-      if (j < KNU) {
-        const double t = wsum(v[j]);
-        if (lane == 0) out[j] = ep.finalize ? t / S : t;
+      for (int j = 0; j < MAXKNU; j++) vj[j] = j < KNU ? wsum(v[j]) : 0.0;
+      for (int g = 0; g < ep.world; g++) {
+        double* slot = ep.peer[g] + EP_XCHG_FLAGS + (size_t)((ep.epoch & 1) * 8 + ep.rank) * EP_XCHG_STRIDE;
+        if (lane == 0) { slot[0] = beta; slot[1] = S; }
+#pragma unroll
+        for (int j = 0; j < MAXKNU; j++) if (j < KNU && lane == (j & 31)) slot[2 + j] = vj[j];
       }
+      __threadfence_system();
+      __syncwarp();
+      if (lane < ep.world) st_release_sys(reinterpret_cast<unsigned long long*>(ep.peer[lane]) + ep.rank, ep.epoch);
+      // ---- wait for every rank's flag of this epoch in OUR buffer (bounded spin: a missing peer must not hang the GPU)
+      bool ok = true;
+      if (lane < ep.world) {
+        const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(ep.peer[ep.rank]) + lane;
+        int spins = 0;
+        while (ld_acquire_sys(fl) < ep.epoch) { __nanosleep(64); if (++spins > (1 << 22)) { ok = false; break; } }
+      }
+      ok = __all_sync(0xffffffffu, ok);
+      // ---- combine the world_size partials (lane g holds rank g's beta / S)
+      const double* own = ep.peer[ep.rank] + EP_XCHG_FLAGS + (size_t)(ep.epoch & 1) * 8 * EP_XCHG_STRIDE;
+      const volatile double* vown = own;
+      const double bg = lane < ep.world ? vown[(size_t)lane * EP_XCHG_STRIDE] : INFINITY;
+      const double sg = lane < ep.world ? vown[(size_t)lane * EP_XCHG_STRIDE + 1] : 0.0;
+      const double bmin = wmin(bg);
+      const double scg = sg > 0 ? exp(-(bg - bmin) / ep.temperature) : 0.0;
+      const double Stot = wsum(sg * scg);
+      for (int j = 0; j < KNU; j++) {
+        const double t = wsum(lane < ep.world ? vown[(size_t)lane * EP_XCHG_STRIDE + 2 + j] * scg : 0.0);
+        if (lane == 0) ep.nominal[j] = ok ? t / Stot : __longlong_as_double(0x7ff8000000000000ll);
+      }
+    } else {
+      double* out = ep.finalize ? ep.nominal : ep.rank_mppi + 2;
+#pragma unroll
+      for (int j = 0; j < MAXKNU; j++) {
+        if (j < KNU) {
+          const double t = wsum(v[j]);
+          if (lane == 0) out[j] = ep.finalize ? t / S : t;
+        }
+      }
+      if (!ep.finalize && lane == 0) { ep.rank_mppi[0] = beta; ep.rank_mppi[1] = S; }
     }
-    if (!ep.finalize && lane == 0) { ep.rank_mppi[0] = beta; ep.rank_mppi[1] = S; }
   }
   if (ep.k > 0 || ep.optimizer == EP_PS) {
     const int k = ep.k, slots = k + 1;

@@ -59,12 +59,33 @@ class ShardedPlanner:
         self.dev = torch.device("cuda", device)
         self.rank, self.world_size, self.group = rank, world_size, group
         self.n_local = n_local
+        self.peer_exchange = False
         self.nu = self.engine.nu
         self.nx = self.engine.nq + self.engine.nv
 
     def _check(self, rc: int) -> None:
         if rc:
             raise RuntimeError(self.lib.b200mpc_last_error(self.engine.handle).decode())
+
+    def enable_peer_exchange(self) -> None:
+        """Open every rank's exchange buffer through CUDA IPC so that the MPPI update's cross-GPU step happens INSIDE the rollout
+        kernel (P2P stores over NVLink + flags) instead of an NCCL all_gather + a combine launch."""
+        import torch.distributed as dist
+
+        t = self.torch
+        mine = np.zeros(64, dtype=np.uint8)
+        self._check(self.lib.b200mpc_exchange_create(self.engine.handle, self.world_size, self.rank, mine.ctypes.data))
+        if self.world_size > 1:
+            buf = t.from_numpy(mine).to(self.dev)
+            allh = t.empty(self.world_size * 64, dtype=t.uint8, device=self.dev)
+            dist.all_gather_into_tensor(allh, buf, group=self.group)
+            handles = np.ascontiguousarray(allh.cpu().numpy())
+        else:
+            handles = mine
+        self._check(self.lib.b200mpc_exchange_open(self.engine.handle, handles.ctypes.data))
+        if self.world_size > 1:
+            dist.barrier(group=self.group)
+        self.peer_exchange = True
 
     def set_problem(self, x0: np.ndarray, basis: np.ndarray, cost_params: np.ndarray, want_cost_matrix: bool = True) -> None:
         t = self.torch
@@ -97,6 +118,12 @@ class ShardedPlanner:
         op = np.ascontiguousarray(np.atleast_1d(opt_params), dtype=np.float64) if np.size(opt_params) else np.zeros(1)
         opp = op.ctypes.data
         single = self.world_size == 1
+        if (not single or getattr(self, "force_peer", False)) and self.peer_exchange and optimizer == "mppi" and self.engine.task != "leap_cube":
+            # ONE kernel per rank: rollout + cost + P2P exchange of the partials + final update
+            self._check(self.lib.b200mpc_plan_step_dev(h, P(self.d_x0), P(self.d_knots), self.n_local, self.K, P(self.d_basis), self.H,
+                                                       P(self.d_params), OPT_IDS[optimizer], opp, 2, int(index_offset), 0, P(self.d_cost),
+                                                       P(self.d_reward), P(self.d_nominal), P(self.d_sigma), P(self.d_elite), P(None), st))
+            return self.d_nominal
         k = int(op[0]) if optimizer == "cem" else 1
         width = 2 + self.knu if optimizer == "mppi" else k * (2 + self.knu)
         part = None if single else t.empty(width, dtype=t.float64, device=self.dev)
