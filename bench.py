@@ -198,7 +198,7 @@ def main() -> None:
     config = {"workload": f"{w['task']}+{w['optimizer']} N={n_local}/GPU H={w['H']} K={w['K']} spline={w['order']} (BASELINE config "
                           f"{'C2' if args.workload == 'cartpole_mppi' else 'C3' if args.workload == 'cylinder_push_cem' else 'C4'})",
               "n_rollouts_per_gpu": n_local, "n_rollouts_total": n_total, "horizon_steps": w["H"], "num_nodes": w["K"],
-              "parallelism": f"rollout-sharded x{world}", "exchange": ("in-kernel P2P over NVLink (CUDA IPC)" if world > 1 and os.environ.get("B200MPC_PEER_EXCHANGE", "1") != "0" and w["optimizer"] == "mppi" and w["task"] != "leap_cube" else ("nccl all_gather" if world > 1 else "none")), "l2": "flushed (256 MiB memset) between timed iterations",
+              "parallelism": f"rollout-sharded x{world}", "exchange": "see exchange_used", "l2": "flushed (256 MiB memset) between timed iterations",
               "contract": "B (fused: knots in, cost matrix f32 + reward out)"}
 
     # ------------------------------------------------------------------ reference arm: CPU path on the host cores
@@ -254,7 +254,8 @@ def main() -> None:
     opt_params = opt.fused_params()
     planner = ShardedPlanner(w["task"], n_local, device=local_rank, rank=rank, world_size=world)
     if world > 1 and os.environ.get("B200MPC_PEER_EXCHANGE", "1") != "0":
-        planner.enable_peer_exchange()   # MPPI partials cross NVLink inside the rollout kernel (falls back to all_gather for CEM/PS/leap)
+        if not planner.enable_peer_exchange():  # MPPI partials cross NVLink inside the rollout kernel (all_gather for CEM/PS/leap)
+            print("bench: CUDA IPC peer exchange unavailable, using the NCCL all_gather path", file=sys.stderr)
     planner.set_problem(x0, basis, params, want_cost_matrix=True)
     planner.set_knots(knots)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -380,6 +381,9 @@ def main() -> None:
                         "(SURVEY.md §8d); see profiles/ for occupancy and stall reasons"}
     # the CPU baseline is timed on rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host cores)
     cpu = time_cpu(w, x0, knots, basis, params, opt, args.cpu_budget, min(n_local, 4096 if w["task"] != "leap_cube" else 256)) if world == 1 else None
+    config["exchange_used"] = ("in-kernel P2P stores over NVLink (CUDA IPC), 1 launch per step" if world > 1 and planner.peer_exchange and
+                               w["optimizer"] == "mppi" and w["task"] != "leap_cube" else ("nccl all_gather + combine kernel" if world > 1 else "none"))
+    config.pop("exchange", None)
     out = {"metric": "rollouts/sec per control step", "value": value, "unit": "rollouts/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": config, "state_steps_per_s": value * w["H"],

@@ -67,14 +67,14 @@ class ShardedPlanner:
         if rc:
             raise RuntimeError(self.lib.b200mpc_last_error(self.engine.handle).decode())
 
-    def enable_peer_exchange(self) -> None:
+    def enable_peer_exchange(self) -> bool:
         """Open every rank's exchange buffer through CUDA IPC so that the MPPI update's cross-GPU step happens INSIDE the rollout
         kernel (P2P stores over NVLink + flags) instead of an NCCL all_gather + a combine launch."""
         import torch.distributed as dist
 
         t = self.torch
         mine = np.zeros(64, dtype=np.uint8)
-        self._check(self.lib.b200mpc_exchange_create(self.engine.handle, self.world_size, self.rank, mine.ctypes.data))
+        ok = self.lib.b200mpc_exchange_create(self.engine.handle, self.world_size, self.rank, mine.ctypes.data) == 0
         if self.world_size > 1:
             buf = t.from_numpy(mine).to(self.dev)
             allh = t.empty(self.world_size * 64, dtype=t.uint8, device=self.dev)
@@ -82,10 +82,14 @@ class ShardedPlanner:
             handles = np.ascontiguousarray(allh.cpu().numpy())
         else:
             handles = mine
-        self._check(self.lib.b200mpc_exchange_open(self.engine.handle, handles.ctypes.data))
+        ok = ok and self.lib.b200mpc_exchange_open(self.engine.handle, handles.ctypes.data) == 0
         if self.world_size > 1:
-            dist.barrier(group=self.group)
-        self.peer_exchange = True
+            # every rank must take the same path: one failed IPC mapping anywhere -> everybody stays on the all_gather path
+            flag = t.tensor([1 if ok else 0], dtype=t.int32, device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            ok = bool(flag.item())
+        self.peer_exchange = ok
+        return ok
 
     def set_problem(self, x0: np.ndarray, basis: np.ndarray, cost_params: np.ndarray, want_cost_matrix: bool = True) -> None:
         t = self.torch
