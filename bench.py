@@ -321,7 +321,9 @@ def main() -> None:
         if dist is not None and i == max(args.warmup, 3):
             barrier()
         t1 = time.perf_counter()
-        res = eng.plan_step(x0, knots, basis, params, w["optimizer"], opt_params, want_rewards=True, n_elite=5)
+        # world > 1 with the peer exchange open: n_elite=0 makes the host-API step a GLOBAL MPPI update across the ranks
+        res = eng.plan_step(x0, knots, basis, params, w["optimizer"], opt_params, want_rewards=True,
+                            n_elite=0 if (world > 1 and planner.peer_exchange and w["optimizer"] == "mppi") else 5)
         e2e_times.append(time.perf_counter() - t1)
     e2e_times = e2e_times[max(args.warmup, 3):]
     e2e_tt = torch.tensor([sum(e2e_times), statistics.median(e2e_times)], dtype=torch.float64, device=dev)
@@ -332,7 +334,8 @@ def main() -> None:
     d2h = 2 * res["nominal"].nbytes + 5 * 8 + n_local * 8
     e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": "rollouts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "plan_latency_p50_ms": float(e2e_tt[1]) * 1e3,
-           "note": "Engine.plan_step per rank with host buffers; multi-GPU e2e = independent per-rank plans (no exchange on the host path)"}
+           "note": "Engine.plan_step per rank with host buffers; at N>1 the MPPI update is global through the in-kernel peer exchange "
+                   "(CEM/PS/leap at N>1: per-rank plans)"}
 
     # ---- e2e in perf mode: candidates drawn on the device (Philox), only the nominal crosses PCIe on the way in
     sig = opt.device_sigma()

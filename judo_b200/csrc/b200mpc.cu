@@ -670,8 +670,10 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
   auto T1 = std::chrono::steady_clock::now();
   if (std::max(n_elite, k_cem) <= EP_MAXK) {
     // one launch: rollout + cost + optimizer update + elite list
+    // multi-GPU handles with an open peer exchange: the MPPI update is GLOBAL (partials cross NVLink inside the kernel)
+    const int fin = (h->xchg_world > 1 && h->xchg && optimizer == B200MPC_OPT_MPPI && h->task != B200MPC_TASK_LEAP_CUBE && n_elite == 0) ? 2 : 1;
     if (b200mpc_plan_step_dev(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), optimizer,
-                              opt_params, /*finalize=*/1, 0, n_elite, nullptr, d_reward, (double*)(dout + o_nom), (double*)(dout + o_sig),
+                              opt_params, fin, 0, n_elite, nullptr, d_reward, (double*)(dout + o_nom), (double*)(dout + o_sig),
                               (double*)(dout + o_el), nullptr, h->stream)) return 1;
   } else {
     // more than 8 elites: separate reduction kernels
