@@ -265,6 +265,7 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    in_kernel_exchange = world > 1 and planner.peer_exchange and w["optimizer"] == "mppi" and w["task"] != "leap_cube"
     for _ in range(max(args.warmup, 3)):
         planner.step(w["optimizer"], opt_params, index_offset=lo)
     barrier()
@@ -279,9 +280,11 @@ def main() -> None:
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
             flush.zero_()                                  # evict L2 between timed iterations (outside the events)
-            if dist is not None:
-                dist.barrier()                             # line the ranks up again (the flush skews them): the timed region must
-                                                           # not contain time spent waiting for a late peer to START its step
+            if dist is not None and not in_kernel_exchange:
+                dist.barrier()                             # all_gather path: line the ranks up again (the flush skews them) so the timed
+                                                           # region holds no time spent waiting for a late peer to START its step.
+                                                           # (in-kernel exchange: every step's exchange already re-aligns the GPUs and
+                                                           # the launches are queued ahead, so the steps run back to back.)
             starts[i].record()
             # dominant kernel alone (for the roofline) is bracketed inside the step by a second event
             planner.step(w["optimizer"], opt_params, index_offset=lo)
