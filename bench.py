@@ -265,7 +265,7 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    in_kernel_exchange = world > 1 and planner.peer_exchange and w["optimizer"] == "mppi" and w["task"] != "leap_cube"
+    in_kernel_exchange = world > 1 and planner.peer_exchange and w["task"] != "leap_cube"
     for _ in range(max(args.warmup, 3)):
         planner.step(w["optimizer"], opt_params, index_offset=lo)
     barrier()
@@ -326,7 +326,7 @@ def main() -> None:
         t1 = time.perf_counter()
         # world > 1 with the peer exchange open: n_elite=0 makes the host-API step a GLOBAL MPPI update across the ranks
         res = eng.plan_step(x0, knots, basis, params, w["optimizer"], opt_params, want_rewards=True,
-                            n_elite=0 if (world > 1 and planner.peer_exchange and w["optimizer"] == "mppi") else 5)
+                            n_elite=0 if (world > 1 and planner.peer_exchange and w["task"] != "leap_cube") else 5)
         e2e_times.append(time.perf_counter() - t1)
     e2e_times = e2e_times[max(args.warmup, 3):]
     e2e_tt = torch.tensor([sum(e2e_times), statistics.median(e2e_times)], dtype=torch.float64, device=dev)
@@ -410,7 +410,7 @@ def main() -> None:
     # the CPU baseline is timed on rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host cores)
     cpu = time_cpu(w, x0, knots, basis, params, opt, args.cpu_budget, min(n_local, 4096 if w["task"] != "leap_cube" else 256)) if world == 1 else None
     config["exchange_used"] = ("in-kernel P2P stores over NVLink (CUDA IPC), 1 launch per step" if world > 1 and planner.peer_exchange and
-                               w["optimizer"] == "mppi" and w["task"] != "leap_cube" else ("nccl all_gather + combine kernel" if world > 1 else "none"))
+                               w["task"] != "leap_cube" else ("nccl all_gather + combine kernel" if world > 1 else "none"))
     config.pop("exchange", None)
     out = {"metric": "rollouts/sec per control step", "value": value, "unit": "rollouts/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -348,9 +348,10 @@ static int plan_step_impl(b200mpc_handle* h, const double* d_x0, const double* d
   if (make_epilogue(h, optimizer, opt_params, n_elite, N, KNU, finalize, index_offset, d_nominal, d_sigma, d_elite, d_rank_partial, st, &ep)) return 1;
   ep.elite_knots = d_elite_knots;
   if (finalize == 2) {
-    if (optimizer != B200MPC_OPT_MPPI) return fail(h, "peer exchange is implemented for MPPI; use the gather path for CEM/PS");
     if (!h->xchg || !h->xchg_peer[h->xchg_world - 1] || !h->xchg_peer[0]) return fail(h, "peer exchange not set up (exchange_create/open)");
-    if (KNU > EP_XCHG_STRIDE - 2) return fail(h, "K*nu too large for the exchange slot");
+    const int kout = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
+    if ((optimizer == B200MPC_OPT_MPPI ? 2 + KNU : kout * (2 + KNU)) > EP_XCHG_STRIDE) return fail(h, "partial too large for the exchange slot");
+    if (n_elite > 0) return fail(h, "elite lists are per rank: pass n_elite = 0 with the peer exchange");
     ep.world = h->xchg_world; ep.rank = h->xchg_rank; ep.epoch = ++h->xchg_epoch;
     for (int g = 0; g < h->xchg_world; g++) ep.peer[g] = (double*)h->xchg_peer[g];
   }
@@ -671,7 +672,9 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
   if (std::max(n_elite, k_cem) <= EP_MAXK) {
     // one launch: rollout + cost + optimizer update + elite list
     // multi-GPU handles with an open peer exchange: the MPPI update is GLOBAL (partials cross NVLink inside the kernel)
-    const int fin = (h->xchg_world > 1 && h->xchg && optimizer == B200MPC_OPT_MPPI && h->task != B200MPC_TASK_LEAP_CUBE && n_elite == 0) ? 2 : 1;
+    const int kout_x = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
+    const bool fits_x = (optimizer == B200MPC_OPT_MPPI ? 2 + KNU : kout_x * (2 + KNU)) <= EP_XCHG_STRIDE;
+    const int fin = (h->xchg_world > 1 && h->xchg && fits_x && h->task != B200MPC_TASK_LEAP_CUBE && n_elite == 0) ? 2 : 1;
     if (b200mpc_plan_step_dev(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), optimizer,
                               opt_params, fin, 0, n_elite, nullptr, d_reward, (double*)(dout + o_nom), (double*)(dout + o_sig),
                               (double*)(dout + o_el), nullptr, h->stream)) return 1;

@@ -80,6 +80,21 @@ __device__ __forceinline__ void warp_best(double& r, long long& i, bool prefer_h
   }
 }
 
+// Raise this rank's epoch flag in every peer's buffer (after the partial stores) and wait, bounded, for all world_size flags of
+// the epoch in OUR buffer.  Returns false on time-out (a peer never launched): the caller writes NaN instead of hanging the GPU.
+__device__ inline bool peer_signal_and_wait(const PlanEpilogue& ep, int lane) {
+  __threadfence_system();
+  __syncwarp();
+  if (lane < ep.world) st_release_sys(reinterpret_cast<unsigned long long*>(ep.peer[lane]) + ep.rank, ep.epoch);
+  bool ok = true;
+  if (lane < ep.world) {
+    const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(ep.peer[ep.rank]) + lane;
+    int spins = 0;
+    while (ld_acquire_sys(fl) < ep.epoch) { __nanosleep(64); if (++spins > (1 << 22)) { ok = false; break; } }
+  }
+  return __all_sync(0xffffffffu, ok);
+}
+
 // Final stage, run by one full warp after all partials are visible.  knots: this launch's (N, KNU) candidates.
 // Loads are issued in batches of independent __ldcg's (the stage is one warp deep: L2 latency, not bandwidth, is the cost).
 template <int MAXKNU>
@@ -116,17 +131,7 @@ __device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KN
 #pragma unroll
         for (int j = 0; j < MAXKNU; j++) if (j < KNU && lane == (j & 31)) slot[2 + j] = vj[j];
       }
-      __threadfence_system();
-      __syncwarp();
-      if (lane < ep.world) st_release_sys(reinterpret_cast<unsigned long long*>(ep.peer[lane]) + ep.rank, ep.epoch);
-      // ---- wait for every rank's flag of this epoch in OUR buffer (bounded spin: a missing peer must not hang the GPU)
-      bool ok = true;
-      if (lane < ep.world) {
-        const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(ep.peer[ep.rank]) + lane;
-        int spins = 0;
-        while (ld_acquire_sys(fl) < ep.epoch) { __nanosleep(64); if (++spins > (1 << 22)) { ok = false; break; } }
-      }
-      ok = __all_sync(0xffffffffu, ok);
+      const bool ok = peer_signal_and_wait(ep, lane);
       // ---- combine the world_size partials (lane g holds rank g's beta / S)
       const double* own = ep.peer[ep.rank] + EP_XCHG_FLAGS + (size_t)(ep.epoch & 1) * 8 * EP_XCHG_STRIDE;
       const volatile double* vown = own;
@@ -198,7 +203,63 @@ __device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KN
       }
       warp_best(pr, pi, false);
     }
-    if (ep.finalize) {
+    if (ep.finalize == 2 && ep.optimizer != EP_MPPI) {
+      // ---- fused exchange of the rank's best candidates: kout x [reward, global index, knots] into every peer's slot
+      const int kout = ep.optimizer == EP_CEM ? ep.k_cem : 1, stride = 2 + KNU;
+      for (int g = 0; g < ep.world; g++) {
+        double* slot = ep.peer[g] + EP_XCHG_FLAGS + (size_t)((ep.epoch & 1) * 8 + ep.rank) * EP_XCHG_STRIDE;
+        for (int e = 0; e < kout; e++) {
+          const bool have = ep.optimizer == EP_CEM ? e < ne : pi >= 0;
+          const long long loc = ep.optimizer == EP_CEM ? ei[e] : pi;
+          const double rr = ep.optimizer == EP_CEM ? er[e] : pr;
+          if (lane == 0) { slot[e * stride] = have ? rr : -INFINITY; slot[e * stride + 1] = have ? (double)(loc + ep.index_offset) : -1.0; }
+          for (int j = lane; j < KNU; j += 32) slot[e * stride + 2 + j] = have ? __ldcg(knots + (size_t)loc * KNU + j) : 0.0;
+        }
+      }
+      const bool ok = peer_signal_and_wait(ep, lane);
+      // ---- global selection over world*kout candidates held in OUR buffer (<= 64: two per lane)
+      const volatile double* own = ep.peer[ep.rank] + EP_XCHG_FLAGS + (size_t)(ep.epoch & 1) * 8 * EP_XCHG_STRIDE;
+      const int ncand = ep.world * kout;
+      const bool hi_first = ep.optimizer == EP_CEM;
+      double cr[2]; long long ci[2]; int cl[2];
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        const int cnd = lane + 32 * t;
+        cr[t] = -INFINITY; ci[t] = -1; cl[t] = -1;
+        if (cnd < ncand) {
+          const int g = cnd / kout, e = cnd - g * kout;
+          cl[t] = g * EP_XCHG_STRIDE + e * stride;
+          cr[t] = own[cl[t]]; ci[t] = (long long)own[cl[t] + 1];
+        }
+      }
+      int wloc[EP_MAXK];
+      int nw = 0;
+      bool used[2] = {false, false};
+      for (int e = 0; e < kout; e++) {
+        double br = -INFINITY; long long bi = -1;
+#pragma unroll
+        for (int t = 0; t < 2; t++) if (!used[t] && better(cr[t], ci[t], br, bi, hi_first)) { br = cr[t]; bi = ci[t]; }
+        warp_best(br, bi, hi_first);
+        if (bi < 0) break;
+        int myloc = -1;
+#pragma unroll
+        for (int t = 0; t < 2; t++) if (!used[t] && ci[t] == bi) { used[t] = true; myloc = cl[t]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) myloc = max(myloc, __shfl_xor_sync(0xffffffffu, myloc, o));
+        wloc[nw++] = myloc;
+      }
+      const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+      for (int j = lane; j < KNU; j += 32) {
+        double mean = 0;
+        for (int e = 0; e < nw; e++) mean += own[wloc[e] + 2 + j];
+        mean = nw ? mean / nw : 0.0;
+        double var = 0;
+        for (int e = 0; e < nw; e++) { const double d = own[wloc[e] + 2 + j] - mean; var += d * d; }
+        var = nw ? var / nw : 0.0;
+        ep.nominal[j] = ok ? mean : qnan;
+        if (ep.optimizer == EP_CEM && ep.sigma) ep.sigma[j] = ok ? fmin(fmax(sqrt(var), ep.sigma_min), ep.sigma_max) : qnan;
+      }
+    } else if (ep.finalize) {
       if (ep.elite) for (int e = lane; e < k; e += 32) ep.elite[e] = e < ne ? (double)(ei[e] + ep.index_offset) : -1.0;
       if (ep.elite_knots)
         for (int e = 0; e < ne; e++)

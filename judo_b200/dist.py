@@ -69,7 +69,7 @@ class ShardedPlanner:
 
     def enable_peer_exchange(self) -> bool:
         """Open every rank's exchange buffer through CUDA IPC so that the MPPI update's cross-GPU step happens INSIDE the rollout
-        kernel (P2P stores over NVLink + flags) instead of an NCCL all_gather + a combine launch."""
+        kernel (P2P stores over NVLink + flags) instead of an NCCL all_gather + a combine launch (MPPI, CEM and PS on the fused kernels)."""
         import torch.distributed as dist
 
         t = self.torch
@@ -122,7 +122,9 @@ class ShardedPlanner:
         op = np.ascontiguousarray(np.atleast_1d(opt_params), dtype=np.float64) if np.size(opt_params) else np.zeros(1)
         opp = op.ctypes.data
         single = self.world_size == 1
-        if (not single or getattr(self, "force_peer", False)) and self.peer_exchange and optimizer == "mppi" and self.engine.task != "leap_cube":
+        k_x = int(op[0]) if optimizer == "cem" else 1
+        fits = (2 + self.knu if optimizer == "mppi" else k_x * (2 + self.knu)) <= 98  # EP_XCHG_STRIDE doubles per rank slot
+        if (not single or getattr(self, "force_peer", False)) and self.peer_exchange and fits and self.engine.task != "leap_cube":
             # ONE kernel per rank: rollout + cost + P2P exchange of the partials + final update
             self._check(self.lib.b200mpc_plan_step_dev(h, P(self.d_x0), P(self.d_knots), self.n_local, self.K, P(self.d_basis), self.H,
                                                        P(self.d_params), OPT_IDS[optimizer], opp, 2, int(index_offset), 0, P(self.d_cost),

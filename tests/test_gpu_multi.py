@@ -21,7 +21,8 @@ def _problem(N):
     return x0, knots, basis, params
 
 
-def test_peer_exchange_path_on_one_rank():
+@pytest.mark.parametrize("optimizer,params", [("mppi", [0.05]), ("cem", [3, 0.1, 1.0]), ("ps", [])])
+def test_peer_exchange_path_on_one_rank(optimizer, params):
     """finalize=2 with world_size 1: the exchange buffer, flags and epochs work (several consecutive steps)."""
     from judo_b200.dist import ShardedPlanner
     from oracle import plan as op
@@ -34,12 +35,16 @@ def test_peer_exchange_path_on_one_rank():
     pl.set_problem(x0, basis, params)
     pl.set_knots(knots)
     for _ in range(4):
-        nominal = pl.step("mppi", np.array([0.05])).cpu().numpy().reshape(4, 1)
+        nominal = pl.step(optimizer, np.array(params)).cpu().numpy().reshape(4, 1)
     rewards = pl.d_reward.cpu().numpy()
-    np.testing.assert_allclose(nominal, op.mppi_update(knots, rewards, 0.05), rtol=1e-11, atol=1e-13)
+    ref = {"mppi": lambda: op.mppi_update(knots, rewards, 0.05), "cem": lambda: op.cem_update(knots, rewards, 3, 0.1, 1.0)[0],
+           "ps": lambda: op.ps_update(knots, rewards)}[optimizer]()
+    np.testing.assert_allclose(nominal, ref, rtol=1e-11, atol=1e-13)
+    if optimizer == "cem":
+        np.testing.assert_allclose(pl.d_sigma.cpu().numpy().reshape(4, 1), op.cem_update(knots, rewards, 3, 0.1, 1.0)[1], rtol=1e-11)
 
 
-def _rank_main(rank, world, port, mode, q):
+def _rank_main(rank, world, port, mode, q, optimizer="mppi", params=(0.05,)):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -60,16 +65,17 @@ def _rank_main(rank, world, port, mode, q):
         pl.set_knots(knots[lo:hi])
         outs = []
         for _ in range(3):
-            outs.append(pl.step("mppi", np.array([0.05]), index_offset=lo).cpu().numpy().copy())
+            outs.append(pl.step(optimizer, np.array(params), index_offset=lo).cpu().numpy().copy())
         torch.cuda.synchronize()
         q.put((rank, outs, pl.d_reward.cpu().numpy(), lo, hi))
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("optimizer,params", [("mppi", (0.05,)), ("cem", (3, 0.1, 1.0)), ("ps", ())])
 @pytest.mark.parametrize("mode", ["peer", "nccl"])
 @pytest.mark.timeout(300)
-def test_two_gpu_mppi_step_matches_unsharded(mode):
+def test_two_gpu_step_matches_unsharded(mode, optimizer, params):
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -80,8 +86,8 @@ def test_two_gpu_mppi_step_matches_unsharded(mode):
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 1000 + (0 if mode == "peer" else 1)
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, mode, q)) for r in range(2)]
+    port = 29600 + (os.getpid() * 7 + hash((mode, optimizer)) % 97) % 2000
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, mode, q, optimizer, params)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
@@ -92,7 +98,8 @@ def test_two_gpu_mppi_step_matches_unsharded(mode):
     rewards = np.empty(1000)
     for rank, outs, r, lo, hi in res:
         rewards[lo:hi] = r
-    ref = op.mppi_update(knots, rewards, 0.05).ravel()
+    ref = {"mppi": lambda: op.mppi_update(knots, rewards, 0.05), "cem": lambda: op.cem_update(knots, rewards, 3, 0.1, 1.0)[0],
+           "ps": lambda: op.ps_update(knots, rewards)}[optimizer]().ravel()
     for rank, outs, r, lo, hi in res:
         for o in outs:
             np.testing.assert_allclose(o, ref, rtol=1e-11, atol=1e-13)   # identical nominal on every rank, every step
