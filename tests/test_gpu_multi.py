@@ -21,8 +21,8 @@ def _problem(N):
     return x0, knots, basis, params
 
 
-@pytest.mark.parametrize("optimizer,params", [("mppi", [0.05]), ("cem", [3, 0.1, 1.0]), ("ps", [])])
-def test_peer_exchange_path_on_one_rank(optimizer, params):
+@pytest.mark.parametrize("optimizer,opt_params", [("mppi", [0.05]), ("cem", [3, 0.1, 1.0]), ("ps", [])])
+def test_peer_exchange_path_on_one_rank(optimizer, opt_params):
     """finalize=2 with world_size 1: the exchange buffer, flags and epochs work (several consecutive steps)."""
     from judo_b200.dist import ShardedPlanner
     from oracle import plan as op
@@ -35,7 +35,7 @@ def test_peer_exchange_path_on_one_rank(optimizer, params):
     pl.set_problem(x0, basis, params)
     pl.set_knots(knots)
     for _ in range(4):
-        nominal = pl.step(optimizer, np.array(params)).cpu().numpy().reshape(4, 1)
+        nominal = pl.step(optimizer, np.array(opt_params)).cpu().numpy().reshape(4, 1)
     rewards = pl.d_reward.cpu().numpy()
     ref = {"mppi": lambda: op.mppi_update(knots, rewards, 0.05), "cem": lambda: op.cem_update(knots, rewards, 3, 0.1, 1.0)[0],
            "ps": lambda: op.ps_update(knots, rewards)}[optimizer]()
@@ -44,7 +44,7 @@ def test_peer_exchange_path_on_one_rank(optimizer, params):
         np.testing.assert_allclose(pl.d_sigma.cpu().numpy().reshape(4, 1), op.cem_update(knots, rewards, 3, 0.1, 1.0)[1], rtol=1e-11)
 
 
-def _rank_main(rank, world, port, mode, q, optimizer="mppi", params=(0.05,)):
+def _rank_main(rank, world, port, mode, q, optimizer="mppi", opt_params=(0.05,)):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -65,17 +65,20 @@ def _rank_main(rank, world, port, mode, q, optimizer="mppi", params=(0.05,)):
         pl.set_knots(knots[lo:hi])
         outs = []
         for _ in range(3):
-            outs.append(pl.step(optimizer, np.array(params), index_offset=lo).cpu().numpy().copy())
+            outs.append(pl.step(optimizer, np.array(opt_params), index_offset=lo).cpu().numpy().copy())
         torch.cuda.synchronize()
         q.put((rank, outs, pl.d_reward.cpu().numpy(), lo, hi))
+    except Exception as e:  # noqa: BLE001 — report instead of letting the parent wait for its time-out
+        q.put((rank, repr(e), None, 0, 0))
+        raise
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("optimizer,params", [("mppi", (0.05,)), ("cem", (3, 0.1, 1.0)), ("ps", ())])
+@pytest.mark.parametrize("optimizer,opt_params", [("mppi", (0.05,)), ("cem", (3, 0.1, 1.0)), ("ps", ())])
 @pytest.mark.parametrize("mode", ["peer", "nccl"])
 @pytest.mark.timeout(300)
-def test_two_gpu_step_matches_unsharded(mode, optimizer, params):
+def test_two_gpu_step_matches_unsharded(mode, optimizer, opt_params):
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -87,10 +90,12 @@ def test_two_gpu_step_matches_unsharded(mode, optimizer, params):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() * 7 + hash((mode, optimizer)) % 97) % 2000
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, mode, q, optimizer, params)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, mode, q, optimizer, opt_params)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=240) for _ in procs]
+    res = [q.get(timeout=120) for _ in procs]
+    for r in res:
+        assert r[2] is not None, f"rank {r[0]} failed: {r[1]}"
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
