@@ -205,10 +205,26 @@ class Controller:
             cand_norm = np.clip(self.optimizer.sample_control_knots(nominal_knots_normalized), lo, hi)
             self.candidate_knots = self.action_normalizer.denormalize(cand_norm)
             self.task.pre_rollout(self.current_state)
-            if self._can_fuse() and isinstance(self.action_normalizer, IdentityNormalizer):
+            if self._can_fuse():
+                # The kernel rolls out (and updates over) the DENORMALISED candidates.  Normalizers are affine per control
+                # dimension (normalization.py), and every update is a convex combination of candidates, so mapping the
+                # resulting nominal back equals updating in normalised space; CEM's sigma scales by 1/|slope| before its clip.
+                identity = isinstance(self.action_normalizer, IdentityNormalizer)
+                fparams = self.optimizer.fused_params()
+                if not identity and self.optimizer.name == "cem":
+                    fparams = np.array([fparams[0], 0.0, np.inf])
                 res = self.engine.plan_step(self.current_state, self.candidate_knots, basis, self.task.cost_params(self.system_metadata),
-                                            self.optimizer.name, self.optimizer.fused_params(), want_rewards=True,
+                                            self.optimizer.name, fparams, want_rewards=True,
                                             n_elite=min(self.max_num_traces, self.optimizer_cfg.num_rollouts))
+                if not identity:
+                    # exact inverse of denormalize (normalize() is NOT it: the reference's eps terms make the pair asymmetric)
+                    nu = self.model.nu
+                    offset = self.action_normalizer.denormalize(np.zeros(nu))
+                    slope = self.action_normalizer.denormalize(np.ones(nu)) - offset
+                    res = dict(res)
+                    res["nominal"] = (res["nominal"] - offset) / slope
+                    if self.optimizer.name == "cem":
+                        res["sigma"] = np.clip(res["sigma"] / np.abs(slope), self.optimizer.sigma_min, self.optimizer.sigma_max)
                 self.rewards = res["rewards"]
                 self._elite = res["elite"]
                 nominal_knots_normalized = self.optimizer.accept_fused(res)

@@ -64,23 +64,42 @@ def test_update_action_shapes(task, opt):
     assert np.all(ctrl.candidate_knots >= lo - 1e-12) and np.all(ctrl.candidate_knots <= hi + 1e-12)
 
 
+@pytest.mark.parametrize("optimizer", ["mppi", "cem", "ps"])
 @pytest.mark.parametrize("normalizer", ["min_max", "running"])
-def test_action_normalizers_route_through_contract_a(normalizer, temp_np_seed):
-    """Non-identity normalizers take the rollout + reward + update path; candidates stay inside ctrlrange and the running
-    statistics equal numpy's over the candidates (reference test_action_normalization.py)."""
+def test_action_normalizers(normalizer, optimizer, temp_np_seed):
+    """Non-identity normalizers: candidates stay inside ctrlrange, the running statistics equal numpy's over the candidates
+    (reference test_action_normalization.py), and the fused step (update over denormalised candidates, affine map applied to
+    the result) equals the contract-A step that updates in normalised space like controller.py:253-288."""
+    from judo_b200.controller import make_controller
+
+    out = {}
+    for fused in (True, False):
+        with temp_np_seed(3):
+            ctrl = make_controller("cylinder_push", optimizer)
+            ctrl.fused = fused
+            ctrl.controller_cfg.action_normalizer = normalizer
+            ctrl.action_normalizer = ctrl._init_action_normalizer()
+            for _ in range(3):
+                ctrl.update_action()
+            assert np.all(np.abs(ctrl.candidate_knots) <= 10.0 + 1e-12)
+            if normalizer == "running":
+                assert ctrl.action_normalizer.count > 0 and np.all(np.isfinite(ctrl.action_normalizer.std))
+            out[fused] = (ctrl.nominal_knots.copy(), np.array(getattr(ctrl.optimizer, "sigma", 0.0), dtype=float).copy())
+    np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(out[True][1], out[False][1], rtol=1e-9, atol=1e-11)
+
+
+def test_running_normalizer_statistics(temp_np_seed):
     from judo_b200.controller import make_controller
 
     with temp_np_seed(3):
         ctrl = make_controller("cartpole", "mppi")
-        ctrl.controller_cfg.action_normalizer = normalizer
+        ctrl.controller_cfg.action_normalizer = "running"
         ctrl.action_normalizer = ctrl._init_action_normalizer()
         ctrl.update_action()
-        assert np.all(np.abs(ctrl.candidate_knots) <= 1.8 + 1e-12)
-        if normalizer == "running":
-            flat = ctrl.candidate_knots.reshape(-1, 1)
-            np.testing.assert_allclose(ctrl.action_normalizer.mean, flat.mean(0), rtol=1e-12)
-            np.testing.assert_allclose(ctrl.action_normalizer.std, np.clip(flat.std(0), 1e-5, 1e3), rtol=1e-9)
-        assert ctrl.states.shape == (32, ctrl.num_timesteps, 4)
+        flat = ctrl.candidate_knots.reshape(-1, 1)
+        np.testing.assert_allclose(ctrl.action_normalizer.mean, flat.mean(0), rtol=1e-12)
+        np.testing.assert_allclose(ctrl.action_normalizer.std, np.clip(flat.std(0), 1e-5, 1e3), rtol=1e-9)
 
 
 def test_user_task_with_numpy_reward_uses_gpu_rollouts(temp_np_seed):
