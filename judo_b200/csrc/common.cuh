@@ -4,8 +4,19 @@
 // third-party wheel: judo/utils/mj_rollout_backend.py:36,84).  The per-thread Newton solver below is the
 // thread-per-rollout form used by the two small tasks (cartpole, cylinder_push: <=4 dofs, <=4 rows).
 #pragma once
+#ifdef B2_HOST_SIM
+#include "warpsim.h"  // tests/warpsim: CPU emulation of the device code for the no-GPU test tier; never part of the shipped library
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
+
+// dynamic shared memory of the calling kernel as `type* name`
+#ifdef B2_HOST_SIM
+#define B2_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(wsim::dyn_smem())
+#else
+#define B2_DYNAMIC_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
 
 #define B2_MINVAL 1e-15
 #define B2_MINIMP 0.0001
@@ -15,6 +26,18 @@
 namespace b2 {
 
 // ------------------------------------------------------------------ 1-D TMA bulk copy (global -> shared) + mbarrier
+#ifdef B2_HOST_SIM
+// emulation: the barrier word counts completed phases (low 32 bits) and pending bytes (high 32 bits)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) { *bar += (uint64_t)bytes << 32; if ((*bar >> 32) == 0) *bar += 1; }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) { while (((*bar) & 1u) == phase) wsim::spin_yield(); }
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  memcpy(dst_smem, src_gmem, bytes);
+  *bar -= (uint64_t)bytes << 32;
+  if ((*bar >> 32) == 0) *bar += 1;
+}
+__device__ __forceinline__ void fence_barrier_init() {}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -42,6 +65,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#endif
 
 // ------------------------------------------------------------------ soft-constraint parameters
 // getimpedance: sigmoid d(r) from solimp = (d0, dwidth, width, midpoint, power)

@@ -44,6 +44,10 @@ constexpr int EP_XCHG_FLAGS = 8;                   // u64 flags in front of the 
 constexpr int EP_XCHG_STRIDE = 2 + 96;             // doubles per rank slot (beta, S, V[<=96])
 constexpr size_t EP_XCHG_BYTES = 8 * EP_XCHG_FLAGS + 2 * 8 * (size_t)EP_XCHG_STRIDE * 8;  // slots double-buffered by epoch parity
 
+#ifdef B2_HOST_SIM
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { *p = v; }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { return *p; }
+#else
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -52,6 +56,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+#endif
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ double wsum(double v) {

@@ -1264,7 +1264,7 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
                                                            int wstride, int prof, const SampleSpec smp, int index_offset) {
   const int sync_mode = prof >> 8;
   prof &= 255;
-  extern __shared__ __align__(16) unsigned char lsm_all[];
+  B2_DYNAMIC_SMEM(unsigned char, lsm_all);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int n = blockIdx.x * wpb + wib;
   const bool active = n < N;
@@ -1361,6 +1361,7 @@ __global__ void leap_reward_kernel(const double* __restrict__ states, int N, int
 }
 
 // ------------------------------------------------------------------ host side
+#ifndef B2_HOST_SIM
 inline int leap_create(LeapModel** out, const double* consts, size_t n, std::string* err) {
   if (n != sizeof(LeapModel) / sizeof(double)) { *err = "wrong number of task constants"; return 1; }
   LeapModel* d = nullptr;
@@ -1418,5 +1419,6 @@ inline int leap_reward_launch(const LeapModel* m, const double* d_states, int N,
   if (e != cudaSuccess) { *err = std::string("leap reward launch: ") + cudaGetErrorString(e); return 1; }
   return 0;
 }
+#endif  // !B2_HOST_SIM
 
 }  // namespace b2
