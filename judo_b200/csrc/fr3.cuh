@@ -1,0 +1,1068 @@
+// fr3.cuh — fr3_pick: warp-per-rollout reduced articulated-body integrator + phase-switched cost.
+//
+// One warp owns one rollout: 16 qpos / 15 dofs (free object + 7 arm hinges + 2 finger slides), state and all per-step work
+// arrays in shared memory.  Every stage of MuJoCo's mj_step that judo/models/xml/fr3_pick.xml switches on is restated and spread
+// over the 32 lanes: kinematics of the serial chain, composite-inertia mass matrix (lane per arm dof), RNE bias forces,
+// collision + signed distances of the 21 box pairs (lane per pair; GJK for the distance sensors), constraint rows
+// (joint equality, friction loss, joint limits, pyramidal contacts kept as 3 frame rows + a 3x3 weight per contact),
+// mj_makeImpedance, the primal Newton solver (dense 15x15 Hessian, warp Cholesky, register line search), position servos with
+// joint-level force clamps, implicitfast integration.  The collision GEOMETRY is reduced to the model's box geoms
+// (judo_b200/tasks/fr3_pick.py); the constraint/solver pipeline is the full one.
+#pragma once
+#include "epilogue.cuh"
+#include "geom.cuh"
+#include "sampling.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+namespace b2 {
+
+constexpr int FR_NQ = 16, FR_NV = 15, FR_NU = 8, FR_NS = 14, FR_NX = 31, FR_NCOST = 23;
+constexpr int FB = 11;        // moving bodies: 0 object, 1..7 links, 8 hand (welded to link 7), 9 left finger, 10 right finger
+constexpr int FNA = 9;        // arm dofs (global dof = 6 + j): 7 hinges, 2 finger slides
+constexpr int FNPAD = 10, FNPAIR = 21;  // pairs: 0 table-object, 1..10 table-pad, 11..20 object-pad
+constexpr int FMAXCON = 48;   // contacts kept per step (4 pyramid rows each)
+constexpr int FMAXS = 20;     // scalar rows: 1 equality + 9 friction loss + <= 9 active limits
+constexpr int FLD = 16;       // leading dimension of the dense matrices
+#ifndef B2_FULLMASK
+#define B2_FULLMASK 0xffffffffu
+#endif
+
+// All-double POD; field order == judo_b200/tasks/fr3_pick.py:fr3_consts.
+struct Fr3Model {
+  double dt, gravity[3], impratio, tolerance, ls_tolerance, meaninertia, iterations, ls_iterations;
+  double base_pos[3], base_quat[4];
+  double body_pos[FB][3], body_quat[FB][4], body_ipos[FB][3], body_imat[FB][9], body_mass[FB], body_inertia[FB][3], body_invw[FB];
+  double jnt_axis[FB][3];
+  double obj_inertia[3];
+  double dof_damping[FR_NV], dof_armature[FR_NV], dof_frictionloss[FR_NV], dof_invw[FR_NV];
+  double fr_solref[2], fr_solimp[5];
+  double lim_lo[FNA], lim_hi[FNA], lim_margin, lim_solref[2], lim_solimp[5];
+  double eq_solref[2], eq_solimp[5];
+  double kp[FR_NU], kv[FR_NU], ctrl_lo[FR_NU], ctrl_hi[FR_NU];
+  double frc_limited[FNA], frc_lo[FNA], frc_hi[FNA];
+  double table_pos[3], table_mat[9], table_size[3], obj_size[3];
+  double pad_body[FNPAD], pad_pos[FNPAD][3], pad_size[FNPAD][3];
+  double con_mu[3], con_solref[3][2], con_solimp[3][5];
+  double site_pos[3];
+  double cutoff;
+};
+
+// per-warp shared-memory work area
+struct Fr3Work {
+  double qpos[FR_NQ], qvel[FR_NV], warm[FR_NV], ctrl[FR_NU];
+  double xpos[FB][3], xmat[FB][9], xipos[FB][3], Iw[FB][6];
+  double anchor[FNA][3], axis[FNA][3];
+  double M[FNA][FLD], L[FNA][FLD], Ld[FLD];   // arm mass matrix, its (or M + h D's) Cholesky factor, reciprocal pivots
+  double H[FR_NV][FLD], Hd[FLD];              // Newton Hessian / factor
+  double qfrc_bias[FR_NV], qfrc_smooth[FR_NV], qacc_smooth[FR_NV], qacc[FR_NV], qfrc_constraint[FR_NV];
+  double Ma[FR_NV], grad[FR_NV], search[FR_NV], Mv[FR_NV];
+  double sD[FMAXS], sR[FMAXS], saref[FMAXS], sjar[FMAXS], sforce[FMAXS], sfl[FMAXS], ssign[FMAXS];
+  int sdof[FMAXS], sstate[FMAXS];
+  double cdist[FMAXCON];
+  double cgeo[FMAXCON][12];     // while rows are built: contact point (3) + frame (9); in the solver: jv (3), force (3), weight (6)
+  double cJ[FMAXCON][3][FR_NV]; // frame-row Jacobians (normal, tangent 1, tangent 2)
+  double cD[FMAXCON], cmu[FMAXCON], caref[FMAXCON][3], cjar[FMAXCON][3];
+  int ccls[FMAXCON], cbody[FMAXCON];
+  double pdist[FNPAIR + 3], sens[FR_NS];
+  int ncon, ns;
+  double cost, gauss;
+};
+
+enum { FST_SATISFIED = 0, FST_QUADRATIC = 1, FST_LINEARNEG = 2, FST_LINEARPOS = 3 };
+
+__device__ __forceinline__ double fwsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(B2_FULLMASK, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ kinematics (mj_kinematics + mj_comPos)
+// lane 0: the arm chain (serial by nature); lane 1: the free object; then lane per body for inertial frames / world inertias.
+__device__ inline void fr3_kinematics(const Fr3Model* __restrict__ m, Fr3Work* W, int lane) {
+  if (lane == 1) {
+    lquat_normalize(W->qpos + 3);
+#pragma unroll
+    for (int k = 0; k < 3; k++) W->xpos[0][k] = W->qpos[k];
+    lquat2mat(W->xmat[0], W->qpos + 3);
+  } else if (lane == 0) {
+    double ppos[3], pquat[4], pmat[9], hpos[3], hquat[4], hmat[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) ppos[k] = m->base_pos[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) pquat[k] = m->base_quat[k];
+    lquat2mat(pmat, pquat);
+    for (int b = 1; b < FB; b++) {
+      if (b == 10) {  // the right finger hangs off the hand too
+#pragma unroll
+        for (int k = 0; k < 3; k++) ppos[k] = hpos[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) pquat[k] = hquat[k];
+#pragma unroll
+        for (int k = 0; k < 9; k++) pmat[k] = hmat[k];
+      }
+      double pos[3], quat[4], t[3], mat[9];
+      lmat_vec(t, pmat, m->body_pos[b]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) pos[k] = ppos[k] + t[k];
+      lquat_mul(quat, pquat, m->body_quat[b]);
+      if (b <= 7) {  // hinge about the local axis through the body origin
+        const int j = b - 1;
+        double axis[3], dq[4], nq[4], sn, cs;
+        lquat2mat(mat, quat);
+        lmat_vec(axis, mat, m->jnt_axis[b]);
+        sincos(0.5 * W->qpos[7 + j], &sn, &cs);
+        dq[0] = cs; dq[1] = sn * m->jnt_axis[b][0]; dq[2] = sn * m->jnt_axis[b][1]; dq[3] = sn * m->jnt_axis[b][2];
+        lquat_mul(nq, quat, dq);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W->anchor[j][k] = pos[k]; W->axis[j][k] = axis[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) quat[k] = nq[k];
+      } else if (b >= 9) {  // slide along the local axis
+        const int j = b - 2;
+        double axis[3];
+        lquat2mat(mat, quat);
+        lmat_vec(axis, mat, m->jnt_axis[b]);
+        const double q = W->qpos[7 + j];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { pos[k] += axis[k] * q; W->anchor[j][k] = pos[k]; W->axis[j][k] = axis[k]; }
+      }
+      lquat_normalize(quat);
+      lquat2mat(mat, quat);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { W->xpos[b][k] = pos[k]; ppos[k] = pos[k]; }
+#pragma unroll
+      for (int k = 0; k < 4; k++) pquat[k] = quat[k];
+#pragma unroll
+      for (int k = 0; k < 9; k++) { W->xmat[b][k] = mat[k]; pmat[k] = mat[k]; }
+      if (b == 8) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) hpos[k] = pos[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) hquat[k] = quat[k];
+#pragma unroll
+        for (int k = 0; k < 9; k++) hmat[k] = mat[k];
+      }
+    }
+  }
+  __syncwarp();
+  if (lane < FB) {
+    const int b = lane;
+    double t[3], im[9];
+    lmat_vec(t, W->xmat[b], m->body_ipos[b]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) W->xipos[b][k] = W->xpos[b][k] + t[k];
+    lmat_mul(im, W->xmat[b], m->body_imat[b]);
+    int e = 0;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = r; c < 3; c++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) s += im[3 * r + k] * m->body_inertia[b][k] * im[3 * c + k];
+        W->Iw[b][e++] = s;  // xx xy xz yy yz zz
+      }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void fIw_mul(double* r, const double* I6, const double* v) {
+  r[0] = I6[0] * v[0] + I6[1] * v[1] + I6[2] * v[2];
+  r[1] = I6[1] * v[0] + I6[3] * v[1] + I6[4] * v[2];
+  r[2] = I6[2] * v[0] + I6[4] * v[1] + I6[5] * v[2];
+}
+
+// arm dof j moves bodies [fr3_sub_lo(j), fr3_sub_hi(j)]
+__device__ __forceinline__ int fr3_sub_lo(int j) { return j < 7 ? j + 1 : j + 2; }
+__device__ __forceinline__ int fr3_sub_hi(int j) { return j < 7 ? 10 : j + 2; }
+
+// ------------------------------------------------------------------ mass matrix (mj_crb) and bias forces (mj_rne)
+// lanes 0..8: column j of the arm mass matrix from the composite inertia of the subtree dof j moves;
+// lane 9: RNE with zero acceleration down and up the arm; lane 10: the free object.
+__device__ inline void fr3_mass_and_bias(const Fr3Model* __restrict__ m, Fr3Work* W, int lane) {
+  if (lane < FNA) {
+    const int j = lane, lo = fr3_sub_lo(j), hi = fr3_sub_hi(j);
+    double mc = 0, c[3] = {0, 0, 0};
+    for (int b = lo; b <= hi; b++) {
+      mc += m->body_mass[b];
+#pragma unroll
+      for (int k = 0; k < 3; k++) c[k] += m->body_mass[b] * W->xipos[b][k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) c[k] /= mc;
+    double Ic[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = lo; b <= hi; b++) {
+      const double d[3] = {W->xipos[b][0] - c[0], W->xipos[b][1] - c[1], W->xipos[b][2] - c[2]};
+      const double mb = m->body_mass[b], dd = ldot3(d, d);
+      Ic[0] += W->Iw[b][0] + mb * (dd - d[0] * d[0]); Ic[1] += W->Iw[b][1] - mb * d[0] * d[1]; Ic[2] += W->Iw[b][2] - mb * d[0] * d[2];
+      Ic[3] += W->Iw[b][3] + mb * (dd - d[1] * d[1]); Ic[4] += W->Iw[b][4] - mb * d[1] * d[2];
+      Ic[5] += W->Iw[b][5] + mb * (dd - d[2] * d[2]);
+    }
+    // momentum of the composite body under unit velocity of dof j: linear h, angular (about c) Lc
+    double h[3], Lc[3] = {0, 0, 0};
+    if (j < 7) {
+      const double r[3] = {c[0] - W->anchor[j][0], c[1] - W->anchor[j][1], c[2] - W->anchor[j][2]};
+      double t[3];
+      lcross3(t, W->axis[j], r);
+#pragma unroll
+      for (int k = 0; k < 3; k++) h[k] = mc * t[k];
+      fIw_mul(Lc, Ic, W->axis[j]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; k++) h[k] = mc * W->axis[j][k];
+    }
+    for (int i = 0; i < FNA; i++) {
+      double v = 0;
+      if (i < 7 && i <= j) {  // hinge ancestor (or j itself)
+        const double r[3] = {c[0] - W->anchor[i][0], c[1] - W->anchor[i][1], c[2] - W->anchor[i][2]};
+        double t[3];
+        lcross3(t, r, h);
+        v = W->axis[i][0] * (Lc[0] + t[0]) + W->axis[i][1] * (Lc[1] + t[1]) + W->axis[i][2] * (Lc[2] + t[2]);
+      } else if (i == j) v = ldot3(W->axis[i], h);
+      else continue;  // not an ancestor: filled by symmetry (or zero between the two fingers)
+      if (i == j) v += m->dof_armature[6 + j];
+      W->M[i][j] = v;
+      W->M[j][i] = v;
+    }
+    if (j == 7) { W->M[7][8] = 0; W->M[8][7] = 0; }
+  } else if (lane == 9) {
+    // classical Newton-Euler in world coordinates (base: w = 0, a = -g); body order 1..10, parent of 9 and 10 is 8
+    double w[FB][3], al[FB][3], ao[FB][3], F[FB][3], N0[FB][3];
+    double Wv[3] = {0, 0, 0}, A[3] = {0, 0, 0}, Ac[3], P[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { Ac[k] = -m->gravity[k]; P[k] = m->base_pos[k]; }
+    for (int b = 1; b < FB; b++) {
+      if (b == 10) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { Wv[k] = w[8][k]; A[k] = al[8][k]; Ac[k] = ao[8][k]; P[k] = W->xpos[8][k]; }
+      }
+      double r[3], t[3], t2[3];
+      if (b <= 7) {
+        const int j = b - 1;
+#pragma unroll
+        for (int k = 0; k < 3; k++) r[k] = W->anchor[j][k] - P[k];
+        lcross3(t, Wv, r); lcross3(t2, Wv, t); lcross3(t, A, r);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { Ac[k] += t[k] + t2[k]; P[k] = W->anchor[j][k]; }
+        const double qd = W->qvel[6 + j];
+        const double u[3] = {W->axis[j][0] * qd, W->axis[j][1] * qd, W->axis[j][2] * qd};
+        lcross3(t, Wv, u);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { A[k] += t[k]; Wv[k] += u[k]; }
+      } else if (b >= 9) {
+        const int j = b - 2;
+        const double qd = W->qvel[6 + j];
+        const double u[3] = {W->axis[j][0] * qd, W->axis[j][1] * qd, W->axis[j][2] * qd};
+        lcross3(t, Wv, u);
+#pragma unroll
+        for (int k = 0; k < 3; k++) Ac[k] += 2 * t[k];  // Coriolis term of the sliding origin
+      }
+      // move the reference point to the body origin
+#pragma unroll
+      for (int k = 0; k < 3; k++) r[k] = W->xpos[b][k] - P[k];
+      lcross3(t, Wv, r); lcross3(t2, Wv, t); lcross3(t, A, r);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { Ac[k] += t[k] + t2[k]; P[k] = W->xpos[b][k]; }
+#pragma unroll
+      for (int k = 0; k < 3; k++) { w[b][k] = Wv[k]; al[b][k] = A[k]; ao[b][k] = Ac[k]; }
+      // wrench of this body about the world origin
+      double ac[3], Iwa[3], Iww[3], n[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) r[k] = W->xipos[b][k] - W->xpos[b][k];
+      lcross3(t, Wv, r); lcross3(t2, Wv, t); lcross3(t, A, r);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { ac[k] = Ac[k] + t[k] + t2[k]; F[b][k] = m->body_mass[b] * ac[k]; }
+      fIw_mul(Iwa, W->Iw[b], A);
+      fIw_mul(Iww, W->Iw[b], Wv);
+      lcross3(t, Wv, Iww);
+      lcross3(n, W->xipos[b], F[b]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) N0[b][k] = Iwa[k] + t[k] + n[k];
+    }
+    for (int b = FB - 1; b >= 1; b--) {
+      if (b <= 7) {
+        const int j = b - 1;
+        double t[3], nn[3];
+        lcross3(t, W->anchor[j], F[b]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) nn[k] = N0[b][k] - t[k];
+        W->qfrc_bias[6 + j] = ldot3(W->axis[j], nn);
+      } else if (b >= 9) W->qfrc_bias[6 + b - 2] = ldot3(W->axis[b - 2], F[b]);
+      const int p = b >= 9 ? 8 : b - 1;
+      if (p >= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { F[p][k] += F[b][k]; N0[p][k] += N0[b][k]; }
+      }
+    }
+  } else if (lane == 10) {
+    const double wl[3] = {W->qvel[3], W->qvel[4], W->qvel[5]};
+    const double Iwl[3] = {m->obj_inertia[0] * wl[0], m->obj_inertia[1] * wl[1], m->obj_inertia[2] * wl[2]};
+    double g[3];
+    lcross3(g, wl, Iwl);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { W->qfrc_bias[k] = -m->body_mass[0] * m->gravity[k]; W->qfrc_bias[3 + k] = g[k]; }
+  }
+  __syncwarp();
+}
+
+// y_i = (M x)_i: object block is diagonal (mass, principal inertia in the body frame), arm block dense
+__device__ __forceinline__ double fr3_mulM_row(const Fr3Model* __restrict__ m, const Fr3Work* W, const double* x, int i) {
+  if (i < 3) return m->body_mass[0] * x[i];
+  if (i < 6) return m->obj_inertia[i - 3] * x[i];
+  const double* row = W->M[i - 6];
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < FNA; k++) s += row[k] * x[6 + k];
+  return s;
+}
+
+// ------------------------------------------------------------------ dense warp Cholesky: lane i owns row i
+// In place on the lower triangle of A (n x n, leading dimension FLD); dinv[k] = 1 / L_kk.
+__device__ inline void warp_chol(double (*A)[FLD], double* dinv, int n, int lane) {
+  for (int k = 0; k < n; k++) {
+    double d = A[k][k];
+    if (d < B2_MINVAL) d = B2_MINVAL;
+    const double rs = rsqrt(d);
+    double l = 0;
+    if (lane == k) dinv[k] = rs;
+    if (lane > k && lane < n) { l = A[lane][k] * rs; A[lane][k] = l; }
+    __syncwarp();
+    if (lane > k && lane < n)
+      for (int j = k + 1; j <= lane; j++) A[lane][j] -= l * A[j][k];
+    __syncwarp();
+  }
+}
+// x <- (L L^T)^-1 x with x_lane in a register (lanes >= n pass 0); column-oriented substitutions, one shuffle per column
+__device__ inline double warp_chol_solve(const double (*A)[FLD], const double* dinv, int n, double x, int lane) {
+  const double di = lane < n ? dinv[lane] : 0.0;
+  for (int k = 0; k < n; k++) {
+    const double yk = __shfl_sync(B2_FULLMASK, x * di, k);
+    if (lane == k) x = yk;
+    else if (lane > k && lane < n) x -= A[lane][k] * yk;
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    const double xk = __shfl_sync(B2_FULLMASK, x * di, k);
+    if (lane == k) x = xk;
+    else if (lane < k) x -= A[k][lane] * xk;
+  }
+  return x;
+}
+
+// arm block: factorise M (+ diag(add)) into W->L; object block is diagonal
+__device__ inline void fr3_factor_arm(Fr3Work* W, const double* add /* [FNA] or null */, int lane) {
+  if (lane < FNA)
+    for (int j = 0; j <= lane; j++) W->L[lane][j] = W->M[lane][j] + ((add && j == lane) ? add[lane] : 0.0);
+  __syncwarp();
+  warp_chol(W->L, W->Ld, FNA, lane);
+}
+
+// ------------------------------------------------------------------ collision + distance sensors, lane per box pair
+__device__ inline void fr3_pair_geoms(const Fr3Model* __restrict__ m, const Fr3Work* W, int p, const double** p1, const double** m1,
+                                      const double** s1, double* p2, const double** m2, const double** s2, int* cls, int* body) {
+  if (p == 0) {  // table - object
+    *p1 = m->table_pos; *m1 = m->table_mat; *s1 = m->table_size;
+    p2[0] = W->xpos[0][0]; p2[1] = W->xpos[0][1]; p2[2] = W->xpos[0][2];
+    *m2 = W->xmat[0]; *s2 = m->obj_size; *cls = 0; *body = 0;
+    return;
+  }
+  const int k = (p - 1) % FNPAD, b = (int)m->pad_body[k];
+  double t[3];
+  lmat_vec(t, W->xmat[b], m->pad_pos[k]);
+  p2[0] = W->xpos[b][0] + t[0]; p2[1] = W->xpos[b][1] + t[1]; p2[2] = W->xpos[b][2] + t[2];
+  *m2 = W->xmat[b]; *s2 = m->pad_size[k]; *body = b;
+  if (p <= FNPAD) { *p1 = m->table_pos; *m1 = m->table_mat; *s1 = m->table_size; *cls = 1; }
+  else { *p1 = W->xpos[0]; *m1 = W->xmat[0]; *s1 = m->obj_size; *cls = 2; }
+}
+
+// dist_mode: 0 = every distance sensor exactly (contract A); 1 = what the cost needs (object-table value, finger-table sign)
+__device__ inline void fr3_collision(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, int dist_mode) {
+  LRaw raw[8];
+  int n = 0, cls = 0, body = 0;
+  if (lane < FNPAIR) {
+    const double *p1, *m1, *s1, *m2, *s2;
+    double p2[3];
+    fr3_pair_geoms(m, W, lane, &p1, &m1, &s1, p2, &m2, &s2, &cls, &body);
+    n = l_box_box(p1, m1, s1, p2, m2, s2, 0.0, raw, 8);
+    const bool want = dist_mode == 0 || lane <= FNPAD;
+    W->pdist[lane] = want ? l_box_box_distance(p1, m1, s1, p2, m2, s2, m->cutoff, dist_mode == 0 || lane == 0) : m->cutoff;
+  }
+  // ordered slot allocation (pair order == the oracle's): exclusive prefix of n over the lanes
+  int pre = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(B2_FULLMASK, pre, o); if (lane >= o) pre += v; }
+  const int total = __shfl_sync(B2_FULLMASK, pre, 31);
+  pre -= n;
+  for (int i = 0; i < n; i++) {
+    const int slot = pre + i;
+    if (slot < FMAXCON) {
+      W->cdist[slot] = raw[i].dist;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { W->cgeo[slot][k] = raw[i].pos[k]; W->cgeo[slot][3 + k] = raw[i].normal[k]; }
+      l_make_frame(W->cgeo[slot] + 3);
+      W->ccls[slot] = cls; W->cbody[slot] = body;
+    }
+  }
+  if (lane == 0) W->ncon = total < FMAXCON ? total : FMAXCON;
+  __syncwarp();
+  // sensors: 5 body-pair distances (min over the pads, clipped to +-cutoff), ee z axis, object position, grasp site
+  if (lane < 5) {
+    const int lo = lane == 0 ? 11 : lane == 1 ? 16 : lane == 2 ? 1 : lane == 3 ? 6 : 0, cnt = lane == 4 ? 1 : 5;
+    double best = m->cutoff;
+    for (int k = 0; k < cnt; k++) best = fmin(best, W->pdist[lo + k]);
+    W->sens[lane] = fmin(fmax(best, -m->cutoff), m->cutoff);
+  } else if (lane < 8) W->sens[lane] = W->xmat[8][3 * (lane - 5) + 2];
+  else if (lane < 11) W->sens[lane] = W->xpos[0][lane - 8];
+  else if (lane < 14) {
+    const int k = lane - 11;
+    W->sens[lane] = W->xpos[8][k] + W->xmat[8][3 * k] * m->site_pos[0] + W->xmat[8][3 * k + 1] * m->site_pos[1] + W->xmat[8][3 * k + 2] * m->site_pos[2];
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ constraint rows (mj_makeConstraint + mj_makeImpedance)
+__device__ __forceinline__ void fr3_KB(const double* solref, const double* solimp, double dt, double* K, double* B) {
+  double ref0 = solref[0];
+  const double ref1 = solref[1], dmax = fmin(fmax(solimp[1], B2_MINIMP), B2_MAXIMP);
+  if (ref0 > 0) {
+    if (ref0 < 2 * dt) ref0 = 2 * dt;
+    *K = 1 / fmax(B2_MINVAL, dmax * dmax * ref0 * ref0 * ref1 * ref1);
+    *B = 2 / fmax(B2_MINVAL, dmax * ref0);
+  } else { *K = -ref0 / fmax(B2_MINVAL, dmax * dmax); *B = -ref1 / fmax(B2_MINVAL, dmax); }
+}
+// J x for scalar row r (row 0 is the equality q13 - q14)
+__device__ __forceinline__ double fr3_srow_dot(const Fr3Work* W, int r, const double* x) {
+  return r == 0 ? x[13] - x[14] : W->ssign[r] * x[W->sdof[r]];
+}
+__device__ __forceinline__ double fr3_cJ_dot(const double* J, int cls, const double* x) {
+  double s = 0;
+  if (cls != 1) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) s += J[i] * x[i];
+  }
+  if (cls != 0) {
+#pragma unroll
+    for (int i = 6; i < FR_NV; i++) s += J[i] * x[i];
+  }
+  return s;
+}
+
+__device__ inline void fr3_make_constraint(const Fr3Model* __restrict__ m, Fr3Work* W, int lane) {
+  // scalar rows: equality, friction loss (arm dof lane-1), limits (joint-major; lower before upper; only one side can be active)
+  bool lim_act = false;
+  double ldist = 0, lsign = 0;
+  if (lane < FNA) {
+    const double q = W->qpos[7 + lane];
+    const double dlo = q - m->lim_lo[lane], dhi = m->lim_hi[lane] - q;
+    if (dlo < m->lim_margin) { lim_act = true; ldist = dlo; lsign = 1; }
+    else if (dhi < m->lim_margin) { lim_act = true; ldist = dhi; lsign = -1; }
+  }
+  const unsigned ml = __ballot_sync(B2_FULLMASK, lim_act);
+  const int ns = 10 + __popc(ml);
+  double pos = 0, margin = 0, vel = 0, diagA = 0, fl = 0;
+  const double *solref = m->fr_solref, *solimp = m->fr_solimp;
+  int r = -1;
+  bool friction_row = false;
+  if (lane == 31) {  // the equality row is built by an otherwise idle lane
+    r = 0;
+    pos = W->qpos[14] - W->qpos[15]; vel = W->qvel[13] - W->qvel[14]; diagA = m->dof_invw[13] + m->dof_invw[14];
+    solref = m->eq_solref; solimp = m->eq_solimp;
+    W->sdof[0] = 13; W->ssign[0] = 1;
+  }
+  if (lane < FNA) {
+    const int rr = 1 + lane, dof = 6 + lane;
+    double K, B;
+    fr3_KB(m->fr_solref, m->fr_solimp, m->dt, &K, &B);
+    const double imp = impedance(m->fr_solimp, 0.0, 0.0);
+    const double R = fmax(B2_MINVAL, (1 - imp) * m->dof_invw[dof] / imp);
+    W->sdof[rr] = dof; W->ssign[rr] = 1; W->sfl[rr] = m->dof_frictionloss[dof];
+    W->sR[rr] = R; W->sD[rr] = 1 / R; W->saref[rr] = -B * W->qvel[dof];
+    if (lim_act) {
+      r = 10 + __popc(ml & ((1u << lane) - 1));
+      pos = ldist; margin = m->lim_margin; vel = lsign * W->qvel[dof]; diagA = m->dof_invw[dof];
+      solref = m->lim_solref; solimp = m->lim_solimp;
+      W->sdof[r] = dof; W->ssign[r] = lsign;
+    }
+  }
+  if (r >= 0) {
+    double K, B;
+    fr3_KB(solref, solimp, m->dt, &K, &B);
+    const double imp = impedance(solimp, pos, margin);
+    const double R = fmax(B2_MINVAL, (1 - imp) * diagA / imp);
+    W->sfl[r] = fl; W->sR[r] = R; W->sD[r] = 1 / R;
+    W->saref[r] = -B * vel - (friction_row ? 0.0 : K) * imp * (pos - margin);
+  }
+  if (lane == 0) W->ns = ns;
+  const int ncon = W->ncon;
+  // contact frame-row Jacobians: lane per (contact, axis);  J = frame_a . (Jp(body2) - Jp(body1)) at the contact point
+  for (int e = lane; e < 3 * ncon; e += 32) {
+    const int c = e / 3, a = e - 3 * c, cls = W->ccls[c], b = W->cbody[c];
+    const double* p = W->cgeo[c];
+    const double* fr = W->cgeo[c] + 3 + 3 * a;
+    double* J = W->cJ[c][a];
+    // object: geom2 of class 0 (+), geom1 of class 2 (-), absent from class 1
+    const double so = cls == 0 ? 1.0 : cls == 2 ? -1.0 : 0.0;
+    const double ro[3] = {p[0] - W->xpos[0][0], p[1] - W->xpos[0][1], p[2] - W->xpos[0][2]};
+#pragma unroll
+    for (int k = 0; k < 3; k++) J[k] = so * fr[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double ax[3] = {W->xmat[0][k], W->xmat[0][3 + k], W->xmat[0][6 + k]};
+      double cr[3];
+      lcross3(cr, ax, ro);
+      J[3 + k] = so * ldot3(fr, cr);
+    }
+    // pad on finger body b (9 or 10): geom2 of classes 1 and 2 (+): the 7 hinges and that finger's slide
+#pragma unroll
+    for (int j = 0; j < FNA; j++) {
+      double v = 0;
+      if (cls != 0) {
+        if (j < 7) {
+          const double rr[3] = {p[0] - W->anchor[j][0], p[1] - W->anchor[j][1], p[2] - W->anchor[j][2]};
+          double cr[3];
+          lcross3(cr, W->axis[j], rr);
+          v = ldot3(fr, cr);
+        } else if (j + 2 == b) v = ldot3(fr, W->axis[j]);
+      }
+      J[6 + j] = v;
+    }
+  }
+  __syncwarp();
+  // per contact: impedance, common pyramid-edge R, reference accelerations in the (n, t1, t2) basis
+  for (int c = lane; c < ncon; c += 32) {
+    const int cls = W->ccls[c], b = W->cbody[c];
+    const double mu = m->con_mu[cls];
+    double K, B;
+    fr3_KB(m->con_solref[cls], m->con_solimp[cls], m->dt, &K, &B);
+    const double imp = impedance(m->con_solimp[cls], W->cdist[c], 0.0);
+    const double tran = (cls == 1 ? 0.0 : m->body_invw[0]) + (cls == 0 ? 0.0 : m->body_invw[b]);
+    const double R0 = fmax(B2_MINVAL, (1 - imp) * (tran + mu * mu * tran) / imp);
+    const double R1 = R0 / fmax(B2_MINVAL, m->impratio);
+    const double mureg = mu * sqrt(R1 / R0);
+    const double Rpy = 2 * mureg * mureg * R0;
+    W->cD[c] = 1 / Rpy; W->cmu[c] = mu;
+    const double vn = fr3_cJ_dot(W->cJ[c][0], cls, W->qvel), v1 = fr3_cJ_dot(W->cJ[c][1], cls, W->qvel), v2 = fr3_cJ_dot(W->cJ[c][2], cls, W->qvel);
+    W->caref[c][0] = -B * vn - K * imp * W->cdist[c];
+    W->caref[c][1] = -B * v1;
+    W->caref[c][2] = -B * v2;
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ Newton solver (mj_solNewton, primal, pyramidal cones)
+// scalar row at x: returns cost, writes force and state (row 0: equality, rows 1..9: friction loss, rest: limits)
+__device__ __forceinline__ double fr3_srow_eval(const Fr3Work* W, int r, double x, double* force, int* state) {
+  const double D = W->sD[r];
+  if (r == 0) { *force = -D * x; *state = FST_QUADRATIC; return 0.5 * D * x * x; }
+  if (r < 10) {
+    const double f = W->sfl[r], R = W->sR[r];
+    if (x <= -R * f) { *force = f; *state = FST_LINEARNEG; return -0.5 * R * f * f - f * x; }
+    if (x >= R * f) { *force = -f; *state = FST_LINEARPOS; return -0.5 * R * f * f + f * x; }
+    *force = -D * x; *state = FST_QUADRATIC; return 0.5 * D * x * x;
+  }
+  if (x < 0) { *force = -D * x; *state = FST_QUADRATIC; return 0.5 * D * x * x; }
+  *force = 0; *state = FST_SATISFIED; return 0;
+}
+// one pyramidal contact at residuals r = (rn, rt1, rt2): the 4 edge rows are rn +- mu rt_a.  Returns the cost; writes the force in the
+// (n, t1, t2) basis and, optionally, the 3x3 weight (nn, nt1, nt2, t1t1, t1t2, t2t2) of its Hessian term.
+__device__ __forceinline__ double fr3_contact_eval(double D, double mu, const double* r, double* f, double* Wt) {
+  double cost = 0, fn = 0, ft[2] = {0, 0}, cnt[2] = {0, 0}, sg[2] = {0, 0};
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const double sgn = s == 0 ? 1.0 : -1.0;
+      const double x = r[0] + sgn * mu * r[1 + a];
+      if (x < 0) { const double fr = -D * x; cost += 0.5 * D * x * x; fn += fr; ft[a] += sgn * mu * fr; cnt[a] += 1; sg[a] += sgn; }
+    }
+  f[0] = fn; f[1] = ft[0]; f[2] = ft[1];
+  if (Wt) {
+    Wt[0] = D * (cnt[0] + cnt[1]); Wt[1] = D * mu * sg[0]; Wt[2] = D * mu * sg[1];
+    Wt[3] = D * mu * mu * cnt[0]; Wt[4] = 0; Wt[5] = D * mu * mu * cnt[1];
+  }
+  return cost;
+}
+
+// jar = J qacc - aref for every row; Ma = M qacc
+__device__ __noinline__ void fr3_set_point(const Fr3Model* __restrict__ m, Fr3Work* W, const double* qacc, int lane) {
+  if (lane < FR_NV) W->Ma[lane] = fr3_mulM_row(m, W, qacc, lane);
+  const int ns = W->ns, ncon = W->ncon;
+  if (lane < ns) W->sjar[lane] = fr3_srow_dot(W, lane, qacc) - W->saref[lane];
+  for (int e = lane; e < 3 * ncon; e += 32) {
+    const int c = e / 3, a = e - 3 * c;
+    W->cjar[c][a] = fr3_cJ_dot(W->cJ[c][a], W->ccls[c], qacc) - W->caref[c][a];
+  }
+  __syncwarp();
+}
+
+// cost / forces / states at the current jar, gradient, Gauss term; optionally the contact Hessian weights
+__device__ __noinline__ void fr3_constraint_update(const Fr3Model* __restrict__ m, Fr3Work* W, const double* qacc, bool want_h, int lane) {
+  const int ns = W->ns, ncon = W->ncon;
+  double cost = 0;
+  if (lane < ns) cost += fr3_srow_eval(W, lane, W->sjar[lane], &W->sforce[lane], &W->sstate[lane]);
+  for (int c = lane; c < ncon; c += 32) cost += fr3_contact_eval(W->cD[c], W->cmu[c], W->cjar[c], W->cgeo[c] + 3, want_h ? W->cgeo[c] + 6 : nullptr);
+  cost = fwsum(cost);
+  __syncwarp();
+  double g = 0;
+  if (lane < FR_NV) {
+    const int i = lane;
+    double f = 0;
+    for (int r = 1; r < ns; r++) if (W->sdof[r] == i) f += W->ssign[r] * W->sforce[r];
+    if (i == 13) f += W->sforce[0]; else if (i == 14) f -= W->sforce[0];
+    for (int c = 0; c < ncon; c++) {
+      const int cls = W->ccls[c];
+      if ((i < 6 && cls == 1) || (i >= 6 && cls == 0)) continue;
+      f += W->cJ[c][0][i] * W->cgeo[c][3] + W->cJ[c][1][i] * W->cgeo[c][4] + W->cJ[c][2][i] * W->cgeo[c][5];
+    }
+    W->qfrc_constraint[i] = f;
+    W->grad[i] = W->Ma[i] - W->qfrc_smooth[i] - f;
+    g = (W->Ma[i] - W->qfrc_smooth[i]) * (qacc[i] - W->qacc_smooth[i]);
+  }
+  g = fwsum(g);
+  if (lane == 0) { W->gauss = 0.5 * g; W->cost = 0.5 * g + cost; }
+  __syncwarp();
+}
+
+// Newton direction: search = -H^-1 grad,  H = M + sum_rows D j j^T + sum_contacts Jc^T Wc Jc  (dense 15x15, lane per entry, warp Cholesky)
+__device__ inline void fr3_newton_direction(const Fr3Model* __restrict__ m, Fr3Work* W, int lane) {
+  const int ns = W->ns, ncon = W->ncon;
+  for (int e = lane; e < FR_NV * (FR_NV + 1) / 2; e += 32) {
+    // lower-triangle index -> (i, j), i >= j
+    int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= e) i++;
+    while (i * (i + 1) / 2 > e) i--;
+    const int j = e - i * (i + 1) / 2;
+    double h = 0;
+    if (i < 6) { if (i == j) h = i < 3 ? m->body_mass[0] : m->obj_inertia[i - 3]; }
+    else if (j >= 6) h = W->M[i - 6][j - 6];
+    if (i == j) {
+      for (int r = 1; r < ns; r++) if (W->sdof[r] == i && W->sstate[r] == FST_QUADRATIC) h += W->sD[r];
+      if (i == 13 || i == 14) h += W->sD[0];
+    } else if (i == 14 && j == 13) h -= W->sD[0];
+    for (int c = 0; c < ncon; c++) {
+      const int cls = W->ccls[c];
+      if ((j < 6 && cls == 1) || (i >= 6 && cls == 0)) continue;  // i >= j: both must be touched by the contact
+      const double* w = W->cgeo[c] + 6;
+      if (w[0] == 0) continue;  // no active edge
+      const double ni = W->cJ[c][0][i], nj = W->cJ[c][0][j], ai = W->cJ[c][1][i], aj = W->cJ[c][1][j], bi = W->cJ[c][2][i], bj = W->cJ[c][2][j];
+      h += w[0] * ni * nj + w[1] * (ni * aj + ai * nj) + w[2] * (ni * bj + bi * nj) + w[3] * ai * aj + w[5] * bi * bj;
+    }
+    W->H[i][j] = h;
+  }
+  __syncwarp();
+  warp_chol(W->H, W->Hd, FR_NV, lane);
+  const double x = warp_chol_solve(W->H, W->Hd, FR_NV, lane < FR_NV ? -W->grad[lane] : 0.0, lane);
+  if (lane < FR_NV) W->search[lane] = x;
+  __syncwarp();
+}
+
+// Line search state in REGISTERS: lane r owns scalar row r (<= 19) and lane c owns contacts c and c + 32 (ncon <= 48).
+struct Fr3LS {
+  double rjar, rjv, rD, rR, rfl;
+  double cjar[2][3], cjv[2][3], cD[2], cmu[2];
+  int kind;  // -1 none, 0 equality, 1 friction, 2 limit
+  int nc;
+};
+__device__ __forceinline__ void fr3_ls_eval(const Fr3LS& L, double alpha, double g1, double g2, double* d1, double* d2) {
+  double p1 = 0, p2 = 0;
+  if (L.kind >= 0) {
+    const double x = L.rjar + alpha * L.rjv;
+    bool quad = L.kind == 0;
+    if (L.kind == 1) {
+      const double lim = L.rR * L.rfl;
+      if (x <= -lim) p1 -= L.rfl * L.rjv;
+      else if (x >= lim) p1 += L.rfl * L.rjv;
+      else quad = true;
+    } else if (L.kind == 2) quad = x < 0;
+    if (quad) { p1 += L.rD * x * L.rjv; p2 += L.rD * L.rjv * L.rjv; }
+  }
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+    if (s < L.nc) {
+      const double mu = L.cmu[s], D = L.cD[s];
+      const double rn = L.cjar[s][0] + alpha * L.cjv[s][0], r1 = L.cjar[s][1] + alpha * L.cjv[s][1], r2 = L.cjar[s][2] + alpha * L.cjv[s][2];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int sg = 0; sg < 2; sg++) {
+          const double sgn = sg == 0 ? mu : -mu;
+          const double x = rn + sgn * (a == 0 ? r1 : r2), v = L.cjv[s][0] + sgn * L.cjv[s][1 + a];
+          if (x < 0) { p1 += D * x * v; p2 += D * v * v; }
+        }
+    }
+  *d1 = g1 + alpha * g2 + fwsum(p1);
+  *d2 = g2 + fwsum(p2);
+}
+
+// exact line search (safeguarded 1-D Newton on the convex piecewise-quadratic cost); leaves jv of the rows in W->sforce-independent
+// storage: scalar rows -> returned through L (registers), contacts -> W->cgeo[c][0..2].  Returns alpha.
+__device__ inline double fr3_line_search(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, Fr3LS& L) {
+  double g1 = 0, g2 = 0, sn = 0, gs = 0;
+  if (lane < FR_NV) {
+    g1 = W->search[lane] * (W->Ma[lane] - W->qfrc_smooth[lane]); g2 = W->search[lane] * W->Mv[lane];
+    sn = W->search[lane] * W->search[lane]; gs = W->grad[lane] * W->search[lane];
+  }
+  g1 = fwsum(g1); g2 = fwsum(g2);
+  const double snorm = sqrt(fwsum(sn));
+  // derivatives at alpha = 0 without touching the rows: d1(0) = grad . search and, for the Newton direction, d2(0) = -d1(0)
+  double d1 = fwsum(gs), d2 = -d1, lo = 0, hi = -1, alpha;
+  if (snorm < B2_MINVAL) return 0;
+  const double gtol = m->tolerance * m->ls_tolerance * snorm * m->meaninertia * FR_NV;
+  if (d1 >= 0 || d2 <= 0) return 0;
+  alpha = 1.0;
+  double prev_step = 1e300;
+  const int iters = (int)m->ls_iterations;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    fr3_ls_eval(L, alpha, g1, g2, &d1, &d2);
+    if (fabs(d1) < gtol) return alpha;
+    if (d1 < 0) lo = alpha; else hi = alpha;
+    double next = d2 > 0 ? alpha - d1 / d2 : -1;
+    if (hi < 0) { if (!(next > lo)) next = 2 * alpha + B2_MINVAL; }
+    else if (!(next > lo && next < hi && fabs(next - alpha) < 0.5 * prev_step)) next = 0.5 * (lo + hi);
+    if (next == alpha) return alpha;
+    prev_step = fabs(next - alpha);
+    alpha = next;
+  }
+  return lo > 0 ? lo : alpha;
+}
+
+// mj_fwdConstraint.  Called by ALL warps of the block; with sync_mode >= 3 the Newton iterations of the block's warps run in
+// lock-step (block barrier per iteration, finished warps idle) so the iteration body is fetched once for all of them.
+__device__ inline void fr3_fwd_constraint(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, bool active, int sync_mode) {
+  bool done = !active;
+  double scale = 0;
+  if (!done) {
+    // warm start: keep qacc_warmstart unless qacc_smooth has lower cost
+    fr3_set_point(m, W, W->warm, lane);
+    fr3_constraint_update(m, W, W->warm, false, lane);
+    const double cw = W->cost;
+    __syncwarp();
+    fr3_set_point(m, W, W->qacc_smooth, lane);
+    fr3_constraint_update(m, W, W->qacc_smooth, false, lane);
+    const double cs = W->cost;
+    __syncwarp();
+    if (lane < FR_NV) W->qacc[lane] = cw > cs ? W->qacc_smooth[lane] : W->warm[lane];
+    __syncwarp();
+    fr3_set_point(m, W, W->qacc, lane);
+    fr3_constraint_update(m, W, W->qacc, true, lane);
+    scale = 1.0 / (m->meaninertia * FR_NV);
+  }
+  const int iters = (int)m->iterations;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    if (sync_mode >= 3) { if (!__syncthreads_or(done ? 0 : 1)) break; }
+    else if (done) break;
+    if (done) continue;
+    double gn = lane < FR_NV ? W->grad[lane] * W->grad[lane] : 0.0;
+    gn = fwsum(gn);
+    if (scale * sqrt(gn) < m->tolerance) { done = true; continue; }
+    fr3_newton_direction(m, W, lane);
+    const int ns = W->ns, ncon = W->ncon;
+    if (lane < FR_NV) W->Mv[lane] = fr3_mulM_row(m, W, W->search, lane);
+    __syncwarp();
+    // row data of the line search, held in registers by the lane that owns the row / contact
+    Fr3LS L;
+    L.kind = lane >= ns ? -1 : lane == 0 ? 0 : lane < 10 ? 1 : 2;
+    L.rjar = L.rjv = L.rD = L.rR = L.rfl = 0;
+    if (lane < ns) { L.rjar = W->sjar[lane]; L.rjv = fr3_srow_dot(W, lane, W->search); L.rD = W->sD[lane]; L.rR = W->sR[lane]; L.rfl = W->sfl[lane]; }
+    L.nc = 0;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const int c = lane + 32 * s;
+#pragma unroll
+      for (int a = 0; a < 3; a++) { L.cjar[s][a] = 0; L.cjv[s][a] = 0; }
+      L.cD[s] = 0; L.cmu[s] = 0;
+      if (c < ncon) {
+        L.nc = s + 1;
+#pragma unroll
+        for (int a = 0; a < 3; a++) { L.cjar[s][a] = W->cjar[c][a]; L.cjv[s][a] = fr3_cJ_dot(W->cJ[c][a], W->ccls[c], W->search); }
+        L.cD[s] = W->cD[c]; L.cmu[s] = W->cmu[c];
+      }
+    }
+    const double alpha = fr3_line_search(m, W, lane, L);
+    if (alpha == 0) { done = true; continue; }
+    const double oldcost = W->cost;
+    __syncwarp();
+    if (lane < FR_NV) { W->qacc[lane] += alpha * W->search[lane]; W->Ma[lane] += alpha * W->Mv[lane]; }
+    if (lane < ns) W->sjar[lane] = L.rjar + alpha * L.rjv;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const int c = lane + 32 * s;
+      if (c < ncon) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) W->cjar[c][a] = L.cjar[s][a] + alpha * L.cjv[s][a];
+      }
+    }
+    __syncwarp();
+    fr3_constraint_update(m, W, W->qacc, true, lane);
+    const double newcost = W->cost;
+    __syncwarp();
+    if (scale * (oldcost - newcost) < m->tolerance) done = true;
+  }
+}
+
+// ------------------------------------------------------------------ one mj_step
+__device__ inline void fr3_step(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, int dist_mode, bool active, int sync_mode) {
+  if (active) {
+    fr3_kinematics(m, W, lane);
+    fr3_mass_and_bias(m, W, lane);
+  }
+  if (sync_mode >= 2) __syncthreads();
+  if (active) {
+    fr3_collision(m, W, lane, dist_mode);
+    fr3_make_constraint(m, W, lane);
+    // passive + actuation -> qfrc_smooth; qacc_smooth = M^-1 qfrc_smooth
+    if (lane < FR_NV) {
+      const int i = lane;
+      double f = -m->dof_damping[i] * W->qvel[i] - W->qfrc_bias[i];
+      if (i >= 6 && i <= 13) {
+        const int a = i - 6;
+        const double u = fmin(fmax(W->ctrl[a], m->ctrl_lo[a]), m->ctrl_hi[a]);
+        double fa = m->kp[a] * u - m->kp[a] * W->qpos[7 + a] - m->kv[a] * W->qvel[i];
+        if (m->frc_limited[a] != 0) fa = fmin(fmax(fa, m->frc_lo[a]), m->frc_hi[a]);
+        f += fa;
+      }
+      W->qfrc_smooth[i] = f;
+    }
+    fr3_factor_arm(W, nullptr, lane);
+    double x = 0;
+    if (lane < 3) x = W->qfrc_smooth[lane] / m->body_mass[0];
+    else if (lane < 6) x = W->qfrc_smooth[lane] / m->obj_inertia[lane - 3];
+    const double xa = warp_chol_solve(W->L, W->Ld, FNA, lane < FNA ? W->qfrc_smooth[6 + lane] : 0.0, lane);
+    if (lane < 6) W->qacc_smooth[lane] = x;
+    if (lane < FNA) W->qacc_smooth[6 + lane] = xa;
+    __syncwarp();
+  }
+  if (sync_mode >= 2) __syncthreads();
+  fr3_fwd_constraint(m, W, lane, active, sync_mode);
+  __syncwarp();
+  if (!active) return;
+  // implicitfast: (M + h (damping + kv)) qacc = qfrc_smooth + qfrc_constraint on the arm block; the object block has no
+  // velocity-dependent forces, so its qacc is the solver's; then the semi-implicit advance
+  const double h = m->dt;
+  if (lane < FNA) W->Mv[lane] = h * (m->dof_damping[6 + lane] + (lane < FR_NU ? m->kv[lane] : 0.0));
+  __syncwarp();
+  fr3_factor_arm(W, W->Mv, lane);
+  const double qa = warp_chol_solve(W->L, W->Ld, FNA, lane < FNA ? W->qfrc_smooth[6 + lane] + W->qfrc_constraint[6 + lane] : 0.0, lane);
+  double qo = 0;
+  if (lane < 3) qo = (W->qfrc_smooth[lane] + W->qfrc_constraint[lane]) / m->body_mass[0];
+  else if (lane < 6) qo = (W->qfrc_smooth[lane] + W->qfrc_constraint[lane]) / m->obj_inertia[lane - 3];
+  __syncwarp();
+  if (lane < FR_NV) W->warm[lane] = W->qacc[lane];
+  if (lane < 6) W->qvel[lane] += h * qo;
+  if (lane < FNA) W->qvel[6 + lane] += h * qa;
+  __syncwarp();
+  if (lane < 3) W->qpos[lane] += h * W->qvel[lane];
+  else if (lane == 3) {
+    double w[3] = {W->qvel[3], W->qvel[4], W->qvel[5]};
+    const double ang = h * lnormalize3(w);
+    double sn, cs, dq[4], nq[4];
+    sincos(0.5 * ang, &sn, &cs);
+    dq[0] = cs; dq[1] = sn * w[0]; dq[2] = sn * w[1]; dq[3] = sn * w[2];
+    lquat_mul(nq, W->qpos + 3, dq);
+    lquat_normalize(nq);
+    for (int k = 0; k < 4; k++) W->qpos[3 + k] = nq[k];
+  } else if (lane >= 6 && lane < FR_NV) W->qpos[lane + 1] += h * W->qvel[lane];
+  __syncwarp();
+}
+
+// per-step cost (fr3_pick.py:225-311): phase term + global terms, from the POST-step state and this step's sensordata.
+// params: [phase, w_lift_close, w_lift_height, w_move_goal, w_move_close, w_place_table, w_place_goal, w_upright, w_coll, w_qvel,
+//          w_open, goal_x, goal_y, pick_height, q_home(9)];  decay = linspace(1, 0, H)[t]
+__device__ inline double fr3_cost(const double* p, const double* qpos, const double* qvel, const double* sens, double decay) {
+  const int phase = (int)p[0];
+  const double gx = sens[11] - qpos[0], gy = sens[12] - qpos[1], gz = sens[13] - qpos[2];
+  const double grasp = gx * gx + gy * gy + gz * gz;
+  const double ex = qpos[0] - p[11], ey = qpos[1] - p[12];
+  const double goal = sqrt(ex * ex + ey * ey);
+  double c;
+  if (phase == 0) { const double e = qpos[2] - p[13]; c = p[1] * grasp + p[2] * e * e; }
+  else if (phase == 1) c = p[3] * goal + p[4] * grasp;
+  else if (phase == 2) c = p[5] * sens[4] + p[6] * goal;
+  else {
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { const double e = qpos[7 + k] - p[14 + k]; s += e * e; }
+    c = sqrt(s);
+  }
+  const double ux = sens[5], uy = sens[6], uz = sens[7] + 1.0;
+  const double touching = (sens[2] <= 0.0 || sens[3] <= 0.0) ? 1.0 : 0.0;
+  double v2 = 0;
+#pragma unroll
+  for (int k = 0; k < FR_NV; k++) v2 += qvel[k] * qvel[k];
+  const double go = qpos[15] - 0.04;
+  c += p[7] * sqrt(ux * ux + uy * uy + uz * uz) - p[8] * (1.0 - touching) + p[9] * decay * sqrt(v2) + p[10] * go * go;
+  return c;
+}
+
+// ------------------------------------------------------------------ kernels
+// COST: in = knots (N,K,8), basis (H,K) -> reward (N) [+ cost (N,H) f32];  !COST: in = controls (N,H,8) -> states, sensors
+template <bool COST>
+__global__ void __launch_bounds__(256) fr3_rollout_kernel(const Fr3Model* __restrict__ m, const double* __restrict__ x0, int x0_batched,
+                                                          const double* __restrict__ in, int N, int H, int K, const double* __restrict__ basis,
+                                                          const double* __restrict__ cost_params, double* __restrict__ states,
+                                                          double* __restrict__ sensors, float* __restrict__ cost_NH, double* __restrict__ reward_N,
+                                                          int wstride, int sync_mode, const SampleSpec smp, int index_offset) {
+  B2_DYNAMIC_SMEM(unsigned char, fsm_all);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int n = blockIdx.x * wpb + wib;
+  const bool active = n < N;
+  unsigned char* fsm = fsm_all + (size_t)wib * wstride;
+  Fr3Work* W = reinterpret_cast<Fr3Work*>(fsm);
+  if (active) {
+    const double* xs = x0 + (x0_batched ? (size_t)n * FR_NX : 0);
+    if (lane < FR_NQ) W->qpos[lane] = xs[lane];
+    if (lane < FR_NV) { W->qvel[lane] = xs[FR_NQ + lane]; W->warm[lane] = 0; }
+  }
+  __syncwarp();
+  if constexpr (COST) {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + ((sizeof(Fr3Work) + 15) & ~(size_t)15));
+    double* sK = reinterpret_cast<double*>(bar + 2);
+    double* sB = sK + K * FR_NU;
+    if (active) {
+      const unsigned bytesK = (unsigned)(K * FR_NU * sizeof(double)), bytesB = (unsigned)(H * K * sizeof(double));
+      const double* gK = in + (size_t)n * K * FR_NU;
+      const bool want_knots = !smp.enabled;
+      const bool tma_ok = (bytesB % 16 == 0) && ((reinterpret_cast<uintptr_t>(basis) & 15) == 0) && (!want_knots || (reinterpret_cast<uintptr_t>(gK) & 15) == 0);
+      if (tma_ok) {
+        if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_expect_tx(bar, (want_knots ? bytesK : 0u) + bytesB);
+          if (want_knots) tma_bulk_g2s(sK, gK, bytesK, bar);
+          tma_bulk_g2s(sB, basis, bytesB, bar);
+        }
+        mbar_wait(bar, 0);
+      } else {
+        if (want_knots) for (int i = lane; i < K * FR_NU; i += 32) sK[i] = gK[i];
+        for (int i = lane; i < H * K; i += 32) sB[i] = basis[i];
+        __syncwarp();
+      }
+      if (smp.enabled) {
+        const long long gn = (long long)n + index_offset;
+        const int KNU = K * FR_NU;
+        for (int p2 = lane; 2 * p2 < KNU; p2 += 32) {
+          double z0, z1;
+          normal_pair(smp, gn, p2, &z0, &z1);
+          const double a = sample_element(smp, gn, 2 * p2, FR_NU, z0);
+          sK[2 * p2] = a; smp.knots_out[(size_t)n * KNU + 2 * p2] = a;
+          if (2 * p2 + 1 < KNU) { const double b = sample_element(smp, gn, 2 * p2 + 1, FR_NU, z1); sK[2 * p2 + 1] = b; smp.knots_out[(size_t)n * KNU + 2 * p2 + 1] = b; }
+        }
+        __syncwarp();
+      }
+    }
+    double total = 0;
+#pragma unroll 1
+    for (int t = 0; t < H; t++) {
+      if (sync_mode >= 1) __syncthreads();
+      if (active && lane < FR_NU) {
+        double u = 0;
+        for (int k = 0; k < K; k++) u += sB[t * K + k] * sK[k * FR_NU + lane];
+        W->ctrl[lane] = u;
+      }
+      __syncwarp();
+      fr3_step(m, W, lane, 1, active, sync_mode);
+      if (active && lane == 0) {
+        double cp[FR_NCOST];
+#pragma unroll
+        for (int i = 0; i < FR_NCOST; i++) cp[i] = cost_params[i];
+        const double decay = H > 1 ? 1.0 - (double)t / (double)(H - 1) : 1.0;
+        const double ct = fr3_cost(cp, W->qpos, W->qvel, W->sens, decay);
+        total += ct;
+        if (cost_NH) cost_NH[(size_t)n * H + t] = (float)ct;
+      }
+    }
+    if (active && lane == 0) reward_N[n] = -total;
+  } else {
+#pragma unroll 1
+    for (int t = 0; t < H; t++) {
+      if (sync_mode >= 1) __syncthreads();
+      if (active && lane < FR_NU) W->ctrl[lane] = in[((size_t)n * H + t) * FR_NU + lane];
+      __syncwarp();
+      fr3_step(m, W, lane, 0, active, sync_mode);
+      if (!active) continue;
+      double* so = states + ((size_t)n * H + t) * FR_NX;
+      if (lane < FR_NQ) so[lane] = W->qpos[lane];
+      if (lane < FR_NV) so[FR_NQ + lane] = W->qvel[lane];
+      if (sensors && lane < FR_NS) sensors[((size_t)n * H + t) * FR_NS + lane] = W->sens[lane];
+    }
+  }
+}
+
+// Task.reward from given trajectories (contract A callers): one thread per rollout
+__global__ void fr3_reward_kernel(const double* __restrict__ states, const double* __restrict__ sensors, int N, int H,
+                                  const double* __restrict__ cost_params, double* __restrict__ reward_N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double cp[FR_NCOST];
+#pragma unroll
+  for (int i = 0; i < FR_NCOST; i++) cp[i] = cost_params[i];
+  double total = 0;
+  for (int t = 0; t < H; t++) {
+    const double* s = states + ((size_t)n * H + t) * FR_NX;
+    const double decay = H > 1 ? 1.0 - (double)t / (double)(H - 1) : 1.0;
+    total += fr3_cost(cp, s, s + FR_NQ, sensors + ((size_t)n * H + t) * FR_NS, decay);
+  }
+  reward_N[n] = -total;
+}
+
+inline size_t fr3_wstride(int cost_mode, int K, int H) {
+  size_t w = ((sizeof(Fr3Work) + 15) & ~(size_t)15) + 16 + (cost_mode ? ((size_t)K * FR_NU + (size_t)H * K) * sizeof(double) : 0);
+  return (w + 15) & ~(size_t)15;
+}
+
+// ------------------------------------------------------------------ host side
+#ifndef B2_HOST_SIM
+inline int fr3_create(Fr3Model** out, const double* consts, size_t n, std::string* err) {
+  if (n != sizeof(Fr3Model) / sizeof(double)) { *err = "wrong number of task constants"; return 1; }
+  Fr3Model* d = nullptr;
+  if (cudaMalloc(&d, sizeof(Fr3Model)) != cudaSuccess) { *err = "cudaMalloc failed"; return 1; }
+  if (cudaMemcpy(d, consts, sizeof(Fr3Model), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); *err = "cudaMemcpy failed"; return 1; }
+  *out = d;
+  return 0;
+}
+inline void fr3_destroy(Fr3Model* m) { cudaFree(m); }
+
+inline int fr3_launch(const Fr3Model* m, int cost_mode, const double* d_x0, int batched, const double* d_in, int N, int H, int K,
+                      const double* d_basis, const double* d_params, double* d_states, double* d_sensors, float* d_cost, double* d_reward,
+                      const PlanEpilogue& ep, const SampleSpec& smp, cudaStream_t st, std::string* err) {
+  const char* sm_env = getenv("B200MPC_FR3_SYNC");
+  const int sync_mode = sm_env ? atoi(sm_env) : 3;
+  const size_t wstride = fr3_wstride(cost_mode, K, H);
+  int wpb = (N + 147) / 148;  // spread the rollouts over the 148 SMs first, then stack warps per SM
+  if (wpb < 1) wpb = 1;
+  if (wpb > 8) wpb = 8;
+  while (wpb > 1 && wpb * wstride > 226 * 1024) wpb--;
+  const size_t smem = wpb * wstride;
+  if (smem > 227 * 1024) { *err = "horizon/knots too large for the shared-memory tile"; return 1; }
+  const int grid = (N + wpb - 1) / wpb;
+  cudaError_t e;
+  if (cost_mode) {
+    e = cudaFuncSetAttribute(fr3_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      fr3_rollout_kernel<true><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, (int)wstride, sync_mode, smp, ep.index_offset);
+  } else {
+    e = cudaFuncSetAttribute(fr3_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      fr3_rollout_kernel<false><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, (int)wstride, sync_mode, smp, 0);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("fr3 launch: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+inline int fr3_reward_launch(const double* d_states, const double* d_sensors, int N, int H, const double* d_params, double* d_reward,
+                             cudaStream_t st, std::string* err) {
+  fr3_reward_kernel<<<(N + 127) / 128, 128, 0, st>>>(d_states, d_sensors, N, H, d_params, d_reward);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("fr3 reward launch: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+#endif  // !B2_HOST_SIM
+
+}  // namespace b2

@@ -9,6 +9,7 @@
 // The collision GEOMETRY is reduced; the constraint/solver pipeline is the full one.
 #pragma once
 #include "epilogue.cuh"
+#include "geom.cuh"
 #include "sampling.cuh"
 
 #include <stdio.h>
@@ -69,55 +70,6 @@ __device__ unsigned long long g_leap_prof[16];
 #define LPROF_ADD(slot, t0) do { if (prof && lane == 0) atomicAdd(&g_leap_prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
 
 enum { LST_SATISFIED = 0, LST_QUADRATIC = 1, LST_LINEARNEG = 2, LST_LINEARPOS = 3, LST_CONE = 4 };
-
-// ------------------------------------------------------------------ small vector helpers (same op order as the oracle)
-__device__ __forceinline__ double ldot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-__device__ __forceinline__ void lcross3(double* r, const double* a, const double* b) {
-  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
-  r[0] = x; r[1] = y; r[2] = z;
-}
-__device__ __forceinline__ double lnorm3(const double* a) { return sqrt(ldot3(a, a)); }
-__device__ __forceinline__ double lnormalize3(double* a) {
-  double n = lnorm3(a);
-  if (n < B2_MINVAL) { a[0] = 1; a[1] = 0; a[2] = 0; return 0; }
-  a[0] /= n; a[1] /= n; a[2] /= n;
-  return n;
-}
-__device__ __forceinline__ void lquat_mul(double* r, const double* a, const double* b) {
-  double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
-  double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
-  double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
-  double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
-  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
-}
-__device__ __forceinline__ void lquat_normalize(double* q) {
-  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  if (n < B2_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
-  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
-}
-__device__ __forceinline__ void lquat2mat(double* m, const double* q) {
-  double w = q[0], x = q[1], y = q[2], z = q[3];
-  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
-  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
-  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
-}
-__device__ __forceinline__ void lmat_vec(double* r, const double* m, const double* v) {
-  double x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2], z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
-  r[0] = x; r[1] = y; r[2] = z;
-}
-__device__ __forceinline__ void lmatT_vec(double* r, const double* m, const double* v) {
-  double x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2], z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
-  r[0] = x; r[1] = y; r[2] = z;
-}
-__device__ __forceinline__ void lmat_mul(double* r, const double* a, const double* b) {
-  double t[9];
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int j = 0; j < 3; j++) t[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
-#pragma unroll
-  for (int i = 0; i < 9; i++) r[i] = t[i];
-}
 
 // ------------------------------------------------------------------ kinematics (mj_kinematics + mj_comPos)
 __device__ inline void leap_kinematics(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
@@ -350,176 +302,7 @@ __device__ inline void leap_block_solve(const LeapModel* __restrict__ m, LeapWor
   __syncwarp();
 }
 
-// ------------------------------------------------------------------ collision (reduced geometry; same routines as the oracle)
-struct LRaw { double dist, pos[3], normal[3]; };
-
-__device__ __noinline__ int l_clip_poly(double (*poly)[2], int n, int axis, double sign, double lim) {
-  double out[16][2];
-  int no = 0;
-  for (int i = 0; i < n; i++) {
-    const double* a = poly[i];
-    const double* b = poly[(i + 1) % n];
-    double da = sign * a[axis] - lim, db = sign * b[axis] - lim;
-    if (da <= 0) { out[no][0] = a[0]; out[no][1] = a[1]; no++; }
-    if ((da < 0 && db > 0) || (da > 0 && db < 0)) {
-      double t = da / (da - db);
-      out[no][0] = a[0] + t * (b[0] - a[0]); out[no][1] = a[1] + t * (b[1] - a[1]); no++;
-    }
-    if (no >= 15) break;
-  }
-  for (int i = 0; i < no; i++) { poly[i][0] = out[i][0]; poly[i][1] = out[i][1]; }
-  return no;
-}
-
-__device__ __noinline__ int l_sphere_box(const double* ps, double rs, const double* pb, const double* mb, const double* sb, double margin, LRaw* out) {
-  double rel[3], loc[3], cl[3];
-  for (int k = 0; k < 3; k++) rel[k] = ps[k] - pb[k];
-  lmatT_vec(loc, mb, rel);
-  int inside = 1;
-  for (int k = 0; k < 3; k++) {
-    cl[k] = fmin(fmax(loc[k], -sb[k]), sb[k]);
-    if (cl[k] != loc[k]) inside = 0;
-  }
-  double nl[3], dist;
-  if (!inside) {
-    double dv[3] = {loc[0] - cl[0], loc[1] - cl[1], loc[2] - cl[2]};
-    double dn = lnorm3(dv);
-    if (dn - rs >= margin) return 0;
-    for (int k = 0; k < 3; k++) nl[k] = -dv[k] / dn;
-    dist = dn - rs;
-  } else {
-    int ax = 0; double best = 1e300;
-    for (int k = 0; k < 3; k++) { double g = sb[k] - fabs(loc[k]); if (g < best) { best = g; ax = k; } }
-    nl[0] = nl[1] = nl[2] = 0; nl[ax] = loc[ax] >= 0 ? -1 : 1;
-    cl[ax] = loc[ax] >= 0 ? sb[ax] : -sb[ax];
-    dist = -best - rs;
-  }
-  lmat_vec(out->normal, mb, nl);
-  double clw[3];
-  lmat_vec(clw, mb, cl);
-  for (int k = 0; k < 3; k++) out->pos[k] = pb[k] + clw[k] - out->normal[k] * (-0.5 * dist);
-  out->dist = dist;
-  return 1;
-}
-
-__device__ __noinline__ int l_box_box(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2, const double* s2,
-                                double margin, LRaw* out, int maxout) {
-  double R[3][3], AR[3][3], t[3], d12[3];
-  for (int k = 0; k < 3; k++) d12[k] = p2[k] - p1[k];
-  lmatT_vec(t, m1, d12);
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) {
-      R[i][j] = m1[i] * m2[j] + m1[3 + i] * m2[3 + j] + m1[6 + i] * m2[6 + j];
-      AR[i][j] = fabs(R[i][j]) + 1e-12;
-    }
-  double best = -1e300; int code = -1; double bsign = 1;
-  for (int i = 0; i < 3; i++) {
-    double sep = fabs(t[i]) - (s1[i] + s2[0] * AR[i][0] + s2[1] * AR[i][1] + s2[2] * AR[i][2]);
-    if (sep >= margin) return 0;
-    if (sep > best) { best = sep; code = i; bsign = t[i] >= 0 ? 1 : -1; }
-  }
-  for (int j = 0; j < 3; j++) {
-    double tj = t[0] * R[0][j] + t[1] * R[1][j] + t[2] * R[2][j];
-    double sep = fabs(tj) - (s2[j] + s1[0] * AR[0][j] + s1[1] * AR[1][j] + s1[2] * AR[2][j]);
-    if (sep >= margin) return 0;
-    if (sep > best) { best = sep; code = 3 + j; bsign = tj >= 0 ? 1 : -1; }
-  }
-  double ebest = -1e300; int ecode = -1; double esign = 1, eaxis[3] = {0, 0, 0};
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) {
-      double a1[3] = {m1[i], m1[3 + i], m1[6 + i]}, a2[3] = {m2[j], m2[3 + j], m2[6 + j]}, ax[3];
-      lcross3(ax, a1, a2);
-      double len = lnorm3(ax);
-      if (len < 1e-8) continue;
-      for (int k = 0; k < 3; k++) ax[k] /= len;
-      double td = ldot3(ax, d12), ra = 0, rb = 0;
-      for (int k = 0; k < 3; k++) {
-        double c1[3] = {m1[k], m1[3 + k], m1[6 + k]}, c2[3] = {m2[k], m2[3 + k], m2[6 + k]};
-        ra += s1[k] * fabs(ldot3(ax, c1)); rb += s2[k] * fabs(ldot3(ax, c2));
-      }
-      double sep = fabs(td) - (ra + rb);
-      if (sep >= margin) return 0;
-      if (sep > ebest) { ebest = sep; ecode = 6 + 3 * i + j; esign = td >= 0 ? 1 : -1; eaxis[0] = ax[0]; eaxis[1] = ax[1]; eaxis[2] = ax[2]; }
-    }
-  if (ecode >= 0 && ebest > best + 1e-6 + 0.05 * fabs(best)) {
-    int i = (ecode - 6) / 3, j = (ecode - 6) % 3;
-    double n[3] = {eaxis[0] * esign, eaxis[1] * esign, eaxis[2] * esign};
-    double c1[3] = {p1[0], p1[1], p1[2]}, c2[3] = {p2[0], p2[1], p2[2]};
-    for (int k = 0; k < 3; k++) {
-      if (k != i) { double a[3] = {m1[k], m1[3 + k], m1[6 + k]}; double sg = ldot3(a, n) > 0 ? 1 : -1; for (int q = 0; q < 3; q++) c1[q] += sg * s1[k] * a[q]; }
-      if (k != j) { double a[3] = {m2[k], m2[3 + k], m2[6 + k]}; double sg = ldot3(a, n) > 0 ? -1 : 1; for (int q = 0; q < 3; q++) c2[q] += sg * s2[k] * a[q]; }
-    }
-    double u1[3] = {m1[i], m1[3 + i], m1[6 + i]}, u2[3] = {m2[j], m2[3 + j], m2[6 + j]}, w0[3];
-    for (int k = 0; k < 3; k++) w0[k] = c1[k] - c2[k];
-    double b = ldot3(u1, u2), dd = ldot3(u1, w0), e = ldot3(u2, w0), den = 1 - b * b;
-    double sc = den > 1e-12 ? (b * e - dd) / den : 0, tc = den > 1e-12 ? (e - b * dd) / den : 0;
-    sc = fmin(fmax(sc, -s1[i]), s1[i]); tc = fmin(fmax(tc, -s2[j]), s2[j]);
-    out[0].dist = ebest;
-    for (int k = 0; k < 3; k++) { out[0].normal[k] = n[k]; out[0].pos[k] = 0.5 * ((c1[k] + sc * u1[k]) + (c2[k] + tc * u2[k])); }
-    return 1;
-  }
-  const double *pr, *mr, *sr, *pi, *mi, *si;
-  int raxis; double nsign;
-  const int ref_is_1 = code < 3;
-  if (ref_is_1) { pr = p1; mr = m1; sr = s1; pi = p2; mi = m2; si = s2; raxis = code; nsign = bsign; }
-  else { pr = p2; mr = m2; sr = s2; pi = p1; mi = m1; si = s1; raxis = code - 3; nsign = -bsign; }
-  double nref[3] = {mr[raxis] * nsign, mr[3 + raxis] * nsign, mr[6 + raxis] * nsign};
-  int iaxis = 0; double imin = 1e300, isign = 1;
-  for (int k = 0; k < 3; k++) {
-    double a[3] = {mi[k], mi[3 + k], mi[6 + k]}, dd = ldot3(a, nref);
-    if (-fabs(dd) < imin) { imin = -fabs(dd); iaxis = k; isign = dd > 0 ? -1 : 1; }
-  }
-  const int iu = (iaxis + 1) % 3, iv = (iaxis + 2) % 3, ru = (raxis + 1) % 3, rv = (raxis + 2) % 3;
-  double fc[3];
-  for (int k = 0; k < 3; k++) fc[k] = pi[k] + isign * si[iaxis] * mi[3 * k + iaxis];
-  double poly[16][2];
-  int n = 4;
-  const double sg[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
-  double verts[4][3];
-  for (int c = 0; c < 4; c++) {
-    for (int k = 0; k < 3; k++) verts[c][k] = fc[k] + sg[c][0] * si[iu] * mi[3 * k + iu] + sg[c][1] * si[iv] * mi[3 * k + iv] - pr[k];
-    double loc[3];
-    lmatT_vec(loc, mr, verts[c]);
-    poly[c][0] = loc[ru]; poly[c][1] = loc[rv];
-  }
-  double l0[3], l1[3], l2[3];
-  lmatT_vec(l0, mr, verts[0]); lmatT_vec(l1, mr, verts[1]); lmatT_vec(l2, mr, verts[3]);
-  const double e1u = l1[ru] - l0[ru], e1v = l1[rv] - l0[rv], e1h = l1[raxis] - l0[raxis];
-  const double e2u = l2[ru] - l0[ru], e2v = l2[rv] - l0[rv], e2h = l2[raxis] - l0[raxis];
-  const double det = e1u * e2v - e1v * e2u;
-  n = l_clip_poly(poly, n, 0, 1, sr[ru]);
-  if (n) n = l_clip_poly(poly, n, 0, -1, sr[ru]);
-  if (n) n = l_clip_poly(poly, n, 1, 1, sr[rv]);
-  if (n) n = l_clip_poly(poly, n, 1, -1, sr[rv]);
-  int nc = 0;
-  for (int c = 0; c < n && nc < maxout; c++) {
-    double du = poly[c][0] - l0[ru], dv = poly[c][1] - l0[rv], h;
-    if (fabs(det) > 1e-14) {
-      double a = (du * e2v - dv * e2u) / det, b = (e1u * dv - e1v * du) / det;
-      h = l0[raxis] + a * e1h + b * e2h;
-    } else h = l0[raxis];
-    double dist = nsign * h - sr[raxis];
-    if (dist >= margin) continue;
-    double loc[3], wpt[3];
-    loc[ru] = poly[c][0]; loc[rv] = poly[c][1]; loc[raxis] = h - 0.5 * dist * nsign;
-    lmat_vec(wpt, mr, loc);
-    out[nc].dist = dist;
-    for (int k = 0; k < 3; k++) { out[nc].pos[k] = pr[k] + wpt[k]; out[nc].normal[k] = ref_is_1 ? nref[k] : -nref[k]; }
-    nc++;
-  }
-  return nc;
-}
-
-__device__ inline void l_make_frame(double* frame) {
-  double* x = frame; double* y = frame + 3; double* z = frame + 6;
-  lnormalize3(x);
-  if (fabs(x[1]) < 0.5) { y[0] = 0; y[1] = 1; y[2] = 0; } else { y[0] = 0; y[1] = 0; y[2] = 1; }
-  double dd = ldot3(x, y);
-  for (int k = 0; k < 3; k++) y[k] -= dd * x[k];
-  lnormalize3(y);
-  lcross3(z, x, y);
-}
-
+// ------------------------------------------------------------------ collision (reduced geometry; routines in geom.cuh)
 __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork* W, int lane, int prof = 0) {
   const int ng = (int)m->ngeom;
   long long tc0 = LPROF_T();

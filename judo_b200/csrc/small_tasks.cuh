@@ -210,7 +210,7 @@ struct CylinderPushTask {
         const double R0 = D[0];
         const double R1 = R0 / fmax(B2_MINVAL, c.impratio);
         const double mureg = mu * sqrt(R1 / R0);
-        const double Rpy = 2 * mureg * mureg * R1;
+        const double Rpy = 2 * mureg * mureg * R0;  // = 2 mu^2 R0 / impratio
 #pragma unroll
         for (int r = 0; r < 4; r++) D[r] = 1 / Rpy;
         double qacc[4];

@@ -229,8 +229,9 @@ def compile_mjcf(path: str) -> dict[str, Any]:
     nq = nv = 0
     qpos0: list[float] = []
 
-    def add_body(elem: ET.Element, parent: int, childclass: str | None) -> None:
+    def add_body(elem: ET.Element, parent: int, childclass: str | None, moving: bool = False) -> None:
         nonlocal nq, nv
+        moving = moving or any(j.tag in ("joint", "freejoint") for j in elem)
         childclass = elem.attrib.get("childclass", childclass)
         bid = len(bodies)
         pos = _vec(elem.attrib.get("pos", "0 0 0"))
@@ -270,6 +271,9 @@ def compile_mjcf(path: str) -> dict[str, Any]:
                 damping=float(a.get("damping", 0)), frictionloss=float(a.get("frictionloss", 0)),
                 armature=float(a.get("armature", 0)), limited=bool(limited), range=rng.tolist(),
                 margin=float(a.get("margin", 0)),
+                actfrclimited=bool(a.get("actuatorfrclimited", "auto") == "true" or
+                                   (a.get("actuatorfrclimited", "auto") == "auto" and autolimits and "actuatorfrcrange" in a)),
+                actfrcrange=_vec(a.get("actuatorfrcrange", "0 0")).tolist(),
                 solref_limit=_vec(a.get("solreflimit", "0.02 1")).tolist(),
                 solimp_limit=_vec(a.get("solimplimit"), 5, [0.9, 0.95, 0.001, 0.5, 2]).tolist(),
                 solref_friction=_vec(a.get("solreffriction", "0.02 1")).tolist(),
@@ -342,6 +346,8 @@ def compile_mjcf(path: str) -> dict[str, Any]:
                 if rec["type"] == "mesh":
                     if rec["density"] == 0 or rec["mass"] == 0:
                         continue
+                    if not moving:
+                        continue  # static body (welded to the world): its inertia never enters the dynamics
                     raise ValueError("mesh inertia requires the mesh asset (unavailable)")
                 if rec["mass"] is not None and rec["mass"] == 0:
                     continue
@@ -367,7 +373,7 @@ def compile_mjcf(path: str) -> dict[str, Any]:
                 body.update(ipos=[0, 0, 0], iquat=[1, 0, 0, 0], mass=0.0, inertia=[0, 0, 0])
 
         for child in elem.findall("body"):
-            add_body(child, bid, childclass)
+            add_body(child, bid, childclass, moving)
 
     wb = root.find("worldbody")
     assert wb is not None
@@ -419,6 +425,13 @@ def compile_mjcf(path: str) -> dict[str, Any]:
             fr = _vec(a.get("forcerange", "0 0"))
             if joints[jid]["type"] == "hinge":
                 cr = cr * 1.0  # ctrlrange of a position servo on a hinge is an angle; leap uses radian
+            inherit = float(a.get("inheritrange", 0))
+            if inherit > 0:  # position servo: ctrlrange = joint range scaled about its midpoint (MuJoCo user_model: inheritrange)
+                assert "ctrlrange" not in a, "inheritrange and ctrlrange are mutually exclusive"
+                lo, hi = joints[jid]["range"]
+                mid, rad = 0.5 * (lo + hi), 0.5 * (hi - lo) * inherit
+                cr = np.array([mid - rad, mid + rad])
+                a["ctrlrange"] = "inherited"
             cl = a.get("ctrllimited", "auto")
             fl = a.get("forcelimited", "auto")
             acts.append(dict(
@@ -435,17 +448,39 @@ def compile_mjcf(path: str) -> dict[str, Any]:
     adr = 0
     for sblock in root.findall("sensor"):
         for s in sblock:
-            if s.tag == "framepos":
-                assert s.attrib.get("objtype") == "site"
+            if s.tag == "framepos" and s.attrib.get("objtype") == "site":
                 sid = next(i for i, x in enumerate(sites) if x["name"] == s.attrib["objname"])
                 sensors.append(dict(name=s.attrib.get("name", ""), type="framepos", obj=sid, adr=adr, dim=3))
                 adr += 3
+            elif s.tag in ("framepos", "framezaxis"):
+                assert s.attrib.get("objtype") == "body"
+                bid = next(i for i, x in enumerate(bodies) if x["name"] == s.attrib["objname"])
+                sensors.append(dict(name=s.attrib.get("name", ""), type=s.tag + "_body", obj=bid, adr=adr, dim=3))
+                adr += 3
+            elif s.tag == "distance":
+                b1 = next(i for i, x in enumerate(bodies) if x["name"] == s.attrib["body1"])
+                b2 = next(i for i, x in enumerate(bodies) if x["name"] == s.attrib["body2"])
+                sensors.append(dict(name=s.attrib.get("name", ""), type="distance", obj=b1, obj2=b2,
+                                    cutoff=float(s.attrib.get("cutoff", 0)), adr=adr, dim=1))
+                adr += 1
             elif s.tag == "jointpos":
                 jid = next(i for i, j in enumerate(joints) if j["name"] == s.attrib["joint"])
                 sensors.append(dict(name=s.attrib.get("name", ""), type="jointpos", obj=jid, adr=adr, dim=1))
                 adr += 1
             else:
                 raise NotImplementedError(f"sensor {s.tag}")
+
+    equalities = []
+    for eblock in root.findall("equality"):
+        for e in eblock:
+            if e.tag != "joint":
+                raise NotImplementedError(f"equality {e.tag}")
+            a = dict(solref="0.02 1", solimp="0.9 0.95 0.001 0.5 2", polycoef="0 1 0 0 0")
+            a.update(defaults.resolve("equality", e, None))
+            j1 = next(i for i, j in enumerate(joints) if j["name"] == a["joint1"])
+            j2 = next(i for i, j in enumerate(joints) if j["name"] == a["joint2"])
+            equalities.append(dict(type="joint", joint1=j1, joint2=j2, polycoef=_vec(a["polycoef"], 5, [0, 1, 0, 0, 0]).tolist(),
+                                   solref=_vec(a["solref"]).tolist(), solimp=_vec(a["solimp"], 5, [0.9, 0.95, 0.001, 0.5, 2]).tolist()))
 
     excludes = []
     for cblock in root.findall("contact"):
@@ -458,7 +493,7 @@ def compile_mjcf(path: str) -> dict[str, Any]:
         name=root.attrib.get("model", os.path.basename(path)), source=os.path.basename(path), opt=opt,
         nq=nq, nv=nv, nu=len(acts), nbody=len(bodies), njnt=len(joints), ngeom=len(geoms), nsite=len(sites),
         nsensordata=adr, qpos0=[float(x) for x in qpos0], bodies=bodies, joints=joints, dofs=dofs, geoms=geoms,
-        sites=sites, actuators=acts, sensors=sensors, excludes=excludes,
+        sites=sites, actuators=acts, sensors=sensors, excludes=excludes, equalities=equalities,
     )
     model["pairs"] = candidate_pairs(model)
     _set_const(model)

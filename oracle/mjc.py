@@ -15,6 +15,7 @@ _MODELS = os.path.join(_HERE, "..", "judo_b200", "models")
 
 _JNT = {"free": 0, "ball": 1, "slide": 2, "hinge": 3}
 _GEOM = {"sphere": 2, "capsule": 3, "cylinder": 5, "box": 6}
+_SENS = {"framepos": 0, "jointpos": 1, "framepos_body": 2, "framezaxis_body": 3, "distance": 4}
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
 
@@ -61,7 +62,7 @@ def serialize_model(model: dict, pairs: list | None = None, geoms: list | None =
     pairs = [[remap[a], remap[b]] for a, b in pairs if a in remap and b in remap]
     opt = model["opt"]
     ib += [model["nq"], model["nv"], model["nu"], model["nbody"], model["njnt"], len(usable), model["nsite"],
-           len(model["sensors"]), model["nsensordata"], len(pairs),
+           len(model["sensors"]), model["nsensordata"], len(pairs), len(model.get("equalities", [])),
            {"Euler": 0, "implicitfast": 1}[opt["integrator"]], {"pyramidal": 0, "elliptic": 1}[opt["cone"]],
            int(opt["contact_disabled"]), opt["iterations"], opt["ls_iterations"]]
     db += [opt["timestep"], *opt["gravity"], opt["impratio"], opt["tolerance"], opt["ls_tolerance"], model["meaninertia"]]
@@ -70,9 +71,9 @@ def serialize_model(model: dict, pairs: list | None = None, geoms: list | None =
         ib += [b["parent"], b["jntadr"], b["jntnum"]]
         db += [*b["pos"], *b["quat"], *b["ipos"], *b["iquat"], b["mass"], *b["inertia"], *b["invweight0"]]
     for j in model["joints"]:
-        ib += [_JNT[j["type"]], j["body"], j["qposadr"], j["dofadr"], int(j.get("limited", False))]
+        ib += [_JNT[j["type"]], j["body"], j["qposadr"], j["dofadr"], int(j.get("limited", False)), int(j.get("actfrclimited", False))]
         db += [*j.get("pos", [0, 0, 0]), *j.get("axis", [0, 0, 1]), *j.get("range", [0, 0]), j.get("margin", 0.0),
-               *j.get("solref_limit", [0.02, 1]), *j.get("solimp_limit", [0.9, 0.95, 0.001, 0.5, 2])]
+               *j.get("solref_limit", [0.02, 1]), *j.get("solimp_limit", [0.9, 0.95, 0.001, 0.5, 2]), *j.get("actfrcrange", [0, 0])]
     for d in model["dofs"]:
         j = model["joints"][d["jnt"]]
         ib += [d["jnt"]]
@@ -91,7 +92,11 @@ def serialize_model(model: dict, pairs: list | None = None, geoms: list | None =
         ib += [a["dof"], int(a["ctrllimited"]), int(a["forcelimited"])]
         db += [a["gear"], a["kp"], a["kv"], *a["ctrlrange"], *a["forcerange"]]
     for s in model["sensors"]:
-        ib += [{"framepos": 0, "jointpos": 1}[s["type"]], s["obj"], s["adr"]]
+        ib += [_SENS[s["type"]], s["obj"], s.get("obj2", -1), s["adr"]]
+        db += [s.get("cutoff", 0.0)]
+    for e in model.get("equalities", []):
+        ib += [e["joint1"], e["joint2"]]
+        db += [*e["polycoef"], *e["solref"], *e["solimp"]]
     return np.array(ib, dtype=np.int32), np.array(db, dtype=np.float64)
 
 

@@ -25,12 +25,12 @@ void mjc_get_counters(long* out) { out[0] = g_ls_evals; out[1] = g_newton_iters;
 void mjc_set_debug(int v) { g_debug = v; }
 
 /* constraint row types, in MuJoCo's row order */
-enum { CT_FRICTION_DOF = 1, CT_LIMIT_JOINT = 3, CT_CONTACT_PYRAMIDAL = 6, CT_CONTACT_ELLIPTIC = 7 };
+enum { CT_EQUALITY = 0, CT_FRICTION_DOF = 1, CT_LIMIT_JOINT = 3, CT_CONTACT_PYRAMIDAL = 6, CT_CONTACT_ELLIPTIC = 7 };
 /* constraint states */
 enum { ST_SATISFIED = 0, ST_QUADRATIC = 1, ST_LINEARNEG = 2, ST_LINEARPOS = 3, ST_CONE = 4 };
 
 struct mjcModel {
-  int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nsensordata, npair;
+  int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nsensordata, npair, neq;
   int integrator, cone, contact_disabled, iterations, ls_iterations;
   double timestep, gravity[3], impratio, tolerance, ls_tolerance, meaninertia;
   double qpos0[MJC_MAXNQ];
@@ -40,6 +40,10 @@ struct mjcModel {
   int jnt_type[MJC_MAXJNT], jnt_body[MJC_MAXJNT], jnt_qposadr[MJC_MAXJNT], jnt_dofadr[MJC_MAXJNT], jnt_limited[MJC_MAXJNT];
   double jnt_pos[MJC_MAXJNT][3], jnt_axis[MJC_MAXJNT][3], jnt_range[MJC_MAXJNT][2], jnt_margin[MJC_MAXJNT];
   double jnt_solref[MJC_MAXJNT][2], jnt_solimp[MJC_MAXJNT][5];
+  int jnt_actfrclimited[MJC_MAXJNT];
+  double jnt_actfrcrange[MJC_MAXJNT][2];
+  int eq_j1[MJC_MAXEQ], eq_j2[MJC_MAXEQ];
+  double eq_polycoef[MJC_MAXEQ][5], eq_solref[MJC_MAXEQ][2], eq_solimp[MJC_MAXEQ][5];
   int dof_jnt[MJC_MAXNV];
   double dof_damping[MJC_MAXNV], dof_frictionloss[MJC_MAXNV], dof_armature[MJC_MAXNV], dof_invweight0[MJC_MAXNV];
   double dof_solref[MJC_MAXNV][2], dof_solimp[MJC_MAXNV][5];
@@ -51,7 +55,8 @@ struct mjcModel {
   double site_pos[MJC_MAXSITE][3];
   int act_dof[MJC_MAXNU], act_ctrllimited[MJC_MAXNU], act_forcelimited[MJC_MAXNU];
   double act_gear[MJC_MAXNU], act_kp[MJC_MAXNU], act_kv[MJC_MAXNU], act_ctrlrange[MJC_MAXNU][2], act_forcerange[MJC_MAXNU][2];
-  int sens_type[MJC_MAXSENSOR], sens_obj[MJC_MAXSENSOR], sens_adr[MJC_MAXSENSOR];
+  int sens_type[MJC_MAXSENSOR], sens_obj[MJC_MAXSENSOR], sens_obj2[MJC_MAXSENSOR], sens_adr[MJC_MAXSENSOR];
+  double sens_cutoff[MJC_MAXSENSOR];
 };
 
 typedef struct {
@@ -136,10 +141,10 @@ mjcModel* mjc_model_create(const int* ib, int ni, const double* db, int nd) {
   mjcModel* m = (mjcModel*)calloc(1, sizeof(mjcModel));
   if (!m) return NULL;
   m->nq = RI(&R); m->nv = RI(&R); m->nu = RI(&R); m->nbody = RI(&R); m->njnt = RI(&R); m->ngeom = RI(&R);
-  m->nsite = RI(&R); m->nsensor = RI(&R); m->nsensordata = RI(&R); m->npair = RI(&R);
+  m->nsite = RI(&R); m->nsensor = RI(&R); m->nsensordata = RI(&R); m->npair = RI(&R); m->neq = RI(&R);
   m->integrator = RI(&R); m->cone = RI(&R); m->contact_disabled = RI(&R); m->iterations = RI(&R); m->ls_iterations = RI(&R);
   if (m->nq > MJC_MAXNQ || m->nv > MJC_MAXNV || m->nu > MJC_MAXNU || m->nbody > MJC_MAXBODY || m->njnt > MJC_MAXJNT ||
-      m->ngeom > MJC_MAXGEOM || m->nsite > MJC_MAXSITE || m->nsensor > MJC_MAXSENSOR || m->npair > MJC_MAXPAIR) {
+      m->ngeom > MJC_MAXGEOM || m->nsite > MJC_MAXSITE || m->nsensor > MJC_MAXSENSOR || m->npair > MJC_MAXPAIR || m->neq > MJC_MAXEQ) {
     free(m);
     return NULL;
   }
@@ -153,9 +158,9 @@ mjcModel* mjc_model_create(const int* ib, int ni, const double* db, int nd) {
   }
   for (int i = 0; i < m->njnt; i++) {
     m->jnt_type[i] = RI(&R); m->jnt_body[i] = RI(&R); m->jnt_qposadr[i] = RI(&R); m->jnt_dofadr[i] = RI(&R);
-    m->jnt_limited[i] = RI(&R);
+    m->jnt_limited[i] = RI(&R); m->jnt_actfrclimited[i] = RI(&R);
     RDV(&R, m->jnt_pos[i], 3); RDV(&R, m->jnt_axis[i], 3); RDV(&R, m->jnt_range[i], 2); m->jnt_margin[i] = RD(&R);
-    RDV(&R, m->jnt_solref[i], 2); RDV(&R, m->jnt_solimp[i], 5);
+    RDV(&R, m->jnt_solref[i], 2); RDV(&R, m->jnt_solimp[i], 5); RDV(&R, m->jnt_actfrcrange[i], 2);
   }
   for (int i = 0; i < m->nv; i++) {
     m->dof_jnt[i] = RI(&R);
@@ -175,7 +180,13 @@ mjcModel* mjc_model_create(const int* ib, int ni, const double* db, int nd) {
     m->act_gear[i] = RD(&R); m->act_kp[i] = RD(&R); m->act_kv[i] = RD(&R);
     RDV(&R, m->act_ctrlrange[i], 2); RDV(&R, m->act_forcerange[i], 2);
   }
-  for (int i = 0; i < m->nsensor; i++) { m->sens_type[i] = RI(&R); m->sens_obj[i] = RI(&R); m->sens_adr[i] = RI(&R); }
+  for (int i = 0; i < m->nsensor; i++) {
+    m->sens_type[i] = RI(&R); m->sens_obj[i] = RI(&R); m->sens_obj2[i] = RI(&R); m->sens_adr[i] = RI(&R); m->sens_cutoff[i] = RD(&R);
+  }
+  for (int i = 0; i < m->neq; i++) {
+    m->eq_j1[i] = RI(&R); m->eq_j2[i] = RI(&R);
+    RDV(&R, m->eq_polycoef[i], 5); RDV(&R, m->eq_solref[i], 2); RDV(&R, m->eq_solimp[i], 5);
+  }
   if (R.err || R.ip != ni || R.dp != nd) { free(m); return NULL; }
   return m;
 }
@@ -624,6 +635,158 @@ static int collide_box_box(const double* p1, const double* m1, const double* s1,
   return nc;
 }
 
+
+/* ------------------------------------------------------------------ signed box-box distance (distance sensors)
+ * mj_geomDistance restated for the reduced (box-only) geometry: penetrating boxes -> minus the penetration depth
+ * (largest separating-axis value over the 15 SAT axes, which is exact for boxes); separated boxes -> the exact
+ * Euclidean distance by GJK on the Minkowski difference (Gilbert-Johnson-Keerthi with Ericson's closest-point
+ * sub-algorithms for segment / triangle / tetrahedron). */
+static void box_support(const double* p, const double* m, const double* s, const double* dir, double* out) {
+  for (int k = 0; k < 3; k++) out[k] = p[k];
+  for (int a = 0; a < 3; a++) {
+    double ax[3] = {m[a], m[3 + a], m[6 + a]};
+    double sg = dot3(ax, dir) >= 0 ? s[a] : -s[a];
+    for (int k = 0; k < 3; k++) out[k] += sg * ax[k];
+  }
+}
+/* closest point to the origin on segment ab; keeps the supporting vertices in W (n updated) */
+static void closest_segment(double (*W)[3], int* n, double* v) {
+  const double *a = W[0], *b = W[1];
+  double ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+  double t = -dot3(a, ab), den = dot3(ab, ab);
+  if (t <= 0 || den <= 0) { *n = 1; memcpy(v, a, 3 * sizeof(double)); return; }
+  if (t >= den) { memcpy(W[0], b, 3 * sizeof(double)); *n = 1; memcpy(v, W[0], 3 * sizeof(double)); return; }
+  t /= den;
+  for (int k = 0; k < 3; k++) v[k] = a[k] + t * ab[k];
+}
+/* closest point to the origin on triangle (Ericson 5.1.5), reducing W to the supporting feature */
+static void closest_triangle(double (*W)[3], int* n, double* v) {
+  double a[3], b[3], c[3];
+  memcpy(a, W[0], sizeof a); memcpy(b, W[1], sizeof b); memcpy(c, W[2], sizeof c);
+  double ab[3], ac[3], bc[3];
+  for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; bc[k] = c[k] - b[k]; }
+  double d1 = -dot3(ab, a), d2 = -dot3(ac, a);
+  if (d1 <= 0 && d2 <= 0) { *n = 1; memcpy(v, a, sizeof a); return; }
+  double d3 = -dot3(ab, b), d4 = -dot3(ac, b);
+  if (d3 >= 0 && d4 <= d3) { memcpy(W[0], b, sizeof b); *n = 1; memcpy(v, b, sizeof b); return; }
+  double vc = d1 * d4 - d3 * d2;
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) {
+    double t = d1 / (d1 - d3);
+    *n = 2; /* a, b already in W[0], W[1] */
+    for (int k = 0; k < 3; k++) v[k] = a[k] + t * ab[k];
+    return;
+  }
+  double d5 = -dot3(ab, c), d6 = -dot3(ac, c);
+  if (d6 >= 0 && d5 <= d6) { memcpy(W[0], c, sizeof c); *n = 1; memcpy(v, c, sizeof c); return; }
+  double vb = d5 * d2 - d1 * d6;
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) {
+    double t = d2 / (d2 - d6);
+    memcpy(W[1], c, sizeof c); *n = 2;
+    for (int k = 0; k < 3; k++) v[k] = a[k] + t * ac[k];
+    return;
+  }
+  double va = d3 * d6 - d5 * d4;
+  if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+    double t = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+    memcpy(W[0], b, sizeof b); memcpy(W[1], c, sizeof c); *n = 2;
+    for (int k = 0; k < 3; k++) v[k] = b[k] + t * bc[k];
+    return;
+  }
+  double den = 1.0 / (va + vb + vc), tv = vb * den, tw = vc * den;
+  *n = 3;
+  for (int k = 0; k < 3; k++) v[k] = a[k] + ab[k] * tv + ac[k] * tw;
+}
+/* closest point to the origin on a tetrahedron: the best of its four faces (all four are evaluated: with the nearly
+ * flat tetrahedra that parallel box faces produce, the inside/outside sign tests alone are not reliable);
+ * returns 1 when the origin is strictly inside (the sets intersect) */
+static int closest_tetrahedron(double (*W)[3], int* n, double* v) {
+  static const int F[4][4] = {{0, 1, 2, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {1, 3, 2, 0}}; /* face (i,j,k), opposite vertex l */
+  double best = 1e300, bv[3] = {0, 0, 0}, BW[3][3];
+  int bn = 0, outside_any = 0;
+  double P[4][3];
+  memcpy(P, W, sizeof P);
+  for (int f = 0; f < 4; f++) {
+    const double *a = P[F[f][0]], *b = P[F[f][1]], *c = P[F[f][2]], *dd = P[F[f][3]];
+    double ab[3], ac[3], nrm[3];
+    for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; }
+    cross3(nrm, ab, ac);
+    double so = -dot3(a, nrm);                                        /* origin side */
+    double ad[3] = {dd[0] - a[0], dd[1] - a[1], dd[2] - a[2]};
+    double sd = dot3(ad, nrm);                                        /* opposite-vertex side */
+    if (!(so * sd > 0)) outside_any = 1; /* origin not strictly on the inner side of this face (or the face is degenerate) */
+    double T[3][3], tv[3];
+    int tn = 3;
+    memcpy(T[0], a, 24); memcpy(T[1], b, 24); memcpy(T[2], c, 24);
+    closest_triangle(T, &tn, tv);
+    double dist = dot3(tv, tv);
+    if (dist < best) { best = dist; bn = tn; memcpy(bv, tv, sizeof bv); memcpy(BW, T, sizeof BW); }
+  }
+  if (!outside_any) return 1;
+  *n = bn; memcpy(v, bv, sizeof bv);
+  for (int i = 0; i < bn; i++) memcpy(W[i], BW[i], 24);
+  return 0;
+}
+static double box_box_distance(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2,
+                               const double* s2, double cutoff) {
+  /* separating-axis values (<= true distance); all negative -> penetration depth */
+  double d12[3], best = -1e300;
+  for (int k = 0; k < 3; k++) d12[k] = p2[k] - p1[k];
+  for (int which = 0; which < 2; which++)
+    for (int i = 0; i < 3; i++) {
+      const double* mm = which ? m2 : m1;
+      double ax[3] = {mm[i], mm[3 + i], mm[6 + i]}, ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) {
+        double c1[3] = {m1[k], m1[3 + k], m1[6 + k]}, c2[3] = {m2[k], m2[3 + k], m2[6 + k]};
+        ra += s1[k] * fabs(dot3(ax, c1)); rb += s2[k] * fabs(dot3(ax, c2));
+      }
+      double sep = fabs(dot3(ax, d12)) - (ra + rb);
+      if (sep > best) best = sep;
+    }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double a1[3] = {m1[i], m1[3 + i], m1[6 + i]}, a2[3] = {m2[j], m2[3 + j], m2[6 + j]}, ax[3];
+      cross3(ax, a1, a2);
+      double len = norm3(ax);
+      if (len < 1e-8) continue;
+      for (int k = 0; k < 3; k++) ax[k] /= len;
+      double ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) {
+        double c1[3] = {m1[k], m1[3 + k], m1[6 + k]}, c2[3] = {m2[k], m2[3 + k], m2[6 + k]};
+        ra += s1[k] * fabs(dot3(ax, c1)); rb += s2[k] * fabs(dot3(ax, c2));
+      }
+      double sep = fabs(dot3(ax, d12)) - (ra + rb);
+      if (sep > best) best = sep;
+    }
+  if (best <= 0) return best;
+  if (best >= cutoff) return cutoff;
+  /* GJK on A - B */
+  double W[4][3], v[3] = {-d12[0], -d12[1], -d12[2]}, vv;
+  int n = 0;
+  if (dot3(v, v) < 1e-30) { v[0] = 1; v[1] = v[2] = 0; }
+  for (int it = 0; it < 64; it++) {
+    double nd[3] = {-v[0], -v[1], -v[2]}, a[3], b[3], w[3];
+    box_support(p1, m1, s1, nd, a);
+    box_support(p2, m2, s2, v, b);
+    for (int k = 0; k < 3; k++) w[k] = a[k] - b[k];
+    vv = dot3(v, v);
+    if (n > 0 && vv - dot3(v, w) <= 1e-14 * vv) break; /* no progress possible along -v: v is the closest point */
+    int dup = 0;
+    for (int i = 0; i < n; i++) if (W[i][0] == w[0] && W[i][1] == w[1] && W[i][2] == w[2]) dup = 1;
+    if (dup) break;
+    memcpy(W[n++], w, sizeof w);
+    if (n == 1) memcpy(v, W[0], sizeof w);
+    else if (n == 2) closest_segment(W, &n, v);
+    else if (n == 3) closest_triangle(W, &n, v);
+    else if (closest_tetrahedron(W, &n, v)) return best; /* numerically touching: fall back to the SAT value */
+    if (dot3(v, v) < 1e-30) return best;
+  }
+  double dist = norm3(v);
+  return dist < cutoff ? dist : cutoff;
+}
+/* test hook */
+double mjc_box_box_distance(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2,
+                            const double* s2, double cutoff) { return box_box_distance(p1, m1, s1, p2, m2, s2, cutoff); }
+
 /* mj_contactParam: combine the two geoms' parameters (equal priority: max friction, solmix-weighted solref/solimp). */
 static void contact_param(const mjcModel* m, int g1, int g2, mjcContact* c) {
   int p1 = m->geom_priority[g1], p2 = m->geom_priority[g2];
@@ -708,6 +871,18 @@ static int add_row(mjcData* d, int nv, int type, int id, double pos, double marg
 static void make_constraint(const mjcModel* m, mjcData* d) {
   int nv = m->nv;
   d->nefc = 0;
+  /* mj_instantiateEquality, joint type: (q1 - q1_0) = poly(q2 - q2_0); always active */
+  for (int e = 0; e < m->neq; e++) {
+    int j1 = m->eq_j1[e], j2 = m->eq_j2[e];
+    const double* c = m->eq_polycoef[e];
+    double y = d->qpos[m->jnt_qposadr[j1]] - m->qpos0[m->jnt_qposadr[j1]];
+    double x = d->qpos[m->jnt_qposadr[j2]] - m->qpos0[m->jnt_qposadr[j2]];
+    double pos = y - (c[0] + x * (c[1] + x * (c[2] + x * (c[3] + x * c[4]))));
+    double deriv = c[1] + x * (2 * c[2] + x * (3 * c[3] + x * 4 * c[4]));
+    int d1 = m->jnt_dofadr[j1], d2 = m->jnt_dofadr[j2];
+    int r = add_row(d, nv, CT_EQUALITY, e, pos, 0, 0, m->dof_invweight0[d1] + m->dof_invweight0[d2]);
+    if (r >= 0) { d->efc_J[r][d1] = 1; d->efc_J[r][d2] = -deriv; }
+  }
   /* mj_instantiateFriction: one row per dof with frictionloss */
   for (int i = 0; i < nv; i++)
     if (m->dof_frictionloss[i] > 0) {
@@ -790,7 +965,8 @@ static void make_impedance(const mjcModel* m, mjcData* d) {
     const double *solref, *solimp;
     int tp = d->efc_type[r], id = d->efc_id[r];
     int friction_row = 0;
-    if (tp == CT_FRICTION_DOF) { solref = m->dof_solref[id]; solimp = m->dof_solimp[id]; friction_row = 1; }
+    if (tp == CT_EQUALITY) { solref = m->eq_solref[id]; solimp = m->eq_solimp[id]; }
+    else if (tp == CT_FRICTION_DOF) { solref = m->dof_solref[id]; solimp = m->dof_solimp[id]; friction_row = 1; }
     else if (tp == CT_LIMIT_JOINT) { solref = m->jnt_solref[id]; solimp = m->jnt_solimp[id]; }
     else {
       solref = d->contact[id].solref; solimp = d->contact[id].solimp;
@@ -820,7 +996,7 @@ static void make_impedance(const mjcModel* m, mjcData* d) {
     if (m->cone == MJC_CONE_ELLIPTIC) {
       for (int j = 1; j < c->dim - 1; j++) R[i + j + 1] = R[i + 1] * c->friction[0] * c->friction[0] / (c->friction[j] * c->friction[j]);
     } else {
-      double Rpy = 2 * c->mu * c->mu * R[i + 1];
+      double Rpy = 2 * c->mu * c->mu * R[i]; /* = 2 friction^2 R0 / impratio (regularised mu): MuJoCo's common pyramid-edge R */
       for (int j = 0; j < 2 * (c->dim - 1); j++) R[i + j] = Rpy;
     }
   }
@@ -840,7 +1016,9 @@ static void row_eval(const mjcModel* m, const mjcData* d, int r, const double* x
                      double* Hc /* 3x3 cone Hessian or NULL */) {
   int tp = d->efc_type[r];
   double D = d->efc_D[r];
-  if (tp == CT_FRICTION_DOF) {
+  if (tp == CT_EQUALITY) {
+    force[0] = -D * x[0]; *cost += 0.5 * D * x[0] * x[0]; state[0] = ST_QUADRATIC;
+  } else if (tp == CT_FRICTION_DOF) {
     double f = d->efc_frictionloss[r], R = d->efc_R[r];
     if (x[0] <= -R * f) { force[0] = f; *cost += -0.5 * R * f * f - f * x[0]; state[0] = ST_LINEARNEG; }
     else if (x[0] >= R * f) { force[0] = -f; *cost += -0.5 * R * f * f + f * x[0]; state[0] = ST_LINEARPOS; }
@@ -1064,8 +1242,28 @@ static void fwd_constraint(const mjcModel* m, mjcData* d, Solver* s) {
 /* ------------------------------------------------------------------ mj_forward */
 static void sensors(const mjcModel* m, mjcData* d) {
   for (int i = 0; i < m->nsensor; i++) {
-    if (m->sens_type[i] == MJC_SENS_FRAMEPOS) memcpy(d->sensordata + m->sens_adr[i], d->site_xpos[m->sens_obj[i]], 3 * sizeof(double));
-    else d->sensordata[m->sens_adr[i]] = d->qpos[m->jnt_qposadr[m->sens_obj[i]]];
+    double* out = d->sensordata + m->sens_adr[i];
+    int o = m->sens_obj[i];
+    switch (m->sens_type[i]) {
+      case MJC_SENS_FRAMEPOS: memcpy(out, d->site_xpos[o], 3 * sizeof(double)); break;
+      case MJC_SENS_JOINTPOS: out[0] = d->qpos[m->jnt_qposadr[o]]; break;
+      case MJC_SENS_FRAMEPOS_BODY: memcpy(out, d->xpos[o], 3 * sizeof(double)); break;
+      case MJC_SENS_FRAMEZAXIS_BODY: out[0] = d->xmat[o][2]; out[1] = d->xmat[o][5]; out[2] = d->xmat[o][8]; break;
+      case MJC_SENS_DISTANCE: { /* mjSENS_GEOMDIST with body1/body2: min over the geom pairs, initialised to the cutoff */
+        double cut = m->sens_cutoff[i], best = cut;
+        for (int g1 = 0; g1 < m->ngeom; g1++) {
+          if (m->geom_body[g1] != o || m->geom_type[g1] != MJC_GEOM_BOX) continue;
+          for (int g2 = 0; g2 < m->ngeom; g2++) {
+            if (m->geom_body[g2] != m->sens_obj2[i] || m->geom_type[g2] != MJC_GEOM_BOX) continue;
+            double dd = box_box_distance(d->geom_xpos[g1], d->geom_xmat[g1], m->geom_size[g1], d->geom_xpos[g2], d->geom_xmat[g2],
+                                         m->geom_size[g2], cut);
+            if (dd < best) best = dd;
+          }
+        }
+        out[0] = fmin(fmax(best, -cut), cut); /* sensor post-processing: real-valued data is clipped to +-cutoff */
+        break;
+      }
+    }
   }
 }
 
@@ -1094,6 +1292,12 @@ static void forward(const mjcModel* m, mjcData* d, Solver* s) {
     d->actuator_force[a] = f;
     d->qfrc_actuator[dof] += m->act_gear[a] * f;
   }
+  /* joint-level clamp of the total actuator force (jnt_actfrcrange, scalar joints) */
+  for (int j = 0; j < m->njnt; j++)
+    if (m->jnt_actfrclimited[j] && (m->jnt_type[j] == MJC_JNT_SLIDE || m->jnt_type[j] == MJC_JNT_HINGE)) {
+      int da = m->jnt_dofadr[j];
+      d->qfrc_actuator[da] = fmin(fmax(d->qfrc_actuator[da], m->jnt_actfrcrange[j][0]), m->jnt_actfrcrange[j][1]);
+    }
   /* mj_fwdAcceleration */
   for (int i = 0; i < nv; i++) { d->qfrc_smooth[i] = d->qfrc_passive[i] - d->qfrc_bias[i] + d->qfrc_actuator[i]; d->qacc_smooth[i] = d->qfrc_smooth[i]; }
   chol_solve(d->L, d->qacc_smooth, nv);

@@ -27,6 +27,7 @@ extern "C" {
 #define MJC_MAXSITE 8
 #define MJC_MAXSENSOR 32
 #define MJC_MAXPAIR 2600
+#define MJC_MAXEQ 4
 #define MJC_MAXCON 96
 #define MJC_MAXEFC 400
 
@@ -34,7 +35,7 @@ enum { MJC_JNT_FREE = 0, MJC_JNT_BALL = 1, MJC_JNT_SLIDE = 2, MJC_JNT_HINGE = 3 
 enum { MJC_GEOM_SPHERE = 2, MJC_GEOM_CAPSULE = 3, MJC_GEOM_CYLINDER = 5, MJC_GEOM_BOX = 6 };
 enum { MJC_INT_EULER = 0, MJC_INT_IMPLICITFAST = 1 };
 enum { MJC_CONE_PYRAMIDAL = 0, MJC_CONE_ELLIPTIC = 1 };
-enum { MJC_SENS_FRAMEPOS = 0, MJC_SENS_JOINTPOS = 1 };
+enum { MJC_SENS_FRAMEPOS = 0, MJC_SENS_JOINTPOS = 1, MJC_SENS_FRAMEPOS_BODY = 2, MJC_SENS_FRAMEZAXIS_BODY = 3, MJC_SENS_DISTANCE = 4 };
 
 typedef struct mjcModel mjcModel;
 
@@ -64,6 +65,11 @@ int mjc_forward_debug(const mjcModel* m, const double* qpos, const double* qvel,
                       double* M, double* qfrc_bias, double* qfrc_passive, double* qfrc_actuator,
                       double* qacc_smooth, double* qacc, double* qfrc_constraint, int* ncon_out,
                       double* contact_dist, double* contact_frame, double* contact_pos, int* solver_iter);
+
+/* Signed distance between two boxes (centre p, 3x3 row-major frame m, half-sizes s), clipped above at cutoff: the routine
+ * behind the restated mjSENS_GEOMDIST sensors; exported for tests. */
+double mjc_box_box_distance(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2,
+                            const double* s2, double cutoff);
 
 #ifdef __cplusplus
 }

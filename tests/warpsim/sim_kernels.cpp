@@ -35,3 +35,37 @@ extern "C" int sim_leap_plan_costs(const double* consts, const double* x0, const
   });
   return 0;
 }
+
+// ------------------------------------------------------------------ fr3_pick
+#include "fr3.cuh"
+
+extern "C" int sim_fr3_nconsts() { return (int)(sizeof(Fr3Model) / sizeof(double)); }
+extern "C" int sim_fr3_work_bytes() { return (int)sizeof(Fr3Work); }
+
+extern "C" int sim_fr3_rollout(const double* consts, const double* x0, int batched, const double* controls, int N, int H, double* states,
+                               double* sensors, int wpb, int sync_mode, int reverse) {
+  const Fr3Model* m = reinterpret_cast<const Fr3Model*>(consts);
+  const size_t ws = fr3_wstride(0, 0, H);
+  wsim::set_reverse(reverse != 0);
+  wsim::launch((N + wpb - 1) / wpb, 32 * wpb, wpb * ws, [&] {
+    fr3_rollout_kernel<false>(m, x0, batched, controls, N, H, 0, nullptr, nullptr, states, sensors, nullptr, nullptr, (int)ws, sync_mode, SampleSpec{}, 0);
+  });
+  return 0;
+}
+
+extern "C" int sim_fr3_plan_costs(const double* consts, const double* x0, const double* knots, int N, int K, const double* basis, int H,
+                                  const double* params, float* cost_NH, double* reward_N, int wpb, int sync_mode, int reverse) {
+  const Fr3Model* m = reinterpret_cast<const Fr3Model*>(consts);
+  const size_t ws = fr3_wstride(1, K, H);
+  wsim::set_reverse(reverse != 0);
+  wsim::launch((N + wpb - 1) / wpb, 32 * wpb, wpb * ws, [&] {
+    fr3_rollout_kernel<true>(m, x0, 0, knots, N, H, K, basis, params, nullptr, nullptr, cost_NH, reward_N, (int)ws, sync_mode, SampleSpec{}, 0);
+  });
+  return 0;
+}
+
+extern "C" int sim_fr3_reward(const double* states, const double* sensors, int N, int H, const double* params, double* reward_N) {
+  wsim::set_reverse(false);
+  wsim::launch((N + 127) / 128, 128, 0, [&] { fr3_reward_kernel(states, sensors, N, H, params, reward_N); });
+  return 0;
+}

@@ -14,7 +14,7 @@ XML = "/root/reference/judo/models/xml"
 OUT = os.path.join(os.path.dirname(__file__), "..", "judo_b200", "models")
 
 for task, fname in [("cartpole", "cartpole.xml"), ("cylinder_push", "cylinder_push.xml"), ("leap_cube", "leap_cube.xml"),
-                    ("leap_cube_down", "leap_cube_palm_down.xml")]:
+                    ("leap_cube_down", "leap_cube_palm_down.xml"), ("fr3_pick", "fr3_pick.xml")]:
     m = compile_mjcf(os.path.join(XML, fname))
     with open(os.path.join(OUT, f"{task}.json"), "w") as f:
         json.dump(m, f, indent=1)
