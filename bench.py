@@ -1,6 +1,6 @@
 """bench.py — the plan-step benchmark (BASELINE.json metric: rollouts/sec per control step; plan latency p50).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cartpole_mppi|cylinder_push_cem|leap_cube_mppi]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cartpole_mppi|cylinder_push_cem|leap_cube_mppi|fr3_pick_cem]
   python bench.py --impl reference ...        # the reference's CPU path (oracle port; MuJoCo is not installable here)
   torchrun --nproc-per-node N bench.py --gpus N ...   # one rank per GPU, weak scaling: every rank owns n_rollouts
 
@@ -33,7 +33,13 @@ WORKLOADS = {
                               algo_bytes_per_rollout=236),
     "leap_cube_mppi": dict(task="leap_cube", optimizer="mppi", n_rollouts=1024, H=40, K=4, order="cubic", horizon=0.4,
                            algo_bytes_per_rollout=420),
+    # SURVEY §8f-2 (not a BASELINE config): the reference's fr3_pick defaults (H = 1.0 s / 4 ms, CEM, 4 linear knots) at N = 1024
+    "fr3_pick_cem": dict(task="fr3_pick", optimizer="cem", n_rollouts=1024, H=250, K=4, order="linear", horizon=1.0,
+                         algo_bytes_per_rollout=4 * 4 * 8 + 4 * 250 + 4),
 }
+WARP_TASKS = ("leap_cube", "fr3_pick")  # warp-per-rollout kernels: ms-scale steps, optimizer update as separate reduction kernels
+CONFIG_TAG = {"cartpole_mppi": "BASELINE config C2", "cylinder_push_cem": "BASELINE config C3", "leap_cube_mppi": "BASELINE config C4",
+              "fr3_pick_cem": "SURVEY 8f-2, reference defaults at N=1024"}
 
 
 def problem(w: dict, n_total: int, seed: int = 42):
@@ -107,11 +113,13 @@ def cpu_port_plan_step(w: dict, x0, knots, basis, params, opt, nthread: int = 0)
 
     om = cpu_port_plan_step.models.setdefault(w["task"], _oracle_model(w["task"]))
     controls = np.einsum("hk,nkj->nhj", basis, knots)
-    states, _ = om.rollout(x0, controls, nthread=nthread or host_threads())  # every host thread this process may run on
+    states, sensors = om.rollout(x0, controls, nthread=nthread or host_threads())  # every host thread this process may run on
     if w["task"] == "cartpole":
         r = op.cartpole_reward(states, controls, *params)
     elif w["task"] == "cylinder_push":
         r = op.cylinder_push_reward(states, controls, params[0], params[1], params[2], params[3], params[4:6])
+    elif w["task"] == "fr3_pick":
+        r = op.fr3_pick_reward(states, sensors, int(params[0]), params[11:13], params[13], params[1:3], params[3:5], params[5:7], params[7:11])
     else:
         r = op.leap_cube_reward(states, params[2:6], params[0], params[1])
     if w["optimizer"] == "mppi":
@@ -140,6 +148,12 @@ def _oracle_model(task: str):
 
         tb = load_table(task)
         geoms, pairs = reduced_collision_model(tb)
+        return OracleModel(tb, pairs=pairs, geoms=geoms)
+    if task == "fr3_pick":
+        from judo_b200.tasks.fr3_pick import reduced_collision_model as fr3_reduced
+
+        tb = load_table(task)
+        geoms, pairs = fr3_reduced(tb)
         return OracleModel(tb, pairs=pairs, geoms=geoms)
     return OracleModel(task)
 
@@ -195,8 +209,7 @@ def main() -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     n_local = w["n_rollouts"]
     n_total = n_local * world
-    config = {"workload": f"{w['task']}+{w['optimizer']} N={n_local}/GPU H={w['H']} K={w['K']} spline={w['order']} (BASELINE config "
-                          f"{'C2' if args.workload == 'cartpole_mppi' else 'C3' if args.workload == 'cylinder_push_cem' else 'C4'})",
+    config = {"workload": f"{w['task']}+{w['optimizer']} N={n_local}/GPU H={w['H']} K={w['K']} spline={w['order']} ({CONFIG_TAG[args.workload]})",
               "n_rollouts_per_gpu": n_local, "n_rollouts_total": n_total, "horizon_steps": w["H"], "num_nodes": w["K"],
               "parallelism": f"rollout-sharded x{world}", "exchange": "see exchange_used", "l2": "flushed (256 MiB memset) between timed iterations",
               "contract": "B (fused: knots in, cost matrix f32 + reward out)"}
@@ -207,7 +220,7 @@ def main() -> None:
             return
         task, opt, x0, knots, basis, params = problem(w, n_local)
         # bounded sample per step so that steps+warmup finish within minutes
-        n_sample = min(n_local, 4096 if w["task"] != "leap_cube" else 256)
+        n_sample = min(n_local, 4096 if w["task"] not in WARP_TASKS else (256 if w["task"] == "leap_cube" else 64))
         nt = best_thread_count(w, x0, knots[:n_sample], basis, params, opt)
         for _ in range(min(args.warmup, 3)):
             cpu_port_plan_step(w, x0, knots[:n_sample], basis, params, opt, nthread=nt)
@@ -265,7 +278,7 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    in_kernel_exchange = world > 1 and planner.peer_exchange and w["task"] != "leap_cube"
+    in_kernel_exchange = world > 1 and planner.peer_exchange and w["task"] not in WARP_TASKS
     for _ in range(max(args.warmup, 3)):
         planner.step(w["optimizer"], opt_params, index_offset=lo)
     barrier()
@@ -326,7 +339,7 @@ def main() -> None:
         t1 = time.perf_counter()
         # world > 1 with the peer exchange open: n_elite=0 makes the host-API step a GLOBAL MPPI update across the ranks
         res = eng.plan_step(x0, knots, basis, params, w["optimizer"], opt_params, want_rewards=True,
-                            n_elite=0 if (world > 1 and planner.peer_exchange and w["task"] != "leap_cube") else 5)
+                            n_elite=0 if (world > 1 and planner.peer_exchange and w["task"] not in WARP_TASKS) else 5)
         e2e_times.append(time.perf_counter() - t1)
     e2e_times = e2e_times[max(args.warmup, 3):]
     e2e_tt = torch.tensor([sum(e2e_times), statistics.median(e2e_times)], dtype=torch.float64, device=dev)
@@ -408,9 +421,9 @@ def main() -> None:
         c1.engine.close()
 
     # the CPU baseline is timed on rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host cores)
-    cpu = time_cpu(w, x0, knots, basis, params, opt, args.cpu_budget, min(n_local, 4096 if w["task"] != "leap_cube" else 256)) if world == 1 else None
+    cpu = time_cpu(w, x0, knots, basis, params, opt, args.cpu_budget, min(n_local, 4096 if w["task"] not in WARP_TASKS else (256 if w["task"] == "leap_cube" else 64))) if world == 1 else None
     config["exchange_used"] = ("in-kernel P2P stores over NVLink (CUDA IPC), 1 launch per step" if world > 1 and planner.peer_exchange and
-                               w["task"] != "leap_cube" else ("nccl all_gather + combine kernel" if world > 1 else "none"))
+                               w["task"] not in WARP_TASKS else ("nccl all_gather + combine kernel" if world > 1 else "none"))
     config.pop("exchange", None)
     out = {"metric": "rollouts/sec per control step", "value": value, "unit": "rollouts/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -19,7 +19,7 @@ extern "C" {
 
 typedef struct b200mpc_handle b200mpc_handle;
 
-enum { B200MPC_TASK_CARTPOLE = 0, B200MPC_TASK_CYLINDER_PUSH = 1, B200MPC_TASK_LEAP_CUBE = 2 };
+enum { B200MPC_TASK_CARTPOLE = 0, B200MPC_TASK_CYLINDER_PUSH = 1, B200MPC_TASK_LEAP_CUBE = 2, B200MPC_TASK_FR3_PICK = 3 };
 enum { B200MPC_OPT_MPPI = 0, B200MPC_OPT_CEM = 1, B200MPC_OPT_PS = 2 };
 
 /* Task dimensions as the reference's MjModel reports them (nq, nv, nu, nsensordata). */
@@ -69,6 +69,10 @@ int b200mpc_plan_costs(b200mpc_handle* h, const double* x0, const double* knots,
  *   states (N,H,nq+nv), controls (N,H,nu) -> reward_N (N) */
 int b200mpc_reward(b200mpc_handle* h, const double* states, const double* controls, int N, int H, const double* cost_params,
                    double* reward_N);
+/* Same with the sensor trajectories, for rewards that read them (judo/tasks/fr3_pick.py:248-252: distance sensors, grasp
+ * site, end-effector axis).   sensors (N,H,nsensordata); NULL is accepted for the tasks whose reward ignores sensors. */
+int b200mpc_reward_sensors(b200mpc_handle* h, const double* states, const double* sensors, const double* controls, int N, int H,
+                           const double* cost_params, double* reward_N);
 
 /* ---- optimizer updates ----------------------------------------------------------------------------------------
  * Replace: MPPI.update_nominal_knots (judo/optimizers/mppi.py:61-82),

@@ -34,6 +34,7 @@ SIGNATURES = {
     "b200mpc_rollout": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp]),
     "b200mpc_plan_costs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "b200mpc_reward": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "b200mpc_reward_sensors": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "b200mpc_update_mppi": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp]),
     "b200mpc_update_cem": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _d, _vp, _vp]),
     "b200mpc_update_ps": (_i, [_vp, _vp, _vp, _i, _i, _vp]),

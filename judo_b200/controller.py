@@ -40,6 +40,8 @@ set_config_overrides("cylinder_push", ControllerConfig, {"horizon": 1.0, "spline
 set_config_overrides("cartpole", ControllerConfig, {"horizon": 1.0, "spline_order": "zero"})
 set_config_overrides("leap_cube", ControllerConfig, {"horizon": 1.0, "spline_order": "cubic", "max_num_traces": 1})
 set_config_overrides("leap_cube_down", ControllerConfig, {"horizon": 1.0, "spline_order": "cubic", "max_num_traces": 1})
+# judo/controller/overrides.py:91-102
+set_config_overrides("fr3_pick", ControllerConfig, {"horizon": 1.0, "spline_order": "linear", "max_num_traces": 3, "control_freq": 20.0})
 
 
 class Spline:
@@ -84,7 +86,7 @@ class Controller:
         self.rewards = np.zeros((N,))
         self.reset()
         self.traces = None
-        self.trace_sensors = [i for i, (tp, nm) in enumerate(zip(self.model.sensor_types, self.model.sensor_names)) if tp == "framepos" and "trace" in nm]
+        self.trace_sensors = [i for i, (tp, nm) in enumerate(zip(self.model.sensor_types, self.model.sensor_names)) if tp in ("framepos", "framepos_body") and "trace" in nm]
         self.num_trace_elites = min(self.max_num_traces, len(self.rewards))
         self.num_trace_sensors = len(self.trace_sensors)
         self.sensor_rollout_size = self.num_timesteps - 1

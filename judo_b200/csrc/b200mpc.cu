@@ -15,6 +15,7 @@
 #ifdef B200MPC_WITH_LEAP
 #include "leap.cuh"
 #endif
+#include "fr3.cuh"
 
 using namespace b2;
 
@@ -31,6 +32,7 @@ struct b200mpc_handle {
 #ifdef B200MPC_WITH_LEAP
   LeapModel* leap = nullptr;  // device-resident constant table
 #endif
+  Fr3Model* fr3 = nullptr;
   // device buffers (grown on demand)
   void* d_in = nullptr; size_t d_in_bytes = 0;      // packed inputs [x0 | basis | params | knots/controls]
   void* d_out = nullptr; size_t d_out_bytes = 0;    // packed small outputs [nominal | sigma | elite | reward_N]
@@ -99,6 +101,10 @@ extern "C" int b200mpc_create(b200mpc_handle** out, int task_id, const double* c
 #else
     return bad("leap_cube kernel not built into this library");
 #endif
+  } else if (task_id == B200MPC_TASK_FR3_PICK) {
+    std::string msg;
+    if (fr3_create(&h->fr3, consts, n_consts, &msg)) return bad("fr3_pick: " + msg);
+    h->dims = {FR_NQ, FR_NV, FR_NU, FR_NS, FR_NCOST};
   } else return bad("unknown task id");
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bad("cudaStreamCreate failed");
   if (const char* z = getenv("B200MPC_ZEROCOPY")) h->zero_copy = atoi(z);
@@ -121,6 +127,7 @@ extern "C" void b200mpc_destroy(b200mpc_handle* h) {
 #ifdef B200MPC_WITH_LEAP
   if (h->leap) { if (getenv("B200MPC_LEAP_PROF")) leap_prof_dump(); leap_destroy(h->leap); }
 #endif
+  if (h->fr3) fr3_destroy(h->fr3);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -224,6 +231,13 @@ extern "C" int b200mpc_rollout_dev(b200mpc_handle* h, const double* d_x0, int ba
       return 0;
     }
 #endif
+    case B200MPC_TASK_FR3_PICK: {
+      PlanEpilogue none{};
+      none.optimizer = EP_NONE;
+      if (fr3_launch(h->fr3, /*cost_mode=*/0, d_x0, batched, d_ctrl, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, none, SampleSpec{}, st, &h->err)) return 1;
+      h->launches++;
+      return 0;
+    }
   }
   return fail(h, "task not supported");
 }
@@ -243,6 +257,11 @@ static int plan_costs_ep(b200mpc_handle* h, const double* d_x0, const double* d_
       return 0;
     }
 #endif
+    case B200MPC_TASK_FR3_PICK: {
+      if (fr3_launch(h->fr3, /*cost_mode=*/1, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep, smp, st, &h->err)) return 1;
+      h->launches++;
+      return 0;
+    }
   }
   return fail(h, "task not supported");
 }
@@ -256,6 +275,7 @@ static int n_warp_partials(const b200mpc_handle* h, int N) {
 #ifdef B200MPC_WITH_LEAP
   if (h->task == B200MPC_TASK_LEAP_CUBE) return leap_num_partials(N);
 #endif
+  if (h->task == B200MPC_TASK_FR3_PICK) return N;
   int thr = pick_threads(N);
   return ((N + thr - 1) / thr) * (thr / 32);
 }
@@ -313,7 +333,7 @@ static int plan_step_impl(b200mpc_handle* h, const double* d_x0, const double* d
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int KNU = K * h->dims.nu;
-  if (h->task == B200MPC_TASK_LEAP_CUBE) {
+  if (h->task == B200MPC_TASK_LEAP_CUBE || h->task == B200MPC_TASK_FR3_PICK) {
     // warp-per-rollout kernel (ms-scale): the update runs as separate reduction kernels (2% of the step)
     PlanEpilogue none{};
     none.optimizer = EP_NONE;
@@ -571,14 +591,22 @@ extern "C" int b200mpc_plan_costs(b200mpc_handle* h, const double* x0, const dou
 
 extern "C" int b200mpc_reward(b200mpc_handle* h, const double* states, const double* controls, int N, int H, const double* params,
                               double* reward_N) {
+  return b200mpc_reward_sensors(h, states, nullptr, controls, N, H, params, reward_N);
+}
+
+extern "C" int b200mpc_reward_sensors(b200mpc_handle* h, const double* states, const double* sensors, const double* controls, int N, int H,
+                                      const double* params, double* reward_N) {
   if (!h) return 1;
   if (!states || !controls || !params || !reward_N) return fail(h, "NULL argument");
+  if (h->task == B200MPC_TASK_FR3_PICK && !sensors) return fail(h, "fr3_pick's reward reads the sensors (fr3_pick.py:248-252): use b200mpc_reward_sensors");
   if (N <= 0 || H <= 0) return fail(h, "N and H must be positive");
   CK(cudaSetDevice(h->device));
   const int nx = h->dims.nq + h->dims.nv, nu = h->dims.nu, np = h->dims.n_cost_params;
   size_t bs = al16((size_t)N * H * nx * 8), bc = al16((size_t)N * H * nu * 8), bp = al16((size_t)np * 8);
-  if (grow(h, &h->d_in, &h->d_in_bytes, bs + bc + bp, false) || grow(h, &h->d_out, &h->d_out_bytes, (size_t)N * 8, false)) return 1;
+  const size_t be = sensors ? al16((size_t)N * H * h->dims.nsensordata * 8) : 0;
+  if (grow(h, &h->d_in, &h->d_in_bytes, bs + bc + bp + be, false) || grow(h, &h->d_out, &h->d_out_bytes, (size_t)N * 8, false)) return 1;
   char* din = (char*)h->d_in;
+  if (sensors) CK(cudaMemcpyAsync(din + bs + bc + bp, sensors, (size_t)N * H * h->dims.nsensordata * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(din, states, (size_t)N * H * nx * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(din + bs, controls, (size_t)N * H * nu * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(din + bs + bc, params, (size_t)np * 8, cudaMemcpyHostToDevice, h->stream));
@@ -595,6 +623,9 @@ extern "C" int b200mpc_reward(b200mpc_handle* h, const double* states, const dou
       if (leap_reward_launch(h->leap, (double*)din, N, H, (double*)(din + bs + bc), (double*)h->d_out, h->stream, &h->err)) return 1;
       break;
 #endif
+    case B200MPC_TASK_FR3_PICK:
+      if (fr3_reward_launch((double*)din, (double*)(din + bs + bc + bp), N, H, (double*)(din + bs + bc), (double*)h->d_out, h->stream, &h->err)) return 1;
+      break;
     default: return fail(h, "task not supported");
   }
   h->launches++;
@@ -674,7 +705,7 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
     // multi-GPU handles with an open peer exchange: the MPPI update is GLOBAL (partials cross NVLink inside the kernel)
     const int kout_x = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
     const bool fits_x = (optimizer == B200MPC_OPT_MPPI ? 2 + KNU : kout_x * (2 + KNU)) <= EP_XCHG_STRIDE;
-    const int fin = (h->xchg_world > 1 && h->xchg && fits_x && h->task != B200MPC_TASK_LEAP_CUBE && n_elite == 0) ? 2 : 1;
+    const int fin = (h->xchg_world > 1 && h->xchg && fits_x && h->task != B200MPC_TASK_LEAP_CUBE && h->task != B200MPC_TASK_FR3_PICK && n_elite == 0) ? 2 : 1;
     if (b200mpc_plan_step_dev(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), optimizer,
                               opt_params, fin, 0, n_elite, nullptr, d_reward, (double*)(dout + o_nom), (double*)(dout + o_sig),
                               (double*)(dout + o_el), nullptr, h->stream)) return 1;

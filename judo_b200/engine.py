@@ -90,11 +90,15 @@ class Engine:
         self._check(self._lib.b200mpc_plan_costs(self._h, _p(x0), _p(knots), N, K, _p(basis), H, _p(cost_params), cp, _p(reward)))
         return reward, cost
 
-    def reward(self, states: np.ndarray, controls: np.ndarray, cost_params: np.ndarray) -> np.ndarray:
-        states, controls, cost_params = _c(states), _c(controls), _c(cost_params)
+    def reward(self, states: np.ndarray, controls: np.ndarray, cost_params: np.ndarray, sensors: np.ndarray | None = None) -> np.ndarray:
+        states, cost_params = _c(states), _c(cost_params)
         N, H, _ = states.shape
+        # rewards that ignore the controls are called with controls=None by the reference's own tests
+        controls = np.zeros((N, H, self.nu)) if controls is None else _c(controls)
+        sensors = None if sensors is None else _c(sensors)
+        assert controls.shape == (N, H, self.nu) and (sensors is None or sensors.shape == (N, H, self.nsensordata))
         out = np.empty(N)
-        self._check(self._lib.b200mpc_reward(self._h, _p(states), _p(controls), N, H, _p(cost_params), _p(out)))
+        self._check(self._lib.b200mpc_reward_sensors(self._h, _p(states), _p(sensors), _p(controls), N, H, _p(cost_params), _p(out)))
         return out
 
     # ---- optimizer updates

@@ -26,6 +26,12 @@ set_config_overrides("leap_cube_down", PredictiveSamplingConfig, dict(_COMMON, n
 set_config_overrides("leap_cube_down", CrossEntropyMethodConfig, dict(_COMMON, num_rollouts=64, num_elites=3, noise_ramp=4.0))
 set_config_overrides("leap_cube_down", MPPIConfig, dict(_COMMON, num_rollouts=64, noise_ramp=4.0, sigma=0.2, temperature=0.0025))
 
+# overrides.py:217-254
+set_config_overrides("fr3_pick", PredictiveSamplingConfig, dict(num_nodes=8, num_rollouts=64, use_noise_ramp=True, noise_ramp=4.0, sigma=0.2))
+set_config_overrides("fr3_pick", CrossEntropyMethodConfig, dict(num_nodes=4, num_rollouts=64, num_elites=3, use_noise_ramp=True, noise_ramp=4.0,
+                                                                sigma_min=0.01, sigma_max=0.3))
+set_config_overrides("fr3_pick", MPPIConfig, dict(num_nodes=4, num_rollouts=64, use_noise_ramp=True, noise_ramp=4.0, sigma=0.01, temperature=0.002))
+
 _registered_optimizers: dict[str, tuple[Type[Optimizer], Type[OptimizerConfig]]] = {
     "cem": (CrossEntropyMethod, CrossEntropyMethodConfig),
     "mppi": (MPPI, MPPIConfig),

@@ -1,4 +1,4 @@
-"""Task registry — mirror of judo/tasks/__init__.py:25-47 for the BASELINE tasks."""
+"""Task registry — mirror of judo/tasks/__init__.py:25-47 for the BASELINE tasks and fr3_pick."""
 
 from __future__ import annotations
 
@@ -20,6 +20,10 @@ try:  # the leap task registers itself once its kernel is in the library
     _registered_tasks[LeapCubeDown.name] = (LeapCubeDown, LeapCubeDownConfig)
 except ImportError:
     pass
+
+from judo_b200.tasks.fr3_pick import FR3Pick, FR3PickConfig  # noqa: E402
+
+_registered_tasks[FR3Pick.name] = (FR3Pick, FR3PickConfig)
 
 
 def get_registered_tasks() -> Dict[str, Tuple[Type[Task], Type[TaskConfig]]]:

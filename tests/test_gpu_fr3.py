@@ -1,0 +1,131 @@
+"""GPU parity for fr3_pick: the warp-per-rollout kernel through the C ABI against the C oracle on the reduced
+(box-geometry) model, against the reference's golden rewards, and through the Controller against the reference Controller's
+golden plan steps.  Tolerances: north_star's 1e-4 on rewards / nominal knots; the fp64 same-algorithm kernel is held tighter."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import plan as op  # noqa: E402
+from tests.fr3_cases import oracle_model, scenario  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from judo_b200.engine import Engine
+
+    e = Engine("fr3_pick", 8)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("name,N,H", [("home", 16, 50), ("grasp", 24, 60), ("wild", 33, 40), ("press", 8, 40)])
+def test_fr3_rollout_matches_oracle(engine, name, N, H):
+    om = oracle_model()
+    engine.update(N)
+    x0, u = scenario(name, N, H)
+    s, e = engine.rollout(x0, u)
+    s_ref, e_ref = om.rollout(x0, u)
+    assert np.all(np.isfinite(s))
+    err = np.abs(s - s_ref).max(axis=(0, 2))
+    print(name, "state error by step:", err[:: max(1, H // 8)])
+    assert err[:5].max() < 1e-9
+    np.testing.assert_allclose(s[..., :16], s_ref[..., :16], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(e, e_ref, rtol=0, atol=1e-6)
+    xb = np.tile(x0, (N, 1))
+    xb[:, 7:14] += 0.01 * np.random.default_rng(1).normal(size=(N, 7))
+    sb, _ = engine.rollout(xb, u, want_sensors=False)
+    np.testing.assert_allclose(sb[..., :16], om.rollout(xb, u)[0][..., :16], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("phase", [0, 1, 2, 3])
+def test_fr3_plan_costs_and_plan_step_match_oracle(engine, phase):
+    from judo_b200.spline import spline_basis
+    from judo_b200.tasks.fr3_pick import FR3Pick, Phase
+
+    om = oracle_model()
+    N, H, K = 40, 50, 4
+    engine.update(N)
+    x0, u = scenario("grasp", N, K, seed=7)
+    knots = u
+    times = np.linspace(0, 0.2, K)
+    query = 0.004 * np.arange(H)
+    basis = spline_basis(times, query, "linear")
+    task = FR3Pick()
+    task.phase = Phase(phase)
+    params = task.cost_params()
+    reward, cost = engine.plan_costs(x0, knots, basis, params, want_cost_matrix=True)
+    ctrl = op.make_spline(times, knots, "linear")(query)
+    states, sensors = om.rollout(x0, ctrl)
+    ref = op.fr3_pick_reward(states, sensors, phase)
+    np.testing.assert_allclose(reward, ref, rtol=1e-4, atol=1e-4)  # north_star's bar
+    print("fr3 reward max abs err", np.abs(reward - ref).max())
+    np.testing.assert_allclose(-cost.astype(np.float64).sum(1), reward, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(engine.reward(states, ctrl, params, sensors=sensors), ref, rtol=1e-12)
+    res = engine.plan_step(x0, knots, basis, params, "cem", np.array([3, 0.01, 0.3]), want_rewards=True, n_elite=3)
+    np.testing.assert_array_equal(res["rewards"], reward)
+    nom, sig = op.cem_update(knots, reward, 3, 0.01, 0.3)
+    np.testing.assert_allclose(res["nominal"], nom, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res["sigma"], sig, rtol=1e-9, atol=1e-12)
+
+
+def test_fr3_rewards_match_reference_golden(engine, golden):
+    from judo_b200.tasks.fr3_pick import FR3Pick, Phase
+
+    g = golden("rewards_fr3")
+    t = FR3Pick()
+    t.engine = engine
+    engine.update(len(g["fr3_states"]))
+    for ph in range(4):
+        t.phase = Phase(ph)
+        np.testing.assert_allclose(t.reward(g["fr3_states"], g["fr3_sensors"], None), g[f"fr3_rewards_phase{ph}"], rtol=1e-12)
+    with pytest.raises(RuntimeError, match="sensors"):
+        engine.reward(g["fr3_states"], np.zeros((5, 7, 8)), t.cost_params())
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_fr3_controller_reproduces_reference_plan_steps(golden, temp_np_seed, fused):
+    """Three consecutive reference Controller.update_action() calls (CEM, linear spline, phase machine in pre_rollout, traces of
+    the object and the grasp site) reproduced through judo_b200's Controller."""
+    from judo_b200.controller import make_controller
+
+    g = golden("plan_fr3_pick_cem")
+    task, opt, N, horizon, seed, order, max_traces = g["meta"]
+    with temp_np_seed(int(seed)):
+        ctrl = make_controller("fr3_pick", "cem")
+        ctrl.optimizer_cfg.num_rollouts = int(N)
+        ctrl.controller_cfg.horizon = float(horizon)
+        ctrl.fused = fused
+        np.random.seed(int(seed))
+        ctrl.reset()
+        np.testing.assert_array_equal(np.concatenate([ctrl.task.data.qpos, ctrl.task.data.qvel]), g["x_init"])
+        for p in range(3):
+            ctrl.current_state = g[f"p{p}_x0"].copy()
+            ctrl.time = float(g[f"p{p}_time"])
+            ctrl.update_action()
+            assert ctrl.task.phase.value == int(g[f"p{p}_phase"])
+            np.testing.assert_allclose(ctrl.candidate_knots, g[f"p{p}_candidate_knots"], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(ctrl.rewards, g[f"p{p}_rewards"], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(ctrl.nominal_knots, g[f"p{p}_nominal_out"], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(ctrl.optimizer.sigma, g[f"p{p}_sigma_out"], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(ctrl.traces, g[f"p{p}_traces"], rtol=0, atol=1e-6)
+
+
+def test_fr3_full_size_properties(engine):
+    """Reference default size (N=64, H=250) and a large batch: finite, deterministic, rollout 0 of identical candidates equals
+    every other rollout, rewards invariant to the block shape (N changes the warps-per-block choice)."""
+    from judo_b200.spline import spline_basis
+    from judo_b200.tasks.fr3_pick import FR3Pick
+
+    task = FR3Pick()
+    H, K = 250, 4
+    basis = spline_basis(np.linspace(0, 1.0, K), 0.004 * np.arange(H), "linear")
+    x0, u = scenario("grasp", 64, K, seed=11)
+    engine.update(64)
+    r1, _ = engine.plan_costs(x0, u, basis, task.cost_params())
+    r2, _ = engine.plan_costs(x0, u, basis, task.cost_params())
+    assert np.all(np.isfinite(r1)) and np.array_equal(r1, r2)
+    big = np.tile(u, (32, 1, 1))  # 2048 rollouts: 64 distinct candidates repeated
+    engine.update(len(big))
+    rb, _ = engine.plan_costs(x0, big, basis, task.cost_params())
+    assert np.array_equal(rb.reshape(32, 64), np.tile(r1, (32, 1)))

@@ -126,9 +126,29 @@ def test_normalizers_closed_form():
 
 
 def test_task_constant_tables_have_the_struct_sizes():
-    # sizes of the all-double structs in csrc/small_tasks.cuh
+    # sizes of the all-double structs in csrc/small_tasks.cuh, csrc/fr3.cuh
     assert task_consts("cartpole").size == 38
     assert task_consts("cylinder_push").size == 39
+    assert task_consts("fr3_pick").size == 592
+
+
+def test_fr3_pick_task_surface_and_phase_machine(golden):
+    """Host side of the fr3_pick task (no GPU): indices as the reference's __init__ derives them (fr3_pick.py:111-144), the phase
+    machine against the reference's own pre_rollout outputs, the inherited control range of the gripper servo."""
+    from judo_b200.tasks.fr3_pick import QPOS_HOME, FR3Pick, Phase
+
+    task = FR3Pick()
+    assert (task.model.nq, task.model.nv, task.model.nu, task.model.nsensordata) == (16, 15, 8, 14)
+    assert task.obj_pos_adr == 0 and task.arm_pos_slice == slice(7, 16) and task.dt == 0.004
+    assert (task.left_finger_table_adr, task.right_finger_table_adr, task.obj_table_adr, task.ee_z_adr, task.grasp_site_adr) == (2, 3, 4, 5, 11)
+    np.testing.assert_array_equal(task.data.qpos, QPOS_HOME)
+    np.testing.assert_allclose(task.actuator_ctrlrange[7], [-0.02, 0.06])  # inheritrange="2.0" on a 0..0.04 joint
+    np.testing.assert_allclose(task.actuator_ctrlrange[3], [-3.0421, -0.1518])
+    g = golden("rewards_fr3")
+    for x, ph in zip(g["fr3_phase_states"], g["fr3_phases"]):
+        task.pre_rollout(x)
+        assert task.phase == Phase(int(ph))
+        assert task.cost_params()[0] == float(ph) and task.cost_params().size == 23
 
 
 def test_c_abi_library_exports_every_declared_symbol():

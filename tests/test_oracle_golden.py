@@ -44,7 +44,19 @@ def test_optimizers_oracle_matches_reference(golden, temp_np_seed):
                 np.testing.assert_array_equal(nom, g[f"c{ci}_nominal_out{it}"])
 
 
-@pytest.mark.parametrize("tag", ["cartpole_ps", "cartpole_mppi", "cylinder_push_cem", "leap_cube_mppi"])
+def test_fr3_reward_and_phase_oracle_match_reference(golden):
+    """FR3Pick.reward (four phases, custom config) and FR3Pick.pre_rollout's phase machine as executed by the reference."""
+    g = golden("rewards_fr3")
+    s, e = g["fr3_states"], g["fr3_sensors"]
+    for ph in range(4):
+        np.testing.assert_allclose(op.fr3_pick_reward(s, e, ph), g[f"fr3_rewards_phase{ph}"], rtol=1e-13)
+    gx, gy, pick, wc = g["fr3_custom"]
+    np.testing.assert_allclose(op.fr3_pick_reward(s, e, 1, goal_pos=(gx, gy), pick_height=pick, w_global=(0.25, wc, 0.005, 2.0)),
+                               g["fr3_rewards_custom"], rtol=1e-13)
+    assert [op.fr3_pick_phase(x) for x in g["fr3_phase_states"]] == list(g["fr3_phases"])
+
+
+@pytest.mark.parametrize("tag", ["cartpole_ps", "cartpole_mppi", "cylinder_push_cem", "leap_cube_mppi", "fr3_pick_cem"])
 def test_plan_golden_is_self_consistent(golden, tag):
     """The stored reference plan steps: oracle physics reproduces the stored states; oracle.plan reproduces
     controls -> rewards -> nominal -> traces from the stored candidates."""
@@ -56,9 +68,13 @@ def test_plan_golden_is_self_consistent(golden, tag):
 
         geoms, pairs = reduced_collision_model(table)
         om = OracleModel(table, pairs=pairs, geoms=geoms)
+    elif task == "fr3_pick":
+        from tests.fr3_cases import oracle_model
+
+        om = oracle_model()
     else:
         om = OracleModel(table)
-    trace_adrs = [s["adr"] for s in table["sensors"] if s["type"] == "framepos" and "trace" in s["name"]]
+    trace_adrs = [s["adr"] for s in table["sensors"] if s["type"] in ("framepos", "framepos_body") and "trace" in s["name"]]
     dt = table["opt"]["timestep"]
     for p in range(3):
         t = float(g[f"p{p}_time"])
@@ -73,6 +89,9 @@ def test_plan_golden_is_self_consistent(golden, tag):
             rew = op.cartpole_reward(states, ctrl)
         elif task == "cylinder_push":
             rew = op.cylinder_push_reward(states, ctrl)
+        elif task == "fr3_pick":
+            assert op.fr3_pick_phase(g[f"p{p}_x0"]) == int(g[f"p{p}_phase"])
+            rew = op.fr3_pick_reward(states, sensors, int(g[f"p{p}_phase"]))
         else:
             rew = op.leap_cube_reward(states, g["goal_quat"])
         np.testing.assert_allclose(rew, g[f"p{p}_rewards"], rtol=1e-13)

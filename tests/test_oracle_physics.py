@@ -101,3 +101,61 @@ def test_joint_limit_and_clamps():
     s = om.rollout(x0, edge)[0]
     jr = np.array([j["range"] for j in tb["joints"][1:]])
     assert np.all(s[0, -1, 7:23] < jr[:, 1] + 0.02) and np.all(s[0, -1, 7:23] > lo - 0.3)   # soft limits hold the joints
+
+
+# ------------------------------------------------------------------ fr3_pick (reduced box geometry)
+def test_fr3_static_equilibrium_resting_object_and_distance_sensors():
+    """The servos hold the home pose against gravity (steady-state sag = gravity torque / kp), the cube rests on the table with a
+    penetration of the order m g / k of the soft contact, the distance sensors report the geometric clearances."""
+    from tests.fr3_cases import U_HOME, oracle_model
+    from judo_b200.tasks.fr3_pick import QPOS_HOME
+
+    om = oracle_model()
+    x0 = np.concatenate([QPOS_HOME, np.zeros(15)])
+    s, e = om.rollout(x0, np.tile(U_HOME, (1, 500, 1)))
+    assert np.abs(s[0, -1, 16:]).max() < 1e-4                      # at rest
+    assert np.abs(s[0, -1, 7:14] - QPOS_HOME[7:14]).max() < 0.01   # |sag| <= tau_g / kp ~ 30 Nm / 4500
+    assert 0.0199 < s[0, -1, 2] <= 0.02 and np.abs(s[0, -1, :2] - [0.7, 0.0]).max() < 1e-6
+    np.testing.assert_allclose(s[0, -1, 3:7], [1, 0, 0, 0], atol=1e-6)
+    assert abs(e[0, -1, 4] - (s[0, -2, 2] - 0.02)) < 1e-9          # obj_table = signed clearance (sensors lag one step)
+    assert np.all(e[0, :, :4] > 0.1)                               # fingers far from object and table
+    # free flight: the cube dropped from 10 cm follows the semi-implicit Euler parabola until it lands
+    x1 = x0.copy()
+    x1[2] = 0.12
+    s, e = om.rollout(x1, np.tile(U_HOME, (1, 20, 1)))
+    k = np.arange(1, 21)
+    np.testing.assert_allclose(s[0, :, 2], 0.12 - 9.81 * 0.004**2 * k * (k + 1) / 2, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(e[0, 1:, 4], s[0, :-1, 2] - 0.02, rtol=0, atol=1e-12)  # GJK distance of a box hovering over the table
+
+
+def test_fr3_finger_equality_and_force_clamps():
+    """Only finger_joint1 is actuated; the joint equality drags finger_joint2 along.  A far-away set point on joint 1 saturates the
+    joint-level actuator force limit (87 N m): the first-step acceleration is bounded by it."""
+    from tests.fr3_cases import U_HOME, oracle_model
+    from judo_b200.tasks.fr3_pick import QPOS_HOME
+
+    om = oracle_model()
+    x0 = np.concatenate([QPOS_HOME, np.zeros(15)])
+    u = np.tile(U_HOME, (1, 150, 1))
+    u[..., 7] = 0.01
+    s, _ = om.rollout(x0, u)
+    assert abs(s[0, -1, 14] - 0.01) < 2e-3 and abs(s[0, -1, 14] - s[0, -1, 15]) < 1e-3
+    u = np.tile(U_HOME, (1, 1, 1))
+    u[..., 0] = 2.7
+    f = om.forward(QPOS_HOME, np.zeros(15), u[0, 0])
+    assert abs(f["qfrc_actuator"][6] - 87.0) < 1e-12               # kp * 2.7 = 12150 clamped to 87
+    f2 = om.forward(QPOS_HOME, np.zeros(15), U_HOME)
+    assert abs(f2["qfrc_actuator"][6]) < 1e-9
+    # friction loss holds a joint against a small torque: zero set-point error on joint 7 -> stays put
+    assert abs(f2["qacc"][12]) < 5e-3                              # (soft constraint: regularised, not exactly zero)
+
+
+def test_fr3_grasp_lifts_the_cube_by_friction():
+    from tests.fr3_cases import oracle_model, scenario
+
+    om = oracle_model()
+    x0, u = scenario("grasp", 2, 60)
+    s, e = om.rollout(x0, u)
+    assert s[:, -1, 2].min() > 0.03                                 # lifted well clear of the table
+    assert (e[:, -1, 4] > 0.005).all()                             # obj_table distance agrees
+    assert np.abs(s[:, -1, 14] - 0.0185).max() < 2e-3              # pads stopped by the 4 cm cube (pad face 1.5 mm inside the finger frame)

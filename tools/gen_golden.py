@@ -149,6 +149,67 @@ def gen_rewards() -> None:
     np.savez_compressed(os.path.join(OUT, "rewards.npz"), **out)
 
 
+def _fr3_fake(table: dict, cfg=None):  # noqa: ANN001, ANN202
+    """An instance of the reference FR3Pick whose MuJoCo objects are namespaces; indices as its __init__ computes them
+    (fr3_pick.py:111-144) from the model's joint / sensor addresses."""
+    from judo.tasks.fr3_pick import QPOS_HOME as FR3_HOME, FR3Pick, FR3PickConfig, Phase
+
+    jq = {j["name"]: j["qposadr"] for j in table["joints"]}
+    jd = {j["name"]: j["dofadr"] for j in table["joints"]}
+    sa = {s_["name"]: s_["adr"] for s_ in table["sensors"]}
+    ova = table["nq"] + jd["object_joint"]
+    extra = dict(
+        reset_command=np.array([0, 0, 0, -1.57079, 0, 1.57079, -0.7853, 0.0]), obj_pos_adr=jq["object_joint"],
+        obj_pos_slice=slice(jq["object_joint"], jq["object_joint"] + 3), obj_vel_slice=slice(ova, ova + 3),
+        obj_angvel_slice=slice(ova + 3, ova + 6), arm_pos_slice=slice(jq["fr3_joint1"], jq["fr3_joint1"] + 9),
+        left_finger_obj_adr=sa["left_finger_obj"], right_finger_obj_adr=sa["right_finger_obj"],
+        left_finger_table_adr=sa["left_finger_table"], right_finger_table_adr=sa["right_finger_table"],
+        grasp_site_adr=sa["trace_grasp_site"], obj_table_adr=sa["obj_table"], ee_z_adr=sa["ee_z"],
+        ee_z_slice=slice(sa["ee_z"], sa["ee_z"] + 3), phase=Phase.LIFT,
+        _data=types.SimpleNamespace(qpos=np.zeros(table["nq"]), qvel=np.zeros(table["nv"])),
+    )
+    t = fake_task(FR3Pick, FR3PickConfig, table, extra)
+    if cfg is not None:
+        t.config = cfg
+    t.data.qpos = FR3_HOME.copy()
+    t.data.ctrl = extra["reset_command"].copy()
+    return t, Phase
+
+
+def gen_rewards_fr3() -> None:
+    """FR3Pick.reward for the four phases and FR3Pick.pre_rollout's phase machine (fr3_pick.py:191-311), reference code executed."""
+    table = load_table("fr3_pick")
+    task, Phase = _fr3_fake(table)
+    rng = np.random.RandomState(21)
+    s = rng.randn(5, 7, 31) * 0.3
+    e = rng.randn(5, 7, 14) * 0.2
+    e[0, 1, 2] = 0.0      # exactly touching counts as touching (<= 0)
+    e[1, :, 3] = -0.01
+    out = dict(fr3_states=s, fr3_sensors=e)
+    for ph in Phase:
+        task.phase = ph
+        out[f"fr3_rewards_phase{ph.value}"] = task.reward(s, e, None)
+    task.config.goal_pos = np.array([0.5, -0.3])
+    task.config.pick_height = 0.2
+    task.config.global_weights.w_coll = 0.7
+    task.phase = Phase.MOVE
+    out["fr3_rewards_custom"] = task.reward(s, e, None)
+    out["fr3_custom"] = np.array([0.5, -0.3, 0.2, 0.7])
+    # phase machine
+    task, Phase = _fr3_fake(table)
+    xs, phases = [], []
+    for x, y, z in ((0.7, 0.0, 0.02), (0.7, 0.0, 0.0211), (0.62, 0.41, 0.1), (0.6, 0.4, 0.02), (0.6, 0.4, 0.021), (0.6, 0.46, 0.5), (0.0, 0.0, 0.0)):
+        st = np.zeros(31)
+        st[:3] = [x, y, z]
+        st[3] = 1
+        task.pre_rollout(st)
+        xs.append(st)
+        phases.append(task.phase.value)
+    out["fr3_phase_states"], out["fr3_phases"] = np.array(xs), np.array(phases)
+    np.savez_compressed(os.path.join(OUT, "rewards_fr3.npz"), **out)
+    print("fr3 rewards golden: phases", phases)
+
+
 # ------------------------------------------------------------------ full plan step through the reference Controller
 class OracleBackend(RolloutBackend):
     """Stands in for MJRolloutBackend (mujoco absent): same contract, physics from the C oracle."""
@@ -190,6 +251,10 @@ def gen_plan(tag: str, task_name: str, opt_name: str, N: int, horizon: float, se
         from judo_b200.tasks.leap_cube import reduced_collision_model  # the SAME reduced geometry the product uses
         geoms, pairs = reduced_collision_model(table)
         om = OracleModel(table, pairs=pairs, geoms=geoms)
+    elif task_name == "fr3_pick":
+        from judo_b200.tasks.fr3_pick import reduced_collision_model as fr3_reduced
+        geoms, pairs = fr3_reduced(table)
+        om = OracleModel(table, pairs=pairs, geoms=geoms)
     else:
         om = OracleModel(table)
     np.random.seed(seed)
@@ -197,6 +262,8 @@ def gen_plan(tag: str, task_name: str, opt_name: str, N: int, horizon: float, se
         task = fake_task(Cartpole, CartpoleConfig, table)
     elif task_name == "cylinder_push":
         task = fake_task(CylinderPush, CylinderPushConfig, table)
+    elif task_name == "fr3_pick":
+        task, _ = _fr3_fake(table)
     else:
         rc = QPOS_HOME[7:].copy()
         task = fake_task(LeapCube, LeapCubeConfig, table, dict(goal_pos=np.array([0.0, 0.03, 0.1]), goal_quat=np.array([1.0, 0, 0, 0]),
@@ -209,7 +276,7 @@ def gen_plan(tag: str, task_name: str, opt_name: str, N: int, horizon: float, se
     ccfg = ControllerConfig()
     ccfg.set_override(task_name)
     ccfg.horizon = horizon
-    trace_ids = [i for i, s in enumerate(table["sensors"]) if s["type"] == "framepos" and "trace" in s["name"]]
+    trace_ids = [i for i, s in enumerate(table["sensors"]) if s["type"] in ("framepos", "framepos_body") and "trace" in s["name"]]
     with mock.patch.object(ref_ctrl, "MJRolloutBackend", lambda model, num_threads: OracleBackend(om, num_threads)), \
             mock.patch.object(ref_ctrl, "get_trace_sensors", lambda model: trace_ids):
         ctrl = Controller(ccfg, task, opt)
@@ -239,6 +306,8 @@ def gen_plan(tag: str, task_name: str, opt_name: str, N: int, horizon: float, se
         out[f"p{step}_traces"] = ctrl.traces.copy()
         if opt_name == "cem":
             out[f"p{step}_sigma_out"] = opt.sigma.copy()
+        if task_name == "fr3_pick":
+            out[f"p{step}_phase"] = np.array(task.phase.value)
         # advance the "plant" along the best rollout for a few steps so x0 changes between plans
         best = int(np.argmax(ctrl.rewards))
         k = 2
@@ -260,6 +329,9 @@ if __name__ == "__main__":
         gen_plan("cartpole_ps", "cartpole", "ps", 32, 1.28, 42)           # BASELINE config C1
         gen_plan("cartpole_mppi", "cartpole", "mppi", 64, 2.56, 43)       # C2 at a size the fixture can hold
         gen_plan("cylinder_push_cem", "cylinder_push", "cem", 48, 1.0, 44)  # C3, reduced N
+    if "fr3" in which:
+        gen_rewards_fr3()
+        gen_plan("fr3_pick_cem", "fr3_pick", "cem", 12, 0.12, 46)          # §8f-2, reduced N and horizon (H = 30)
     if "leap" in which:
         gen_plan("leap_cube_mppi", "leap_cube", "mppi", 16, 0.4, 45)      # C4, reduced N
     print("golden written to", os.path.abspath(OUT))
