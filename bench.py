@@ -394,7 +394,8 @@ def main() -> None:
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
-                "kernel": ("leap_rollout_kernel<COST>" if w["task"].startswith("leap") else "rollout_kernel<Task, COST, MAXK>") + " (fused spline+dynamics+cost)", "kernel_ms": kernel_ms,
+                "kernel": ("leap_rollout_kernel<COST>" if w["task"].startswith("leap") else "fr3_rollout_kernel<COST>" if w["task"] == "fr3_pick"
+                           else "rollout_kernel<Task, COST, MAXK>") + " (fused spline+dynamics+cost)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "N independent serial recurrences: latency/issue-bound by construction, HBM fraction is expected to be <<1% "
                         "(SURVEY.md §8d); see profiles/ for occupancy and stall reasons"}

@@ -78,6 +78,7 @@ __device__ inline double impedance(const double* solimp, double pos, double marg
   if (x <= 0) return d0;
   double y;
   if (power == 1) y = x;
+  else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);  // MuJoCo's default power without two pow() calls
   else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
   else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
   return d0 + y * (dw - d0);

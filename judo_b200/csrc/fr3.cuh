@@ -26,7 +26,8 @@ constexpr int FB = 11;        // moving bodies: 0 object, 1..7 links, 8 hand (we
 constexpr int FNA = 9;        // arm dofs (global dof = 6 + j): 7 hinges, 2 finger slides
 constexpr int FNPAD = 10, FNPAIR = 21;  // pairs: 0 table-object, 1..10 table-pad, 11..20 object-pad
 constexpr int FMAXCON = 48;   // contacts kept per step (4 pyramid rows each)
-constexpr int FMAXS = 20;     // scalar rows: 1 equality + 9 friction loss + <= 9 active limits
+constexpr int FNS = 19;       // scalar rows in FIXED slots: 0 equality, 1 + j friction loss of arm dof j, 10 + j joint limit of arm dof j
+constexpr int FMAXS = 20;
 constexpr int FLD = 16;       // leading dimension of the dense matrices
 #ifndef B2_FULLMASK
 #define B2_FULLMASK 0xffffffffu
@@ -52,28 +53,42 @@ struct Fr3Model {
   double cutoff;
 };
 
-// per-warp shared-memory work area
+// per-warp shared-memory work area (31.7 KB: seven rollouts per SM, i.e. N = 1024 is a single wave on 148 SMs)
 struct Fr3Work {
   double qpos[FR_NQ], qvel[FR_NV], warm[FR_NV], ctrl[FR_NU];
   double xpos[FB][3], xmat[FB][9], xipos[FB][3], Iw[FB][6];
   double anchor[FNA][3], axis[FNA][3];
-  double M[FNA][FLD], L[FNA][FLD], Ld[FLD];   // arm mass matrix, its (or M + h D's) Cholesky factor, reciprocal pivots
-  double H[FR_NV][FLD], Hd[FLD];              // Newton Hessian / factor
+  double M[FNA][FNA + 1], Ld[FLD];            // arm mass matrix; reciprocal pivots of the arm factor
+  double H[FR_NV][FLD], Hd[FLD];              // Newton Hessian / factor; outside the solver rows 0..8 hold the arm factor of M (+ h D)
   double qfrc_bias[FR_NV], qfrc_smooth[FR_NV], qacc_smooth[FR_NV], qacc[FR_NV], qfrc_constraint[FR_NV];
   double Ma[FR_NV], grad[FR_NV], search[FR_NV], Mv[FR_NV];
   double sD[FMAXS], sR[FMAXS], saref[FMAXS], sjar[FMAXS], sforce[FMAXS], sfl[FMAXS], ssign[FMAXS];
-  int sdof[FMAXS], sstate[FMAXS];
+  int sstate[FMAXS];
   double cdist[FMAXCON];
-  double cgeo[FMAXCON][12];     // while rows are built: contact point (3) + frame (9); in the solver: jv (3), force (3), weight (6)
+  double cgeo[FMAXCON][12];     // while rows are built: contact point (3) + frame (9); in the solver: aref (3), jar (3), force (3)
   double cJ[FMAXCON][3][FR_NV]; // frame-row Jacobians (normal, tangent 1, tangent 2)
-  double cD[FMAXCON], cmu[FMAXCON], caref[FMAXCON][3], cjar[FMAXCON][3];
+  double cD[FMAXCON], cmu[FMAXCON];
   int ccls[FMAXCON], cbody[FMAXCON];
   double pdist[FNPAIR + 3], sens[FR_NS];
-  int ncon, ns;
+  int ncon;
   double cost, gauss;
 };
+constexpr int CG_AREF = 0, CG_JAR = 3, CG_FORCE = 6;  // solver-phase layout of cgeo[c]
 
-enum { FST_SATISFIED = 0, FST_QUADRATIC = 1, FST_LINEARNEG = 2, FST_LINEARPOS = 3 };
+// lower-triangle entry e -> (row, column) of the 15x15 Hessian, packed as row * 16 + column
+__device__ const unsigned char FR3_TRI[FR_NV * (FR_NV + 1) / 2] = {
+    0x00, 0x10, 0x11, 0x20, 0x21, 0x22, 0x30, 0x31, 0x32, 0x33, 0x40, 0x41, 0x42, 0x43, 0x44, 0x50, 0x51, 0x52, 0x53, 0x54, 0x55, 0x60, 0x61, 0x62,
+    0x63, 0x64, 0x65, 0x66, 0x70, 0x71, 0x72, 0x73, 0x74, 0x75, 0x76, 0x77, 0x80, 0x81, 0x82, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x90, 0x91, 0x92,
+    0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0xa0, 0xa1, 0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb0, 0xb1, 0xb2, 0xb3, 0xb4, 0xb5,
+    0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xbb, 0xc0, 0xc1, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xcb, 0xcc, 0xd0, 0xd1, 0xd2, 0xd3, 0xd4,
+    0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xdb, 0xdc, 0xdd, 0xe0, 0xe1, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xeb, 0xec, 0xed, 0xee};
+
+// optional phase timers (B200MPC_FR3_PROF=1): clock64 deltas accumulated by lane 0
+__device__ unsigned long long g_fr3_prof[16];
+#define FPROF_T() (prof ? clock64() : 0)
+#define FPROF_ADD(slot, t0) do { if (prof && lane == 0) atomicAdd(&g_fr3_prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
+
+enum { FST_SATISFIED = 0, FST_QUADRATIC = 1, FST_LINEARNEG = 2, FST_LINEARPOS = 3, FST_INACTIVE = 4 };
 
 __device__ __forceinline__ double fwsum(double v) {
 #pragma unroll
@@ -82,90 +97,102 @@ __device__ __forceinline__ double fwsum(double v) {
 }
 
 // ------------------------------------------------------------------ kinematics (mj_kinematics + mj_comPos)
-// lane 0: the arm chain (serial by nature); lane 1: the free object; then lane per body for inertial frames / world inertias.
+// The arm is a serial chain, but composing rigid transforms is associative: lane c < 9 builds the parent-relative transform of chain
+// body 1 + c (links 1..7, hand, left finger), an inclusive warp scan (4 shuffle rounds) turns them into world transforms; lane 9 hangs the
+// right finger off the hand's result; lane 10 is the free object.  (Rotation matrices are composed instead of quaternions: the
+// difference to the oracle's sequential quaternion recursion is rounding-level.)
+__device__ __forceinline__ void fr3_xf_compose(double* R, double* p, const double* Ra, const double* pa) {  // (R, p) <- (Ra, pa) o (R, p)
+  double t[3], Rn[9];
+  lmat_vec(t, Ra, p);
+  lmat_mul(Rn, Ra, R);
+#pragma unroll
+  for (int k = 0; k < 3; k++) p[k] = pa[k] + t[k];
+#pragma unroll
+  for (int k = 0; k < 9; k++) R[k] = Rn[k];
+}
 __device__ inline void fr3_kinematics(const Fr3Model* __restrict__ m, Fr3Work* W, int lane) {
-  if (lane == 1) {
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+  const int b = lane + 1;  // body of this lane (lanes 0..9)
+  if (lane < 10) {
+    double quat[4] = {m->body_quat[b][0], m->body_quat[b][1], m->body_quat[b][2], m->body_quat[b][3]};
+    if (b <= 7) {  // hinge about the local axis through the body origin
+      double sn, cs, dq[4], nq[4];
+      sincos(0.5 * W->qpos[7 + lane], &sn, &cs);
+      dq[0] = cs; dq[1] = sn * m->jnt_axis[b][0]; dq[2] = sn * m->jnt_axis[b][1]; dq[3] = sn * m->jnt_axis[b][2];
+      lquat_mul(nq, quat, dq);
+#pragma unroll
+      for (int k = 0; k < 4; k++) quat[k] = nq[k];
+    }
+    lquat_normalize(quat);
+    lquat2mat(R, quat);
+#pragma unroll
+    for (int k = 0; k < 3; k++) p[k] = m->body_pos[b][k];
+    if (b >= 9) {  // slide along the local axis
+      double ax[3];
+      lmat_vec(ax, R, m->jnt_axis[b]);
+      const double q = W->qpos[7 + b - 2];
+#pragma unroll
+      for (int k = 0; k < 3; k++) p[k] += ax[k] * q;
+    }
+    if (lane == 0) {  // the chain hangs off the (static) base frame
+      double Rb[9];
+      lquat2mat(Rb, m->base_quat);
+      fr3_xf_compose(R, p, Rb, m->base_pos);
+    }
+  } else if (lane == 10) {
     lquat_normalize(W->qpos + 3);
 #pragma unroll
     for (int k = 0; k < 3; k++) W->xpos[0][k] = W->qpos[k];
     lquat2mat(W->xmat[0], W->qpos + 3);
-  } else if (lane == 0) {
-    double ppos[3], pquat[4], pmat[9], hpos[3], hquat[4], hmat[9];
+  }
+  // inclusive scan over the chain lanes 0..8
 #pragma unroll
-    for (int k = 0; k < 3; k++) ppos[k] = m->base_pos[k];
+  for (int d = 1; d < 16; d <<= 1) {
+    double Ra[9], pa[3];
 #pragma unroll
-    for (int k = 0; k < 4; k++) pquat[k] = m->base_quat[k];
-    lquat2mat(pmat, pquat);
-    for (int b = 1; b < FB; b++) {
-      if (b == 10) {  // the right finger hangs off the hand too
+    for (int k = 0; k < 9; k++) Ra[k] = __shfl_up_sync(B2_FULLMASK, R[k], d);
 #pragma unroll
-        for (int k = 0; k < 3; k++) ppos[k] = hpos[k];
+    for (int k = 0; k < 3; k++) pa[k] = __shfl_up_sync(B2_FULLMASK, p[k], d);
+    if (lane >= d && lane < 9) fr3_xf_compose(R, p, Ra, pa);
+  }
+  {  // right finger: parent = hand = lane 7
+    double Ra[9], pa[3];
 #pragma unroll
-        for (int k = 0; k < 4; k++) pquat[k] = hquat[k];
+    for (int k = 0; k < 9; k++) Ra[k] = __shfl_sync(B2_FULLMASK, R[k], 7);
 #pragma unroll
-        for (int k = 0; k < 9; k++) pmat[k] = hmat[k];
-      }
-      double pos[3], quat[4], t[3], mat[9];
-      lmat_vec(t, pmat, m->body_pos[b]);
+    for (int k = 0; k < 3; k++) pa[k] = __shfl_sync(B2_FULLMASK, p[k], 7);
+    if (lane == 9) fr3_xf_compose(R, p, Ra, pa);
+  }
+  if (lane < 10) {
 #pragma unroll
-      for (int k = 0; k < 3; k++) pos[k] = ppos[k] + t[k];
-      lquat_mul(quat, pquat, m->body_quat[b]);
-      if (b <= 7) {  // hinge about the local axis through the body origin
-        const int j = b - 1;
-        double axis[3], dq[4], nq[4], sn, cs;
-        lquat2mat(mat, quat);
-        lmat_vec(axis, mat, m->jnt_axis[b]);
-        sincos(0.5 * W->qpos[7 + j], &sn, &cs);
-        dq[0] = cs; dq[1] = sn * m->jnt_axis[b][0]; dq[2] = sn * m->jnt_axis[b][1]; dq[3] = sn * m->jnt_axis[b][2];
-        lquat_mul(nq, quat, dq);
+    for (int k = 0; k < 3; k++) W->xpos[b][k] = p[k];
 #pragma unroll
-        for (int k = 0; k < 3; k++) { W->anchor[j][k] = pos[k]; W->axis[j][k] = axis[k]; }
+    for (int k = 0; k < 9; k++) W->xmat[b][k] = R[k];
+    if (b != 8) {  // joint anchor (= body origin) and world axis of arm dof j
+      const int j = b <= 7 ? b - 1 : b - 2;
+      double ax[3];
+      lmat_vec(ax, R, m->jnt_axis[b]);
 #pragma unroll
-        for (int k = 0; k < 4; k++) quat[k] = nq[k];
-      } else if (b >= 9) {  // slide along the local axis
-        const int j = b - 2;
-        double axis[3];
-        lquat2mat(mat, quat);
-        lmat_vec(axis, mat, m->jnt_axis[b]);
-        const double q = W->qpos[7 + j];
-#pragma unroll
-        for (int k = 0; k < 3; k++) { pos[k] += axis[k] * q; W->anchor[j][k] = pos[k]; W->axis[j][k] = axis[k]; }
-      }
-      lquat_normalize(quat);
-      lquat2mat(mat, quat);
-#pragma unroll
-      for (int k = 0; k < 3; k++) { W->xpos[b][k] = pos[k]; ppos[k] = pos[k]; }
-#pragma unroll
-      for (int k = 0; k < 4; k++) pquat[k] = quat[k];
-#pragma unroll
-      for (int k = 0; k < 9; k++) { W->xmat[b][k] = mat[k]; pmat[k] = mat[k]; }
-      if (b == 8) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) hpos[k] = pos[k];
-#pragma unroll
-        for (int k = 0; k < 4; k++) hquat[k] = quat[k];
-#pragma unroll
-        for (int k = 0; k < 9; k++) hmat[k] = mat[k];
-      }
+      for (int k = 0; k < 3; k++) { W->anchor[j][k] = p[k]; W->axis[j][k] = ax[k]; }
     }
   }
   __syncwarp();
   if (lane < FB) {
-    const int b = lane;
+    const int bb = lane;
     double t[3], im[9];
-    lmat_vec(t, W->xmat[b], m->body_ipos[b]);
+    lmat_vec(t, W->xmat[bb], m->body_ipos[bb]);
 #pragma unroll
-    for (int k = 0; k < 3; k++) W->xipos[b][k] = W->xpos[b][k] + t[k];
-    lmat_mul(im, W->xmat[b], m->body_imat[b]);
+    for (int k = 0; k < 3; k++) W->xipos[bb][k] = W->xpos[bb][k] + t[k];
+    lmat_mul(im, W->xmat[bb], m->body_imat[bb]);
     int e = 0;
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
       for (int c = r; c < 3; c++) {
-        double s = 0;
+        double sacc = 0;
 #pragma unroll
-        for (int k = 0; k < 3; k++) s += im[3 * r + k] * m->body_inertia[b][k] * im[3 * c + k];
-        W->Iw[b][e++] = s;  // xx xy xz yy yz zz
+        for (int k = 0; k < 3; k++) sacc += im[3 * r + k] * m->body_inertia[bb][k] * im[3 * c + k];
+        W->Iw[bb][e++] = sacc;  // xx xy xz yy yz zz
       }
   }
   __syncwarp();
@@ -180,6 +207,107 @@ __device__ __forceinline__ void fIw_mul(double* r, const double* I6, const doubl
 // arm dof j moves bodies [fr3_sub_lo(j), fr3_sub_hi(j)]
 __device__ __forceinline__ int fr3_sub_lo(int j) { return j < 7 ? j + 1 : j + 2; }
 __device__ __forceinline__ int fr3_sub_hi(int j) { return j < 7 ? 10 : j + 2; }
+
+// ------------------------------------------------------------------ bias forces of the arm (mj_rne with zero acceleration)
+// Newton-Euler in world coordinates (base: w = 0, a = -g).  Down the chain every quantity is a running sum whose increments depend
+// only on the parent's totals, so the forward pass is three warp prefix sums over the chain lanes 0..8 (body 1 + lane; lane 9 = right
+// finger, child of the hand on lane 7):  w_b = w_p + a qd;  alpha_b = alpha_p + w_p x (a qd);
+// acc_b (body origin) = acc_p + alpha_p x r + w_p x (w_p x r) [+ 2 w_p x (a qd) for a slide],  r = x_b - x_p.
+// Then lane per body: wrench about the world origin; lane per dof: projection of the subtree wrench on the joint axis.
+__device__ __forceinline__ void fr3_scan3(double* v, int lane) {  // inclusive prefix sum of a 3-vector over lanes 0..8
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const double t = __shfl_up_sync(B2_FULLMASK, v[k], d); if (lane >= d && lane < 9) v[k] += t; }
+  }
+}
+__device__ inline void fr3_rne_bias(const Fr3Model* __restrict__ m, Fr3Work* W, int lane) {
+  const int b = lane + 1;
+  const bool on = lane < 10, hinge = lane < 7, slide = lane == 8 || lane == 9;
+  const int j = hinge ? lane : lane - 1;  // arm dof of this body (hand: unused)
+  double u[3] = {0, 0, 0};                // joint velocity a qd (hinge: angular, slide: linear)
+  if (on && (hinge || slide)) {
+    const double qd = W->qvel[6 + j];
+#pragma unroll
+    for (int k = 0; k < 3; k++) u[k] = W->axis[j][k] * qd;
+  }
+  double w[3] = {0, 0, 0};
+  if (hinge) { w[0] = u[0]; w[1] = u[1]; w[2] = u[2]; }
+  fr3_scan3(w, lane);
+  double wp[3];   // parent's angular velocity
+  {
+    const double h7[3] = {__shfl_sync(B2_FULLMASK, w[0], 7), __shfl_sync(B2_FULLMASK, w[1], 7), __shfl_sync(B2_FULLMASK, w[2], 7)};
+    if (lane == 9) { w[0] = h7[0]; w[1] = h7[1]; w[2] = h7[2]; }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) wp[k] = hinge ? w[k] - u[k] : w[k];
+  double al[3] = {0, 0, 0}, dal[3] = {0, 0, 0};
+  if (hinge) lcross3(dal, wp, u);
+#pragma unroll
+  for (int k = 0; k < 3; k++) al[k] = dal[k];
+  fr3_scan3(al, lane);
+  {
+    const double h7[3] = {__shfl_sync(B2_FULLMASK, al[0], 7), __shfl_sync(B2_FULLMASK, al[1], 7), __shfl_sync(B2_FULLMASK, al[2], 7)};
+    if (lane == 9) { al[0] = h7[0]; al[1] = h7[1]; al[2] = h7[2]; }
+  }
+  double alp[3];  // parent's angular acceleration
+#pragma unroll
+  for (int k = 0; k < 3; k++) alp[k] = al[k] - dal[k];
+  double ac[3] = {0, 0, 0};
+  if (on) {
+    const double* xp = lane == 0 ? m->base_pos : (lane == 9 ? W->xpos[8] : W->xpos[b - 1]);
+    const double r[3] = {W->xpos[b][0] - xp[0], W->xpos[b][1] - xp[1], W->xpos[b][2] - xp[2]};
+    double t[3], t2[3], t3[3];
+    lcross3(t, wp, r); lcross3(t2, wp, t); lcross3(t3, alp, r);
+#pragma unroll
+    for (int k = 0; k < 3; k++) ac[k] = t3[k] + t2[k];
+    if (slide) {
+      lcross3(t, wp, u);
+#pragma unroll
+      for (int k = 0; k < 3; k++) ac[k] += 2 * t[k];
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) ac[k] -= m->gravity[k];
+    }
+  }
+  double dac[3] = {ac[0], ac[1], ac[2]};
+  fr3_scan3(ac, lane);
+  {
+    const double h7[3] = {__shfl_sync(B2_FULLMASK, ac[0], 7), __shfl_sync(B2_FULLMASK, ac[1], 7), __shfl_sync(B2_FULLMASK, ac[2], 7)};
+    if (lane == 9) { ac[0] = h7[0] + dac[0]; ac[1] = h7[1] + dac[1]; ac[2] = h7[2] + dac[2]; }
+  }
+  // wrench of this body about the world origin -> scratch rows of H (free outside the solver)
+  if (on) {
+    double rc[3], t[3], t2[3], t3[3], F[3], Iwa[3], Iww[3], n[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) rc[k] = W->xipos[b][k] - W->xpos[b][k];
+    lcross3(t, w, rc); lcross3(t2, w, t); lcross3(t3, al, rc);
+#pragma unroll
+    for (int k = 0; k < 3; k++) F[k] = m->body_mass[b] * (ac[k] + t3[k] + t2[k]);
+    fIw_mul(Iwa, W->Iw[b], al);
+    fIw_mul(Iww, W->Iw[b], w);
+    lcross3(t, w, Iww);
+    lcross3(n, W->xipos[b], F);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { W->H[b][k] = F[k]; W->H[b][3 + k] = Iwa[k] + t[k] + n[k]; }
+  }
+  __syncwarp();
+  if (lane < FNA) {
+    const int jj = lane, lo = fr3_sub_lo(jj), hi = fr3_sub_hi(jj);
+    double F[3] = {0, 0, 0}, N0[3] = {0, 0, 0};
+    for (int bb = lo; bb <= hi; bb++) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) { F[k] += W->H[bb][k]; N0[k] += W->H[bb][3 + k]; }
+    }
+    if (jj < 7) {
+      double t[3];
+      lcross3(t, W->anchor[jj], F);
+      W->qfrc_bias[6 + jj] = W->axis[jj][0] * (N0[0] - t[0]) + W->axis[jj][1] * (N0[1] - t[1]) + W->axis[jj][2] * (N0[2] - t[2]);
+    } else W->qfrc_bias[6 + jj] = ldot3(W->axis[jj], F);
+  }
+  __syncwarp();
+}
 
 // ------------------------------------------------------------------ mass matrix (mj_crb) and bias forces (mj_rne)
 // lanes 0..8: column j of the arm mass matrix from the composite inertia of the subtree dof j moves;
@@ -230,76 +358,8 @@ __device__ inline void fr3_mass_and_bias(const Fr3Model* __restrict__ m, Fr3Work
       W->M[j][i] = v;
     }
     if (j == 7) { W->M[7][8] = 0; W->M[8][7] = 0; }
-  } else if (lane == 9) {
-    // classical Newton-Euler in world coordinates (base: w = 0, a = -g); body order 1..10, parent of 9 and 10 is 8
-    double w[FB][3], al[FB][3], ao[FB][3], F[FB][3], N0[FB][3];
-    double Wv[3] = {0, 0, 0}, A[3] = {0, 0, 0}, Ac[3], P[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) { Ac[k] = -m->gravity[k]; P[k] = m->base_pos[k]; }
-    for (int b = 1; b < FB; b++) {
-      if (b == 10) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) { Wv[k] = w[8][k]; A[k] = al[8][k]; Ac[k] = ao[8][k]; P[k] = W->xpos[8][k]; }
-      }
-      double r[3], t[3], t2[3];
-      if (b <= 7) {
-        const int j = b - 1;
-#pragma unroll
-        for (int k = 0; k < 3; k++) r[k] = W->anchor[j][k] - P[k];
-        lcross3(t, Wv, r); lcross3(t2, Wv, t); lcross3(t, A, r);
-#pragma unroll
-        for (int k = 0; k < 3; k++) { Ac[k] += t[k] + t2[k]; P[k] = W->anchor[j][k]; }
-        const double qd = W->qvel[6 + j];
-        const double u[3] = {W->axis[j][0] * qd, W->axis[j][1] * qd, W->axis[j][2] * qd};
-        lcross3(t, Wv, u);
-#pragma unroll
-        for (int k = 0; k < 3; k++) { A[k] += t[k]; Wv[k] += u[k]; }
-      } else if (b >= 9) {
-        const int j = b - 2;
-        const double qd = W->qvel[6 + j];
-        const double u[3] = {W->axis[j][0] * qd, W->axis[j][1] * qd, W->axis[j][2] * qd};
-        lcross3(t, Wv, u);
-#pragma unroll
-        for (int k = 0; k < 3; k++) Ac[k] += 2 * t[k];  // Coriolis term of the sliding origin
-      }
-      // move the reference point to the body origin
-#pragma unroll
-      for (int k = 0; k < 3; k++) r[k] = W->xpos[b][k] - P[k];
-      lcross3(t, Wv, r); lcross3(t2, Wv, t); lcross3(t, A, r);
-#pragma unroll
-      for (int k = 0; k < 3; k++) { Ac[k] += t[k] + t2[k]; P[k] = W->xpos[b][k]; }
-#pragma unroll
-      for (int k = 0; k < 3; k++) { w[b][k] = Wv[k]; al[b][k] = A[k]; ao[b][k] = Ac[k]; }
-      // wrench of this body about the world origin
-      double ac[3], Iwa[3], Iww[3], n[3];
-#pragma unroll
-      for (int k = 0; k < 3; k++) r[k] = W->xipos[b][k] - W->xpos[b][k];
-      lcross3(t, Wv, r); lcross3(t2, Wv, t); lcross3(t, A, r);
-#pragma unroll
-      for (int k = 0; k < 3; k++) { ac[k] = Ac[k] + t[k] + t2[k]; F[b][k] = m->body_mass[b] * ac[k]; }
-      fIw_mul(Iwa, W->Iw[b], A);
-      fIw_mul(Iww, W->Iw[b], Wv);
-      lcross3(t, Wv, Iww);
-      lcross3(n, W->xipos[b], F[b]);
-#pragma unroll
-      for (int k = 0; k < 3; k++) N0[b][k] = Iwa[k] + t[k] + n[k];
-    }
-    for (int b = FB - 1; b >= 1; b--) {
-      if (b <= 7) {
-        const int j = b - 1;
-        double t[3], nn[3];
-        lcross3(t, W->anchor[j], F[b]);
-#pragma unroll
-        for (int k = 0; k < 3; k++) nn[k] = N0[b][k] - t[k];
-        W->qfrc_bias[6 + j] = ldot3(W->axis[j], nn);
-      } else if (b >= 9) W->qfrc_bias[6 + b - 2] = ldot3(W->axis[b - 2], F[b]);
-      const int p = b >= 9 ? 8 : b - 1;
-      if (p >= 1) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) { F[p][k] += F[b][k]; N0[p][k] += N0[b][k]; }
-      }
-    }
-  } else if (lane == 10) {
+  }
+  if (lane == 10) {
     const double wl[3] = {W->qvel[3], W->qvel[4], W->qvel[5]};
     const double Iwl[3] = {m->obj_inertia[0] * wl[0], m->obj_inertia[1] * wl[1], m->obj_inertia[2] * wl[2]};
     double g[3];
@@ -307,7 +367,7 @@ __device__ inline void fr3_mass_and_bias(const Fr3Model* __restrict__ m, Fr3Work
 #pragma unroll
     for (int k = 0; k < 3; k++) { W->qfrc_bias[k] = -m->body_mass[0] * m->gravity[k]; W->qfrc_bias[3 + k] = g[k]; }
   }
-  __syncwarp();
+  fr3_rne_bias(m, W, lane);
 }
 
 // y_i = (M x)_i: object block is diagonal (mass, principal inertia in the body frame), arm block dense
@@ -353,12 +413,49 @@ __device__ inline double warp_chol_solve(const double (*A)[FLD], const double* d
   return x;
 }
 
-// arm block: factorise M (+ diag(add)) into W->L; object block is diagonal
+// Same for a BLOCK-DIAGONAL matrix made of an object block (rows 0..5) and an arm block (rows 6..14): the two blocks are independent, so
+// their columns are eliminated side by side — 9 sequential columns instead of 15.
+__device__ inline void warp_chol2(double (*A)[FLD], double* dinv, int lane) {
+  const int base = lane < 6 ? 0 : 6, nloc = lane < 6 ? 6 : (lane < FR_NV ? 9 : 0);
+  for (int k = 0; k < 9; k++) {
+    const bool act = k < nloc;
+    const int col = act ? base + k : 0;
+    double d = A[col][col];
+    if (d < B2_MINVAL) d = B2_MINVAL;
+    const double rs = rsqrt(d);
+    double l = 0;
+    if (act && lane == col) dinv[col] = rs;
+    if (act && lane > col) { l = A[lane][col] * rs; A[lane][col] = l; }
+    __syncwarp();
+    if (act && lane > col)
+      for (int j = col + 1; j <= lane; j++) A[lane][j] -= l * A[j][col];
+    __syncwarp();
+  }
+}
+__device__ inline double warp_chol2_solve(const double (*A)[FLD], const double* dinv, double x, int lane) {
+  const int base = lane < 6 ? 0 : 6, nloc = lane < 6 ? 6 : (lane < FR_NV ? 9 : 0);
+  const double di = lane < FR_NV ? dinv[lane] : 0.0;
+  for (int k = 0; k < 9; k++) {
+    const bool act = k < nloc;
+    const int col = act ? base + k : 0;
+    const double yk = __shfl_sync(B2_FULLMASK, x * di, col);
+    if (act) { if (lane == col) x = yk; else if (lane > col) x -= A[lane][col] * yk; }
+  }
+  for (int k = 8; k >= 0; k--) {
+    const bool act = k < nloc;
+    const int col = act ? base + k : 0;
+    const double xk = __shfl_sync(B2_FULLMASK, x * di, col);
+    if (act) { if (lane == col) x = xk; else if (lane < col && lane >= base) x -= A[col][lane] * xk; }
+  }
+  return x;
+}
+
+// arm block: factorise M (+ diag(add)) into rows 0..8 of W->H (free outside the solver); object block is diagonal
 __device__ inline void fr3_factor_arm(Fr3Work* W, const double* add /* [FNA] or null */, int lane) {
   if (lane < FNA)
-    for (int j = 0; j <= lane; j++) W->L[lane][j] = W->M[lane][j] + ((add && j == lane) ? add[lane] : 0.0);
+    for (int j = 0; j <= lane; j++) W->H[lane][j] = W->M[lane][j] + ((add && j == lane) ? add[lane] : 0.0);
   __syncwarp();
-  warp_chol(W->L, W->Ld, FNA, lane);
+  warp_chol(W->H, W->Ld, FNA, lane);
 }
 
 // ------------------------------------------------------------------ collision + distance sensors, lane per box pair
@@ -379,17 +476,21 @@ __device__ inline void fr3_pair_geoms(const Fr3Model* __restrict__ m, const Fr3W
   else { *p1 = W->xpos[0]; *m1 = W->xmat[0]; *s1 = m->obj_size; *cls = 2; }
 }
 
-// dist_mode: 0 = every distance sensor exactly (contract A); 1 = what the cost needs (object-table value, finger-table sign)
+// dist_mode: 0 = every distance sensor exactly (contract A); 1 = what the cost needs: the SIGN of the finger-table distances (taken
+// from the contact routine's separating-axis stage, no extra work); 2 = as 1 plus the object-table VALUE (PLACE phase)
 __device__ inline void fr3_collision(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, int dist_mode) {
   LRaw raw[8];
   int n = 0, cls = 0, body = 0;
   if (lane < FNPAIR) {
     const double *p1, *m1, *s1, *m2, *s2;
     double p2[3];
+    int overlap = 0;
     fr3_pair_geoms(m, W, lane, &p1, &m1, &s1, p2, &m2, &s2, &cls, &body);
-    n = l_box_box(p1, m1, s1, p2, m2, s2, 0.0, raw, 8);
-    const bool want = dist_mode == 0 || lane <= FNPAD;
-    W->pdist[lane] = want ? l_box_box_distance(p1, m1, s1, p2, m2, s2, m->cutoff, dist_mode == 0 || lane == 0) : m->cutoff;
+    n = l_box_box(p1, m1, s1, p2, m2, s2, 0.0, raw, 8, &overlap);
+    double dist = m->cutoff;
+    if (dist_mode == 0 || (dist_mode == 2 && lane == 0)) dist = l_box_box_distance(p1, m1, s1, p2, m2, s2, m->cutoff, true);
+    else if (lane >= 1 && lane <= FNPAD) dist = overlap ? -1.0 : 1.0;
+    W->pdist[lane] = dist;
   }
   // ordered slot allocation (pair order == the oracle's): exclusive prefix of n over the lanes
   int pre = n;
@@ -425,7 +526,10 @@ __device__ inline void fr3_collision(const Fr3Model* __restrict__ m, Fr3Work* W,
 }
 
 // ------------------------------------------------------------------ constraint rows (mj_makeConstraint + mj_makeImpedance)
-__device__ __forceinline__ void fr3_KB(const double* solref, const double* solimp, double dt, double* K, double* B) {
+// one out-of-line copy of the impedance sigmoid / (K, B) conversion (pow() and the fp64 divisions are hundreds of instructions each:
+// inlining them at every call site bloats a kernel whose instruction footprint already exceeds the instruction caches)
+__device__ __noinline__ double fr3_impedance(const double* solimp, double pos, double margin) { return impedance(solimp, pos, margin); }
+__device__ __noinline__ void fr3_KB(const double* solref, const double* solimp, double dt, double* K, double* B) {
   double ref0 = solref[0];
   const double ref1 = solref[1], dmax = fmin(fmax(solimp[1], B2_MINIMP), B2_MAXIMP);
   if (ref0 > 0) {
@@ -434,9 +538,9 @@ __device__ __forceinline__ void fr3_KB(const double* solref, const double* solim
     *B = 2 / fmax(B2_MINVAL, dmax * ref0);
   } else { *K = -ref0 / fmax(B2_MINVAL, dmax * dmax); *B = -ref1 / fmax(B2_MINVAL, dmax); }
 }
-// J x for scalar row r (row 0 is the equality q13 - q14)
+// J x for scalar row r: row 0 is the equality q13 - q14, rows 1..9 / 10..18 act on arm dof r - 1 / r - 10
 __device__ __forceinline__ double fr3_srow_dot(const Fr3Work* W, int r, const double* x) {
-  return r == 0 ? x[13] - x[14] : W->ssign[r] * x[W->sdof[r]];
+  return r == 0 ? x[13] - x[14] : W->ssign[r] * x[r < 10 ? 5 + r : r - 4];
 }
 __device__ __forceinline__ double fr3_cJ_dot(const double* J, int cls, const double* x) {
   double s = 0;
@@ -452,51 +556,39 @@ __device__ __forceinline__ double fr3_cJ_dot(const double* J, int cls, const dou
 }
 
 __device__ inline void fr3_make_constraint(const Fr3Model* __restrict__ m, Fr3Work* W, int lane) {
-  // scalar rows: equality, friction loss (arm dof lane-1), limits (joint-major; lower before upper; only one side can be active)
-  bool lim_act = false;
-  double ldist = 0, lsign = 0;
-  if (lane < FNA) {
-    const double q = W->qpos[7 + lane];
-    const double dlo = q - m->lim_lo[lane], dhi = m->lim_hi[lane] - q;
-    if (dlo < m->lim_margin) { lim_act = true; ldist = dlo; lsign = 1; }
-    else if (dhi < m->lim_margin) { lim_act = true; ldist = dhi; lsign = -1; }
-  }
-  const unsigned ml = __ballot_sync(B2_FULLMASK, lim_act);
-  const int ns = 10 + __popc(ml);
-  double pos = 0, margin = 0, vel = 0, diagA = 0, fl = 0;
-  const double *solref = m->fr_solref, *solimp = m->fr_solimp;
-  int r = -1;
-  bool friction_row = false;
-  if (lane == 31) {  // the equality row is built by an otherwise idle lane
-    r = 0;
-    pos = W->qpos[14] - W->qpos[15]; vel = W->qvel[13] - W->qvel[14]; diagA = m->dof_invw[13] + m->dof_invw[14];
-    solref = m->eq_solref; solimp = m->eq_solimp;
-    W->sdof[0] = 13; W->ssign[0] = 1;
+  // scalar rows in fixed slots: lane 31 -> equality (row 0); lane j < 9 -> friction loss (row 1 + j) and joint limit (row 10 + j;
+  // lower or upper side, whichever is violated — never both; FST_INACTIVE when neither)
+  if (lane == 31) {
+    double K, B;
+    fr3_KB(m->eq_solref, m->eq_solimp, m->dt, &K, &B);
+    const double pos = W->qpos[14] - W->qpos[15], vel = W->qvel[13] - W->qvel[14];
+    const double imp = fr3_impedance(m->eq_solimp, pos, 0.0);
+    const double R = fmax(B2_MINVAL, (1 - imp) * (m->dof_invw[13] + m->dof_invw[14]) / imp);
+    W->sR[0] = R; W->sD[0] = 1 / R; W->sfl[0] = 0; W->ssign[0] = 1; W->sstate[0] = FST_QUADRATIC;
+    W->saref[0] = -B * vel - K * imp * pos;
   }
   if (lane < FNA) {
-    const int rr = 1 + lane, dof = 6 + lane;
+    const int rf = 1 + lane, rl = 10 + lane, dof = 6 + lane;
     double K, B;
     fr3_KB(m->fr_solref, m->fr_solimp, m->dt, &K, &B);
-    const double imp = impedance(m->fr_solimp, 0.0, 0.0);
-    const double R = fmax(B2_MINVAL, (1 - imp) * m->dof_invw[dof] / imp);
-    W->sdof[rr] = dof; W->ssign[rr] = 1; W->sfl[rr] = m->dof_frictionloss[dof];
-    W->sR[rr] = R; W->sD[rr] = 1 / R; W->saref[rr] = -B * W->qvel[dof];
-    if (lim_act) {
-      r = 10 + __popc(ml & ((1u << lane) - 1));
-      pos = ldist; margin = m->lim_margin; vel = lsign * W->qvel[dof]; diagA = m->dof_invw[dof];
-      solref = m->lim_solref; solimp = m->lim_solimp;
-      W->sdof[r] = dof; W->ssign[r] = lsign;
-    }
+    double imp = fr3_impedance(m->fr_solimp, 0.0, 0.0);
+    double R = fmax(B2_MINVAL, (1 - imp) * m->dof_invw[dof] / imp);
+    W->ssign[rf] = 1; W->sfl[rf] = m->dof_frictionloss[dof]; W->sstate[rf] = FST_QUADRATIC;
+    W->sR[rf] = R; W->sD[rf] = 1 / R; W->saref[rf] = -B * W->qvel[dof];
+    const double q = W->qpos[7 + lane];
+    const double dlo = q - m->lim_lo[lane], dhi = m->lim_hi[lane] - q;
+    double pos = 0, sign = 0;
+    if (dlo < m->lim_margin) { pos = dlo; sign = 1; }
+    else if (dhi < m->lim_margin) { pos = dhi; sign = -1; }
+    W->ssign[rl] = sign; W->sfl[rl] = 0; W->sforce[rl] = 0; W->sjar[rl] = 0;
+    if (sign != 0) {
+      fr3_KB(m->lim_solref, m->lim_solimp, m->dt, &K, &B);
+      imp = fr3_impedance(m->lim_solimp, pos, m->lim_margin);
+      R = fmax(B2_MINVAL, (1 - imp) * m->dof_invw[dof] / imp);
+      W->sR[rl] = R; W->sD[rl] = 1 / R; W->sstate[rl] = FST_SATISFIED;
+      W->saref[rl] = -B * sign * W->qvel[dof] - K * imp * (pos - m->lim_margin);
+    } else { W->sR[rl] = 1; W->sD[rl] = 0; W->saref[rl] = 0; W->sstate[rl] = FST_INACTIVE; }
   }
-  if (r >= 0) {
-    double K, B;
-    fr3_KB(solref, solimp, m->dt, &K, &B);
-    const double imp = impedance(solimp, pos, margin);
-    const double R = fmax(B2_MINVAL, (1 - imp) * diagA / imp);
-    W->sfl[r] = fl; W->sR[r] = R; W->sD[r] = 1 / R;
-    W->saref[r] = -B * vel - (friction_row ? 0.0 : K) * imp * (pos - margin);
-  }
-  if (lane == 0) W->ns = ns;
   const int ncon = W->ncon;
   // contact frame-row Jacobians: lane per (contact, axis);  J = frame_a . (Jp(body2) - Jp(body1)) at the contact point
   for (int e = lane; e < 3 * ncon; e += 32) {
@@ -538,7 +630,7 @@ __device__ inline void fr3_make_constraint(const Fr3Model* __restrict__ m, Fr3Wo
     const double mu = m->con_mu[cls];
     double K, B;
     fr3_KB(m->con_solref[cls], m->con_solimp[cls], m->dt, &K, &B);
-    const double imp = impedance(m->con_solimp[cls], W->cdist[c], 0.0);
+    const double imp = fr3_impedance(m->con_solimp[cls], W->cdist[c], 0.0);
     const double tran = (cls == 1 ? 0.0 : m->body_invw[0]) + (cls == 0 ? 0.0 : m->body_invw[b]);
     const double R0 = fmax(B2_MINVAL, (1 - imp) * (tran + mu * mu * tran) / imp);
     const double R1 = R0 / fmax(B2_MINVAL, m->impratio);
@@ -546,9 +638,10 @@ __device__ inline void fr3_make_constraint(const Fr3Model* __restrict__ m, Fr3Wo
     const double Rpy = 2 * mureg * mureg * R0;
     W->cD[c] = 1 / Rpy; W->cmu[c] = mu;
     const double vn = fr3_cJ_dot(W->cJ[c][0], cls, W->qvel), v1 = fr3_cJ_dot(W->cJ[c][1], cls, W->qvel), v2 = fr3_cJ_dot(W->cJ[c][2], cls, W->qvel);
-    W->caref[c][0] = -B * vn - K * imp * W->cdist[c];
-    W->caref[c][1] = -B * v1;
-    W->caref[c][2] = -B * v2;
+    // (the contact point / frame in cgeo[c] are dead once the Jacobians exist: the slot now holds aref, jar, force)
+    W->cgeo[c][CG_AREF] = -B * vn - K * imp * W->cdist[c];
+    W->cgeo[c][CG_AREF + 1] = -B * v1;
+    W->cgeo[c][CG_AREF + 2] = -B * v2;
   }
   __syncwarp();
 }
@@ -564,59 +657,68 @@ __device__ __forceinline__ double fr3_srow_eval(const Fr3Work* W, int r, double 
     if (x >= R * f) { *force = -f; *state = FST_LINEARPOS; return -0.5 * R * f * f + f * x; }
     *force = -D * x; *state = FST_QUADRATIC; return 0.5 * D * x * x;
   }
+  if (*state == FST_INACTIVE) { *force = 0; return 0; }
   if (x < 0) { *force = -D * x; *state = FST_QUADRATIC; return 0.5 * D * x * x; }
   *force = 0; *state = FST_SATISFIED; return 0;
 }
 // one pyramidal contact at residuals r = (rn, rt1, rt2): the 4 edge rows are rn +- mu rt_a.  Returns the cost; writes the force in the
-// (n, t1, t2) basis and, optionally, the 3x3 weight (nn, nt1, nt2, t1t1, t1t2, t2t2) of its Hessian term.
-__device__ __forceinline__ double fr3_contact_eval(double D, double mu, const double* r, double* f, double* Wt) {
-  double cost = 0, fn = 0, ft[2] = {0, 0}, cnt[2] = {0, 0}, sg[2] = {0, 0};
+// (n, t1, t2) basis.
+__device__ __forceinline__ double fr3_contact_eval(double D, double mu, const double* r, double* f) {
+  double cost = 0, fn = 0, ft[2] = {0, 0};
 #pragma unroll
   for (int a = 0; a < 2; a++)
 #pragma unroll
     for (int s = 0; s < 2; s++) {
       const double sgn = s == 0 ? 1.0 : -1.0;
       const double x = r[0] + sgn * mu * r[1 + a];
-      if (x < 0) { const double fr = -D * x; cost += 0.5 * D * x * x; fn += fr; ft[a] += sgn * mu * fr; cnt[a] += 1; sg[a] += sgn; }
+      if (x < 0) { const double fr = -D * x; cost += 0.5 * D * x * x; fn += fr; ft[a] += sgn * mu * fr; }
     }
   f[0] = fn; f[1] = ft[0]; f[2] = ft[1];
-  if (Wt) {
-    Wt[0] = D * (cnt[0] + cnt[1]); Wt[1] = D * mu * sg[0]; Wt[2] = D * mu * sg[1];
-    Wt[3] = D * mu * mu * cnt[0]; Wt[4] = 0; Wt[5] = D * mu * mu * cnt[1];
-  }
   return cost;
+}
+// 3x3 weight (nn, nt1, nt2, t1t1, t2t2) of the contact's Hessian term J^T W J in the (n, t1, t2) basis, from the active edge rows
+__device__ __forceinline__ bool fr3_contact_weight(double D, double mu, const double* r, double* w) {
+  double cnt[2] = {0, 0}, sg[2] = {0, 0};
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    if (r[0] + mu * r[1 + a] < 0) { cnt[a] += 1; sg[a] += 1; }
+    if (r[0] - mu * r[1 + a] < 0) { cnt[a] += 1; sg[a] -= 1; }
+  }
+  w[0] = D * (cnt[0] + cnt[1]); w[1] = D * mu * sg[0]; w[2] = D * mu * sg[1]; w[3] = D * mu * mu * cnt[0]; w[4] = D * mu * mu * cnt[1];
+  return cnt[0] + cnt[1] > 0;
 }
 
 // jar = J qacc - aref for every row; Ma = M qacc
 __device__ __noinline__ void fr3_set_point(const Fr3Model* __restrict__ m, Fr3Work* W, const double* qacc, int lane) {
   if (lane < FR_NV) W->Ma[lane] = fr3_mulM_row(m, W, qacc, lane);
-  const int ns = W->ns, ncon = W->ncon;
-  if (lane < ns) W->sjar[lane] = fr3_srow_dot(W, lane, qacc) - W->saref[lane];
+  const int ncon = W->ncon;
+  if (lane < FNS) W->sjar[lane] = fr3_srow_dot(W, lane, qacc) - W->saref[lane];
   for (int e = lane; e < 3 * ncon; e += 32) {
     const int c = e / 3, a = e - 3 * c;
-    W->cjar[c][a] = fr3_cJ_dot(W->cJ[c][a], W->ccls[c], qacc) - W->caref[c][a];
+    W->cgeo[c][CG_JAR + a] = fr3_cJ_dot(W->cJ[c][a], W->ccls[c], qacc) - W->cgeo[c][CG_AREF + a];
   }
   __syncwarp();
 }
 
-// cost / forces / states at the current jar, gradient, Gauss term; optionally the contact Hessian weights
-__device__ __noinline__ void fr3_constraint_update(const Fr3Model* __restrict__ m, Fr3Work* W, const double* qacc, bool want_h, int lane) {
-  const int ns = W->ns, ncon = W->ncon;
+// cost / forces / states at the current jar, gradient, Gauss term
+__device__ __noinline__ void fr3_constraint_update(const Fr3Model* __restrict__ m, Fr3Work* W, const double* qacc, int lane) {
+  const int ncon = W->ncon;
   double cost = 0;
-  if (lane < ns) cost += fr3_srow_eval(W, lane, W->sjar[lane], &W->sforce[lane], &W->sstate[lane]);
-  for (int c = lane; c < ncon; c += 32) cost += fr3_contact_eval(W->cD[c], W->cmu[c], W->cjar[c], W->cgeo[c] + 3, want_h ? W->cgeo[c] + 6 : nullptr);
+  if (lane < FNS) cost += fr3_srow_eval(W, lane, W->sjar[lane], &W->sforce[lane], &W->sstate[lane]);
+  for (int c = lane; c < ncon; c += 32) cost += fr3_contact_eval(W->cD[c], W->cmu[c], W->cgeo[c] + CG_JAR, W->cgeo[c] + CG_FORCE);
   cost = fwsum(cost);
   __syncwarp();
   double g = 0;
   if (lane < FR_NV) {
     const int i = lane;
     double f = 0;
-    for (int r = 1; r < ns; r++) if (W->sdof[r] == i) f += W->ssign[r] * W->sforce[r];
+    if (i >= 6) f = W->sforce[i - 5] + W->ssign[i + 4] * W->sforce[i + 4];  // friction-loss row 1 + j, limit row 10 + j (j = i - 6)
     if (i == 13) f += W->sforce[0]; else if (i == 14) f -= W->sforce[0];
     for (int c = 0; c < ncon; c++) {
       const int cls = W->ccls[c];
       if ((i < 6 && cls == 1) || (i >= 6 && cls == 0)) continue;
-      f += W->cJ[c][0][i] * W->cgeo[c][3] + W->cJ[c][1][i] * W->cgeo[c][4] + W->cJ[c][2][i] * W->cgeo[c][5];
+      const double* fc = W->cgeo[c] + CG_FORCE;
+      f += W->cJ[c][0][i] * fc[0] + W->cJ[c][1][i] * fc[1] + W->cJ[c][2][i] * fc[2];
     }
     W->qfrc_constraint[i] = f;
     W->grad[i] = W->Ma[i] - W->qfrc_smooth[i] - f;
@@ -629,33 +731,39 @@ __device__ __noinline__ void fr3_constraint_update(const Fr3Model* __restrict__ 
 
 // Newton direction: search = -H^-1 grad,  H = M + sum_rows D j j^T + sum_contacts Jc^T Wc Jc  (dense 15x15, lane per entry, warp Cholesky)
 __device__ inline void fr3_newton_direction(const Fr3Model* __restrict__ m, Fr3Work* W, int lane) {
-  const int ns = W->ns, ncon = W->ncon;
+  const int ncon = W->ncon;
   for (int e = lane; e < FR_NV * (FR_NV + 1) / 2; e += 32) {
-    // lower-triangle index -> (i, j), i >= j
-    int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-    while ((i + 1) * (i + 2) / 2 <= e) i++;
-    while (i * (i + 1) / 2 > e) i--;
-    const int j = e - i * (i + 1) / 2;
+    const int i = FR3_TRI[e] >> 4, j = FR3_TRI[e] & 15;  // i >= j
     double h = 0;
     if (i < 6) { if (i == j) h = i < 3 ? m->body_mass[0] : m->obj_inertia[i - 3]; }
     else if (j >= 6) h = W->M[i - 6][j - 6];
-    if (i == j) {
-      for (int r = 1; r < ns; r++) if (W->sdof[r] == i && W->sstate[r] == FST_QUADRATIC) h += W->sD[r];
-      if (i == 13 || i == 14) h += W->sD[0];
+    if (i == j && i >= 6) {
+      if (W->sstate[i - 5] == FST_QUADRATIC) h += W->sD[i - 5];
+      if (W->sstate[i + 4] == FST_QUADRATIC) h += W->sD[i + 4];
+      if (i >= 13) h += W->sD[0];
     } else if (i == 14 && j == 13) h -= W->sD[0];
     for (int c = 0; c < ncon; c++) {
       const int cls = W->ccls[c];
       if ((j < 6 && cls == 1) || (i >= 6 && cls == 0)) continue;  // i >= j: both must be touched by the contact
-      const double* w = W->cgeo[c] + 6;
-      if (w[0] == 0) continue;  // no active edge
+      double w[5];
+      if (!fr3_contact_weight(W->cD[c], W->cmu[c], W->cgeo[c] + CG_JAR, w)) continue;  // no active edge
       const double ni = W->cJ[c][0][i], nj = W->cJ[c][0][j], ai = W->cJ[c][1][i], aj = W->cJ[c][1][j], bi = W->cJ[c][2][i], bj = W->cJ[c][2][j];
-      h += w[0] * ni * nj + w[1] * (ni * aj + ai * nj) + w[2] * (ni * bj + bi * nj) + w[3] * ai * aj + w[5] * bi * bj;
+      h += w[0] * ni * nj + w[1] * (ni * aj + ai * nj) + w[2] * (ni * bj + bi * nj) + w[3] * ai * aj + w[4] * bi * bj;
     }
     W->H[i][j] = h;
   }
-  __syncwarp();
-  warp_chol(W->H, W->Hd, FR_NV, lane);
-  const double x = warp_chol_solve(W->H, W->Hd, FR_NV, lane < FR_NV ? -W->grad[lane] : 0.0, lane);
+  // object-pad contacts are the only coupling between the object block and the arm block
+  bool coupled = false;
+  for (int c = lane; c < ncon; c += 32) coupled = coupled || W->ccls[c] == 2;
+  coupled = __any_sync(B2_FULLMASK, coupled);  // (also orders the H stores above before the factorisation reads them)
+  double x;
+  if (coupled) {
+    warp_chol(W->H, W->Hd, FR_NV, lane);
+    x = warp_chol_solve(W->H, W->Hd, FR_NV, lane < FR_NV ? -W->grad[lane] : 0.0, lane);
+  } else {
+    warp_chol2(W->H, W->Hd, lane);
+    x = warp_chol2_solve(W->H, W->Hd, lane < FR_NV ? -W->grad[lane] : 0.0, lane);
+  }
   if (lane < FR_NV) W->search[lane] = x;
   __syncwarp();
 }
@@ -664,7 +772,7 @@ __device__ inline void fr3_newton_direction(const Fr3Model* __restrict__ m, Fr3W
 struct Fr3LS {
   double rjar, rjv, rD, rR, rfl;
   double cjar[2][3], cjv[2][3], cD[2], cmu[2];
-  int kind;  // -1 none, 0 equality, 1 friction, 2 limit
+  int kind;  // -1 none / inactive limit, 0 equality, 1 friction, 2 limit
   int nc;
 };
 __device__ __forceinline__ void fr3_ls_eval(const Fr3LS& L, double alpha, double g1, double g2, double* d1, double* d2) {
@@ -733,23 +841,26 @@ __device__ inline double fr3_line_search(const Fr3Model* __restrict__ m, Fr3Work
 
 // mj_fwdConstraint.  Called by ALL warps of the block; with sync_mode >= 3 the Newton iterations of the block's warps run in
 // lock-step (block barrier per iteration, finished warps idle) so the iteration body is fetched once for all of them.
-__device__ inline void fr3_fwd_constraint(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, bool active, int sync_mode) {
+__device__ inline void fr3_fwd_constraint(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, bool active, int sync_mode, int prof) {
   bool done = !active;
   double scale = 0;
   if (!done) {
-    // warm start: keep qacc_warmstart unless qacc_smooth has lower cost
-    fr3_set_point(m, W, W->warm, lane);
-    fr3_constraint_update(m, W, W->warm, false, lane);
-    const double cw = W->cost;
-    __syncwarp();
+    // warm start: keep qacc_warmstart unless qacc_smooth has lower cost.  qacc_smooth is evaluated FIRST so that in the common case
+    // (the warm start wins) the row residuals / forces / gradient left behind are already those of the chosen point
     fr3_set_point(m, W, W->qacc_smooth, lane);
-    fr3_constraint_update(m, W, W->qacc_smooth, false, lane);
+    fr3_constraint_update(m, W, W->qacc_smooth, lane);
     const double cs = W->cost;
+    __syncwarp();
+    fr3_set_point(m, W, W->warm, lane);
+    fr3_constraint_update(m, W, W->warm, lane);
+    const double cw = W->cost;
     __syncwarp();
     if (lane < FR_NV) W->qacc[lane] = cw > cs ? W->qacc_smooth[lane] : W->warm[lane];
     __syncwarp();
-    fr3_set_point(m, W, W->qacc, lane);
-    fr3_constraint_update(m, W, W->qacc, true, lane);
+    if (cw > cs) {
+      fr3_set_point(m, W, W->qacc, lane);
+      fr3_constraint_update(m, W, W->qacc, lane);
+    }
     scale = 1.0 / (m->meaninertia * FR_NV);
   }
   const int iters = (int)m->iterations;
@@ -761,15 +872,18 @@ __device__ inline void fr3_fwd_constraint(const Fr3Model* __restrict__ m, Fr3Wor
     double gn = lane < FR_NV ? W->grad[lane] * W->grad[lane] : 0.0;
     gn = fwsum(gn);
     if (scale * sqrt(gn) < m->tolerance) { done = true; continue; }
+    long long t1 = FPROF_T();
     fr3_newton_direction(m, W, lane);
-    const int ns = W->ns, ncon = W->ncon;
+    FPROF_ADD(8, t1); t1 = FPROF_T();
+    if (prof && lane == 0) atomicAdd(&g_fr3_prof[10], 1ull);
+    const int ncon = W->ncon;
     if (lane < FR_NV) W->Mv[lane] = fr3_mulM_row(m, W, W->search, lane);
     __syncwarp();
     // row data of the line search, held in registers by the lane that owns the row / contact
     Fr3LS L;
-    L.kind = lane >= ns ? -1 : lane == 0 ? 0 : lane < 10 ? 1 : 2;
+    L.kind = lane >= FNS ? -1 : lane == 0 ? 0 : lane < 10 ? 1 : (W->sstate[lane] == FST_INACTIVE ? -1 : 2);
     L.rjar = L.rjv = L.rD = L.rR = L.rfl = 0;
-    if (lane < ns) { L.rjar = W->sjar[lane]; L.rjv = fr3_srow_dot(W, lane, W->search); L.rD = W->sD[lane]; L.rR = W->sR[lane]; L.rfl = W->sfl[lane]; }
+    if (L.kind >= 0) { L.rjar = W->sjar[lane]; L.rjv = fr3_srow_dot(W, lane, W->search); L.rD = W->sD[lane]; L.rR = W->sR[lane]; L.rfl = W->sfl[lane]; }
     L.nc = 0;
 #pragma unroll
     for (int s = 0; s < 2; s++) {
@@ -780,26 +894,28 @@ __device__ inline void fr3_fwd_constraint(const Fr3Model* __restrict__ m, Fr3Wor
       if (c < ncon) {
         L.nc = s + 1;
 #pragma unroll
-        for (int a = 0; a < 3; a++) { L.cjar[s][a] = W->cjar[c][a]; L.cjv[s][a] = fr3_cJ_dot(W->cJ[c][a], W->ccls[c], W->search); }
+        for (int a = 0; a < 3; a++) { L.cjar[s][a] = W->cgeo[c][CG_JAR + a]; L.cjv[s][a] = fr3_cJ_dot(W->cJ[c][a], W->ccls[c], W->search); }
         L.cD[s] = W->cD[c]; L.cmu[s] = W->cmu[c];
       }
     }
     const double alpha = fr3_line_search(m, W, lane, L);
+    FPROF_ADD(9, t1); t1 = FPROF_T();
     if (alpha == 0) { done = true; continue; }
     const double oldcost = W->cost;
     __syncwarp();
     if (lane < FR_NV) { W->qacc[lane] += alpha * W->search[lane]; W->Ma[lane] += alpha * W->Mv[lane]; }
-    if (lane < ns) W->sjar[lane] = L.rjar + alpha * L.rjv;
+    if (L.kind >= 0) W->sjar[lane] = L.rjar + alpha * L.rjv;
 #pragma unroll
     for (int s = 0; s < 2; s++) {
       const int c = lane + 32 * s;
       if (c < ncon) {
 #pragma unroll
-        for (int a = 0; a < 3; a++) W->cjar[c][a] = L.cjar[s][a] + alpha * L.cjv[s][a];
+        for (int a = 0; a < 3; a++) W->cgeo[c][CG_JAR + a] = L.cjar[s][a] + alpha * L.cjv[s][a];
       }
     }
     __syncwarp();
-    fr3_constraint_update(m, W, W->qacc, true, lane);
+    fr3_constraint_update(m, W, W->qacc, lane);
+    FPROF_ADD(7, t1);
     const double newcost = W->cost;
     __syncwarp();
     if (scale * (oldcost - newcost) < m->tolerance) done = true;
@@ -807,15 +923,21 @@ __device__ inline void fr3_fwd_constraint(const Fr3Model* __restrict__ m, Fr3Wor
 }
 
 // ------------------------------------------------------------------ one mj_step
-__device__ inline void fr3_step(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, int dist_mode, bool active, int sync_mode) {
+__device__ inline void fr3_step(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, int dist_mode, bool active, int sync_mode, int prof) {
+  long long t0 = FPROF_T();
   if (active) {
     fr3_kinematics(m, W, lane);
+    FPROF_ADD(0, t0); t0 = FPROF_T();
     fr3_mass_and_bias(m, W, lane);
+    FPROF_ADD(1, t0);
   }
   if (sync_mode >= 2) __syncthreads();
+  t0 = FPROF_T();
   if (active) {
     fr3_collision(m, W, lane, dist_mode);
+    FPROF_ADD(2, t0); t0 = FPROF_T();
     fr3_make_constraint(m, W, lane);
+    FPROF_ADD(3, t0); t0 = FPROF_T();
     // passive + actuation -> qfrc_smooth; qacc_smooth = M^-1 qfrc_smooth
     if (lane < FR_NV) {
       const int i = lane;
@@ -833,22 +955,25 @@ __device__ inline void fr3_step(const Fr3Model* __restrict__ m, Fr3Work* W, int 
     double x = 0;
     if (lane < 3) x = W->qfrc_smooth[lane] / m->body_mass[0];
     else if (lane < 6) x = W->qfrc_smooth[lane] / m->obj_inertia[lane - 3];
-    const double xa = warp_chol_solve(W->L, W->Ld, FNA, lane < FNA ? W->qfrc_smooth[6 + lane] : 0.0, lane);
+    const double xa = warp_chol_solve(W->H, W->Ld, FNA, lane < FNA ? W->qfrc_smooth[6 + lane] : 0.0, lane);
     if (lane < 6) W->qacc_smooth[lane] = x;
     if (lane < FNA) W->qacc_smooth[6 + lane] = xa;
     __syncwarp();
+    FPROF_ADD(4, t0);
   }
   if (sync_mode >= 2) __syncthreads();
-  fr3_fwd_constraint(m, W, lane, active, sync_mode);
+  t0 = FPROF_T();
+  fr3_fwd_constraint(m, W, lane, active, sync_mode, prof);
   __syncwarp();
   if (!active) return;
+  FPROF_ADD(5, t0); t0 = FPROF_T();
   // implicitfast: (M + h (damping + kv)) qacc = qfrc_smooth + qfrc_constraint on the arm block; the object block has no
   // velocity-dependent forces, so its qacc is the solver's; then the semi-implicit advance
   const double h = m->dt;
   if (lane < FNA) W->Mv[lane] = h * (m->dof_damping[6 + lane] + (lane < FR_NU ? m->kv[lane] : 0.0));
   __syncwarp();
   fr3_factor_arm(W, W->Mv, lane);
-  const double qa = warp_chol_solve(W->L, W->Ld, FNA, lane < FNA ? W->qfrc_smooth[6 + lane] + W->qfrc_constraint[6 + lane] : 0.0, lane);
+  const double qa = warp_chol_solve(W->H, W->Ld, FNA, lane < FNA ? W->qfrc_smooth[6 + lane] + W->qfrc_constraint[6 + lane] : 0.0, lane);
   double qo = 0;
   if (lane < 3) qo = (W->qfrc_smooth[lane] + W->qfrc_constraint[lane]) / m->body_mass[0];
   else if (lane < 6) qo = (W->qfrc_smooth[lane] + W->qfrc_constraint[lane]) / m->obj_inertia[lane - 3];
@@ -869,6 +994,7 @@ __device__ inline void fr3_step(const Fr3Model* __restrict__ m, Fr3Work* W, int 
     for (int k = 0; k < 4; k++) W->qpos[3 + k] = nq[k];
   } else if (lane >= 6 && lane < FR_NV) W->qpos[lane + 1] += h * W->qvel[lane];
   __syncwarp();
+  FPROF_ADD(6, t0);
 }
 
 // per-step cost (fr3_pick.py:225-311): phase term + global terms, from the POST-step state and this step's sensordata.
@@ -908,6 +1034,8 @@ __global__ void __launch_bounds__(256) fr3_rollout_kernel(const Fr3Model* __rest
                                                           const double* __restrict__ cost_params, double* __restrict__ states,
                                                           double* __restrict__ sensors, float* __restrict__ cost_NH, double* __restrict__ reward_N,
                                                           int wstride, int sync_mode, const SampleSpec smp, int index_offset) {
+  const int prof = sync_mode >> 8;
+  sync_mode &= 255;
   B2_DYNAMIC_SMEM(unsigned char, fsm_all);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int n = blockIdx.x * wpb + wib;
@@ -921,29 +1049,25 @@ __global__ void __launch_bounds__(256) fr3_rollout_kernel(const Fr3Model* __rest
   }
   __syncwarp();
   if constexpr (COST) {
+    // this rollout's knots (K*8 doubles) are staged behind the work area with one TMA bulk copy; the (H,K) basis is shared by
+    // every rollout and stays in global memory (K cached loads per lane and step) so that seven work areas fit one SM
     uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + ((sizeof(Fr3Work) + 15) & ~(size_t)15));
     double* sK = reinterpret_cast<double*>(bar + 2);
-    double* sB = sK + K * FR_NU;
+    const int dist_mode = (int)cost_params[0] == 2 ? 2 : 1;  // only the PLACE phase reads the object-table distance value
     if (active) {
-      const unsigned bytesK = (unsigned)(K * FR_NU * sizeof(double)), bytesB = (unsigned)(H * K * sizeof(double));
+      const unsigned bytesK = (unsigned)(K * FR_NU * sizeof(double));
       const double* gK = in + (size_t)n * K * FR_NU;
-      const bool want_knots = !smp.enabled;
-      const bool tma_ok = (bytesB % 16 == 0) && ((reinterpret_cast<uintptr_t>(basis) & 15) == 0) && (!want_knots || (reinterpret_cast<uintptr_t>(gK) & 15) == 0);
-      if (tma_ok) {
-        if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_expect_tx(bar, (want_knots ? bytesK : 0u) + bytesB);
-          if (want_knots) tma_bulk_g2s(sK, gK, bytesK, bar);
-          tma_bulk_g2s(sB, basis, bytesB, bar);
+      if (!smp.enabled) {
+        if ((reinterpret_cast<uintptr_t>(gK) & 15) == 0) {
+          if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+          __syncwarp();
+          if (lane == 0) { mbar_expect_tx(bar, bytesK); tma_bulk_g2s(sK, gK, bytesK, bar); }
+          mbar_wait(bar, 0);
+        } else {
+          for (int i = lane; i < K * FR_NU; i += 32) sK[i] = gK[i];
+          __syncwarp();
         }
-        mbar_wait(bar, 0);
       } else {
-        if (want_knots) for (int i = lane; i < K * FR_NU; i += 32) sK[i] = gK[i];
-        for (int i = lane; i < H * K; i += 32) sB[i] = basis[i];
-        __syncwarp();
-      }
-      if (smp.enabled) {
         const long long gn = (long long)n + index_offset;
         const int KNU = K * FR_NU;
         for (int p2 = lane; 2 * p2 < KNU; p2 += 32) {
@@ -962,11 +1086,11 @@ __global__ void __launch_bounds__(256) fr3_rollout_kernel(const Fr3Model* __rest
       if (sync_mode >= 1) __syncthreads();
       if (active && lane < FR_NU) {
         double u = 0;
-        for (int k = 0; k < K; k++) u += sB[t * K + k] * sK[k * FR_NU + lane];
+        for (int k = 0; k < K; k++) u += __ldg(basis + t * K + k) * sK[k * FR_NU + lane];
         W->ctrl[lane] = u;
       }
       __syncwarp();
-      fr3_step(m, W, lane, 1, active, sync_mode);
+      fr3_step(m, W, lane, dist_mode, active, sync_mode, prof);
       if (active && lane == 0) {
         double cp[FR_NCOST];
 #pragma unroll
@@ -984,7 +1108,7 @@ __global__ void __launch_bounds__(256) fr3_rollout_kernel(const Fr3Model* __rest
       if (sync_mode >= 1) __syncthreads();
       if (active && lane < FR_NU) W->ctrl[lane] = in[((size_t)n * H + t) * FR_NU + lane];
       __syncwarp();
-      fr3_step(m, W, lane, 0, active, sync_mode);
+      fr3_step(m, W, lane, 0, active, sync_mode, prof);
       if (!active) continue;
       double* so = states + ((size_t)n * H + t) * FR_NX;
       if (lane < FR_NQ) so[lane] = W->qpos[lane];
@@ -1012,7 +1136,8 @@ __global__ void fr3_reward_kernel(const double* __restrict__ states, const doubl
 }
 
 inline size_t fr3_wstride(int cost_mode, int K, int H) {
-  size_t w = ((sizeof(Fr3Work) + 15) & ~(size_t)15) + 16 + (cost_mode ? ((size_t)K * FR_NU + (size_t)H * K) * sizeof(double) : 0);
+  (void)H;
+  size_t w = ((sizeof(Fr3Work) + 15) & ~(size_t)15) + 16 + (cost_mode ? (size_t)K * FR_NU * sizeof(double) : 0);
   return (w + 15) & ~(size_t)15;
 }
 
@@ -1026,13 +1151,21 @@ inline int fr3_create(Fr3Model** out, const double* consts, size_t n, std::strin
   *out = d;
   return 0;
 }
-inline void fr3_destroy(Fr3Model* m) { cudaFree(m); }
+inline void fr3_prof_dump() {
+  unsigned long long h[16];
+  if (cudaMemcpyFromSymbol(h, g_fr3_prof, sizeof(h)) != cudaSuccess) return;
+  const char* names[11] = {"kinematics", "mass+bias", "collision", "constraints", "smooth", "solver(total)", "integrate", "  update", "  direction", "  linesearch", "newton iters"};
+  for (int i = 0; i < 11; i++) fprintf(stderr, "fr3_prof %-14s %llu\n", names[i], h[i]);
+  memset(h, 0, sizeof(h));
+  cudaMemcpyToSymbol(g_fr3_prof, h, sizeof(h));
+}
+inline void fr3_destroy(Fr3Model* m) { if (getenv("B200MPC_FR3_PROF")) fr3_prof_dump(); cudaFree(m); }
 
 inline int fr3_launch(const Fr3Model* m, int cost_mode, const double* d_x0, int batched, const double* d_in, int N, int H, int K,
                       const double* d_basis, const double* d_params, double* d_states, double* d_sensors, float* d_cost, double* d_reward,
                       const PlanEpilogue& ep, const SampleSpec& smp, cudaStream_t st, std::string* err) {
   const char* sm_env = getenv("B200MPC_FR3_SYNC");
-  const int sync_mode = sm_env ? atoi(sm_env) : 3;
+  const int sync_mode = (sm_env ? atoi(sm_env) : 3) | ((getenv("B200MPC_FR3_PROF") ? 1 : 0) << 8);
   const size_t wstride = fr3_wstride(cost_mode, K, H);
   int wpb = (N + 147) / 148;  // spread the rollouts over the 148 SMs first, then stack warps per SM
   if (wpb < 1) wpb = 1;

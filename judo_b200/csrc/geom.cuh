@@ -15,7 +15,8 @@ __device__ __forceinline__ double lnorm3(const double* a) { return sqrt(ldot3(a,
 __device__ __forceinline__ double lnormalize3(double* a) {
   double n = lnorm3(a);
   if (n < B2_MINVAL) { a[0] = 1; a[1] = 0; a[2] = 0; return 0; }
-  a[0] /= n; a[1] /= n; a[2] /= n;
+  const double inv = 1.0 / n;  // one reciprocal instead of three fp64 divisions (each is a ~40-instruction sequence)
+  a[0] *= inv; a[1] *= inv; a[2] *= inv;
   return n;
 }
 __device__ __forceinline__ void lquat_mul(double* r, const double* a, const double* b) {
@@ -28,7 +29,8 @@ __device__ __forceinline__ void lquat_mul(double* r, const double* a, const doub
 __device__ __forceinline__ void lquat_normalize(double* q) {
   double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   if (n < B2_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
-  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+  const double inv = 1.0 / n;
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
 }
 __device__ __forceinline__ void lquat2mat(double* m, const double* q) {
   double w = q[0], x = q[1], y = q[2], z = q[3];
@@ -106,8 +108,10 @@ __device__ __noinline__ int l_sphere_box(const double* ps, double rs, const doub
   return 1;
 }
 
+// overlap (optional): set to 1 when no separating axis was found (the boxes interpenetrate), 0 otherwise
 __device__ __noinline__ int l_box_box(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2, const double* s2,
-                                double margin, LRaw* out, int maxout) {
+                                double margin, LRaw* out, int maxout, int* overlap = nullptr) {
+  if (overlap) *overlap = 0;
   double R[3][3], AR[3][3], t[3], d12[3];
   for (int k = 0; k < 3; k++) d12[k] = p2[k] - p1[k];
   lmatT_vec(t, m1, d12);
@@ -128,26 +132,33 @@ __device__ __noinline__ int l_box_box(const double* p1, const double* m1, const 
     if (sep >= margin) return 0;
     if (sep > best) { best = sep; code = 3 + j; bsign = tj >= 0 ? 1 : -1; }
   }
-  double ebest = -1e300; int ecode = -1; double esign = 1, eaxis[3] = {0, 0, 0};
+  // edge-edge axes L = A_i x B_j in closed form (orthonormal frames): with i1 = i+1, i2 = i+2 (mod 3), same for j,
+  //   d12 . L = t[i2] R[i1][j] - t[i1] R[i2][j],   r1 = s1[i1] |R[i2][j]| + s1[i2] |R[i1][j]|,   r2 = s2[j1] |R[i][j2]| + s2[j2] |R[i][j1]|,
+  //   |L|^2 = R[i1][j]^2 + R[i2][j]^2  — one rsqrt per axis, no square root / division chain
+  double ebest = -1e300; int ecode = -1; double esign = 1;
+#pragma unroll
   for (int i = 0; i < 3; i++)
+#pragma unroll
     for (int j = 0; j < 3; j++) {
-      double a1[3] = {m1[i], m1[3 + i], m1[6 + i]}, a2[3] = {m2[j], m2[3 + j], m2[6 + j]}, ax[3];
-      lcross3(ax, a1, a2);
-      double len = lnorm3(ax);
-      if (len < 1e-8) continue;
-      for (int k = 0; k < 3; k++) ax[k] /= len;
-      double td = ldot3(ax, d12), ra = 0, rb = 0;
-      for (int k = 0; k < 3; k++) {
-        double c1[3] = {m1[k], m1[3 + k], m1[6 + k]}, c2[3] = {m2[k], m2[3 + k], m2[6 + k]};
-        ra += s1[k] * fabs(ldot3(ax, c1)); rb += s2[k] * fabs(ldot3(ax, c2));
-      }
-      double sep = fabs(td) - (ra + rb);
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const double len2 = R[i1][j] * R[i1][j] + R[i2][j] * R[i2][j];
+      if (len2 < 1e-16) continue;
+      const double td = t[i2] * R[i1][j] - t[i1] * R[i2][j];
+      const double rr = s1[i1] * fabs(R[i2][j]) + s1[i2] * fabs(R[i1][j]) + s2[j1] * fabs(R[i][j2]) + s2[j2] * fabs(R[i][j1]);
+      const double sep = (fabs(td) - rr) * rsqrt(len2);
       if (sep >= margin) return 0;
-      if (sep > ebest) { ebest = sep; ecode = 6 + 3 * i + j; esign = td >= 0 ? 1 : -1; eaxis[0] = ax[0]; eaxis[1] = ax[1]; eaxis[2] = ax[2]; }
+      if (sep > ebest) { ebest = sep; ecode = 6 + 3 * i + j; esign = td >= 0 ? 1 : -1; }
     }
+  if (overlap) *overlap = 1;
   if (ecode >= 0 && ebest > best + 1e-6 + 0.05 * fabs(best)) {
     int i = (ecode - 6) / 3, j = (ecode - 6) % 3;
-    double n[3] = {eaxis[0] * esign, eaxis[1] * esign, eaxis[2] * esign};
+    double n[3];
+    {
+      const double a1[3] = {m1[i], m1[3 + i], m1[6 + i]}, a2[3] = {m2[j], m2[3 + j], m2[6 + j]};
+      lcross3(n, a1, a2);
+      const double sc = esign * rsqrt(ldot3(n, n));
+      n[0] *= sc; n[1] *= sc; n[2] *= sc;
+    }
     double c1[3] = {p1[0], p1[1], p1[2]}, c2[3] = {p2[0], p2[1], p2[2]};
     for (int k = 0; k < 3; k++) {
       if (k != i) { double a[3] = {m1[k], m1[3 + k], m1[6 + k]}; double sg = ldot3(a, n) > 0 ? 1 : -1; for (int q = 0; q < 3; q++) c1[q] += sg * s1[k] * a[q]; }
@@ -191,15 +202,22 @@ __device__ __noinline__ int l_box_box(const double* p1, const double* m1, const 
   const double e1u = l1[ru] - l0[ru], e1v = l1[rv] - l0[rv], e1h = l1[raxis] - l0[raxis];
   const double e2u = l2[ru] - l0[ru], e2v = l2[rv] - l0[rv], e2h = l2[raxis] - l0[raxis];
   const double det = e1u * e2v - e1v * e2u;
+  const double idet = fabs(det) > 1e-14 ? 1.0 / det : 0.0;
+  // clipping is the identity when the whole incident face projects inside the reference face (the common case on large faces)
+  bool inside = true;
+#pragma unroll
+  for (int c = 0; c < 4; c++) inside = inside && fabs(poly[c][0]) <= sr[ru] && fabs(poly[c][1]) <= sr[rv];
+  if (!inside) {
   n = l_clip_poly(poly, n, 0, 1, sr[ru]);
   if (n) n = l_clip_poly(poly, n, 0, -1, sr[ru]);
   if (n) n = l_clip_poly(poly, n, 1, 1, sr[rv]);
   if (n) n = l_clip_poly(poly, n, 1, -1, sr[rv]);
+  }
   int nc = 0;
   for (int c = 0; c < n && nc < maxout; c++) {
     double du = poly[c][0] - l0[ru], dv = poly[c][1] - l0[rv], h;
     if (fabs(det) > 1e-14) {
-      double a = (du * e2v - dv * e2u) / det, b = (e1u * dv - e1v * du) / det;
+      double a = (du * e2v - dv * e2u) * idet, b = (e1u * dv - e1v * du) * idet;
       h = l0[raxis] + a * e1h + b * e2h;
     } else h = l0[raxis];
     double dist = nsign * h - sr[raxis];
@@ -313,34 +331,35 @@ __device__ __noinline__ int l_closest_tetrahedron(double (*W)[3], int* n, double
 }
 __device__ __noinline__ double l_box_box_distance(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2,
                                                 const double* s2, double cutoff, bool want_value) {
-  double d12[3], best = -1e300;
+  double d12[3], best = -1e300, R[3][3], t[3];
   for (int k = 0; k < 3; k++) d12[k] = p2[k] - p1[k];
-  for (int which = 0; which < 2; which++)
-    for (int i = 0; i < 3; i++) {
-      const double* mm = which ? m2 : m1;
-      const double ax[3] = {mm[i], mm[3 + i], mm[6 + i]};
-      double ra = 0, rb = 0;
-      for (int k = 0; k < 3; k++) {
-        const double c1[3] = {m1[k], m1[3 + k], m1[6 + k]}, c2[3] = {m2[k], m2[3 + k], m2[6 + k]};
-        ra += s1[k] * fabs(ldot3(ax, c1)); rb += s2[k] * fabs(ldot3(ax, c2));
-      }
-      const double sep = fabs(ldot3(ax, d12)) - (ra + rb);
-      if (sep > best) best = sep;
-    }
+  lmatT_vec(t, m1, d12);
+#pragma unroll
   for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) R[i][j] = m1[i] * m2[j] + m1[3 + i] * m2[3 + j] + m1[6 + i] * m2[6 + j];
+  // the 15 separating-axis values in closed form (see l_box_box)
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double sep = fabs(t[i]) - (s1[i] + s2[0] * fabs(R[i][0]) + s2[1] * fabs(R[i][1]) + s2[2] * fabs(R[i][2]));
+    if (sep > best) best = sep;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const double tj = t[0] * R[0][j] + t[1] * R[1][j] + t[2] * R[2][j];
+    const double sep = fabs(tj) - (s2[j] + s1[0] * fabs(R[0][j]) + s1[1] * fabs(R[1][j]) + s1[2] * fabs(R[2][j]));
+    if (sep > best) best = sep;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
     for (int j = 0; j < 3; j++) {
-      const double a1[3] = {m1[i], m1[3 + i], m1[6 + i]}, a2[3] = {m2[j], m2[3 + j], m2[6 + j]};
-      double ax[3];
-      lcross3(ax, a1, a2);
-      const double len = lnorm3(ax);
-      if (len < 1e-8) continue;
-      for (int k = 0; k < 3; k++) ax[k] /= len;
-      double ra = 0, rb = 0;
-      for (int k = 0; k < 3; k++) {
-        const double c1[3] = {m1[k], m1[3 + k], m1[6 + k]}, c2[3] = {m2[k], m2[3 + k], m2[6 + k]};
-        ra += s1[k] * fabs(ldot3(ax, c1)); rb += s2[k] * fabs(ldot3(ax, c2));
-      }
-      const double sep = fabs(ldot3(ax, d12)) - (ra + rb);
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const double len2 = R[i1][j] * R[i1][j] + R[i2][j] * R[i2][j];
+      if (len2 < 1e-16) continue;
+      const double td = t[i2] * R[i1][j] - t[i1] * R[i2][j];
+      const double rr = s1[i1] * fabs(R[i2][j]) + s1[i2] * fabs(R[i1][j]) + s2[j1] * fabs(R[i][j2]) + s2[j2] * fabs(R[i][j1]);
+      const double sep = (fabs(td) - rr) * rsqrt(len2);
       if (sep > best) best = sep;
     }
   if (best <= 0) return best;

@@ -54,6 +54,7 @@ struct LeapWork {
   double qfrc_bias[LEAP_NV], qfrc_smooth[LEAP_NV], qacc_smooth[LEAP_NV], qacc[LEAP_NV], qfrc_constraint[LEAP_NV];
   double Ma[LEAP_NV], grad[LEAP_NV], search[LEAP_NV], Mv[LEAP_NV], tmp[LEAP_NV];
   double cdist[LMAXCON], cpos[LMAXCON][3], cframe[LMAXCON][9], cmu[LMAXCON], cfri[LMAXCON], cHc[LMAXCON][9];
+  double cDm[LMAXCON];   // D0 / (mu^2 (1 + mu^2)) of the contact's middle (cone) zone: fixed during the solve, divided once per step
   double Jc[3 * LMAXCON][10];  // compressed contact rows: 6 cube dofs + 4 dofs of the touched finger
   double eD[LMAXEFC], eR[LMAXEFC], earef[LMAXEFC], ejar[LMAXEFC], ejv[LMAXEFC], eforce[LMAXEFC], efloss[LMAXEFC], esign[LMAXEFC];
   int estate[LMAXEFC], edof[LMAXEFC];
@@ -509,6 +510,8 @@ __device__ inline void leap_make_constraint(const LeapModel* __restrict__ m, Lea
   __syncwarp();
   for (int r = lane; r < nefc; r += 32) W->eD[r] = 1 / W->eR[r];
   __syncwarp();
+  for (int c = lane; c < ncon; c += 32) { const double mu = W->cmu[c]; W->cDm[c] = W->eD[nfl + 3 * c] / (mu * mu * (1 + mu * mu)); }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------ Newton solver (mj_solNewton, primal, elliptic cones)
@@ -525,7 +528,7 @@ __device__ __noinline__ double leap_cone_eval(const LeapWork* W, int c, int row0
     for (int k = 0; k < 3; k++) { force[k] = -W->eD[row0 + k] * x[k]; cost += 0.5 * W->eD[row0 + k] * x[k] * x[k]; }
     *state = LST_QUADRATIC;
   } else {
-    const double Dm = D0 / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+    const double Dm = W->cDm[c], NmT = N - mu * T;
     cost = 0.5 * Dm * NmT * NmT;
     force[0] = -Dm * NmT * mu;
     force[1] = T > B2_MINVAL ? -force[0] / T * U1 * f1 : 0;
@@ -796,7 +799,7 @@ __device__ inline void leap_newton_direction(const LeapModel* __restrict__ m, Le
 // so one evaluation of the 1-D cost derivatives is register math plus two warp reductions.
 struct LeapLS {
   double rjar, rjv, rD, rR, rfl;           // my friction/limit row
-  double cjar[3], cjv[3], cD[3], cmu, cfr;  // my contact
+  double cjar[3], cjv[3], cD[3], cmu, cfr, cDm;  // my contact
   bool has_row, row_is_friction, has_con;
 };
 
@@ -808,7 +811,7 @@ __device__ __forceinline__ void leap_ls_load(const LeapModel* __restrict__ m, co
     const int r0 = nfl + 3 * lane;
 #pragma unroll
     for (int k = 0; k < 3; k++) { L.cjar[k] = W->ejar[r0 + k]; L.cjv[k] = W->ejv[r0 + k]; L.cD[k] = W->eD[r0 + k]; }
-    L.cmu = W->cmu[lane]; L.cfr = W->cfri[lane];
+    L.cmu = W->cmu[lane]; L.cfr = W->cfri[lane]; L.cDm = W->cDm[lane];
   }
 }
 
@@ -835,7 +838,7 @@ __device__ __forceinline__ void leap_ls_eval(const LeapLS& L, double alpha, doub
       p2 += L.cD[0] * L.cjv[0] * L.cjv[0] + L.cD[1] * L.cjv[1] * L.cjv[1] + L.cD[2] * L.cjv[2] * L.cjv[2];
     } else {
       // s = 0.5 Dm (N - mu T)^2 in the scaled space U = S x; chain rule with dU/dalpha = S jv
-      const double Dm = L.cD[0] / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+      const double Dm = L.cDm, NmT = N - mu * T;
       const double Ti = T > B2_MINVAL ? 1 / T : 0;
       const double v0 = mu * L.cjv[0], v1 = f * L.cjv[1], v2 = f * L.cjv[2];
       const double dT = (U1 * v1 + U2 * v2) * Ti;
@@ -893,19 +896,22 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
   double scale = 0;
   int nfl = 0;
   if (!done) {
-    // warm start: keep qacc_warmstart unless qacc_smooth has lower cost
-    leap_set_point(m, W, W->warm, lane);
-    leap_constraint_update(m, W, W->warm, false, lane);
-    const double cw = W->cost;
-    __syncwarp();
+    // warm start: keep qacc_warmstart unless qacc_smooth has lower cost.  qacc_smooth is evaluated FIRST so that in the common case
+    // (the warm start wins) the residuals / forces / gradient / cone Hessians left behind are already those of the chosen point
     leap_set_point(m, W, W->qacc_smooth, lane);
     leap_constraint_update(m, W, W->qacc_smooth, false, lane);
     const double cs = W->cost;
     __syncwarp();
+    leap_set_point(m, W, W->warm, lane);
+    leap_constraint_update(m, W, W->warm, true, lane);
+    const double cw = W->cost;
+    __syncwarp();
     if (lane < LEAP_NV) W->qacc[lane] = cw > cs ? W->qacc_smooth[lane] : W->warm[lane];
     __syncwarp();
-    leap_set_point(m, W, W->qacc, lane);
-    leap_constraint_update(m, W, W->qacc, true, lane);
+    if (cw > cs) {
+      leap_set_point(m, W, W->qacc, lane);
+      leap_constraint_update(m, W, W->qacc, true, lane);
+    }
     scale = 1.0 / (m->meaninertia * LEAP_NV);
     nfl = W->nfl;
   }

@@ -69,3 +69,5 @@ extern "C" int sim_fr3_reward(const double* states, const double* sensors, int N
   wsim::launch((N + 127) / 128, 128, 0, [&] { fr3_reward_kernel(states, sensors, N, H, params, reward_N); });
   return 0;
 }
+
+extern "C" int sim_leap_work_bytes() { return (int)sizeof(LeapWork); }
