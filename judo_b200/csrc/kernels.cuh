@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
                                                       float* __restrict__ cost_NH, double* __restrict__ reward_N,
                                                       const PlanEpilogue ep, const SampleSpec smp) {
   constexpr int NU = Task::NU, NX = Task::NX, NS = Task::NS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  B2_DYNAMIC_SMEM(unsigned char, smem_raw);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int n0 = blockIdx.x * nthr, n = n0 + tid;
   const int nblk = min(nthr, N - n0);
@@ -214,7 +214,7 @@ __device__ inline double block_sum(double v, double* sh) {
 __global__ void __launch_bounds__(256) mppi_partial_kernel(const double* __restrict__ knots, const double* __restrict__ rewards, int N,
                                                            int KNU, double temperature, double* __restrict__ partial) {
   __shared__ double sh[32];
-  extern __shared__ double sw[];  // weights of this block's chunk
+  B2_DYNAMIC_SMEM(double, sw);  // weights of this block's chunk
   const int nb = gridDim.x, b = blockIdx.x;
   const int chunk = (N + nb - 1) / nb, lo = b * chunk, hi = min(N, lo + chunk), cnt = max(0, hi - lo);
   double m = INFINITY;

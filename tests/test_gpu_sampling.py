@@ -17,7 +17,7 @@ def _setup(task, N, K, H, order="zero"):
     t = cls.__new__(cls)
     t.config = cfg()
     eng = Engine(task, N)
-    dt = {"cartpole": 0.04, "cylinder_push": 0.02, "leap_cube": 0.01}[task]
+    dt = {"cartpole": 0.04, "cylinder_push": 0.02, "leap_cube": 0.01, "fr3_pick": 0.004}[task]
     basis = spline_basis(np.linspace(0, H * dt, K), dt * np.arange(H), order)
     return eng, t, basis
 
@@ -52,14 +52,29 @@ def test_distribution_rows_clip_and_determinism():
 
 
 @pytest.mark.parametrize("task,nu,optimizer,params", [("cartpole", 1, "mppi", [0.05]), ("cylinder_push", 2, "cem", [3, 0.1, 1.0]),
-                                                      ("cartpole", 1, "ps", []), ("leap_cube", 16, "mppi", [0.0025])])
+                                                      ("cartpole", 1, "ps", []), ("leap_cube", 16, "mppi", [0.0025]),
+                                                      ("fr3_pick", 8, "cem", [3, 0.01, 0.3])])
 def test_sampled_plan_step_is_consistent_with_host_path(task, nu, optimizer, params):
     """The generated candidates, pushed through the seed-parity path (host knots) and through the oracle, give the same
     rewards / nominal / elite list; sharding the launch (index_offset) reproduces the same candidates."""
     N, K, H = 96, 4, 12
-    eng, t, basis = _setup(task, N, K, H, "cubic" if task == "leap_cube" else "zero")
+    eng, t, basis = _setup(task, N, K, H, {"leap_cube": "cubic", "fr3_pick": "linear"}.get(task, "zero"))
     rng = np.random.default_rng(1)
-    if task == "leap_cube":
+    sensors_needed = False
+    if task == "fr3_pick":
+        from judo_b200.tasks.fr3_pick import Phase
+        from tests.fr3_cases import Q_GRASP, oracle_model, scenario
+
+        om = oracle_model()
+        x0, _ = scenario("grasp", 1, 1)
+        nominal = np.tile(np.concatenate([Q_GRASP, [0.0]]), (K, 1))   # closing the gripper on the cube
+        lo = np.array([a["ctrlrange"][0] for a in om.table["actuators"]])
+        hi = np.array([a["ctrlrange"][1] for a in om.table["actuators"]])
+        t.phase, t.arm_pos_slice = Phase.MOVE, slice(7, 16)
+        cp = t.cost_params()
+        sigma = 0.05 * np.linspace(0.25, 1, K)[:, None] * np.ones((K, nu))
+        sensors_needed = True
+    elif task == "leap_cube":
         from judo_b200.tasks.leap_cube import QPOS_HOME, reduced_collision_model
         from oracle.mjc import load_table
 
@@ -93,9 +108,10 @@ def test_sampled_plan_step_is_consistent_with_host_path(task, nu, optimizer, par
         np.testing.assert_array_equal(r["sigma"], h["sigma"])
     # (b) against the oracle
     ctrl = np.einsum("hk,nkj->nhj", basis, kn)
-    states, _ = om.rollout(x0, ctrl)
+    states, sens = om.rollout(x0, ctrl)
+    assert sensors_needed == (task == "fr3_pick")
     ref = {"cartpole": lambda: op.cartpole_reward(states, ctrl), "cylinder_push": lambda: op.cylinder_push_reward(states, ctrl),
-           "leap_cube": lambda: op.leap_cube_reward(states)}[task]()
+           "leap_cube": lambda: op.leap_cube_reward(states), "fr3_pick": lambda: op.fr3_pick_reward(states, sens, 1)}[task]()
     np.testing.assert_allclose(r["rewards"], ref, rtol=1e-7, atol=1e-7)
     # (c) shard invariance: two launches of 48 with index offsets 0 / 48 generate the same 96 candidates
     eng.update(48)

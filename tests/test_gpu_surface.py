@@ -45,7 +45,7 @@ def test_max_opt_iters_chains_iterations(temp_np_seed):
 
 
 @pytest.mark.parametrize("opt", ["cem", "mppi", "ps"])
-@pytest.mark.parametrize("task", ["cylinder_push", "cartpole", "leap_cube"])
+@pytest.mark.parametrize("task", ["cylinder_push", "cartpole", "leap_cube", "fr3_pick"])
 def test_update_action_shapes(task, opt):
     """Reference test_update_action (:80-112): shapes after one plan step, every optimizer."""
     from judo_b200.controller import make_controller

@@ -170,3 +170,7 @@ inline void sincospi(double x, double* s, double* c) { sincos(3.1415926535897932
 using std::isfinite;
 
 typedef void* cudaStream_t;
+struct float4 { float x, y, z, w; };
+struct double2 { double x, y; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
