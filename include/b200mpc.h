@@ -148,6 +148,11 @@ int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all_handles_wo
 /* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
 long long b200mpc_launch_count(const b200mpc_handle* h);
 
+/* Number of rollout steps (process-wide, since load) in which an articulated-body kernel found more contacts than its per-step
+ * buffer holds (leap_cube 24, fr3_pick 48; MuJoCo itself grows its arena) and dropped the surplus.  0 means every rollout so far used
+ * the full contact set; callers that need the guarantee check it after planning.  -1 on CUDA errors. */
+long long b200mpc_contact_overflows(b200mpc_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,7 @@ SIGNATURES = {
     "b200mpc_exchange_create": (_i, [_vp, _i, _i, _vp]),
     "b200mpc_exchange_open": (_i, [_vp, _vp]),
     "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),
+    "b200mpc_contact_overflows": (ctypes.c_longlong, [_vp]),
 }
 
 _lib = None

@@ -165,6 +165,13 @@ extern "C" int b200mpc_get_dims(const b200mpc_handle* h, b200mpc_dims* out) { if
 extern "C" int b200mpc_update(b200mpc_handle* h, int n) { if (!h) return 1; if (n <= 0) return fail(h, "num_rollouts must be positive"); h->N = n; return 0; }
 extern "C" int b200mpc_num_rollouts(const b200mpc_handle* h) { return h ? h->N : -1; }
 extern "C" long long b200mpc_launch_count(const b200mpc_handle* h) { return h ? h->launches : 0; }
+extern "C" long long b200mpc_contact_overflows(b200mpc_handle* h) {
+  if (!h) return -1;
+  unsigned long long v = 0;
+  if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess ||
+      cudaMemcpyFromSymbol(&v, g_contact_overflow, sizeof(v)) != cudaSuccess) { h->err = "b200mpc_contact_overflows: CUDA error"; return -1; }
+  return (long long)v;
+}
 
 // ------------------------------------------------------------------ launch helpers
 static int pick_threads(int N) {

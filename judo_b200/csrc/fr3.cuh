@@ -508,7 +508,7 @@ __device__ inline void fr3_collision(const Fr3Model* __restrict__ m, Fr3Work* W,
       W->ccls[slot] = cls; W->cbody[slot] = body;
     }
   }
-  if (lane == 0) W->ncon = total < FMAXCON ? total : FMAXCON;
+  if (lane == 0) { W->ncon = total < FMAXCON ? total : FMAXCON; if (total > FMAXCON) atomicAdd(&g_contact_overflow, 1ull); }
   __syncwarp();
   // sensors: 5 body-pair distances (min over the pads, clipped to +-cutoff), ee z axis, object position, grasp site
   if (lane < 5) {

@@ -5,6 +5,10 @@
 
 namespace b2 {
 
+// Rollout-steps in which a warp-per-rollout kernel found more contacts than its per-step buffer holds (leap: 24, fr3: 48) and had to
+// drop the surplus.  Queried through b200mpc_contact_overflows(): truncation is never silent.
+__device__ unsigned long long g_contact_overflow;
+
 // ------------------------------------------------------------------ small vector helpers (same op order as the oracle)
 __device__ __forceinline__ double ldot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 __device__ __forceinline__ void lcross3(double* r, const double* a, const double* b) {

@@ -398,7 +398,7 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
     ncon += total;
   }
   __syncwarp();
-  if (lane == 0) W->ncon = ncon < LMAXCON ? ncon : LMAXCON;
+  if (lane == 0) { W->ncon = ncon < LMAXCON ? ncon : LMAXCON; if (ncon > LMAXCON) atomicAdd(&g_contact_overflow, 1ull); }
   __syncwarp();
   LPROF_ADD(12, tc0);
   if (prof && lane == 0) atomicAdd(&g_leap_prof[14], (unsigned long long)ncon);
@@ -1066,28 +1066,23 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
   }
   __syncwarp();
   if constexpr (COST) {
-    // stage this rollout's knots (K*16 doubles) and the basis behind the work area with TMA bulk copies
+    // stage this rollout's knots (K*16 doubles) behind the work area with one TMA bulk copy; the (H,K) basis is shared by every
+    // rollout and is read from global memory (K cached loads per lane and step) to keep the per-warp shared-memory footprint small
     uint64_t* bar = reinterpret_cast<uint64_t*>(lsm + ((sizeof(LeapWork) + 15) & ~(size_t)15));
     double* sK = reinterpret_cast<double*>(bar + 2);
-    double* sB = sK + K * LEAP_NU;
     if (active) {
-      const unsigned bytesK = (unsigned)(K * LEAP_NU * sizeof(double)), bytesB = (unsigned)(H * K * sizeof(double));
+      const unsigned bytesK = (unsigned)(K * LEAP_NU * sizeof(double));
       const double* gK = in + (size_t)n * K * LEAP_NU;
-      const bool want_knots = !smp.enabled;
-      const bool tma_ok = (bytesB % 16 == 0) && ((reinterpret_cast<uintptr_t>(basis) & 15) == 0) && (!want_knots || (reinterpret_cast<uintptr_t>(gK) & 15) == 0);
-      if (tma_ok) {
-        if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_expect_tx(bar, (want_knots ? bytesK : 0u) + bytesB);
-          if (want_knots) tma_bulk_g2s(sK, gK, bytesK, bar);
-          tma_bulk_g2s(sB, basis, bytesB, bar);
+      if (!smp.enabled) {
+        if ((reinterpret_cast<uintptr_t>(gK) & 15) == 0) {
+          if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+          __syncwarp();
+          if (lane == 0) { mbar_expect_tx(bar, bytesK); tma_bulk_g2s(sK, gK, bytesK, bar); }
+          mbar_wait(bar, 0);
+        } else {
+          for (int i = lane; i < K * LEAP_NU; i += 32) sK[i] = gK[i];
+          __syncwarp();
         }
-        mbar_wait(bar, 0);
-      } else {
-        if (want_knots) for (int i = lane; i < K * LEAP_NU; i += 32) sK[i] = gK[i];
-        for (int i = lane; i < H * K; i += 32) sB[i] = basis[i];
-        __syncwarp();
       }
       if (smp.enabled) {  // on-device sampling: lane p draws the normal pair for elements 2p, 2p+1 (Philox keyed by the global index)
         const long long gn = (long long)n + index_offset;
@@ -1108,7 +1103,7 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
       if (sync_mode >= 1) __syncthreads();
       if (active && lane < LEAP_NU) {
         double u = 0;
-        for (int k = 0; k < K; k++) u += sB[t * K + k] * sK[k * LEAP_NU + lane];
+        for (int k = 0; k < K; k++) u += __ldg(basis + t * K + k) * sK[k * LEAP_NU + lane];
         W->ctrl[lane] = u;
       }
       __syncwarp();
@@ -1176,11 +1171,12 @@ inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, in
   const char* sm_env = getenv("B200MPC_LEAP_SYNC");
   const int prof = (getenv("B200MPC_LEAP_PROF") ? 1 : 0) | ((sm_env ? atoi(sm_env) : 3) << 8);
   (void)ep;  // the leap path runs the optimizer update as separate reduction kernels (b200mpc.cu)
-  size_t wstride = ((sizeof(LeapWork) + 15) & ~(size_t)15) + 16 + (cost_mode ? ((size_t)K * LEAP_NU + (size_t)H * K) * sizeof(double) : 0);
+  size_t wstride = ((sizeof(LeapWork) + 15) & ~(size_t)15) + 16 + (cost_mode ? (size_t)K * LEAP_NU * sizeof(double) : 0);
   wstride = (wstride + 15) & ~(size_t)15;
   int wpb = (N + 147) / 148;  // spread the rollouts over the 148 SMs first, then stack up to 7 warps per SM
   if (wpb < 1) wpb = 1;
   if (wpb > 7) wpb = 7;
+  if (const char* wenv = getenv("B200MPC_LEAP_WPB")) wpb = atoi(wenv) > 0 ? atoi(wenv) : wpb;  // experiment knob: warps per block
   while (wpb > 1 && wpb * wstride > 226 * 1024) wpb--;
   const size_t smem = wpb * wstride;
   if (smem > 227 * 1024) { *err = "horizon/knots too large for the shared-memory tile"; return 1; }

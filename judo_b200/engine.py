@@ -65,6 +65,14 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.b200mpc_launch_count(self._h))
 
+    @property
+    def contact_overflows(self) -> int:
+        """Rollout steps (process-wide) whose contact count exceeded the kernel's per-step buffer (truncation is never silent)."""
+        n = int(self._lib.b200mpc_contact_overflows(self._h))
+        if n < 0:
+            raise RuntimeError(self._lib.b200mpc_last_error(self._h).decode())
+        return n
+
     def update(self, num_rollouts: int) -> None:
         self._check(self._lib.b200mpc_update(self._h, int(num_rollouts)))
 

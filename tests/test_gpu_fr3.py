@@ -36,6 +36,7 @@ def test_fr3_rollout_matches_oracle(engine, name, N, H):
     xb[:, 7:14] += 0.01 * np.random.default_rng(1).normal(size=(N, 7))
     sb, _ = engine.rollout(xb, u, want_sensors=False)
     np.testing.assert_allclose(sb[..., :16], om.rollout(xb, u)[0][..., :16], rtol=0, atol=1e-6)
+    assert engine.contact_overflows == 0  # no contact was dropped (buffer: 48 per step)
 
 
 @pytest.mark.parametrize("phase", [0, 1, 2, 3])

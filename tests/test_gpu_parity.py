@@ -368,6 +368,7 @@ def test_leap_rollout_matches_oracle(engines, N, H, scale):
     assert err[: min(H, 5)].max() < 1e-9          # free fall + first steps: bit-near
     np.testing.assert_allclose(states[..., :23], s_ref[..., :23], rtol=0, atol=1e-5)   # positions over the whole horizon
     np.testing.assert_allclose(sensors, e_ref, rtol=0, atol=1e-5)
+    assert eng.contact_overflows == 0  # no contact was dropped (buffer: 24 per step)
 
 
 def test_leap_plan_costs_and_reward_match_oracle(engines):
