@@ -95,6 +95,14 @@ __device__ __forceinline__ double fwsum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(B2_FULLMASK, v, o);
   return v;
 }
+// two independent sums reduced together: the shuffle rounds interleave, so the pair costs the latency of one reduction
+__device__ __forceinline__ void fwsum2(double& a, double& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ta = __shfl_xor_sync(B2_FULLMASK, a, o), tb = __shfl_xor_sync(B2_FULLMASK, b, o);
+    a += ta; b += tb;
+  }
+}
 
 // ------------------------------------------------------------------ kinematics (mj_kinematics + mj_comPos)
 // The arm is a serial chain, but composing rigid transforms is associative: lane c < 9 builds the parent-relative transform of chain
@@ -802,8 +810,9 @@ __device__ __forceinline__ void fr3_ls_eval(const Fr3LS& L, double alpha, double
           if (x < 0) { p1 += D * x * v; p2 += D * v * v; }
         }
     }
-  *d1 = g1 + alpha * g2 + fwsum(p1);
-  *d2 = g2 + fwsum(p2);
+  fwsum2(p1, p2);
+  *d1 = g1 + alpha * g2 + p1;
+  *d2 = g2 + p2;
 }
 
 // exact line search (safeguarded 1-D Newton on the convex piecewise-quadratic cost); leaves jv of the rows in W->sforce-independent
@@ -814,10 +823,11 @@ __device__ inline double fr3_line_search(const Fr3Model* __restrict__ m, Fr3Work
     g1 = W->search[lane] * (W->Ma[lane] - W->qfrc_smooth[lane]); g2 = W->search[lane] * W->Mv[lane];
     sn = W->search[lane] * W->search[lane]; gs = W->grad[lane] * W->search[lane];
   }
-  g1 = fwsum(g1); g2 = fwsum(g2);
-  const double snorm = sqrt(fwsum(sn));
+  fwsum2(g1, g2);
+  fwsum2(sn, gs);
+  const double snorm = sqrt(sn);
   // derivatives at alpha = 0 without touching the rows: d1(0) = grad . search and, for the Newton direction, d2(0) = -d1(0)
-  double d1 = fwsum(gs), d2 = -d1, lo = 0, hi = -1, alpha;
+  double d1 = gs, d2 = -d1, lo = 0, hi = -1, alpha;
   if (snorm < B2_MINVAL) return 0;
   const double gtol = m->tolerance * m->ls_tolerance * snorm * m->meaninertia * FR_NV;
   if (d1 >= 0 || d2 <= 0) return 0;

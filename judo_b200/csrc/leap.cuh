@@ -41,6 +41,7 @@ struct LeapModel {
   double ngeom, geom_type[LMAXG], geom_body[LMAXG], geom_pos[LMAXG][3], geom_mat[LMAXG][9], geom_size[LMAXG][3], geom_rbound[LMAXG], geom_mu[LMAXG];
   double cube_size[3], cube_rbound, con_solref[2], con_solimp[5];
   double site_body[5], site_pos[5][3];
+  double fr_row[LEAP_NV];  // friction-loss row of each dof (-1: none)
 };
 
 // per-warp shared-memory work area
@@ -60,6 +61,7 @@ struct LeapWork {
   int estate[LMAXEFC], edof[LMAXEFC];
   int cbody[LMAXCON], cfinger[LMAXCON], cdepth[LMAXCON], cswap[LMAXCON];
   int cand[LMAXG];
+  int limrow[16][2];   // efc row of joint j's lower / upper limit, -1 when inactive
   int ncon, nefc, nfl, ncand, solver_iter;
   double cost, gauss;
 };
@@ -257,7 +259,7 @@ __device__ __forceinline__ double leap_mulM_row(const LeapModel* __restrict__ m,
 // Small dense Cholesky per block, same recurrences as the oracle's dense factorisation restricted to the block.
 template <int N>
 __device__ __forceinline__ void small_chol_solve(double (&A)[N][N], double* x) {
-  double L[N][N];
+  double L[N][N];  // the diagonal holds RECIPROCAL pivots (one rsqrt per pivot; every later division becomes a multiplication)
 #pragma unroll
   for (int i = 0; i < N; i++)
 #pragma unroll
@@ -265,18 +267,18 @@ __device__ __forceinline__ void small_chol_solve(double (&A)[N][N], double* x) {
       double s = A[i][j];
 #pragma unroll
       for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
-      if (i == j) { if (s < B2_MINVAL) s = B2_MINVAL; L[i][i] = sqrt(s); } else L[i][j] = s / L[j][j];
+      if (i == j) { if (s < B2_MINVAL) s = B2_MINVAL; L[i][i] = rsqrt(s); } else L[i][j] = s * L[j][j];
     }
 #pragma unroll
   for (int i = 0; i < N; i++) { double s = x[i];
 #pragma unroll
     for (int k = 0; k < i; k++) s -= L[i][k] * x[k];
-    x[i] = s / L[i][i]; }
+    x[i] = s * L[i][i]; }
 #pragma unroll
   for (int i = N - 1; i >= 0; i--) { double s = x[i];
 #pragma unroll
     for (int k = i + 1; k < N; k++) s -= L[k][i] * x[k];
-    x[i] = s / L[i][i]; }
+    x[i] = s * L[i][i]; }
 }
 __device__ inline void leap_block_solve(const LeapModel* __restrict__ m, LeapWork* W, const double* add, double* x, int lane) {
   if (lane == 0) {
@@ -433,6 +435,7 @@ __device__ inline void leap_make_constraint(const LeapModel* __restrict__ m, Lea
   const int rbase = nfr + __popc(mlo & below) + __popc(mhi & below);
   if (lo_act) { W->edof[rbase] = 6 + lane; W->esign[rbase] = 1; W->efloss[rbase] = 0; W->ejar[rbase] = dlo; }
   if (hi_act) { const int r = rbase + (lo_act ? 1 : 0); W->edof[r] = 6 + lane; W->esign[r] = -1; W->efloss[r] = 0; W->ejar[r] = dhi; }
+  if (lane < 16) { W->limrow[lane][0] = lo_act ? rbase : -1; W->limrow[lane][1] = hi_act ? rbase + (lo_act ? 1 : 0) : -1; }
   const int nfl = nfr + __popc(mlo) + __popc(mhi);
   const int ncon = W->ncon;
   __syncwarp();
@@ -573,6 +576,14 @@ __device__ __forceinline__ double lwsum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
+// two independent sums reduced together: the shuffle rounds interleave, so the pair costs the latency of one reduction
+__device__ __forceinline__ void lwsum2(double& a, double& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ta = __shfl_xor_sync(FULL, a, o), tb = __shfl_xor_sync(FULL, b, o);
+    a += ta; b += tb;
+  }
+}
 
 // jar = J qacc - aref for every row; Ma = M qacc
 __device__ __noinline__ void leap_set_point(const LeapModel* __restrict__ m, LeapWork* W, const double* qacc, int lane) {
@@ -603,7 +614,13 @@ __device__ __noinline__ void leap_constraint_update(const LeapModel* __restrict_
   if (lane < LEAP_NV) {
     const int i = lane;
     double f = 0;
-    for (int r = 0; r < nfl; r++) if (W->edof[r] == i) f += W->esign[r] * W->eforce[r];
+    if (i >= 6) {  // friction-loss row of dof i is row fr_row[i] (O(1) lookups instead of a search over the rows)
+      const int fr = (int)m->fr_row[i];
+      if (fr >= 0) f += W->eforce[fr];
+      const int rl = W->limrow[i - 6][0], rh = W->limrow[i - 6][1];
+      if (rl >= 0) f += W->eforce[rl];
+      if (rh >= 0) f -= W->eforce[rh];
+    }
     const int fi = i >= 6 ? (i - 6) >> 2 : -1, ki = i < 6 ? i : 6 + ((i - 6) & 3);
     for (int c = 0; c < ncon; c++) {
       if (i >= 6 && W->cfinger[c] != fi) continue;
@@ -688,8 +705,8 @@ __device__ inline void leap_newton_direction(const LeapModel* __restrict__ m, Le
         for (int b = 0; b < 3; b++) h += Wm[3 * a + b] * J[a][6 + r] * J[b][cc];
       W->Hcf[fc][r][cc] += h;
     }
-    __syncwarp();
   }
+  __syncwarp();  // (every Hessian entry is accumulated by ONE lane across all contacts: no barrier is needed inside the loop)
   // ---- factorise the finger blocks (lane f), keep 1/L_kk on the diagonal slot for the substitutions
   if (lane < 4) {
     const int f = lane;
@@ -831,7 +848,9 @@ __device__ __forceinline__ void leap_ls_eval(const LeapLS& L, double alpha, doub
     const double mu = L.cmu, f = L.cfr;
     const double x0 = L.cjar[0] + alpha * L.cjv[0], x1 = L.cjar[1] + alpha * L.cjv[1], x2 = L.cjar[2] + alpha * L.cjv[2];
     const double U1 = x1 * f, U2 = x2 * f;
-    const double N = x0 * mu, T = sqrt(U1 * U1 + U2 * U2);
+    const double T2 = U1 * U1 + U2 * U2;
+    const double Ti = T2 > B2_MINVAL * B2_MINVAL ? rsqrt(T2) : 0;  // one rsqrt instead of a square root and a division
+    const double N = x0 * mu, T = T2 * Ti;
     if (N >= mu * T) { /* separating: no force */ }
     else if (mu * N + T <= 0) {
       p1 += L.cD[0] * x0 * L.cjv[0] + L.cD[1] * x1 * L.cjv[1] + L.cD[2] * x2 * L.cjv[2];
@@ -839,7 +858,6 @@ __device__ __forceinline__ void leap_ls_eval(const LeapLS& L, double alpha, doub
     } else {
       // s = 0.5 Dm (N - mu T)^2 in the scaled space U = S x; chain rule with dU/dalpha = S jv
       const double Dm = L.cDm, NmT = N - mu * T;
-      const double Ti = T > B2_MINVAL ? 1 / T : 0;
       const double v0 = mu * L.cjv[0], v1 = f * L.cjv[1], v2 = f * L.cjv[2];
       const double dT = (U1 * v1 + U2 * v2) * Ti;
       const double dNmT = v0 - mu * dT;
@@ -848,22 +866,25 @@ __device__ __forceinline__ void leap_ls_eval(const LeapLS& L, double alpha, doub
       p2 += Dm * (dNmT * dNmT - NmT * mu * d2T);
     }
   }
-  *d1 = g1 + alpha * g2 + lwsum(p1);
-  *d2 = g2 + lwsum(p2);
+  lwsum2(p1, p2);
+  *d1 = g1 + alpha * g2 + p1;
+  *d2 = g2 + p2;
 }
 
 __device__ inline double leap_line_search(const LeapModel* __restrict__ m, const LeapWork* W, int lane) {
   double g1 = 0, g2 = 0, sn = 0;
   if (lane < LEAP_NV) { g1 = W->search[lane] * (W->Ma[lane] - W->qfrc_smooth[lane]); g2 = W->search[lane] * W->Mv[lane]; sn = W->search[lane] * W->search[lane]; }
-  g1 = lwsum(g1); g2 = lwsum(g2);
-  const double snorm = sqrt(lwsum(sn));
+  lwsum2(g1, g2);
+  double gs = lane < LEAP_NV ? W->grad[lane] * W->search[lane] : 0.0;
+  lwsum2(sn, gs);
+  const double snorm = sqrt(sn);
   if (snorm < B2_MINVAL) return 0;
   const double gtol = m->tolerance * m->ls_tolerance * snorm * m->meaninertia * LEAP_NV;
   LeapLS L;
   leap_ls_load(m, W, lane, L);
   // derivatives at alpha = 0 without evaluating the rows: d1(0) = grad . search, and for the Newton direction H search = -grad
   // gives d2(0) = search^T H search = -d1(0), i.e. the first trial step is the full Newton step
-  double d1 = lwsum(lane < LEAP_NV ? W->grad[lane] * W->search[lane] : 0.0), d2 = -d1, lo = 0, hi = -1, alpha;
+  double d1 = gs, d2 = -d1, lo = 0, hi = -1, alpha;
   if (d1 >= 0 || d2 <= 0) return 0;
   alpha = 1.0;
   double prev_step = 1e300;

@@ -231,6 +231,8 @@ def leap_consts(table: dict) -> np.ndarray:
     order = [s["obj"] for s in table["sensors"] if s["type"] == "framepos"]
     assert [s["type"] for s in table["sensors"]] == ["jointpos"] * 16 + ["framepos"] * 5
     v += [float(remap[sites[i]["body"]]) for i in order] + [x for i in order for x in sites[i]["pos"]]
+    assert all(d >= 6 for d in fr)  # the cube's free joint has no friction loss (the kernel's per-dof lookup relies on it)
+    v += [float(fr.index(d)) if d in fr else -1.0 for d in range(22)]
     return np.array(v, dtype=np.float64)
 
 
