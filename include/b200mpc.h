@@ -148,6 +148,16 @@ int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all_handles_wo
 /* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
 long long b200mpc_launch_count(const b200mpc_handle* h);
 
+/* ---- trace capture (warp-per-rollout tasks: leap_cube, fr3_pick) ----------------------------------------------------------------
+ * Replaces the `self.sensors[elite]` lookup of Controller.update_traces (judo/controller/controller.py:323-363) on the fused path,
+ * where no (N, H, nsensordata) array exists: with capture enabled the fused kernel keeps the task's "trace" framepos sensors
+ * (b200mpc_trace_width doubles per step: leap_cube 5 sites x 3, fr3_pick trace_object + trace_grasp_site) of EVERY rollout of the last
+ * plan step in HBM, and b200mpc_elite_traces copies the rows of the given rollouts out: (n, H, trace_width).  Without it the elite
+ * rollouts would have to be simulated a second time, which for these serial ms-scale kernels doubles the plan latency. */
+int b200mpc_set_trace_capture(b200mpc_handle* h, int enable);
+int b200mpc_trace_width(const b200mpc_handle* h);
+int b200mpc_elite_traces(b200mpc_handle* h, const int* rollout_idx, int n, int H, double* traces_out);
+
 /* Number of rollout steps (process-wide, since load) in which an articulated-body kernel found more contacts than its per-step
  * buffer holds (leap_cube 24, fr3_pick 48; MuJoCo itself grows its arena) and dropped the surplus.  0 means every rollout so far used
  * the full contact set; callers that need the guarantee check it after planning.  -1 on CUDA errors. */

@@ -52,6 +52,9 @@ SIGNATURES = {
     "b200mpc_exchange_open": (_i, [_vp, _vp]),
     "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),
     "b200mpc_contact_overflows": (ctypes.c_longlong, [_vp]),
+    "b200mpc_set_trace_capture": (_i, [_vp, _i]),
+    "b200mpc_trace_width": (_i, [_vp]),
+    "b200mpc_elite_traces": (_i, [_vp, _vp, _i, _i, _vp]),
 }
 
 _lib = None

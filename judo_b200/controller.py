@@ -92,6 +92,10 @@ class Controller:
         self.sensor_rollout_size = self.num_timesteps - 1
         self.all_traces_rollout_size = self.sensor_rollout_size * self.num_trace_sensors
         self.fused = True  # set False to force the contract-A path (rollout + Task.reward + optimizer update)
+        # warp-per-rollout tasks: the fused kernel keeps every rollout's trace sensors so the elites need no second simulation
+        self._trace_capture = self.num_trace_sensors > 0 and self.engine.trace_width == 3 * self.num_trace_sensors
+        if self._trace_capture:
+            self.engine.set_trace_capture(True)
         # "host": np.random.randn exactly as the reference (seed parity).  "device": Philox inside the rollout kernel (perf mode:
         # same distribution, nothing but the nominal crosses PCIe; candidate_knots then holds only the elite candidates).
         self.sampling: Literal["host", "device"] = "host"
@@ -278,6 +282,16 @@ class Controller:
         if getattr(self, "_rollout_cache_valid", False) or getattr(self, "_elite", None) is None:
             elite = np.argsort(self.rewards)[-ne:][::-1]
             elite_sensors = self.sensors[elite]
+        elif self._trace_capture and self.sampling == "host":
+            elite = np.asarray(self._elite[:ne])
+            tr = self.engine.elite_traces(elite, self.num_timesteps)  # (ne, H, 3 * nts): the trace sensors, in sensor order
+            self.elite_indices = elite
+            rep = np.repeat(tr, 2, axis=1)[:, 1:-1, :]
+            out = np.zeros((nts * ne, size, 2, 3))
+            for s in range(nts):
+                out[s::nts] = np.reshape(rep[:, :, 3 * s:3 * s + 3], (ne, size, 2, 3))
+            self.traces = np.reshape(out, (ne * nts * size, 2, 3))
+            return
         else:
             elite = np.asarray(self._elite[:ne])
             ctrl = np.einsum("hk,nkj->nhj", self._basis, self.candidate_knots[elite])

@@ -39,6 +39,8 @@ struct b200mpc_handle {
   void* d_big = nullptr; size_t d_big_bytes = 0;    // states / sensors / cost matrix
   void* d_part = nullptr; size_t d_part_bytes = 0;  // reduction partials
   void* d_work = nullptr; size_t d_work_bytes = 0;  // per-rollout scratch (leap)
+  // trace capture (warp-per-rollout tasks): the fused kernel keeps the trace sensors of every rollout of the LAST plan step
+  bool trace_capture = false; void* d_trace = nullptr; size_t d_trace_bytes = 0; int trace_N = 0, trace_H = 0;
   void* h_in = nullptr; size_t h_in_bytes = 0;      // pinned staging
   void* h_out = nullptr; size_t h_out_bytes = 0;
   int zero_copy = 2;           // plan_step: bit0 = kernel READS the pinned staging buffer, bit1 = kernel WRITES results to pinned memory
@@ -122,7 +124,7 @@ extern "C" void b200mpc_destroy(b200mpc_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int g = 0; g < h->xchg_world; g++) if (h->xchg_peer[g] && g != h->xchg_rank) cudaIpcCloseMemHandle(h->xchg_peer[g]);
   cudaFree(h->xchg);
-  cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work);
+  cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work); cudaFree(h->d_trace);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
 #ifdef B200MPC_WITH_LEAP
   if (h->leap) { if (getenv("B200MPC_LEAP_PROF")) leap_prof_dump(); leap_destroy(h->leap); }
@@ -165,6 +167,31 @@ extern "C" int b200mpc_get_dims(const b200mpc_handle* h, b200mpc_dims* out) { if
 extern "C" int b200mpc_update(b200mpc_handle* h, int n) { if (!h) return 1; if (n <= 0) return fail(h, "num_rollouts must be positive"); h->N = n; return 0; }
 extern "C" int b200mpc_num_rollouts(const b200mpc_handle* h) { return h ? h->N : -1; }
 extern "C" long long b200mpc_launch_count(const b200mpc_handle* h) { return h ? h->launches : 0; }
+
+static int trace_width(const b200mpc_handle* h) { return h->task == B200MPC_TASK_LEAP_CUBE ? LEAP_NTRACE : h->task == B200MPC_TASK_FR3_PICK ? FR_NTRACE : 0; }
+extern "C" int b200mpc_set_trace_capture(b200mpc_handle* h, int enable) {
+  if (!h) return 1;
+  if (enable && trace_width(h) == 0) return fail(h, "trace capture exists for the warp-per-rollout tasks only (the others recompute their elite traces in microseconds)");
+  h->trace_capture = enable != 0;
+  if (!enable) h->trace_N = h->trace_H = 0;
+  return 0;
+}
+extern "C" int b200mpc_trace_width(const b200mpc_handle* h) { return h ? trace_width(h) : 0; }
+extern "C" int b200mpc_elite_traces(b200mpc_handle* h, const int* idx, int n, int H, double* out) {
+  if (!h) return 1;
+  if (!idx || !out || n <= 0) return fail(h, "NULL / empty argument");
+  const int nt = trace_width(h);
+  if (!h->trace_capture || h->trace_N == 0) return fail(h, "no captured traces: enable b200mpc_set_trace_capture and run a fused plan step first");
+  if (H != h->trace_H) return fail(h, "H does not match the captured plan step");
+  CK(cudaSetDevice(h->device));
+  const size_t row = (size_t)H * nt * 8;
+  for (int i = 0; i < n; i++) {
+    if (idx[i] < 0 || idx[i] >= h->trace_N) return fail(h, "rollout index out of range");
+    CK(cudaMemcpyAsync((char*)out + (size_t)i * row, (const char*)h->d_trace + (size_t)idx[i] * row, row, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
 extern "C" long long b200mpc_contact_overflows(b200mpc_handle* h) {
   if (!h) return -1;
   unsigned long long v = 0;
@@ -249,6 +276,18 @@ extern "C" int b200mpc_rollout_dev(b200mpc_handle* h, const double* d_x0, int ba
   return fail(h, "task not supported");
 }
 
+// (N, H, nt) device buffer for the trace capture of this launch, or NULL when capture is off
+static int trace_buffer(b200mpc_handle* h, int N, int H, int nt, cudaStream_t st, double** out) {
+  *out = nullptr;
+  h->trace_N = h->trace_H = 0;
+  if (!h->trace_capture) return 0;
+  const size_t need = (size_t)N * H * nt * 8;
+  if (need > h->d_trace_bytes) { CK(cudaStreamSynchronize(st)); if (grow(h, &h->d_trace, &h->d_trace_bytes, need, false)) return 1; }
+  *out = (double*)h->d_trace;
+  h->trace_N = N; h->trace_H = H;
+  return 0;
+}
+
 static int plan_costs_ep(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis, int H,
                          const double* d_params, float* d_cost, double* d_reward, const PlanEpilogue& ep, cudaStream_t st,
                          const SampleSpec& smp = SampleSpec{}) {
@@ -259,13 +298,17 @@ static int plan_costs_ep(b200mpc_handle* h, const double* d_x0, const double* d_
     case B200MPC_TASK_CYLINDER_PUSH: return launch_costs<CylinderPushTask>(h, h->cyl, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, smp, st);
 #ifdef B200MPC_WITH_LEAP
     case B200MPC_TASK_LEAP_CUBE: {
-      if (leap_launch(h->leap, /*cost_mode=*/1, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep, smp, st, &h->err)) return 1;
+      double* d_trace = nullptr;
+      if (trace_buffer(h, N, H, LEAP_NTRACE, st, &d_trace)) return 1;
+      if (leap_launch(h->leap, /*cost_mode=*/1, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep, smp, st, &h->err, d_trace)) return 1;
       h->launches++;
       return 0;
     }
 #endif
     case B200MPC_TASK_FR3_PICK: {
-      if (fr3_launch(h->fr3, /*cost_mode=*/1, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep, smp, st, &h->err)) return 1;
+      double* d_trace = nullptr;
+      if (trace_buffer(h, N, H, FR_NTRACE, st, &d_trace)) return 1;
+      if (fr3_launch(h->fr3, /*cost_mode=*/1, d_x0, 0, d_knots, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, ep, smp, st, &h->err, d_trace)) return 1;
       h->launches++;
       return 0;
     }

@@ -22,6 +22,7 @@
 namespace b2 {
 
 constexpr int FR_NQ = 16, FR_NV = 15, FR_NU = 8, FR_NS = 14, FR_NX = 31, FR_NCOST = 23;
+constexpr int FR_NTRACE = 6;  // doubles per step kept by the fused kernel's trace capture: trace_object, trace_grasp_site
 constexpr int FB = 11;        // moving bodies: 0 object, 1..7 links, 8 hand (welded to link 7), 9 left finger, 10 right finger
 constexpr int FNA = 9;        // arm dofs (global dof = 6 + j): 7 hinges, 2 finger slides
 constexpr int FNPAD = 10, FNPAIR = 21;  // pairs: 0 table-object, 1..10 table-pad, 11..20 object-pad
@@ -1043,7 +1044,8 @@ __global__ void __launch_bounds__(256) fr3_rollout_kernel(const Fr3Model* __rest
                                                           const double* __restrict__ in, int N, int H, int K, const double* __restrict__ basis,
                                                           const double* __restrict__ cost_params, double* __restrict__ states,
                                                           double* __restrict__ sensors, float* __restrict__ cost_NH, double* __restrict__ reward_N,
-                                                          int wstride, int sync_mode, const SampleSpec smp, int index_offset) {
+                                                          int wstride, int sync_mode, const SampleSpec smp, int index_offset,
+                                                          double* __restrict__ trace_out = nullptr /* COST: (N, H, 6) or null */) {
   const int prof = sync_mode >> 8;
   sync_mode &= 255;
   B2_DYNAMIC_SMEM(unsigned char, fsm_all);
@@ -1101,6 +1103,7 @@ __global__ void __launch_bounds__(256) fr3_rollout_kernel(const Fr3Model* __rest
       }
       __syncwarp();
       fr3_step(m, W, lane, dist_mode, active, sync_mode, prof);
+      if (trace_out && active && lane < FR_NTRACE) trace_out[((size_t)n * H + t) * FR_NTRACE + lane] = W->sens[8 + lane];  // T1: trace sensors of every rollout
       if (active && lane == 0) {
         double cp[FR_NCOST];
 #pragma unroll
@@ -1173,7 +1176,7 @@ inline void fr3_destroy(Fr3Model* m) { if (getenv("B200MPC_FR3_PROF")) fr3_prof_
 
 inline int fr3_launch(const Fr3Model* m, int cost_mode, const double* d_x0, int batched, const double* d_in, int N, int H, int K,
                       const double* d_basis, const double* d_params, double* d_states, double* d_sensors, float* d_cost, double* d_reward,
-                      const PlanEpilogue& ep, const SampleSpec& smp, cudaStream_t st, std::string* err) {
+                      const PlanEpilogue& ep, const SampleSpec& smp, cudaStream_t st, std::string* err, double* d_trace = nullptr) {
   const char* sm_env = getenv("B200MPC_FR3_SYNC");
   const int sync_mode = (sm_env ? atoi(sm_env) : 3) | ((getenv("B200MPC_FR3_PROF") ? 1 : 0) << 8);
   const size_t wstride = fr3_wstride(cost_mode, K, H);
@@ -1188,7 +1191,7 @@ inline int fr3_launch(const Fr3Model* m, int cost_mode, const double* d_x0, int 
   if (cost_mode) {
     e = cudaFuncSetAttribute(fr3_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      fr3_rollout_kernel<true><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, (int)wstride, sync_mode, smp, ep.index_offset);
+      fr3_rollout_kernel<true><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, (int)wstride, sync_mode, smp, ep.index_offset, d_trace);
   } else {
     e = cudaFuncSetAttribute(fr3_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)

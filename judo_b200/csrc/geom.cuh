@@ -369,7 +369,7 @@ __device__ __noinline__ double l_box_box_distance(const double* p1, const double
   if (best <= 0) return best;
   if (best >= cutoff) return cutoff;
   if (!want_value) return best;
-  double W[4][3], v[3] = {-d12[0], -d12[1], -d12[2]};
+  double W[4][3], v[3] = {-d12[0], -d12[1], -d12[2]}, vv_prev = 1e300;
   int n = 0;
   if (ldot3(v, v) < 1e-30) { v[0] = 1; v[1] = v[2] = 0; }
   for (int it = 0; it < 64; it++) {
@@ -379,7 +379,9 @@ __device__ __noinline__ double l_box_box_distance(const double* p1, const double
     l_box_support(p2, m2, s2, v, b);
     for (int k = 0; k < 3; k++) w[k] = a[k] - b[k];
     const double vv = ldot3(v, v);
-    if (n > 0 && vv - ldot3(v, w) <= 1e-14 * vv) break;
+    if (n > 0 && vv - ldot3(v, w) <= 1e-13 * vv) break;
+    if (n > 0 && vv >= vv_prev * (1 - 1e-15)) break;  // parallel faces: the simplex cycles between equivalent vertices; v no longer shortens
+    if (n > 0) vv_prev = vv;  // (the initial v, the centre difference, is not a point of the simplex yet)
     bool dup = false;
     for (int i = 0; i < n; i++) if (W[i][0] == w[0] && W[i][1] == w[1] && W[i][2] == w[2]) dup = true;
     if (dup) break;

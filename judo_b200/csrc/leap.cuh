@@ -21,6 +21,7 @@
 namespace b2 {
 
 constexpr int LEAP_NQ = 23, LEAP_NV = 22, LEAP_NU = 16, LEAP_NS = 31, LEAP_NX = 45, LEAP_NCOST = 9;
+constexpr int LEAP_NTRACE = 15;  // doubles per step kept by the fused kernel's trace capture: the 5 framepos trace sensors
 constexpr int LB = 17;         // moving bodies: 0 = cube, 1 + 4f + d = link d of finger f
 constexpr int LMAXG = 80;      // hand collision geoms
 constexpr int LMAXCON = 24;    // contacts kept per step (3 rows each)
@@ -972,7 +973,7 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
 // All warps of the block call this together; `active` masks the tail warps.  The two block barriers keep the warps in
 // the same code region (see the kernel comment) — they are NOT data dependencies.
 __device__ inline void leap_step(const LeapModel* __restrict__ m, LeapWork* W, int lane, double* sens /* global, may be null */, int prof,
-                                 bool active, int sync_mode) {
+                                 bool active, int sync_mode, double* trace = nullptr /* global: the 5 framepos trace sensors only */) {
   long long t0 = LPROF_T();
   if (active) {
     leap_kinematics(m, W, lane);
@@ -987,6 +988,12 @@ __device__ inline void leap_step(const LeapModel* __restrict__ m, LeapWork* W, i
     LPROF_ADD(2, t0); t0 = LPROF_T();
     leap_make_constraint(m, W, lane);
     LPROF_ADD(3, t0); t0 = LPROF_T();
+    if (trace && lane < 5) {  // fused mode: only the trace sensors (T1, controller.py:323-363) are kept, for every rollout
+      const int b = (int)m->site_body[lane];
+      double t[3];
+      lmat_vec(t, W->xmat[b], m->site_pos[lane]);
+      for (int k = 0; k < 3; k++) trace[3 * lane + k] = W->xpos[b][k] + t[k];
+    }
     if (sens) {  // position-stage sensors: 16 jointpos then 5 framepos sites (pre-step state)
       if (lane < 16) sens[lane] = W->qpos[7 + lane];
       if (lane < 5) {
@@ -1071,7 +1078,8 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
                                                            const double* __restrict__ in, int N, int H, int K, const double* __restrict__ basis,
                                                            const double* __restrict__ cost_params, double* __restrict__ states,
                                                            double* __restrict__ sensors, float* __restrict__ cost_NH, double* __restrict__ reward_N,
-                                                           int wstride, int prof, const SampleSpec smp, int index_offset) {
+                                                           int wstride, int prof, const SampleSpec smp, int index_offset,
+                                                           double* __restrict__ trace_out = nullptr /* COST: (N, H, 15) or null */) {
   const int sync_mode = prof >> 8;
   prof &= 255;
   B2_DYNAMIC_SMEM(unsigned char, lsm_all);
@@ -1128,7 +1136,7 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
         W->ctrl[lane] = u;
       }
       __syncwarp();
-      leap_step(m, W, lane, nullptr, prof, active, sync_mode);
+      leap_step(m, W, lane, nullptr, prof, active, sync_mode, (trace_out && active) ? trace_out + ((size_t)n * H + t) * LEAP_NTRACE : nullptr);
       if (active && lane == 0) {
         double cp[LEAP_NCOST];
 #pragma unroll
@@ -1188,7 +1196,7 @@ inline int leap_num_partials(int N) { return N; }
 
 inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, int batched, const double* d_in, int N, int H, int K,
                        const double* d_basis, const double* d_params, double* d_states, double* d_sensors, float* d_cost, double* d_reward,
-                       const PlanEpilogue& ep, const SampleSpec& smp, cudaStream_t st, std::string* err) {
+                       const PlanEpilogue& ep, const SampleSpec& smp, cudaStream_t st, std::string* err, double* d_trace = nullptr) {
   const char* sm_env = getenv("B200MPC_LEAP_SYNC");
   const int prof = (getenv("B200MPC_LEAP_PROF") ? 1 : 0) | ((sm_env ? atoi(sm_env) : 3) << 8);
   (void)ep;  // the leap path runs the optimizer update as separate reduction kernels (b200mpc.cu)
@@ -1206,7 +1214,7 @@ inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, in
   if (cost_mode) {
     e = cudaFuncSetAttribute(leap_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      leap_rollout_kernel<true><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, (int)wstride, prof, smp, ep.index_offset);
+      leap_rollout_kernel<true><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, (int)wstride, prof, smp, ep.index_offset, d_trace);
   } else {
     e = cudaFuncSetAttribute(leap_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)

@@ -65,6 +65,22 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.b200mpc_launch_count(self._h))
 
+    # ---- trace capture (warp-per-rollout tasks)
+    @property
+    def trace_width(self) -> int:
+        """Doubles per step the fused kernel can keep per rollout (0: the task has no trace capture)."""
+        return int(self._lib.b200mpc_trace_width(self._h))
+
+    def set_trace_capture(self, enable: bool) -> None:
+        self._check(self._lib.b200mpc_set_trace_capture(self._h, int(enable)))
+
+    def elite_traces(self, idx: np.ndarray, H: int) -> np.ndarray:
+        """Trace sensors (len(idx), H, trace_width) of the given rollouts of the LAST fused plan step."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = np.empty((len(idx), H, self.trace_width))
+        self._check(self._lib.b200mpc_elite_traces(self._h, idx.ctypes.data, len(idx), int(H), out.ctypes.data))
+        return out
+
     @property
     def contact_overflows(self) -> int:
         """Rollout steps (process-wide) whose contact count exceeded the kernel's per-step buffer (truncation is never silent)."""

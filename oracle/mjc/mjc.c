@@ -760,7 +760,7 @@ static double box_box_distance(const double* p1, const double* m1, const double*
   if (best <= 0) return best;
   if (best >= cutoff) return cutoff;
   /* GJK on A - B */
-  double W[4][3], v[3] = {-d12[0], -d12[1], -d12[2]}, vv;
+  double W[4][3], v[3] = {-d12[0], -d12[1], -d12[2]}, vv, vv_prev = 1e300;
   int n = 0;
   if (dot3(v, v) < 1e-30) { v[0] = 1; v[1] = v[2] = 0; }
   for (int it = 0; it < 64; it++) {
@@ -769,7 +769,11 @@ static double box_box_distance(const double* p1, const double* m1, const double*
     box_support(p2, m2, s2, v, b);
     for (int k = 0; k < 3; k++) w[k] = a[k] - b[k];
     vv = dot3(v, v);
-    if (n > 0 && vv - dot3(v, w) <= 1e-14 * vv) break; /* no progress possible along -v: v is the closest point */
+    if (n > 0 && vv - dot3(v, w) <= 1e-13 * vv) break; /* no progress possible along -v: v is the closest point */
+    /* |v| decreases strictly until the optimum; with parallel faces (a whole face of closest points) rounding makes the
+     * simplex cycle between equivalent vertices instead: stop at the first iteration that no longer shortens v */
+    if (n > 0 && vv >= vv_prev * (1 - 1e-15)) break;
+    if (n > 0) vv_prev = vv; /* (the initial v, the centre difference, is not a point of the simplex yet) */
     int dup = 0;
     for (int i = 0; i < n; i++) if (W[i][0] == w[0] && W[i][1] == w[1] && W[i][2] == w[2]) dup = 1;
     if (dup) break;

@@ -159,3 +159,47 @@ def test_fr3_grasp_lifts_the_cube_by_friction():
     assert s[:, -1, 2].min() > 0.03                                 # lifted well clear of the table
     assert (e[:, -1, 4] > 0.005).all()                             # obj_table distance agrees
     assert np.abs(s[:, -1, 14] - 0.0185).max() < 2e-3              # pads stopped by the 4 cm cube (pad face 1.5 mm inside the finger frame)
+
+
+def test_box_box_signed_distance_matches_a_bounded_qp():
+    """The routine behind the restated distance sensors (SAT depth when penetrating, GJK when separated) against an independent
+    solve of  min |x - y|  over the two boxes (L-BFGS-B on the box-bounded QP), on random poses and on the degenerate poses the
+    fr3 gripper produces all the time: parallel faces (a whole face of closest points) and axis-aligned boxes."""
+    import ctypes
+
+    from scipy.optimize import minimize
+    from scipy.spatial.transform import Rotation as Rt
+
+    from oracle.mjc import lib
+
+    L = lib()
+    L.mjc_box_box_distance.restype = ctypes.c_double
+    dp = ctypes.POINTER(ctypes.c_double)
+    P = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)  # noqa: E731
+    rng = np.random.default_rng(0)
+    nsep = 0
+    for it in range(120):
+        p1, p2 = 0.1 * rng.normal(size=3), 0.1 * rng.normal(size=3) + np.array([0.15, 0, 0]) * rng.random()
+        m1 = Rt.random(random_state=int(rng.integers(1 << 30))).as_matrix()
+        m2 = Rt.random(random_state=int(rng.integers(1 << 30))).as_matrix()
+        if it % 3 == 0:   # parallel faces: box 2 is box 1's frame turned about a shared axis
+            m2 = m1 @ Rt.from_euler("z", rng.uniform(0, 6.28)).as_matrix()
+        if it % 7 == 0:
+            m1 = m2 = np.eye(3)
+        s1, s2 = 0.01 + 0.05 * rng.random(3), 0.01 + 0.05 * rng.random(3)
+        m1c, m2c = np.ascontiguousarray(m1), np.ascontiguousarray(m2)
+        d = L.mjc_box_box_distance(P(p1), P(m1c), P(s1), P(p2), P(m2c), P(s2), ctypes.c_double(10.0))
+
+        def f(z):
+            r = (p1 + m1 @ z[:3]) - (p2 + m2 @ z[3:])
+            return r @ r, np.concatenate([2 * m1.T @ r, -2 * m2.T @ r])
+
+        best = min(minimize(f, np.concatenate([rng.uniform(-s1, s1), rng.uniform(-s2, s2)]), jac=True, method="L-BFGS-B",
+                            bounds=list(zip(np.concatenate([-s1, -s2]), np.concatenate([s1, s2]))),
+                            options=dict(ftol=1e-18, gtol=1e-14, maxiter=5000)).fun for _ in range(3))
+        if d > 0:
+            nsep += 1
+            assert abs(d - np.sqrt(best)) < 1e-7, (it, d, np.sqrt(best))
+        else:
+            assert best < 1e-10, (it, d, best)   # penetrating (or touching): the QP distance is zero
+    assert nsep > 60

@@ -73,10 +73,11 @@ def test_fr3_fused_cost_kernel_on_emulator_matches_oracle(sim, fr3, phase):
     task.phase = Phase(phase)
     task.arm_pos_slice = slice(7, 16)
     params = task.cost_params()
-    cost, rew = np.zeros((N, H), dtype=np.float32), np.zeros(N)
-    sim.sim_fr3_plan_costs(P(consts), P(x0), P(knots), N, K, P(basis), H, P(params), P(cost), P(rew), 2, 3, 0)
+    cost, rew, trace = np.zeros((N, H), dtype=np.float32), np.zeros(N), np.zeros((N, H, 6))
+    sim.sim_fr3_plan_costs(P(consts), P(x0), P(knots), N, K, P(basis), H, P(params), P(cost), P(rew), 2, 3, 0, P(trace))
     controls = np.einsum("hk,nkj->nhj", basis, knots)
     states, sensors = om.rollout(x0, controls)
+    np.testing.assert_allclose(trace, sensors[..., 8:14], rtol=0, atol=1e-9)  # trace capture: trace_object + trace_grasp_site of every rollout
     ref = op.fr3_pick_reward(states, sensors, phase)
     np.testing.assert_allclose(rew, ref, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(-cost.sum(1), ref, rtol=1e-5, atol=1e-5)  # f32 per-step costs

@@ -59,8 +59,9 @@ def test_leap_fused_cost_kernel_on_emulator_matches_oracle(sim, leap):
     basis /= basis.sum(1, keepdims=True)
     gq = rng.normal(size=4)
     params = np.concatenate([[100.0, 0.1], gq / np.linalg.norm(gq), [0.0, 0.03, 0.1]])
-    cost, rew = np.zeros((N, H), dtype=np.float32), np.zeros(N)
-    sim.sim_leap_plan_costs(P(consts), P(x0), P(knots), N, K, P(basis), H, P(params), P(cost), P(rew), 2, 3, 0)
+    cost, rew, trace = np.zeros((N, H), dtype=np.float32), np.zeros(N), np.zeros((N, H, 15))
+    sim.sim_leap_plan_costs(P(consts), P(x0), P(knots), N, K, P(basis), H, P(params), P(cost), P(rew), 2, 3, 0, P(trace))
     controls = np.einsum("hk,nkj->nhj", basis, knots)
+    np.testing.assert_allclose(trace, om.rollout(x0, controls)[1][..., 16:31], rtol=0, atol=1e-10)  # trace capture: the 5 framepos sensors
     ref = op.leap_cube_reward(om.rollout(x0, controls)[0], params[2:6], 100.0, 0.1)
     np.testing.assert_allclose(rew, ref, rtol=0, atol=1e-10)

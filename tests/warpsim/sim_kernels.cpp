@@ -27,12 +27,12 @@ extern "C" int sim_leap_rollout(const double* consts, const double* x0, int batc
 
 // contract B through leap_rollout_kernel<true>
 extern "C" int sim_leap_plan_costs(const double* consts, const double* x0, const double* knots, int N, int K, const double* basis, int H,
-                                   const double* params, float* cost_NH, double* reward_N, int wpb, int sync_mode, int reverse) {
+                                   const double* params, float* cost_NH, double* reward_N, int wpb, int sync_mode, int reverse, double* trace_out) {
   const LeapModel* m = reinterpret_cast<const LeapModel*>(consts);
   const size_t ws = leap_wstride(1, K, H);
   wsim::set_reverse(reverse != 0);
   wsim::launch((N + wpb - 1) / wpb, 32 * wpb, wpb * ws, [&] {
-    leap_rollout_kernel<true>(m, x0, 0, knots, N, H, K, basis, params, nullptr, nullptr, cost_NH, reward_N, (int)ws, sync_mode << 8, SampleSpec{}, 0);
+    leap_rollout_kernel<true>(m, x0, 0, knots, N, H, K, basis, params, nullptr, nullptr, cost_NH, reward_N, (int)ws, sync_mode << 8, SampleSpec{}, 0, trace_out);
   });
   return 0;
 }
@@ -55,12 +55,12 @@ extern "C" int sim_fr3_rollout(const double* consts, const double* x0, int batch
 }
 
 extern "C" int sim_fr3_plan_costs(const double* consts, const double* x0, const double* knots, int N, int K, const double* basis, int H,
-                                  const double* params, float* cost_NH, double* reward_N, int wpb, int sync_mode, int reverse) {
+                                  const double* params, float* cost_NH, double* reward_N, int wpb, int sync_mode, int reverse, double* trace_out) {
   const Fr3Model* m = reinterpret_cast<const Fr3Model*>(consts);
   const size_t ws = fr3_wstride(1, K, H);
   wsim::set_reverse(reverse != 0);
   wsim::launch((N + wpb - 1) / wpb, 32 * wpb, wpb * ws, [&] {
-    fr3_rollout_kernel<true>(m, x0, 0, knots, N, H, K, basis, params, nullptr, nullptr, cost_NH, reward_N, (int)ws, sync_mode, SampleSpec{}, 0);
+    fr3_rollout_kernel<true>(m, x0, 0, knots, N, H, K, basis, params, nullptr, nullptr, cost_NH, reward_N, (int)ws, sync_mode, SampleSpec{}, 0, trace_out);
   });
   return 0;
 }
