@@ -1,0 +1,44 @@
+"""No-GPU tier: judo_b200's Controller (the mirror of judo/controller/controller.py:210-363) driven end to end on an emulator-backed
+engine (tests/sim_engine.py) against three consecutive update_action() calls of the UNMODIFIED reference Controller
+(tests/golden/plan_*.npz): bit-exact candidates under the same seed, rewards / nominal knots / CEM sigma / traces within tolerance."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture
+def sim_controller(monkeypatch):
+    import judo_b200.rollout_backend as rb
+    from tests.sim_engine import SimEngine
+
+    monkeypatch.setattr(rb, "Engine", SimEngine)
+    from judo_b200.controller import make_controller
+
+    return make_controller
+
+
+@pytest.mark.parametrize("tag", ["cartpole_ps", "cartpole_mppi", "cylinder_push_cem", "fr3_pick_cem"])
+def test_controller_on_emulator_reproduces_reference_plan_steps(sim_controller, golden, temp_np_seed, tag):
+    g = golden("plan_" + tag)
+    task, opt, N, horizon, seed, order, max_traces = g["meta"]
+    with temp_np_seed(int(seed)):
+        ctrl = sim_controller(str(task), str(opt))
+        ctrl.optimizer_cfg.num_rollouts = int(N)
+        ctrl.controller_cfg.horizon = float(horizon)
+        np.random.seed(int(seed))  # the golden run seeded the RNG and then built its Controller, whose reset() calls Task.reset() once
+        ctrl.reset()
+        np.testing.assert_array_equal(np.concatenate([ctrl.task.data.qpos, ctrl.task.data.qvel]), g["x_init"])
+        tol = 1e-8 if task != "fr3_pick" else 1e-6
+        for p in range(3):
+            ctrl.current_state = g[f"p{p}_x0"].copy()
+            ctrl.time = float(g[f"p{p}_time"])
+            np.testing.assert_allclose(ctrl.nominal_knots, g[f"p{p}_nominal_in"], rtol=0, atol=1e-9)
+            ctrl.update_action()
+            np.testing.assert_allclose(ctrl.candidate_knots, g[f"p{p}_candidate_knots"], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(ctrl.rewards, g[f"p{p}_rewards"], rtol=tol, atol=tol)
+            np.testing.assert_allclose(ctrl.nominal_knots, g[f"p{p}_nominal_out"], rtol=0, atol=tol)
+            np.testing.assert_array_equal(ctrl.times, g[f"p{p}_times_out"])
+            np.testing.assert_allclose(ctrl.traces, g[f"p{p}_traces"], rtol=0, atol=tol)
+            if opt == "cem":
+                np.testing.assert_allclose(ctrl.optimizer.sigma, g[f"p{p}_sigma_out"], rtol=1e-6, atol=1e-9)
+            if task == "fr3_pick":
+                assert ctrl.task.phase.value == int(g[f"p{p}_phase"])
