@@ -37,9 +37,12 @@ WORKLOADS = {
     "fr3_pick_cem": dict(task="fr3_pick", optimizer="cem", n_rollouts=1024, H=250, K=4, order="linear", horizon=1.0,
                          algo_bytes_per_rollout=4 * 4 * 8 + 4 * 250 + 4),
 }
+# the same kernel in its contact-rich regime: the gripper closes on the cube and lifts it (40 pad/table contacts, ~170 constraint rows)
+WORKLOADS["fr3_pick_cem_grasp"] = dict(WORKLOADS["fr3_pick_cem"], scenario="grasp")
 WARP_TASKS = ("leap_cube", "fr3_pick")  # warp-per-rollout kernels: ms-scale steps, optimizer update as separate reduction kernels
 CONFIG_TAG = {"cartpole_mppi": "BASELINE config C2", "cylinder_push_cem": "BASELINE config C3", "leap_cube_mppi": "BASELINE config C4",
-              "fr3_pick_cem": "SURVEY 8f-2, reference defaults at N=1024"}
+              "fr3_pick_cem": "SURVEY 8f-2, reference defaults at N=1024",
+              "fr3_pick_cem_grasp": "SURVEY 8f-2 in its contact-rich regime: pre-grasp pose, nominal plan closes the gripper and lifts"}
 
 
 def problem(w: dict, n_total: int, seed: int = 42):
@@ -58,6 +61,13 @@ def problem(w: dict, n_total: int, seed: int = 42):
     cfg.num_rollouts, cfg.num_nodes = n_total, w["K"]
     opt = opt_cls(cfg, task.nu)
     nominal = np.tile(task.optimizer_warm_start(), (w["K"], 1))
+    if w.get("scenario") == "grasp":
+        from judo_b200.tasks.fr3_pick import Q_PREGRASP
+
+        x0[7:14] = Q_PREGRASP
+        nominal = np.tile(np.concatenate([Q_PREGRASP, [0.0]]), (w["K"], 1))
+        nominal[w["K"] // 2:, 1] -= 0.3  # shoulder back: lift
+        task.pre_rollout(x0)
     lo, hi = task.actuator_ctrlrange[:, 0], task.actuator_ctrlrange[:, 1]
     knots = np.clip(opt.sample_control_knots(nominal), lo, hi)
     times = np.linspace(0, w["horizon"], w["K"], endpoint=True)

@@ -741,30 +741,45 @@ __device__ __noinline__ void fr3_constraint_update(const Fr3Model* __restrict__ 
 // Newton direction: search = -H^-1 grad,  H = M + sum_rows D j j^T + sum_contacts Jc^T Wc Jc  (dense 15x15, lane per entry, warp Cholesky)
 __device__ inline void fr3_newton_direction(const Fr3Model* __restrict__ m, Fr3Work* W, int lane) {
   const int ncon = W->ncon;
-  for (int e = lane; e < FR_NV * (FR_NV + 1) / 2; e += 32) {
-    const int i = FR3_TRI[e] >> 4, j = FR3_TRI[e] & 15;  // i >= j
-    double h = 0;
-    if (i < 6) { if (i == j) h = i < 3 ? m->body_mass[0] : m->obj_inertia[i - 3]; }
-    else if (j >= 6) h = W->M[i - 6][j - 6];
+  // every lane owns up to four entries (i >= j) of the lower triangle: mass matrix + scalar rows first ...
+  constexpr int NE = FR_NV * (FR_NV + 1) / 2;
+  int ei[4], ej[4];
+  double h[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int e = lane + 32 * q;
+    const int i = e < NE ? FR3_TRI[e] >> 4 : 0, j = e < NE ? FR3_TRI[e] & 15 : 0;
+    double v = 0;
+    if (i < 6) { if (i == j) v = i < 3 ? m->body_mass[0] : m->obj_inertia[i - 3]; }
+    else if (j >= 6) v = W->M[i - 6][j - 6];
     if (i == j && i >= 6) {
-      if (W->sstate[i - 5] == FST_QUADRATIC) h += W->sD[i - 5];
-      if (W->sstate[i + 4] == FST_QUADRATIC) h += W->sD[i + 4];
-      if (i >= 13) h += W->sD[0];
-    } else if (i == 14 && j == 13) h -= W->sD[0];
-    for (int c = 0; c < ncon; c++) {
-      const int cls = W->ccls[c];
-      if ((j < 6 && cls == 1) || (i >= 6 && cls == 0)) continue;  // i >= j: both must be touched by the contact
-      double w[5];
-      if (!fr3_contact_weight(W->cD[c], W->cmu[c], W->cgeo[c] + CG_JAR, w)) continue;  // no active edge
-      const double ni = W->cJ[c][0][i], nj = W->cJ[c][0][j], ai = W->cJ[c][1][i], aj = W->cJ[c][1][j], bi = W->cJ[c][2][i], bj = W->cJ[c][2][j];
-      h += w[0] * ni * nj + w[1] * (ni * aj + ai * nj) + w[2] * (ni * bj + bi * nj) + w[3] * ai * aj + w[4] * bi * bj;
-    }
-    W->H[i][j] = h;
+      if (W->sstate[i - 5] == FST_QUADRATIC) v += W->sD[i - 5];
+      if (W->sstate[i + 4] == FST_QUADRATIC) v += W->sD[i + 4];
+      if (i >= 13) v += W->sD[0];
+    } else if (i == 14 && j == 13) v -= W->sD[0];
+    ei[q] = i; ej[q] = j; h[q] = v;
   }
+  // ... then the contacts: the 3x3 weight of a contact is evaluated once per lane and applied to the lane's entries
+  for (int c = 0; c < ncon; c++) {
+    double w[5];
+    if (!fr3_contact_weight(W->cD[c], W->cmu[c], W->cgeo[c] + CG_JAR, w)) continue;  // no active edge
+    const int cls = W->ccls[c];
+    const double (*J)[FR_NV] = W->cJ[c];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int i = ei[q], j = ej[q];
+      if ((j < 6 && cls == 1) || (i >= 6 && cls == 0)) continue;  // i >= j: both dofs must be touched by the contact
+      const double ni = J[0][i], nj = J[0][j], ai = J[1][i], aj = J[1][j], bi = J[2][i], bj = J[2][j];
+      h[q] += w[0] * ni * nj + w[1] * (ni * aj + ai * nj) + w[2] * (ni * bj + bi * nj) + w[3] * ai * aj + w[4] * bi * bj;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) if (lane + 32 * q < NE) W->H[ei[q]][ej[q]] = h[q];
+  __syncwarp();
   // object-pad contacts are the only coupling between the object block and the arm block
   bool coupled = false;
   for (int c = lane; c < ncon; c += 32) coupled = coupled || W->ccls[c] == 2;
-  coupled = __any_sync(B2_FULLMASK, coupled);  // (also orders the H stores above before the factorisation reads them)
+  coupled = __any_sync(B2_FULLMASK, coupled);
   double x;
   if (coupled) {
     warp_chol(W->H, W->Hd, FR_NV, lane);

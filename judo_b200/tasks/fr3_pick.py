@@ -25,6 +25,11 @@ QPOS_HOME = np.array([
     0.04, 0.04,  # gripper, equality constrained
 ])  # judo/tasks/fr3_pick.py:16-22
 
+# Arm configuration whose grasp site sits at (0.7, 0, 0.03) with the hand pointing down and the fingers along world y: the open
+# gripper straddles the cube at its home position (least squares on the compiled kinematics; used by tests and bench.py's
+# contact-rich workload, not by the task itself)
+Q_PREGRASP = np.array([-0.07377, 0.87632, 0.08669, -1.54048, -0.10002, 2.41246, 0.8419])
+
 MINMU = 1e-5
 FR3_NCOST = 23
 

@@ -2,12 +2,12 @@
 import numpy as np
 
 from judo_b200.consts import load_table
-from judo_b200.tasks.fr3_pick import QPOS_HOME, reduced_collision_model
+from judo_b200.tasks.fr3_pick import Q_PREGRASP, QPOS_HOME, reduced_collision_model
 from oracle.mjc import OracleModel
 
 # arm configuration whose grasp site sits at (0.7, 0, 0.03) with the hand pointing down and the fingers along world y:
 # the open gripper straddles the 4 cm cube at its home position (found by least squares on the compiled kinematics)
-Q_GRASP = np.array([-0.07377, 0.87632, 0.08669, -1.54048, -0.10002, 2.41246, 0.8419])
+Q_GRASP = Q_PREGRASP
 U_HOME = np.array([0, -0.7854, 0, -2.3562, 0, 1.5708, 0.7854, 0.04])
 
 
