@@ -16,7 +16,7 @@ def sim_controller(monkeypatch):
     return make_controller
 
 
-@pytest.mark.parametrize("tag", ["cartpole_ps", "cartpole_mppi", "cylinder_push_cem", "fr3_pick_cem"])
+@pytest.mark.parametrize("tag", ["cartpole_ps", "cartpole_mppi", "cylinder_push_cem", "fr3_pick_cem", "leap_cube_mppi"])
 def test_controller_on_emulator_reproduces_reference_plan_steps(sim_controller, golden, temp_np_seed, tag):
     g = golden("plan_" + tag)
     task, opt, N, horizon, seed, order, max_traces = g["meta"]
@@ -27,7 +27,9 @@ def test_controller_on_emulator_reproduces_reference_plan_steps(sim_controller, 
         np.random.seed(int(seed))  # the golden run seeded the RNG and then built its Controller, whose reset() calls Task.reset() once
         ctrl.reset()
         np.testing.assert_array_equal(np.concatenate([ctrl.task.data.qpos, ctrl.task.data.qvel]), g["x_init"])
-        tol = 1e-8 if task != "fr3_pick" else 1e-6
+        tol = {"fr3_pick": 1e-6, "leap_cube": 2e-5}.get(str(task), 1e-8)  # contact-rich rollouts amplify rounding (see the GPU tier)
+        if task == "leap_cube":
+            ctrl.system_metadata = {"goal_quat": g["goal_quat"]}
         for p in range(3):
             ctrl.current_state = g[f"p{p}_x0"].copy()
             ctrl.time = float(g[f"p{p}_time"])
@@ -35,7 +37,7 @@ def test_controller_on_emulator_reproduces_reference_plan_steps(sim_controller, 
             ctrl.update_action()
             np.testing.assert_allclose(ctrl.candidate_knots, g[f"p{p}_candidate_knots"], rtol=0, atol=1e-9)
             np.testing.assert_allclose(ctrl.rewards, g[f"p{p}_rewards"], rtol=tol, atol=tol)
-            np.testing.assert_allclose(ctrl.nominal_knots, g[f"p{p}_nominal_out"], rtol=0, atol=tol)
+            np.testing.assert_allclose(ctrl.nominal_knots, g[f"p{p}_nominal_out"], rtol=0, atol=max(tol, 1e-4 if task == "leap_cube" else 0))
             np.testing.assert_array_equal(ctrl.times, g[f"p{p}_times_out"])
             np.testing.assert_allclose(ctrl.traces, g[f"p{p}_traces"], rtol=0, atol=tol)
             if opt == "cem":
