@@ -441,6 +441,8 @@ def main() -> None:
            "dtype": "f64", "data": "synthetic", "config": config, "state_steps_per_s": value * w["H"],
            "plan_latency_p50_ms": statistics.median(step_ms), "plan_latency_c1": plan_latency, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
            "gpu_launches": int(launches), "clocks": clocks.summary(), "wall_s_timed_region": t_wall}
+    if w["task"] in WARP_TASKS:  # rollout steps (whole run) that exceeded the kernel's per-step contact buffer and dropped contacts
+        out["contact_overflows"] = int(planner.engine.contact_overflows)
     sys.stdout.flush()
     os.dup2(_saved_stdout, 1)
     print(json.dumps(out), flush=True)
