@@ -24,7 +24,7 @@ constexpr int LEAP_NQ = 23, LEAP_NV = 22, LEAP_NU = 16, LEAP_NS = 31, LEAP_NX = 
 constexpr int LEAP_NTRACE = 15;  // doubles per step kept by the fused kernel's trace capture: the 5 framepos trace sensors
 constexpr int LB = 17;         // moving bodies: 0 = cube, 1 + 4f + d = link d of finger f
 constexpr int LMAXG = 80;      // hand collision geoms
-constexpr int LMAXCON = 24;    // contacts kept per step (3 rows each)
+constexpr int LMAXCON = 30;    // contacts kept per step (3 rows each; one contact per lane in the line search: <= 32)
 constexpr int LMAXEFC = 32 + 3 * LMAXCON;
 constexpr unsigned FULL = 0xffffffffu;
 
