@@ -1,7 +1,7 @@
 // leap.cuh — leap_cube: warp-per-rollout reduced articulated-body integrator + cost.
 //
 // One warp owns one rollout: 23 qpos / 22 dofs (free cube + 4 fingers x 4 hinges), state and all per-step work
-// arrays live in shared memory (~29 KB per warp -> 7 resident rollouts per SM, one wave at N = 1024).
+// arrays live in shared memory (~32 KB per warp -> 7 resident rollouts per SM, one wave at N = 1024).
 // Every stage of MuJoCo's mj_step that judo/models/xml/leap_cube.xml switches on is restated and spread over the
 // 32 lanes: kinematics (lane per chain), mass matrix + RNE (lane per finger), collision of the cube against the hand
 // geoms (lane per geom / per candidate pair), constraint rows (lane per row), the primal Newton solver with elliptic
