@@ -430,6 +430,29 @@ def main() -> None:
         plan_latency = {"config": "C1: cartpole + ps, N=32, H=32, K=4 — full Controller.update_action() incl. host sampling and traces",
                         "p50_ms": statistics.median(lat) * 1e3, "mean_ms": statistics.mean(lat) * 1e3, "samples": len(lat)}
         c1.engine.close()
+        # the same span for THIS workload at its own size (host sampling of N x K x nu knots, fused GPU step, elite traces)
+        try:
+            np.random.seed(42)
+            cw = make_controller(w["task"], w["optimizer"], device=local_rank)
+            cw.optimizer_cfg.num_rollouts, cw.optimizer_cfg.num_nodes = n_local, w["K"]
+            cw.controller_cfg.horizon = w["horizon"]
+            cw.reset()
+            if hasattr(cw.task, "get_sim_metadata"):
+                cw.system_metadata = cw.task.get_sim_metadata()
+            n_lat = 100 if w["task"] not in WARP_TASKS else 15
+            for _ in range(3):
+                cw.update_action()
+            latw = []
+            for i in range(n_lat):
+                cw.time = cw.task.dt * i
+                t1 = time.perf_counter()
+                cw.update_action()
+                latw.append(time.perf_counter() - t1)
+            plan_latency["workload"] = {"config": f"{w['task']} + {w['optimizer']}, N={n_local}, H={cw.num_timesteps}, K={w['K']} — full Controller.update_action()",
+                                        "p50_ms": statistics.median(latw) * 1e3, "mean_ms": statistics.mean(latw) * 1e3, "samples": len(latw)}
+            cw.engine.close()
+        except Exception as exc:  # noqa: BLE001 — an auxiliary figure must never cost the bench line
+            plan_latency["workload"] = {"error": repr(exc)}
 
     # the CPU baseline is timed on rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host cores)
     cpu = time_cpu(w, x0, knots, basis, params, opt, args.cpu_budget, min(n_local, 4096 if w["task"] not in WARP_TASKS else (256 if w["task"] == "leap_cube" else 64))) if world == 1 else None
