@@ -131,3 +131,81 @@ extern "C" int sim_rollout(int task, const double* consts, const double* x0, int
   if (task == 0) return sim_small_rollout<CartpoleTask>(consts, x0, batched, controls, N, H, states, sensors, threads);
   return sim_small_rollout<CylinderPushTask>(consts, x0, batched, controls, N, H, states, sensors, threads);
 }
+
+// ------------------------------------------------------------------ self-test kernels of the emulator itself (tests/test_warpsim_selftest.py)
+namespace selftest {
+
+__global__ void warp_collectives(const double* in, double* sum_out, unsigned* ballot_out, double* scan_out, int* all_out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gw = blockIdx.x * (blockDim.x >> 5) + w;
+  double v = in[gw * 32 + lane], s = v;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) sum_out[gw] = s;
+  const unsigned b = __ballot_sync(0xffffffffu, v > 0.5);
+  if (lane == 0) { ballot_out[gw] = b; all_out[gw] = __popc(b); }
+  double p = v;
+  for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, p, o); if (lane >= o) p += t; }
+  scan_out[gw * 32 + lane] = p;
+  const int a = __all_sync(0xffffffffu, v >= 0.0);
+  if (lane == 1) all_out[gw] += 1000 * a;
+}
+
+// block reduction through static shared memory, then a lock-step loop in which warp w needs w + 1 rounds
+__global__ void block_sync(const double* in, double* out, int* rounds_out) {
+  __shared__ double part[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double s = in[blockIdx.x * blockDim.x + threadIdx.x];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) part[w] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int i = 0; i < nw; i++) t += part[i]; out[blockIdx.x] = t; }
+  int mine = 0, rounds = 0;
+  bool done = false;
+  for (int it = 0; it < 100; it++) {
+    if (!__syncthreads_or(done ? 0 : 1)) break;
+    rounds++;
+    if (done) continue;
+    if (++mine > w) done = true;
+  }
+  if (lane == 0) rounds_out[blockIdx.x * nw + w] = 100 * rounds + mine;
+}
+
+// lane L writes slot L, then reads its neighbour's slot: correct only with the barrier in between
+__global__ void neighbour(double* out, int with_barrier) {
+  __shared__ double slot[32];
+  const int lane = threadIdx.x & 31;
+  slot[lane] = -1.0;
+  __syncwarp();
+  slot[lane] = (double)lane;
+  if (with_barrier) __syncwarp();
+  out[lane] = slot[(lane + 1) & 31];
+}
+
+__global__ void tma_copy(const double* src, double* out, int n) {
+  B2_DYNAMIC_SMEM(unsigned char, raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(raw);
+  double* buf = reinterpret_cast<double*>(raw + 16);
+  if (threadIdx.x == 0) { b2::mbar_init(bar, 1); b2::fence_barrier_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) { b2::mbar_expect_tx(bar, n * 8); b2::tma_bulk_g2s(buf, src, n * 8, bar); }
+  b2::mbar_wait(bar, 0);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = 2 * buf[i];
+}
+
+}  // namespace selftest
+
+extern "C" void sim_selftest_warp(const double* in, int nblocks, int warps, double* sum_out, unsigned* ballot_out, double* scan_out, int* all_out, int reverse) {
+  wsim::set_reverse(reverse != 0);
+  wsim::launch(nblocks, 32 * warps, 0, [&] { selftest::warp_collectives(in, sum_out, ballot_out, scan_out, all_out); });
+}
+extern "C" void sim_selftest_block(const double* in, int nblocks, int warps, double* out, int* rounds_out, int reverse) {
+  wsim::set_reverse(reverse != 0);
+  wsim::launch(nblocks, 32 * warps, 0, [&] { selftest::block_sync(in, out, rounds_out); });
+}
+extern "C" void sim_selftest_neighbour(double* out, int with_barrier, int reverse) {
+  wsim::set_reverse(reverse != 0);
+  wsim::launch(1, 32, 0, [&] { selftest::neighbour(out, with_barrier); });
+}
+extern "C" void sim_selftest_tma(const double* src, double* out, int n, int reverse) {
+  wsim::set_reverse(reverse != 0);
+  wsim::launch(1, 64, 16 + n * 8, [&] { selftest::tma_copy(src, out, n); });
+}
