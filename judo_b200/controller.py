@@ -114,13 +114,23 @@ class Controller:
     def num_timesteps(self) -> int:
         return int(np.ceil(self.horizon / self.task.dt))
 
+    # (both grids only change with the config; they are rebuilt on a key change instead of on every plan step — at the reference's
+    # sizes update_action() is dominated by host-side NumPy call overhead, not by the GPU)
     @property
     def rollout_times(self) -> np.ndarray:
-        return self.task.dt * np.arange(self.num_timesteps)
+        key = (self.task.dt, self.num_timesteps)
+        if getattr(self, "_rt_key", None) != key:
+            self._rt_key, self._rt = key, self.task.dt * np.arange(self.num_timesteps)
+            self._rt.flags.writeable = False
+        return self._rt
 
     @property
     def spline_timesteps(self) -> np.ndarray:
-        return np.linspace(0, self.horizon, self.optimizer_cfg.num_nodes, endpoint=True)
+        key = (self.horizon, self.optimizer_cfg.num_nodes)
+        if getattr(self, "_st_key", None) != key:
+            self._st_key, self._st = key, np.linspace(0, self.horizon, self.optimizer_cfg.num_nodes, endpoint=True)
+            self._st.flags.writeable = False
+        return self._st
 
     @property
     def optimizer_cfg(self) -> OptimizerConfig:
@@ -284,13 +294,8 @@ class Controller:
             elite_sensors = self.sensors[elite]
         elif self._trace_capture and self.sampling == "host":
             elite = np.asarray(self._elite[:ne])
-            tr = self.engine.elite_traces(elite, self.num_timesteps)  # (ne, H, 3 * nts): the trace sensors, in sensor order
             self.elite_indices = elite
-            rep = np.repeat(tr, 2, axis=1)[:, 1:-1, :]
-            out = np.zeros((nts * ne, size, 2, 3))
-            for s in range(nts):
-                out[s::nts] = np.reshape(rep[:, :, 3 * s:3 * s + 3], (ne, size, 2, 3))
-            self.traces = np.reshape(out, (ne * nts * size, 2, 3))
+            self.traces = self._segments(self.engine.elite_traces(elite, self.num_timesteps), ne, nts, size)  # (ne, H, 3 nts), sensor order
             return
         else:
             elite = np.asarray(self._elite[:ne])
@@ -300,12 +305,20 @@ class Controller:
             _, elite_sensors = self.engine.rollout(self.current_state, self.task.task_to_sim_ctrl(ctrl), want_sensors=True)
             self.engine.update(N)
         self.elite_indices = elite
-        inds = [int(self.model.sensor_adr[s]) + p for s in self.trace_sensors for p in range(3)]
-        rep = np.repeat(elite_sensors, 2, axis=1)[:, 1:-1, :][:, :, inds]
-        out = np.zeros((nts * ne, size, 2, 3))
+        if getattr(self, "_trace_cols", None) is None:
+            self._trace_cols = np.array([int(self.model.sensor_adr[s]) + p for s in self.trace_sensors for p in range(3)], dtype=np.intp)
+        self.traces = self._segments(elite_sensors[:, :, self._trace_cols], ne, nts, size)
+
+    @staticmethod
+    def _segments(tr: np.ndarray, ne: int, nts: int, size: int) -> np.ndarray:
+        """(ne, H, 3 nts) trace-sensor positions -> (ne * nts * (H - 1), 2, 3) line segments in the reference's order
+        (controller.py:341-363: consecutive positions of each sensor, elites interleaved with sensors)."""
+        out = np.empty((nts * ne, size, 2, 3))
         for s in range(nts):
-            out[s::nts] = np.reshape(rep[:, :, 3 * s:3 * s + 3], (ne, size, 2, 3))
-        self.traces = np.reshape(out, (ne * nts * size, 2, 3))
+            blk = tr[:, :, 3 * s:3 * s + 3]
+            out[s::nts, :, 0, :] = blk[:, :-1]
+            out[s::nts, :, 1, :] = blk[:, 1:]
+        return out.reshape(ne * nts * size, 2, 3)
 
     def update_states(self, state_msg) -> None:  # noqa: ANN001
         """state_msg: any object with qpos, qvel, time, sim_metadata (judo/app/structs.py:30-41)."""

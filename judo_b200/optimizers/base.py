@@ -68,13 +68,21 @@ class Optimizer(ABC, Generic[ConfigT]):
         return False
 
     def _ramp(self) -> np.ndarray:
-        K = self.num_nodes
-        return self.noise_ramp * np.linspace(1 / K, 1, K, endpoint=True)[:, None]
+        key = (self.num_nodes, self.noise_ramp)
+        if getattr(self, "_ramp_key", None) != key:  # rebuilt only when the config changes (read-only: callers multiply, never mutate)
+            K = self.num_nodes
+            self._ramp_key, self._ramp_val = key, self.noise_ramp * np.linspace(1 / K, 1, K, endpoint=True)[:, None]
+            self._ramp_val.flags.writeable = False
+        return self._ramp_val
 
     def _noised(self, nominal_knots: np.ndarray, sigma: np.ndarray | float) -> np.ndarray:
         """Row 0 is the un-noised nominal; rows 1.. get sigma * N(0, 1) (mppi.py:58-59, cem.py:73-74, ps.py:49-50)."""
         noise = np.random.randn(self.num_rollouts - 1, self.num_nodes, self.nu)
-        return np.concatenate([nominal_knots[None], nominal_knots + sigma * noise])
+        out = np.empty((self.num_rollouts, self.num_nodes, self.nu))
+        out[0] = nominal_knots
+        np.multiply(noise, sigma, out=out[1:])  # same two roundings as nominal + sigma * noise, without the temporaries
+        out[1:] += nominal_knots
+        return out
 
     @abstractmethod
     def sample_control_knots(self, nominal_knots: np.ndarray) -> np.ndarray:

@@ -41,32 +41,33 @@ def spline_basis(times: np.ndarray, query: np.ndarray, order: str) -> np.ndarray
         raise ValueError(f"spline_order must be one of {SPLINE_ORDERS}, got {order!r}")
     if order == "cubic" and K < 4:
         raise ValueError("cubic splines need at least 4 knots")
+    # segment of every query: index of the last knot <= q, clamped to a valid interval; queries outside the knot span are pinned to
+    # the first / last knot afterwards.  (Few, flat NumPy calls: at the reference's sizes this function is Python-overhead bound and
+    # it sits twice on the plan step's critical path.)
     B = np.zeros((H, K))
-    below, above = q < t[0], q > t[-1]
-    B[below, 0] = 1.0
-    B[above, K - 1] = 1.0
-    inside = np.nonzero(~(below | above))[0]
-    if len(inside) == 0:
-        return B
-    qi = q[inside]
-    seg = np.clip(np.searchsorted(t, qi, side="right") - 1, 0, K - 2)
+    rows = np.arange(H)
+    seg = np.searchsorted(t, q, side="right") - 1   # -1 below the first knot, K - 1 from the last knot on
     if order == "zero":
-        idx = np.where(qi >= t[-1], K - 1, seg)
-        B[inside, idx] = 1.0
+        B[rows, np.maximum(seg, 0)] = 1.0
         return B
-    h = t[seg + 1] - t[seg]
-    a = (t[seg + 1] - qi) / h
-    b = (qi - t[seg]) / h
+    below, above = seg < 0, q > t[-1]
+    seg = np.minimum(np.maximum(seg, 0), K - 2)
+    t0, t1 = t[seg], t[seg + 1]
+    h = t1 - t0
+    a = (t1 - q) / h
+    b = (q - t0) / h
+    out = below | above
+    if out.any():
+        a[below], b[below] = 1.0, 0.0
+        a[above], b[above] = 0.0, 1.0
     if order == "linear":
-        B[inside, seg] += a
-        B[inside, seg + 1] += b
+        B[rows, seg] = a
+        B[rows, seg + 1] = b
         return B
     C = _cubic_not_a_knot_matrix(t)
     ca = (a**3 - a) * h * h / 6.0
     cb = (b**3 - b) * h * h / 6.0
-    rows = np.zeros((len(inside), K))
-    rows[np.arange(len(inside)), seg] += a
-    rows[np.arange(len(inside)), seg + 1] += b
-    rows += ca[:, None] * C[seg] + cb[:, None] * C[seg + 1]
-    B[inside] = rows
+    B[rows, seg] = a
+    B[rows, seg + 1] = b
+    B += ca[:, None] * C[seg] + cb[:, None] * C[seg + 1]
     return B
