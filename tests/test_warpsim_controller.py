@@ -44,3 +44,26 @@ def test_controller_on_emulator_reproduces_reference_plan_steps(sim_controller, 
                 np.testing.assert_allclose(ctrl.optimizer.sigma, g[f"p{p}_sigma_out"], rtol=1e-6, atol=1e-9)
             if task == "fr3_pick":
                 assert ctrl.task.phase.value == int(g[f"p{p}_phase"])
+
+
+def test_runtime_config_changes_are_picked_up(sim_controller, temp_np_seed):
+    """The reference lets the GUI change horizon, num_nodes, num_rollouts and the noise ramp between plan steps
+    (controller.py:145-157, 215-226); the cached time grids / ramp must follow."""
+    with temp_np_seed(3):
+        ctrl = sim_controller("cartpole", "mppi")
+        ctrl.update_action()
+        assert ctrl.nominal_knots.shape == (4, 1) and ctrl.candidate_knots.shape == (32, 4, 1) and ctrl.num_timesteps == 25
+        t0 = ctrl.spline_timesteps
+        assert t0 is ctrl.spline_timesteps and not t0.flags.writeable            # cached, read-only
+        ctrl.controller_cfg.horizon = 2.0
+        ctrl.optimizer_cfg.num_nodes = 6
+        ctrl.optimizer_cfg.num_rollouts = 48
+        ctrl.optimizer_cfg.noise_ramp = 1.5
+        ctrl.time = 0.08
+        ctrl.update_action()
+        np.testing.assert_array_equal(ctrl.spline_timesteps, np.linspace(0, 2.0, 6))
+        np.testing.assert_array_equal(ctrl.rollout_times, 0.04 * np.arange(50))
+        np.testing.assert_array_equal(ctrl.times, 0.08 + np.linspace(0, 2.0, 6))
+        assert ctrl.nominal_knots.shape == (6, 1) and ctrl.candidate_knots.shape == (48, 6, 1) and ctrl.rewards.shape == (48,)
+        np.testing.assert_array_equal(ctrl.optimizer._ramp(), 1.5 * np.linspace(1 / 6, 1, 6)[:, None])
+        assert ctrl.traces.shape == (5 * 2 * 49, 2, 3)
