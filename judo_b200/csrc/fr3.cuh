@@ -831,8 +831,8 @@ __device__ __forceinline__ void fr3_ls_eval(const Fr3LS& L, double alpha, double
   *d2 = g2 + p2;
 }
 
-// exact line search (safeguarded 1-D Newton on the convex piecewise-quadratic cost); leaves jv of the rows in W->sforce-independent
-// storage: scalar rows -> returned through L (registers), contacts -> W->cgeo[c][0..2].  Returns alpha.
+// exact line search: safeguarded 1-D Newton on the convex piecewise-quadratic cost along the search direction.  The residuals (jar)
+// and their directional derivatives (jv) of the rows / contacts this lane owns are in L (registers); returns the step alpha.
 __device__ inline double fr3_line_search(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, Fr3LS& L) {
   double g1 = 0, g2 = 0, sn = 0, gs = 0;
   if (lane < FR_NV) {
