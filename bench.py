@@ -210,6 +210,7 @@ def main() -> None:
     ap.add_argument("--workload", default="cartpole_mppi", choices=list(WORKLOADS))
     ap.add_argument("--n-rollouts", type=int, default=0, help="per-GPU rollouts (default: the workload's)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-extras", action="store_true", help="kernel sweeps: skip the Controller-latency and CPU-baseline legs")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.n_rollouts:
@@ -413,7 +414,7 @@ def main() -> None:
     # the whole Controller.update_action() — host sampling, clip, spline basis, fused GPU step, spline refresh, traces —
     # i.e. the span judo's ControllerNode times as plan_time (judo/app/dora/controller.py:138-142)
     plan_latency = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         from judo_b200.controller import make_controller
 
         np.random.seed(42)
@@ -455,7 +456,7 @@ def main() -> None:
             plan_latency["workload"] = {"error": repr(exc)}
 
     # the CPU baseline is timed on rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host cores)
-    cpu = time_cpu(w, x0, knots, basis, params, opt, args.cpu_budget, min(n_local, 4096 if w["task"] not in WARP_TASKS else (256 if w["task"] == "leap_cube" else 64))) if world == 1 else None
+    cpu = time_cpu(w, x0, knots, basis, params, opt, args.cpu_budget, min(n_local, 4096 if w["task"] not in WARP_TASKS else (256 if w["task"] == "leap_cube" else 64))) if world == 1 and not args.no_extras else None
     config["exchange_used"] = ("in-kernel P2P stores over NVLink (CUDA IPC), 1 launch per step" if world > 1 and planner.peer_exchange and
                                w["task"] not in WARP_TASKS else ("nccl all_gather + combine kernel" if world > 1 else "none"))
     config.pop("exchange", None)

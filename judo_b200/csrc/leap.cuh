@@ -1080,7 +1080,8 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
                                                            double* __restrict__ sensors, float* __restrict__ cost_NH, double* __restrict__ reward_N,
                                                            int wstride, int prof, const SampleSpec smp, int index_offset,
                                                            double* __restrict__ trace_out = nullptr /* COST: (N, H, 15) or null */) {
-  const int sync_mode = prof >> 8;
+  const int sync_period = (prof >> 16) > 0 ? (prof >> 16) : 1;  // experiment knob: block barrier every sync_period time steps (sync_mode 1)
+  const int sync_mode = (prof >> 8) & 255;
   prof &= 255;
   B2_DYNAMIC_SMEM(unsigned char, lsm_all);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -1129,7 +1130,7 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
     double total = 0;
 #pragma unroll 1
     for (int t = 0; t < H; t++) {
-      if (sync_mode >= 1) __syncthreads();
+      if (sync_mode >= 1 && (sync_period == 1 || t % sync_period == 0)) __syncthreads();
       if (active && lane < LEAP_NU) {
         double u = 0;
         for (int k = 0; k < K; k++) u += __ldg(basis + t * K + k) * sK[k * LEAP_NU + lane];
@@ -1198,7 +1199,8 @@ inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, in
                        const double* d_basis, const double* d_params, double* d_states, double* d_sensors, float* d_cost, double* d_reward,
                        const PlanEpilogue& ep, const SampleSpec& smp, cudaStream_t st, std::string* err, double* d_trace = nullptr) {
   const char* sm_env = getenv("B200MPC_LEAP_SYNC");
-  const int prof = (getenv("B200MPC_LEAP_PROF") ? 1 : 0) | ((sm_env ? atoi(sm_env) : 3) << 8);
+  const char* sp_env = getenv("B200MPC_LEAP_SYNC_PERIOD");
+  const int prof = (getenv("B200MPC_LEAP_PROF") ? 1 : 0) | ((sm_env ? atoi(sm_env) : 3) << 8) | ((sp_env ? atoi(sp_env) : 1) << 16);
   (void)ep;  // the leap path runs the optimizer update as separate reduction kernels (b200mpc.cu)
   size_t wstride = ((sizeof(LeapWork) + 15) & ~(size_t)15) + 16 + (cost_mode ? (size_t)K * LEAP_NU * sizeof(double) : 0);
   wstride = (wstride + 15) & ~(size_t)15;
