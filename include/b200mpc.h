@@ -108,6 +108,59 @@ int b200mpc_plan_step_sampled(b200mpc_handle* h, const double* x0, const double*
                               unsigned long long counter, int index_offset, double* nominal, double* sigma, double* reward_N,
                               int* elite_idx, int n_elite, double* elite_knots, double* knots_out);
 
+/* ---- Controller.update_action fast path: ONE call per optimisation iteration ----------------------------------------------------
+ * Replaces the body of the while-loop in Controller.update_action (judo/controller/controller.py:250-293) plus update_traces
+ * (:323-363) for the built-in optimizers and tasks, WITH the reference's host-side sampling:
+ *   candidates = clip(nominal + sigma * np.random.randn(N-1, K, nu), lo, hi), row 0 = the nominal
+ *   (judo/optimizers/mppi.py:38-59, cem.py:55-74, ps.py:29-50; clip controller.py:253-258)
+ * where the normals come from NumPy's legacy global MT19937 stream, reproduced bit for bit from the generator's own state
+ * (mt_key / mt_pos point INTO numpy's mt19937_state: 624 words + position; they are advanced exactly as np.random.randn would).
+ * The generator's cached-gaussian flag is not reachable from outside numpy, so the caller keeps it consistent: it draws the first
+ * one or two normals through numpy (head[], n_head) so that the flag is known to be clear, this call draws an EVEN number, and when one
+ * more is needed the step is split: phase 1 samples, the caller draws that last normal through numpy (tail), phase 2 finishes.
+ * Then: spline basis (H, K) for query times time + dt * arange(H) (controller.py:261-262,382-401), one H2D copy, the fused
+ * rollout + cost + update kernel (+ the elites' trace sensors from the captured positions), results written by the kernel into
+ * pinned host memory, trace segments assembled (controller.py:341-363). */
+typedef struct {
+  int N, K, H;
+  int optimizer;              /* B200MPC_OPT_* */
+  int spline_order;           /* 0 zero, 1 linear, 2 cubic */
+  int n_elite;                /* best rollouts to list and trace, 0..8 */
+  int phase;                  /* 0: whole step; 1: sample only; 2: finish a step started with phase 1 */
+  int n_head;                 /* 0..2 normals already drawn by the caller (head[]) */
+  int has_tail;               /* phase 2: `tail` is the last normal of the block */
+  int n_trace_sensors;        /* framepos trace sensors per elite (0: no traces) */
+  double time, dt;
+  double head[2], tail;
+  const double* knot_times;   /* (K) */
+  const double* x0;           /* (nq+nv) */
+  const double* nominal;      /* (K, nu) nominal knots at knot_times */
+  const double* sigma;        /* (K, nu) */
+  const double* lo;           /* (nu) */
+  const double* hi;           /* (nu) */
+  const double* cost_params;
+  const double* opt_params;   /* as b200mpc_plan_step */
+  const int* trace_cols;      /* (3 * n_trace_sensors) sensordata columns of the trace sensors */
+  unsigned int* mt_key;       /* numpy's mt19937_state.key (624 words) */
+  int* mt_pos;                /* numpy's mt19937_state.pos */
+  /* outputs (caller-owned; any may be NULL except nominal_out) */
+  double* nominal_out;        /* (K, nu) */
+  double* sigma_out;          /* (K, nu), CEM */
+  double* rewards;            /* (N) */
+  int* elite_idx;             /* (n_elite) */
+  double* traces;             /* (n_elite * n_trace_sensors * (H-1), 2, 3) */
+  double* basis_out;          /* (H, K) */
+  double* knots_out;          /* (N, K, nu) the candidates (NULL: read them later with b200mpc_last_candidates) */
+} b200mpc_step_request;
+int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* req);
+/* The candidates of the last b200mpc_controller_step, (N, K, nu), copied out of the pinned staging buffer. */
+int b200mpc_last_candidates(b200mpc_handle* h, double* knots_out, int N, int K);
+/* Host-only helpers behind the call above, exported for the parity tests (no GPU needed):
+ *   b200mpc_legacy_normals : the next n_even legacy normals of the stream (cached-gaussian flag clear);
+ *   b200mpc_spline_basis    : interp1d's (H, K) matrix, order 0 zero / 1 linear / 2 cubic. */
+int b200mpc_legacy_normals(unsigned int* mt_key, int* mt_pos, double* out, size_t n_even);
+int b200mpc_spline_basis(int order, const double* knot_times, int K, const double* query, int H, double* basis_HK);
+
 /* ---- resident (device-pointer) API: inputs/outputs already in HBM, asynchronous on `stream` ------------------------
  * Used by bench.py's device-resident measurement and by the multi-GPU sharded plan step (judo_b200/dist.py), where
  * torch owns the allocations and NCCL moves the partials.  All pointers are device pointers; stream is a

@@ -19,7 +19,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 
 def sources() -> list[str]:
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.cpp")) +
                   [os.path.join(_HERE, "..", "include", "b200mpc.h")])
 
 
@@ -36,9 +36,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     defs = []
     if os.path.exists(os.path.join(CSRC, "leap.cuh")):
         defs.append("-DB200MPC_WITH_LEAP")
-    cmd = [NVCC, *FLAGS, *defs, "-o", LIB_PATH, os.path.join(CSRC, "b200mpc.cu")]
+    # host-only glue (sampler / spline basis / trace segments): plain g++, strict IEEE rounding (no FMA contraction: the candidates must
+    # be bit-identical to NumPy's), SIMD variants selected at load time (the library is built here and runs on another CPU)
+    glue_o = os.path.join(_HERE, "host_glue.o")
+    gcmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-math-errno", "-c",
+            os.path.join(CSRC, "host_glue.cpp"), "-o", glue_o]
+    gres = subprocess.run(gcmd, capture_output=True, text=True)
+    if gres.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + (gres.stdout + gres.stderr)[-6000:])
+    cmd = [NVCC, *FLAGS, *defs, "-o", LIB_PATH, os.path.join(CSRC, "b200mpc.cu"), glue_o]
     res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    log = " ".join(gcmd) + "\n" + gres.stdout + gres.stderr + res.stdout + res.stderr
     with open(os.path.join(_HERE, "build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:

@@ -17,10 +17,14 @@ import numpy as np
 
 from judo_b200.config import OverridableConfig, set_config_overrides
 from judo_b200.normalization import IdentityNormalizer, Normalizer, make_normalizer, normalizer_registry
-from judo_b200.optimizers import Optimizer, OptimizerConfig, get_registered_optimizers
+import ctypes
+
+from judo_b200 import _lib
+from judo_b200.engine import OPT_IDS, SPLINE_IDS, legacy_stream
+from judo_b200.optimizers import Optimizer, OptimizerConfig, fused_optimizer_ok, get_registered_optimizers
 from judo_b200.rollout_backend import B200RolloutBackend, RolloutBackend
 from judo_b200.spline import spline_basis
-from judo_b200.tasks import Task, TaskConfig, get_registered_tasks
+from judo_b200.tasks import Task, TaskConfig, fused_task_ok, get_registered_tasks
 
 
 @dataclass
@@ -52,6 +56,9 @@ class Spline:
 
     def __call__(self, query: np.ndarray | float) -> np.ndarray:
         q = np.atleast_1d(np.asarray(query, dtype=np.float64))
+        if self.order == "zero" and self.knots.ndim == 2:  # previous-knot hold: a gather (same values as the basis product, 1.0 * knot)
+            out = self.knots[np.maximum(np.searchsorted(self.times, q, side="right") - 1, 0)]
+            return out[0] if np.ndim(query) == 0 else out
         out = np.einsum("hk,...kj->...hj", spline_basis(self.times, q, self.order), self.knots)
         return out[..., 0, :] if np.ndim(query) == 0 else out
 
@@ -93,7 +100,8 @@ class Controller:
         self.all_traces_rollout_size = self.sensor_rollout_size * self.num_trace_sensors
         self.fused = True  # set False to force the contract-A path (rollout + Task.reward + optimizer update)
         # warp-per-rollout tasks: the fused kernel keeps every rollout's trace sensors so the elites need no second simulation
-        self._trace_capture = self.num_trace_sensors > 0 and self.engine.trace_width == 3 * self.num_trace_sensors
+        self._engine_trace_width = self.engine.trace_width
+        self._trace_capture = self.num_trace_sensors > 0 and self._engine_trace_width == 3 * self.num_trace_sensors
         if self._trace_capture:
             self.engine.set_trace_capture(True)
         # "host": np.random.randn exactly as the reference (seed parity).  "device": Philox inside the rollout kernel (perf mode:
@@ -101,6 +109,21 @@ class Controller:
         self.sampling: Literal["host", "device"] = "host"
         self.device_seed = 0
         self._plan_counter = 0
+        # One C call per optimisation iteration (b200mpc_controller_step: sampling from numpy's own stream, clip, spline basis, fused
+        # kernel, traces) whenever optimizer, task hooks and normalizer are the built-ins; False forces the NumPy glue below.
+        self.fast_path = True
+        self._rq = _lib.StepRequest()
+
+    # the candidates of the last plan step; after a fast-path step they are fetched from the engine's staging buffer on first use
+    @property
+    def candidate_knots(self) -> np.ndarray:
+        if self._cand is None:
+            self._cand = self.engine.last_candidates(*self._cand_shape)
+        return self._cand
+
+    @candidate_knots.setter
+    def candidate_knots(self, value: np.ndarray) -> None:
+        self._cand = value
 
     # ---- config views (controller.py:109-208) ----------------------------------------------------------------
     horizon = property(lambda self: self.controller_cfg.horizon)
@@ -167,8 +190,53 @@ class Controller:
 
     # ---- the plan step (controller.py:210-299) -----------------------------------------------------------------
     def _can_fuse(self) -> bool:
-        return self.fused and self.task.cost_params(self.system_metadata) is not None and self.optimizer.name in ("mppi", "cem", "ps") \
-            and type(self.optimizer).update_nominal_knots is get_registered_optimizers()[self.optimizer.name][0].update_nominal_knots
+        """The fused kernel restates the BUILT-IN reward / hooks / update: a user subclass that overrides any of them takes the
+        contract-A path (GPU rollouts + its own Python code), exactly as the reference would run it."""
+        return self.fused and self.optimizer.name in OPT_IDS and fused_optimizer_ok(self.optimizer) and fused_task_ok(self.task) \
+            and self.task.cost_params(self.system_metadata) is not None
+
+    def _can_fast_path(self) -> bool:
+        opt = self.optimizer
+        k = max(min(self.max_num_traces, opt.num_rollouts), opt.num_elites if opt.name == "cem" else 0)
+        return self.fast_path and getattr(self.engine, "supports_controller_step", False) and self.sampling == "host" and type(self.action_normalizer) is IdentityNormalizer and k <= 8 \
+            and opt.num_nodes <= 12 and legacy_stream().ok and fused_optimizer_ok(opt, sampling=True) and self._can_fuse() \
+            and (self.num_trace_sensors == 0 or self._engine_trace_width == 0 or self._trace_capture)
+
+    def _fast_iteration(self, nominal: np.ndarray, new_times: np.ndarray, lo: np.ndarray, hi: np.ndarray) -> np.ndarray:
+        """One iteration of the optimisation loop through b200mpc_controller_step; returns the new nominal knots."""
+        opt, rq = self.optimizer, self._rq
+        N, K, H, nu = opt.num_rollouts, opt.num_nodes, self.num_timesteps, self.model.nu
+        sigma = np.ascontiguousarray(opt.device_sigma())        # CEM: applies the ramp's mutation exactly as sample_control_knots does
+        self.task.pre_rollout(self.current_state)
+        ne = min(self.max_num_traces, N)
+        nts = self.num_trace_sensors
+        x0 = np.ascontiguousarray(self.current_state, dtype=np.float64)
+        nominal = np.ascontiguousarray(nominal, dtype=np.float64)
+        params = np.ascontiguousarray(self.task.cost_params(self.system_metadata), dtype=np.float64)
+        fparams = opt.fused_params()
+        fparams = np.ascontiguousarray(fparams, dtype=np.float64) if np.size(fparams) else np.zeros(1)
+        if getattr(self, "_trace_cols32", None) is None:
+            self._trace_cols32 = np.array([int(self.model.sensor_adr[s]) + p for s in self.trace_sensors for p in range(3)] or [0], dtype=np.int32)
+        out_nom = np.empty((K, nu))
+        out_sig = np.empty((K, nu)) if opt.name == "cem" else None
+        rewards = np.empty(N)
+        elite = np.empty(8, dtype=np.int32)
+        traces = np.empty((ne * nts * (H - 1), 2, 3)) if nts and ne else None
+        basis = np.empty((H, K))
+        rq.N, rq.K, rq.H, rq.optimizer, rq.spline_order, rq.n_elite = N, K, H, OPT_IDS[opt.name], SPLINE_IDS[self.spline_order], ne
+        rq.n_trace_sensors = nts if traces is not None else 0
+        rq.time, rq.dt = self.time, self.task.dt
+        rq.knot_times, rq.x0, rq.nominal, rq.sigma = new_times.ctypes.data, x0.ctypes.data, nominal.ctypes.data, sigma.ctypes.data
+        rq.lo, rq.hi, rq.cost_params, rq.opt_params = lo.ctypes.data, hi.ctypes.data, params.ctypes.data, fparams.ctypes.data
+        rq.trace_cols = self._trace_cols32.ctypes.data
+        rq.nominal_out, rq.sigma_out, rq.rewards = out_nom.ctypes.data, (out_sig.ctypes.data if out_sig is not None else None), rewards.ctypes.data
+        rq.elite_idx, rq.traces, rq.basis_out, rq.knots_out = elite.ctypes.data, (traces.ctypes.data if traces is not None else None), basis.ctypes.data, None
+        self.engine.controller_step(rq, legacy_stream(), (N - 1) * K * nu)
+        self.rewards, self._elite, self._basis = rewards, elite[:ne], basis
+        self._cand, self._cand_shape = None, (N, K)
+        self._fast_traces = traces
+        self._rollout_cache_valid = False
+        return opt.accept_fused({"nominal": out_nom, "sigma": out_sig})
 
     def update_action(self) -> None:
         assert self.current_state.shape == (self.model.nq + self.model.nv,), "Current state must be of shape (nq + nv,)"
@@ -194,13 +262,23 @@ class Controller:
 
         self.optimizer.pre_optimization(self.times, new_times)
 
-        query = self.time + self.rollout_times
-        basis = spline_basis(new_times, query, self.spline_order)  # (H, K): controls = basis @ knots
+        fast = self._can_fast_path()
+        basis = None
+        if not fast:
+            query = self.time + self.rollout_times
+            basis = spline_basis(new_times, query, self.spline_order)  # (H, K): controls = basis @ knots
         lo = self.action_normalizer.normalize(self.task.actuator_ctrlrange[:, 0])
         hi = self.action_normalizer.normalize(self.task.actuator_ctrlrange[:, 1])
         self._rollout_cache_valid = False
+        self._fast_traces = None
         i = 0
+        if fast:
+            lo, hi, new_times = np.ascontiguousarray(lo, dtype=np.float64), np.ascontiguousarray(hi, dtype=np.float64), np.ascontiguousarray(new_times)
         while i < self.max_opt_iters and not self.optimizer.stop_cond():
+            if fast:
+                nominal_knots_normalized = self._fast_iteration(nominal_knots_normalized, new_times, lo, hi)
+                i += 1
+                continue
             if self.sampling == "device" and self._can_fuse() and isinstance(self.action_normalizer, IdentityNormalizer):
                 self.task.pre_rollout(self.current_state)
                 ne = min(self.max_num_traces, self.optimizer_cfg.num_rollouts)
@@ -289,6 +367,10 @@ class Controller:
         self.all_traces_rollout_size = self.sensor_rollout_size * self.num_trace_sensors
         self.num_trace_elites = min(self.max_num_traces, self.optimizer_cfg.num_rollouts)
         ne, nts, size = self.num_trace_elites, self.num_trace_sensors, self.sensor_rollout_size
+        if getattr(self, "_fast_traces", None) is not None:  # the fast path's C call already assembled the segments
+            self.elite_indices = np.asarray(self._elite[:ne])
+            self.traces = self._fast_traces
+            return
         if getattr(self, "_rollout_cache_valid", False) or getattr(self, "_elite", None) is None:
             elite = np.argsort(self.rewards)[-ne:][::-1]
             elite_sensors = self.sensors[elite]

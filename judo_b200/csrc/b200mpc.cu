@@ -19,6 +19,14 @@
 
 using namespace b2;
 
+namespace b2host {  // host_glue.cpp
+void mt19937_normals(uint32_t* key, int* pos, double* out, size_t n);
+void assemble_candidates(const double* z, const double* nominal, const double* sigma, const double* lo, const double* hi, int N, int K, int nu,
+                         double* knots);
+int spline_basis(int order, const double* t, int K, const double* q, int H, double* B);
+void trace_segments(const double* sens, int ne, int H, int ns, const int* cols, int nts, double* out);
+}  // namespace b2host
+
 static thread_local std::string g_create_error;
 
 struct b200mpc_handle {
@@ -48,6 +56,12 @@ struct b200mpc_handle {
   // peer exchange (multi-GPU fused MPPI): local buffer + peers' buffers opened through CUDA IPC
   void* xchg = nullptr; void* xchg_peer[8] = {nullptr}; int xchg_world = 0, xchg_rank = 0; unsigned long long xchg_epoch = 0;
   double t_stage = 0, t_launch = 0, t_sync = 0, t_out = 0; long long t_calls = 0; bool timing = false;  // B200MPC_TIMING=1
+  // b200mpc_controller_step: normals of the current block, captured positions (N, H, nq) for the in-kernel elite traces, and where the
+  // last step's candidates sit in the pinned staging buffer
+  std::vector<double> zbuf, qtimes; bool step_sampled = false, step_tail_pending = false;
+  void* d_traceq = nullptr; size_t d_traceq_bytes = 0;
+  size_t cand_off = 0; int cand_N = 0, cand_K = 0;
+  std::vector<double> trace_tmp;
 };
 
 #define CK(call)                                                                                   \
@@ -124,7 +138,7 @@ extern "C" void b200mpc_destroy(b200mpc_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int g = 0; g < h->xchg_world; g++) if (h->xchg_peer[g] && g != h->xchg_rank) cudaIpcCloseMemHandle(h->xchg_peer[g]);
   cudaFree(h->xchg);
-  cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work); cudaFree(h->d_trace);
+  cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work); cudaFree(h->d_trace); cudaFree(h->d_traceq);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
 #ifdef B200MPC_WITH_LEAP
   if (h->leap) { if (getenv("B200MPC_LEAP_PROF")) leap_prof_dump(); leap_destroy(h->leap); }
@@ -374,7 +388,8 @@ extern "C" int b200mpc_plan_costs_dev(b200mpc_handle* h, const double* d_x0, con
 static int plan_step_impl(b200mpc_handle* h, const double* d_x0, const double* d_knots, int N, int K, const double* d_basis,
                           int H, const double* d_params, int optimizer, const double* opt_params, int finalize,
                           int index_offset, int n_elite, float* d_cost, double* d_reward, double* d_nominal, double* d_sigma,
-                          double* d_elite, double* d_elite_knots, double* d_rank_partial, const SampleSpec& smp, void* stream) {
+                          double* d_elite, double* d_elite_knots, double* d_rank_partial, const SampleSpec& smp, void* stream,
+                          double* d_trace_q = nullptr, double* d_elite_sens = nullptr) {
   if (!h) return 1;
   if (optimizer < 0 || optimizer > 2) return fail(h, "unknown optimizer");
   if (optimizer == B200MPC_OPT_MPPI && !(opt_params && opt_params[0] > 0)) return fail(h, "temperature must be positive");
@@ -417,6 +432,7 @@ static int plan_step_impl(b200mpc_handle* h, const double* d_x0, const double* d
   PlanEpilogue ep;
   if (make_epilogue(h, optimizer, opt_params, n_elite, N, KNU, finalize, index_offset, d_nominal, d_sigma, d_elite, d_rank_partial, st, &ep)) return 1;
   ep.elite_knots = d_elite_knots;
+  ep.trace_q = d_trace_q; ep.elite_sens = d_elite_sens;
   if (finalize == 2) {
     if (!h->xchg || !h->xchg_peer[h->xchg_world - 1] || !h->xchg_peer[0]) return fail(h, "peer exchange not set up (exchange_create/open)");
     const int kout = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
@@ -796,6 +812,132 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
     auto T4 = std::chrono::steady_clock::now();
     auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
     h->t_stage += us(T0, T1); h->t_launch += us(T1, T2); h->t_sync += us(T2, T3); h->t_out += us(T3, T4); h->t_calls++;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ Controller.update_action fast path (include/b200mpc.h)
+extern "C" int b200mpc_legacy_normals(unsigned int* mt_key, int* mt_pos, double* out, size_t n_even) {
+  if (!mt_key || !mt_pos || (!out && n_even) || (n_even & 1) || *mt_pos < 0 || *mt_pos > 624) return 1;
+  b2host::mt19937_normals(mt_key, mt_pos, out, n_even);
+  return 0;
+}
+extern "C" int b200mpc_spline_basis(int order, const double* knot_times, int K, const double* query, int H, double* basis_HK) {
+  if (!knot_times || !query || !basis_HK) return 1;
+  return b2host::spline_basis(order, knot_times, K, query, H, basis_HK);
+}
+
+extern "C" int b200mpc_last_candidates(b200mpc_handle* h, double* knots_out, int N, int K) {
+  if (!h) return 1;
+  if (!knots_out || !h->h_in || h->cand_N == 0) return fail(h, "no candidates: run b200mpc_controller_step first");
+  if (N != h->cand_N || K != h->cand_K) return fail(h, "N / K do not match the last b200mpc_controller_step");
+  memcpy(knots_out, (const char*)h->h_in + h->cand_off, (size_t)N * K * h->dims.nu * 8);
+  return 0;
+}
+
+extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* rq) {
+  if (!h) return 1;
+  if (!rq) return fail(h, "NULL request");
+  const int N = rq->N, K = rq->K, H = rq->H, optimizer = rq->optimizer;
+  if (!rq->x0 || !rq->nominal || !rq->sigma || !rq->lo || !rq->hi || !rq->cost_params || !rq->knot_times || !rq->nominal_out)
+    return fail(h, "NULL argument");
+  if (N <= 0 || H <= 0 || K <= 0) return fail(h, "N, H and K must be positive");
+  if (optimizer < 0 || optimizer > 2) return fail(h, "unknown optimizer");
+  if (optimizer == B200MPC_OPT_MPPI && !(rq->opt_params && rq->opt_params[0] > 0)) return fail(h, "temperature must be positive");
+  if (optimizer == B200MPC_OPT_CEM && !rq->opt_params) return fail(h, "CEM needs {num_elites, sigma_min, sigma_max}");
+  if (rq->n_elite < 0 || rq->n_elite > EP_MAXK) return fail(h, "n_elite must be in 0..8");
+  if (optimizer == B200MPC_OPT_CEM && ((int)rq->opt_params[0] > EP_MAXK || (int)rq->opt_params[0] <= 0)) return fail(h, "num_elites must be in 1..8 on the fast path");
+  if (rq->phase < 0 || rq->phase > 2) return fail(h, "phase must be 0, 1 or 2");
+  const int nx = h->dims.nq + h->dims.nv, nu = h->dims.nu, np = h->dims.n_cost_params, ns = h->dims.nsensordata, KNU = K * nu;
+  const size_t n = (size_t)(N - 1) * KNU;
+  if (rq->n_head < 0 || rq->n_head > 2 || (size_t)rq->n_head > n) return fail(h, "n_head must be 0..2 and <= (N-1)*K*nu");
+  if (n > (size_t)rq->n_head && (!rq->mt_key || !rq->mt_pos)) return fail(h, "NULL generator state");
+  const bool warp_task = h->task == B200MPC_TASK_LEAP_CUBE || h->task == B200MPC_TASK_FR3_PICK;
+  const int nts = rq->n_trace_sensors, ne = rq->n_elite;
+  if (nts < 0 || (nts > 0 && (!rq->trace_cols || !rq->traces))) return fail(h, "trace sensors requested without trace_cols / traces");
+  if (nts > 0 && warp_task && (!h->trace_capture || trace_width(h) != 3 * nts)) return fail(h, "enable b200mpc_set_trace_capture for the traces of this task");
+  CK(cudaSetDevice(h->device));
+
+  // ---- phase 0 / 1: draw the block of normals (head values first, then an even number straight from the generator state)
+  if (rq->phase != 2) {
+    h->zbuf.resize(n + 2);
+    double* z = h->zbuf.data();
+    for (int i = 0; i < rq->n_head; i++) z[i] = rq->head[i];
+    const size_t rem = n - (size_t)rq->n_head, gen = rem & ~(size_t)1;
+    if (gen) {
+      if (*rq->mt_pos < 0 || *rq->mt_pos > 624) return fail(h, "generator position out of range");
+      b2host::mt19937_normals(rq->mt_key, rq->mt_pos, z + rq->n_head, gen);
+    }
+    h->step_tail_pending = (rem & 1) != 0;
+    h->step_sampled = true;
+    if (rq->phase == 1) return 0;
+    if (h->step_tail_pending) { h->step_sampled = false; return fail(h, "an odd number of normals is left: sample with phase 1, draw the last one, finish with phase 2"); }
+  } else {
+    if (!h->step_sampled || h->zbuf.size() != n + 2) return fail(h, "phase 2 without a matching phase 1");
+    if (h->step_tail_pending) {
+      if (!rq->has_tail) return fail(h, "the block is one normal short: pass it as tail");
+      h->zbuf[n - 1] = rq->tail;
+    }
+  }
+  h->step_sampled = false;
+
+  // ---- stage [x0 | basis | params | knots] in pinned memory: the basis and the candidates are produced in place
+  size_t o = 0;
+  const size_t ox0 = o; o += al16((size_t)nx * 8);
+  const size_t ob = o; o += al16((size_t)H * K * 8);
+  const size_t op = o; o += al16((size_t)np * 8);
+  const size_t ok = o; o += (size_t)N * KNU * 8;
+  if (grow(h, &h->h_in, &h->h_in_bytes, o, true) || grow(h, &h->d_in, &h->d_in_bytes, o, false)) return 1;
+  char* hp = (char*)h->h_in;
+  memcpy(hp + ox0, rq->x0, (size_t)nx * 8);
+  memcpy(hp + op, rq->cost_params, (size_t)np * 8);
+  h->qtimes.resize(H);
+  for (int i = 0; i < H; i++) h->qtimes[i] = rq->time + rq->dt * (double)i;  // self.time + task.dt * arange(H) (controller.py:261)
+  if (b2host::spline_basis(rq->spline_order, rq->knot_times, K, h->qtimes.data(), H, (double*)(hp + ob))) return fail(h, "bad spline request (order / number of knots)");
+  if (rq->basis_out) memcpy(rq->basis_out, hp + ob, (size_t)H * K * 8);
+  b2host::assemble_candidates(h->zbuf.data(), rq->nominal, rq->sigma, rq->lo, rq->hi, N, K, nu, (double*)(hp + ok));
+  h->cand_off = ok; h->cand_N = N; h->cand_K = K;
+  if (rq->knots_out) memcpy(rq->knots_out, hp + ok, (size_t)N * KNU * 8);
+  CK(cudaMemcpyAsync(h->d_in, h->h_in, o, cudaMemcpyHostToDevice, h->stream));
+
+  // ---- outputs, written by the kernels straight into pinned host memory: [nominal | sigma | elite idx | elite sensors | reward]
+  const bool kernel_traces = nts > 0 && ne > 0 && !warp_task;
+  const size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_es = o_el + al16((size_t)std::max(ne, 1) * 8);
+  const size_t o_rw = o_es + (kernel_traces ? al16((size_t)ne * H * ns * 8) : 0), out_bytes = o_rw + (size_t)N * 8;
+  if (grow(h, &h->h_out, &h->h_out_bytes, out_bytes, true)) return 1;
+  if (kernel_traces && grow(h, &h->d_traceq, &h->d_traceq_bytes, (size_t)N * H * h->dims.nq * 8, false)) return 1;
+  void* dout_v = nullptr;
+  CK(cudaHostGetDevicePointer(&dout_v, h->h_out, 0));
+  char* din = (char*)h->d_in; char* dout = (char*)dout_v;
+  if (plan_step_impl(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), optimizer, rq->opt_params,
+                     /*finalize=*/1, /*index_offset=*/0, ne, nullptr, (double*)(dout + o_rw), (double*)(dout + o_nom), (double*)(dout + o_sig),
+                     (double*)(dout + o_el), nullptr, nullptr, SampleSpec{}, h->stream, kernel_traces ? (double*)h->d_traceq : nullptr,
+                     kernel_traces ? (double*)(dout + o_es) : nullptr)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  const char* ho = (const char*)h->h_out;
+  memcpy(rq->nominal_out, ho + o_nom, (size_t)KNU * 8);
+  if (rq->sigma_out && optimizer == B200MPC_OPT_CEM) memcpy(rq->sigma_out, ho + o_sig, (size_t)KNU * 8);
+  int el[EP_MAXK];
+  for (int i = 0; i < ne; i++) { el[i] = (int)((const double*)(ho + o_el))[i]; if (rq->elite_idx) rq->elite_idx[i] = el[i]; }
+  if (rq->rewards) memcpy(rq->rewards, ho + o_rw, (size_t)N * 8);
+  if (nts > 0 && ne > 0) {
+    if (kernel_traces) {
+      b2host::trace_segments((const double*)(ho + o_es), ne, H, ns, rq->trace_cols, nts, rq->traces);
+    } else {
+      // warp-per-rollout tasks: the fused kernel captured every rollout's trace sensors (N, H, 3 nts); fetch the elites' rows
+      const int nt = 3 * nts;
+      const size_t row = (size_t)H * nt * 8;
+      h->trace_tmp.resize((size_t)ne * H * nt);
+      for (int i = 0; i < ne; i++) {
+        if (el[i] < 0 || el[i] >= h->trace_N) return fail(h, "elite index out of range");
+        CK(cudaMemcpyAsync((char*)h->trace_tmp.data() + (size_t)i * row, (const char*)h->d_trace + (size_t)el[i] * row, row, cudaMemcpyDeviceToHost, h->stream));
+      }
+      CK(cudaStreamSynchronize(h->stream));
+      int cols[3 * 16];
+      if (nt > 48) return fail(h, "too many trace sensors");
+      for (int i = 0; i < nt; i++) cols[i] = i;
+      b2host::trace_segments(h->trace_tmp.data(), ne, H, nt, cols, nts, rq->traces);
+    }
   }
   return 0;
 }

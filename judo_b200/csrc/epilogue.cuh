@@ -31,6 +31,11 @@ struct PlanEpilogue {
   double* sigma;          // [KNU]  (finalize, CEM)
   double* elite;          // [k] global indices as doubles, -1 padded (finalize)
   double* elite_knots;    // [k][KNU] the elite candidates themselves, or NULL (finalize)
+  // elite traces (thread-per-rollout kernels, finalize == 1): with trace_q set every rollout keeps its positions after each step
+  // (N, H, NQ) in HBM, and the last warp evaluates the sensors of the k elite rollouts from them into elite_sens (k, H, NS) — what
+  // Controller.update_traces reads (controller.py:323-363) without a second launch that re-simulates the elites
+  double* trace_q;
+  double* elite_sens;
   double* rank_mppi;      // [2+KNU]            (!finalize)
   double* rank_topk;      // CEM: [k][2+KNU]; PS: [1][2+KNU]   (!finalize)
   // peer exchange (finalize == 2, MPPI): the last warp writes this rank's partial straight into every peer's exchange buffer
@@ -103,8 +108,10 @@ __device__ inline bool peer_signal_and_wait(const PlanEpilogue& ep, int lane) {
 // Final stage, run by one full warp after all partials are visible.  knots: this launch's (N, KNU) candidates.
 // Loads are issued in batches of independent __ldcg's (the stage is one warp deep: L2 latency, not bandwidth, is the cost).
 template <int MAXKNU>
-__device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KNU, const double* __restrict__ knots) {
+__device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KNU, const double* __restrict__ knots,
+                                      long long (&elite_local)[EP_MAXK], int& n_elite_local) {
   const int lane = threadIdx.x & 31;
+  n_elite_local = 0;
   if (ep.optimizer == EP_MPPI) {
     const int stride = 2 + KNU;
     double b = INFINITY;
@@ -198,6 +205,9 @@ __device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KN
         }
       }
     }
+#pragma unroll
+    for (int e = 0; e < EP_MAXK; e++) elite_local[e] = ei[e];
+    n_elite_local = ne;
     // PS: first maximum (ties -> lower index)
     double pr = -INFINITY; long long pi = -1;
     if (ep.optimizer == EP_PS) {
@@ -300,8 +310,10 @@ __device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KN
 }
 
 // Publish this warp's partial (already written by the caller), take a ticket, and run the final stage in the last warp.
+// Returns true in the warp that ran the final stage; elite_local / n_elite_local then hold the LOCAL indices of the listed elites.
 template <int MAXKNU>
-__device__ inline void epilogue_commit(const PlanEpilogue& ep, int nparts, int KNU, const double* __restrict__ knots) {
+__device__ inline bool epilogue_commit(const PlanEpilogue& ep, int nparts, int KNU, const double* __restrict__ knots,
+                                       long long (&elite_local)[EP_MAXK], int& n_elite_local) {
   __threadfence();
   __syncwarp();
   unsigned t = 0;
@@ -309,16 +321,19 @@ __device__ inline void epilogue_commit(const PlanEpilogue& ep, int nparts, int K
   t = __shfl_sync(0xffffffffu, t, 0);
   if (t == (unsigned)nparts - 1) {
     __threadfence();
-    epilogue_final<MAXKNU>(ep, nparts, KNU, knots);
+    epilogue_final<MAXKNU>(ep, nparts, KNU, knots, elite_local, n_elite_local);
     __syncwarp();
     if ((threadIdx.x & 31) == 0) *ep.ticket = 0;
+    return true;
   }
+  return false;
 }
 
 // Thread-per-rollout flavour: lane owns rollout `n` (valid or not) with reward r and knots kn[0..KNU).
 template <int MAXKNU>
-__device__ inline void epilogue_thread_per_rollout(const PlanEpilogue& ep, bool valid, int n_local, double r, const double (&kn)[MAXKNU],
-                                                   int KNU, int warp_global, int nwarps, const double* __restrict__ knots) {
+__device__ inline bool epilogue_thread_per_rollout(const PlanEpilogue& ep, bool valid, int n_local, double r, const double (&kn)[MAXKNU],
+                                                   int KNU, int warp_global, int nwarps, const double* __restrict__ knots,
+                                                   long long (&elite_local)[EP_MAXK], int& n_elite_local) {
   const int lane = threadIdx.x & 31;
   if (ep.optimizer == EP_MPPI) {
     const double c = valid ? -r : INFINITY;
@@ -349,7 +364,7 @@ __device__ inline void epilogue_thread_per_rollout(const PlanEpilogue& ep, bool 
     warp_best(br, bi, false);
     if (lane == 0) { out[2 * ep.k] = bi >= 0 ? br : -INFINITY; out[2 * ep.k + 1] = (double)bi; }
   }
-  epilogue_commit<MAXKNU>(ep, nwarps, KNU, knots);
+  return epilogue_commit<MAXKNU>(ep, nwarps, KNU, knots, elite_local, n_elite_local);
 }
 
 }  // namespace b2

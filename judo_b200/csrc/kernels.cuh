@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
           }
         }
         Task::step(c, s, u, nullptr);
+        if (ep.trace_q) {  // positions after step t: the elites' trace sensors are evaluated from them by the last warp (below)
+#pragma unroll
+          for (int j = 0; j < Task::NQ; j++) ep.trace_q[((size_t)n * H + t) * Task::NQ + j] = s.q[j];
+        }
         double ct = Task::cost(cp, s, u);
         total += ct;
         if (cost_NH) sC[(size_t)tid * (H + 1) + t] = (float)ct;
@@ -104,9 +108,30 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
       reward = Task::finish(total, H);
       reward_N[n] = reward;
     }
-    if (ep.optimizer != EP_NONE || ep.k > 0)
-      epilogue_thread_per_rollout<MAXK * NU>(ep, n < N, n, reward, kn, K * NU, blockIdx.x * (nthr >> 5) + (tid >> 5), gridDim.x * (nthr >> 5),
-                                             smp.enabled ? smp.knots_out : in);
+    if (ep.optimizer != EP_NONE || ep.k > 0) {
+      long long el[EP_MAXK];
+      int ne = 0;
+      const bool last = epilogue_thread_per_rollout<MAXK * NU>(ep, n < N, n, reward, kn, K * NU, blockIdx.x * (nthr >> 5) + (tid >> 5),
+                                                               gridDim.x * (nthr >> 5), smp.enabled ? smp.knots_out : in, el, ne);
+      if (last && ep.elite_sens && ep.trace_q) {
+        // T1 (controller.py:323-363): sensors of the elite rollouts at every step, from the captured positions.  MuJoCo evaluates
+        // position sensors in mj_forward, i.e. at the PRE-step state: step 0 sees x0, step t the positions after step t-1.
+        // (Every rollout's trace_q stores precede its warp's ticket (threadfence + atomic), so they are visible here; __ldcg reads L2.)
+        const int lane = tid & 31;
+        for (int idx = lane; idx < ne * H; idx += 32) {
+          const int e = idx / H, t = idx - e * H;
+          long long r = el[0];
+#pragma unroll
+          for (int i = 1; i < EP_MAXK; i++) if (i == e) r = el[i];
+          double q[Task::NQ], sens[NS];
+#pragma unroll
+          for (int j = 0; j < Task::NQ; j++) q[j] = t == 0 ? x0[j] : __ldcg(ep.trace_q + ((size_t)r * H + (t - 1)) * Task::NQ + j);
+          Task::sensors(c, q, sens);
+#pragma unroll
+          for (int j = 0; j < NS; j++) ep.elite_sens[((size_t)e * H + t) * NS + j] = sens[j];
+        }
+      }
+    }
     if (cost_NH) {
       __syncthreads();
       // coalesced write-back of the block's (nblk, H) tile: consecutive threads write consecutive floats

@@ -34,15 +34,23 @@ struct CartpoleTask {
   }
   __device__ static inline void store(const State& s, double* x) { x[0] = s.q[0]; x[1] = s.q[1]; x[2] = s.v[0]; x[3] = s.v[1]; }
 
+  // the two framepos sensors as functions of the positions (sn, cs = sincos(q[1]))
+  __device__ static inline void sensors_sc(const Consts& c, double q0, double sn, double cs, double* sens) {
+    sens[0] = q0 + c.site_cart[0]; sens[1] = c.site_cart[1]; sens[2] = c.site_cart[2];
+    sens[3] = q0 + cs * c.site_pole[0] + sn * c.site_pole[2];
+    sens[4] = c.site_pole[1];
+    sens[5] = -sn * c.site_pole[0] + cs * c.site_pole[2];
+  }
+  __device__ static inline void sensors(const Consts& c, const double* q, double* sens) {
+    double sn, cs;
+    sincos(q[1], &sn, &cs);
+    sensors_sc(c, q[0], sn, cs, sens);
+  }
+
   // cart: slide along x; pole: hinge about +y at the cart origin, COM at (0,0,l) in the pole frame.
   __device__ static inline void step(const Consts& c, State& s, const double* u, double* sens) {
     const double sn = s.sn, cs = s.cs;
-    if (sens) {  // framepos sensors are evaluated in mj_forward, i.e. at the pre-step state
-      sens[0] = s.q[0] + c.site_cart[0]; sens[1] = c.site_cart[1]; sens[2] = c.site_cart[2];
-      sens[3] = s.q[0] + cs * c.site_pole[0] + sn * c.site_pole[2];
-      sens[4] = c.site_pole[1];
-      sens[5] = -sn * c.site_pole[0] + cs * c.site_pole[2];
-    }
+    if (sens) sensors_sc(c, s.q[0], sn, cs, sens);  // framepos sensors are evaluated in mj_forward, i.e. at the pre-step state
     const double h = c.dt, mp = c.m_pole, l = c.l_pole;
     const double m00 = c.m_cart + mp, m01 = mp * l * cs, m11 = c.iyy_pole + mp * l * l;
     // passive (joint damping), bias (Coriolis + gravity), actuation (position servo with ctrl/force clamps)
@@ -139,11 +147,13 @@ struct CylinderPushTask {
     for (int i = 0; i < 4; i++) { x[i] = s.q[i]; x[4 + i] = s.v[i]; }
   }
 
+  __device__ static inline void sensors(const Consts& c, const double* q, double* sens) {
+    sens[0] = q[0] + c.site_pusher[0]; sens[1] = q[1] + c.site_pusher[1]; sens[2] = c.site_pusher[2];
+    sens[3] = q[2] + c.site_cart[0]; sens[4] = q[3] + c.site_cart[1]; sens[5] = c.site_cart[2];
+  }
+
   __device__ static inline void step(const Consts& c, State& s, const double* u, double* sens) {
-    if (sens) {
-      sens[0] = s.q[0] + c.site_pusher[0]; sens[1] = s.q[1] + c.site_pusher[1]; sens[2] = c.site_pusher[2];
-      sens[3] = s.q[2] + c.site_cart[0]; sens[4] = s.q[3] + c.site_cart[1]; sens[5] = c.site_cart[2];
-    }
+    if (sens) sensors(c, s.q, sens);
     const double h = c.dt;
     if (!s.ready) {
 #pragma unroll

@@ -39,6 +39,19 @@ _registered_optimizers: dict[str, tuple[Type[Optimizer], Type[OptimizerConfig]]]
 }
 
 
+BUILTIN_OPTIMIZERS: tuple[Type[Optimizer], ...] = (CrossEntropyMethod, MPPI, PredictiveSampling)
+
+
+def fused_optimizer_ok(opt: Optimizer, sampling: bool = False) -> bool:
+    """True when the optimizer's update (and, with ``sampling``, its sampling) is the built-in implementation the fused kernel / the
+    C-side sampler restates; a subclass overriding them keeps its own Python code path."""
+    base = next((c for c in type(opt).__mro__ if c in BUILTIN_OPTIMIZERS), None)
+    if base is None:
+        return False
+    names = ["update_nominal_knots", "fused_params", "accept_fused"] + (["sample_control_knots", "device_sigma"] if sampling else [])
+    return all(getattr(type(opt), m) is getattr(base, m) for m in names)
+
+
 def get_registered_optimizers() -> dict[str, tuple[Type[Optimizer], Type[OptimizerConfig]]]:
     return _registered_optimizers
 

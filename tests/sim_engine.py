@@ -21,6 +21,7 @@ _OPT = {"mppi": 0, "cem": 1, "ps": 2}
 
 
 class SimEngine(Engine):
+    supports_controller_step = False  # the emulator covers the device code; the C-side host glue has its own CPU tests
     def __init__(self, task: str, num_rollouts: int, device: int = 0, consts: np.ndarray | None = None) -> None:  # noqa: ARG002
         self._sim = warpsim.lib()
         self.task = task

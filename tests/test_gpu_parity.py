@@ -167,11 +167,16 @@ def test_optimizer_updates_sizes_and_edges(engines, N, KNU):
 
 
 @pytest.mark.parametrize("tag", ["cartpole_ps", "cartpole_mppi", "cylinder_push_cem", "leap_cube_mppi"])
-@pytest.mark.parametrize("fused", [True, False])
-def test_controller_reproduces_reference_plan_steps(golden, temp_np_seed, tag, fused):
-    """End to end through the plugin surface: same seed as the reference Controller run -> same candidates (bit exact),
-    rewards / nominal knots / traces within tolerance, for three consecutive plan steps."""
+@pytest.mark.parametrize("mode", ["fast", "fused", "contract_a"])
+def test_controller_reproduces_reference_plan_steps(golden, temp_np_seed, tag, mode):
+    """End to end through the plugin surface: same seed as the reference Controller run -> same candidates (bit exact in the first
+    step, where the nominal is the warm start; afterwards they inherit the GPU update's rounding), rewards / nominal knots / traces
+    within tolerance, for three consecutive plan steps.  mode: "fast" = update_action's default (one b200mpc_controller_step call per
+    iteration: C-side sampling from numpy's stream, clip, basis, fused kernel, traces), "fused" = NumPy glue + Engine.plan_step,
+    "contract_a" = the drop-in RolloutBackend path (rollout -> Task.reward -> update_nominal_knots)."""
     from judo_b200.controller import make_controller
+
+    fused = mode != "contract_a"
 
     g = golden("plan_" + tag)
     task, opt, N, horizon, seed, order, max_traces = g["meta"]
@@ -180,6 +185,8 @@ def test_controller_reproduces_reference_plan_steps(golden, temp_np_seed, tag, f
         ctrl.optimizer_cfg.num_rollouts = int(N)
         ctrl.controller_cfg.horizon = float(horizon)
         ctrl.fused = fused
+        ctrl.fast_path = mode == "fast"
+        assert ctrl._can_fast_path() == (mode == "fast")
         # the golden run seeded the RNG and then built its Controller, whose reset() calls Task.reset() once
         np.random.seed(int(seed))
         ctrl.reset()
@@ -195,6 +202,8 @@ def test_controller_reproduces_reference_plan_steps(golden, temp_np_seed, tag, f
             np.testing.assert_allclose(ctrl.nominal_knots, g[f"p{p}_nominal_in"], rtol=0, atol=1e-9)
             ctrl.update_action()
             np.testing.assert_allclose(ctrl.candidate_knots, g[f"p{p}_candidate_knots"], rtol=0, atol=1e-9)
+            if p == 0:
+                np.testing.assert_array_equal(ctrl.candidate_knots, g["p0_candidate_knots"])
             np.testing.assert_allclose(ctrl.rewards, g[f"p{p}_rewards"], rtol=tol, atol=tol)
             np.testing.assert_allclose(ctrl.nominal_knots, g[f"p{p}_nominal_out"], rtol=0, atol=max(tol, 1e-4 if task == "leap_cube" else 0))
             np.testing.assert_array_equal(ctrl.times, g[f"p{p}_times_out"])
