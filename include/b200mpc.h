@@ -130,6 +130,8 @@ typedef struct {
   int n_head;                 /* 0..2 normals already drawn by the caller (head[]) */
   int has_tail;               /* phase 2: `tail` is the last normal of the block */
   int n_trace_sensors;        /* framepos trace sensors per elite (0: no traces) */
+  int speculate;              /* 1: while the GPU runs this step, draw the NEXT step's block of normals from a COPY of the generator state */
+  int use_speculated;         /* 1: b200mpc_controller_speculation() just returned 1 for the (n - n_head) & ~1 normals after the head */
   double time, dt;
   double head[2], tail;
   const double* knot_times;   /* (K) */
@@ -153,6 +155,19 @@ typedef struct {
   double* knots_out;          /* (N, K, nu) the candidates (NULL: read them later with b200mpc_last_candidates) */
 } b200mpc_step_request;
 int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* req);
+/* Speculative sampling (hides the sampling time of large blocks behind the GPU's rollout time): with req->speculate the call above draws,
+ * while it waits for the GPU, the block of normals the NEXT step will need — from a private copy of the generator state, numpy's own
+ * state is not touched.  The noise does not depend on the nominal (judo/optimizers/mppi.py:58), so if nobody drew from or re-seeded the
+ * generator in between, the next step would draw exactly these values.  This function says whether that is the case: 1 when a block of
+ * n normals is held that was drawn from exactly the state the generator is in NOW (624 key words and the position compare equal).
+ * The block covers what the next step would ask THIS library to draw, i.e. everything after its head values: all n normals when the
+ * generator's gaussian cache is empty after this step, (n - 1) & ~1 when this step ended with a tail drawn through numpy (the cache
+ * then holds that pair's second value, which becomes the next head).  A caller therefore asks twice: before drawing head values with
+ * the full block size, and after drawing them with (n - n_head) & ~1.  b200mpc_controller_step with use_speculated = 1 installs the
+ * advanced state into the generator and uses the block; otherwise it is dropped and the step samples as usual.  The stream numpy's
+ * users see is identical either way: a draw or re-seed in between changes the key / position (a lone cached gaussian being consumed
+ * does not, but then the head draw moves the state and the second query fails). */
+int b200mpc_controller_speculation(b200mpc_handle* h, const unsigned int* mt_key, const int* mt_pos, size_t n);
 /* The candidates of the last b200mpc_controller_step, (N, K, nu), copied out of the pinned staging buffer. */
 int b200mpc_last_candidates(b200mpc_handle* h, double* knots_out, int N, int K);
 /* Host-only helpers behind the call above, exported for the parity tests (no GPU needed):

@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200mpc_elite_traces": (_i, [_vp, _vp, _i, _i, _vp]),
     "b200mpc_controller_step": (_i, [_vp, _vp]),
     "b200mpc_last_candidates": (_i, [_vp, _vp, _i, _i]),
+    "b200mpc_controller_speculation": (_i, [_vp, _vp, _vp, ctypes.c_size_t]),
     "b200mpc_legacy_normals": (_i, [_vp, _vp, _vp, ctypes.c_size_t]),
     "b200mpc_spline_basis": (_i, [_i, _vp, _i, _vp, _i, _vp]),
 }
@@ -66,7 +67,7 @@ class StepRequest(ctypes.Structure):
     """b200mpc_step_request (include/b200mpc.h)."""
 
     _fields_ = [("N", _i), ("K", _i), ("H", _i), ("optimizer", _i), ("spline_order", _i), ("n_elite", _i), ("phase", _i), ("n_head", _i),
-                ("has_tail", _i), ("n_trace_sensors", _i), ("time", _d), ("dt", _d), ("head", _d * 2), ("tail", _d),
+                ("has_tail", _i), ("n_trace_sensors", _i), ("speculate", _i), ("use_speculated", _i), ("time", _d), ("dt", _d), ("head", _d * 2), ("tail", _d),
                 ("knot_times", _vp), ("x0", _vp), ("nominal", _vp), ("sigma", _vp), ("lo", _vp), ("hi", _vp), ("cost_params", _vp),
                 ("opt_params", _vp), ("trace_cols", _vp), ("mt_key", _vp), ("mt_pos", _vp),
                 ("nominal_out", _vp), ("sigma_out", _vp), ("rewards", _vp), ("elite_idx", _vp), ("traces", _vp), ("basis_out", _vp),

@@ -192,31 +192,40 @@ class Controller:
     def _can_fuse(self) -> bool:
         """The fused kernel restates the BUILT-IN reward / hooks / update: a user subclass that overrides any of them takes the
         contract-A path (GPU rollouts + its own Python code), exactly as the reference would run it."""
-        return self.fused and self.optimizer.name in OPT_IDS and fused_optimizer_ok(self.optimizer) and fused_task_ok(self.task) \
-            and self.task.cost_params(self.system_metadata) is not None
+        key = (type(self.task), type(self.optimizer))
+        if getattr(self, "_fuse_key", None) != key:  # class identities only change when task / optimizer are swapped
+            self._fuse_key = key
+            self._fuse_ok = self.optimizer.name in OPT_IDS and fused_optimizer_ok(self.optimizer) and fused_task_ok(self.task)
+            self._fast_ok = self._fuse_ok and fused_optimizer_ok(self.optimizer, sampling=True)
+        return self.fused and self._fuse_ok and self.task.cost_params(self.system_metadata) is not None
 
     def _can_fast_path(self) -> bool:
         opt = self.optimizer
         k = max(min(self.max_num_traces, opt.num_rollouts), opt.num_elites if opt.name == "cem" else 0)
-        return self.fast_path and getattr(self.engine, "supports_controller_step", False) and self.sampling == "host" and type(self.action_normalizer) is IdentityNormalizer and k <= 8 \
-            and opt.num_nodes <= 12 and legacy_stream().ok and fused_optimizer_ok(opt, sampling=True) and self._can_fuse() \
-            and (self.num_trace_sensors == 0 or self._engine_trace_width == 0 or self._trace_capture)
+        return self.fast_path and getattr(self.engine, "supports_controller_step", False) and self.sampling == "host" and \
+            type(self.action_normalizer) is IdentityNormalizer and k <= 8 and opt.num_nodes <= 12 and legacy_stream().ok and \
+            self._can_fuse() and self._fast_ok and (self.num_trace_sensors == 0 or self._engine_trace_width == 0 or self._trace_capture)
 
-    def _fast_iteration(self, nominal: np.ndarray, new_times: np.ndarray, lo: np.ndarray, hi: np.ndarray) -> np.ndarray:
+    def _fast_iteration(self, nominal: np.ndarray, new_times: np.ndarray) -> np.ndarray:
         """One iteration of the optimisation loop through b200mpc_controller_step; returns the new nominal knots."""
         opt, rq = self.optimizer, self._rq
         N, K, H, nu = opt.num_rollouts, opt.num_nodes, self.num_timesteps, self.model.nu
-        sigma = np.ascontiguousarray(opt.device_sigma())        # CEM: applies the ramp's mutation exactly as sample_control_knots does
+        sigma = opt.device_sigma()        # (K, nu) contiguous; CEM: applies the ramp's mutation exactly as sample_control_knots does
         self.task.pre_rollout(self.current_state)
         ne = min(self.max_num_traces, N)
         nts = self.num_trace_sensors
         x0 = np.ascontiguousarray(self.current_state, dtype=np.float64)
         nominal = np.ascontiguousarray(nominal, dtype=np.float64)
+        new_times = np.ascontiguousarray(new_times, dtype=np.float64)
         params = np.ascontiguousarray(self.task.cost_params(self.system_metadata), dtype=np.float64)
         fparams = opt.fused_params()
         fparams = np.ascontiguousarray(fparams, dtype=np.float64) if np.size(fparams) else np.zeros(1)
-        if getattr(self, "_trace_cols32", None) is None:
+        if getattr(self, "_fast_task", None) is not self.task:  # per-task constants: clip range, trace columns
+            self._fast_task = self.task
+            rng = self.task.actuator_ctrlrange
+            self._fast_lo, self._fast_hi = np.ascontiguousarray(rng[:, 0], dtype=np.float64), np.ascontiguousarray(rng[:, 1], dtype=np.float64)
             self._trace_cols32 = np.array([int(self.model.sensor_adr[s]) + p for s in self.trace_sensors for p in range(3)] or [0], dtype=np.int32)
+            rq.lo, rq.hi, rq.trace_cols = self._fast_lo.ctypes.data, self._fast_hi.ctypes.data, self._trace_cols32.ctypes.data
         out_nom = np.empty((K, nu))
         out_sig = np.empty((K, nu)) if opt.name == "cem" else None
         rewards = np.empty(N)
@@ -227,8 +236,7 @@ class Controller:
         rq.n_trace_sensors = nts if traces is not None else 0
         rq.time, rq.dt = self.time, self.task.dt
         rq.knot_times, rq.x0, rq.nominal, rq.sigma = new_times.ctypes.data, x0.ctypes.data, nominal.ctypes.data, sigma.ctypes.data
-        rq.lo, rq.hi, rq.cost_params, rq.opt_params = lo.ctypes.data, hi.ctypes.data, params.ctypes.data, fparams.ctypes.data
-        rq.trace_cols = self._trace_cols32.ctypes.data
+        rq.cost_params, rq.opt_params = params.ctypes.data, fparams.ctypes.data
         rq.nominal_out, rq.sigma_out, rq.rewards = out_nom.ctypes.data, (out_sig.ctypes.data if out_sig is not None else None), rewards.ctypes.data
         rq.elite_idx, rq.traces, rq.basis_out, rq.knots_out = elite.ctypes.data, (traces.ctypes.data if traces is not None else None), basis.ctypes.data, None
         self.engine.controller_step(rq, legacy_stream(), (N - 1) * K * nu)
@@ -267,16 +275,15 @@ class Controller:
         if not fast:
             query = self.time + self.rollout_times
             basis = spline_basis(new_times, query, self.spline_order)  # (H, K): controls = basis @ knots
-        lo = self.action_normalizer.normalize(self.task.actuator_ctrlrange[:, 0])
-        hi = self.action_normalizer.normalize(self.task.actuator_ctrlrange[:, 1])
+        if not fast:
+            lo = self.action_normalizer.normalize(self.task.actuator_ctrlrange[:, 0])
+            hi = self.action_normalizer.normalize(self.task.actuator_ctrlrange[:, 1])
         self._rollout_cache_valid = False
         self._fast_traces = None
         i = 0
-        if fast:
-            lo, hi, new_times = np.ascontiguousarray(lo, dtype=np.float64), np.ascontiguousarray(hi, dtype=np.float64), np.ascontiguousarray(new_times)
         while i < self.max_opt_iters and not self.optimizer.stop_cond():
             if fast:
-                nominal_knots_normalized = self._fast_iteration(nominal_knots_normalized, new_times, lo, hi)
+                nominal_knots_normalized = self._fast_iteration(nominal_knots_normalized, new_times)
                 i += 1
                 continue
             if self.sampling == "device" and self._can_fuse() and isinstance(self.action_normalizer, IdentityNormalizer):

@@ -55,13 +55,16 @@ struct b200mpc_handle {
   bool zero_copy_now = false;  // set for the duration of a zero-copy plan_step
   // peer exchange (multi-GPU fused MPPI): local buffer + peers' buffers opened through CUDA IPC
   void* xchg = nullptr; void* xchg_peer[8] = {nullptr}; int xchg_world = 0, xchg_rank = 0; unsigned long long xchg_epoch = 0;
-  double t_stage = 0, t_launch = 0, t_sync = 0, t_out = 0; long long t_calls = 0; bool timing = false;  // B200MPC_TIMING=1
+  double t_stage = 0, t_launch = 0, t_sync = 0, t_out = 0, t_spec = 0; long long t_calls = 0; bool timing = false;  // B200MPC_TIMING=1
   // b200mpc_controller_step: normals of the current block, captured positions (N, H, nq) for the in-kernel elite traces, and where the
   // last step's candidates sit in the pinned staging buffer
   std::vector<double> zbuf, qtimes; bool step_sampled = false, step_tail_pending = false;
   void* d_traceq = nullptr; size_t d_traceq_bytes = 0;
   size_t cand_off = 0; int cand_N = 0, cand_K = 0;
   std::vector<double> trace_tmp;
+  // speculative sampling: the next block of normals, the generator state it was drawn from and the state after it
+  std::vector<double> znext; size_t znext_n = 0; bool znext_valid = false;
+  uint32_t snap_key[624]; int snap_pos = 0; uint32_t adv_key[624]; int adv_pos = 0;
 };
 
 #define CK(call)                                                                                   \
@@ -132,8 +135,8 @@ extern "C" int b200mpc_create(b200mpc_handle** out, int task_id, const double* c
 extern "C" void b200mpc_destroy(b200mpc_handle* h) {
   if (!h) return;
   if (h->timing && h->t_calls)
-    fprintf(stderr, "b200mpc plan_step host timing over %lld calls (us): stage %.1f launch %.1f sync(wait for GPU) %.1f copy-out %.1f\n", h->t_calls,
-            h->t_stage / h->t_calls, h->t_launch / h->t_calls, h->t_sync / h->t_calls, h->t_out / h->t_calls);
+    fprintf(stderr, "b200mpc host timing over %lld calls (us) [plan_step: stage|launch|wait|copy-out; controller_step: sample|assemble|h2d+launch|wait (+ speculative sampling before the wait)]: %.1f %.1f %.1f %.1f (+ %.1f)\n", h->t_calls,
+            h->t_stage / h->t_calls, h->t_launch / h->t_calls, h->t_sync / h->t_calls, h->t_out / h->t_calls, h->t_spec / h->t_calls);
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int g = 0; g < h->xchg_world; g++) if (h->xchg_peer[g] && g != h->xchg_rank) cudaIpcCloseMemHandle(h->xchg_peer[g]);
@@ -835,6 +838,11 @@ extern "C" int b200mpc_last_candidates(b200mpc_handle* h, double* knots_out, int
   return 0;
 }
 
+extern "C" int b200mpc_controller_speculation(b200mpc_handle* h, const unsigned int* mt_key, const int* mt_pos, size_t n) {
+  if (!h || !mt_key || !mt_pos) return 0;
+  return h->znext_valid && h->znext_n == n && *mt_pos == h->snap_pos && memcmp(mt_key, h->snap_key, sizeof(h->snap_key)) == 0;
+}
+
 extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* rq) {
   if (!h) return 1;
   if (!rq) return fail(h, "NULL request");
@@ -857,6 +865,7 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
   if (nts < 0 || (nts > 0 && (!rq->trace_cols || !rq->traces))) return fail(h, "trace sensors requested without trace_cols / traces");
   if (nts > 0 && warp_task && (!h->trace_capture || trace_width(h) != 3 * nts)) return fail(h, "enable b200mpc_set_trace_capture for the traces of this task");
   CK(cudaSetDevice(h->device));
+  auto T0 = std::chrono::steady_clock::now();
 
   // ---- phase 0 / 1: draw the block of normals (head values first, then an even number straight from the generator state)
   if (rq->phase != 2) {
@@ -864,10 +873,17 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
     double* z = h->zbuf.data();
     for (int i = 0; i < rq->n_head; i++) z[i] = rq->head[i];
     const size_t rem = n - (size_t)rq->n_head, gen = rem & ~(size_t)1;
-    if (gen) {
+    if (rq->use_speculated) {
+      // the `gen` normals that follow the head values were drawn during the previous step's GPU time (see below)
+      if (!gen || !b200mpc_controller_speculation(h, rq->mt_key, rq->mt_pos, gen)) return fail(h, "the speculated block does not match the generator state");
+      memcpy(z + rq->n_head, h->znext.data(), gen * sizeof(double));
+      memcpy(rq->mt_key, h->adv_key, sizeof(h->adv_key));  // the generator now stands where drawing them would have left it
+      *rq->mt_pos = h->adv_pos;
+    } else if (gen) {
       if (*rq->mt_pos < 0 || *rq->mt_pos > 624) return fail(h, "generator position out of range");
       b2host::mt19937_normals(rq->mt_key, rq->mt_pos, z + rq->n_head, gen);
     }
+    h->znext_valid = false;
     h->step_tail_pending = (rem & 1) != 0;
     h->step_sampled = true;
     if (rq->phase == 1) return 0;
@@ -880,6 +896,7 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
     }
   }
   h->step_sampled = false;
+  auto T1 = std::chrono::steady_clock::now();
 
   // ---- stage [x0 | basis | params | knots] in pinned memory: the basis and the candidates are produced in place
   size_t o = 0;
@@ -898,6 +915,7 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
   b2host::assemble_candidates(h->zbuf.data(), rq->nominal, rq->sigma, rq->lo, rq->hi, N, K, nu, (double*)(hp + ok));
   h->cand_off = ok; h->cand_N = N; h->cand_K = K;
   if (rq->knots_out) memcpy(rq->knots_out, hp + ok, (size_t)N * KNU * 8);
+  auto T2 = std::chrono::steady_clock::now();
   CK(cudaMemcpyAsync(h->d_in, h->h_in, o, cudaMemcpyHostToDevice, h->stream));
 
   // ---- outputs, written by the kernels straight into pinned host memory: [nominal | sigma | elite idx | elite sensors | reward]
@@ -913,7 +931,33 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
                      /*finalize=*/1, /*index_offset=*/0, ne, nullptr, (double*)(dout + o_rw), (double*)(dout + o_nom), (double*)(dout + o_sig),
                      (double*)(dout + o_el), nullptr, nullptr, SampleSpec{}, h->stream, kernel_traces ? (double*)h->d_traceq : nullptr,
                      kernel_traces ? (double*)(dout + o_es) : nullptr)) return 1;
+  auto T3 = std::chrono::steady_clock::now();
+  // ---- while the GPU works: the normals the next step will ask this routine for, from a COPY of the generator state
+  // (b200mpc_controller_speculation).  What the next step asks for follows from the generator's gaussian cache, which is known here:
+  //   this step ended without a tail -> cache empty -> the next block (n even) is drawn here in full, no head values;
+  //   this step drew a tail through numpy -> cache occupied -> the next step's head is that cached value (no state change), then
+  //   (n - 1) & ~1 normals from here, then its own tail.
+  h->znext_valid = false;
+  {
+    const size_t cnt = !h->step_tail_pending ? ((n & 1) == 0 ? n : 0) : ((n - 1) & ~(size_t)1);
+    if (rq->speculate && cnt >= 2 && rq->mt_key && rq->mt_pos && *rq->mt_pos >= 0 && *rq->mt_pos <= 624) {
+      memcpy(h->snap_key, rq->mt_key, sizeof(h->snap_key));
+      h->snap_pos = *rq->mt_pos;
+      memcpy(h->adv_key, h->snap_key, sizeof(h->adv_key));
+      h->adv_pos = h->snap_pos;
+      h->znext.resize(cnt);
+      b2host::mt19937_normals(h->adv_key, &h->adv_pos, h->znext.data(), cnt);
+      h->znext_n = cnt;
+      h->znext_valid = true;
+    }
+  }
+  auto T3b = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(h->stream));
+  if (h->timing) {  // B200MPC_TIMING=1: sample | assemble (basis, candidates) | H2D + launch | wait for the GPU
+    auto T4 = std::chrono::steady_clock::now();
+    auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    h->t_stage += us(T0, T1); h->t_launch += us(T1, T2); h->t_sync += us(T2, T3); h->t_out += us(T3b, T4); h->t_spec += us(T3, T3b); h->t_calls++;
+  }
   const char* ho = (const char*)h->h_out;
   memcpy(rq->nominal_out, ho + o_nom, (size_t)KNU * 8);
   if (rq->sigma_out && optimizer == B200MPC_OPT_CEM) memcpy(rq->sigma_out, ho + o_sig, (size_t)KNU * 8);

@@ -25,6 +25,20 @@
 
 namespace b2 {
 
+#ifndef B2_HOST_SIM
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs tens of microseconds per call: raise the limit once per (device, kernel slot)
+// and only again when a launch needs more.  slot: a small caller-chosen id per kernel instantiation.
+inline cudaError_t set_max_dynamic_smem_once(const void* func, int slot, size_t smem) {
+  static size_t have[16][8] = {{0}};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 16 && slot >= 0 && slot < 8 && have[dev][slot] >= smem) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && dev >= 0 && dev < 16 && slot >= 0 && slot < 8) have[dev][slot] = smem;
+  return e;
+}
+#endif
+
 // ------------------------------------------------------------------ 1-D TMA bulk copy (global -> shared) + mbarrier
 #ifdef B2_HOST_SIM
 // emulation: the barrier word counts completed phases (low 32 bits) and pending bytes (high 32 bits)

@@ -1204,11 +1204,11 @@ inline int fr3_launch(const Fr3Model* m, int cost_mode, const double* d_x0, int 
   const int grid = (N + wpb - 1) / wpb;
   cudaError_t e;
   if (cost_mode) {
-    e = cudaFuncSetAttribute(fr3_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dynamic_smem_once((const void*)fr3_rollout_kernel<true>, 3, smem);
     if (e == cudaSuccess)
       fr3_rollout_kernel<true><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, (int)wstride, sync_mode, smp, ep.index_offset, d_trace);
   } else {
-    e = cudaFuncSetAttribute(fr3_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dynamic_smem_once((const void*)fr3_rollout_kernel<false>, 2, smem);
     if (e == cudaSuccess)
       fr3_rollout_kernel<false><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, (int)wstride, sync_mode, smp, 0);
   }

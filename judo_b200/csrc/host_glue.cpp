@@ -61,11 +61,36 @@ B2_SIMD_CLONES static void mt_words(uint32_t* key, int* ppos, uint32_t* out, siz
   *ppos = pos;
 }
 
+// One slice [lo, hi) of a round's attempts: legacy_double conversion, acceptance test, order-preserving compaction to the front of
+// the slice, one libm log per accepted pair, the two normals of each pair into pairs[2 * lo ...].  Returns the accepted count.
+B2_SIMD_CLONES static size_t normals_slice(const uint32_t* w, double* x1, double* x2, double* r2, double* lg, double* pairs, size_t lo, size_t hi) {
+  // legacy_double: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53; then 2 x - 1 for both coordinates
+  for (size_t a = lo; a < hi; a++) {
+    const double u = ((double)(int32_t)(w[4 * a] >> 5) * 67108864.0 + (double)(int32_t)(w[4 * a + 1] >> 6)) / 9007199254740992.0;
+    const double v = ((double)(int32_t)(w[4 * a + 2] >> 5) * 67108864.0 + (double)(int32_t)(w[4 * a + 3] >> 6)) / 9007199254740992.0;
+    const double p = 2.0 * u - 1.0, q = 2.0 * v - 1.0;
+    x1[a] = p; x2[a] = q; r2[a] = p * p + q * q;
+  }
+  size_t acc = lo;  // branch-free compaction of the accepted attempts (r2 < 1 and r2 != 0)
+  for (size_t a = lo; a < hi; a++) {
+    const double r = r2[a];
+    x1[acc] = x1[a]; x2[acc] = x2[a]; r2[acc] = r;
+    acc += !(r >= 1.0 || r == 0.0);
+  }
+  for (size_t a = lo; a < acc; a++) lg[a] = log(r2[a]);  // the same libm log numpy calls
+  for (size_t a = lo; a < acc; a++) {
+    const double f = sqrt(-2.0 * lg[a] / r2[a]);
+    pairs[2 * a] = f * x2[a];       // legacy_gauss returns f * x2 first and keeps f * x1 for the next call
+    pairs[2 * a + 1] = f * x1[a];
+  }
+  return acc - lo;
+}
+
 // out[0..n): the next n legacy normals, n EVEN, the generator's has_gauss flag clear on entry (and left clear).
 // Attempts are processed in rounds of exactly as many as there are pairs still missing, so the stream is never consumed past the
 // last accepted attempt (a rejected attempt costs 4 words, exactly as in legacy_gauss).
-B2_SIMD_CLONES void mt19937_normals(uint32_t* key, int* pos, double* out, size_t n) {
-  constexpr size_t CH = 8192;  // attempts per round (scratch: 7 x 64 KB, thread-local)
+void mt19937_normals(uint32_t* key, int* pos, double* out, size_t n) {
+  constexpr size_t CH = 8192;  // attempts per round (scratch stays L2-resident)
   static thread_local std::vector<uint32_t> wbuf(4 * CH);
   static thread_local std::vector<double> X1(CH), X2(CH), R2(CH), LG(CH);
   uint32_t* w = wbuf.data();
@@ -75,26 +100,7 @@ B2_SIMD_CLONES void mt19937_normals(uint32_t* key, int* pos, double* out, size_t
     const size_t need = (n - i) / 2;
     const size_t na = need < CH ? need : CH;
     mt_words(key, pos, w, 4 * na);
-    // legacy_double: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53; then 2 x - 1 for both coordinates
-    for (size_t a = 0; a < na; a++) {
-      const double u = ((double)(int32_t)(w[4 * a] >> 5) * 67108864.0 + (double)(int32_t)(w[4 * a + 1] >> 6)) / 9007199254740992.0;
-      const double v = ((double)(int32_t)(w[4 * a + 2] >> 5) * 67108864.0 + (double)(int32_t)(w[4 * a + 3] >> 6)) / 9007199254740992.0;
-      const double p = 2.0 * u - 1.0, q = 2.0 * v - 1.0;
-      x1[a] = p; x2[a] = q; r2[a] = p * p + q * q;
-    }
-    size_t acc = 0;  // branch-free compaction of the accepted attempts (r2 < 1 and r2 != 0), order preserved
-    for (size_t a = 0; a < na; a++) {
-      const double r = r2[a];
-      x1[acc] = x1[a]; x2[acc] = x2[a]; r2[acc] = r;
-      acc += !(r >= 1.0 || r == 0.0);
-    }
-    for (size_t a = 0; a < acc; a++) lg[a] = log(r2[a]);  // the same libm log numpy calls
-    for (size_t a = 0; a < acc; a++) {
-      const double f = sqrt(-2.0 * lg[a] / r2[a]);
-      out[i + 2 * a] = f * x2[a];       // legacy_gauss returns f * x2 first and keeps f * x1 for the next call
-      out[i + 2 * a + 1] = f * x1[a];
-    }
-    i += 2 * acc;
+    i += 2 * normals_slice(w, x1, x2, r2, lg, out + i, 0, na);
   }
 }
 

@@ -1214,11 +1214,11 @@ inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, in
   const int grid = (N + wpb - 1) / wpb;
   cudaError_t e;
   if (cost_mode) {
-    e = cudaFuncSetAttribute(leap_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dynamic_smem_once((const void*)leap_rollout_kernel<true>, 1, smem);
     if (e == cudaSuccess)
       leap_rollout_kernel<true><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, K, d_basis, d_params, nullptr, nullptr, d_cost, d_reward, (int)wstride, prof, smp, ep.index_offset, d_trace);
   } else {
-    e = cudaFuncSetAttribute(leap_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = set_max_dynamic_smem_once((const void*)leap_rollout_kernel<false>, 0, smem);
     if (e == cudaSuccess)
       leap_rollout_kernel<false><<<grid, 32 * wpb, smem, st>>>(m, d_x0, batched, d_in, N, H, 0, nullptr, nullptr, d_states, d_sensors, nullptr, nullptr, (int)wstride, prof, smp, 0);
   }

@@ -92,6 +92,10 @@ class Engine:
     """Owns a b200mpc_handle.  Raises RuntimeError with the library's message on any failure."""
 
     supports_controller_step = True  # b200mpc_controller_step (the Controller's one-call fast path)
+    # While the GPU runs a plan step, draw the NEXT step's normals from a copy of numpy's generator state; the block is used only if the
+    # generator is still in exactly that state when the next step starts (include/b200mpc.h) — same stream, sampling time hidden.
+    speculative_sampling = True
+    SPECULATE_MIN = 2048      # normals per block below which sampling is too cheap to be worth hiding
 
     def __init__(self, task: str, num_rollouts: int, device: int = 0, consts: np.ndarray | None = None) -> None:
         self._lib = _lib.load()
@@ -236,11 +240,20 @@ class Engine:
     def controller_step(self, rq: "_lib.StepRequest", stream: LegacyStream, n_normals: int) -> None:
         """Run one optimisation iteration described by ``rq`` (pointers already set), drawing the candidates' normals from numpy's
         global legacy stream.  Splits into phase 1 / tail / phase 2 when an odd number of normals is left after the head values."""
-        head = stream.head(n_normals)
+        rq.mt_key, rq.mt_pos = stream.key_addr, stream.pos_addr
+        spec = self.speculative_sampling and n_normals >= self.SPECULATE_MIN
+        rq.speculate, rq.use_speculated = int(spec), 0
+        holds = self._lib.b200mpc_controller_speculation
+        if spec and not (n_normals & 1) and holds(self._h, stream.key_addr, stream.pos_addr, n_normals):
+            head = []        # the whole block was drawn during the previous step's GPU time, from exactly this generator state
+            rq.use_speculated = 1
+        else:
+            head = stream.head(n_normals)
+            if spec and holds(self._h, stream.key_addr, stream.pos_addr, (n_normals - len(head)) & ~1):
+                rq.use_speculated = 1
         rq.n_head = len(head)
         for i, z in enumerate(head):
             rq.head[i] = z
-        rq.mt_key, rq.mt_pos = stream.key_addr, stream.pos_addr
         if (n_normals - len(head)) & 1:
             rq.phase = 1
             self._check(self._lib.b200mpc_controller_step(self._h, ctypes.addressof(rq)))
