@@ -213,6 +213,10 @@ int b200mpc_topk_combine_dev(b200mpc_handle* h, const double* d_partials, int n_
 int b200mpc_exchange_create(b200mpc_handle* h, int world_size, int rank, unsigned char* ipc_handle_out_64B);
 int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all_handles_world_x_64B);
 
+/* Measurement helper for bench.py's issue-bound roofline: DFMA warp instructions per second this GPU sustains with every SM full of
+ * independent chains (the path is bound by fp64 issue / dependent latency, not by HBM). */
+int b200mpc_fp64_peak(int device, double* dfma_warp_inst_per_s);
+
 /* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
 long long b200mpc_launch_count(const b200mpc_handle* h);
 
@@ -226,9 +230,9 @@ int b200mpc_set_trace_capture(b200mpc_handle* h, int enable);
 int b200mpc_trace_width(const b200mpc_handle* h);
 int b200mpc_elite_traces(b200mpc_handle* h, const int* rollout_idx, int n, int H, double* traces_out);
 
-/* Number of rollout steps (process-wide, since load) in which an articulated-body kernel found more contacts than its per-step
- * buffer holds (leap_cube 24, fr3_pick 48; MuJoCo itself grows its arena) and dropped the surplus.  0 means every rollout so far used
- * the full contact set; callers that need the guarantee check it after planning.  -1 on CUDA errors. */
+/* Number of rollout steps run THROUGH THIS HANDLE since its creation in which an articulated-body kernel found more contacts than its
+ * per-step buffer holds (leap_cube 30, fr3_pick 48; MuJoCo itself grows its arena) and dropped the surplus.  0 means every rollout so far
+ * used the full contact set; callers that need the guarantee check it after planning.  -1 on CUDA errors. */
 long long b200mpc_contact_overflows(b200mpc_handle* h);
 
 #ifdef __cplusplus

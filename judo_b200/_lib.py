@@ -51,6 +51,7 @@ SIGNATURES = {
     "b200mpc_exchange_create": (_i, [_vp, _i, _i, _vp]),
     "b200mpc_exchange_open": (_i, [_vp, _vp]),
     "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),
+    "b200mpc_fp64_peak": (_i, [_i, ctypes.POINTER(_d)]),
     "b200mpc_contact_overflows": (ctypes.c_longlong, [_vp]),
     "b200mpc_set_trace_capture": (_i, [_vp, _i]),
     "b200mpc_trace_width": (_i, [_vp]),

@@ -212,8 +212,14 @@ extern "C" int b200mpc_elite_traces(b200mpc_handle* h, const int* idx, int n, in
 extern "C" long long b200mpc_contact_overflows(b200mpc_handle* h) {
   if (!h) return -1;
   unsigned long long v = 0;
+  const void* src = nullptr;  // the counter sits behind the handle's device-resident model table
+#ifdef B200MPC_WITH_LEAP
+  if (h->leap) src = h->leap + 1;
+#endif
+  if (h->fr3) src = h->fr3 + 1;
+  if (!src) return 0;  // thread-per-rollout tasks: at most one contact, nothing to overflow
   if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess ||
-      cudaMemcpyFromSymbol(&v, g_contact_overflow, sizeof(v)) != cudaSuccess) { h->err = "b200mpc_contact_overflows: CUDA error"; return -1; }
+      cudaMemcpy(&v, src, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) { h->err = "b200mpc_contact_overflows: CUDA error"; return -1; }
   return (long long)v;
 }
 
@@ -984,4 +990,47 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
     }
   }
   return 0;
+}
+
+// ------------------------------------------------------------------ measurement helper: FP64 issue peak of this GPU
+// Every resident warp runs 8 independent DFMA chains; enough blocks to fill all SMs.  bench.py divides the fp64 instruction count of the
+// rollout kernels by this to state an issue-bound roofline (the path is latency / issue bound, not HBM bound).
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == 12345.678) out[0] = x0;  // keep the chains alive
+}
+
+extern "C" int b200mpc_fp64_peak(int device, double* dfma_warp_inst_per_s) {
+  if (!dfma_warp_inst_per_s) return 1;
+  if (cudaSetDevice(device) != cudaSuccess) return 1;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 1;
+  double* d = nullptr;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, 256>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return 1; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double warp_inst = (double)blocks * 8 /*warps*/ * iters * 16 * 8;
+    if (rep > 0 && ms > 0) best = std::max(best, warp_inst / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  *dfma_warp_inst_per_s = best;
+  return cudaGetLastError() != cudaSuccess;
 }

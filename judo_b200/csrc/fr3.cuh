@@ -517,7 +517,7 @@ __device__ inline void fr3_collision(const Fr3Model* __restrict__ m, Fr3Work* W,
       W->ccls[slot] = cls; W->cbody[slot] = body;
     }
   }
-  if (lane == 0) { W->ncon = total < FMAXCON ? total : FMAXCON; if (total > FMAXCON) atomicAdd(&g_contact_overflow, 1ull); }
+  if (lane == 0) { W->ncon = total < FMAXCON ? total : FMAXCON; if (total > FMAXCON) atomicAdd(contact_overflow_counter(m), 1ull); }
   __syncwarp();
   // sensors: 5 body-pair distances (min over the pads, clipped to +-cutoff), ee z axis, object position, grasp site
   if (lane < 5) {
@@ -1174,7 +1174,8 @@ inline size_t fr3_wstride(int cost_mode, int K, int H) {
 inline int fr3_create(Fr3Model** out, const double* consts, size_t n, std::string* err) {
   if (n != sizeof(Fr3Model) / sizeof(double)) { *err = "wrong number of task constants"; return 1; }
   Fr3Model* d = nullptr;
-  if (cudaMalloc(&d, sizeof(Fr3Model)) != cudaSuccess) { *err = "cudaMalloc failed"; return 1; }
+  if (cudaMalloc(&d, sizeof(Fr3Model) + 16) != cudaSuccess) { *err = "cudaMalloc failed"; return 1; }  // + the handle's contact-overflow counter (geom.cuh)
+  if (cudaMemset(d + 1, 0, 16) != cudaSuccess) { cudaFree(d); *err = "cudaMemset failed"; return 1; }
   if (cudaMemcpy(d, consts, sizeof(Fr3Model), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); *err = "cudaMemcpy failed"; return 1; }
   *out = d;
   return 0;

@@ -5,9 +5,19 @@
 
 namespace b2 {
 
-// Rollout-steps in which a warp-per-rollout kernel found more contacts than its per-step buffer holds (leap: 24, fr3: 48) and had to
-// drop the surplus.  Queried through b200mpc_contact_overflows(): truncation is never silent.
-__device__ unsigned long long g_contact_overflow;
+// Rollout-steps in which a warp-per-rollout kernel found more contacts than its per-step buffer holds (leap: 30, fr3: 48) and had to
+// drop the surplus.  Queried through b200mpc_contact_overflows(): truncation is never silent.  The counter is PER HANDLE: it lives in the
+// 16 bytes the host allocates behind the handle's device-resident model table (leap_create / fr3_create).
+#ifdef B2_HOST_SIM
+static unsigned long long g_contact_overflow_sim;  // the CPU emulator passes bare model tables: one process-wide counter there
+template <class Model>
+__device__ __forceinline__ unsigned long long* contact_overflow_counter(const Model*) { return &g_contact_overflow_sim; }
+#else
+template <class Model>
+__device__ __forceinline__ unsigned long long* contact_overflow_counter(const Model* m) {
+  return reinterpret_cast<unsigned long long*>(const_cast<Model*>(m + 1));
+}
+#endif
 
 // ------------------------------------------------------------------ small vector helpers (same op order as the oracle)
 __device__ __forceinline__ double ldot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }

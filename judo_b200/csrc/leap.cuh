@@ -401,7 +401,7 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
     ncon += total;
   }
   __syncwarp();
-  if (lane == 0) { W->ncon = ncon < LMAXCON ? ncon : LMAXCON; if (ncon > LMAXCON) atomicAdd(&g_contact_overflow, 1ull); }
+  if (lane == 0) { W->ncon = ncon < LMAXCON ? ncon : LMAXCON; if (ncon > LMAXCON) atomicAdd(contact_overflow_counter(m), 1ull); }
   __syncwarp();
   LPROF_ADD(12, tc0);
   if (prof && lane == 0) atomicAdd(&g_leap_prof[14], (unsigned long long)ncon);
@@ -1179,7 +1179,8 @@ __global__ void leap_reward_kernel(const double* __restrict__ states, int N, int
 inline int leap_create(LeapModel** out, const double* consts, size_t n, std::string* err) {
   if (n != sizeof(LeapModel) / sizeof(double)) { *err = "wrong number of task constants"; return 1; }
   LeapModel* d = nullptr;
-  if (cudaMalloc(&d, sizeof(LeapModel)) != cudaSuccess) { *err = "cudaMalloc failed"; return 1; }
+  if (cudaMalloc(&d, sizeof(LeapModel) + 16) != cudaSuccess) { *err = "cudaMalloc failed"; return 1; }  // + the handle's contact-overflow counter (geom.cuh)
+  if (cudaMemset(d + 1, 0, 16) != cudaSuccess) { cudaFree(d); *err = "cudaMemset failed"; return 1; }
   if (cudaMemcpy(d, consts, sizeof(LeapModel), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); *err = "cudaMemcpy failed"; return 1; }
   *out = d;
   return 0;

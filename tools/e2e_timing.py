@@ -5,7 +5,7 @@ import numpy as np
 import bench
 from judo_b200.engine import Engine
 w = dict(bench.WORKLOADS["cartpole_mppi"])
-task, opt, x0, knots, basis, params = bench.problem(w, 4096)
+task, opt, x0, knots, basis, params, _ = bench.problem(w, 4096)
 for zc in ("0", "1", "2", "3"):
     os.environ["B200MPC_ZEROCOPY"] = zc
     eng = Engine("cartpole", 4096)

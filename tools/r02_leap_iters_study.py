@@ -4,7 +4,7 @@ sys.path.insert(0, '' + __import__("os").path.dirname(__import__("os").path.dirn
 import bench
 from oracle.mjc import lib
 w = dict(bench.WORKLOADS["leap_cube_mppi"])
-task, opt, x0, knots, basis, params = bench.problem(w, 1024)
+task, opt, x0, knots, basis, params, _ = bench.problem(w, 1024)
 om = bench._oracle_model("leap_cube")
 controls = np.einsum("hk,nkj->nhj", basis, knots)
 N, H = 1024, 40
