@@ -89,7 +89,9 @@ int b200mpc_update_ps(b200mpc_handle* h, const double* knots, const double* rewa
  * Replaces one iteration of the while-loop body in Controller.update_action (controller.py:261-288) after
  * sampling/clipping.  opt_params: MPPI {temperature}; CEM {num_elites, sigma_min, sigma_max}; PS {}.
  *   nominal (K,nu) OUT; sigma (K,nu) OUT (CEM only, else may be NULL); reward_N (N) OUT, may be NULL;
- *   elite_idx (n_elite) OUT indices of the best rollouts in descending reward order, may be NULL (n_elite=0) */
+ *   elite_idx (n_elite) OUT indices of the best rollouts in descending reward order, may be NULL (n_elite=0).
+ * n_elite and CEM's num_elites may be up to 256 (the reference has no limit; up to 8 the whole step is one launch, beyond that the
+ * update runs as separate reduction kernels). */
 int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const double* knots, int N, int K, const double* basis, int H,
                       const double* cost_params, int optimizer, const double* opt_params, double* nominal, double* sigma,
                       double* reward_N, int* elite_idx, int n_elite);

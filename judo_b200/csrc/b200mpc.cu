@@ -139,7 +139,7 @@ extern "C" void b200mpc_destroy(b200mpc_handle* h) {
             h->t_stage / h->t_calls, h->t_launch / h->t_calls, h->t_sync / h->t_calls, h->t_out / h->t_calls, h->t_spec / h->t_calls);
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (int g = 0; g < h->xchg_world; g++) if (h->xchg_peer[g] && g != h->xchg_rank) cudaIpcCloseMemHandle(h->xchg_peer[g]);
+  for (int g = 0; g < 8; g++) if (h->xchg_peer[g] && h->xchg_peer[g] != h->xchg) cudaIpcCloseMemHandle(h->xchg_peer[g]);
   cudaFree(h->xchg);
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work); cudaFree(h->d_trace); cudaFree(h->d_traceq);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
@@ -156,10 +156,15 @@ extern "C" int b200mpc_exchange_create(b200mpc_handle* h, int world, int rank, u
   if (!h) return 1;
   if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(h, "exchange: world must be 1..8 and 0 <= rank < world");
   CK(cudaSetDevice(h->device));
-  if (!h->xchg) {
-    CK(cudaMalloc(&h->xchg, EP_XCHG_BYTES));
-    CK(cudaMemset(h->xchg, 0, EP_XCHG_BYTES));
+  // a second create on the same handle starts from scratch: mappings of the previous peers are closed, flags and slots are cleared
+  // (stale epoch flags >= the restarted epoch would let a step combine partials that were never written)
+  for (int g = 0; g < 8; g++) {
+    if (h->xchg_peer[g] && h->xchg_peer[g] != h->xchg) cudaIpcCloseMemHandle(h->xchg_peer[g]);
+    h->xchg_peer[g] = nullptr;
   }
+  if (!h->xchg) CK(cudaMalloc(&h->xchg, EP_XCHG_BYTES));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemset(h->xchg, 0, EP_XCHG_BYTES));
   h->xchg_world = world; h->xchg_rank = rank; h->xchg_epoch = 0;
   cudaIpcMemHandle_t ih;
   CK(cudaIpcGetMemHandle(&ih, h->xchg));
@@ -175,7 +180,11 @@ extern "C" int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all
     if (g == h->xchg_rank) { h->xchg_peer[g] = h->xchg; continue; }
     cudaIpcMemHandle_t ih;
     memcpy(&ih, all_handles + 64 * g, 64);
-    CK(cudaIpcOpenMemHandle(&h->xchg_peer[g], ih, cudaIpcMemLazyEnablePeerAccess));
+    cudaError_t e = cudaIpcOpenMemHandle(&h->xchg_peer[g], ih, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {  // leave no half-open exchange behind: callers then stay on the all_gather path
+      for (int q = 0; q < 8; q++) { if (h->xchg_peer[q] && h->xchg_peer[q] != h->xchg) cudaIpcCloseMemHandle(h->xchg_peer[q]); h->xchg_peer[q] = nullptr; }
+      return fail(h, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
   }
   return 0;
 }
@@ -185,6 +194,12 @@ extern "C" int b200mpc_update(b200mpc_handle* h, int n) { if (!h) return 1; if (
 extern "C" int b200mpc_num_rollouts(const b200mpc_handle* h) { return h ? h->N : -1; }
 extern "C" long long b200mpc_launch_count(const b200mpc_handle* h) { return h ? h->launches : 0; }
 
+// every rank's exchange buffer is mapped (b200mpc_exchange_open succeeded): only then may a step use the in-kernel exchange
+static bool exchange_ready(const b200mpc_handle* h) {
+  if (h->xchg_world < 1 || !h->xchg) return false;
+  for (int g = 0; g < h->xchg_world; g++) if (!h->xchg_peer[g]) return false;
+  return true;
+}
 static int trace_width(const b200mpc_handle* h) { return h->task == B200MPC_TASK_LEAP_CUBE ? LEAP_NTRACE : h->task == B200MPC_TASK_FR3_PICK ? FR_NTRACE : 0; }
 extern "C" int b200mpc_set_trace_capture(b200mpc_handle* h, int enable) {
   if (!h) return 1;
@@ -403,12 +418,14 @@ static int plan_step_impl(b200mpc_handle* h, const double* d_x0, const double* d
   if (optimizer < 0 || optimizer > 2) return fail(h, "unknown optimizer");
   if (optimizer == B200MPC_OPT_MPPI && !(opt_params && opt_params[0] > 0)) return fail(h, "temperature must be positive");
   if (optimizer == B200MPC_OPT_CEM && !opt_params) return fail(h, "CEM needs {num_elites, sigma_min, sigma_max}");
-  if (n_elite < 0 || n_elite > EP_MAXK) return fail(h, "n_elite must be in 0..8");
+  if (n_elite < 0 || n_elite > 256) return fail(h, "n_elite must be in 0..256");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int KNU = K * h->dims.nu;
-  if (h->task == B200MPC_TASK_LEAP_CUBE || h->task == B200MPC_TASK_FR3_PICK) {
-    // warp-per-rollout kernel (ms-scale): the update runs as separate reduction kernels (2% of the step)
+  const int k_need = std::max(n_elite, optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 0);
+  if (h->task == B200MPC_TASK_LEAP_CUBE || h->task == B200MPC_TASK_FR3_PICK || (k_need > EP_MAXK && finalize != 2)) {
+    // warp-per-rollout kernels (ms-scale steps), or more elites than the fused epilogue keeps in registers (8; the reference has no
+    // limit on num_elites / max_num_traces): the update runs as separate reduction kernels
     PlanEpilogue none{};
     none.optimizer = EP_NONE;
     none.index_offset = index_offset;
@@ -443,7 +460,7 @@ static int plan_step_impl(b200mpc_handle* h, const double* d_x0, const double* d
   ep.elite_knots = d_elite_knots;
   ep.trace_q = d_trace_q; ep.elite_sens = d_elite_sens;
   if (finalize == 2) {
-    if (!h->xchg || !h->xchg_peer[h->xchg_world - 1] || !h->xchg_peer[0]) return fail(h, "peer exchange not set up (exchange_create/open)");
+    if (!exchange_ready(h)) return fail(h, "peer exchange not set up (exchange_create/open)");
     const int kout = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
     if ((optimizer == B200MPC_OPT_MPPI ? 2 + KNU : kout * (2 + KNU)) > EP_XCHG_STRIDE) return fail(h, "partial too large for the exchange slot");
     if (n_elite > 0) return fail(h, "elite lists are per rank: pass n_elite = 0 with the peer exchange");
@@ -473,8 +490,8 @@ extern "C" int b200mpc_plan_step_sampled(b200mpc_handle* h, const double* x0, co
   if (optimizer < 0 || optimizer > 2) return fail(h, "unknown optimizer");
   if (optimizer == B200MPC_OPT_MPPI && !(opt_params && opt_params[0] > 0)) return fail(h, "temperature must be positive");
   if (optimizer == B200MPC_OPT_CEM && !opt_params) return fail(h, "CEM needs {num_elites, sigma_min, sigma_max}");
-  if (n_elite < 0 || n_elite > EP_MAXK) return fail(h, "n_elite must be in 0..8");
-  if (optimizer == B200MPC_OPT_CEM && (int)opt_params[0] > EP_MAXK) return fail(h, "device sampling supports at most 8 elites");
+  if (n_elite < 0 || n_elite > 256) return fail(h, "n_elite must be in 0..256");
+  if (optimizer == B200MPC_OPT_CEM && ((int)opt_params[0] > 256 || (int)opt_params[0] <= 0)) return fail(h, "num_elites must be in 1..256");
   CK(cudaSetDevice(h->device));
   const int nx = h->dims.nq + h->dims.nv, nu = h->dims.nu, np = h->dims.n_cost_params, KNU = K * nu;
   // staged inputs: [x0 | basis | params | nominal | sigma | lo | hi]  (~1-3 KB: the only bytes that cross PCIe on the way in)
@@ -560,7 +577,7 @@ extern "C" int b200mpc_mppi_combine_dev(b200mpc_handle* h, const double* d_parti
 extern "C" int b200mpc_topk_partial_dev(b200mpc_handle* h, const double* d_knots, const double* d_rewards, int N, int KNU, int k,
                                         int index_offset, int prefer_high, double* d_partial, void* stream) {
   if (!h) return 1;
-  if (k <= 0 || k > 64) return fail(h, "num_elites must be in 1..64");
+  if (k <= 0 || k > 256) return fail(h, "num_elites must be in 1..256");
   CK(cudaSetDevice(h->device));
   topk_partial_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_knots, d_rewards, N, KNU, k, index_offset, prefer_high, d_partial);
   h->launches++;
@@ -572,7 +589,7 @@ extern "C" int b200mpc_topk_combine_dev(b200mpc_handle* h, const double* d_parti
                                         double sigma_min, double sigma_max, double* d_nominal, double* d_sigma, double* d_elite,
                                         void* stream) {
   if (!h) return 1;
-  if (k <= 0 || k > 64) return fail(h, "num_elites must be in 1..64");
+  if (k <= 0 || k > 256) return fail(h, "num_elites must be in 1..256");
   if ((long long)np * k >= (1 << 20)) return fail(h, "too many candidates");
   CK(cudaSetDevice(h->device));
   topk_combine_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_partials, np, KNU, k, prefer_high, sigma_min, sigma_max, d_nominal, d_sigma, d_elite);
@@ -594,7 +611,7 @@ static int run_update(b200mpc_handle* h, int optimizer, const double* opt_params
   }
   int k = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
   int prefer_high = optimizer == B200MPC_OPT_CEM ? 1 : 0;
-  if (k <= 0 || k > 64) return fail(h, "num_elites must be in 1..64");
+  if (k <= 0 || k > 256) return fail(h, "num_elites must be in 1..256");
   if (grow(h, &h->d_work, &h->d_work_bytes, (size_t)nb * k * (2 + KNU) * 8, false)) return 1;
   topk_partial_kernel<<<nb, 256, 0, st>>>(d_knots, d_rewards, N, KNU, k, 0, prefer_high, (double*)h->d_work);
   h->launches++;
@@ -751,11 +768,12 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
   if (N <= 0 || H <= 0 || K <= 0) return fail(h, "N, H and K must be positive");
   if (optimizer == B200MPC_OPT_MPPI && !(opt_params && opt_params[0] > 0)) return fail(h, "temperature must be positive");
   if (optimizer == B200MPC_OPT_CEM && !opt_params) return fail(h, "CEM needs {num_elites, sigma_min, sigma_max}");
-  if (n_elite < 0 || n_elite > 64) return fail(h, "n_elite must be in 0..64");
+  if (n_elite < 0 || n_elite > 256) return fail(h, "n_elite must be in 0..256");
   if (optimizer < 0 || optimizer > 2) return fail(h, "unknown optimizer");
   CK(cudaSetDevice(h->device));
   const int KNU = K * h->dims.nu;
   int k_cem = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 0;
+  if (k_cem > 256) return fail(h, "num_elites must be in 1..256");
   // Zero-copy outputs (default): the fused kernel writes nominal/sigma/elite/rewards straight into pinned host memory, so the
   // step is ONE H2D copy + ONE launch.  Zero-copy inputs (bit0) make the kernel pull the candidates over PCIe itself (slower).
   const bool fusable = std::max(n_elite, k_cem) <= EP_MAXK;
@@ -780,7 +798,7 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
     // multi-GPU handles with an open peer exchange: the MPPI update is GLOBAL (partials cross NVLink inside the kernel)
     const int kout_x = optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 1;
     const bool fits_x = (optimizer == B200MPC_OPT_MPPI ? 2 + KNU : kout_x * (2 + KNU)) <= EP_XCHG_STRIDE;
-    const int fin = (h->xchg_world > 1 && h->xchg && fits_x && h->task != B200MPC_TASK_LEAP_CUBE && h->task != B200MPC_TASK_FR3_PICK && n_elite == 0) ? 2 : 1;
+    const int fin = (h->xchg_world > 1 && exchange_ready(h) && fits_x && h->task != B200MPC_TASK_LEAP_CUBE && h->task != B200MPC_TASK_FR3_PICK && n_elite == 0) ? 2 : 1;
     if (b200mpc_plan_step_dev(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), optimizer,
                               opt_params, fin, 0, n_elite, nullptr, d_reward, (double*)(dout + o_nom), (double*)(dout + o_sig),
                               (double*)(dout + o_el), nullptr, h->stream)) return 1;
@@ -817,6 +835,12 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
   if (sigma && optimizer == B200MPC_OPT_CEM) memcpy(sigma, ho + o_sig, (size_t)KNU * 8);
   if (elite_idx) for (int i = 0; i < n_elite; i++) elite_idx[i] = (int)((const double*)(ho + o_el))[i];
   if (reward_N) memcpy(reward_N, ho + o_rw, (size_t)N * 8);
+  if (h->xchg_world > 1 && exchange_ready(h) && nominal[0] != nominal[0]) {
+    // the in-kernel exchange writes NaN when a peer's flag never arrived (bounded spin): surface it instead of poisoning the caller's spline
+    bool finite_in = true;
+    for (size_t i = 0; i < (size_t)N * KNU && finite_in; i++) finite_in = knots[i] == knots[i];
+    if (finite_in) return fail(h, "peer exchange timed out: a rank did not run this plan step (nominal not updated)");
+  }
   if (h->timing) {
     auto T4 = std::chrono::steady_clock::now();
     auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) topk_combine_kernel(const double* __restr
                                                            double* __restrict__ sigma, double* __restrict__ elite_idx) {
   __shared__ double sr[256];
   __shared__ long long si[256];
-  __shared__ int chosen[64];
+  __shared__ int chosen[256];
   __shared__ int nch;
   const int ncand = np * k, stride = 2 + KNU;
   double prev_r = INFINITY;
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(256) topk_combine_kernel(const double* __restr
   bool have_prev = false;
   if (threadIdx.x == 0) nch = 0;
   __syncthreads();
-  for (int e = 0; e < k && e < 64; e++) {
+  for (int e = 0; e < k && e < 256; e++) {
     double br = -INFINITY; long long bi = -1; int bc = -1;
     for (int cidx = threadIdx.x; cidx < ncand; cidx += blockDim.x) {
       const double* p = partials + (size_t)cidx * stride;

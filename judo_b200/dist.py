@@ -123,7 +123,7 @@ class ShardedPlanner:
         opp = op.ctypes.data
         single = self.world_size == 1
         k_x = int(op[0]) if optimizer == "cem" else 1
-        fits = (2 + self.knu if optimizer == "mppi" else k_x * (2 + self.knu)) <= 98  # EP_XCHG_STRIDE doubles per rank slot
+        fits = (2 + self.knu if optimizer == "mppi" else k_x * (2 + self.knu)) <= 98 and k_x <= 8  # EP_XCHG_STRIDE doubles per rank slot, EP_MAXK elites
         if (not single or getattr(self, "force_peer", False)) and self.peer_exchange and fits and self.engine.task not in ("leap_cube", "leap_cube_down", "fr3_pick"):
             # ONE kernel per rank: rollout + cost + P2P exchange of the partials + final update
             self._check(self.lib.b200mpc_plan_step_dev(h, P(self.d_x0), P(self.d_knots), self.n_local, self.K, P(self.d_basis), self.H,

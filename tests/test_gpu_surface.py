@@ -254,3 +254,39 @@ def test_closed_loop_sim_plan_act_matches_cpu_loop(temp_np_seed):
                 t += dt
             cpu_traj.append(x.copy())
     np.testing.assert_allclose(np.array(gpu_traj), np.array(cpu_traj), rtol=0, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_many_elites_and_traces_are_not_capped(temp_np_seed):
+    """the reference accepts any num_elites / max_num_traces; beyond the 8 the fused epilogue keeps in registers the update
+    runs as separate reduction kernels instead of raising."""
+    from judo_b200.controller import make_controller
+    from judo_b200.engine import Engine
+    from oracle import plan as op
+
+    rng = np.random.default_rng(0)
+    eng = Engine("cartpole", 300)
+    knots = rng.normal(size=(300, 4, 1))
+    basis = np.eye(4)[np.repeat(np.arange(4), 5)]
+    x0, params = np.array([0.1, 3.0, 0.0, 0.0]), np.array([10.0, 10.0, 0.1, 0.1, 0.01, 0.1])
+    for k in (9, 20, 100):
+        res = eng.plan_step(x0, knots, basis, params, "cem", np.array([k, 0.1, 1.0]), want_rewards=True, n_elite=k)
+        nom, sig = op.cem_update(knots, res["rewards"], k, 0.1, 1.0)
+        np.testing.assert_allclose(res["nominal"], nom, atol=1e-12)
+        np.testing.assert_allclose(res["sigma"], sig, atol=1e-12)
+        np.testing.assert_array_equal(res["elite"], np.argsort(res["rewards"], kind="stable")[::-1][:k])
+        r2 = eng.plan_step_sampled(x0, np.zeros((4, 1)), np.full((4, 1), 0.3), np.array([-1.8]), np.array([1.8]), 300, basis, params, "cem",
+                                   np.array([k, 0.1, 1.0]), seed=1, counter=0, n_elite=k, want_knots=True)
+        nom2, sig2 = op.cem_update(r2["knots"], r2["rewards"], k, 0.1, 1.0)
+        np.testing.assert_allclose(r2["nominal"], nom2, atol=1e-12)
+        np.testing.assert_allclose(r2["elite_knots"], r2["knots"][r2["elite"]], atol=0)
+    eng.close()
+    with temp_np_seed(1):
+        for sampling in ("host", "device"):
+            ctrl = make_controller("cylinder_push", "cem")
+            ctrl.controller_cfg.max_num_traces = 12
+            ctrl.optimizer_cfg.num_elites = 11
+            ctrl.sampling = sampling
+            ctrl.update_action()
+            assert ctrl.traces.shape == (12 * 2 * (ctrl.num_timesteps - 1), 2, 3) and np.isfinite(ctrl.nominal_knots).all()
+            ctrl.engine.close()

@@ -154,7 +154,7 @@ def test_fr3_pick_task_surface_and_phase_machine(golden):
 def test_c_abi_library_exports_every_declared_symbol():
     """include/b200mpc.h, judo_b200/_lib.py and the built library agree (loading needs no GPU)."""
     header = open(os.path.join(ROOT, "include", "b200mpc.h")).read()
-    declared = set(re.findall(r"\b(b200mpc_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(b200mpc_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load()
     for name in declared:
