@@ -401,15 +401,45 @@ def measure(wname: str, w: dict, steps: int, warmup: int, rank: int, world: int,
         t_wall0 = time.perf_counter()
         for i in range(steps):
             flush.zero_()                                  # evict L2 between timed iterations (outside the events)
-            if dist is not None and not in_kernel_exchange:
-                dist.barrier()                             # all_gather path: line the ranks up again (the flush skews them)
+            if dist is not None:                           # line the ranks up again: the flushes do not take equally long on every GPU and a
+                if in_kernel_exchange:                     # step cannot finish before the slowest rank has STARTED it.  In-kernel exchange:
+                    planner.align()                        # a one-warp signal/wait kernel on the stream (no host round trip); all_gather
+                else:                                      # path: a host barrier.
+                    dist.barrier()
             starts[i].record()
             planner.step(w["optimizer"], opt_params, index_offset=lo)
             ends[i].record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    launches = planner.engine.launch_count - launches0
+    launches = planner.engine.launch_count - launches0 - (steps if in_kernel_exchange else 0)  # (the align kernels are not plan-step work)
+    # the same loop WITHOUT lining the ranks up, and the in-kernel %globaltimer stamps of a step: separates launch / flush skew between
+    # the ranks from the cost of the exchange itself
+    exchange_timing = None
+    if in_kernel_exchange:
+        nu_ = min(steps, 50)
+        for i in range(nu_):
+            flush.zero_()
+            starts[i].record()
+            planner.step(w["optimizer"], opt_params, index_offset=lo)
+            ends[i].record()
+        barrier()
+        un_ms = statistics.mean(starts[i].elapsed_time(ends[i]) for i in range(nu_))
+        planner.align()
+        planner.step(w["optimizer"], opt_params, index_offset=lo)
+        torch.cuda.synchronize(dev)
+        t_in, t_pub, t_done = planner.exchange_stamps()
+        mine = torch.tensor([un_ms, (t_done - t_pub) * 1e-3, (t_done - t_in) * 1e-3, statistics.mean(step_ms)], dtype=torch.float64, device=dev)
+        allm = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        allm = torch.stack(allm).cpu().numpy()
+        exchange_timing = {"aligned_ms_per_step_max_rank": float(allm[:, 3].max()), "unaligned_ms_per_step_max_rank": float(allm[:, 0].max()),
+                           "wait_for_peers_us_per_rank": [round(float(x), 2) for x in allm[:, 1]],
+                           "kernel_entry_to_done_us_per_rank": [round(float(x), 2) for x in allm[:, 2]],
+                           "note": "aligned: the ranks are lined up by a one-warp signal/wait kernel between the L2 flush and the start event "
+                                   "(what `value` reports); unaligned: no line-up, so each step also absorbs how differently long the ranks' "
+                                   "flushes took; wait_for_peers: %globaltimer from 'partial published' to 'all peers seen' in one aligned "
+                                   "step (the last rank to arrive waits ~ the NVLink flag latency, the others additionally the skew)"}
 
     # dominant kernel alone: rollout+cost, timed live with events on the launching stream, L2 flushed
     st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -540,6 +570,8 @@ def measure(wname: str, w: dict, steps: int, warmup: int, rank: int, world: int,
         out["contact_overflows"] = overflows  # rollout steps (whole run) that exceeded the kernel's per-step contact buffer
     if verified is not None:
         out["exchange_verified"] = verified
+    if exchange_timing is not None:
+        out["exchange_timing"] = exchange_timing
     return out
 
 

@@ -178,6 +178,38 @@ int b200mpc_last_candidates(b200mpc_handle* h, double* knots_out, int N, int K);
 int b200mpc_legacy_normals(unsigned int* mt_key, int* mt_pos, double* out, size_t n_even);
 int b200mpc_spline_basis(int order, const double* knot_times, int K, const double* query, int H, double* basis_HK);
 
+/* ---- several GPUs behind ONE backend, in one process ------------------------------------------------------------------------------
+ * The reference's Controller is one process with one rollout backend (judo/controller/controller.py:72-85); a group keeps that shape:
+ * one object whose rollouts are sharded along N over `devices` (rollout 0, the un-noised nominal, on the first; remainders to the lowest
+ * ranks), everything issued asynchronously from the calling thread.  Each entry mirrors its single-GPU counterpart above:
+ *   b200mpc_group_rollout          = b200mpc_rollout (RolloutBackend.rollout, judo/utils/mj_rollout_backend.py:45-88)
+ *   b200mpc_group_plan_step        = b200mpc_plan_step: every device runs the fused rollout+cost kernel on its slice, the slices' rewards
+ *                                    go peer-to-peer to the first device, which holds all candidates and runs the optimizer update
+ *                                    (one small exchange per plan step) and the elite selection
+ *   b200mpc_group_controller_step  = b200mpc_controller_step (same request, same sampling protocol)
+ * num_rollouts is the TOTAL over the group.  Errors: b200mpc_group_last_error (g may be NULL: last failed create). */
+typedef struct b200mpc_group b200mpc_group;
+int b200mpc_group_create(b200mpc_group** out, int task_id, const double* task_consts, size_t n_consts, const int* devices, int n_devices,
+                         int num_rollouts);
+void b200mpc_group_destroy(b200mpc_group* g);
+const char* b200mpc_group_last_error(const b200mpc_group* g);
+int b200mpc_group_size(const b200mpc_group* g);
+b200mpc_handle* b200mpc_group_handle(b200mpc_group* g, int i); /* the i-th device's handle (owned by the group) */
+int b200mpc_group_update(b200mpc_group* g, int num_rollouts);
+int b200mpc_group_num_rollouts(const b200mpc_group* g);
+int b200mpc_group_rollout(b200mpc_group* g, const double* x0, int x0_batched, const double* controls, int N, int H, double* states,
+                          double* sensors);
+int b200mpc_group_plan_step(b200mpc_group* g, const double* x0, const double* knots, int N, int K, const double* basis, int H,
+                            const double* cost_params, int optimizer, const double* opt_params, double* nominal, double* sigma,
+                            double* reward_N, int* elite_idx, int n_elite);
+int b200mpc_group_controller_step(b200mpc_group* g, b200mpc_step_request* req);
+int b200mpc_group_controller_speculation(b200mpc_group* g, const unsigned int* mt_key, const int* mt_pos, size_t n);
+int b200mpc_group_last_candidates(b200mpc_group* g, double* knots_out, int N, int K);
+int b200mpc_group_set_trace_capture(b200mpc_group* g, int enable);
+int b200mpc_group_elite_traces(b200mpc_group* g, const int* global_rollout_idx, int n, int H, double* traces_out);
+long long b200mpc_group_launch_count(const b200mpc_group* g);
+long long b200mpc_group_contact_overflows(b200mpc_group* g);
+
 /* ---- resident (device-pointer) API: inputs/outputs already in HBM, asynchronous on `stream` ------------------------
  * Used by bench.py's device-resident measurement and by the multi-GPU sharded plan step (judo_b200/dist.py), where
  * torch owns the allocations and NCCL moves the partials.  All pointers are device pointers; stream is a
@@ -214,6 +246,11 @@ int b200mpc_topk_combine_dev(b200mpc_handle* h, const double* d_partials, int n_
  * knots — the collective of SURVEY.md §8e happens inside the rollout kernel (no NCCL call, no extra launch on the data path). */
 int b200mpc_exchange_create(b200mpc_handle* h, int world_size, int rank, unsigned char* ipc_handle_out_64B);
 int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all_handles_world_x_64B);
+/* Measurement helpers for the scaling bench.  align: a one-warp kernel on `stream` that raises this rank's align flag in every peer buffer
+ * and waits for all of them (lines the GPUs up between the L2 flush and the timed step, moving no data).  stamps: %globaltimer (ns) of
+ * the last finalize=2 step on this rank: [0] kernel entry, [1] partial published to the peers, [2] all peers' partials seen. */
+int b200mpc_exchange_align_dev(b200mpc_handle* h, void* stream);
+int b200mpc_exchange_stamps(b200mpc_handle* h, unsigned long long* out3);
 
 /* Measurement helper for bench.py's issue-bound roofline: DFMA warp instructions per second this GPU sustains with every SM full of
  * independent chains (the path is bound by fp64 issue / dependent latency, not by HBM). */

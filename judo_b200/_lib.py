@@ -50,6 +50,8 @@ SIGNATURES = {
     "b200mpc_topk_combine_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp]),
     "b200mpc_exchange_create": (_i, [_vp, _i, _i, _vp]),
     "b200mpc_exchange_open": (_i, [_vp, _vp]),
+    "b200mpc_exchange_align_dev": (_i, [_vp, _vp]),
+    "b200mpc_exchange_stamps": (_i, [_vp, _vp]),
     "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),
     "b200mpc_fp64_peak": (_i, [_i, ctypes.POINTER(_d)]),
     "b200mpc_contact_overflows": (ctypes.c_longlong, [_vp]),
@@ -59,6 +61,22 @@ SIGNATURES = {
     "b200mpc_controller_step": (_i, [_vp, _vp]),
     "b200mpc_last_candidates": (_i, [_vp, _vp, _i, _i]),
     "b200mpc_controller_speculation": (_i, [_vp, _vp, _vp, ctypes.c_size_t]),
+    "b200mpc_group_create": (_i, [ctypes.POINTER(_vp), _i, _vp, ctypes.c_size_t, _vp, _i, _i]),
+    "b200mpc_group_destroy": (None, [_vp]),
+    "b200mpc_group_last_error": (ctypes.c_char_p, [_vp]),
+    "b200mpc_group_size": (_i, [_vp]),
+    "b200mpc_group_handle": (_vp, [_vp, _i]),
+    "b200mpc_group_update": (_i, [_vp, _i]),
+    "b200mpc_group_num_rollouts": (_i, [_vp]),
+    "b200mpc_group_rollout": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp]),
+    "b200mpc_group_plan_step": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "b200mpc_group_controller_step": (_i, [_vp, _vp]),
+    "b200mpc_group_controller_speculation": (_i, [_vp, _vp, _vp, ctypes.c_size_t]),
+    "b200mpc_group_last_candidates": (_i, [_vp, _vp, _i, _i]),
+    "b200mpc_group_set_trace_capture": (_i, [_vp, _i]),
+    "b200mpc_group_elite_traces": (_i, [_vp, _vp, _i, _i, _vp]),
+    "b200mpc_group_launch_count": (ctypes.c_longlong, [_vp]),
+    "b200mpc_group_contact_overflows": (ctypes.c_longlong, [_vp]),
     "b200mpc_legacy_normals": (_i, [_vp, _vp, _vp, ctypes.c_size_t]),
     "b200mpc_spline_basis": (_i, [_i, _vp, _i, _vp, _i, _vp]),
 }

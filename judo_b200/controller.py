@@ -71,14 +71,15 @@ class Controller:
     """The controller object (judo/controller/controller.py:45-380)."""
 
     def __init__(self, controller_config: ControllerConfig, task: Task, optimizer: Optimizer,
-                 rollout_backend: Literal["b200"] = "b200", device: int = 0) -> None:
+                 rollout_backend: Literal["b200"] = "b200", device: int = 0, devices: "list[int] | None" = None) -> None:
         self._controller_cfg = controller_config
         self.task = task
         self.optimizer = optimizer
         self.available_optimizers = get_registered_optimizers()
         self.available_tasks = get_registered_tasks()
         self.model = self.task.model
-        self.rollout_backend: RolloutBackend = B200RolloutBackend(self.task, self.optimizer_cfg.num_rollouts, device=device)
+        # devices=[0, 1, ...]: the rollouts are sharded over several GPUs of this process behind the same backend / Controller surface
+        self.rollout_backend: RolloutBackend = B200RolloutBackend(self.task, self.optimizer_cfg.num_rollouts, device=device, devices=devices)
         self.engine = self.rollout_backend.engine
         self.task.engine = self.engine
         self.optimizer.bind(self.engine)
@@ -424,7 +425,8 @@ class Controller:
         return make_normalizer(self.action_normalizer_type, self.model.nu, **kwargs)
 
 
-def make_controller(init_task: str, init_optimizer: str, rollout_backend: Literal["b200"] = "b200", device: int = 0) -> Controller:
+def make_controller(init_task: str, init_optimizer: str, rollout_backend: Literal["b200"] = "b200", device: int = 0,
+                    devices: "list[int] | None" = None) -> Controller:
     """judo/controller/controller.py:404-442."""
     task_entry = get_registered_tasks().get(init_task)
     optimizer_entry = get_registered_optimizers().get(init_optimizer)
@@ -437,4 +439,5 @@ def make_controller(init_task: str, init_optimizer: str, rollout_backend: Litera
     optimizer = optimizer_cls(optimizer_cfg, task.nu)
     controller_cfg = ControllerConfig()
     controller_cfg.set_override(init_task)
-    return Controller(controller_config=controller_cfg, task=task, optimizer=optimizer, rollout_backend=rollout_backend, device=device)
+    return Controller(controller_config=controller_cfg, task=task, optimizer=optimizer, rollout_backend=rollout_backend, device=device,
+                      devices=devices)

@@ -54,7 +54,8 @@ struct b200mpc_handle {
   int zero_copy = 2;           // plan_step: bit0 = kernel READS the pinned staging buffer, bit1 = kernel WRITES results to pinned memory
   bool zero_copy_now = false;  // set for the duration of a zero-copy plan_step
   // peer exchange (multi-GPU fused MPPI): local buffer + peers' buffers opened through CUDA IPC
-  void* xchg = nullptr; void* xchg_peer[8] = {nullptr}; int xchg_world = 0, xchg_rank = 0; unsigned long long xchg_epoch = 0;
+  void* xchg = nullptr; void* xchg_peer[8] = {nullptr}; int xchg_world = 0, xchg_rank = 0; unsigned long long xchg_epoch = 0, xchg_align_epoch = 0;
+  unsigned long long* d_stamps = nullptr;  // %globaltimer stamps of the last finalize=2 step (b200mpc_exchange_stamps)
   double t_stage = 0, t_launch = 0, t_sync = 0, t_out = 0, t_spec = 0; long long t_calls = 0; bool timing = false;  // B200MPC_TIMING=1
   // b200mpc_controller_step: normals of the current block, captured positions (N, H, nq) for the in-kernel elite traces, and where the
   // last step's candidates sit in the pinned staging buffer
@@ -77,6 +78,13 @@ struct b200mpc_handle {
   } while (0)
 
 static int fail(b200mpc_handle* h, const std::string& msg) { h->err = msg; return 1; }
+// every rank's exchange buffer is mapped (b200mpc_exchange_open succeeded): only then may a step use the in-kernel exchange
+static bool exchange_ready(const b200mpc_handle* h) {
+  if (h->xchg_world < 1 || !h->xchg) return false;
+  for (int g = 0; g < h->xchg_world; g++) if (!h->xchg_peer[g]) return false;
+  return true;
+}
+
 
 static int grow(b200mpc_handle* h, void** p, size_t* cur, size_t need, bool pinned) {
   if (need <= *cur) return 0;
@@ -140,7 +148,7 @@ extern "C" void b200mpc_destroy(b200mpc_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int g = 0; g < 8; g++) if (h->xchg_peer[g] && h->xchg_peer[g] != h->xchg) cudaIpcCloseMemHandle(h->xchg_peer[g]);
-  cudaFree(h->xchg);
+  cudaFree(h->xchg); cudaFree(h->d_stamps);
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work); cudaFree(h->d_trace); cudaFree(h->d_traceq);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
 #ifdef B200MPC_WITH_LEAP
@@ -165,7 +173,8 @@ extern "C" int b200mpc_exchange_create(b200mpc_handle* h, int world, int rank, u
   if (!h->xchg) CK(cudaMalloc(&h->xchg, EP_XCHG_BYTES));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaMemset(h->xchg, 0, EP_XCHG_BYTES));
-  h->xchg_world = world; h->xchg_rank = rank; h->xchg_epoch = 0;
+  h->xchg_world = world; h->xchg_rank = rank; h->xchg_epoch = 0; h->xchg_align_epoch = 0;
+  if (!h->d_stamps) { CK(cudaMalloc(&h->d_stamps, 32)); CK(cudaMemset(h->d_stamps, 0, 32)); }
   cudaIpcMemHandle_t ih;
   CK(cudaIpcGetMemHandle(&ih, h->xchg));
   static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -189,17 +198,30 @@ extern "C" int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all
   return 0;
 }
 
+extern "C" int b200mpc_exchange_align_dev(b200mpc_handle* h, void* stream) {
+  if (!h) return 1;
+  if (!exchange_ready(h)) return fail(h, "peer exchange not set up (exchange_create/open)");
+  CK(cudaSetDevice(h->device));
+  PlanEpilogue ep{};
+  ep.world = h->xchg_world; ep.rank = h->xchg_rank; ep.epoch = ++h->xchg_align_epoch;
+  for (int g = 0; g < h->xchg_world; g++) ep.peer[g] = (double*)h->xchg_peer[g];
+  exchange_align_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ep);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int b200mpc_exchange_stamps(b200mpc_handle* h, unsigned long long* out3) {
+  if (!h || !out3) return 1;
+  if (!h->d_stamps) return fail(h, "peer exchange not set up (exchange_create/open)");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(out3, h->d_stamps, 24, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" int b200mpc_get_dims(const b200mpc_handle* h, b200mpc_dims* out) { if (!h || !out) return 1; *out = h->dims; return 0; }
 extern "C" int b200mpc_update(b200mpc_handle* h, int n) { if (!h) return 1; if (n <= 0) return fail(h, "num_rollouts must be positive"); h->N = n; return 0; }
 extern "C" int b200mpc_num_rollouts(const b200mpc_handle* h) { return h ? h->N : -1; }
 extern "C" long long b200mpc_launch_count(const b200mpc_handle* h) { return h ? h->launches : 0; }
 
-// every rank's exchange buffer is mapped (b200mpc_exchange_open succeeded): only then may a step use the in-kernel exchange
-static bool exchange_ready(const b200mpc_handle* h) {
-  if (h->xchg_world < 1 || !h->xchg) return false;
-  for (int g = 0; g < h->xchg_world; g++) if (!h->xchg_peer[g]) return false;
-  return true;
-}
 static int trace_width(const b200mpc_handle* h) { return h->task == B200MPC_TASK_LEAP_CUBE ? LEAP_NTRACE : h->task == B200MPC_TASK_FR3_PICK ? FR_NTRACE : 0; }
 extern "C" int b200mpc_set_trace_capture(b200mpc_handle* h, int enable) {
   if (!h) return 1;
@@ -378,6 +400,7 @@ static int make_epilogue(b200mpc_handle* h, int optimizer, const double* opt_par
   if (optimizer == B200MPC_OPT_CEM && k_cem <= 0) return fail(h, "num_elites must be positive");
   ep->k = std::max(n_elite, k_cem);
   ep->k_cem = k_cem;
+  ep->n_trace = n_elite;
   if (ep->k > EP_MAXK) return fail(h, "fused epilogue supports at most 8 elites");
   ep->finalize = finalize;
   ep->index_offset = index_offset;
@@ -465,6 +488,7 @@ static int plan_step_impl(b200mpc_handle* h, const double* d_x0, const double* d
     if ((optimizer == B200MPC_OPT_MPPI ? 2 + KNU : kout * (2 + KNU)) > EP_XCHG_STRIDE) return fail(h, "partial too large for the exchange slot");
     if (n_elite > 0) return fail(h, "elite lists are per rank: pass n_elite = 0 with the peer exchange");
     ep.world = h->xchg_world; ep.rank = h->xchg_rank; ep.epoch = ++h->xchg_epoch;
+    ep.stamps = h->d_stamps;
     for (int g = 0; g < h->xchg_world; g++) ep.peer[g] = (double*)h->xchg_peer[g];
   }
   return plan_costs_ep(h, d_x0, d_knots, N, K, d_basis, H, d_params, d_cost, d_reward, ep, st, smp);
@@ -510,8 +534,10 @@ extern "C" int b200mpc_plan_step_sampled(b200mpc_handle* h, const double* x0, co
   memcpy(hp + ol, lo, (size_t)nu * 8); memcpy(hp + oh, hi, (size_t)nu * 8);
   CK(cudaMemcpyAsync(h->d_in, h->h_in, o, cudaMemcpyHostToDevice, h->stream));
   // outputs (pinned, written by the kernel): [nominal | sigma | elite idx | elite knots | reward]
-  size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_ek = o_el + al16((size_t)std::max(n_elite, 1) * 8);
-  size_t o_rw = o_ek + al16((size_t)std::max(n_elite, 1) * KNU * 8), out_bytes = o_rw + (size_t)N * 8;
+  // (the fused epilogue lists max(n_elite, num_elites) rollouts: CEM's elites are part of the list even when fewer are asked for)
+  const int kslots = std::max(std::max(n_elite, optimizer == B200MPC_OPT_CEM ? (int)opt_params[0] : 0), 1);
+  size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_ek = o_el + al16((size_t)kslots * 8);
+  size_t o_rw = o_ek + al16((size_t)kslots * KNU * 8), out_bytes = o_rw + (size_t)N * 8;
   if (grow(h, &h->h_out, &h->h_out_bytes, out_bytes, true)) return 1;
   void* dout_v = nullptr;
   CK(cudaHostGetDevicePointer(&dout_v, h->h_out, 0));
@@ -785,7 +811,8 @@ extern "C" int b200mpc_plan_step(b200mpc_handle* h, const double* x0, const doub
   h->zero_copy_now = false;
   if (rc_stage) return 1;
   // packed outputs: [nominal KNU | sigma KNU | elite n_elite | reward N]
-  size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_rw = o_el + al16((size_t)std::max(n_elite, 1) * 8);
+  // (the fused epilogue lists max(n_elite, num_elites) rollouts: CEM's elites are part of the list even when fewer are asked for)
+  size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_rw = o_el + al16((size_t)std::max(std::max(n_elite, k_cem), 1) * 8);
   size_t out_bytes = o_rw + (size_t)N * 8;
   if (grow(h, &h->d_out, &h->d_out_bytes, out_bytes, false) || grow(h, &h->h_out, &h->h_out_bytes, out_bytes, true)) return 1;
   char* din = (char*)h->d_in; char* dout = (char*)h->d_out;
@@ -873,6 +900,61 @@ extern "C" int b200mpc_controller_speculation(b200mpc_handle* h, const unsigned 
   return h->znext_valid && h->znext_n == n && *mt_pos == h->snap_pos && memcmp(mt_key, h->snap_key, sizeof(h->snap_key)) == 0;
 }
 
+
+// The sampling stage of b200mpc_controller_step (shared with the multi-GPU group): fills h->zbuf with the n normals of this step's
+// block.  Returns 0 when the block is complete, 2 after a phase-1 call (the caller still owes the tail), 1 on error.
+static int step_sample(b200mpc_handle* h, b200mpc_step_request* rq, size_t n) {
+  if (rq->phase != 2) {
+    h->zbuf.resize(n + 2);
+    double* z = h->zbuf.data();
+    for (int i = 0; i < rq->n_head; i++) z[i] = rq->head[i];
+    const size_t rem = n - (size_t)rq->n_head, gen = rem & ~(size_t)1;
+    if (rq->use_speculated) {
+      // the `gen` normals that follow the head values were drawn during the previous step's GPU time (step_speculate)
+      if (!gen || !b200mpc_controller_speculation(h, rq->mt_key, rq->mt_pos, gen)) return fail(h, "the speculated block does not match the generator state");
+      memcpy(z + rq->n_head, h->znext.data(), gen * sizeof(double));
+      memcpy(rq->mt_key, h->adv_key, sizeof(h->adv_key));  // the generator now stands where drawing them would have left it
+      *rq->mt_pos = h->adv_pos;
+    } else if (gen) {
+      if (*rq->mt_pos < 0 || *rq->mt_pos > 624) return fail(h, "generator position out of range");
+      b2host::mt19937_normals(rq->mt_key, rq->mt_pos, z + rq->n_head, gen);
+    }
+    h->znext_valid = false;
+    h->step_tail_pending = (rem & 1) != 0;
+    h->step_sampled = true;
+    if (rq->phase == 1) return 2;
+    if (h->step_tail_pending) { h->step_sampled = false; return fail(h, "an odd number of normals is left: sample with phase 1, draw the last one, finish with phase 2"); }
+  } else {
+    if (!h->step_sampled || h->zbuf.size() != n + 2) return fail(h, "phase 2 without a matching phase 1");
+    if (h->step_tail_pending) {
+      if (!rq->has_tail) return fail(h, "the block is one normal short: pass it as tail");
+      h->zbuf[n - 1] = rq->tail;
+    }
+  }
+  h->step_sampled = false;
+  return 0;
+}
+
+// While the GPU works: the normals the next step will ask this library for, from a COPY of the generator state
+// (b200mpc_controller_speculation).  What the next step asks for follows from the generator's gaussian cache, which is known here:
+//   this step ended without a tail -> cache empty -> the next block (n even) is drawn here in full, no head values;
+//   this step drew a tail through numpy -> cache occupied -> the next step's head is that cached value (no state change), then
+//   (n - 1) & ~1 normals from here, then its own tail.
+static void step_speculate(b200mpc_handle* h, const b200mpc_step_request* rq, size_t n) {
+  h->znext_valid = false;
+  const size_t cnt = !h->step_tail_pending ? ((n & 1) == 0 ? n : 0) : ((n - 1) & ~(size_t)1);
+  if (rq->speculate && cnt >= 2 && rq->mt_key && rq->mt_pos && *rq->mt_pos >= 0 && *rq->mt_pos <= 624) {
+    memcpy(h->snap_key, rq->mt_key, sizeof(h->snap_key));
+    h->snap_pos = *rq->mt_pos;
+    memcpy(h->adv_key, h->snap_key, sizeof(h->adv_key));
+    h->adv_pos = h->snap_pos;
+    h->znext.resize(cnt);
+    b2host::mt19937_normals(h->adv_key, &h->adv_pos, h->znext.data(), cnt);
+    h->znext_n = cnt;
+    h->znext_valid = true;
+  }
+}
+
 extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* rq) {
   if (!h) return 1;
   if (!rq) return fail(h, "NULL request");
@@ -898,34 +980,11 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
   auto T0 = std::chrono::steady_clock::now();
 
   // ---- phase 0 / 1: draw the block of normals (head values first, then an even number straight from the generator state)
-  if (rq->phase != 2) {
-    h->zbuf.resize(n + 2);
-    double* z = h->zbuf.data();
-    for (int i = 0; i < rq->n_head; i++) z[i] = rq->head[i];
-    const size_t rem = n - (size_t)rq->n_head, gen = rem & ~(size_t)1;
-    if (rq->use_speculated) {
-      // the `gen` normals that follow the head values were drawn during the previous step's GPU time (see below)
-      if (!gen || !b200mpc_controller_speculation(h, rq->mt_key, rq->mt_pos, gen)) return fail(h, "the speculated block does not match the generator state");
-      memcpy(z + rq->n_head, h->znext.data(), gen * sizeof(double));
-      memcpy(rq->mt_key, h->adv_key, sizeof(h->adv_key));  // the generator now stands where drawing them would have left it
-      *rq->mt_pos = h->adv_pos;
-    } else if (gen) {
-      if (*rq->mt_pos < 0 || *rq->mt_pos > 624) return fail(h, "generator position out of range");
-      b2host::mt19937_normals(rq->mt_key, rq->mt_pos, z + rq->n_head, gen);
-    }
-    h->znext_valid = false;
-    h->step_tail_pending = (rem & 1) != 0;
-    h->step_sampled = true;
-    if (rq->phase == 1) return 0;
-    if (h->step_tail_pending) { h->step_sampled = false; return fail(h, "an odd number of normals is left: sample with phase 1, draw the last one, finish with phase 2"); }
-  } else {
-    if (!h->step_sampled || h->zbuf.size() != n + 2) return fail(h, "phase 2 without a matching phase 1");
-    if (h->step_tail_pending) {
-      if (!rq->has_tail) return fail(h, "the block is one normal short: pass it as tail");
-      h->zbuf[n - 1] = rq->tail;
-    }
+  {
+    const int rc = step_sample(h, rq, n);
+    if (rc == 2) return 0;   // phase 1: sampled, waiting for the caller's tail normal
+    if (rc) return 1;
   }
-  h->step_sampled = false;
   auto T1 = std::chrono::steady_clock::now();
 
   // ---- stage [x0 | basis | params | knots] in pinned memory: the basis and the candidates are produced in place
@@ -950,7 +1009,8 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
 
   // ---- outputs, written by the kernels straight into pinned host memory: [nominal | sigma | elite idx | elite sensors | reward]
   const bool kernel_traces = nts > 0 && ne > 0 && !warp_task;
-  const size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_es = o_el + al16((size_t)std::max(ne, 1) * 8);
+  const int kslots = std::max(std::max(ne, optimizer == B200MPC_OPT_CEM ? (int)rq->opt_params[0] : 0), 1);  // the epilogue lists max(n_elite, num_elites)
+  const size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_es = o_el + al16((size_t)kslots * 8);
   const size_t o_rw = o_es + (kernel_traces ? al16((size_t)ne * H * ns * 8) : 0), out_bytes = o_rw + (size_t)N * 8;
   if (grow(h, &h->h_out, &h->h_out_bytes, out_bytes, true)) return 1;
   if (kernel_traces && grow(h, &h->d_traceq, &h->d_traceq_bytes, (size_t)N * H * h->dims.nq * 8, false)) return 1;
@@ -962,25 +1022,7 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
                      (double*)(dout + o_el), nullptr, nullptr, SampleSpec{}, h->stream, kernel_traces ? (double*)h->d_traceq : nullptr,
                      kernel_traces ? (double*)(dout + o_es) : nullptr)) return 1;
   auto T3 = std::chrono::steady_clock::now();
-  // ---- while the GPU works: the normals the next step will ask this routine for, from a COPY of the generator state
-  // (b200mpc_controller_speculation).  What the next step asks for follows from the generator's gaussian cache, which is known here:
-  //   this step ended without a tail -> cache empty -> the next block (n even) is drawn here in full, no head values;
-  //   this step drew a tail through numpy -> cache occupied -> the next step's head is that cached value (no state change), then
-  //   (n - 1) & ~1 normals from here, then its own tail.
-  h->znext_valid = false;
-  {
-    const size_t cnt = !h->step_tail_pending ? ((n & 1) == 0 ? n : 0) : ((n - 1) & ~(size_t)1);
-    if (rq->speculate && cnt >= 2 && rq->mt_key && rq->mt_pos && *rq->mt_pos >= 0 && *rq->mt_pos <= 624) {
-      memcpy(h->snap_key, rq->mt_key, sizeof(h->snap_key));
-      h->snap_pos = *rq->mt_pos;
-      memcpy(h->adv_key, h->snap_key, sizeof(h->adv_key));
-      h->adv_pos = h->snap_pos;
-      h->znext.resize(cnt);
-      b2host::mt19937_normals(h->adv_key, &h->adv_pos, h->znext.data(), cnt);
-      h->znext_n = cnt;
-      h->znext_valid = true;
-    }
-  }
+  step_speculate(h, rq, n);   // while the GPU works: the next step's normals, from a copy of the generator state
   auto T3b = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(h->stream));
   if (h->timing) {  // B200MPC_TIMING=1: sample | assemble (basis, candidates) | H2D + launch | wait for the GPU
@@ -1057,4 +1099,367 @@ extern "C" int b200mpc_fp64_peak(int device, double* dfma_warp_inst_per_s) {
   cudaFree(d);
   *dfma_warp_inst_per_s = best;
   return cudaGetLastError() != cudaSuccess;
+}
+
+// ====================================================================================================================================
+// Several GPUs behind ONE backend, in one process (include/b200mpc.h: b200mpc_group_*).  The reference's Controller is a single process
+// with one rollout backend (judo/controller/controller.py:72-85); the group keeps that shape: one object, rollouts sharded along N over
+// its devices (rollout 0, the un-noised nominal, on the first), everything issued asynchronously from the calling thread.
+//   contract A: every device rolls out its slice; states / sensors land in the caller's arrays.
+//   plan step : every device runs the fused rollout+cost kernel on its slice; the slices' rewards are copied peer-to-peer into device
+//               0, which also holds all candidates and runs the optimizer update (reduction kernels over all N) and the elite
+//               selection; only nominal / sigma / elites / rewards come back.
+struct b200mpc_group {
+  std::vector<b200mpc_handle*> hs;
+  std::vector<int> lo;            // shard r owns rollouts [lo[r], lo[r+1])
+  int N = 0;
+  std::string err;
+  std::vector<cudaEvent_t> ev;    // per device: "this slice's rollouts are done"
+  cudaEvent_t ev_copy = nullptr;  // device 0: all candidates uploaded
+  cudaStream_t copy_stream = nullptr;
+  void* d_knots_all = nullptr; size_t d_knots_all_bytes = 0;    // device 0
+  void* d_reward_all = nullptr; size_t d_reward_all_bytes = 0;  // device 0
+  void* h_knots_all = nullptr; size_t h_knots_all_bytes = 0;    // pinned: the whole candidate block
+  int cand_N = 0, cand_K = 0;
+  std::vector<double> tmp;
+};
+static thread_local std::string g_group_error;
+
+static int gfail(b200mpc_group* g, const std::string& m) { g->err = m; return 1; }
+#define GCK(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) { g->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } \
+  } while (0)
+
+static void group_shards(b200mpc_group* g, int N) {
+  const int n = (int)g->hs.size(), base = N / n, rem = N % n;
+  g->lo.assign(n + 1, 0);
+  for (int r = 0; r < n; r++) g->lo[r + 1] = g->lo[r] + base + (r < rem ? 1 : 0);  // remainders go to the lowest ranks (judo_b200/dist.py:shard_range)
+  g->N = N;
+  for (int r = 0; r < n; r++) g->hs[r]->N = std::max(1, g->lo[r + 1] - g->lo[r]);
+}
+
+extern "C" const char* b200mpc_group_last_error(const b200mpc_group* g) { return g ? g->err.c_str() : g_group_error.c_str(); }
+
+extern "C" int b200mpc_group_create(b200mpc_group** out, int task_id, const double* consts, size_t n_consts, const int* devices, int n_devices,
+                                    int num_rollouts) {
+  if (!out) { g_group_error = "out is NULL"; return 1; }
+  *out = nullptr;
+  if (!devices || n_devices < 1 || n_devices > 8) { g_group_error = "1..8 devices"; return 1; }
+  if (num_rollouts <= 0) { g_group_error = "num_rollouts must be positive"; return 1; }
+  for (int i = 0; i < n_devices; i++)
+    for (int j = 0; j < i; j++) if (devices[i] == devices[j]) { g_group_error = "duplicate device"; return 1; }
+  b200mpc_group* g = new b200mpc_group();
+  for (int r = 0; r < n_devices; r++) {
+    b200mpc_handle* h = nullptr;
+    if (b200mpc_create(&h, task_id, consts, n_consts, devices[r], 1)) {
+      g_group_error = std::string("device ") + std::to_string(devices[r]) + ": " + b200mpc_last_error(nullptr);
+      for (auto* q : g->hs) b200mpc_destroy(q);
+      delete g;
+      return 1;
+    }
+    g->hs.push_back(h);
+  }
+  g->ev.resize(n_devices);
+  bool ok = true;
+  for (int r = 0; r < n_devices && ok; r++) ok = cudaSetDevice(devices[r]) == cudaSuccess && cudaEventCreateWithFlags(&g->ev[r], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaSetDevice(devices[0]) == cudaSuccess && cudaEventCreateWithFlags(&g->ev_copy, cudaEventDisableTiming) == cudaSuccess &&
+       cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) { g_group_error = "event / stream creation failed"; for (auto* q : g->hs) b200mpc_destroy(q); delete g; return 1; }
+  // direct peer access where the hardware has it (NVLink / NVSwitch); cudaMemcpyPeerAsync stages through the host otherwise
+  for (int r = 1; r < n_devices; r++) {
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, devices[0], devices[r]) == cudaSuccess && can) {
+      cudaSetDevice(devices[0]);
+      cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else cudaGetLastError();
+    }
+  }
+  group_shards(g, num_rollouts);
+  *out = g;
+  return 0;
+}
+
+extern "C" void b200mpc_group_destroy(b200mpc_group* g) {
+  if (!g) return;
+  if (!g->hs.empty()) cudaSetDevice(g->hs[0]->device);
+  if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
+  if (g->ev_copy) cudaEventDestroy(g->ev_copy);
+  cudaFree(g->d_knots_all); cudaFree(g->d_reward_all); cudaFreeHost(g->h_knots_all);
+  for (size_t r = 0; r < g->hs.size(); r++) { cudaSetDevice(g->hs[r]->device); if (g->ev[r]) cudaEventDestroy(g->ev[r]); }
+  for (auto* h : g->hs) b200mpc_destroy(h);
+  delete g;
+}
+
+extern "C" int b200mpc_group_size(const b200mpc_group* g) { return g ? (int)g->hs.size() : 0; }
+extern "C" b200mpc_handle* b200mpc_group_handle(b200mpc_group* g, int i) { return (g && i >= 0 && i < (int)g->hs.size()) ? g->hs[i] : nullptr; }
+extern "C" int b200mpc_group_num_rollouts(const b200mpc_group* g) { return g ? g->N : -1; }
+extern "C" int b200mpc_group_update(b200mpc_group* g, int num_rollouts) {
+  if (!g) return 1;
+  if (num_rollouts <= 0) return gfail(g, "num_rollouts must be positive");
+  group_shards(g, num_rollouts);
+  return 0;
+}
+extern "C" long long b200mpc_group_launch_count(const b200mpc_group* g) {
+  long long n = 0;
+  if (g) for (auto* h : g->hs) n += h->launches;
+  return n;
+}
+extern "C" long long b200mpc_group_contact_overflows(b200mpc_group* g) {
+  if (!g) return -1;
+  long long n = 0;
+  for (auto* h : g->hs) { long long v = b200mpc_contact_overflows(h); if (v < 0) { g->err = h->err; return -1; } n += v; }
+  return n;
+}
+extern "C" int b200mpc_group_set_trace_capture(b200mpc_group* g, int enable) {
+  if (!g) return 1;
+  for (auto* h : g->hs) if (b200mpc_set_trace_capture(h, enable)) return gfail(g, h->err);
+  return 0;
+}
+
+// contract A over the group: RolloutBackend.rollout with the rollouts split across the devices
+extern "C" int b200mpc_group_rollout(b200mpc_group* g, const double* x0, int batched, const double* controls, int N, int H, double* states,
+                                     double* sensors) {
+  if (!g) return 1;
+  if (!x0 || !controls || !states) return gfail(g, "NULL argument");
+  if (N != g->N) return gfail(g, "controls batch size does not match num_rollouts (call update first)");
+  if (H <= 0) return gfail(g, "H must be positive");
+  const int n = (int)g->hs.size();
+  b200mpc_handle* h0 = g->hs[0];
+  const int nx = h0->dims.nq + h0->dims.nv, nu = h0->dims.nu, ns = h0->dims.nsensordata;
+  for (int r = 0; r < n; r++) {  // issue every device's upload + launch first, then the downloads: the devices run concurrently
+    b200mpc_handle* h = g->hs[r];
+    const int lo = g->lo[r], nr = g->lo[r + 1] - lo;
+    if (nr <= 0) continue;
+    GCK(cudaSetDevice(h->device));
+    const size_t bx = al16((size_t)(batched ? nr : 1) * nx * 8), bc = (size_t)nr * H * nu * 8;
+    const size_t bs = al16((size_t)nr * H * nx * 8), be = sensors ? (size_t)nr * H * ns * 8 : 0;
+    if (grow(h, &h->d_in, &h->d_in_bytes, bx + bc, false) || grow(h, &h->d_big, &h->d_big_bytes, bs + be, false)) return gfail(g, h->err);
+    char* din = (char*)h->d_in; char* dbig = (char*)h->d_big;
+    GCK(cudaMemcpyAsync(din, x0 + (batched ? (size_t)lo * nx : 0), (size_t)(batched ? nr : 1) * nx * 8, cudaMemcpyHostToDevice, h->stream));
+    GCK(cudaMemcpyAsync(din + bx, controls + (size_t)lo * H * nu, bc, cudaMemcpyHostToDevice, h->stream));
+    if (b200mpc_rollout_dev(h, (double*)din, batched, (double*)(din + bx), nr, H, (double*)dbig, sensors ? (double*)(dbig + bs) : nullptr, h->stream))
+      return gfail(g, h->err);
+  }
+  for (int r = 0; r < n; r++) {
+    b200mpc_handle* h = g->hs[r];
+    const int lo = g->lo[r], nr = g->lo[r + 1] - lo;
+    if (nr <= 0) continue;
+    GCK(cudaSetDevice(h->device));
+    const size_t bs = al16((size_t)nr * H * nx * 8);
+    char* dbig = (char*)h->d_big;
+    GCK(cudaMemcpyAsync(states + (size_t)lo * H * nx, dbig, (size_t)nr * H * nx * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (sensors) GCK(cudaMemcpyAsync(sensors + (size_t)lo * H * ns, dbig + bs, (size_t)nr * H * ns * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  for (int r = 0; r < n; r++) { GCK(cudaSetDevice(g->hs[r]->device)); GCK(cudaStreamSynchronize(g->hs[r]->stream)); }
+  return 0;
+}
+
+// The sharded plan step over candidates that sit in g->h_knots_all (pinned).  Outputs as b200mpc_plan_step; elite_knots (n_elite, K*nu) may
+// be NULL.
+static int group_plan_core(b200mpc_group* g, const double* x0, int N, int K, const double* basis, int H, const double* params, int optimizer,
+                           const double* opt_params, double* nominal, double* sigma, double* reward_N, int* elite_idx, int n_elite,
+                           double* elite_knots) {
+  const int n = (int)g->hs.size();
+  b200mpc_handle* h0 = g->hs[0];
+  const int nx = h0->dims.nq + h0->dims.nv, nu = h0->dims.nu, np = h0->dims.n_cost_params, KNU = K * nu;
+  if (optimizer < 0 || optimizer > 2) return gfail(g, "unknown optimizer");
+  if (optimizer == B200MPC_OPT_MPPI && !(opt_params && opt_params[0] > 0)) return gfail(g, "temperature must be positive");
+  if (optimizer == B200MPC_OPT_CEM && (!opt_params || (int)opt_params[0] <= 0 || (int)opt_params[0] > 256)) return gfail(g, "CEM needs {num_elites in 1..256, sigma_min, sigma_max}");
+  if (n_elite < 0 || n_elite > 256) return gfail(g, "n_elite must be in 0..256");
+  const double* knots_all = (const double*)g->h_knots_all;
+  // device 0: all candidates (the update's weighted sums and the elite rows read them), uploaded on its own stream while the rollouts run
+  GCK(cudaSetDevice(h0->device));
+  if (grow(h0, &g->d_knots_all, &g->d_knots_all_bytes, (size_t)N * KNU * 8, false) || grow(h0, &g->d_reward_all, &g->d_reward_all_bytes, (size_t)N * 8, false))
+    return gfail(g, h0->err);
+  GCK(cudaMemcpyAsync(g->d_knots_all, knots_all, (size_t)N * KNU * 8, cudaMemcpyHostToDevice, g->copy_stream));
+  GCK(cudaEventRecord(g->ev_copy, g->copy_stream));
+  for (int r = 0; r < n; r++) {
+    b200mpc_handle* h = g->hs[r];
+    const int lo = g->lo[r], nr = g->lo[r + 1] - lo;
+    if (nr <= 0) continue;
+    GCK(cudaSetDevice(h->device));
+    size_t o = 0;
+    const size_t ox0 = o; o += al16((size_t)nx * 8);
+    const size_t ob = o; o += al16((size_t)H * K * 8);
+    const size_t op = o; o += al16((size_t)np * 8);
+    const size_t small = o;
+    const size_t ok = o; o += (size_t)nr * KNU * 8;
+    if (grow(h, &h->h_in, &h->h_in_bytes, small, true) || grow(h, &h->d_in, &h->d_in_bytes, o, false) ||
+        grow(h, &h->d_big, &h->d_big_bytes, (size_t)nr * 8, false)) return gfail(g, h->err);
+    char* hp = (char*)h->h_in;
+    memcpy(hp + ox0, x0, (size_t)nx * 8); memcpy(hp + ob, basis, (size_t)H * K * 8); memcpy(hp + op, params, (size_t)np * 8);
+    char* din = (char*)h->d_in;
+    GCK(cudaMemcpyAsync(din, hp, small, cudaMemcpyHostToDevice, h->stream));
+    GCK(cudaMemcpyAsync(din + ok, knots_all + (size_t)lo * KNU, (size_t)nr * KNU * 8, cudaMemcpyHostToDevice, h->stream));  // straight from the pinned block
+    PlanEpilogue none{};
+    none.optimizer = EP_NONE;
+    none.index_offset = lo;
+    if (plan_costs_ep(h, (double*)(din + ox0), (double*)(din + ok), nr, K, (double*)(din + ob), H, (double*)(din + op), nullptr, (double*)h->d_big, none,
+                      h->stream)) return gfail(g, h->err);
+    GCK(cudaEventRecord(g->ev[r], h->stream));
+  }
+  // device 0: collect the slices' rewards, then the update over all N
+  GCK(cudaSetDevice(h0->device));
+  cudaStream_t s0 = h0->stream;
+  for (int r = 0; r < n; r++) {
+    const int lo = g->lo[r], nr = g->lo[r + 1] - lo;
+    if (nr <= 0) continue;
+    if (r > 0) GCK(cudaStreamWaitEvent(s0, g->ev[r], 0));
+    GCK(cudaMemcpyPeerAsync((double*)g->d_reward_all + lo, h0->device, g->hs[r]->d_big, g->hs[r]->device, (size_t)nr * 8, s0));
+  }
+  GCK(cudaStreamWaitEvent(s0, g->ev_copy, 0));
+  const size_t o_nom = 0, o_sig = al16((size_t)KNU * 8), o_el = o_sig + al16((size_t)KNU * 8), o_ek = o_el + al16((size_t)std::max(n_elite, 1) * 8);
+  const size_t o_rw = o_ek + al16((size_t)std::max(n_elite, 1) * KNU * 8), out_bytes = o_rw + (size_t)N * 8;
+  if (grow(h0, &h0->h_out, &h0->h_out_bytes, out_bytes, true)) return gfail(g, h0->err);
+  void* dout_v = nullptr;
+  GCK(cudaHostGetDevicePointer(&dout_v, h0->h_out, 0));
+  char* dout = (char*)dout_v;
+  const double* dk = (const double*)g->d_knots_all;
+  const double* dr = (const double*)g->d_reward_all;
+  if (run_update(h0, optimizer, opt_params, dk, dr, N, KNU, (double*)(dout + o_nom), (double*)(dout + o_sig), nullptr, 0, s0)) return gfail(g, h0->err);
+  if (n_elite > 0) {
+    const int nb = n_partials_for(N);
+    const size_t need = 16 + (size_t)nb * n_elite * (2 + KNU) * 8 + al16((size_t)KNU * 8);  // 16: the ticket slot in front
+    if (need > h0->d_part_bytes) { GCK(cudaStreamSynchronize(s0)); if (grow(h0, &h0->d_part, &h0->d_part_bytes, need, false)) return gfail(g, h0->err); GCK(cudaMemsetAsync(h0->d_part, 0, 16, s0)); }
+    double* part = (double*)h0->d_part + 2;
+    double* dummy = part + (size_t)nb * n_elite * (2 + KNU);
+    topk_partial_kernel<<<nb, 256, 0, s0>>>(dk, dr, N, KNU, n_elite, 0, 1, part);
+    h0->launches++;
+    GCK(cudaGetLastError());
+    if (b200mpc_topk_combine_dev(h0, part, nb, KNU, n_elite, 1, 0, 0, dummy, nullptr, (double*)(dout + o_el), s0)) return gfail(g, h0->err);
+    gather_rows_kernel<<<n_elite, 64, 0, s0>>>(dk, (double*)(dout + o_el), 0, KNU, (double*)(dout + o_ek));
+    h0->launches++;
+    GCK(cudaGetLastError());
+  }
+  if (reward_N) GCK(cudaMemcpyAsync((char*)h0->h_out + o_rw, g->d_reward_all, (size_t)N * 8, cudaMemcpyDeviceToHost, s0));
+  GCK(cudaStreamSynchronize(s0));
+  const char* ho = (const char*)h0->h_out;
+  memcpy(nominal, ho + o_nom, (size_t)KNU * 8);
+  if (sigma && optimizer == B200MPC_OPT_CEM) memcpy(sigma, ho + o_sig, (size_t)KNU * 8);
+  if (elite_idx) for (int i = 0; i < n_elite; i++) elite_idx[i] = (int)((const double*)(ho + o_el))[i];
+  if (elite_knots && n_elite > 0) memcpy(elite_knots, ho + o_ek, (size_t)n_elite * KNU * 8);
+  if (reward_N) memcpy(reward_N, ho + o_rw, (size_t)N * 8);
+  return 0;
+}
+
+extern "C" int b200mpc_group_plan_step(b200mpc_group* g, const double* x0, const double* knots, int N, int K, const double* basis, int H,
+                                       const double* params, int optimizer, const double* opt_params, double* nominal, double* sigma,
+                                       double* reward_N, int* elite_idx, int n_elite) {
+  if (!g) return 1;
+  if (!x0 || !knots || !basis || !params || !nominal) return gfail(g, "NULL argument");
+  if (N <= 0 || H <= 0 || K <= 0) return gfail(g, "N, H and K must be positive");
+  if (N != g->N) return gfail(g, "knots batch size does not match num_rollouts (call update first)");
+  b200mpc_handle* h0 = g->hs[0];
+  const size_t bytes = (size_t)N * K * h0->dims.nu * 8;
+  GCK(cudaSetDevice(h0->device));
+  if (grow(h0, &g->h_knots_all, &g->h_knots_all_bytes, bytes, true)) return gfail(g, h0->err);
+  memcpy(g->h_knots_all, knots, bytes);
+  g->cand_N = N; g->cand_K = K;
+  return group_plan_core(g, x0, N, K, basis, H, params, optimizer, opt_params, nominal, sigma, reward_N, elite_idx, n_elite, nullptr);
+}
+
+// trace sensors (ne, H, trace_width) of the given GLOBAL rollout indices of the last plan step (warp-per-rollout tasks with trace capture)
+extern "C" int b200mpc_group_elite_traces(b200mpc_group* g, const int* idx, int ne, int H, double* out) {
+  if (!g) return 1;
+  if (!idx || !out || ne <= 0) return gfail(g, "NULL / empty argument");
+  const int nt = trace_width(g->hs[0]);
+  const size_t row = (size_t)H * nt * 8;
+  for (int i = 0; i < ne; i++) {
+    int r = 0;
+    while (r + 1 < (int)g->hs.size() && idx[i] >= g->lo[r + 1]) r++;
+    b200mpc_handle* h = g->hs[r];
+    const int loc = idx[i] - g->lo[r];
+    if (!h->trace_capture || h->trace_N == 0) return gfail(g, "no captured traces: enable trace capture and run a plan step first");
+    if (H != h->trace_H || loc < 0 || loc >= h->trace_N) return gfail(g, "rollout index / H do not match the captured plan step");
+    GCK(cudaSetDevice(h->device));
+    GCK(cudaMemcpyAsync((char*)out + (size_t)i * row, (const char*)h->d_trace + (size_t)loc * row, row, cudaMemcpyDeviceToHost, h->stream));
+  }
+  for (auto* h : g->hs) { GCK(cudaSetDevice(h->device)); GCK(cudaStreamSynchronize(h->stream)); }
+  return 0;
+}
+
+extern "C" int b200mpc_group_last_candidates(b200mpc_group* g, double* knots_out, int N, int K) {
+  if (!g) return 1;
+  if (!knots_out || !g->h_knots_all || g->cand_N == 0) return gfail(g, "no candidates: run a plan step first");
+  if (N != g->cand_N || K != g->cand_K) return gfail(g, "N / K do not match the last plan step");
+  memcpy(knots_out, g->h_knots_all, (size_t)N * K * g->hs[0]->dims.nu * 8);
+  return 0;
+}
+
+extern "C" int b200mpc_group_controller_speculation(b200mpc_group* g, const unsigned int* mt_key, const int* mt_pos, size_t n) {
+  return g ? b200mpc_controller_speculation(g->hs[0], mt_key, mt_pos, n) : 0;
+}
+
+// b200mpc_controller_step over the group: same request, same sampling protocol (the generator bookkeeping lives in the first handle)
+extern "C" int b200mpc_group_controller_step(b200mpc_group* g, b200mpc_step_request* rq) {
+  if (!g) return 1;
+  if (!rq) return gfail(g, "NULL request");
+  b200mpc_handle* h0 = g->hs[0];
+  const int N = rq->N, K = rq->K, H = rq->H;
+  if (!rq->x0 || !rq->nominal || !rq->sigma || !rq->lo || !rq->hi || !rq->cost_params || !rq->knot_times || !rq->nominal_out) return gfail(g, "NULL argument");
+  if (N <= 0 || H <= 0 || K <= 0) return gfail(g, "N, H and K must be positive");
+  if (N != g->N) return gfail(g, "N does not match num_rollouts (call update first)");
+  if (rq->phase < 0 || rq->phase > 2) return gfail(g, "phase must be 0, 1 or 2");
+  const int nu = h0->dims.nu, KNU = K * nu, ns = h0->dims.nsensordata;
+  const size_t n = (size_t)(N - 1) * KNU;
+  if (rq->n_head < 0 || rq->n_head > 2 || (size_t)rq->n_head > n) return gfail(g, "n_head must be 0..2 and <= (N-1)*K*nu");
+  if (n > (size_t)rq->n_head && (!rq->mt_key || !rq->mt_pos)) return gfail(g, "NULL generator state");
+  const bool warp_task = h0->task == B200MPC_TASK_LEAP_CUBE || h0->task == B200MPC_TASK_FR3_PICK;
+  const int nts = rq->n_trace_sensors, ne = rq->n_elite;
+  if (nts < 0 || (nts > 0 && (!rq->trace_cols || !rq->traces))) return gfail(g, "trace sensors requested without trace_cols / traces");
+  if (nts > 0 && warp_task && (!h0->trace_capture || trace_width(h0) != 3 * nts)) return gfail(g, "enable trace capture for the traces of this task");
+  {
+    const int rc = step_sample(h0, rq, n);
+    if (rc == 2) return 0;
+    if (rc) return gfail(g, h0->err);
+  }
+  GCK(cudaSetDevice(h0->device));
+  if (grow(h0, &g->h_knots_all, &g->h_knots_all_bytes, (size_t)N * KNU * 8, true)) return gfail(g, h0->err);
+  std::vector<double> basis((size_t)H * K);
+  h0->qtimes.resize(H);
+  for (int i = 0; i < H; i++) h0->qtimes[i] = rq->time + rq->dt * (double)i;
+  if (b2host::spline_basis(rq->spline_order, rq->knot_times, K, h0->qtimes.data(), H, basis.data())) return gfail(g, "bad spline request (order / number of knots)");
+  if (rq->basis_out) memcpy(rq->basis_out, basis.data(), (size_t)H * K * 8);
+  b2host::assemble_candidates(h0->zbuf.data(), rq->nominal, rq->sigma, rq->lo, rq->hi, N, K, nu, (double*)g->h_knots_all);
+  g->cand_N = N; g->cand_K = K;
+  if (rq->knots_out) memcpy(rq->knots_out, g->h_knots_all, (size_t)N * KNU * 8);
+  // The sharded step blocks until device 0 has the result; the next block of normals is drawn first only when the rollouts are long enough
+  // to hide it (the warp-per-rollout tasks), otherwise after.
+  std::vector<double> ek((size_t)std::max(ne, 1) * KNU);
+  int el[256];
+  if (warp_task) step_speculate(h0, rq, n);
+  if (group_plan_core(g, rq->x0, N, K, basis.data(), H, rq->cost_params, rq->optimizer, rq->opt_params, rq->nominal_out, rq->sigma_out, rq->rewards,
+                      el, ne, ek.data())) return 1;
+  if (!warp_task) step_speculate(h0, rq, n);
+  if (rq->elite_idx) for (int i = 0; i < ne; i++) rq->elite_idx[i] = el[i];
+  if (nts > 0 && ne > 0) {
+    if (warp_task) {
+      const int nt = 3 * nts;
+      if (nt > 48) return gfail(g, "too many trace sensors");
+      g->tmp.resize((size_t)ne * H * nt);
+      if (b200mpc_group_elite_traces(g, el, ne, H, g->tmp.data())) return 1;
+      int cols[48];
+      for (int i = 0; i < nt; i++) cols[i] = i;
+      b2host::trace_segments(g->tmp.data(), ne, H, nt, cols, nts, rq->traces);
+    } else {
+      // thread-per-rollout tasks: re-simulate the <= 8 elite candidates on the first device (microseconds) and read their sensors
+      std::vector<double> ctrl((size_t)ne * H * nu, 0.0), st((size_t)ne * H * (h0->dims.nq + h0->dims.nv)), se((size_t)ne * H * ns);
+      for (int e = 0; e < ne; e++)
+        for (int t = 0; t < H; t++)
+          for (int k = 0; k < K; k++) {
+            const double b = basis[(size_t)t * K + k];
+            if (b != 0.0) for (int j = 0; j < nu; j++) ctrl[((size_t)e * H + t) * nu + j] += b * ek[(size_t)e * KNU + k * nu + j];
+          }
+      const int keep = h0->N;
+      h0->N = ne;
+      const int rc = b200mpc_rollout(h0, rq->x0, 0, ctrl.data(), ne, H, st.data(), se.data());
+      h0->N = keep;
+      if (rc) return gfail(g, h0->err);
+      b2host::trace_segments(se.data(), ne, H, ns, rq->trace_cols, nts, rq->traces);
+    }
+  }
+  return 0;
 }

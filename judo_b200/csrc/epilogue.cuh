@@ -21,6 +21,7 @@ struct PlanEpilogue {
   int optimizer;          // EP_*
   int k;                  // best rollouts to list (descending, ties: higher index first), 0..EP_MAXK
   int k_cem;              // elites entering CEM's mean/var (<= k)
+  int n_trace;            // elites whose sensors go to elite_sens (<= k): the caller's n_elite
   int finalize;           // 1: write nominal/sigma/elite;  0: write rank partials for the exchange
   int index_offset;       // global index of this launch's rollout 0
   double temperature, sigma_min, sigma_max;
@@ -44,8 +45,9 @@ struct PlanEpilogue {
   int world, rank;
   unsigned long long epoch;
   double* peer[8];        // peer[g]: exchange buffer of rank g mapped into this process (peer[rank] is local)
+  unsigned long long* stamps;  // optional (finalize == 2): %globaltimer at [0] kernel entry (block 0), [1] partial published, [2] all peers seen
 };
-constexpr int EP_XCHG_FLAGS = 8;                   // u64 flags in front of the partial slots
+constexpr int EP_XCHG_FLAGS = 16;                  // u64 flags in front of the partial slots: [0..8) step epochs, [8..16) align epochs
 constexpr int EP_XCHG_STRIDE = 2 + 96;             // doubles per rank slot (beta, S, V[<=96])
 constexpr size_t EP_XCHG_BYTES = 8 * EP_XCHG_FLAGS + 2 * 8 * (size_t)EP_XCHG_STRIDE * 8;  // slots double-buffered by epoch parity
 
@@ -62,6 +64,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 #endif
+
+__device__ __forceinline__ unsigned long long global_ns() {
+#ifdef B2_HOST_SIM
+  return 0;
+#else
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#endif
+}
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ double wsum(double v) {
@@ -95,6 +107,7 @@ __device__ __forceinline__ void warp_best(double& r, long long& i, bool prefer_h
 __device__ inline bool peer_signal_and_wait(const PlanEpilogue& ep, int lane) {
   __threadfence_system();
   __syncwarp();
+  if (ep.stamps && lane == 0) ep.stamps[1] = global_ns();
   if (lane < ep.world) st_release_sys(reinterpret_cast<unsigned long long*>(ep.peer[lane]) + ep.rank, ep.epoch);
   bool ok = true;
   if (lane < ep.world) {
@@ -102,7 +115,22 @@ __device__ inline bool peer_signal_and_wait(const PlanEpilogue& ep, int lane) {
     int spins = 0;
     while (ld_acquire_sys(fl) < ep.epoch) { __nanosleep(64); if (++spins > (1 << 22)) { ok = false; break; } }
   }
-  return __all_sync(0xffffffffu, ok);
+  const bool all_ok = __all_sync(0xffffffffu, ok);
+  if (ep.stamps && lane == 0) ep.stamps[2] = global_ns();
+  return all_ok;
+}
+
+// Line the ranks up WITHOUT exchanging data: raise this rank's align flag in every peer buffer and wait for all of them.  bench.py runs it
+// between the L2 flush and the start event so that the timed step measures the exchange, not how differently long the flushes took.
+__global__ void exchange_align_kernel(PlanEpilogue ep) {
+  const int lane = threadIdx.x & 31;
+  __threadfence_system();
+  if (lane < ep.world) st_release_sys(reinterpret_cast<unsigned long long*>(ep.peer[lane]) + 8 + ep.rank, ep.epoch);
+  if (lane < ep.world) {
+    const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(ep.peer[ep.rank]) + 8 + lane;
+    int spins = 0;
+    while (ld_acquire_sys(fl) < ep.epoch) { __nanosleep(32); if (++spins > (1 << 22)) break; }
+  }
 }
 
 // Final stage, run by one full warp after all partials are visible.  knots: this launch's (N, KNU) candidates.

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
   const int n0 = blockIdx.x * nthr, n = n0 + tid;
   const int nblk = min(nthr, N - n0);
 
+  if (ep.stamps && blockIdx.x == 0 && tid == 0) ep.stamps[0] = global_ns();
   typename Task::State s;
   if constexpr (COST) {
     // shared layout: [mbarrier 16B][basis H*K doubles (padded to 16B)][knots nthr*K*NU doubles][cost tile nthr*(H+1) floats]
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
         // position sensors in mj_forward, i.e. at the PRE-step state: step 0 sees x0, step t the positions after step t-1.
         // (Every rollout's trace_q stores precede its warp's ticket (threadfence + atomic), so they are visible here; __ldcg reads L2.)
         const int lane = tid & 31;
-        for (int idx = lane; idx < ne * H; idx += 32) {
+        const int nt = min(ne, ep.n_trace);
+        for (int idx = lane; idx < nt * H; idx += 32) {
           const int e = idx / H, t = idx - e * H;
           long long r = el[0];
 #pragma unroll

@@ -91,6 +91,17 @@ class ShardedPlanner:
         self.peer_exchange = ok
         return ok
 
+    def align(self) -> None:
+        """Line the ranks' GPUs up on the current stream (no data moves): a one-warp kernel that signals every peer and waits for all."""
+        st = ctypes.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+        self._check(self.lib.b200mpc_exchange_align_dev(self.engine.handle, st))
+
+    def exchange_stamps(self) -> tuple[int, int, int]:
+        """%globaltimer (ns) of the last in-kernel-exchange step: kernel entry, partial published, all peers seen."""
+        out = (ctypes.c_ulonglong * 3)()
+        self._check(self.lib.b200mpc_exchange_stamps(self.engine.handle, out))
+        return int(out[0]), int(out[1]), int(out[2])
+
     def set_problem(self, x0: np.ndarray, basis: np.ndarray, cost_params: np.ndarray, want_cost_matrix: bool = True) -> None:
         t = self.torch
         self.H, self.K = basis.shape

@@ -289,3 +289,111 @@ class Engine:
             ctypes.c_ulonglong(int(seed) & (2**64 - 1)), ctypes.c_ulonglong(int(counter) & (2**64 - 1)), int(index_offset), _p(nom_out),
             _p(sig_out), _p(rewards), elite.ctypes.data, int(n_elite), _p(elite_knots), _p(knots)))
         return dict(nominal=nom_out, sigma=sig_out, rewards=rewards, elite=elite[:n_elite], elite_knots=elite_knots[:n_elite], knots=knots)
+
+
+class MultiEngine(Engine):
+    """One engine over several GPUs of THIS process (b200mpc_group_*, include/b200mpc.h): rollouts sharded along N over ``devices``
+    (rollout 0, the un-noised nominal, on the first), the optimizer update over all of them on the first device.  Same methods as Engine;
+    entry points that have no sharded form (reward(), update_*, plan_costs, plan_step_sampled) run on the first device."""
+
+    def __init__(self, task: str, num_rollouts: int, devices: "list[int]", consts: np.ndarray | None = None) -> None:
+        self._lib = _lib.load()
+        self.task = task
+        c = _c(task_consts(task) if consts is None else consts)
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        g = ctypes.c_void_p()
+        if self._lib.b200mpc_group_create(ctypes.byref(g), TASK_IDS[task], _p(c), c.size, dv.ctypes.data, len(dv), int(num_rollouts)):
+            raise RuntimeError("b200mpc_group_create: " + self._lib.b200mpc_group_last_error(None).decode())
+        self._g = g
+        self._h = ctypes.c_void_p(self._lib.b200mpc_group_handle(g, 0))
+        d = _lib.Dims()
+        self._check(self._lib.b200mpc_get_dims(self._h, ctypes.byref(d)))
+        self.nq, self.nv, self.nu, self.nsensordata, self.n_cost_params = d.nq, d.nv, d.nu, d.nsensordata, d.n_cost_params
+        self.devices, self.device = [int(x) for x in dv], int(dv[0])
+
+    def close(self) -> None:
+        if getattr(self, "_g", None):
+            self._lib.b200mpc_group_destroy(self._g)
+            self._g, self._h = None, None
+
+    def _gcheck(self, rc: int) -> None:
+        if rc:
+            raise RuntimeError(self._lib.b200mpc_group_last_error(self._g).decode())
+
+    @property
+    def num_rollouts(self) -> int:
+        return self._lib.b200mpc_group_num_rollouts(self._g)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.b200mpc_group_launch_count(self._g))
+
+    @property
+    def contact_overflows(self) -> int:
+        n = int(self._lib.b200mpc_group_contact_overflows(self._g))
+        if n < 0:
+            raise RuntimeError(self._lib.b200mpc_group_last_error(self._g).decode())
+        return n
+
+    def update(self, num_rollouts: int) -> None:
+        self._gcheck(self._lib.b200mpc_group_update(self._g, int(num_rollouts)))
+
+    def set_trace_capture(self, enable: bool) -> None:
+        self._gcheck(self._lib.b200mpc_group_set_trace_capture(self._g, int(enable)))
+
+    def elite_traces(self, idx: np.ndarray, H: int) -> np.ndarray:
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = np.empty((len(idx), H, self.trace_width))
+        self._gcheck(self._lib.b200mpc_group_elite_traces(self._g, idx.ctypes.data, len(idx), int(H), out.ctypes.data))
+        return out
+
+    def rollout(self, x0: np.ndarray, controls: np.ndarray, want_sensors: bool = True) -> tuple[np.ndarray, np.ndarray | None]:
+        x0, controls = _c(x0), _c(controls)
+        N, H, _ = controls.shape
+        states = np.empty((N, H, self.nq + self.nv))
+        sensors = np.empty((N, H, self.nsensordata)) if want_sensors else None
+        self._gcheck(self._lib.b200mpc_group_rollout(self._g, _p(x0), int(x0.ndim == 2), _p(controls), N, H, _p(states), _p(sensors)))
+        return states, sensors
+
+    def plan_step(self, x0: np.ndarray, knots: np.ndarray, basis: np.ndarray, cost_params: np.ndarray, optimizer: str,
+                  opt_params: np.ndarray, want_rewards: bool = True, n_elite: int = 0) -> dict:
+        x0, knots, basis, cost_params = _c(x0), _c(knots), _c(basis), _c(cost_params)
+        op = _c(np.atleast_1d(opt_params)) if opt_params is not None and np.size(opt_params) else np.zeros(1)
+        N, K, nu = knots.shape
+        H = basis.shape[0]
+        assert basis.shape == (H, K) and cost_params.size == self.n_cost_params and x0.shape == (self.nq + self.nv,) and nu == self.nu
+        nominal = np.empty((K, nu))
+        sigma = np.empty((K, nu)) if optimizer == "cem" else None
+        rewards = np.empty(N) if want_rewards else None
+        elite = np.empty(max(n_elite, 1), dtype=np.int32)
+        self._gcheck(self._lib.b200mpc_group_plan_step(self._g, _p(x0), _p(knots), N, K, _p(basis), H, _p(cost_params), OPT_IDS[optimizer], _p(op),
+                                                       _p(nominal), _p(sigma), _p(rewards), elite.ctypes.data, int(n_elite)))
+        return dict(nominal=nominal, sigma=sigma, rewards=rewards, elite=elite[:n_elite])
+
+    def controller_step(self, rq: "_lib.StepRequest", stream: LegacyStream, n_normals: int) -> None:
+        rq.mt_key, rq.mt_pos = stream.key_addr, stream.pos_addr
+        spec = self.speculative_sampling and n_normals >= self.SPECULATE_MIN
+        rq.speculate, rq.use_speculated = int(spec), 0
+        holds = self._lib.b200mpc_group_controller_speculation
+        if spec and not (n_normals & 1) and holds(self._g, stream.key_addr, stream.pos_addr, n_normals):
+            head = []
+            rq.use_speculated = 1
+        else:
+            head = stream.head(n_normals)
+            if spec and holds(self._g, stream.key_addr, stream.pos_addr, (n_normals - len(head)) & ~1):
+                rq.use_speculated = 1
+        rq.n_head = len(head)
+        for i, z in enumerate(head):
+            rq.head[i] = z
+        if (n_normals - len(head)) & 1:
+            rq.phase = 1
+            self._gcheck(self._lib.b200mpc_group_controller_step(self._g, ctypes.addressof(rq)))
+            rq.tail, rq.has_tail, rq.phase = stream.tail(), 1, 2
+        else:
+            rq.has_tail, rq.phase = 0, 0
+        self._gcheck(self._lib.b200mpc_group_controller_step(self._g, ctypes.addressof(rq)))
+
+    def last_candidates(self, N: int, K: int) -> np.ndarray:
+        out = np.empty((N, K, self.nu))
+        self._gcheck(self._lib.b200mpc_group_last_candidates(self._g, out.ctypes.data, int(N), int(K)))
+        return out

@@ -13,7 +13,7 @@ from abc import ABC, abstractmethod
 
 import numpy as np
 
-from judo_b200.engine import Engine
+from judo_b200.engine import Engine, MultiEngine
 
 
 class RolloutBackend(ABC):
@@ -34,8 +34,9 @@ class RolloutBackend(ABC):
 class B200RolloutBackend(RolloutBackend):
     """GPU rollouts behind the reference's backend contract."""
 
-    def __init__(self, model: "str | object", num_threads: int, device: int = 0) -> None:
-        """``model``: a task name ("cartpole", "cylinder_push", "leap_cube"), a judo_b200 Task, or an Engine."""
+    def __init__(self, model: "str | object", num_threads: int, device: int = 0, devices: "list[int] | None" = None) -> None:
+        """``model``: a task name ("cartpole", "cylinder_push", "leap_cube", "fr3_pick"), a judo_b200 Task, or an Engine.
+        ``devices``: several GPUs of this process behind the one backend (rollouts sharded along N)."""
         if isinstance(model, Engine):
             self.engine = model
             self.engine.update(num_threads)
@@ -43,7 +44,8 @@ class B200RolloutBackend(RolloutBackend):
             name = model if isinstance(model, str) else getattr(model, "name", None)
             if not isinstance(name, str):
                 raise ValueError("B200RolloutBackend needs a task name, a judo_b200 Task or an Engine")
-            self.engine = Engine(name, num_threads, device=device)
+            self.engine = MultiEngine(name, num_threads, devices) if devices is not None and len(devices) > 1 else \
+                Engine(name, num_threads, device=(devices[0] if devices else device))
         self.num_threads = num_threads
 
     def rollout(self, x0: np.ndarray, controls: np.ndarray, last_policy_output: np.ndarray | None = None

@@ -108,3 +108,133 @@ def test_two_gpu_step_matches_unsharded(mode, optimizer, opt_params):
     for rank, outs, r, lo, hi in res:
         for o in outs:
             np.testing.assert_allclose(o, ref, rtol=1e-11, atol=1e-13)   # identical nominal on every rank, every step
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# several GPUs of ONE process behind the backend / Controller surface (b200mpc_group_*, MultiEngine)
+def _need(devs):
+    import torch
+
+    if torch.cuda.device_count() < len(devs):
+        pytest.skip(f"needs {len(devs)} GPUs")
+
+
+@pytest.mark.parametrize("devs", [[0], [0, 1]])
+@pytest.mark.parametrize("task,N,H", [("cartpole", 1001, 40), ("cylinder_push", 130, 30), ("leap_cube", 9, 12), ("fr3_pick", 5, 20)])
+def test_group_rollout_equals_single_gpu(devs, task, N, H):
+    _need(devs)
+    from judo_b200.engine import Engine, MultiEngine
+
+    rng = np.random.default_rng(3)
+    single, multi = Engine(task, N), MultiEngine(task, N, devs)
+    nx, nu = single.nq + single.nv, single.nu
+    if task == "leap_cube":
+        from judo_b200.tasks.leap_cube import QPOS_HOME
+        x0 = np.concatenate([QPOS_HOME, np.zeros(22)]); x0[2] = 0.07
+        u = QPOS_HOME[7:] + 0.3 * rng.normal(size=(N, H, nu))
+    elif task == "fr3_pick":
+        from tests.fr3_cases import scenario
+        x0, u = scenario("grasp", N, H)
+    else:
+        x0 = 0.3 * rng.normal(size=nx) + (np.array([0, 3.0, 0, 0]) if task == "cartpole" else np.array([1.0, 0, 1.4, 0.1, 0, 0, 0, 0]))
+        u = rng.normal(size=(N, H, nu))
+    s1, e1 = single.rollout(x0, u)
+    s2, e2 = multi.rollout(x0, u)
+    np.testing.assert_array_equal(s1, s2)
+    np.testing.assert_array_equal(e1, e2)
+    xb = np.tile(x0, (N, 1)) + (0.0 if task in ("leap_cube", "fr3_pick") else 0.01 * rng.normal(size=(N, nx)))   # batched x0 is sharded too
+    np.testing.assert_array_equal(single.rollout(xb, u)[0], multi.rollout(xb, u)[0])
+    single.close(); multi.close()
+
+
+@pytest.mark.parametrize("devs", [[0], [0, 1]])
+@pytest.mark.parametrize("optimizer,opt_params", [("mppi", [0.05]), ("cem", [3, 0.1, 1.0]), ("cem", [11, 0.1, 1.0]), ("ps", [])])
+def test_group_plan_step_equals_single_gpu_and_the_reference_update(devs, optimizer, opt_params):
+    _need(devs)
+    from judo_b200.engine import Engine, MultiEngine
+    from oracle import plan as op
+
+    N = 1003
+    x0, knots, basis, params = _problem(N)
+    single, multi = Engine("cartpole", N), MultiEngine("cartpole", N, devs)
+    a = single.plan_step(x0, knots, basis, params, optimizer, np.array(opt_params), n_elite=5)
+    b = multi.plan_step(x0, knots, basis, params, optimizer, np.array(opt_params), n_elite=5)
+    np.testing.assert_array_equal(a["rewards"], b["rewards"])
+    np.testing.assert_array_equal(a["elite"], b["elite"])
+    ref = {"mppi": lambda: op.mppi_update(knots, a["rewards"], 0.05), "cem": lambda: op.cem_update(knots, a["rewards"], int(opt_params[0]), 0.1, 1.0)[0],
+           "ps": lambda: op.ps_update(knots, a["rewards"])}[optimizer]()
+    np.testing.assert_allclose(b["nominal"], ref, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(b["nominal"], a["nominal"], rtol=1e-11, atol=1e-13)
+    if optimizer == "cem":
+        np.testing.assert_allclose(b["sigma"], a["sigma"], rtol=1e-11, atol=1e-13)
+    multi.update(77)
+    assert multi.num_rollouts == 77
+    c = multi.plan_step(x0, knots[:77], basis, params, optimizer, np.array(opt_params), n_elite=2)
+    single.update(77)
+    d = single.plan_step(x0, knots[:77], basis, params, optimizer, np.array(opt_params), n_elite=2)
+    np.testing.assert_array_equal(c["rewards"], d["rewards"])
+    np.testing.assert_allclose(c["nominal"], d["nominal"], rtol=1e-11, atol=1e-13)
+    single.close(); multi.close()
+
+
+@pytest.mark.parametrize("devs", [[0], [0, 1]])
+@pytest.mark.parametrize("task,opt,N,kw", [("cartpole", "mppi", 1025, {}), ("cylinder_push", "cem", 64, {}), ("leap_cube", "mppi", 10, {"horizon": 0.15}),
+                                           ("fr3_pick", "cem", 6, {"horizon": 0.08})])
+def test_controller_over_a_device_group_equals_the_single_gpu_controller(devs, task, opt, N, kw, temp_np_seed):
+    """make_controller(..., devices=[...]): same plugin surface, same numbers (the group path is used even for one device here)."""
+    _need(devs)
+    from judo_b200.controller import make_controller
+    from judo_b200.engine import MultiEngine
+
+    def run(multi):
+        np.random.seed(9)
+        c = make_controller(task, opt)
+        if multi:
+            c.engine.close()
+            c.rollout_backend.engine = c.engine = c.task.engine = MultiEngine(task, c.optimizer_cfg.num_rollouts, devs)
+            c.optimizer.bind(c.engine)
+            if c._trace_capture:
+                c.engine.set_trace_capture(True)
+        c.optimizer_cfg.num_rollouts = N
+        if "horizon" in kw:
+            c.controller_cfg.horizon = kw["horizon"]
+        np.random.seed(9)
+        c.reset()
+        if hasattr(c.task, "get_sim_metadata"):
+            c.system_metadata = c.task.get_sim_metadata()
+        out = []
+        for i in range(3):
+            c.time = c.task.dt * 2 * i
+            c.update_action()
+            out.append((c.candidate_knots.copy(), c.rewards.copy(), c.nominal_knots.copy(), c.traces.copy(), np.array(c.elite_indices)))
+        assert c._can_fast_path()
+        c.engine.close()
+        return out
+
+    with temp_np_seed(9):
+        a, b = run(False), run(True)
+    exact = task in ("cartpole", "cylinder_push")
+    for i, (x, y) in enumerate(zip(a, b)):
+        if i == 0:   # same seed, same warm start: identical candidates and rewards; afterwards the two updates' summation orders differ
+            np.testing.assert_array_equal(x[0], y[0])     # in the last bit (fused epilogue vs reduction kernels over all N)
+            np.testing.assert_array_equal(x[1], y[1])
+        else:
+            np.testing.assert_allclose(x[0], y[0], rtol=0, atol=1e-12 if exact else 1e-6)
+            np.testing.assert_allclose(x[1], y[1], rtol=1e-9 if exact else 1e-6, atol=1e-9 if exact else 1e-6)
+        np.testing.assert_allclose(x[2], y[2], rtol=0, atol=1e-12 if exact else 1e-6)
+        np.testing.assert_allclose(x[3], y[3], rtol=0, atol=1e-12 if exact else 1e-6)
+        np.testing.assert_array_equal(x[4], y[4])
+
+
+def test_make_controller_devices_argument():
+    import torch
+
+    from judo_b200.controller import make_controller
+    from judo_b200.engine import MultiEngine
+
+    n = min(torch.cuda.device_count(), 2)
+    c = make_controller("cartpole", "ps", devices=list(range(n)))
+    assert isinstance(c.engine, MultiEngine) == (n > 1)
+    c.update_action()
+    assert np.isfinite(c.nominal_knots).all() and c.rewards.shape == (32,)
+    c.engine.close()

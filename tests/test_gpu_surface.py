@@ -290,3 +290,26 @@ def test_many_elites_and_traces_are_not_capped(temp_np_seed):
             ctrl.update_action()
             assert ctrl.traces.shape == (12 * 2 * (ctrl.num_timesteps - 1), 2, 3) and np.isfinite(ctrl.nominal_knots).all()
             ctrl.engine.close()
+
+
+@pytest.mark.gpu
+def test_cem_with_more_elites_than_listed_does_not_clobber_rewards():
+    """num_elites > n_elite: the fused epilogue lists max(n_elite, num_elites) rollouts, the host buffers must hold that many."""
+    from judo_b200.engine import Engine
+    from oracle import plan as op
+
+    rng = np.random.default_rng(1)
+    eng = Engine("cartpole", 77)
+    knots = rng.normal(size=(77, 4, 1))
+    basis = np.eye(4)[np.repeat(np.arange(4), 5)]
+    x0, params = np.array([0.1, 3.0, 0.0, 0.0]), np.array([10.0, 10.0, 0.1, 0.1, 0.01, 0.1])
+    ref = eng.plan_step(x0, knots, basis, params, "cem", np.array([3, 0.1, 1.0]), n_elite=8)
+    for ne in (0, 1, 2):
+        res = eng.plan_step(x0, knots, basis, params, "cem", np.array([3, 0.1, 1.0]), n_elite=ne)
+        np.testing.assert_array_equal(res["rewards"], ref["rewards"])
+        np.testing.assert_array_equal(res["elite"], ref["elite"][:ne])
+        np.testing.assert_allclose(res["nominal"], op.cem_update(knots, ref["rewards"], 3, 0.1, 1.0)[0], atol=1e-12)
+    r2 = eng.plan_step_sampled(x0, np.zeros((4, 1)), np.full((4, 1), 0.3), np.array([-1.8]), np.array([1.8]), 77, basis, params, "cem",
+                               np.array([3, 0.1, 1.0]), seed=1, counter=0, n_elite=1, want_knots=True)
+    np.testing.assert_allclose(r2["nominal"], op.cem_update(r2["knots"], r2["rewards"], 3, 0.1, 1.0)[0], atol=1e-12)
+    eng.close()
