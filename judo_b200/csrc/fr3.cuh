@@ -487,15 +487,21 @@ __device__ inline void fr3_pair_geoms(const Fr3Model* __restrict__ m, const Fr3W
 
 // dist_mode: 0 = every distance sensor exactly (contract A); 1 = what the cost needs: the SIGN of the finger-table distances (taken
 // from the contact routine's separating-axis stage, no extra work); 2 = as 1 plus the object-table VALUE (PLACE phase)
+// Narrow-phase scratch of one box pair; the FNPAIR of them alias the contact Jacobians cJ, which are only built after the collision pass,
+// so the contact routines touch no local memory (the kernel used to carry a 1.1 KB stack frame per thread).
+struct Fr3ColScratch { double p2[3]; LRaw raw[8]; LBoxScratch box; };
+static_assert(sizeof(Fr3ColScratch) * FNPAIR <= sizeof(double) * FMAXCON * 3 * FR_NV, "collision scratch must fit into cJ");
+
 __device__ inline void fr3_collision(const Fr3Model* __restrict__ m, Fr3Work* W, int lane, int dist_mode) {
-  LRaw raw[8];
+  Fr3ColScratch* S = reinterpret_cast<Fr3ColScratch*>(&W->cJ[0][0][0]) + (lane < FNPAIR ? lane : 0);
+  const LRaw* raw = S->raw;
   int n = 0, cls = 0, body = 0;
   if (lane < FNPAIR) {
     const double *p1, *m1, *s1, *m2, *s2;
-    double p2[3];
+    double* p2 = S->p2;
     int overlap = 0;
     fr3_pair_geoms(m, W, lane, &p1, &m1, &s1, p2, &m2, &s2, &cls, &body);
-    n = l_box_box(p1, m1, s1, p2, m2, s2, 0.0, raw, 8, &overlap);
+    n = l_box_box(p1, m1, s1, p2, m2, s2, 0.0, S->raw, 8, &S->box, &overlap);
     double dist = m->cutoff;
     if (dist_mode == 0 || (dist_mode == 2 && lane == 0)) dist = l_box_box_distance(p1, m1, s1, p2, m2, s2, m->cutoff, true);
     else if (lane >= 1 && lane <= FNPAD) dist = overlap ? -1.0 : 1.0;

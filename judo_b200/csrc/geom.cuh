@@ -73,8 +73,15 @@ __device__ __forceinline__ void lmat_mul(double* r, const double* a, const doubl
 // ------------------------------------------------------------------ collision (reduced geometry; same routines as the oracle)
 struct LRaw { double dist, pos[3], normal[3]; };
 
-__device__ __noinline__ int l_clip_poly(double (*poly)[2], int n, int axis, double sign, double lim) {
-  double out[16][2];
+// Scratch of one box-box call: the clipped polygon and its double buffer.  Callers choose where it lives: the leap kernel hands out a slice
+// of its per-warp shared-memory work area (no local-memory stack frame, no DRAM traffic), fr3 a local array.
+constexpr int L_POLY_MAX = 9;  // a quadrilateral clipped by four half-planes has at most 8 vertices
+struct LBoxScratch { double poly[L_POLY_MAX][2], out[L_POLY_MAX][2]; };
+
+// v[idx] for a runtime idx in 0..2 without indexing a local array (which would force it into local memory)
+__device__ __forceinline__ double sel3(const double* v, int idx) { return idx == 0 ? v[0] : (idx == 1 ? v[1] : v[2]); }
+
+__device__ __noinline__ int l_clip_poly(double (*poly)[2], double (*out)[2], int n, int axis, double sign, double lim) {
   int no = 0;
   for (int i = 0; i < n; i++) {
     const double* a = poly[i];
@@ -85,7 +92,7 @@ __device__ __noinline__ int l_clip_poly(double (*poly)[2], int n, int axis, doub
       double t = da / (da - db);
       out[no][0] = a[0] + t * (b[0] - a[0]); out[no][1] = a[1] + t * (b[1] - a[1]); no++;
     }
-    if (no >= 15) break;
+    if (no >= L_POLY_MAX - 1) break;
   }
   for (int i = 0; i < no; i++) { poly[i][0] = out[i][0]; poly[i][1] = out[i][1]; }
   return no;
@@ -93,9 +100,11 @@ __device__ __noinline__ int l_clip_poly(double (*poly)[2], int n, int axis, doub
 
 __device__ __noinline__ int l_sphere_box(const double* ps, double rs, const double* pb, const double* mb, const double* sb, double margin, LRaw* out) {
   double rel[3], loc[3], cl[3];
+#pragma unroll
   for (int k = 0; k < 3; k++) rel[k] = ps[k] - pb[k];
   lmatT_vec(loc, mb, rel);
   int inside = 1;
+#pragma unroll
   for (int k = 0; k < 3; k++) {
     cl[k] = fmin(fmax(loc[k], -sb[k]), sb[k]);
     if (cl[k] != loc[k]) inside = 0;
@@ -105,18 +114,24 @@ __device__ __noinline__ int l_sphere_box(const double* ps, double rs, const doub
     double dv[3] = {loc[0] - cl[0], loc[1] - cl[1], loc[2] - cl[2]};
     double dn = lnorm3(dv);
     if (dn - rs >= margin) return 0;
+#pragma unroll
     for (int k = 0; k < 3; k++) nl[k] = -dv[k] / dn;
     dist = dn - rs;
   } else {
     int ax = 0; double best = 1e300;
+#pragma unroll
     for (int k = 0; k < 3; k++) { double g = sb[k] - fabs(loc[k]); if (g < best) { best = g; ax = k; } }
-    nl[0] = nl[1] = nl[2] = 0; nl[ax] = loc[ax] >= 0 ? -1 : 1;
-    cl[ax] = loc[ax] >= 0 ? sb[ax] : -sb[ax];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {  // (no runtime index into the local arrays: they stay in registers)
+      nl[k] = k == ax ? (loc[k] >= 0 ? -1.0 : 1.0) : 0.0;
+      if (k == ax) cl[k] = loc[k] >= 0 ? sb[k] : -sb[k];
+    }
     dist = -best - rs;
   }
   lmat_vec(out->normal, mb, nl);
   double clw[3];
   lmat_vec(clw, mb, cl);
+#pragma unroll
   for (int k = 0; k < 3; k++) out->pos[k] = pb[k] + clw[k] - out->normal[k] * (-0.5 * dist);
   out->dist = dist;
   return 1;
@@ -124,22 +139,27 @@ __device__ __noinline__ int l_sphere_box(const double* ps, double rs, const doub
 
 // overlap (optional): set to 1 when no separating axis was found (the boxes interpenetrate), 0 otherwise
 __device__ __noinline__ int l_box_box(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2, const double* s2,
-                                double margin, LRaw* out, int maxout, int* overlap = nullptr) {
+                                double margin, LRaw* out, int maxout, LBoxScratch* scr, int* overlap = nullptr) {
   if (overlap) *overlap = 0;
   double R[3][3], AR[3][3], t[3], d12[3];
+#pragma unroll
   for (int k = 0; k < 3; k++) d12[k] = p2[k] - p1[k];
   lmatT_vec(t, m1, d12);
+#pragma unroll
   for (int i = 0; i < 3; i++)
+#pragma unroll
     for (int j = 0; j < 3; j++) {
       R[i][j] = m1[i] * m2[j] + m1[3 + i] * m2[3 + j] + m1[6 + i] * m2[6 + j];
       AR[i][j] = fabs(R[i][j]) + 1e-12;
     }
   double best = -1e300; int code = -1; double bsign = 1;
+#pragma unroll
   for (int i = 0; i < 3; i++) {
     double sep = fabs(t[i]) - (s1[i] + s2[0] * AR[i][0] + s2[1] * AR[i][1] + s2[2] * AR[i][2]);
     if (sep >= margin) return 0;
     if (sep > best) { best = sep; code = i; bsign = t[i] >= 0 ? 1 : -1; }
   }
+#pragma unroll
   for (int j = 0; j < 3; j++) {
     double tj = t[0] * R[0][j] + t[1] * R[1][j] + t[2] * R[2][j];
     double sep = fabs(tj) - (s2[j] + s1[0] * AR[0][j] + s1[1] * AR[1][j] + s1[2] * AR[2][j]);
@@ -174,16 +194,23 @@ __device__ __noinline__ int l_box_box(const double* p1, const double* m1, const 
       n[0] *= sc; n[1] *= sc; n[2] *= sc;
     }
     double c1[3] = {p1[0], p1[1], p1[2]}, c2[3] = {p2[0], p2[1], p2[2]};
+#pragma unroll
     for (int k = 0; k < 3; k++) {
-      if (k != i) { double a[3] = {m1[k], m1[3 + k], m1[6 + k]}; double sg = ldot3(a, n) > 0 ? 1 : -1; for (int q = 0; q < 3; q++) c1[q] += sg * s1[k] * a[q]; }
-      if (k != j) { double a[3] = {m2[k], m2[3 + k], m2[6 + k]}; double sg = ldot3(a, n) > 0 ? -1 : 1; for (int q = 0; q < 3; q++) c2[q] += sg * s2[k] * a[q]; }
+      if (k != i) { double a[3] = {m1[k], m1[3 + k], m1[6 + k]}; double sg = ldot3(a, n) > 0 ? 1 : -1;
+#pragma unroll
+        for (int q = 0; q < 3; q++) c1[q] += sg * s1[k] * a[q]; }
+      if (k != j) { double a[3] = {m2[k], m2[3 + k], m2[6 + k]}; double sg = ldot3(a, n) > 0 ? -1 : 1;
+#pragma unroll
+        for (int q = 0; q < 3; q++) c2[q] += sg * s2[k] * a[q]; }
     }
     double u1[3] = {m1[i], m1[3 + i], m1[6 + i]}, u2[3] = {m2[j], m2[3 + j], m2[6 + j]}, w0[3];
+#pragma unroll
     for (int k = 0; k < 3; k++) w0[k] = c1[k] - c2[k];
     double b = ldot3(u1, u2), dd = ldot3(u1, w0), e = ldot3(u2, w0), den = 1 - b * b;
     double sc = den > 1e-12 ? (b * e - dd) / den : 0, tc = den > 1e-12 ? (e - b * dd) / den : 0;
     sc = fmin(fmax(sc, -s1[i]), s1[i]); tc = fmin(fmax(tc, -s2[j]), s2[j]);
     out[0].dist = ebest;
+#pragma unroll
     for (int k = 0; k < 3; k++) { out[0].normal[k] = n[k]; out[0].pos[k] = 0.5 * ((c1[k] + sc * u1[k]) + (c2[k] + tc * u2[k])); }
     return 1;
   }
@@ -194,52 +221,63 @@ __device__ __noinline__ int l_box_box(const double* p1, const double* m1, const 
   else { pr = p2; mr = m2; sr = s2; pi = p1; mi = m1; si = s1; raxis = code - 3; nsign = -bsign; }
   double nref[3] = {mr[raxis] * nsign, mr[3 + raxis] * nsign, mr[6 + raxis] * nsign};
   int iaxis = 0; double imin = 1e300, isign = 1;
+#pragma unroll
   for (int k = 0; k < 3; k++) {
     double a[3] = {mi[k], mi[3 + k], mi[6 + k]}, dd = ldot3(a, nref);
     if (-fabs(dd) < imin) { imin = -fabs(dd); iaxis = k; isign = dd > 0 ? -1 : 1; }
   }
   const int iu = (iaxis + 1) % 3, iv = (iaxis + 2) % 3, ru = (raxis + 1) % 3, rv = (raxis + 2) % 3;
   double fc[3];
+#pragma unroll
   for (int k = 0; k < 3; k++) fc[k] = pi[k] + isign * si[iaxis] * mi[3 * k + iaxis];
-  double poly[16][2];
+  double (*poly)[2] = scr->poly;
   int n = 4;
-  const double sg[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
-  double verts[4][3];
+  // the incident face's corners (+u+v, -u+v, -u-v, +u-v) in the reference box's frame; corners 0, 1 and 3 span the face plane
+  double l0[3] = {0, 0, 0}, l1[3] = {0, 0, 0}, l2[3] = {0, 0, 0};
+#pragma unroll
   for (int c = 0; c < 4; c++) {
-    for (int k = 0; k < 3; k++) verts[c][k] = fc[k] + sg[c][0] * si[iu] * mi[3 * k + iu] + sg[c][1] * si[iv] * mi[3 * k + iv] - pr[k];
-    double loc[3];
-    lmatT_vec(loc, mr, verts[c]);
-    poly[c][0] = loc[ru]; poly[c][1] = loc[rv];
+    const double su = (c == 0 || c == 3) ? 1.0 : -1.0, sv = c < 2 ? 1.0 : -1.0;
+    double vert[3], loc[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) vert[k] = fc[k] + su * si[iu] * mi[3 * k + iu] + sv * si[iv] * mi[3 * k + iv] - pr[k];
+    lmatT_vec(loc, mr, vert);
+    poly[c][0] = sel3(loc, ru); poly[c][1] = sel3(loc, rv);
+    if (c == 0) { l0[0] = loc[0]; l0[1] = loc[1]; l0[2] = loc[2]; }
+    if (c == 1) { l1[0] = loc[0]; l1[1] = loc[1]; l1[2] = loc[2]; }
+    if (c == 3) { l2[0] = loc[0]; l2[1] = loc[1]; l2[2] = loc[2]; }
   }
-  double l0[3], l1[3], l2[3];
-  lmatT_vec(l0, mr, verts[0]); lmatT_vec(l1, mr, verts[1]); lmatT_vec(l2, mr, verts[3]);
-  const double e1u = l1[ru] - l0[ru], e1v = l1[rv] - l0[rv], e1h = l1[raxis] - l0[raxis];
-  const double e2u = l2[ru] - l0[ru], e2v = l2[rv] - l0[rv], e2h = l2[raxis] - l0[raxis];
+  const double l0u = sel3(l0, ru), l0v = sel3(l0, rv), l0h = sel3(l0, raxis);
+  const double e1u = sel3(l1, ru) - l0u, e1v = sel3(l1, rv) - l0v, e1h = sel3(l1, raxis) - l0h;
+  const double e2u = sel3(l2, ru) - l0u, e2v = sel3(l2, rv) - l0v, e2h = sel3(l2, raxis) - l0h;
   const double det = e1u * e2v - e1v * e2u;
   const double idet = fabs(det) > 1e-14 ? 1.0 / det : 0.0;
+  const double sru = sr[ru], srv = sr[rv];
   // clipping is the identity when the whole incident face projects inside the reference face (the common case on large faces)
   bool inside = true;
 #pragma unroll
-  for (int c = 0; c < 4; c++) inside = inside && fabs(poly[c][0]) <= sr[ru] && fabs(poly[c][1]) <= sr[rv];
+  for (int c = 0; c < 4; c++) inside = inside && fabs(poly[c][0]) <= sru && fabs(poly[c][1]) <= srv;
   if (!inside) {
-  n = l_clip_poly(poly, n, 0, 1, sr[ru]);
-  if (n) n = l_clip_poly(poly, n, 0, -1, sr[ru]);
-  if (n) n = l_clip_poly(poly, n, 1, 1, sr[rv]);
-  if (n) n = l_clip_poly(poly, n, 1, -1, sr[rv]);
+    n = l_clip_poly(poly, scr->out, n, 0, 1, sru);
+    if (n) n = l_clip_poly(poly, scr->out, n, 0, -1, sru);
+    if (n) n = l_clip_poly(poly, scr->out, n, 1, 1, srv);
+    if (n) n = l_clip_poly(poly, scr->out, n, 1, -1, srv);
   }
   int nc = 0;
   for (int c = 0; c < n && nc < maxout; c++) {
-    double du = poly[c][0] - l0[ru], dv = poly[c][1] - l0[rv], h;
+    double du = poly[c][0] - l0u, dv = poly[c][1] - l0v, h;
     if (fabs(det) > 1e-14) {
       double a = (du * e2v - dv * e2u) * idet, b = (e1u * dv - e1v * du) * idet;
-      h = l0[raxis] + a * e1h + b * e2h;
-    } else h = l0[raxis];
+      h = l0h + a * e1h + b * e2h;
+    } else h = l0h;
     double dist = nsign * h - sr[raxis];
     if (dist >= margin) continue;
     double loc[3], wpt[3];
-    loc[ru] = poly[c][0]; loc[rv] = poly[c][1]; loc[raxis] = h - 0.5 * dist * nsign;
+    const double hh = h - 0.5 * dist * nsign;
+#pragma unroll
+    for (int k = 0; k < 3; k++) loc[k] = k == ru ? poly[c][0] : (k == rv ? poly[c][1] : hh);
     lmat_vec(wpt, mr, loc);
     out[nc].dist = dist;
+#pragma unroll
     for (int k = 0; k < 3; k++) { out[nc].pos[k] = pr[k] + wpt[k]; out[nc].normal[k] = ref_is_1 ? nref[k] : -nref[k]; }
     nc++;
   }

@@ -12,6 +12,7 @@
 #include "geom.cuh"
 #include "sampling.cuh"
 
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -66,6 +67,14 @@ struct LeapWork {
   int ncon, nefc, nfl, ncand, solver_iter;
   double cost, gauss;
 };
+
+// Narrow-phase scratch of ONE candidate pair (geom pose, raw contacts, clipping polygons).  LCOL_LANES of them alias the solver arrays
+// cHc / cDm / Jc of the work area, which are dead until the constraint rows are built: the collision routines then touch no local memory
+// (the kernel had a 1 152-byte stack frame per thread = 38 MB of local memory per launch, 17 MB of it reaching DRAM).
+struct LeapColScratch { double gp[3], gm[9]; LRaw raw[8]; LBoxScratch box; };
+constexpr int LCOL_LANES = 8;
+static_assert(sizeof(LeapColScratch) * LCOL_LANES <= sizeof(double) * (LMAXCON * 9 + LMAXCON + 3 * LMAXCON * 10), "collision scratch must fit into cHc + cDm + Jc");
+static_assert(offsetof(LeapWork, Jc) == offsetof(LeapWork, cHc) + sizeof(double) * (LMAXCON * 9 + LMAXCON), "cHc, cDm, Jc must be contiguous");
 
 // optional phase timers (clock64 deltas accumulated by lane 0): kin, mass+bias, collision, constraints, smooth, solver, integrate,
 // and inside the solver: update, direction (H + Cholesky + solve), line search, #newton iterations
@@ -360,14 +369,17 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
   LPROF_ADD(11, tc0); tc0 = LPROF_T();
   if (prof && lane == 0) atomicAdd(&g_leap_prof[13], (unsigned long long)ncand);
   int ncon = 0;
-  for (int c0 = 0; c0 < ncand; c0 += 32) {
+  LeapColScratch* scr_all = reinterpret_cast<LeapColScratch*>(&W->cHc[0][0]);
+  for (int c0 = 0; c0 < ncand; c0 += LCOL_LANES) {  // LCOL_LANES pairs per round (2.7 candidates per step on average), one per lane
     const int ci = c0 + lane;
-    LRaw raw[8];
+    LeapColScratch* S = scr_all + (lane < LCOL_LANES ? lane : 0);
+    const LRaw* raw = S->raw;
     int n = 0, g = -1, b = -1, swap = 0;
-    if (ci < ncand) {
+    if (lane < LCOL_LANES && ci < ncand) {
       g = W->cand[ci];
       b = (int)m->geom_body[g];
-      double gp[3], gm[9];
+      double* gp = S->gp;
+      double* gm = S->gm;
       if (b < 0) {
         for (int k = 0; k < 3; k++) gp[k] = m->geom_pos[g][k];
         for (int k = 0; k < 9; k++) gm[k] = m->geom_mat[g][k];
@@ -377,8 +389,8 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
         for (int k = 0; k < 3; k++) gp[k] = W->xpos[b][k] + t[k];
         lmat_mul(gm, W->xmat[b], m->geom_mat[g]);
       }
-      if ((int)m->geom_type[g] == 6) n = l_box_box(cp, W->xmat[0], m->cube_size, gp, gm, m->geom_size[g], 0.0, raw, 8);  // geom1 = cube
-      else { n = l_sphere_box(gp, m->geom_size[g][0], cp, W->xmat[0], m->cube_size, 0.0, raw); swap = 1; }          // geom1 = sphere
+      if ((int)m->geom_type[g] == 6) n = l_box_box(cp, W->xmat[0], m->cube_size, gp, gm, m->geom_size[g], 0.0, S->raw, 8, &S->box);  // geom1 = cube
+      else { n = l_sphere_box(gp, m->geom_size[g][0], cp, W->xmat[0], m->cube_size, 0.0, S->raw); swap = 1; }          // geom1 = sphere
     }
     // ordered slot allocation: exclusive prefix of n over the lanes
     int pre = n;
@@ -604,9 +616,8 @@ __device__ __noinline__ void leap_constraint_update(const LeapModel* __restrict_
   for (int r = lane; r < nfl; r += 32) cost += leap_row_eval(W, r, nfr, W->ejar[r], &W->eforce[r], &W->estate[r]);
   for (int c = lane; c < ncon; c += 32) {
     const int r0 = nfl + 3 * c;
-    int st;
-    cost += leap_cone_eval(W, c, r0, W->ejar + r0, W->eforce + r0, &st, want_h ? W->cHc[c] : nullptr);
-    W->estate[r0] = W->estate[r0 + 1] = W->estate[r0 + 2] = st;
+    cost += leap_cone_eval(W, c, r0, W->ejar + r0, W->eforce + r0, &W->estate[r0], want_h ? W->cHc[c] : nullptr);
+    W->estate[r0 + 1] = W->estate[r0 + 2] = W->estate[r0];
   }
   cost = lwsum(cost);
   __syncwarp();
@@ -1100,6 +1111,7 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
     // rollout and is read from global memory (K cached loads per lane and step) to keep the per-warp shared-memory footprint small
     uint64_t* bar = reinterpret_cast<uint64_t*>(lsm + ((sizeof(LeapWork) + 15) & ~(size_t)15));
     double* sK = reinterpret_cast<double*>(bar + 2);
+    float* sC = reinterpret_cast<float*>(sK + K * LEAP_NU);  // this rollout's cost row (H floats), written back coalesced at the end
     if (active) {
       const unsigned bytesK = (unsigned)(K * LEAP_NU * sizeof(double));
       const double* gK = in + (size_t)n * K * LEAP_NU;
@@ -1144,10 +1156,14 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
         for (int i = 0; i < LEAP_NCOST; i++) cp[i] = cost_params[i];
         const double ct = leap_cost(cp, W->qpos);
         total += ct;
-        if (cost_NH) cost_NH[(size_t)n * H + t] = (float)ct;
+        if (cost_NH) sC[t] = (float)ct;
       }
     }
     if (active && lane == 0) reward_N[n] = -(total / H);
+    if (active && cost_NH) {
+      __syncwarp();
+      for (int i = lane; i < H; i += 32) cost_NH[(size_t)n * H + i] = sC[i];  // one coalesced row per rollout instead of H scalar stores
+    }
   } else {
 #pragma unroll 1
     for (int t = 0; t < H; t++) {
@@ -1175,6 +1191,11 @@ __global__ void leap_reward_kernel(const double* __restrict__ states, int N, int
 }
 
 // ------------------------------------------------------------------ host side
+// shared memory per warp: work area + mbarrier + (fused mode) this rollout's knots and its cost row
+inline size_t leap_wstride(int cost_mode, int K, int H) {
+  size_t w = ((sizeof(LeapWork) + 15) & ~(size_t)15) + 16 + (cost_mode ? (size_t)K * LEAP_NU * sizeof(double) + (size_t)H * sizeof(float) : 0);
+  return (w + 15) & ~(size_t)15;
+}
 #ifndef B2_HOST_SIM
 inline int leap_create(LeapModel** out, const double* consts, size_t n, std::string* err) {
   if (n != sizeof(LeapModel) / sizeof(double)) { *err = "wrong number of task constants"; return 1; }
@@ -1203,8 +1224,7 @@ inline int leap_launch(const LeapModel* m, int cost_mode, const double* d_x0, in
   const char* sp_env = getenv("B200MPC_LEAP_SYNC_PERIOD");
   const int prof = (getenv("B200MPC_LEAP_PROF") ? 1 : 0) | ((sm_env ? atoi(sm_env) : 3) << 8) | ((sp_env ? atoi(sp_env) : 1) << 16);
   (void)ep;  // the leap path runs the optimizer update as separate reduction kernels (b200mpc.cu)
-  size_t wstride = ((sizeof(LeapWork) + 15) & ~(size_t)15) + 16 + (cost_mode ? (size_t)K * LEAP_NU * sizeof(double) : 0);
-  wstride = (wstride + 15) & ~(size_t)15;
+  const size_t wstride = leap_wstride(cost_mode, K, H);
   int wpb = (N + 147) / 148;  // spread the rollouts over the 148 SMs first, then stack up to 7 warps per SM
   if (wpb < 1) wpb = 1;
   if (wpb > 7) wpb = 7;

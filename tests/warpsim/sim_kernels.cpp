@@ -4,11 +4,6 @@
 
 using namespace b2;
 
-static size_t leap_wstride(int cost_mode, int K, int H) {
-  (void)H;
-  size_t w = ((sizeof(LeapWork) + 15) & ~(size_t)15) + 16 + (cost_mode ? (size_t)K * LEAP_NU * sizeof(double) : 0);
-  return (w + 15) & ~(size_t)15;
-}
 
 extern "C" int sim_leap_nconsts() { return (int)(sizeof(LeapModel) / sizeof(double)); }
 
