@@ -251,6 +251,9 @@ int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all_handles_wo
  * the last finalize=2 step on this rank: [0] kernel entry, [1] partial published to the peers, [2] all peers' partials seen. */
 int b200mpc_exchange_align_dev(b200mpc_handle* h, void* stream);
 int b200mpc_exchange_stamps(b200mpc_handle* h, unsigned long long* out3);
+/* Two more %globaltimer stamps (ns): [0] exit of this rank's last line-up kernel (with stamps[0] above it brackets the launch gap between the
+ * line-up and the timed rollout kernel), [1] the last instruction of the last finalize=2 step's exchange (final nominal written). */
+int b200mpc_exchange_align_stamp(b200mpc_handle* h, unsigned long long* out2);
 
 /* Measurement helper for bench.py's issue-bound roofline: DFMA warp instructions per second this GPU sustains with every SM full of
  * independent chains (the path is bound by fp64 issue / dependent latency, not by HBM). */

@@ -52,6 +52,7 @@ SIGNATURES = {
     "b200mpc_exchange_open": (_i, [_vp, _vp]),
     "b200mpc_exchange_align_dev": (_i, [_vp, _vp]),
     "b200mpc_exchange_stamps": (_i, [_vp, _vp]),
+    "b200mpc_exchange_align_stamp": (_i, [_vp, _vp]),
     "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),
     "b200mpc_fp64_peak": (_i, [_i, ctypes.POINTER(_d)]),
     "b200mpc_contact_overflows": (ctypes.c_longlong, [_vp]),

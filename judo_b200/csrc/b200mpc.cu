@@ -174,7 +174,7 @@ extern "C" int b200mpc_exchange_create(b200mpc_handle* h, int world, int rank, u
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaMemset(h->xchg, 0, EP_XCHG_BYTES));
   h->xchg_world = world; h->xchg_rank = rank; h->xchg_epoch = 0; h->xchg_align_epoch = 0;
-  if (!h->d_stamps) { CK(cudaMalloc(&h->d_stamps, 32)); CK(cudaMemset(h->d_stamps, 0, 32)); }
+  if (!h->d_stamps) { CK(cudaMalloc(&h->d_stamps, 64)); CK(cudaMemset(h->d_stamps, 0, 64)); }
   cudaIpcMemHandle_t ih;
   CK(cudaIpcGetMemHandle(&ih, h->xchg));
   static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -205,6 +205,7 @@ extern "C" int b200mpc_exchange_align_dev(b200mpc_handle* h, void* stream) {
   PlanEpilogue ep{};
   ep.world = h->xchg_world; ep.rank = h->xchg_rank; ep.epoch = ++h->xchg_align_epoch;
   for (int g = 0; g < h->xchg_world; g++) ep.peer[g] = (double*)h->xchg_peer[g];
+  ep.stamps = h->d_stamps;
   exchange_align_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ep);
   CK(cudaGetLastError());
   return 0;
@@ -214,6 +215,14 @@ extern "C" int b200mpc_exchange_stamps(b200mpc_handle* h, unsigned long long* ou
   if (!h->d_stamps) return fail(h, "peer exchange not set up (exchange_create/open)");
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpy(out3, h->d_stamps, 24, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int b200mpc_exchange_align_stamp(b200mpc_handle* h, unsigned long long* out2) {
+  if (!h || !out2) return 1;
+  if (!h->d_stamps) return fail(h, "peer exchange not set up (exchange_create/open)");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(out2, h->d_stamps + 3, 16, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -45,11 +45,39 @@ struct PlanEpilogue {
   int world, rank;
   unsigned long long epoch;
   double* peer[8];        // peer[g]: exchange buffer of rank g mapped into this process (peer[rank] is local)
-  unsigned long long* stamps;  // optional (finalize == 2): %globaltimer at [0] kernel entry (block 0), [1] partial published, [2] all peers seen
+  unsigned long long* stamps;  // optional (finalize == 2): %globaltimer at [0] kernel entry (block 0), [1] partial published, [2] all peers seen, [3] line-up kernel exit, [4] exchange branch done
 };
 constexpr int EP_XCHG_FLAGS = 16;                  // u64 flags in front of the partial slots: [0..8) step epochs, [8..16) align epochs
 constexpr int EP_XCHG_STRIDE = 2 + 96;             // doubles per rank slot (beta, S, V[<=96])
-constexpr size_t EP_XCHG_BYTES = 8 * EP_XCHG_FLAGS + 2 * 8 * (size_t)EP_XCHG_STRIDE * 8;  // slots double-buffered by epoch parity
+constexpr size_t EP_XCHG_LL = 8 * EP_XCHG_FLAGS + 2 * 8 * (size_t)EP_XCHG_STRIDE * 8;     // byte offset of the flag-in-data slots (MPPI)
+constexpr size_t EP_XCHG_BYTES = EP_XCHG_LL + 2 * 8 * (size_t)EP_XCHG_STRIDE * 16;          // slots double-buffered by epoch parity
+
+// Flag-in-data exchange (the "LL" protocol of NCCL): every double travels as ONE 16-byte store {lo, epoch, hi, epoch}.  NVLink delivers
+// 8-byte units atomically, so a reader that sees both epoch words has the value: no fence between data and flag on the writer, no
+// separate flag to poll and no second round trip for the data on the reader.
+struct __align__(16) LLWord { unsigned lo, f0, hi, f1; };
+#ifdef B2_HOST_SIM
+__device__ __forceinline__ void ll_store(LLWord* p, double v, unsigned epoch) {
+  unsigned long long b; memcpy(&b, &v, 8);
+  p->lo = (unsigned)b; p->f0 = epoch; p->hi = (unsigned)(b >> 32); p->f1 = epoch;
+}
+__device__ __forceinline__ LLWord ll_load(const LLWord* p) { return *p; }
+#else
+__device__ __forceinline__ void ll_store(LLWord* p, double v, unsigned epoch) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(epoch), "r"((unsigned)(b >> 32)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ LLWord ll_load(const LLWord* p) {
+  LLWord w;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.lo), "=r"(w.f0), "=r"(w.hi), "=r"(w.f1) : "l"(p) : "memory");
+  return w;
+}
+#endif
+__device__ __forceinline__ bool ll_ready(const LLWord& w, unsigned epoch) { return w.f0 == epoch && w.f1 == epoch; }
+__device__ __forceinline__ double ll_value(const LLWord& w) { return __longlong_as_double((long long)(((unsigned long long)w.hi << 32) | w.lo)); }
+__device__ __forceinline__ LLWord* ll_slot(double* buf, unsigned long long epoch, int src_rank) {
+  return reinterpret_cast<LLWord*>(reinterpret_cast<char*>(buf) + EP_XCHG_LL) + (size_t)((epoch & 1) * 8 + src_rank) * EP_XCHG_STRIDE;
+}
 
 #ifdef B2_HOST_SIM
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { *p = v; }
@@ -131,6 +159,8 @@ __global__ void exchange_align_kernel(PlanEpilogue ep) {
     int spins = 0;
     while (ld_acquire_sys(fl) < ep.epoch) { __nanosleep(32); if (++spins > (1 << 22)) break; }
   }
+  __syncwarp();
+  if (ep.stamps && lane == 0) ep.stamps[3] = global_ns();  // [3]: the line-up kernel's exit (bench: start of the launch gap)
 }
 
 // Final stage, run by one full warp after all partials are visible.  knots: this launch's (N, KNU) candidates.
@@ -161,29 +191,64 @@ __device__ inline void epilogue_final(const PlanEpilogue& ep, int nparts, int KN
     }
     const double S = wsum(s);
     if (ep.finalize == 2) {
-      // ---- fused exchange: publish [beta, S, V] into every peer's slot for this rank, then raise the epoch flag there
+      // ---- fused exchange: publish [beta, S, V] into every peer's slot for this rank as flag-in-data words (one-way NVLink stores,
+      // no fence, no separate flag), then gather the world_size partials from OUR buffer: lane g polls rank g's (beta, S), lane j
+      // polls column j of every rank's V — all loads of a poll round are in flight together, so the exchange costs one NVLink
+      // store latency plus one local poll round instead of fence + flag + dependent reads.
       double vj[MAXKNU];
 #pragma unroll
       for (int j = 0; j < MAXKNU; j++) vj[j] = j < KNU ? wsum(v[j]) : 0.0;
+      const unsigned ep32 = (unsigned)ep.epoch;
       for (int g = 0; g < ep.world; g++) {
-        double* slot = ep.peer[g] + EP_XCHG_FLAGS + (size_t)((ep.epoch & 1) * 8 + ep.rank) * EP_XCHG_STRIDE;
-        if (lane == 0) { slot[0] = beta; slot[1] = S; }
+        LLWord* slot = ll_slot(ep.peer[g], ep.epoch, ep.rank);
+        if (lane == 0) ll_store(slot, beta, ep32);
+        if (lane == 1) ll_store(slot + 1, S, ep32);
 #pragma unroll
-        for (int j = 0; j < MAXKNU; j++) if (j < KNU && lane == (j & 31)) slot[2 + j] = vj[j];
+        for (int j = 0; j < MAXKNU; j++) if (j < KNU && lane == ((j + 2) & 31)) ll_store(slot + 2 + j, vj[j], ep32);
       }
-      const bool ok = peer_signal_and_wait(ep, lane);
-      // ---- combine the world_size partials (lane g holds rank g's beta / S)
-      const double* own = ep.peer[ep.rank] + EP_XCHG_FLAGS + (size_t)(ep.epoch & 1) * 8 * EP_XCHG_STRIDE;
-      const volatile double* vown = own;
-      const double bg = lane < ep.world ? vown[(size_t)lane * EP_XCHG_STRIDE] : INFINITY;
-      const double sg = lane < ep.world ? vown[(size_t)lane * EP_XCHG_STRIDE + 1] : 0.0;
+      if (ep.stamps && lane == 0) ep.stamps[1] = global_ns();
+      constexpr int NT = (MAXKNU + 31) / 32;
+      LLWord wb, ws, wv[NT][8];
+      bool ok = false;
+      for (int spins = 0; spins < (1 << 22); spins++) {
+        bool ready = true;
+        if (lane < ep.world) {
+          const LLWord* src = ll_slot(ep.peer[ep.rank], ep.epoch, lane);
+          wb = ll_load(src); ws = ll_load(src + 1);
+        }
+#pragma unroll
+        for (int t = 0; t < NT; t++)
+#pragma unroll
+          for (int g = 0; g < 8; g++)
+            if (g < ep.world && lane + 32 * t < KNU) wv[t][g] = ll_load(ll_slot(ep.peer[ep.rank], ep.epoch, g) + 2 + lane + 32 * t);
+        if (lane < ep.world) ready = ll_ready(wb, ep32) && ll_ready(ws, ep32);
+#pragma unroll
+        for (int t = 0; t < NT; t++)
+#pragma unroll
+          for (int g = 0; g < 8; g++)
+            if (g < ep.world && lane + 32 * t < KNU) ready = ready && ll_ready(wv[t][g], ep32);
+        if (__all_sync(0xffffffffu, ready)) { ok = true; break; }
+        __nanosleep(32);
+      }
+      if (ep.stamps && lane == 0) ep.stamps[2] = global_ns();
+      // ---- combine (lane g holds rank g's beta / S; every rank sums the ranks in the same order: identical nominal everywhere)
+      const double bg = lane < ep.world ? ll_value(wb) : INFINITY;
+      const double sg = lane < ep.world ? ll_value(ws) : 0.0;
       const double bmin = wmin(bg);
       const double scg = sg > 0 ? exp(-(bg - bmin) / ep.temperature) : 0.0;
       const double Stot = wsum(sg * scg);
-      for (int j = 0; j < KNU; j++) {
-        const double t = wsum(lane < ep.world ? vown[(size_t)lane * EP_XCHG_STRIDE + 2 + j] * scg : 0.0);
-        if (lane == 0) ep.nominal[j] = ok ? t / Stot : __longlong_as_double(0x7ff8000000000000ll);
+      double sc[8];
+#pragma unroll
+      for (int g = 0; g < 8; g++) sc[g] = __shfl_sync(0xffffffffu, scg, g);
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        double acc = 0;
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+          if (g < ep.world && lane + 32 * t < KNU) acc += ll_value(wv[t][g]) * sc[g];
+        if (lane + 32 * t < KNU) ep.nominal[lane + 32 * t] = ok ? acc / Stot : __longlong_as_double(0x7ff8000000000000ll);
       }
+      if (ep.stamps && lane == 0) ep.stamps[4] = global_ns();
     } else {
       double* out = ep.finalize ? ep.nominal : ep.rank_mppi + 2;
 #pragma unroll

@@ -98,6 +98,52 @@ __device__ __noinline__ int l_clip_poly(double (*poly)[2], double (*out)[2], int
   return no;
 }
 
+// Sphere vs sphere (the oracle's collide_sphere_sphere): normal from geom1 to geom2, position midway between the surfaces.
+__device__ inline int l_sphere_sphere(const double* p1, double r1, const double* p2, double r2, double margin, LRaw* out) {
+  double dv[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  const double dn = lnorm3(dv);
+  if (dn - r1 - r2 >= margin) return 0;
+  if (dn < B2_MINVAL) { out->normal[0] = 1; out->normal[1] = 0; out->normal[2] = 0; }
+  else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) out->normal[k] = dv[k] / dn;
+  }
+  out->dist = dn - r1 - r2;
+#pragma unroll
+  for (int k = 0; k < 3; k++) out->pos[k] = p1[k] + out->normal[k] * (r1 + 0.5 * out->dist);
+  return 1;
+}
+
+// Conservative pre-filters in front of the divergent contact-generation pass: they never reject a touching pair.
+// box-box: the 6 face axes of the separating-axis test (slack 1e-9); sphere-box: the exact sphere-box distance.
+__device__ inline bool l_box_box_may_touch(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2, const double* s2) {
+  const double dc[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  double t[3], R[3][3];
+  lmatT_vec(t, m1, dc);  // centre of box 2 in the frame of box 1
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) R[i][j] = fabs(m1[i] * m2[j] + m1[3 + i] * m2[3 + j] + m1[6 + i] * m2[6 + j]) + 1e-12;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    if (fabs(t[i]) - (s1[i] + s2[0] * R[i][0] + s2[1] * R[i][1] + s2[2] * R[i][2]) >= 1e-9) return false;
+  double t2[3];
+  lmatT_vec(t2, m2, dc);
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    if (fabs(t2[j]) - (s2[j] + s1[0] * R[0][j] + s1[1] * R[1][j] + s1[2] * R[2][j]) >= 1e-9) return false;
+  return true;
+}
+__device__ inline bool l_sphere_box_may_touch(const double* ps, double rs, const double* pb, const double* mb, const double* sb) {
+  const double dc[3] = {ps[0] - pb[0], ps[1] - pb[1], ps[2] - pb[2]};
+  double t[3], d2 = 0;
+  lmatT_vec(t, mb, dc);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const double ex = fabs(t[k]) - sb[k]; if (ex > 0) d2 += ex * ex; }
+  const double rr = rs + 1e-9;
+  return d2 < rr * rr;
+}
+
 __device__ __noinline__ int l_sphere_box(const double* ps, double rs, const double* pb, const double* mb, const double* sb, double margin, LRaw* out) {
   double rel[3], loc[3], cl[3];
 #pragma unroll

@@ -6,7 +6,8 @@
 // 32 lanes: kinematics (lane per chain), mass matrix + RNE (lane per finger), collision of the cube against the hand
 // geoms (lane per geom / per candidate pair), constraint rows (lane per row), the primal Newton solver with elliptic
 // cones (lane per row / per contact / per Hessian entry, warp Cholesky), implicitfast integration.
-// The collision GEOMETRY is reduced; the constraint/solver pipeline is the full one.
+// Collision covers every geom pair MuJoCo's static filters leave (cube-hand AND hand-hand); only the fingertip meshes are replaced
+// by spheres; the constraint/solver pipeline is the full one.
 #pragma once
 #include "epilogue.cuh"
 #include "geom.cuh"
@@ -25,8 +26,10 @@ constexpr int LEAP_NQ = 23, LEAP_NV = 22, LEAP_NU = 16, LEAP_NS = 31, LEAP_NX = 
 constexpr int LEAP_NTRACE = 15;  // doubles per step kept by the fused kernel's trace capture: the 5 framepos trace sensors
 constexpr int LB = 17;         // moving bodies: 0 = cube, 1 + 4f + d = link d of finger f
 constexpr int LMAXG = 80;      // hand collision geoms
-constexpr int LMAXCON = 30;    // contacts kept per step (3 rows each; one contact per lane in the line search: <= 32)
-constexpr int LMAXEFC = 32 + 3 * LMAXCON;
+constexpr int LMAXHH = 1664;   // hand-hand candidate pairs (finger-finger, finger-palm, links of one finger: 1 621 for leap_cube)
+constexpr int LMAXCON = 40;    // contacts kept per step (3 rows each); the C4 bench scenario peaks at 36 with the hand-hand pairs
+constexpr int LMAXFL = 32;     // friction-loss rows (16) + active joint-limit rows (at most one side per joint)
+constexpr int LMAXEFC = LMAXFL + 3 * LMAXCON;
 constexpr unsigned FULL = 0xffffffffu;
 
 // All-double POD; field order == judo_b200/tasks/leap_cube.py:leap_consts.
@@ -44,41 +47,62 @@ struct LeapModel {
   double cube_size[3], cube_rbound, con_solref[2], con_solimp[5];
   double site_body[5], site_pos[5][3];
   double fr_row[LEAP_NV];  // friction-loss row of each dof (-1: none)
+  double geom_fr[LMAXG];   // sliding friction of each hand geom (hand-hand contacts mix by max)
+  // hand-hand pairs that survive MuJoCo's static filters, body pair by body pair: 16-bit codes g1 * 256 + g2, four to a double (the
+  // table is streamed once per step by every warp: 3.2 KB instead of 13 KB, L1 is ~28 KB next to 227 KB of shared memory)
+  double nhh, hh_pair[LMAXHH / 4];
 };
 
 // per-warp shared-memory work area
 struct LeapWork {
   double qpos[LEAP_NQ], qvel[LEAP_NV], warm[LEAP_NV], ctrl[LEAP_NU];
-  double xpos[LB][3], xquat[LB][4], xmat[LB][9], xipos[LB][3], Iw[LB][6], xanchor[LB][3], xaxis[LB][3];
+  double xpos[LB][3], xmat[LB][9], xanchor[LB][3], xaxis[LB][3];  // (xquat / xipos / Iw are dead after the mass matrix: they alias Jc, see below)
   double Mc[6];          // cube block: 3 translational masses are Mc[0..2]; rotational block is model.cube_Irot
   double Mf[4][4][4];    // finger blocks
   // Newton Hessian in arrow form (dof order: 6 cube dofs, then 4 fingers x 4): cube block, finger blocks, coupling
   double Hcc[6][6], Hcf[4][4][6], Hff[4][4][4], xc[6], yf[4][4];
   double qfrc_bias[LEAP_NV], qfrc_smooth[LEAP_NV], qacc_smooth[LEAP_NV], qacc[LEAP_NV], qfrc_constraint[LEAP_NV];
   double Ma[LEAP_NV], grad[LEAP_NV], search[LEAP_NV], Mv[LEAP_NV], tmp[LEAP_NV];
-  double cdist[LMAXCON], cpos[LMAXCON][3], cframe[LMAXCON][9], cmu[LMAXCON], cfri[LMAXCON], cHc[LMAXCON][9];
+  double cdist[LMAXCON], cpos[LMAXCON][3], cframe[LMAXCON][9], cmu[LMAXCON], cfri[LMAXCON];  // (cframe doubles as the cone Hessian, see leap_cHc)
   double cDm[LMAXCON];   // D0 / (mu^2 (1 + mu^2)) of the contact's middle (cone) zone: fixed during the solve, divided once per step
   double Jc[3 * LMAXCON][10];  // compressed contact rows: 6 cube dofs + 4 dofs of the touched finger
-  double eD[LMAXEFC], eR[LMAXEFC], earef[LMAXEFC], ejar[LMAXEFC], ejv[LMAXEFC], eforce[LMAXEFC], efloss[LMAXEFC], esign[LMAXEFC];
-  int estate[LMAXEFC], edof[LMAXEFC];
-  int cbody[LMAXCON], cfinger[LMAXCON], cdepth[LMAXCON], cswap[LMAXCON];
-  int cand[LMAXG];
+  double eD[LMAXEFC], eR[LMAXEFC], earef[LMAXEFC], ejar[LMAXEFC], ejv[LMAXEFC], eforce[LMAXEFC];
+  double efloss[LMAXFL], esign[LMAXFL];  // friction-loss / limit rows only
+  int estate[LMAXEFC], edof[LMAXFL];
+  // bodies of geom1 / geom2 (-1 static, 0 cube, 1 + 4f + d link d of finger f) and where their Jacobian entries sit in the compressed row:
+  // cfa = first block Jc[.][0..5] (-1: the cube's 6 dofs, f >= 0: finger f's 4 dofs, -2: empty), cfinger = second block Jc[.][6..9] (finger, -1: empty)
+  int cbA[LMAXCON], cbB[LMAXCON], cfa[LMAXCON], cfinger[LMAXCON];
   int limrow[16][2];   // efc row of joint j's lower / upper limit, -1 when inactive
-  int ncon, nefc, nfl, ncand, solver_iter;
+  int ncon, nefc, nfl, ncand, solver_iter, ncross;  // ncross: contacts between two different fingers (they break the arrow structure)
   double cost, gauss;
 };
 
 // Narrow-phase scratch of ONE candidate pair (geom pose, raw contacts, clipping polygons).  LCOL_LANES of them alias the solver arrays
 // cHc / cDm / Jc of the work area, which are dead until the constraint rows are built: the collision routines then touch no local memory
 // (the kernel had a 1 152-byte stack frame per thread = 38 MB of local memory per launch, 17 MB of it reaching DRAM).
-struct LeapColScratch { double gp[3], gm[9]; LRaw raw[8]; LBoxScratch box; };
+struct LeapColScratch { double gp[3], gm[9], gp2[3], gm2[9]; LRaw raw[8]; LBoxScratch box; };
 constexpr int LCOL_LANES = 8;
-static_assert(sizeof(LeapColScratch) * LCOL_LANES <= sizeof(double) * (LMAXCON * 9 + LMAXCON + 3 * LMAXCON * 10), "collision scratch must fit into cHc + cDm + Jc");
-static_assert(offsetof(LeapWork, Jc) == offsetof(LeapWork, cHc) + sizeof(double) * (LMAXCON * 9 + LMAXCON), "cHc, cDm, Jc must be contiguous");
+static_assert(sizeof(LeapColScratch) * LCOL_LANES <= sizeof(double) * (LMAXCON + 3 * LMAXCON * 10), "collision scratch must fit into cDm + Jc");
+static_assert(offsetof(LeapWork, Jc) == offsetof(LeapWork, cDm) + sizeof(double) * LMAXCON, "cDm, Jc must be contiguous");
+
+// Arrays with disjoint lifetimes share storage (the work area decides how many rollouts fit on an SM):
+//  * xquat / xipos / Iw are written by the kinematics and last read by the mass matrix + bias pass; Jc is written when the constraint rows
+//    are built, later in the same step;
+//  * a contact's frame is last read when its Jacobian rows are built; its 3x3 cone Hessian is first written by the solver after that;
+//  * the solver's row arrays eD .. eforce are dead during collision detection: geom centres and candidate lists live there.
+__device__ __forceinline__ double (*leap_xquat(LeapWork* W))[4] { return reinterpret_cast<double(*)[4]>(&W->Jc[0][0]); }
+__device__ __forceinline__ double (*leap_xipos(LeapWork* W))[3] { return reinterpret_cast<double(*)[3]>(&W->Jc[0][0] + 4 * LB); }
+__device__ __forceinline__ double (*leap_Iw(LeapWork* W))[6] { return reinterpret_cast<double(*)[6]>(&W->Jc[0][0] + 7 * LB); }
+__device__ __forceinline__ double* leap_cHc(LeapWork* W, int c) { return W->cframe[c]; }
+__device__ __forceinline__ const double* leap_cHc(const LeapWork* W, int c) { return W->cframe[c]; }
+struct LeapColLists { double gc[LMAXG][4]; unsigned short hc[512], hf[512]; int cand[LMAXG]; };  // geom centre + bounding radius, hand-hand candidates, cube candidates
+static_assert(sizeof(LeapColLists) <= sizeof(double) * 6 * LMAXEFC, "collision lists must fit into eD .. eforce");
+static_assert(offsetof(LeapWork, eforce) == offsetof(LeapWork, eD) + sizeof(double) * 5 * LMAXEFC, "eD .. eforce must be contiguous");
+__device__ __forceinline__ LeapColLists* leap_col_lists(LeapWork* W) { return reinterpret_cast<LeapColLists*>(&W->eD[0]); }
 
 // optional phase timers (clock64 deltas accumulated by lane 0): kin, mass+bias, collision, constraints, smooth, solver, integrate,
 // and inside the solver: update, direction (H + Cholesky + solve), line search, #newton iterations
-__device__ unsigned long long g_leap_prof[16];
+__device__ unsigned long long g_leap_prof[24];  // [16..18]: dense Newton directions, hand-hand contacts, of those inside one finger / against the palm; [19..20]: hand-hand pairs past the bounding spheres / past the pre-filter; [21..23]: slowest block (cycles), sum over blocks, blocks
 #define LPROF_T() (prof ? clock64() : 0)
 #define LPROF_ADD(slot, t0) do { if (prof && lane == 0) atomicAdd(&g_leap_prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
 
@@ -86,13 +110,16 @@ enum { LST_SATISFIED = 0, LST_QUADRATIC = 1, LST_LINEARNEG = 2, LST_LINEARPOS = 
 
 // ------------------------------------------------------------------ kinematics (mj_kinematics + mj_comPos)
 __device__ inline void leap_kinematics(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  double(*xquat)[4] = leap_xquat(W);
+  double(*xipos)[3] = leap_xipos(W);
+  double(*Iw)[6] = leap_Iw(W);
   if (lane == 0) {  // chain 0: the free cube
     lquat_normalize(W->qpos + 3);
 #pragma unroll
     for (int k = 0; k < 3; k++) { W->xpos[0][k] = W->qpos[k]; W->xanchor[0][k] = W->qpos[k]; W->xaxis[0][k] = (k == 2); }
 #pragma unroll
-    for (int k = 0; k < 4; k++) W->xquat[0][k] = W->qpos[3 + k];
-    lquat2mat(W->xmat[0], W->xquat[0]);
+    for (int k = 0; k < 4; k++) xquat[0][k] = W->qpos[3 + k];
+    lquat2mat(W->xmat[0], xquat[0]);
   } else if (lane <= 4) {  // chains 1..4: fingers hanging off the static palm
     const int f = lane - 1;
     double ppos[3], pquat[4], pmat[9];
@@ -127,7 +154,7 @@ __device__ inline void leap_kinematics(const LeapModel* __restrict__ m, LeapWork
 #pragma unroll
       for (int k = 0; k < 3; k++) { W->xpos[b][k] = pos[k]; ppos[k] = pos[k]; }
 #pragma unroll
-      for (int k = 0; k < 4; k++) { W->xquat[b][k] = nq[k]; pquat[k] = nq[k]; }
+      for (int k = 0; k < 4; k++) { xquat[b][k] = nq[k]; pquat[k] = nq[k]; }
 #pragma unroll
       for (int k = 0; k < 9; k++) { W->xmat[b][k] = mat[k]; pmat[k] = mat[k]; }
     }
@@ -138,7 +165,7 @@ __device__ inline void leap_kinematics(const LeapModel* __restrict__ m, LeapWork
     double t[3], im[9];
     lmat_vec(t, W->xmat[b], m->body_ipos[b]);
 #pragma unroll
-    for (int k = 0; k < 3; k++) W->xipos[b][k] = W->xpos[b][k] + t[k];
+    for (int k = 0; k < 3; k++) xipos[b][k] = W->xpos[b][k] + t[k];
     lmat_mul(im, W->xmat[b], m->body_imat[b]);
     int e = 0;
 #pragma unroll
@@ -148,7 +175,7 @@ __device__ inline void leap_kinematics(const LeapModel* __restrict__ m, LeapWork
         double s = 0;
 #pragma unroll
         for (int k = 0; k < 3; k++) s += im[3 * r + k] * m->body_inertia[b][k] * im[3 * c + k];
-        W->Iw[b][e++] = s;  // xx xy xz yy yz zz
+        Iw[b][e++] = s;  // xx xy xz yy yz zz
       }
   }
   __syncwarp();
@@ -162,6 +189,8 @@ __device__ __forceinline__ void Iw_mul(double* r, const double* I6, const double
 
 // ------------------------------------------------------------------ mass matrix (mj_crb) and bias forces (mj_rne), lane per chain
 __device__ inline void leap_mass_and_bias(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  const double(*xipos)[3] = leap_xipos(W);
+  const double(*Iw)[6] = leap_Iw(W);
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 3; k++) W->Mc[k] = m->body_mass[0];
@@ -181,9 +210,9 @@ __device__ inline void leap_mass_and_bias(const LeapModel* __restrict__ m, LeapW
       for (int b = i; b < 4; b++) {
         double r[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) r[k] = W->xipos[b0 + b][k] - W->xanchor[b0 + i][k];
+        for (int k = 0; k < 3; k++) r[k] = xipos[b0 + b][k] - W->xanchor[b0 + i][k];
         lcross3(c[i][b], W->xaxis[b0 + i], r);
-        Iw_mul(Ia[i][b], W->Iw[b0 + b], W->xaxis[b0 + i]);
+        Iw_mul(Ia[i][b], Iw[b0 + b], W->xaxis[b0 + i]);
       }
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -228,14 +257,14 @@ __device__ inline void leap_mass_and_bias(const LeapModel* __restrict__ m, LeapW
       for (int k = 0; k < 3; k++) { Ac[k] += t[k] + t2[k]; P[k] = W->xpos[b][k]; }
       double ac[3], Iwa[3], Iww[3], n[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) r[k] = W->xipos[b][k] - W->xpos[b][k];
+      for (int k = 0; k < 3; k++) r[k] = xipos[b][k] - W->xpos[b][k];
       lcross3(t, Wv, r); lcross3(t2, Wv, t); lcross3(t, A, r);
 #pragma unroll
       for (int k = 0; k < 3; k++) { ac[k] = Ac[k] + t[k] + t2[k]; F[d][k] = m->body_mass[b] * ac[k]; }
-      Iw_mul(Iwa, W->Iw[b], A);
-      Iw_mul(Iww, W->Iw[b], Wv);
+      Iw_mul(Iwa, Iw[b], A);
+      Iw_mul(Iww, Iw[b], Wv);
       lcross3(t, Wv, Iww);
-      lcross3(n, W->xipos[b], F[d]);
+      lcross3(n, xipos[b], F[d]);
 #pragma unroll
       for (int k = 0; k < 3; k++) N0[d][k] = Iwa[k] + t[k] + n[k];
     }
@@ -315,11 +344,54 @@ __device__ inline void leap_block_solve(const LeapModel* __restrict__ m, LeapWor
   __syncwarp();
 }
 
-// ------------------------------------------------------------------ collision (reduced geometry; routines in geom.cuh)
+// ------------------------------------------------------------------ collision (routines in geom.cuh)
+// world pose of hand geom g (static geoms are stored in the world frame)
+__device__ __forceinline__ void leap_geom_pose(const LeapModel* __restrict__ m, const LeapWork* W, int g, double* gp, double* gm) {
+  const int b = (int)m->geom_body[g];
+  if (b < 0) {
+    for (int k = 0; k < 3; k++) gp[k] = m->geom_pos[g][k];
+    for (int k = 0; k < 9; k++) gm[k] = m->geom_mat[g][k];
+  } else {
+    double t[3];
+    lmat_vec(t, W->xmat[b], m->geom_pos[g]);
+    for (int k = 0; k < 3; k++) gp[k] = W->xpos[b][k] + t[k];
+    lmat_mul(gm, W->xmat[b], m->geom_mat[g]);
+  }
+}
+
+// Append this round's raw contacts (n per lane) behind the ncon already stored, in lane order (= pair order): exclusive prefix of n
+// over the lanes.  bA / bB: bodies of geom1 / geom2.  Returns the new running total (which may exceed LMAXCON: the surplus is dropped).
+__device__ __forceinline__ int leap_store_contacts(LeapWork* W, int lane, int n, const LRaw* raw, int ncon, int bA, int bB, double mu) {
+  int pre = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += v; }
+  const int total = __shfl_sync(FULL, pre, 31);
+  pre -= n;
+  for (int i = 0; i < n; i++) {
+    const int slot = ncon + pre + i;
+    if (slot < LMAXCON) {
+      W->cdist[slot] = raw[i].dist;
+      for (int k = 0; k < 3; k++) { W->cpos[slot][k] = raw[i].pos[k]; W->cframe[slot][k] = raw[i].normal[k]; }
+      l_make_frame(W->cframe[slot]);
+      const int fA = bA >= 1 ? (bA - 1) >> 2 : -1, fB = bB >= 1 ? (bB - 1) >> 2 : -1;
+      W->cbA[slot] = bA; W->cbB[slot] = bB;
+      if (bA == 0 || bB == 0) { W->cfa[slot] = -1; W->cfinger[slot] = bA == 0 ? fB : fA; }        // cube against a finger or the palm
+      else if (fA >= 0 && fB >= 0 && fA != fB) { W->cfa[slot] = fA; W->cfinger[slot] = fB; }      // two different fingers
+      else { W->cfa[slot] = -2; W->cfinger[slot] = fA >= 0 ? fA : fB; }                           // one finger: against itself or the palm
+      W->cfri[slot] = mu;
+    }
+  }
+  return ncon + total;
+}
+
 __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork* W, int lane, int prof = 0) {
   const int ng = (int)m->ngeom;
   long long tc0 = LPROF_T();
   const double* cp = W->xpos[0];
+  // the solver's row arrays are dead until the constraint rows are built: they hold the world centres (+ bounding radii) of the hand
+  // geoms and the candidate lists
+  LeapColLists* CL = leap_col_lists(W);
+  double(*gc)[4] = CL->gc;
   // broad phase: bounding spheres against the cube's; ordered compaction keeps the geom order of the pair list
   int base = 0;
   for (int g0 = 0; g0 < ng; g0 += 32) {
@@ -330,6 +402,7 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
       double gp[3];
       if (b < 0) { gp[0] = m->geom_pos[g][0]; gp[1] = m->geom_pos[g][1]; gp[2] = m->geom_pos[g][2]; }
       else { double t[3]; lmat_vec(t, W->xmat[b], m->geom_pos[g]); gp[0] = W->xpos[b][0] + t[0]; gp[1] = W->xpos[b][1] + t[1]; gp[2] = W->xpos[b][2] + t[2]; }
+      gc[g][0] = gp[0]; gc[g][1] = gp[1]; gc[g][2] = gp[2]; gc[g][3] = m->geom_rbound[g];
       double dc[3] = {gp[0] - cp[0], gp[1] - cp[1], gp[2] - cp[2]};
       keep = !(lnorm3(dc) > m->geom_rbound[g] + m->cube_rbound);  // the oracle's bounding-sphere test
       if (keep) {
@@ -361,7 +434,7 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
       }
     }
     const unsigned mask = __ballot_sync(FULL, keep);
-    if (keep) W->cand[base + __popc(mask & ((1u << lane) - 1))] = g;
+    if (keep) CL->cand[base + __popc(mask & ((1u << lane) - 1))] = g;
     base += __popc(mask);
   }
   __syncwarp();
@@ -369,61 +442,135 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
   LPROF_ADD(11, tc0); tc0 = LPROF_T();
   if (prof && lane == 0) atomicAdd(&g_leap_prof[13], (unsigned long long)ncand);
   int ncon = 0;
-  LeapColScratch* scr_all = reinterpret_cast<LeapColScratch*>(&W->cHc[0][0]);
+  LeapColScratch* scr_all = reinterpret_cast<LeapColScratch*>(&W->cDm[0]);
   for (int c0 = 0; c0 < ncand; c0 += LCOL_LANES) {  // LCOL_LANES pairs per round (2.7 candidates per step on average), one per lane
     const int ci = c0 + lane;
     LeapColScratch* S = scr_all + (lane < LCOL_LANES ? lane : 0);
-    const LRaw* raw = S->raw;
-    int n = 0, g = -1, b = -1, swap = 0;
+    int n = 0, g = 0, b = -1, swap = 0;
     if (lane < LCOL_LANES && ci < ncand) {
-      g = W->cand[ci];
+      g = CL->cand[ci];
       b = (int)m->geom_body[g];
-      double* gp = S->gp;
-      double* gm = S->gm;
-      if (b < 0) {
-        for (int k = 0; k < 3; k++) gp[k] = m->geom_pos[g][k];
-        for (int k = 0; k < 9; k++) gm[k] = m->geom_mat[g][k];
-      } else {
-        double t[3];
-        lmat_vec(t, W->xmat[b], m->geom_pos[g]);
-        for (int k = 0; k < 3; k++) gp[k] = W->xpos[b][k] + t[k];
-        lmat_mul(gm, W->xmat[b], m->geom_mat[g]);
-      }
-      if ((int)m->geom_type[g] == 6) n = l_box_box(cp, W->xmat[0], m->cube_size, gp, gm, m->geom_size[g], 0.0, S->raw, 8, &S->box);  // geom1 = cube
-      else { n = l_sphere_box(gp, m->geom_size[g][0], cp, W->xmat[0], m->cube_size, 0.0, S->raw); swap = 1; }          // geom1 = sphere
+      leap_geom_pose(m, W, g, S->gp, S->gm);
+      if ((int)m->geom_type[g] == 6) n = l_box_box(cp, W->xmat[0], m->cube_size, S->gp, S->gm, m->geom_size[g], 0.0, S->raw, 8, &S->box);  // geom1 = cube
+      else { n = l_sphere_box(S->gp, m->geom_size[g][0], cp, W->xmat[0], m->cube_size, 0.0, S->raw); swap = 1; }          // geom1 = sphere
     }
-    // ordered slot allocation: exclusive prefix of n over the lanes
-    int pre = n;
+    ncon = leap_store_contacts(W, lane, n, S->raw, ncon, swap ? b : 0, swap ? 0 : b, m->geom_mu[g]);
+  }
+  LPROF_ADD(12, tc0); tc0 = LPROF_T();
+  // ---- hand-hand pairs.  (1) bounding spheres of every listed pair (squared form with a relative slack: a superset of the oracle's
+  // survivors, the contact routines decide), (2) the conservative pre-filters on the survivors, (3) contact generation, LCOL_LANES
+  // pairs per round.  Typical step: ~14 of 1 621 pairs pass (1), none pass (2).
+  const int nhh = (int)m->nhh;
+  unsigned short* hc = CL->hc;
+  unsigned short* hf = CL->hf;
+  constexpr int HCAP = 512;
+  const unsigned short* hp = reinterpret_cast<const unsigned short*>(m->hh_pair);
+  int nh = 0;
+  // four pairs per lane and round, all table loads of a round in flight together, the next round's prefetched: the loop is bound by
+  // load latency (global table -> shared geom centres), not by arithmetic
+  int nxt[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += v; }
-    const int total = __shfl_sync(FULL, pre, 31);
-    pre -= n;
-    for (int i = 0; i < n; i++) {
-      const int slot = ncon + pre + i;
-      if (slot < LMAXCON) {
-        W->cdist[slot] = raw[i].dist;
-        for (int k = 0; k < 3; k++) { W->cpos[slot][k] = raw[i].pos[k]; W->cframe[slot][k] = raw[i].normal[k]; }
-        l_make_frame(W->cframe[slot]);
-        W->cbody[slot] = b; W->cswap[slot] = swap;
-        W->cfinger[slot] = b >= 1 ? (b - 1) >> 2 : -1;
-        W->cdepth[slot] = b >= 1 ? (b - 1) & 3 : -1;
-        W->cfri[slot] = m->geom_mu[g];
+  for (int k = 0; k < 4; k++) { const int p = 32 * k + lane; nxt[k] = p < nhh ? (int)__ldg(hp + p) : -1; }
+  for (int p0 = 0; p0 < nhh; p0 += 128) {
+    int code[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) code[k] = nxt[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int p = p0 + 128 + 32 * k + lane; nxt[k] = p < nhh ? (int)__ldg(hp + p) : -1; }
+    bool keep[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      keep[k] = false;
+      if (code[k] >= 0) {
+        const double* a = gc[code[k] >> 8];
+        const double* b = gc[code[k] & 255];
+        const double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2], rr = a[3] + b[3];
+        keep[k] = dx * dx + dy * dy + dz * dz <= rr * rr * (1 + 1e-12);
       }
     }
-    ncon += total;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned mask = __ballot_sync(FULL, keep[k]);
+      const int at = nh + __popc(mask & ((1u << lane) - 1));
+      if (keep[k] && at < HCAP) hc[at] = (unsigned short)code[k];
+      nh += __popc(mask);
+    }
   }
   __syncwarp();
-  if (lane == 0) { W->ncon = ncon < LMAXCON ? ncon : LMAXCON; if (ncon > LMAXCON) atomicAdd(contact_overflow_counter(m), 1ull); }
+  bool hh_overflow = nh > HCAP;
+  if (hh_overflow) nh = HCAP;
+  int nf = 0;
+  for (int c0 = 0; c0 < nh; c0 += 32) {
+    const int ci = c0 + lane;
+    bool keep = false;
+    int code = 0;
+    if (ci < nh) {
+      code = hc[ci];
+      const int g1 = code >> 8, g2 = code & 255;
+      const bool box1 = (int)m->geom_type[g1] == 6, box2 = (int)m->geom_type[g2] == 6;
+      if (box1 && box2) {
+        double p1[3], m1[9], p2[3], m2[9];
+        leap_geom_pose(m, W, g1, p1, m1);
+        leap_geom_pose(m, W, g2, p2, m2);
+        keep = l_box_box_may_touch(p1, m1, m->geom_size[g1], p2, m2, m->geom_size[g2]);
+      } else if (box1 != box2) {
+        const int gs = box1 ? g2 : g1, gb = box1 ? g1 : g2;
+        double pb[3], mb[9];
+        leap_geom_pose(m, W, gb, pb, mb);
+        keep = l_sphere_box_may_touch(gc[gs], m->geom_size[gs][0], pb, mb, m->geom_size[gb]);
+      } else keep = true;  // sphere-sphere: the bounding spheres ARE the geoms
+    }
+    const unsigned mask = __ballot_sync(FULL, keep);
+    if (keep) hf[nf + __popc(mask & ((1u << lane) - 1))] = (unsigned short)code;
+    nf += __popc(mask);
+  }
   __syncwarp();
-  LPROF_ADD(12, tc0);
-  if (prof && lane == 0) atomicAdd(&g_leap_prof[14], (unsigned long long)ncon);
+  for (int c0 = 0; c0 < nf; c0 += LCOL_LANES) {
+    const int ci = c0 + lane;
+    LeapColScratch* S = scr_all + (lane < LCOL_LANES ? lane : 0);
+    int n = 0, bA = -1, bB = -1;
+    double mu = 0;
+    if (lane < LCOL_LANES && ci < nf) {
+      const int code = hf[ci];
+      int g1 = code >> 8, g2 = code & 255;
+      if ((int)m->geom_type[g1] > (int)m->geom_type[g2]) { const int t = g1; g1 = g2; g2 = t; }  // the oracle orders a pair by geom type (sphere < box)
+      bA = (int)m->geom_body[g1]; bB = (int)m->geom_body[g2];
+      mu = fmax(m->geom_fr[g1], m->geom_fr[g2]);
+      leap_geom_pose(m, W, g1, S->gp, S->gm);
+      leap_geom_pose(m, W, g2, S->gp2, S->gm2);
+      const bool box1 = (int)m->geom_type[g1] == 6, box2 = (int)m->geom_type[g2] == 6;
+      if (box1 && box2) n = l_box_box(S->gp, S->gm, m->geom_size[g1], S->gp2, S->gm2, m->geom_size[g2], 0.0, S->raw, 8, &S->box);
+      else if (box2) n = l_sphere_box(S->gp, m->geom_size[g1][0], S->gp2, S->gm2, m->geom_size[g2], 0.0, S->raw);
+      else n = l_sphere_sphere(S->gp, m->geom_size[g1][0], S->gp2, m->geom_size[g2][0], 0.0, S->raw);
+    }
+    ncon = leap_store_contacts(W, lane, n, S->raw, ncon, bA, bB, mu);
+  }
+  __syncwarp();
+  const int nkept = ncon < LMAXCON ? ncon : LMAXCON;
+  int ncross = 0;
+  for (int c0 = 0; c0 < nkept; c0 += 32) ncross += __popc(__ballot_sync(FULL, c0 + lane < nkept && W->cfa[c0 + lane] >= 0));
+  if (lane == 0) {
+    W->ncon = nkept; W->ncross = ncross;
+    if (ncon > LMAXCON || hh_overflow) atomicAdd(contact_overflow_counter(m), 1ull);
+  }
+  __syncwarp();
+  LPROF_ADD(15, tc0);
+  if (prof && lane == 0) {
+    atomicAdd(&g_leap_prof[14], (unsigned long long)ncon);
+    int nh2 = 0, none = 0;
+    for (int c = 0; c < nkept; c++) { if (W->cbA[c] != 0 && W->cbB[c] != 0) { nh2++; if (W->cfa[c] == -2) none++; } }
+    atomicAdd(&g_leap_prof[17], (unsigned long long)nh2); atomicAdd(&g_leap_prof[18], (unsigned long long)none);
+    atomicAdd(&g_leap_prof[19], (unsigned long long)nh); atomicAdd(&g_leap_prof[20], (unsigned long long)nf);
+  }
 }
 
 // ------------------------------------------------------------------ constraint rows (mj_makeConstraint + mj_makeImpedance)
 __device__ __forceinline__ double leap_Jrow_dot(const LeapWork* W, int crow, const double* x) {
   const double* J = W->Jc[crow];
-  const int f = W->cfinger[crow / 3];
-  double s = J[0] * x[0] + J[1] * x[1] + J[2] * x[2] + J[3] * x[3] + J[4] * x[4] + J[5] * x[5];
+  const int fa = W->cfa[crow / 3], f = W->cfinger[crow / 3];
+  double s = 0;
+  if (fa == -1) s = J[0] * x[0] + J[1] * x[1] + J[2] * x[2] + J[3] * x[3] + J[4] * x[4] + J[5] * x[5];
+  else if (fa >= 0) { const double* xx = x + 6 + 4 * fa; s = J[0] * xx[0] + J[1] * xx[1] + J[2] * xx[2] + J[3] * xx[3]; }
   if (f >= 0) { const double* xx = x + 6 + 4 * f; s += J[6] * xx[0] + J[7] * xx[1] + J[8] * xx[2] + J[9] * xx[3]; }
   return s;
 }
@@ -452,34 +599,44 @@ __device__ inline void leap_make_constraint(const LeapModel* __restrict__ m, Lea
   const int nfl = nfr + __popc(mlo) + __popc(mhi);
   const int ncon = W->ncon;
   __syncwarp();
-  // contact Jacobians: lane per (contact, frame axis): 6 cube entries + up to 4 finger entries
+  // contact Jacobians, lane per (contact, frame axis): J = frame^T (Jp(body2) - Jp(body1)) in the compressed layout of the work area
+  // (first block: the cube's 6 dofs or a finger's 4, second block: a finger's 4; a contact inside ONE finger sums both sides into
+  // the second block)
   for (int e = lane; e < 3 * ncon; e += 32) {
     const int c = e / 3, a = e - 3 * c;
     const double* fr = W->cframe[c] + 3 * a;
     const double* p = W->cpos[c];
-    const double sgn_cube = W->cswap[c] ? 1.0 : -1.0;  // J = frame^T (Jp(body2) - Jp(body1)); cube is body2 when swapped
     double* J = W->Jc[e];
-    // cube: translation columns are the identity, rotation columns are (body axis) x (p - xpos)
-    double r[3] = {p[0] - W->xpos[0][0], p[1] - W->xpos[0][1], p[2] - W->xpos[0][2]};
 #pragma unroll
-    for (int k = 0; k < 3; k++) J[k] = sgn_cube * fr[k];
+    for (int k = 0; k < 10; k++) J[k] = 0;
+    const int fa = W->cfa[c];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      double ax[3] = {W->xmat[0][k], W->xmat[0][3 + k], W->xmat[0][6 + k]}, cr[3];
-      lcross3(cr, ax, r);
-      J[3 + k] = sgn_cube * ldot3(fr, cr);
-    }
-    const int f = W->cfinger[c], dep = W->cdepth[c];
+    for (int side = 0; side < 2; side++) {
+      const int b = side ? W->cbB[c] : W->cbA[c];
+      const double sgn = side ? 1.0 : -1.0;
+      if (b == 0) {
+        // cube: translation columns are the identity, rotation columns are (body axis) x (p - xpos)
+        double r[3] = {p[0] - W->xpos[0][0], p[1] - W->xpos[0][1], p[2] - W->xpos[0][2]};
 #pragma unroll
-    for (int d = 0; d < 4; d++) {
-      double v = 0;
-      if (f >= 0 && d <= dep) {
-        const int b = 1 + 4 * f + d;
-        double rr[3] = {p[0] - W->xanchor[b][0], p[1] - W->xanchor[b][1], p[2] - W->xanchor[b][2]}, cr[3];
-        lcross3(cr, W->xaxis[b], rr);
-        v = -sgn_cube * ldot3(fr, cr);
+        for (int k = 0; k < 3; k++) J[k] = sgn * fr[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double ax[3] = {W->xmat[0][k], W->xmat[0][3 + k], W->xmat[0][6 + k]}, cr[3];
+          lcross3(cr, ax, r);
+          J[3 + k] = sgn * ldot3(fr, cr);
+        }
+      } else if (b >= 1) {
+        const int f = (b - 1) >> 2, dep = (b - 1) & 3, off = fa == f ? 0 : 6;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+          if (d <= dep) {
+            const int bb = 1 + 4 * f + d;
+            double rr[3] = {p[0] - W->xanchor[bb][0], p[1] - W->xanchor[bb][1], p[2] - W->xanchor[bb][2]}, cr[3];
+            lcross3(cr, W->xaxis[bb], rr);
+            J[off + d] += sgn * ldot3(fr, cr);
+          }
+        }
       }
-      J[6 + d] = v;
     }
   }
   if (lane == 0) { W->nfl = nfl; W->nefc = nfl + 3 * ncon; }
@@ -496,10 +653,9 @@ __device__ inline void leap_make_constraint(const LeapModel* __restrict__ m, Lea
       const int e = r - nfl, c = e / 3;
       solref = m->con_solref; solimp = m->con_solimp; pos = W->cdist[c];
       vel = leap_Jrow_dot(W, e, W->qvel);
-      const int b = W->cbody[c];
-      diagA = m->body_invw[0] + (b >= 0 ? m->body_invw[b] : 0.0);
+      const int bA = W->cbA[c], bB = W->cbB[c];
+      diagA = (bA >= 0 ? m->body_invw[bA] : 0.0) + (bB >= 0 ? m->body_invw[bB] : 0.0);
       friction_row = (e - 3 * c) > 0;
-      W->efloss[r] = 0;
     }
     double ref0 = solref[0], ref1 = solref[1];
     const double dmax = fmin(fmax(solimp[1], B2_MINIMP), B2_MAXIMP);
@@ -616,7 +772,7 @@ __device__ __noinline__ void leap_constraint_update(const LeapModel* __restrict_
   for (int r = lane; r < nfl; r += 32) cost += leap_row_eval(W, r, nfr, W->ejar[r], &W->eforce[r], &W->estate[r]);
   for (int c = lane; c < ncon; c += 32) {
     const int r0 = nfl + 3 * c;
-    cost += leap_cone_eval(W, c, r0, W->ejar + r0, W->eforce + r0, &W->estate[r0], want_h ? W->cHc[c] : nullptr);
+    cost += leap_cone_eval(W, c, r0, W->ejar + r0, W->eforce + r0, &W->estate[r0], want_h ? leap_cHc(W, c) : nullptr);
     W->estate[r0 + 1] = W->estate[r0 + 2] = W->estate[r0];
   }
   cost = lwsum(cost);
@@ -635,10 +791,16 @@ __device__ __noinline__ void leap_constraint_update(const LeapModel* __restrict_
     }
     const int fi = i >= 6 ? (i - 6) >> 2 : -1, ki = i < 6 ? i : 6 + ((i - 6) & 3);
     for (int c = 0; c < ncon; c++) {
-      if (i >= 6 && W->cfinger[c] != fi) continue;
+      if (i < 6 ? W->cfa[c] != -1 : W->cfinger[c] != fi) continue;
 #pragma unroll
       for (int a = 0; a < 3; a++) f += W->Jc[3 * c + a][ki] * W->eforce[nfl + 3 * c + a];
     }
+    if (i >= 6 && W->ncross > 0)  // contacts between two fingers keep the first finger's entries in the first block
+      for (int c = 0; c < ncon; c++) {
+        if (W->cfa[c] != fi) continue;
+#pragma unroll
+        for (int a = 0; a < 3; a++) f += W->Jc[3 * c + a][ki - 6] * W->eforce[nfl + 3 * c + a];
+      }
     W->qfrc_constraint[i] = f;
     W->grad[i] = W->Ma[i] - W->qfrc_smooth[i] - f;
     g = (W->Ma[i] - W->qfrc_smooth[i]) * (qacc[i] - W->qacc_smooth[i]);
@@ -691,13 +853,14 @@ __device__ inline void leap_newton_direction(const LeapModel* __restrict__ m, Le
       Wm[0] = W->eD[nfl + 3 * c]; Wm[4] = W->eD[nfl + 3 * c + 1]; Wm[8] = W->eD[nfl + 3 * c + 2];
     } else {
 #pragma unroll
-      for (int k = 0; k < 9; k++) Wm[k] = W->cHc[c][k];
+      for (int k = 0; k < 9; k++) Wm[k] = leap_cHc(W, c)[k];
     }
     const double(*J)[10] = &W->Jc[3 * c];
     // pass A: cube-cube (lanes 0..20) and finger-finger (lanes 21..30)
     int ia = -1, ja = -1;
     double* dst = nullptr;
-    if (lane < 21) { ia = tri_get(TRI6_I, lane); ja = tri_get(TRI6_J, lane); dst = &W->Hcc[ia][ja]; }
+    const bool with_cube = W->cfa[c] == -1;  // (a contact inside one finger / finger-palm only touches that finger's block)
+    if (lane < 21) { if (with_cube) { ia = tri_get(TRI6_I, lane); ja = tri_get(TRI6_J, lane); dst = &W->Hcc[ia][ja]; } }
     else if (lane < 31 && fc >= 0) { const int e = lane - 21; ia = 6 + tri_get(TRI4_I, e); ja = 6 + tri_get(TRI4_J, e); dst = &W->Hff[fc][ia - 6][ja - 6]; }
     if (dst) {
       double h = 0;
@@ -708,7 +871,7 @@ __device__ inline void leap_newton_direction(const LeapModel* __restrict__ m, Le
       *dst += h;
     }
     // pass B: finger-cube coupling (lanes 0..23)
-    if (fc >= 0 && lane < 24) {
+    if (with_cube && fc >= 0 && lane < 24) {
       const int r = lane / 6, cc = lane - 6 * r;
       double h = 0;
 #pragma unroll
@@ -824,8 +987,110 @@ __device__ inline void leap_newton_direction(const LeapModel* __restrict__ m, Le
   __syncwarp();
 }
 
-// Line search state held in REGISTERS: lane r owns friction/limit row r (nfl <= 32) and lane c owns contact c (ncon <= 24),
-// so one evaluation of the 1-D cost derivatives is register math plus two warp reductions.
+// Newton direction when two DIFFERENT fingers touch each other (rare: ~0.1 % of the rollout steps of the C4 bench scenario): the finger
+// blocks couple, the arrow structure is gone, so the Hessian is assembled dense (22 x 22, lower triangle) and factorised by the
+// warp, lane per row.  The (packed) matrix aliases the kinematics arrays, which are dead once the constraint rows are built.
+static_assert(LEAP_NV * (LEAP_NV + 1) / 2 <= LB * 18, "packed dense Hessian must fit into xpos .. xaxis");
+static_assert(offsetof(LeapWork, Mc) == offsetof(LeapWork, xpos) + sizeof(double) * LB * 18, "xpos .. xaxis must be contiguous");
+#define LH(i, j) Hp[(i) * ((i) + 1) / 2 + (j)] /* lower triangle, row-packed */
+__device__ __noinline__ void leap_newton_direction_dense(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  const int nfl = W->nfl, ncon = W->ncon;
+  double* Hp = &W->xpos[0][0];
+  double* dinv = W->tmp;
+  for (int e = lane; e < LEAP_NV * (LEAP_NV + 1) / 2; e += 32) Hp[e] = 0.0;
+  // (row, column) of entries `lane` and `lane + 32` of a 10 x 10 lower triangle, decoded once for all contacts
+  int si0 = 0, sj0 = lane, si1 = 0, sj1 = lane + 32;
+  while (sj0 > si0) { sj0 -= si0 + 1; si0++; }
+  while (sj1 > si1) { sj1 -= si1 + 1; si1++; }
+  if (lane + 32 >= 55) si1 = -1;
+  __syncwarp();
+  if (lane < LEAP_NV) {  // mass matrix + friction-loss / limit rows in their quadratic zone (diagonal), lane per dof
+    const int i = lane;
+    if (i < 3) LH(i, i) = W->Mc[i];
+    else if (i < 6) { for (int j = 3; j <= i; j++) LH(i, j) = m->cube_Irot[3 * (i - 3) + (j - 3)]; }
+    else {
+      const int f = (i - 6) >> 2, r = (i - 6) & 3;
+      for (int j = 0; j <= r; j++) LH(i, 6 + 4 * f + j) = W->Mf[f][r][j];
+      const int fr = (int)m->fr_row[i], rl = W->limrow[i - 6][0], rh = W->limrow[i - 6][1];
+      if (fr >= 0 && W->estate[fr] == LST_QUADRATIC) LH(i, i) += W->eD[fr];
+      if (rl >= 0 && W->estate[rl] == LST_QUADRATIC) LH(i, i) += W->eD[rl];
+      if (rh >= 0 && W->estate[rh] == LST_QUADRATIC) LH(i, i) += W->eD[rh];
+    }
+  }
+  __syncwarp();
+  for (int c = 0; c < ncon; c++) {
+    const int st = W->estate[nfl + 3 * c];
+    if (st == LST_SATISFIED) continue;
+    double Wm[9];
+    if (st == LST_QUADRATIC) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) Wm[k] = 0;
+      Wm[0] = W->eD[nfl + 3 * c]; Wm[4] = W->eD[nfl + 3 * c + 1]; Wm[8] = W->eD[nfl + 3 * c + 2];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; k++) Wm[k] = leap_cHc(W, c)[k];
+    }
+    const double(*J)[10] = &W->Jc[3 * c];
+    const int fa = W->cfa[c], fb = W->cfinger[c];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {  // lower triangle of the 10 x 10 block the compressed row spans: entries lane and lane + 32
+      const int si = half ? si1 : si0, sj = half ? sj1 : sj0;
+      if (si < 0) continue;
+      const int di = si < 6 ? (fa == -1 ? si : (fa >= 0 && si < 4 ? 6 + 4 * fa + si : -1)) : (fb >= 0 ? 6 + 4 * fb + si - 6 : -1);
+      const int dj = sj < 6 ? (fa == -1 ? sj : (fa >= 0 && sj < 4 ? 6 + 4 * fa + sj : -1)) : (fb >= 0 ? 6 + 4 * fb + sj - 6 : -1);
+      if (di < 0 || dj < 0) continue;
+      double h = 0;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) h += Wm[3 * a + b] * J[a][si] * J[b][sj];
+      if (di >= dj) LH(di, dj) += h; else LH(dj, di) += h;
+    }
+    __syncwarp();
+  }
+  // Cholesky, lane i owns row i; dinv[k] = 1 / L_kk
+  for (int k = 0; k < LEAP_NV; k++) {
+    double d = LH(k, k);
+    if (d < B2_MINVAL) d = B2_MINVAL;
+    const double rs = rsqrt(d);
+    double l = 0;
+    if (lane == k) dinv[k] = rs;
+    if (lane > k && lane < LEAP_NV) { l = LH(lane, k) * rs; LH(lane, k) = l; }
+    __syncwarp();
+    if (lane > k && lane < LEAP_NV) {
+      // row update in batches of four independent entries (loads first: the column is read-only in this phase, the compiler cannot know)
+      double* row = &LH(lane, 0);
+      int j = k + 1;
+      for (; j + 3 <= lane; j += 4) {
+        const double c0 = LH(j, k), c1 = LH(j + 1, k), c2 = LH(j + 2, k), c3 = LH(j + 3, k);
+        const double r0 = row[j], r1 = row[j + 1], r2 = row[j + 2], r3 = row[j + 3];
+        row[j] = r0 - l * c0; row[j + 1] = r1 - l * c1; row[j + 2] = r2 - l * c2; row[j + 3] = r3 - l * c3;
+      }
+      for (; j <= lane; j++) row[j] -= l * LH(j, k);
+    }
+    __syncwarp();
+  }
+  // search = -(L L^T)^-1 grad: column-oriented substitutions, one shuffle per column
+  double x = lane < LEAP_NV ? -W->grad[lane] : 0.0;
+  const double di = lane < LEAP_NV ? dinv[lane] : 0.0;
+  for (int k = 0; k < LEAP_NV; k++) {
+    const double yk = __shfl_sync(FULL, x * di, k);
+    if (lane == k) x = yk;
+    else if (lane > k && lane < LEAP_NV) x -= LH(lane, k) * yk;
+  }
+  for (int k = LEAP_NV - 1; k >= 0; k--) {
+    const double xk = __shfl_sync(FULL, x * di, k);
+    if (lane == k) x = xk;
+    else if (lane < k) x -= LH(k, lane) * xk;
+  }
+  if (lane < LEAP_NV) W->search[lane] = x;
+  __syncwarp();
+}
+#undef LH
+
+// Line search state held in REGISTERS: lane r owns friction/limit row r (nfl <= 32) and lane c owns contact c, so one evaluation of
+// the 1-D cost derivatives is register math plus two warp reductions.  Contacts 32 .. LMAXCON-1 (rare: more than 32 contacts in a step)
+// are evaluated from shared memory by the low lanes on top of their own.
 struct LeapLS {
   double rjar, rjv, rD, rR, rfl;           // my friction/limit row
   double cjar[3], cjv[3], cD[3], cmu, cfr, cDm;  // my contact
@@ -844,8 +1109,32 @@ __device__ __forceinline__ void leap_ls_load(const LeapModel* __restrict__ m, co
   }
 }
 
+// one elliptic contact's contribution to the first / second derivative of the cost along the search direction at step alpha
+__device__ __forceinline__ void leap_ls_contact(const double* cjar, const double* cjv, const double* cD, double mu, double f, double Dm, double alpha,
+                                                double& p1, double& p2) {
+  const double x0 = cjar[0] + alpha * cjv[0], x1 = cjar[1] + alpha * cjv[1], x2 = cjar[2] + alpha * cjv[2];
+  const double U1 = x1 * f, U2 = x2 * f;
+  const double T2 = U1 * U1 + U2 * U2;
+  const double Ti = T2 > B2_MINVAL * B2_MINVAL ? rsqrt(T2) : 0;  // one rsqrt instead of a square root and a division
+  const double N = x0 * mu, T = T2 * Ti;
+  if (N >= mu * T) { /* separating: no force */ }
+  else if (mu * N + T <= 0) {
+    p1 += cD[0] * x0 * cjv[0] + cD[1] * x1 * cjv[1] + cD[2] * x2 * cjv[2];
+    p2 += cD[0] * cjv[0] * cjv[0] + cD[1] * cjv[1] * cjv[1] + cD[2] * cjv[2] * cjv[2];
+  } else {
+    // s = 0.5 Dm (N - mu T)^2 in the scaled space U = S x; chain rule with dU/dalpha = S jv
+    const double NmT = N - mu * T;
+    const double v0 = mu * cjv[0], v1 = f * cjv[1], v2 = f * cjv[2];
+    const double dT = (U1 * v1 + U2 * v2) * Ti;
+    const double dNmT = v0 - mu * dT;
+    const double d2T = (v1 * v1 + v2 * v2 - dT * dT) * Ti;  // curvature of |U_T| along a line
+    p1 += Dm * NmT * dNmT;
+    p2 += Dm * (dNmT * dNmT - NmT * mu * d2T);
+  }
+}
+
 // first and second derivative of the cost along the search direction at step alpha (all lanes get the result)
-__device__ __forceinline__ void leap_ls_eval(const LeapLS& L, double alpha, double g1, double g2, double* d1, double* d2) {
+__device__ __forceinline__ void leap_ls_eval(const LeapLS& L, const LeapWork* W, int lane, double alpha, double g1, double g2, double* d1, double* d2) {
   double p1 = 0, p2 = 0;
   if (L.has_row) {
     const double x = L.rjar + alpha * L.rjv;
@@ -856,27 +1145,10 @@ __device__ __forceinline__ void leap_ls_eval(const LeapLS& L, double alpha, doub
       else { p1 += L.rD * x * L.rjv; p2 += L.rD * L.rjv * L.rjv; }
     } else if (x < 0) { p1 += L.rD * x * L.rjv; p2 += L.rD * L.rjv * L.rjv; }
   }
-  if (L.has_con) {
-    const double mu = L.cmu, f = L.cfr;
-    const double x0 = L.cjar[0] + alpha * L.cjv[0], x1 = L.cjar[1] + alpha * L.cjv[1], x2 = L.cjar[2] + alpha * L.cjv[2];
-    const double U1 = x1 * f, U2 = x2 * f;
-    const double T2 = U1 * U1 + U2 * U2;
-    const double Ti = T2 > B2_MINVAL * B2_MINVAL ? rsqrt(T2) : 0;  // one rsqrt instead of a square root and a division
-    const double N = x0 * mu, T = T2 * Ti;
-    if (N >= mu * T) { /* separating: no force */ }
-    else if (mu * N + T <= 0) {
-      p1 += L.cD[0] * x0 * L.cjv[0] + L.cD[1] * x1 * L.cjv[1] + L.cD[2] * x2 * L.cjv[2];
-      p2 += L.cD[0] * L.cjv[0] * L.cjv[0] + L.cD[1] * L.cjv[1] * L.cjv[1] + L.cD[2] * L.cjv[2] * L.cjv[2];
-    } else {
-      // s = 0.5 Dm (N - mu T)^2 in the scaled space U = S x; chain rule with dU/dalpha = S jv
-      const double Dm = L.cDm, NmT = N - mu * T;
-      const double v0 = mu * L.cjv[0], v1 = f * L.cjv[1], v2 = f * L.cjv[2];
-      const double dT = (U1 * v1 + U2 * v2) * Ti;
-      const double dNmT = v0 - mu * dT;
-      const double d2T = (v1 * v1 + v2 * v2 - dT * dT) * Ti;  // curvature of |U_T| along a line
-      p1 += Dm * NmT * dNmT;
-      p2 += Dm * (dNmT * dNmT - NmT * mu * d2T);
-    }
+  if (L.has_con) leap_ls_contact(L.cjar, L.cjv, L.cD, L.cmu, L.cfr, L.cDm, alpha, p1, p2);
+  if (W->ncon > 32 && lane + 32 < W->ncon) {
+    const int c = lane + 32, r0 = W->nfl + 3 * c;
+    leap_ls_contact(W->ejar + r0, W->ejv + r0, W->eD + r0, W->cmu[c], W->cfri[c], W->cDm[c], alpha, p1, p2);
   }
   lwsum2(p1, p2);
   *d1 = g1 + alpha * g2 + p1;
@@ -903,7 +1175,7 @@ __device__ inline double leap_line_search(const LeapModel* __restrict__ m, const
   const int iters = (int)m->ls_iterations;
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
-    leap_ls_eval(L, alpha, g1, g2, &d1, &d2);
+    leap_ls_eval(L, W, lane, alpha, g1, g2, &d1, &d2);
     if (fabs(d1) < gtol) return alpha;
     if (d1 < 0) lo = alpha; else hi = alpha;
     double next = d2 > 0 ? alpha - d1 / d2 : -1;
@@ -958,7 +1230,8 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
     gn = lwsum(gn);
     if (scale * sqrt(gn) < m->tolerance) { done = true; continue; }
     long long t1 = LPROF_T();
-    leap_newton_direction(m, W, lane);
+    if (W->ncross > 0) { leap_newton_direction_dense(m, W, lane); if (prof && lane == 0) atomicAdd(&g_leap_prof[16], 1ull); }
+    else leap_newton_direction(m, W, lane);
     LPROF_ADD(8, t1); t1 = LPROF_T();
     if (lane < LEAP_NV) W->Mv[lane] = leap_mulM_row(m, W, W->search, lane);
     for (int r = lane; r < nefc; r += 32) W->ejv[r] = r < nfl ? W->esign[r] * W->search[W->edof[r]] : leap_Jrow_dot(W, r - nfl, W->search);
@@ -1098,6 +1371,7 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int n = blockIdx.x * wpb + wib;
   const bool active = n < N;
+  const long long t_block0 = LPROF_T();
   unsigned char* lsm = lsm_all + (size_t)wib * wstride;
   LeapWork* W = reinterpret_cast<LeapWork*>(lsm);
   if (active) {
@@ -1160,6 +1434,13 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
       }
     }
     if (active && lane == 0) reward_N[n] = -(total / H);
+    if (prof) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned long long dt = (unsigned long long)(clock64() - t_block0);
+        atomicMax(&g_leap_prof[21], dt); atomicAdd(&g_leap_prof[22], dt); atomicAdd(&g_leap_prof[23], 1ull);
+      }
+    }
     if (active && cost_NH) {
       __syncwarp();
       for (int i = lane; i < H; i += 32) cost_NH[(size_t)n * H + i] = sC[i];  // one coalesced row per rollout instead of H scalar stores
@@ -1208,10 +1489,10 @@ inline int leap_create(LeapModel** out, const double* consts, size_t n, std::str
 }
 inline void leap_destroy(LeapModel* m) { cudaFree(m); }
 inline void leap_prof_dump() {
-  unsigned long long h[16];
+  unsigned long long h[24];
   if (cudaMemcpyFromSymbol(h, g_leap_prof, sizeof(h)) != cudaSuccess) return;
-  const char* names[15] = {"kinematics", "mass+bias", "collision", "constraints", "smooth", "solver(total)", "integrate", "  update", "  direction", "  linesearch", "newton iters", "  coll:broad", "  coll:narrow", "candidates", "contacts"};
-  for (int i = 0; i < 15; i++) fprintf(stderr, "leap_prof %-14s %llu\n", names[i], h[i]);
+  const char* names[24] = {"kinematics", "mass+bias", "collision", "constraints", "smooth", "solver(total)", "integrate", "  update", "  direction", "  linesearch", "newton iters", "  coll:broad", "  coll:narrow", "candidates", "contacts", "  coll:hand-hand", "dense directions", "hand-hand contacts", "  one finger/palm", "hh past spheres", "hh past prefilter", "slowest block", "sum of blocks", "blocks"};
+  for (int i = 0; i < 24; i++) fprintf(stderr, "leap_prof %-14s %llu\n", names[i], h[i]);
   memset(h, 0, sizeof(h));
   cudaMemcpyToSymbol(g_leap_prof, h, sizeof(h));
 }

@@ -102,6 +102,12 @@ class ShardedPlanner:
         self._check(self.lib.b200mpc_exchange_stamps(self.engine.handle, out))
         return int(out[0]), int(out[1]), int(out[2])
 
+    def exchange_gap_stamps(self) -> tuple[int, int]:
+        """%globaltimer (ns): exit of the last line-up kernel, last instruction of the last in-kernel exchange."""
+        out = (ctypes.c_ulonglong * 2)()
+        self._check(self.lib.b200mpc_exchange_align_stamp(self.engine.handle, out))
+        return int(out[0]), int(out[1])
+
     def set_problem(self, x0: np.ndarray, basis: np.ndarray, cost_params: np.ndarray, want_cost_matrix: bool = True) -> None:
         t = self.torch
         self.H, self.K = basis.shape

@@ -1,10 +1,11 @@
-"""LEAP cube rotation — mirror of judo/tasks/leap_cube.py:14-131, plus the REDUCED collision model the kernel integrates.
+"""LEAP cube rotation — mirror of judo/tasks/leap_cube.py:14-131, plus the collision model the kernel integrates.
 
-Reduced model: the full articulated dynamics of judo/models/xml/leap_cube.xml (free cube + 16 hinge
-joints, implicitfast, elliptic cones, impratio 100, joint limits, friction loss, position servos with kv) with this
-collision geometry: the cube box against every hand collision box (67) and against the 4 fingertips, whose convex
-meshes (tip.obj / thumb_tip.obj — not in git, assets.xml:8,12) are replaced by spheres at the mesh's nominal centre;
-hand-hand pairs are dropped.
+Collision model: the full articulated dynamics of judo/models/xml/leap_cube.xml (free cube + 16 hinge
+joints, implicitfast, elliptic cones, impratio 100, joint limits, friction loss, position servos with kv) and EVERY geom
+pair that survives MuJoCo's static filters (same body, parent-child, the 18 <exclude>s of params_and_default.xml:76-101,
+contype/conaffinity): the cube against the 67 hand boxes and the 4 fingertips (71 pairs) and the 1 621 hand-hand pairs
+(finger-finger, finger-palm, links of one finger).  The one substitution left: the fingertip convex meshes (tip.obj /
+thumb_tip.obj — not in git, assets.xml:8,12) are replaced by spheres at the mesh's nominal centre.
 """
 
 from __future__ import annotations
@@ -31,8 +32,10 @@ TIP_SPHERES = {"if_tip": ([0.0, -0.0325, 0.0145], 0.0125), "mf_tip": ([0.0, -0.0
                "rf_tip": ([0.0, -0.0325, 0.0145], 0.0125), "th_tip": ([0.0, -0.0430, -0.0150], 0.0125)}
 
 
-def reduced_collision_model(table: dict) -> tuple[list[dict], list[list[int]]]:
-    """(geoms, pairs) of the reduced model: tips -> spheres, pairs = cube x every hand geom (in geom order)."""
+def reduced_collision_model(table: dict, hand_hand: bool = True) -> tuple[list[dict], list[list[int]]]:
+    """(geoms, pairs) of the model the kernel integrates: tips -> spheres; pairs = cube x every hand geom (in geom order), then the
+    hand-hand pairs that survive MuJoCo's static filters (``table["pairs"]``, judo_b200/mjcf.py:candidate_pairs) in mj_collision's
+    order: body pair by body pair, geoms of the first body outermost.  ``hand_hand=False`` gives the round-1 model (cube pairs only)."""
     geoms = []
     for g in table["geoms"]:
         g = dict(g)
@@ -42,6 +45,10 @@ def reduced_collision_model(table: dict) -> tuple[list[dict], list[list[int]]]:
         geoms.append(g)
     cube = next(i for i, g in enumerate(geoms) if g["name"] == "cube")
     pairs = [[min(cube, i), max(cube, i)] for i in range(len(geoms)) if i != cube]
+    if hand_hand:
+        hh = [(a, b) for a, b in table["pairs"] if cube not in (a, b)]
+        hh.sort(key=lambda p: (geoms[p[0]]["body"], geoms[p[1]]["body"], p[0], p[1]))
+        pairs += [list(p) for p in hh]
     return geoms, pairs
 
 
@@ -140,6 +147,7 @@ class LeapCubeDown(LeapCube):
 
 # ------------------------------------------------------------------------------------------ constant table
 LEAP_MAXG = 80
+LEAP_MAXHH = 1664  # hand-hand candidate pairs (leap_cube: 1 621)
 
 
 def leap_consts(table: dict) -> np.ndarray:
@@ -198,7 +206,9 @@ def leap_consts(table: dict) -> np.ndarray:
     assert [a["dof"] for a in acts] == list(range(6, 22)) and all(a["gear"] == 1 and not a["forcelimited"] for a in acts)
     v += [a["kp"] for a in acts] + [a["kv"] for a in acts] + [float(a["ctrllimited"]) for a in acts]
     v += [a["ctrlrange"][0] for a in acts] + [a["ctrlrange"][1] for a in acts]
-    geoms, pairs = reduced_collision_model(table)
+    import os
+
+    geoms, pairs = reduced_collision_model(table, hand_hand=os.environ.get("B200MPC_LEAP_NO_HH", "0") != "1")  # (experiment knob: cube pairs only)
     cube_g = next(g for g in geoms if g["name"] == "cube")
     hand = [g for g in geoms if g["name"] != "cube"]
     assert len(hand) <= LEAP_MAXG and cube_g["type"] == "box" and np.allclose(cube_g["pos"], 0) and np.allclose(cube_g["quat"], [1, 0, 0, 0])
@@ -233,7 +243,19 @@ def leap_consts(table: dict) -> np.ndarray:
     v += [float(remap[sites[i]["body"]]) for i in order] + [x for i in order for x in sites[i]["pos"]]
     assert all(d >= 6 for d in fr)  # the cube's free joint has no friction loss (the kernel's per-dof lookup relies on it)
     v += [float(fr.index(d)) if d in fr else -1.0 for d in range(22)]
-    return np.array(v, dtype=np.float64)
+    # hand-hand pairs: raw sliding friction per hand geom (contact mixing = max of the two) and the pair list as g1 * 256 + g2 over the
+    # hand-geom indices, in the order of `pairs` (body-pair major), packed as 16-bit codes
+    v += [max(MINMU_, g["friction"][0]) for g in hand] + [0.0] * pad
+    hidx = {gi: k for k, gi in enumerate(i for i, g in enumerate(geoms) if g["name"] != "cube")}
+    cube_i = next(i for i, g in enumerate(geoms) if g["name"] == "cube")
+    hh = [(a, b) for a, b in pairs if cube_i not in (a, b)]
+    assert len(hh) <= LEAP_MAXHH
+    for a, b in hh:  # same-body and static-static pairs never reach the kernel
+        assert geoms[a]["body"] != geoms[b]["body"] and (geoms[a]["body"] in remap or geoms[b]["body"] in remap)
+    v += [float(len(hh))]
+    codes = np.zeros(LEAP_MAXHH, dtype=np.uint16)  # 16-bit codes, four to a double (raw bits: never touched as floating point)
+    codes[:len(hh)] = [hidx[a] * 256 + hidx[b] for a, b in hh]
+    return np.concatenate([np.array(v, dtype=np.float64), codes.view(np.float64)])
 
 
 MINMU_ = 1e-5

@@ -461,6 +461,18 @@ static int collide_cylinder_cylinder(const double* p1, const double* m1, const d
   return 1;
 }
 
+/* Sphere vs sphere (mjc_SphereSphere semantics: normal from geom1 to geom2, position midway between the surfaces). */
+static int collide_sphere_sphere(const double* p1, double r1, const double* p2, double r2, double margin, RawContact* out) {
+  double dv[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  double dn = norm3(dv);
+  if (dn - r1 - r2 >= margin) return 0;
+  if (dn < MINVAL) { out->normal[0] = 1; out->normal[1] = out->normal[2] = 0; }
+  else for (int k = 0; k < 3; k++) out->normal[k] = dv[k] / dn;
+  out->dist = dn - r1 - r2;
+  for (int k = 0; k < 3; k++) out->pos[k] = p1[k] + out->normal[k] * (r1 + 0.5 * out->dist);
+  return 1;
+}
+
 /* Sphere vs box (mjc_SphereBox semantics: closest point on the box, inside case pushes out the nearest face). */
 static int collide_sphere_box(const double* ps, double rs, const double* pb, const double* mb, const double* sb,
                               double margin, RawContact* out) {
@@ -844,6 +856,8 @@ static void collision(const mjcModel* m, mjcData* d) {
       n = collide_cylinder_cylinder(d->geom_xpos[g1], d->geom_xmat[g1], m->geom_size[g1], d->geom_xpos[g2], d->geom_xmat[g2], m->geom_size[g2], margin, raw);
     else if (t1 == MJC_GEOM_BOX && t2 == MJC_GEOM_BOX)
       n = collide_box_box(d->geom_xpos[g1], d->geom_xmat[g1], m->geom_size[g1], d->geom_xpos[g2], d->geom_xmat[g2], m->geom_size[g2], margin, raw, 8);
+    else if (t1 == MJC_GEOM_SPHERE && t2 == MJC_GEOM_SPHERE)
+      n = collide_sphere_sphere(d->geom_xpos[g1], m->geom_size[g1][0], d->geom_xpos[g2], m->geom_size[g2][0], margin, raw);
     else if (t1 == MJC_GEOM_SPHERE && t2 == MJC_GEOM_BOX)
       n = collide_sphere_box(d->geom_xpos[g1], m->geom_size[g1][0], d->geom_xpos[g2], d->geom_xmat[g2], m->geom_size[g2], margin, raw);
     else
@@ -1399,6 +1413,16 @@ int mjc_rollout(const mjcModel* m, const double* x0, int x0_batched, const doubl
     free(d); free(s);
   }
   return fail;
+}
+
+/* Diagnostics for tests / studies: world poses of every geom at qpos (xpos: ngeom x 3, xmat: ngeom x 9). */
+void mjc_geom_poses(const mjcModel* m, const double* qpos, double* xpos, double* xmat) {
+  mjcData* d = (mjcData*)calloc(1, sizeof(mjcData));
+  memcpy(d->qpos, qpos, sizeof(double) * m->nq);
+  kinematics(m, d);
+  memcpy(xpos, d->geom_xpos, sizeof(double) * 3 * m->ngeom);
+  memcpy(xmat, d->geom_xmat, sizeof(double) * 9 * m->ngeom);
+  free(d);
 }
 
 int mjc_forward_debug(const mjcModel* m, const double* qpos, const double* qvel, const double* ctrl, double* M,

@@ -66,6 +66,9 @@ int mjc_forward_debug(const mjcModel* m, const double* qpos, const double* qvel,
                       double* qacc_smooth, double* qacc, double* qfrc_constraint, int* ncon_out,
                       double* contact_dist, double* contact_frame, double* contact_pos, int* solver_iter);
 
+/* World poses of every geom at qpos (xpos: ngeom x 3, xmat: ngeom x 9 row-major); for tests and studies. */
+void mjc_geom_poses(const mjcModel* m, const double* qpos, double* xpos, double* xmat);
+
 /* Signed distance between two boxes (centre p, 3x3 row-major frame m, half-sizes s), clipped above at cutoff: the routine
  * behind the restated mjSENS_GEOMDIST sensors; exported for tests. */
 double mjc_box_box_distance(const double* p1, const double* m1, const double* s1, const double* p2, const double* m2,

@@ -8,11 +8,11 @@ import numpy as np
 from oracle.mjc import OracleModel, load_table
 
 
-def _leap():
+def _leap(hand_hand=True):
     from judo_b200.tasks.leap_cube import QPOS_HOME, reduced_collision_model
 
     tb = load_table("leap_cube")
-    geoms, pairs = reduced_collision_model(tb)
+    geoms, pairs = reduced_collision_model(tb, hand_hand=hand_hand)
     return OracleModel(tb, pairs=pairs, geoms=geoms), tb, QPOS_HOME
 
 
@@ -89,7 +89,7 @@ def test_cube_rests_on_the_hand_in_static_equilibrium():
 
 def test_joint_limit_and_clamps():
     tb = load_table("leap_cube")
-    om, _, home = _leap()
+    om, _, home = _leap(hand_hand=False)  # every joint driven to its upper limit: without hand-hand contacts, so that only the limits stop them
     lo = np.array([a["ctrlrange"][0] for a in tb["actuators"]])
     hi = np.array([a["ctrlrange"][1] for a in tb["actuators"]])
     q = home.copy()
@@ -101,6 +101,9 @@ def test_joint_limit_and_clamps():
     s = om.rollout(x0, edge)[0]
     jr = np.array([j["range"] for j in tb["joints"][1:]])
     assert np.all(s[0, -1, 7:23] < jr[:, 1] + 0.02) and np.all(s[0, -1, 7:23] > lo - 0.3)   # soft limits hold the joints
+    # the same command WITH the hand-hand pairs: the fingers run into each other and into the palm long before the limits
+    s2 = _leap()[0].rollout(x0, edge)[0]
+    assert np.abs(s2[0, -1, 7:23] - s[0, -1, 7:23]).max() > 0.2 and np.all(np.isfinite(s2))
 
 
 # ------------------------------------------------------------------ fr3_pick (reduced box geometry)

@@ -65,3 +65,56 @@ def test_leap_fused_cost_kernel_on_emulator_matches_oracle(sim, leap):
     np.testing.assert_allclose(trace, om.rollout(x0, controls)[1][..., 16:31], rtol=0, atol=1e-10)  # trace capture: the 5 framepos sensors
     ref = op.leap_cube_reward(om.rollout(x0, controls)[0], params[2:6], 100.0, 0.1)
     np.testing.assert_allclose(rew, ref, rtol=0, atol=1e-10)
+
+
+def test_leap_hand_hand_contacts_on_emulator_match_oracle(sim, leap):
+    """Fingers driven into each other and into the palm (targets drawn over the whole actuator range): finger-finger contacts take the
+    dense Newton direction, contacts inside one finger / against the palm stay on the arrow path.  The pair list is MuJoCo's
+    (params_and_default.xml:76-101 excludes applied); dropping the hand-hand pairs must change these rollouts."""
+    consts, om = leap
+    tb = load_table("leap_cube")
+    geoms0, pairs0 = reduced_collision_model(tb, hand_hand=False)
+    om0 = OracleModel(tb, pairs=pairs0, geoms=geoms0)
+    lo = np.array([a["ctrlrange"][0] for a in tb["actuators"]])
+    hi = np.array([a["ctrlrange"][1] for a in tb["actuators"]])
+    rng = np.random.default_rng(5)
+    N, H = 48, 30
+    x0 = np.concatenate([QPOS_HOME, np.zeros(22)])
+    x0[2] = 0.07
+    u = np.ascontiguousarray(np.repeat(lo + (hi - lo) * rng.random((N, 1, 16)), H, axis=1))
+    s_ref, e_ref = om.rollout(x0, u)
+    matter = np.where(np.abs(s_ref - om0.rollout(x0, u)[0]).max(axis=(1, 2)) > 1e-6)[0]
+    assert matter.size >= 6
+    pick = np.concatenate([matter[:8], [0, 1]])
+    u, s_ref, e_ref = np.ascontiguousarray(u[pick]), s_ref[pick], e_ref[pick]
+    sim.sim_leap_set_prof(1)
+    outs = []
+    for reverse, wpb in ((0, 2), (1, 3)):
+        s, e = np.zeros_like(s_ref), np.zeros_like(e_ref)
+        sim.sim_leap_rollout(P(consts), P(x0), 0, P(u), len(pick), H, P(s), P(e), wpb, 3, reverse)
+        prof = (ctypes.c_ulonglong * 20)()
+        sim.sim_leap_read_prof(prof)
+        assert prof[16] > 0 and prof[17] > prof[18] > 0  # dense directions ran; finger-finger AND one-finger / palm contacts occurred
+        np.testing.assert_allclose(s, s_ref, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(e, e_ref, rtol=0, atol=1e-9)
+        outs.append(s)
+    sim.sim_leap_set_prof(0)
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_leap_step_with_more_than_32_contacts_on_emulator(sim, leap):
+    """Rollout 491 of the C4 bench problem (bench.problem, seed 42) reaches 31 and 36 simultaneous contacts at steps 35 / 39 once the
+    hand-hand pairs are in: the line search's low lanes own a second contact there."""
+    import bench
+
+    consts, om = leap
+    w = bench.WORKLOADS["leap_cube_mppi"]
+    _, _, x0, knots, basis, _, _ = bench.problem(w, w["n_rollouts"])
+    u = np.ascontiguousarray(np.einsum("hk,nkj->nhj", basis, knots[[491, 0]]))
+    s_ref, e_ref = om.rollout(x0, u)
+    fwd = om.forward(s_ref[0, 38, :23], s_ref[0, 38, 23:], u[0, 39])
+    assert 32 < fwd["ncon"] <= 40
+    s, e = np.zeros_like(s_ref), np.zeros_like(e_ref)
+    sim.sim_leap_rollout(P(consts), P(x0), 0, P(u), 2, w["H"], P(s), P(e), 2, 3, 1)
+    np.testing.assert_allclose(s, s_ref, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(e, e_ref, rtol=0, atol=1e-9)

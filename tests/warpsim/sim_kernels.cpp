@@ -6,6 +6,11 @@ using namespace b2;
 
 
 extern "C" int sim_leap_nconsts() { return (int)(sizeof(LeapModel) / sizeof(double)); }
+// the kernel's optional counters (B200MPC_LEAP_PROF on the GPU): switch them on for the next launches / read and clear them
+static int g_sim_leap_prof = 0;
+extern "C" void sim_leap_set_prof(int on) { g_sim_leap_prof = on ? 1 : 0; }
+extern "C" void sim_leap_read_prof(unsigned long long* out20) { for (int i = 0; i < 20; i++) { out20[i] = g_leap_prof[i]; g_leap_prof[i] = 0; }
+  for (int i = 20; i < 24; i++) g_leap_prof[i] = 0; }
 
 // contract A through leap_rollout_kernel<false>; wpb warps per block, sync_mode as B200MPC_LEAP_SYNC, reverse = lane order
 extern "C" int sim_leap_rollout(const double* consts, const double* x0, int batched, const double* controls, int N, int H, double* states,
@@ -14,7 +19,7 @@ extern "C" int sim_leap_rollout(const double* consts, const double* x0, int batc
   const size_t ws = leap_wstride(0, 0, H);
   wsim::set_reverse(reverse != 0);
   wsim::launch((N + wpb - 1) / wpb, 32 * wpb, wpb * ws, [&] {
-    leap_rollout_kernel<false>(m, x0, batched, controls, N, H, 0, nullptr, nullptr, states, sensors, nullptr, nullptr, (int)ws, sync_mode << 8,
+    leap_rollout_kernel<false>(m, x0, batched, controls, N, H, 0, nullptr, nullptr, states, sensors, nullptr, nullptr, (int)ws, (sync_mode << 8) | g_sim_leap_prof,
                                SampleSpec{}, 0);
   });
   return 0;
@@ -27,7 +32,7 @@ extern "C" int sim_leap_plan_costs(const double* consts, const double* x0, const
   const size_t ws = leap_wstride(1, K, H);
   wsim::set_reverse(reverse != 0);
   wsim::launch((N + wpb - 1) / wpb, 32 * wpb, wpb * ws, [&] {
-    leap_rollout_kernel<true>(m, x0, 0, knots, N, H, K, basis, params, nullptr, nullptr, cost_NH, reward_N, (int)ws, sync_mode << 8, SampleSpec{}, 0, trace_out);
+    leap_rollout_kernel<true>(m, x0, 0, knots, N, H, K, basis, params, nullptr, nullptr, cost_NH, reward_N, (int)ws, (sync_mode << 8) | g_sim_leap_prof, SampleSpec{}, 0, trace_out);
   });
   return 0;
 }

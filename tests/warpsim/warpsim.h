@@ -163,6 +163,8 @@ template <class T>
 inline T __ldg(const T* p) { return *p; }
 template <class T, class U>
 inline T atomicAdd(T* p, U v) { T old = *p; *p = old + (T)v; return old; }
+template <class T, class U>
+inline T atomicMax(T* p, U v) { T old = *p; if ((T)v > old) *p = (T)v; return old; }
 inline unsigned atomicInc(unsigned* p, unsigned lim) { unsigned old = *p; *p = old >= lim ? 0 : old + 1; return old; }
 inline long long clock64() { return 0; }
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
