@@ -246,6 +246,10 @@ int b200mpc_topk_combine_dev(b200mpc_handle* h, const double* d_partials, int n_
  * knots — the collective of SURVEY.md §8e happens inside the rollout kernel (no NCCL call, no extra launch on the data path). */
 int b200mpc_exchange_create(b200mpc_handle* h, int world_size, int rank, unsigned char* ipc_handle_out_64B);
 int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all_handles_world_x_64B);
+/* The same wiring for peers inside ONE process (handles sharing a GPU, or GPUs with peer access enabled): after exchange_create on every
+ * handle, pass each one the world_size buffer pointers obtained with b200mpc_exchange_buffer. */
+int b200mpc_exchange_buffer(b200mpc_handle* h, void** buffer_out);
+int b200mpc_exchange_open_local(b200mpc_handle* h, void* const* peer_buffers_world);
 /* Measurement helpers for the scaling bench.  align: a one-warp kernel on `stream` that raises this rank's align flag in every peer buffer
  * and waits for all of them (lines the GPUs up between the L2 flush and the timed step, moving no data).  stamps: %globaltimer (ns) of
  * the last finalize=2 step on this rank: [0] kernel entry, [1] partial published to the peers, [2] all peers' partials seen. */

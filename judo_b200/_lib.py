@@ -51,6 +51,8 @@ SIGNATURES = {
     "b200mpc_exchange_create": (_i, [_vp, _i, _i, _vp]),
     "b200mpc_exchange_open": (_i, [_vp, _vp]),
     "b200mpc_exchange_align_dev": (_i, [_vp, _vp]),
+    "b200mpc_exchange_buffer": (_i, [_vp, _vp]),
+    "b200mpc_exchange_open_local": (_i, [_vp, _vp]),
     "b200mpc_exchange_stamps": (_i, [_vp, _vp]),
     "b200mpc_exchange_align_stamp": (_i, [_vp, _vp]),
     "b200mpc_launch_count": (ctypes.c_longlong, [_vp]),

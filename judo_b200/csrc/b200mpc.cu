@@ -54,7 +54,7 @@ struct b200mpc_handle {
   int zero_copy = 2;           // plan_step: bit0 = kernel READS the pinned staging buffer, bit1 = kernel WRITES results to pinned memory
   bool zero_copy_now = false;  // set for the duration of a zero-copy plan_step
   // peer exchange (multi-GPU fused MPPI): local buffer + peers' buffers opened through CUDA IPC
-  void* xchg = nullptr; void* xchg_peer[8] = {nullptr}; int xchg_world = 0, xchg_rank = 0; unsigned long long xchg_epoch = 0, xchg_align_epoch = 0;
+  void* xchg = nullptr; void* xchg_peer[8] = {nullptr}; int xchg_world = 0, xchg_rank = 0; unsigned long long xchg_epoch = 0, xchg_align_epoch = 0; bool xchg_local = false;
   unsigned long long* d_stamps = nullptr;  // %globaltimer stamps of the last finalize=2 step (b200mpc_exchange_stamps)
   double t_stage = 0, t_launch = 0, t_sync = 0, t_out = 0, t_spec = 0; long long t_calls = 0; bool timing = false;  // B200MPC_TIMING=1
   // b200mpc_controller_step: normals of the current block, captured positions (N, H, nq) for the in-kernel elite traces, and where the
@@ -147,7 +147,7 @@ extern "C" void b200mpc_destroy(b200mpc_handle* h) {
             h->t_stage / h->t_calls, h->t_launch / h->t_calls, h->t_sync / h->t_calls, h->t_out / h->t_calls, h->t_spec / h->t_calls);
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (int g = 0; g < 8; g++) if (h->xchg_peer[g] && h->xchg_peer[g] != h->xchg) cudaIpcCloseMemHandle(h->xchg_peer[g]);
+  for (int g = 0; g < 8; g++) if (h->xchg_peer[g] && h->xchg_peer[g] != h->xchg && !h->xchg_local) cudaIpcCloseMemHandle(h->xchg_peer[g]);
   cudaFree(h->xchg); cudaFree(h->d_stamps);
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work); cudaFree(h->d_trace); cudaFree(h->d_traceq);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
@@ -167,13 +167,13 @@ extern "C" int b200mpc_exchange_create(b200mpc_handle* h, int world, int rank, u
   // a second create on the same handle starts from scratch: mappings of the previous peers are closed, flags and slots are cleared
   // (stale epoch flags >= the restarted epoch would let a step combine partials that were never written)
   for (int g = 0; g < 8; g++) {
-    if (h->xchg_peer[g] && h->xchg_peer[g] != h->xchg) cudaIpcCloseMemHandle(h->xchg_peer[g]);
+    if (h->xchg_peer[g] && h->xchg_peer[g] != h->xchg && !h->xchg_local) cudaIpcCloseMemHandle(h->xchg_peer[g]);
     h->xchg_peer[g] = nullptr;
   }
   if (!h->xchg) CK(cudaMalloc(&h->xchg, EP_XCHG_BYTES));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaMemset(h->xchg, 0, EP_XCHG_BYTES));
-  h->xchg_world = world; h->xchg_rank = rank; h->xchg_epoch = 0; h->xchg_align_epoch = 0;
+  h->xchg_world = world; h->xchg_rank = rank; h->xchg_epoch = 0; h->xchg_align_epoch = 0; h->xchg_local = false;
   if (!h->d_stamps) { CK(cudaMalloc(&h->d_stamps, 64)); CK(cudaMemset(h->d_stamps, 0, 64)); }
   cudaIpcMemHandle_t ih;
   CK(cudaIpcGetMemHandle(&ih, h->xchg));
@@ -191,9 +191,28 @@ extern "C" int b200mpc_exchange_open(b200mpc_handle* h, const unsigned char* all
     memcpy(&ih, all_handles + 64 * g, 64);
     cudaError_t e = cudaIpcOpenMemHandle(&h->xchg_peer[g], ih, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) {  // leave no half-open exchange behind: callers then stay on the all_gather path
-      for (int q = 0; q < 8; q++) { if (h->xchg_peer[q] && h->xchg_peer[q] != h->xchg) cudaIpcCloseMemHandle(h->xchg_peer[q]); h->xchg_peer[q] = nullptr; }
+      for (int q = 0; q < 8; q++) { if (h->xchg_peer[q] && h->xchg_peer[q] != h->xchg && !h->xchg_local) cudaIpcCloseMemHandle(h->xchg_peer[q]); h->xchg_peer[q] = nullptr; }
       return fail(h, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
     }
+  }
+  return 0;
+}
+
+// Peers that live in THIS process (handles on the same GPU, or on GPUs with peer access enabled): their exchange buffers are plain device
+// pointers, no IPC handle can or needs to be opened.
+extern "C" int b200mpc_exchange_buffer(b200mpc_handle* h, void** out) {
+  if (!h || !out) return 1;
+  if (!h->xchg) return fail(h, "peer exchange not set up (exchange_create)");
+  *out = h->xchg;
+  return 0;
+}
+extern "C" int b200mpc_exchange_open_local(b200mpc_handle* h, void* const* peer_buffers /* world pointers */) {
+  if (!h || !h->xchg || !peer_buffers) return 1;
+  for (int g = 0; g < 8; g++) { if (h->xchg_peer[g] && h->xchg_peer[g] != h->xchg && !h->xchg_local) cudaIpcCloseMemHandle(h->xchg_peer[g]); h->xchg_peer[g] = nullptr; }
+  h->xchg_local = true;
+  for (int g = 0; g < h->xchg_world; g++) {
+    if (g != h->xchg_rank && !peer_buffers[g]) return fail(h, "exchange: NULL peer buffer");
+    h->xchg_peer[g] = g == h->xchg_rank ? h->xchg : peer_buffers[g];
   }
   return 0;
 }
@@ -570,7 +589,8 @@ extern "C" int b200mpc_plan_step_sampled(b200mpc_handle* h, const double* x0, co
 }
 
 // ------------------------------------------------------------------ reductions (device-pointer API)
-static int n_partials_for(int N) { return std::max(1, std::min(64, (N + 511) / 512)); }
+// (64 rollouts per block: at 512 the two blocks of the C4 update walked 128 dependent L2 loads per thread — 65 us for a 1 K x 64 reduction)
+static int n_partials_for(int N) { return std::max(1, std::min(128, (N + 63) / 64)); }
 
 extern "C" int b200mpc_mppi_partial_dev(b200mpc_handle* h, const double* d_knots, const double* d_rewards, int N, int KNU,
                                         double temperature, double* d_partial, void* stream) {

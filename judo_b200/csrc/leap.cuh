@@ -103,6 +103,10 @@ __device__ __forceinline__ LeapColLists* leap_col_lists(LeapWork* W) { return re
 // optional phase timers (clock64 deltas accumulated by lane 0): kin, mass+bias, collision, constraints, smooth, solver, integrate,
 // and inside the solver: update, direction (H + Cholesky + solve), line search, #newton iterations
 __device__ unsigned long long g_leap_prof[24];  // [16..18]: dense Newton directions, hand-hand contacts, of those inside one finger / against the palm; [19..20]: hand-hand pairs past the bounding spheres / past the pre-filter; [21..23]: slowest block (cycles), sum over blocks, blocks
+// per-block counters (prof mode): [0] block cycles, [1] lock-step Newton iterations the block walked, [2] iterations its warps were active in,
+// [3] dense directions, [4] contacts (sum over warps and steps), [5] cube narrow-phase rounds, [6] hand-hand narrow-phase rounds, [7] launches
+__device__ unsigned long long g_leap_blk[160][8];
+#define LPROF_BLK(slot, v) do { if (prof && lane == 0 && blockIdx.x < 160) atomicAdd(&g_leap_blk[blockIdx.x][slot], (unsigned long long)(v)); } while (0)
 #define LPROF_T() (prof ? clock64() : 0)
 #define LPROF_ADD(slot, t0) do { if (prof && lane == 0) atomicAdd(&g_leap_prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
 
@@ -561,6 +565,7 @@ __device__ inline void leap_collision(const LeapModel* __restrict__ m, LeapWork*
     for (int c = 0; c < nkept; c++) { if (W->cbA[c] != 0 && W->cbB[c] != 0) { nh2++; if (W->cfa[c] == -2) none++; } }
     atomicAdd(&g_leap_prof[17], (unsigned long long)nh2); atomicAdd(&g_leap_prof[18], (unsigned long long)none);
     atomicAdd(&g_leap_prof[19], (unsigned long long)nh); atomicAdd(&g_leap_prof[20], (unsigned long long)nf);
+    LPROF_BLK(4, nkept); LPROF_BLK(5, (ncand + LCOL_LANES - 1) / LCOL_LANES); LPROF_BLK(6, (nf + LCOL_LANES - 1) / LCOL_LANES);
   }
 }
 
@@ -817,6 +822,163 @@ __device__ __noinline__ void leap_constraint_update(const LeapModel* __restrict_
 #define TRI4_J 0x1a211040ull         /* 0,0,1,0,1,2,0,1,2,3 */
 __device__ __forceinline__ int tri_get(unsigned long long tab, int e) { return (int)((tab >> (3 * e)) & 7ull); }
 
+// Tail shared by the two direction routines: with X = L_F^-1 B in Hcf (16 x 6, rows = finger dofs) and y = L_F^-1 (-grad_F) in yf,
+// Schur complement of the cube block, its Cholesky and both substitutions in one lane -> xc = search[0..5].
+__device__ __forceinline__ void leap_schur_cube(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  // Schur complement S = C - sum_f X_f^T X_f (lanes 0..20) and reduced right-hand side (lanes 21..26)
+  if (lane < 21) {
+    const int i = tri_get(TRI6_I, lane), j = tri_get(TRI6_J, lane);
+    double sacc = W->Hcc[i][j];
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) sacc -= W->Hcf[f][r][i] * W->Hcf[f][r][j];
+    W->Hcc[i][j] = sacc;
+  } else if (lane < 27) {
+    const int cc = lane - 21;
+    double sacc = -W->grad[cc];
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) sacc -= W->Hcf[f][r][cc] * W->yf[f][r];
+    W->xc[cc] = sacc;
+  }
+  __syncwarp();
+  // cube block: Cholesky + both substitutions in one lane (6x6)
+  if (lane == 0) {
+    double L[6][6], x[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        double sacc = W->Hcc[i][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
+        if (i == j) { if (sacc < B2_MINVAL) sacc = B2_MINVAL; L[i][i] = rsqrt(sacc); } else L[i][j] = sacc * L[j][j];
+      }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { double sacc = W->xc[i];
+#pragma unroll
+      for (int k = 0; k < i; k++) sacc -= L[i][k] * x[k];
+      x[i] = sacc * L[i][i]; }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) { double sacc = x[i];
+#pragma unroll
+      for (int k = i + 1; k < 6; k++) sacc -= L[k][i] * x[k];
+      x[i] = sacc * L[i][i]; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { W->xc[i] = x[i]; W->search[i] = x[i]; }
+  }
+  __syncwarp();
+}
+
+// Finger part of the Newton direction when two DIFFERENT fingers touch each other (~0.8 % of the Newton iterations of the C4 bench
+// scenario, but the rollouts they sit in are the slowest of their blocks): the finger blocks couple, so the 16 finger dofs are
+// factorised as ONE dense block by the warp (lane per row, left-looking Cholesky) instead of four 4 x 4 blocks; cube block, couplings
+// and the assembly of everything but the cross-finger terms stay those of the arrow form.  The 16 x 16 matrix (packed lower triangle)
+// aliases the kinematics arrays, which are dead once the constraint rows are built.
+static_assert(16 * 17 / 2 <= LB * 18, "packed finger Hessian must fit into xpos .. xaxis");
+static_assert(offsetof(LeapWork, Mc) == offsetof(LeapWork, xpos) + sizeof(double) * LB * 18, "xpos .. xaxis must be contiguous");
+#define LF(i, j) Fp[(i) * ((i) + 1) / 2 + (j)] /* lower triangle, row-packed */
+__device__ __noinline__ void leap_coupled_fingers(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
+  const int nfl = W->nfl, ncon = W->ncon;
+  double* Fp = &W->xpos[0][0];
+  double* dinv = W->tmp;
+  double* Bm = &W->Hcf[0][0][0];  // (16, 6): row 4 f + r
+  double* yv = &W->yf[0][0];      // (16)
+  // block diagonal from the assembled finger blocks, zeros elsewhere
+  for (int e = lane; e < 136; e += 32) {
+    int i = 0, j = e;
+    while (j > i) { j -= i + 1; i++; }
+    Fp[e] = (i >> 2) == (j >> 2) ? W->Hff[i >> 2][i & 3][j & 3] : 0.0;
+  }
+  __syncwarp();
+  // cross-finger contacts: first finger's own block (lanes 0..9) and the coupling block (lanes 10..25); the second finger's own block
+  // was accumulated by the arrow assembly
+  for (int c = 0; c < ncon; c++) {
+    const int fa = W->cfa[c];
+    if (fa < 0) continue;
+    const int st = W->estate[nfl + 3 * c];
+    if (st == LST_SATISFIED) continue;
+    const int fb = W->cfinger[c];
+    double Wm[9];
+    if (st == LST_QUADRATIC) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) Wm[k] = 0;
+      Wm[0] = W->eD[nfl + 3 * c]; Wm[4] = W->eD[nfl + 3 * c + 1]; Wm[8] = W->eD[nfl + 3 * c + 2];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; k++) Wm[k] = leap_cHc(W, c)[k];
+    }
+    const double(*J)[10] = &W->Jc[3 * c];
+    int si = -1, sj = 0, row = 0, col = 0;
+    if (lane < 10) { si = tri_get(TRI4_I, lane); sj = tri_get(TRI4_J, lane); row = 4 * fa + si; col = 4 * fa + sj; }
+    else if (lane < 26) { const int r = (lane - 10) >> 2, q = (lane - 10) & 3; si = 6 + r; sj = q; row = 4 * fb + r; col = 4 * fa + q; }
+    if (si >= 0) {
+      double h = 0;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) h += Wm[3 * a + b] * J[a][si] * J[b][sj];
+      if (row >= col) LF(row, col) += h; else LF(col, row) += h;
+    }
+    __syncwarp();
+  }
+  // left-looking Cholesky, lane i < 16 owns row i; dinv[k] = 1 / L_kk
+  for (int k = 0; k < 16; k++) {
+    double sres = 0;
+    if (lane >= k && lane < 16) {
+      const double* ri = &LF(lane, 0);
+      const double* rk = &LF(k, 0);
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      int j = 0;
+      for (; j + 3 < k; j += 4) { s0 += ri[j] * rk[j]; s1 += ri[j + 1] * rk[j + 1]; s2 += ri[j + 2] * rk[j + 2]; s3 += ri[j + 3] * rk[j + 3]; }
+      for (; j < k; j++) s0 += ri[j] * rk[j];
+      sres = ri[k] - ((s0 + s1) + (s2 + s3));
+    }
+    double d = __shfl_sync(FULL, sres, k);
+    if (d < B2_MINVAL) d = B2_MINVAL;
+    const double rs = rsqrt(d);
+    if (lane == k) dinv[k] = rs;
+    else if (lane > k && lane < 16) LF(lane, k) = sres * rs;
+    __syncwarp();
+  }
+  // y = L^-1 (-grad_F): one shuffle per column
+  const double di = lane < 16 ? dinv[lane] : 0.0;
+  double x = lane < 16 ? -W->grad[6 + lane] : 0.0;
+  for (int k = 0; k < 16; k++) {
+    const double yk = __shfl_sync(FULL, x * di, k);
+    if (lane == k) x = yk;
+    else if (lane > k && lane < 16) x -= LF(lane, k) * yk;
+  }
+  if (lane < 16) yv[lane] = x;
+  // X = L^-1 B in place, one cube column per lane
+  if (lane < 6) {
+    for (int i = 0; i < 16; i++) {
+      double sacc = Bm[6 * i + lane];
+      for (int k = 0; k < i; k++) sacc -= LF(i, k) * Bm[6 * k + lane];
+      Bm[6 * i + lane] = sacc * dinv[i];
+    }
+  }
+  __syncwarp();
+  leap_schur_cube(m, W, lane);
+  // fingers: x_F = L^-T (y - X x_C)
+  x = 0;
+  if (lane < 16) {
+    x = yv[lane];
+#pragma unroll
+    for (int cc = 0; cc < 6; cc++) x -= Bm[6 * lane + cc] * W->xc[cc];
+  }
+  for (int k = 15; k >= 0; k--) {
+    const double xk = __shfl_sync(FULL, x * di, k);
+    if (lane == k) x = xk;
+    else if (lane < k) x -= LF(k, lane) * xk;
+  }
+  if (lane < 16) W->search[6 + lane] = x;
+  __syncwarp();
+}
+#undef LF
+
 // Newton direction: search = -H^-1 grad, H = M + sum_rows D J^T J (+ elliptic cone blocks).
 // Contacts only involve the cube, so H is an ARROW matrix: cube block C (6x6), four independent finger blocks F_f (4x4)
 // and couplings B_f (4x6).  Eliminating the fingers first:  L_f = chol(F_f),  X_f = L_f^-1 B_f,
@@ -882,6 +1044,7 @@ __device__ inline void leap_newton_direction(const LeapModel* __restrict__ m, Le
     }
   }
   __syncwarp();  // (every Hessian entry is accumulated by ONE lane across all contacts: no barrier is needed inside the loop)
+  if (W->ncross > 0) { leap_coupled_fingers(m, W, lane); return; }
   // ---- factorise the finger blocks (lane f), keep 1/L_kk on the diagonal slot for the substitutions
   if (lane < 4) {
     const int f = lane;
@@ -922,51 +1085,7 @@ __device__ inline void leap_newton_direction(const LeapModel* __restrict__ m, Le
     for (int i = 0; i < 4; i++) W->Hcf[f][i][cc] = x[i];
   }
   __syncwarp();
-  // Schur complement S = C - sum_f X_f^T X_f (lanes 0..20) and reduced right-hand side (lanes 21..26)
-  if (lane < 21) {
-    const int i = tri_get(TRI6_I, lane), j = tri_get(TRI6_J, lane);
-    double sacc = W->Hcc[i][j];
-#pragma unroll
-    for (int f = 0; f < 4; f++)
-#pragma unroll
-      for (int r = 0; r < 4; r++) sacc -= W->Hcf[f][r][i] * W->Hcf[f][r][j];
-    W->Hcc[i][j] = sacc;
-  } else if (lane < 27) {
-    const int cc = lane - 21;
-    double sacc = -W->grad[cc];
-#pragma unroll
-    for (int f = 0; f < 4; f++)
-#pragma unroll
-      for (int r = 0; r < 4; r++) sacc -= W->Hcf[f][r][cc] * W->yf[f][r];
-    W->xc[cc] = sacc;
-  }
-  __syncwarp();
-  // cube block: Cholesky + both substitutions in one lane (6x6)
-  if (lane == 0) {
-    double L[6][6], x[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++)
-#pragma unroll
-      for (int j = 0; j <= i; j++) {
-        double sacc = W->Hcc[i][j];
-#pragma unroll
-        for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
-        if (i == j) { if (sacc < B2_MINVAL) sacc = B2_MINVAL; L[i][i] = rsqrt(sacc); } else L[i][j] = sacc * L[j][j];
-      }
-#pragma unroll
-    for (int i = 0; i < 6; i++) { double sacc = W->xc[i];
-#pragma unroll
-      for (int k = 0; k < i; k++) sacc -= L[i][k] * x[k];
-      x[i] = sacc * L[i][i]; }
-#pragma unroll
-    for (int i = 5; i >= 0; i--) { double sacc = x[i];
-#pragma unroll
-      for (int k = i + 1; k < 6; k++) sacc -= L[k][i] * x[k];
-      x[i] = sacc * L[i][i]; }
-#pragma unroll
-    for (int i = 0; i < 6; i++) { W->xc[i] = x[i]; W->search[i] = x[i]; }
-  }
-  __syncwarp();
+  leap_schur_cube(m, W, lane);
   // fingers: x_f = L_f^-T (y_f - X_f x_C)
   if (lane < 4) {
     const int f = lane;
@@ -986,107 +1105,6 @@ __device__ inline void leap_newton_direction(const LeapModel* __restrict__ m, Le
   }
   __syncwarp();
 }
-
-// Newton direction when two DIFFERENT fingers touch each other (rare: ~0.1 % of the rollout steps of the C4 bench scenario): the finger
-// blocks couple, the arrow structure is gone, so the Hessian is assembled dense (22 x 22, lower triangle) and factorised by the
-// warp, lane per row.  The (packed) matrix aliases the kinematics arrays, which are dead once the constraint rows are built.
-static_assert(LEAP_NV * (LEAP_NV + 1) / 2 <= LB * 18, "packed dense Hessian must fit into xpos .. xaxis");
-static_assert(offsetof(LeapWork, Mc) == offsetof(LeapWork, xpos) + sizeof(double) * LB * 18, "xpos .. xaxis must be contiguous");
-#define LH(i, j) Hp[(i) * ((i) + 1) / 2 + (j)] /* lower triangle, row-packed */
-__device__ __noinline__ void leap_newton_direction_dense(const LeapModel* __restrict__ m, LeapWork* W, int lane) {
-  const int nfl = W->nfl, ncon = W->ncon;
-  double* Hp = &W->xpos[0][0];
-  double* dinv = W->tmp;
-  for (int e = lane; e < LEAP_NV * (LEAP_NV + 1) / 2; e += 32) Hp[e] = 0.0;
-  // (row, column) of entries `lane` and `lane + 32` of a 10 x 10 lower triangle, decoded once for all contacts
-  int si0 = 0, sj0 = lane, si1 = 0, sj1 = lane + 32;
-  while (sj0 > si0) { sj0 -= si0 + 1; si0++; }
-  while (sj1 > si1) { sj1 -= si1 + 1; si1++; }
-  if (lane + 32 >= 55) si1 = -1;
-  __syncwarp();
-  if (lane < LEAP_NV) {  // mass matrix + friction-loss / limit rows in their quadratic zone (diagonal), lane per dof
-    const int i = lane;
-    if (i < 3) LH(i, i) = W->Mc[i];
-    else if (i < 6) { for (int j = 3; j <= i; j++) LH(i, j) = m->cube_Irot[3 * (i - 3) + (j - 3)]; }
-    else {
-      const int f = (i - 6) >> 2, r = (i - 6) & 3;
-      for (int j = 0; j <= r; j++) LH(i, 6 + 4 * f + j) = W->Mf[f][r][j];
-      const int fr = (int)m->fr_row[i], rl = W->limrow[i - 6][0], rh = W->limrow[i - 6][1];
-      if (fr >= 0 && W->estate[fr] == LST_QUADRATIC) LH(i, i) += W->eD[fr];
-      if (rl >= 0 && W->estate[rl] == LST_QUADRATIC) LH(i, i) += W->eD[rl];
-      if (rh >= 0 && W->estate[rh] == LST_QUADRATIC) LH(i, i) += W->eD[rh];
-    }
-  }
-  __syncwarp();
-  for (int c = 0; c < ncon; c++) {
-    const int st = W->estate[nfl + 3 * c];
-    if (st == LST_SATISFIED) continue;
-    double Wm[9];
-    if (st == LST_QUADRATIC) {
-#pragma unroll
-      for (int k = 0; k < 9; k++) Wm[k] = 0;
-      Wm[0] = W->eD[nfl + 3 * c]; Wm[4] = W->eD[nfl + 3 * c + 1]; Wm[8] = W->eD[nfl + 3 * c + 2];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 9; k++) Wm[k] = leap_cHc(W, c)[k];
-    }
-    const double(*J)[10] = &W->Jc[3 * c];
-    const int fa = W->cfa[c], fb = W->cfinger[c];
-#pragma unroll
-    for (int half = 0; half < 2; half++) {  // lower triangle of the 10 x 10 block the compressed row spans: entries lane and lane + 32
-      const int si = half ? si1 : si0, sj = half ? sj1 : sj0;
-      if (si < 0) continue;
-      const int di = si < 6 ? (fa == -1 ? si : (fa >= 0 && si < 4 ? 6 + 4 * fa + si : -1)) : (fb >= 0 ? 6 + 4 * fb + si - 6 : -1);
-      const int dj = sj < 6 ? (fa == -1 ? sj : (fa >= 0 && sj < 4 ? 6 + 4 * fa + sj : -1)) : (fb >= 0 ? 6 + 4 * fb + sj - 6 : -1);
-      if (di < 0 || dj < 0) continue;
-      double h = 0;
-#pragma unroll
-      for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b = 0; b < 3; b++) h += Wm[3 * a + b] * J[a][si] * J[b][sj];
-      if (di >= dj) LH(di, dj) += h; else LH(dj, di) += h;
-    }
-    __syncwarp();
-  }
-  // Cholesky, lane i owns row i; dinv[k] = 1 / L_kk
-  for (int k = 0; k < LEAP_NV; k++) {
-    double d = LH(k, k);
-    if (d < B2_MINVAL) d = B2_MINVAL;
-    const double rs = rsqrt(d);
-    double l = 0;
-    if (lane == k) dinv[k] = rs;
-    if (lane > k && lane < LEAP_NV) { l = LH(lane, k) * rs; LH(lane, k) = l; }
-    __syncwarp();
-    if (lane > k && lane < LEAP_NV) {
-      // row update in batches of four independent entries (loads first: the column is read-only in this phase, the compiler cannot know)
-      double* row = &LH(lane, 0);
-      int j = k + 1;
-      for (; j + 3 <= lane; j += 4) {
-        const double c0 = LH(j, k), c1 = LH(j + 1, k), c2 = LH(j + 2, k), c3 = LH(j + 3, k);
-        const double r0 = row[j], r1 = row[j + 1], r2 = row[j + 2], r3 = row[j + 3];
-        row[j] = r0 - l * c0; row[j + 1] = r1 - l * c1; row[j + 2] = r2 - l * c2; row[j + 3] = r3 - l * c3;
-      }
-      for (; j <= lane; j++) row[j] -= l * LH(j, k);
-    }
-    __syncwarp();
-  }
-  // search = -(L L^T)^-1 grad: column-oriented substitutions, one shuffle per column
-  double x = lane < LEAP_NV ? -W->grad[lane] : 0.0;
-  const double di = lane < LEAP_NV ? dinv[lane] : 0.0;
-  for (int k = 0; k < LEAP_NV; k++) {
-    const double yk = __shfl_sync(FULL, x * di, k);
-    if (lane == k) x = yk;
-    else if (lane > k && lane < LEAP_NV) x -= LH(lane, k) * yk;
-  }
-  for (int k = LEAP_NV - 1; k >= 0; k--) {
-    const double xk = __shfl_sync(FULL, x * di, k);
-    if (lane == k) x = xk;
-    else if (lane < k) x -= LH(k, lane) * xk;
-  }
-  if (lane < LEAP_NV) W->search[lane] = x;
-  __syncwarp();
-}
-#undef LH
 
 // Line search state held in REGISTERS: lane r owns friction/limit row r (nfl <= 32) and lane c owns contact c, so one evaluation of
 // the 1-D cost derivatives is register math plus two warp reductions.  Contacts 32 .. LMAXCON-1 (rare: more than 32 contacts in a step)
@@ -1225,13 +1243,15 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
   for (int it = 0; it < iters; it++) {
     if (sync_mode >= 3) { if (!__syncthreads_or(done ? 0 : 1)) break; }
     else if (done) break;
+    if (threadIdx.x < 32) LPROF_BLK(1, 1);
     if (done) continue;
+    LPROF_BLK(2, 1);
     double gn = lane < LEAP_NV ? W->grad[lane] * W->grad[lane] : 0.0;
     gn = lwsum(gn);
     if (scale * sqrt(gn) < m->tolerance) { done = true; continue; }
     long long t1 = LPROF_T();
-    if (W->ncross > 0) { leap_newton_direction_dense(m, W, lane); if (prof && lane == 0) atomicAdd(&g_leap_prof[16], 1ull); }
-    else leap_newton_direction(m, W, lane);
+    leap_newton_direction(m, W, lane);
+    if (W->ncross > 0) { if (prof && lane == 0) atomicAdd(&g_leap_prof[16], 1ull); LPROF_BLK(3, 1); }
     LPROF_ADD(8, t1); t1 = LPROF_T();
     if (lane < LEAP_NV) W->Mv[lane] = leap_mulM_row(m, W, W->search, lane);
     for (int r = lane; r < nefc; r += 32) W->ejv[r] = r < nfl ? W->esign[r] * W->search[W->edof[r]] : leap_Jrow_dot(W, r - nfl, W->search);
@@ -1439,6 +1459,7 @@ __global__ void __launch_bounds__(224) leap_rollout_kernel(const LeapModel* __re
       if (threadIdx.x == 0) {
         const unsigned long long dt = (unsigned long long)(clock64() - t_block0);
         atomicMax(&g_leap_prof[21], dt); atomicAdd(&g_leap_prof[22], dt); atomicAdd(&g_leap_prof[23], 1ull);
+        if (blockIdx.x < 160) { atomicAdd(&g_leap_blk[blockIdx.x][0], dt); atomicAdd(&g_leap_blk[blockIdx.x][7], 1ull); }
       }
     }
     if (active && cost_NH) {
@@ -1493,6 +1514,21 @@ inline void leap_prof_dump() {
   if (cudaMemcpyFromSymbol(h, g_leap_prof, sizeof(h)) != cudaSuccess) return;
   const char* names[24] = {"kinematics", "mass+bias", "collision", "constraints", "smooth", "solver(total)", "integrate", "  update", "  direction", "  linesearch", "newton iters", "  coll:broad", "  coll:narrow", "candidates", "contacts", "  coll:hand-hand", "dense directions", "hand-hand contacts", "  one finger/palm", "hh past spheres", "hh past prefilter", "slowest block", "sum of blocks", "blocks"};
   for (int i = 0; i < 24; i++) fprintf(stderr, "leap_prof %-14s %llu\n", names[i], h[i]);
+  static unsigned long long hb[160][8];
+  if (cudaMemcpyFromSymbol(hb, g_leap_blk, sizeof(hb)) == cudaSuccess) {
+    int order[160];
+    for (int i = 0; i < 160; i++) order[i] = i;
+    for (int i = 0; i < 160; i++) for (int j = i + 1; j < 160; j++) if (hb[order[j]][0] > hb[order[i]][0]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+    fprintf(stderr, "leap_blk  block: cycles/launch lockstep-iters active-iters dense contacts cube-rounds hh-rounds (per launch; slowest 6, median, fastest)\n");
+    const int show[8] = {0, 1, 2, 3, 4, 5, 73, 146};
+    for (int q = 0; q < 8; q++) {
+      const int b = order[show[q]];
+      const double L = hb[b][7] ? (double)hb[b][7] : 1.0;
+      fprintf(stderr, "leap_blk %4d: %.0f %.1f %.1f %.1f %.1f %.1f %.1f\n", b, hb[b][0] / L, hb[b][1] / L, hb[b][2] / L, hb[b][3] / L, hb[b][4] / L, hb[b][5] / L, hb[b][6] / L);
+    }
+    memset(hb, 0, sizeof(hb));
+    cudaMemcpyToSymbol(g_leap_blk, hb, sizeof(hb));
+  }
   memset(h, 0, sizeof(h));
   cudaMemcpyToSymbol(g_leap_prof, h, sizeof(h));
 }

@@ -91,6 +91,21 @@ class ShardedPlanner:
         self.peer_exchange = ok
         return ok
 
+    @staticmethod
+    def wire_local(planners: list) -> None:
+        """Peer exchange between planners that live in ONE process (one per stream / device): buffers are exchanged as plain device pointers."""
+        world = len(planners)
+        bufs = (ctypes.c_void_p * world)()
+        for r, p in enumerate(planners):
+            mine = np.zeros(64, dtype=np.uint8)
+            p._check(p.lib.b200mpc_exchange_create(p.engine.handle, world, r, mine.ctypes.data))
+            b = ctypes.c_void_p()
+            p._check(p.lib.b200mpc_exchange_buffer(p.engine.handle, ctypes.byref(b)))
+            bufs[r] = b.value
+        for p in planners:
+            p._check(p.lib.b200mpc_exchange_open_local(p.engine.handle, bufs))
+            p.peer_exchange = True
+
     def align(self) -> None:
         """Line the ranks' GPUs up on the current stream (no data moves): a one-warp kernel that signals every peer and waits for all."""
         st = ctypes.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)

@@ -238,3 +238,39 @@ def test_make_controller_devices_argument():
     c.update_action()
     assert np.isfinite(c.nominal_knots).all() and c.rewards.shape == (32,)
     c.engine.close()
+
+
+@pytest.mark.parametrize("optimizer,opt_params", [("mppi", (0.05,)), ("cem", (3, 0.1, 1.0)), ("ps", ())])
+def test_two_rank_exchange_on_one_gpu(optimizer, opt_params):
+    """The in-kernel exchange with world_size 2 on ONE device: two handles, two streams, the two rollout kernels run side by side and
+    trade their partials through each other's exchange buffer (same-process peers: plain pointers instead of IPC handles).  Both ranks
+    must end with the update over ALL candidates, step after step (epoch parity, flags)."""
+    import torch
+
+    from judo_b200.dist import ShardedPlanner, shard_range
+    from oracle import plan as op
+
+    N = 1000
+    x0, knots, basis, params = _problem(N)
+    pls, streams = [], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for r in range(2):
+        lo, hi = shard_range(N, 2, r)
+        pl = ShardedPlanner("cartpole", hi - lo, device=0, rank=r, world_size=2)
+        pl.set_problem(x0, basis, params)
+        pl.set_knots(knots[lo:hi])
+        pls.append(pl)
+    ShardedPlanner.wire_local(pls)
+    for _ in range(3):
+        outs = []
+        for r, pl in enumerate(pls):
+            with torch.cuda.stream(streams[r]):
+                outs.append(pl.step(optimizer, np.array(opt_params), index_offset=shard_range(N, 2, r)[0]))
+        torch.cuda.synchronize()
+        rewards = np.concatenate([pl.d_reward.cpu().numpy() for pl in pls])
+        ref = {"mppi": lambda: op.mppi_update(knots, rewards, 0.05), "cem": lambda: op.cem_update(knots, rewards, 3, 0.1, 1.0)[0],
+               "ps": lambda: op.ps_update(knots, rewards)}[optimizer]()
+        a, b = (o.cpu().numpy().reshape(4, 1) for o in outs)
+        assert np.array_equal(a, b) and np.isfinite(a).all()
+        np.testing.assert_allclose(a, ref, rtol=1e-11, atol=1e-13)
+    for pl in pls:
+        pl.engine.close()

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 ( B200MPC_LEAP_PROF=1 timeout 300 python bench.py --workload leap_cube_mppi --steps 3 --warmup 3 --no-extras ) > gpurun_out/r02_leap_prof_c0.json 2> gpurun_out/r02_leap_prof_c0.txt
-grep leap_prof gpurun_out/r02_leap_prof_c0.txt | head -24
+grep "leap_blk\|leap_prof" gpurun_out/r02_leap_prof_c0.txt | head -34
 ( timeout 300 python bench.py --workload leap_cube_mppi --steps 10 --warmup 3 --no-extras ) > gpurun_out/r02_bench_leap_hh.json 2> gpurun_out/r02_bench_leap_hh.err
 python - <<'PY'
 import json
