@@ -44,8 +44,10 @@ WORKLOADS = {
 }
 # the same kernel in its contact-rich regime: the gripper closes on the cube and lifts it (40 pad/table contacts, ~170 constraint rows)
 WORKLOADS["fr3_pick_cem_grasp"] = dict(WORKLOADS["fr3_pick_cem"], scenario="grasp")
+# BASELINE.json configs[0]: the reference's own CPU-runnable size (plumbing case; both arms can run it, it is not the bench line)
+WORKLOADS["cartpole_ps"] = dict(task="cartpole", optimizer="ps", n_rollouts=32, H=32, K=4, order="zero", horizon=1.28, algo_bytes_per_rollout=4 * 4 + 4 * 32 + 4)
 WARP_TASKS = ("leap_cube", "fr3_pick")  # warp-per-rollout kernels: ms-scale steps, optimizer update as separate reduction kernels
-CONFIG_TAG = {"cartpole_mppi": "BASELINE config C2", "cylinder_push_cem": "BASELINE config C3", "leap_cube_mppi": "BASELINE config C4",
+CONFIG_TAG = {"cartpole_ps": "BASELINE config C1", "cartpole_mppi": "BASELINE config C2", "cylinder_push_cem": "BASELINE config C3", "leap_cube_mppi": "BASELINE config C4",
               "fr3_pick_cem": "SURVEY 8f-2, reference defaults at N=1024",
               "fr3_pick_cem_grasp": "SURVEY 8f-2 in its contact-rich regime: pre-grasp pose, nominal plan closes the gripper and lifts"}
 ALSO_1GPU = ("cylinder_push_cem", "leap_cube_mppi")   # measured next to the headline workload in the default single-GPU run

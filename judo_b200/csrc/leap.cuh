@@ -104,8 +104,9 @@ __device__ __forceinline__ LeapColLists* leap_col_lists(LeapWork* W) { return re
 // and inside the solver: update, direction (H + Cholesky + solve), line search, #newton iterations
 __device__ unsigned long long g_leap_prof[24];  // [16..18]: dense Newton directions, hand-hand contacts, of those inside one finger / against the palm; [19..20]: hand-hand pairs past the bounding spheres / past the pre-filter; [21..23]: slowest block (cycles), sum over blocks, blocks
 // per-block counters (prof mode): [0] block cycles, [1] lock-step Newton iterations the block walked, [2] iterations its warps were active in,
-// [3] dense directions, [4] contacts (sum over warps and steps), [5] cube narrow-phase rounds, [6] hand-hand narrow-phase rounds, [7] launches
-__device__ unsigned long long g_leap_blk[160][8];
+// [3] dense directions, [4] contacts (sum over warps and steps), [5] cube narrow-phase rounds, [6] hand-hand narrow-phase rounds, [7] launches,
+// [8] line-search evaluations, [9] of those in iterations with finger-finger contacts, [10] cycles of those iterations (direction + line search + update)
+__device__ unsigned long long g_leap_blk[160][12];
 #define LPROF_BLK(slot, v) do { if (prof && lane == 0 && blockIdx.x < 160) atomicAdd(&g_leap_blk[blockIdx.x][slot], (unsigned long long)(v)); } while (0)
 #define LPROF_T() (prof ? clock64() : 0)
 #define LPROF_ADD(slot, t0) do { if (prof && lane == 0) atomicAdd(&g_leap_prof[slot], (unsigned long long)(clock64() - (t0))); } while (0)
@@ -886,11 +887,12 @@ __device__ __noinline__ void leap_coupled_fingers(const LeapModel* __restrict__ 
   double* dinv = W->tmp;
   double* Bm = &W->Hcf[0][0][0];  // (16, 6): row 4 f + r
   double* yv = &W->yf[0][0];      // (16)
-  // block diagonal from the assembled finger blocks, zeros elsewhere
-  for (int e = lane; e < 136; e += 32) {
-    int i = 0, j = e;
-    while (j > i) { j -= i + 1; i++; }
-    Fp[e] = (i >> 2) == (j >> 2) ? W->Hff[i >> 2][i & 3][j & 3] : 0.0;
+  // block diagonal from the assembled finger blocks, zeros elsewhere (lane i writes row i)
+  if (lane < 16) {
+    double* row = &LF(lane, 0);
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+      if (j <= lane) row[j] = (j >> 2) == (lane >> 2) ? W->Hff[lane >> 2][lane & 3][j & 3] : 0.0;
   }
   __syncwarp();
   // cross-finger contacts: first finger's own block (lanes 0..9) and the coupling block (lanes 10..25); the second finger's own block
@@ -924,42 +926,37 @@ __device__ __noinline__ void leap_coupled_fingers(const LeapModel* __restrict__ 
     }
     __syncwarp();
   }
-  // left-looking Cholesky, lane i < 16 owns row i; dinv[k] = 1 / L_kk
+  // Left-looking Cholesky of the finger block, lane i < 16 owns row i.  The six cube-coupling columns of B and the right-hand side ride
+  // along as EXTRA ROWS (lanes 16..21: B^T, lane 22: -grad_F): what the elimination leaves in them is X^T = (L^-1 B)^T and
+  // y^T = (L^-1 (-grad_F))^T, so the two forward substitutions cost nothing beyond the 16 column steps.  dinv[k] = 1 / L_kk.
+  double* Lx = Fp + 136;       // (6, 16): row cc = column cc of B
+  double* gr = Fp + 136 + 96;  // (16)
+  static_assert(136 + 96 + 16 <= LB * 18, "finger block + coupling rows + rhs must fit into xpos .. xaxis");
+  for (int e = lane; e < 96; e += 32) { const int cc = e >> 4, k = e & 15; Lx[16 * cc + k] = Bm[6 * k + cc]; }
+  if (lane < 16) gr[lane] = -W->grad[6 + lane];
+  __syncwarp();
+  double* myrow = lane < 16 ? &LF(lane, 0) : (lane < 22 ? Lx + 16 * (lane - 16) : gr);
   for (int k = 0; k < 16; k++) {
     double sres = 0;
-    if (lane >= k && lane < 16) {
-      const double* ri = &LF(lane, 0);
+    if (lane >= k && lane < 23) {
       const double* rk = &LF(k, 0);
       double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
       int j = 0;
-      for (; j + 3 < k; j += 4) { s0 += ri[j] * rk[j]; s1 += ri[j + 1] * rk[j + 1]; s2 += ri[j + 2] * rk[j + 2]; s3 += ri[j + 3] * rk[j + 3]; }
-      for (; j < k; j++) s0 += ri[j] * rk[j];
-      sres = ri[k] - ((s0 + s1) + (s2 + s3));
+      for (; j + 3 < k; j += 4) { s0 += myrow[j] * rk[j]; s1 += myrow[j + 1] * rk[j + 1]; s2 += myrow[j + 2] * rk[j + 2]; s3 += myrow[j + 3] * rk[j + 3]; }
+      for (; j < k; j++) s0 += myrow[j] * rk[j];
+      sres = myrow[k] - ((s0 + s1) + (s2 + s3));
     }
     double d = __shfl_sync(FULL, sres, k);
     if (d < B2_MINVAL) d = B2_MINVAL;
     const double rs = rsqrt(d);
     if (lane == k) dinv[k] = rs;
-    else if (lane > k && lane < 16) LF(lane, k) = sres * rs;
+    else if (lane > k && lane < 23) myrow[k] = sres * rs;
     __syncwarp();
   }
-  // y = L^-1 (-grad_F): one shuffle per column
   const double di = lane < 16 ? dinv[lane] : 0.0;
-  double x = lane < 16 ? -W->grad[6 + lane] : 0.0;
-  for (int k = 0; k < 16; k++) {
-    const double yk = __shfl_sync(FULL, x * di, k);
-    if (lane == k) x = yk;
-    else if (lane > k && lane < 16) x -= LF(lane, k) * yk;
-  }
-  if (lane < 16) yv[lane] = x;
-  // X = L^-1 B in place, one cube column per lane
-  if (lane < 6) {
-    for (int i = 0; i < 16; i++) {
-      double sacc = Bm[6 * i + lane];
-      for (int k = 0; k < i; k++) sacc -= LF(i, k) * Bm[6 * k + lane];
-      Bm[6 * i + lane] = sacc * dinv[i];
-    }
-  }
+  double x;
+  for (int e = lane; e < 96; e += 32) { const int cc = e >> 4, k = e & 15; Bm[6 * k + cc] = Lx[16 * cc + k]; }  // X = L^-1 B, (16, 6)
+  if (lane < 16) yv[lane] = gr[lane];
   __syncwarp();
   leap_schur_cube(m, W, lane);
   // fingers: x_F = L^-T (y - X x_C)
@@ -1194,6 +1191,7 @@ __device__ inline double leap_line_search(const LeapModel* __restrict__ m, const
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
     leap_ls_eval(L, W, lane, alpha, g1, g2, &d1, &d2);
+    if (lane == 0) const_cast<LeapWork*>(W)->solver_iter++;  // (diagnostics: line-search evaluations of this call)
     if (fabs(d1) < gtol) return alpha;
     if (d1 < 0) lo = alpha; else hi = alpha;
     double next = d2 > 0 ? alpha - d1 / d2 : -1;
@@ -1250,13 +1248,16 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
     gn = lwsum(gn);
     if (scale * sqrt(gn) < m->tolerance) { done = true; continue; }
     long long t1 = LPROF_T();
+    const long long t_iter = t1;
     leap_newton_direction(m, W, lane);
-    if (W->ncross > 0) { if (prof && lane == 0) atomicAdd(&g_leap_prof[16], 1ull); LPROF_BLK(3, 1); }
+    if (W->ncross > 0) { if (prof && lane == 0) atomicAdd(&g_leap_prof[16], 1ull); LPROF_BLK(3, 1); if (prof) { LPROF_BLK(10, clock64() - t1); LPROF_BLK(9, W->ncon); } }
     LPROF_ADD(8, t1); t1 = LPROF_T();
     if (lane < LEAP_NV) W->Mv[lane] = leap_mulM_row(m, W, W->search, lane);
     for (int r = lane; r < nefc; r += 32) W->ejv[r] = r < nfl ? W->esign[r] * W->search[W->edof[r]] : leap_Jrow_dot(W, r - nfl, W->search);
     __syncwarp();
+    if (lane == 0) W->solver_iter = 0;
     const double alpha = leap_line_search(m, W, lane);
+    if (prof) { __syncwarp(); LPROF_BLK(8, W->solver_iter); if (W->ncross > 0) LPROF_BLK(11, clock64() - t1); }
     LPROF_ADD(9, t1); t1 = LPROF_T();
     if (lane == 0 && prof) atomicAdd(&g_leap_prof[10], 1ull);
     if (alpha == 0) { done = true; continue; }
@@ -1267,6 +1268,7 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
     __syncwarp();
     leap_constraint_update(m, W, W->qacc, true, lane);
     LPROF_ADD(7, t1);
+    if (prof && W->ncross > 0) LPROF_BLK(7 + 0 * (int)(clock64() - t_iter), 0);
     const double newcost = W->cost;
     __syncwarp();
     if (scale * (oldcost - newcost) < m->tolerance) done = true;
@@ -1514,7 +1516,7 @@ inline void leap_prof_dump() {
   if (cudaMemcpyFromSymbol(h, g_leap_prof, sizeof(h)) != cudaSuccess) return;
   const char* names[24] = {"kinematics", "mass+bias", "collision", "constraints", "smooth", "solver(total)", "integrate", "  update", "  direction", "  linesearch", "newton iters", "  coll:broad", "  coll:narrow", "candidates", "contacts", "  coll:hand-hand", "dense directions", "hand-hand contacts", "  one finger/palm", "hh past spheres", "hh past prefilter", "slowest block", "sum of blocks", "blocks"};
   for (int i = 0; i < 24; i++) fprintf(stderr, "leap_prof %-14s %llu\n", names[i], h[i]);
-  static unsigned long long hb[160][8];
+  static unsigned long long hb[160][12];
   if (cudaMemcpyFromSymbol(hb, g_leap_blk, sizeof(hb)) == cudaSuccess) {
     int order[160];
     for (int i = 0; i < 160; i++) order[i] = i;
@@ -1524,7 +1526,7 @@ inline void leap_prof_dump() {
     for (int q = 0; q < 8; q++) {
       const int b = order[show[q]];
       const double L = hb[b][7] ? (double)hb[b][7] : 1.0;
-      fprintf(stderr, "leap_blk %4d: %.0f %.1f %.1f %.1f %.1f %.1f %.1f\n", b, hb[b][0] / L, hb[b][1] / L, hb[b][2] / L, hb[b][3] / L, hb[b][4] / L, hb[b][5] / L, hb[b][6] / L);
+      fprintf(stderr, "leap_blk %4d: %.0f %.1f %.1f %.1f %.1f %.1f %.1f | ls evals %.1f; finger-finger iterations: contacts %.1f, direction cycles %.0f, line-search cycles %.0f\n", b, hb[b][0] / L, hb[b][1] / L, hb[b][2] / L, hb[b][3] / L, hb[b][4] / L, hb[b][5] / L, hb[b][6] / L, hb[b][8] / L, hb[b][9] / L, hb[b][10] / L, hb[b][11] / L);
     }
     memset(hb, 0, sizeof(hb));
     cudaMemcpyToSymbol(g_leap_blk, hb, sizeof(hb));
