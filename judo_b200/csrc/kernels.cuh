@@ -97,12 +97,11 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
             for (int j = 0; j < NU; j++) u[j] += b * kn[k * NU + j];
           }
         }
-        Task::step(c, s, u, nullptr);
+        const double ct = Task::step_cost(c, s, u, cp);
         if (ep.trace_q) {  // positions after step t: the elites' trace sensors are evaluated from them by the last warp (below)
 #pragma unroll
           for (int j = 0; j < Task::NQ; j++) ep.trace_q[((size_t)n * H + t) * Task::NQ + j] = s.q[j];
         }
-        double ct = Task::cost(cp, s, u);
         total += ct;
         if (cost_NH) sC[(size_t)tid * (H + 1) + t] = (float)ct;
       }

@@ -25,11 +25,11 @@ struct CartpoleTask {
   // sn/cs cache sincos(q[1]) (shared by this step's kinematics and the previous step's cost); the warm start
   // qacc_{t-1} = M_{t-1}^-1 qfrc_smooth_{t-1} of an unconstrained step is kept in factored form (wm01, wq) and only
   // evaluated if a constraint row turns up.
-  struct State { double q[2], v[2], warm[2], sn, cs, wm01, wq[2]; bool lazy; };
+  struct State { double q[2], v[2], warm[2], sn, cs, wm01, wq[2]; bool lazy; int since_exact; };
 
   __device__ static inline void load(State& s, const double* x) {
     s.q[0] = x[0]; s.q[1] = x[1]; s.v[0] = x[2]; s.v[1] = x[3]; s.warm[0] = s.warm[1] = 0; s.lazy = false;
-    s.wm01 = 0; s.wq[0] = s.wq[1] = 0;
+    s.wm01 = 0; s.wq[0] = s.wq[1] = 0; s.since_exact = 0;
     sincos(s.q[1], &s.sn, &s.cs);
   }
   __device__ static inline void store(const State& s, double* x) { x[0] = s.q[0]; x[1] = s.q[1]; x[2] = s.v[0]; x[3] = s.v[1]; }
@@ -107,6 +107,7 @@ struct CartpoleTask {
     s.v[0] += h * qa0; s.v[1] += h * qa1;
     s.q[0] += h * s.v[0]; s.q[1] += h * s.v[1];
     sincos(s.q[1], &s.sn, &s.cs);
+    s.since_exact = 0;
   }
 
   // cost params: [w_vertical, w_centered, w_velocity, w_control, p_vertical, p_centered]
@@ -117,6 +118,59 @@ struct CartpoleTask {
     double vel = 0.5 * (s.v[0] * s.v[0] + s.v[1] * s.v[1]);
     double ctl = 0.5 * u[0] * u[0];
     return p[0] * vertical + p[1] * centered + p[2] * vel + p[3] * ctl;
+  }
+
+  // the general path
+  __device__ static inline double step_cost_general(const Consts& c, State& s, const double* u, const double* p) {
+    step(c, s, u, nullptr);  // limit rows through the Newton solver, exact sincos at the end
+    return cost(p, s, u);
+  }
+
+  // One step + its cost for the fused kernel, arranged as ONE straight-line block: a lone warp per SM sub-partition issues in order, so
+  // what the step costs is the length of its dependent fp64 chain and how well the compiler can interleave the independent chains
+  // (dynamics, cost) — every branch in between is a scheduling barrier.  The unconstrained update (no joint-limit row: nefc == 0,
+  // qacc = qacc_smooth) and its cost are computed unconditionally; the rare cases redo the step through step() afterwards:
+  // a limit row is active, the pole turned by >= 0.5 rad in one step, or 31 incremental rotations have been chained.
+  // (sin, cos) of the advanced pole angle come from rotating the cached pair by the increment dq = h * v1 — Taylor series to the first
+  // term below 1e-17 for |dq| < 0.5 (sin through dq^15, cos through dq^14), evaluated pairwise (Estrin) to keep the chain short —
+  // instead of a full sincos (argument reduction, two polynomials, quadrant selection: the longest link of the old chain).
+  __device__ static inline double step_cost(const Consts& c, State& s, const double* u, const double* p) {
+    const double sn = s.sn, cs = s.cs;
+    const double h = c.dt, mp = c.m_pole, l = c.l_pole;
+    const double m00 = c.m_cart + mp, m01 = mp * l * cs, m11 = c.iyy_pole + mp * l * l;
+    double uc = u[0];
+    if (c.ctrllimited != 0) uc = fmin(fmax(uc, c.ctrl_lo), c.ctrl_hi);
+    double fa = c.kp * uc - c.kp * s.q[0];
+    if (c.forcelimited != 0) fa = fmin(fmax(fa, c.frc_lo), c.frc_hi);
+    const double bias0 = -mp * l * sn * s.v[1] * s.v[1];
+    const double bias1 = -mp * c.gravity * l * sn;
+    const double qfs0 = -c.damp_cart * s.v[0] - bias0 + fa, qfs1 = -c.damp_pole * s.v[1] - bias1;
+    const double dlo = s.q[0] - c.lim_lo, dhi = c.lim_hi - s.q[0];
+    const bool constrained = c.limited != 0 && (dlo < c.lim_margin || dhi < c.lim_margin);
+    const double a00 = m00 + h * c.damp_cart, a11 = m11 + h * c.damp_pole;
+    const double idet = fast_rcp_pos(a00 * a11 - m01 * m01);
+    const double qa0 = (a11 * qfs0 - m01 * qfs1) * idet, qa1 = (a00 * qfs1 - m01 * qfs0) * idet;
+    const double v0 = s.v[0] + h * qa0, v1 = s.v[1] + h * qa1;
+    const double q0 = s.q[0] + h * v0, dq = h * v1, q1 = s.q[1] + dq;
+    const double z = dq * dq, z2 = z * z, z4 = z2 * z2;
+    // sin(dq) = dq (1 + z S(z)),  S = s3 + s5 z + s7 z^2 + ... + s15 z^6;  cos(dq) = 1 + z C(z),  C = c2 + c4 z + ... + c14 z^6
+    const double S01 = fma(z, 1.0 / 120.0, -1.0 / 6.0), S23 = fma(z, 1.0 / 362880.0, -1.0 / 5040.0);
+    const double S45 = fma(z, 1.0 / 6227020800.0, -1.0 / 39916800.0), S6 = -1.0 / 1307674368000.0;
+    const double Sp = fma(z4, fma(z2, S6, S45), fma(z2, S23, S01));
+    const double C01 = fma(z, 1.0 / 24.0, -0.5), C23 = fma(z, 1.0 / 40320.0, -1.0 / 720.0);
+    const double C45 = fma(z, 1.0 / 479001600.0, -1.0 / 3628800.0), C6 = -1.0 / 87178291200.0;
+    const double Cp = fma(z4, fma(z2, C6, C45), fma(z2, C23, C01));
+    const double sd = fma(dq, z * Sp, dq), cd = fma(z, Cp, 1.0);
+    const double nsn = fma(sn, cd, cs * sd), ncs = fma(cs, cd, -sn * sd);
+    // cost at the new state (cartpole.py:66-71)
+    const double cz = ncs - 1;
+    const double vertical = fast_sqrt_nonneg(cz * cz + p[4] * p[4]) - p[4];
+    const double centered = fast_sqrt_nonneg(q0 * q0 + p[5] * p[5]) - p[5];
+    const double ct = p[0] * vertical + p[1] * centered + p[2] * (0.5 * (v0 * v0 + v1 * v1)) + p[3] * (0.5 * u[0] * u[0]);
+    if (constrained || !(fabs(dq) < 0.5) || s.since_exact >= 31) return step_cost_general(c, s, u, p);
+    s.wm01 = m01; s.wq[0] = qfs0; s.wq[1] = qfs1; s.lazy = true;  // (what step() keeps for a later warm start)
+    s.v[0] = v0; s.v[1] = v1; s.q[0] = q0; s.q[1] = q1; s.sn = nsn; s.cs = ncs; s.since_exact++;
+    return ct;
   }
   __device__ static inline double finish(double sum, int H) { return -sum; }
 };
@@ -254,6 +308,10 @@ struct CylinderPushTask {
     double vel = 0.5 * (s.v[0] * s.v[0] + s.v[1] * s.v[1]);
     double goal = 0.5 * (gx * gx + gy * gy);
     return p[0] * prox + p[1] * vel + p[2] * goal;
+  }
+  __device__ static inline double step_cost(const Consts& c, State& s, const double* u, const double* p) {
+    step(c, s, u, nullptr);
+    return cost(p, s, u);
   }
   __device__ static inline double finish(double sum, int H) { return -sum; }
 };

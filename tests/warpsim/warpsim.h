@@ -25,6 +25,7 @@
 
 // (after every standard header: libstdc++ itself spells attributes with these names)
 #define __device__
+#define __constant__ static const
 #define __host__
 #define __global__
 #define __forceinline__ inline
