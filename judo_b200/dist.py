@@ -93,7 +93,9 @@ class ShardedPlanner:
 
     @staticmethod
     def wire_local(planners: list) -> None:
-        """Peer exchange between planners that live in ONE process (one per stream / device): buffers are exchanged as plain device pointers."""
+        """Peer exchange between planners that live in ONE process (one per stream / device): buffers are exchanged as plain device pointers.
+        Run one step per planner BEFORE wiring (it sizes the handle's scratch buffers): an allocation inside a step may wait for the
+        device while a peer's kernel is already spinning on this rank's partial."""
         world = len(planners)
         bufs = (ctypes.c_void_p * world)()
         for r, p in enumerate(planners):
