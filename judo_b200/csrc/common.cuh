@@ -162,6 +162,18 @@ __device__ __forceinline__ double fast_rcp_pos(double d) {
   return r;
 #endif
 }
+__device__ __forceinline__ double fast_rsqrt_pos(double x) {  // x positive, normal
+#ifdef B2_HOST_SIM
+  return 1.0 / sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double t = fma(-hx * y, y, 0.5); y = fma(y, t, y);
+  t = fma(-hx * y, y, 0.5); y = fma(y, t, y);
+  return y;
+#endif
+}
 __device__ __forceinline__ double fast_sqrt_nonneg(double x) {  // x >= 0, not huge; sqrt(0) = 0
 #ifdef B2_HOST_SIM
   return sqrt(x);

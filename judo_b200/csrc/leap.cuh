@@ -22,6 +22,17 @@
 
 namespace b2 {
 
+// solver-loop reciprocals / roots without the library's special-case branches (common.cuh); B2_LEAP_LIBMATH restores the library calls
+#ifdef B2_LEAP_LIBMATH
+#define L_RSQRT(x) rsqrt(x)
+#define L_SQRT(x) sqrt(x)
+#define L_RCP(x) (1.0 / (x))
+#else
+#define L_RSQRT(x) fast_rsqrt_pos(x)
+#define L_SQRT(x) fast_sqrt_nonneg(x)
+#define L_RCP(x) fast_rcp_pos(x)
+#endif
+
 constexpr int LEAP_NQ = 23, LEAP_NV = 22, LEAP_NU = 16, LEAP_NS = 31, LEAP_NX = 45, LEAP_NCOST = 9;
 constexpr int LEAP_NTRACE = 15;  // doubles per step kept by the fused kernel's trace capture: the 5 framepos trace sensors
 constexpr int LB = 17;         // moving bodies: 0 = cube, 1 + 4f + d = link d of finger f
@@ -311,7 +322,7 @@ __device__ __forceinline__ void small_chol_solve(double (&A)[N][N], double* x) {
       double s = A[i][j];
 #pragma unroll
       for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
-      if (i == j) { if (s < B2_MINVAL) s = B2_MINVAL; L[i][i] = rsqrt(s); } else L[i][j] = s * L[j][j];
+      if (i == j) { if (s < B2_MINVAL) s = B2_MINVAL; L[i][i] = L_RSQRT(s); } else L[i][j] = s * L[j][j];
     }
 #pragma unroll
   for (int i = 0; i < N; i++) { double s = x[i];
@@ -698,7 +709,7 @@ __device__ __noinline__ double leap_cone_eval(const LeapWork* W, int c, int row0
   const double mu = W->cmu[c], f1 = W->cfri[c], f2 = W->cfri[c];
   const double D0 = W->eD[row0];
   const double U0 = x[0] * mu, U1 = x[1] * f1, U2 = x[2] * f2;
-  const double N = U0, T = sqrt(U1 * U1 + U2 * U2);
+  const double N = U0, T = L_SQRT(U1 * U1 + U2 * U2);
   double cost = 0;
   if (N >= mu * T) { force[0] = force[1] = force[2] = 0; *state = LST_SATISFIED; }
   else if (mu * N + T <= 0) {
@@ -709,13 +720,14 @@ __device__ __noinline__ double leap_cone_eval(const LeapWork* W, int c, int row0
     const double Dm = W->cDm[c], NmT = N - mu * T;
     cost = 0.5 * Dm * NmT * NmT;
     force[0] = -Dm * NmT * mu;
-    force[1] = T > B2_MINVAL ? -force[0] / T * U1 * f1 : 0;
-    force[2] = T > B2_MINVAL ? -force[0] / T * U2 * f2 : 0;
+    const double Tinv = T > B2_MINVAL ? L_RCP(T) : 0;
+    force[1] = -force[0] * Tinv * U1 * f1;
+    force[2] = -force[0] * Tinv * U2 * f2;
     *state = LST_CONE;
     if (Hc) {
       const double S[3] = {mu, f1, f2}, U[3] = {U0, U1, U2};
       double HU[9];
-      const double Ti = T > B2_MINVAL ? 1 / T : 0;
+      const double Ti = Tinv;
       HU[0] = Dm;
 #pragma unroll
       for (int j = 1; j < 3; j++) HU[j] = HU[3 * j] = -Dm * mu * U[j] * Ti;
@@ -855,7 +867,7 @@ __device__ __forceinline__ void leap_schur_cube(const LeapModel* __restrict__ m,
         double sacc = W->Hcc[i][j];
 #pragma unroll
         for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
-        if (i == j) { if (sacc < B2_MINVAL) sacc = B2_MINVAL; L[i][i] = rsqrt(sacc); } else L[i][j] = sacc * L[j][j];
+        if (i == j) { if (sacc < B2_MINVAL) sacc = B2_MINVAL; L[i][i] = L_RSQRT(sacc); } else L[i][j] = sacc * L[j][j];
       }
 #pragma unroll
     for (int i = 0; i < 6; i++) { double sacc = W->xc[i];
@@ -948,7 +960,7 @@ __device__ __noinline__ void leap_coupled_fingers(const LeapModel* __restrict__ 
     }
     double d = __shfl_sync(FULL, sres, k);
     if (d < B2_MINVAL) d = B2_MINVAL;
-    const double rs = rsqrt(d);
+    const double rs = L_RSQRT(d);
     if (lane == k) dinv[k] = rs;
     else if (lane > k && lane < 23) myrow[k] = sres * rs;
     __syncwarp();
@@ -1054,7 +1066,7 @@ __device__ inline void leap_newton_direction(const LeapModel* __restrict__ m, Le
 #pragma unroll
         for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
         // pivots are kept as RECIPROCALS (one rsqrt per pivot, every later division becomes a multiplication)
-        if (i == j) { if (sacc < B2_MINVAL) sacc = B2_MINVAL; L[i][i] = rsqrt(sacc); } else L[i][j] = sacc * L[j][j];
+        if (i == j) { if (sacc < B2_MINVAL) sacc = B2_MINVAL; L[i][i] = L_RSQRT(sacc); } else L[i][j] = sacc * L[j][j];
       }
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -1130,7 +1142,7 @@ __device__ __forceinline__ void leap_ls_contact(const double* cjar, const double
   const double x0 = cjar[0] + alpha * cjv[0], x1 = cjar[1] + alpha * cjv[1], x2 = cjar[2] + alpha * cjv[2];
   const double U1 = x1 * f, U2 = x2 * f;
   const double T2 = U1 * U1 + U2 * U2;
-  const double Ti = T2 > B2_MINVAL * B2_MINVAL ? rsqrt(T2) : 0;  // one rsqrt instead of a square root and a division
+  const double Ti = T2 > B2_MINVAL * B2_MINVAL ? L_RSQRT(T2) : 0;  // one rsqrt instead of a square root and a division
   const double N = x0 * mu, T = T2 * Ti;
   if (N >= mu * T) { /* separating: no force */ }
   else if (mu * N + T <= 0) {
@@ -1176,7 +1188,7 @@ __device__ inline double leap_line_search(const LeapModel* __restrict__ m, const
   lwsum2(g1, g2);
   double gs = lane < LEAP_NV ? W->grad[lane] * W->search[lane] : 0.0;
   lwsum2(sn, gs);
-  const double snorm = sqrt(sn);
+  const double snorm = L_SQRT(sn);
   if (snorm < B2_MINVAL) return 0;
   const double gtol = m->tolerance * m->ls_tolerance * snorm * m->meaninertia * LEAP_NV;
   LeapLS L;
@@ -1194,7 +1206,7 @@ __device__ inline double leap_line_search(const LeapModel* __restrict__ m, const
     if (lane == 0) const_cast<LeapWork*>(W)->solver_iter++;  // (diagnostics: line-search evaluations of this call)
     if (fabs(d1) < gtol) return alpha;
     if (d1 < 0) lo = alpha; else hi = alpha;
-    double next = d2 > 0 ? alpha - d1 / d2 : -1;
+    double next = d2 > 0 ? alpha - d1 * L_RCP(fmax(d2, 1e-200)) : -1;
     if (hi < 0) { if (!(next > lo)) next = 2 * alpha + B2_MINVAL; }
     else if (!(next > lo && next < hi && fabs(next - alpha) < 0.5 * prev_step)) next = 0.5 * (lo + hi);
     if (next == alpha) return alpha;
@@ -1246,7 +1258,7 @@ __device__ inline void leap_fwd_constraint(const LeapModel* __restrict__ m, Leap
     LPROF_BLK(2, 1);
     double gn = lane < LEAP_NV ? W->grad[lane] * W->grad[lane] : 0.0;
     gn = lwsum(gn);
-    if (scale * sqrt(gn) < m->tolerance) { done = true; continue; }
+    if (scale * L_SQRT(gn) < m->tolerance) { done = true; continue; }
     long long t1 = LPROF_T();
     const long long t_iter = t1;
     leap_newton_direction(m, W, lane);
