@@ -8,7 +8,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -66,6 +69,10 @@ struct b200mpc_handle {
   // speculative sampling: the next block of normals, the generator state it was drawn from and the state after it
   std::vector<double> znext; size_t znext_n = 0; bool znext_valid = false;
   uint32_t snap_key[624]; int snap_pos = 0; uint32_t adv_key[624]; int adv_pos = 0;
+  // the speculative block is drawn by a helper thread while the GPU runs AND while the caller goes on (copy-out, Python glue, the next
+  // call's staging): at C2 drawing 16 K normals takes twice as long as the GPU step.  Readers of znext / adv_* join first (spec_join).
+  std::thread spec_thread; std::mutex spec_mu; std::condition_variable spec_cv; bool spec_pending = false, spec_busy = false, spec_quit = false;
+  size_t spec_cnt = 0;
 };
 
 #define CK(call)                                                                                   \
@@ -140,11 +147,14 @@ extern "C" int b200mpc_create(b200mpc_handle** out, int task_id, const double* c
   return 0;
 }
 
+static void spec_stop(b200mpc_handle* h);
+
 extern "C" void b200mpc_destroy(b200mpc_handle* h) {
   if (!h) return;
   if (h->timing && h->t_calls)
     fprintf(stderr, "b200mpc host timing over %lld calls (us) [plan_step: stage|launch|wait|copy-out; controller_step: sample|assemble|h2d+launch|wait (+ speculative sampling before the wait)]: %.1f %.1f %.1f %.1f (+ %.1f)\n", h->t_calls,
             h->t_stage / h->t_calls, h->t_launch / h->t_calls, h->t_sync / h->t_calls, h->t_out / h->t_calls, h->t_spec / h->t_calls);
+  spec_stop(h);
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int g = 0; g < 8; g++) if (h->xchg_peer[g] && h->xchg_peer[g] != h->xchg && !h->xchg_local) cudaIpcCloseMemHandle(h->xchg_peer[g]);
@@ -924,8 +934,39 @@ extern "C" int b200mpc_last_candidates(b200mpc_handle* h, double* knots_out, int
   return 0;
 }
 
+static void spec_worker(b200mpc_handle* h) {
+  std::unique_lock<std::mutex> lk(h->spec_mu);
+  for (;;) {
+    h->spec_cv.wait(lk, [h] { return h->spec_pending || h->spec_quit; });
+    if (h->spec_quit) return;
+    h->spec_pending = false;
+    const size_t cnt = h->spec_cnt;
+    lk.unlock();
+    h->znext.resize(cnt);
+    b2host::mt19937_normals(h->adv_key, &h->adv_pos, h->znext.data(), cnt);  // (adv_* / znext belong to the worker until spec_busy drops)
+    lk.lock();
+    h->znext_n = cnt;
+    h->znext_valid = true;
+    h->spec_busy = false;
+    h->spec_cv.notify_all();
+  }
+}
+// wait until the helper thread has finished the block it is drawing (no-op when it is idle)
+static void spec_join(b200mpc_handle* h) {
+  if (!h->spec_thread.joinable()) return;
+  std::unique_lock<std::mutex> lk(h->spec_mu);
+  h->spec_cv.wait(lk, [h] { return !h->spec_busy; });
+}
+static void spec_stop(b200mpc_handle* h) {
+  if (!h->spec_thread.joinable()) return;
+  { std::lock_guard<std::mutex> lk(h->spec_mu); h->spec_quit = true; }
+  h->spec_cv.notify_all();
+  h->spec_thread.join();
+}
+
 extern "C" int b200mpc_controller_speculation(b200mpc_handle* h, const unsigned int* mt_key, const int* mt_pos, size_t n) {
   if (!h || !mt_key || !mt_pos) return 0;
+  spec_join(h);
   return h->znext_valid && h->znext_n == n && *mt_pos == h->snap_pos && memcmp(mt_key, h->snap_key, sizeof(h->snap_key)) == 0;
 }
 
@@ -938,6 +979,7 @@ static int step_sample(b200mpc_handle* h, b200mpc_step_request* rq, size_t n) {
     double* z = h->zbuf.data();
     for (int i = 0; i < rq->n_head; i++) z[i] = rq->head[i];
     const size_t rem = n - (size_t)rq->n_head, gen = rem & ~(size_t)1;
+    spec_join(h);
     if (rq->use_speculated) {
       // the `gen` normals that follow the head values were drawn during the previous step's GPU time (step_speculate)
       if (!gen || !b200mpc_controller_speculation(h, rq->mt_key, rq->mt_pos, gen)) return fail(h, "the speculated block does not match the generator state");
@@ -970,6 +1012,7 @@ static int step_sample(b200mpc_handle* h, b200mpc_step_request* rq, size_t n) {
 //   this step drew a tail through numpy -> cache occupied -> the next step's head is that cached value (no state change), then
 //   (n - 1) & ~1 normals from here, then its own tail.
 static void step_speculate(b200mpc_handle* h, const b200mpc_step_request* rq, size_t n) {
+  spec_join(h);
   h->znext_valid = false;
   const size_t cnt = !h->step_tail_pending ? ((n & 1) == 0 ? n : 0) : ((n - 1) & ~(size_t)1);
   if (rq->speculate && cnt >= 2 && rq->mt_key && rq->mt_pos && *rq->mt_pos >= 0 && *rq->mt_pos <= 624) {
@@ -977,10 +1020,9 @@ static void step_speculate(b200mpc_handle* h, const b200mpc_step_request* rq, si
     h->snap_pos = *rq->mt_pos;
     memcpy(h->adv_key, h->snap_key, sizeof(h->adv_key));
     h->adv_pos = h->snap_pos;
-    h->znext.resize(cnt);
-    b2host::mt19937_normals(h->adv_key, &h->adv_pos, h->znext.data(), cnt);
-    h->znext_n = cnt;
-    h->znext_valid = true;
+    if (!h->spec_thread.joinable()) h->spec_thread = std::thread(spec_worker, h);
+    { std::lock_guard<std::mutex> lk(h->spec_mu); h->spec_cnt = cnt; h->spec_pending = true; h->spec_busy = true; }
+    h->spec_cv.notify_all();  // the block is drawn while the GPU runs and the caller carries on; whoever reads it joins first
   }
 }
 
