@@ -21,6 +21,17 @@
 
 namespace b2 {
 
+// solver-loop reciprocals / roots without the library's special-case branches (common.cuh); B2_FR3_LIBMATH restores the library calls
+#ifdef B2_FR3_LIBMATH
+#define F_RSQRT(x) rsqrt(x)
+#define F_SQRT(x) sqrt(x)
+#define F_RCP(x) (1.0 / (x))
+#else
+#define F_RSQRT(x) fast_rsqrt_pos(x)
+#define F_SQRT(x) fast_sqrt_nonneg(x)
+#define F_RCP(x) fast_rcp_pos(x)
+#endif
+
 constexpr int FR_NQ = 16, FR_NV = 15, FR_NU = 8, FR_NS = 14, FR_NX = 31, FR_NCOST = 23;
 constexpr int FR_NTRACE = 6;  // doubles per step kept by the fused kernel's trace capture: trace_object, trace_grasp_site
 constexpr int FB = 11;        // moving bodies: 0 object, 1..7 links, 8 hand (welded to link 7), 9 left finger, 10 right finger
@@ -396,7 +407,7 @@ __device__ inline void warp_chol(double (*A)[FLD], double* dinv, int n, int lane
   for (int k = 0; k < n; k++) {
     double d = A[k][k];
     if (d < B2_MINVAL) d = B2_MINVAL;
-    const double rs = rsqrt(d);
+    const double rs = F_RSQRT(d);  // (d is clamped to B2_MINVAL above: positive, normal)
     double l = 0;
     if (lane == k) dinv[k] = rs;
     if (lane > k && lane < n) { l = A[lane][k] * rs; A[lane][k] = l; }
@@ -431,7 +442,7 @@ __device__ inline void warp_chol2(double (*A)[FLD], double* dinv, int lane) {
     const int col = act ? base + k : 0;
     double d = A[col][col];
     if (d < B2_MINVAL) d = B2_MINVAL;
-    const double rs = rsqrt(d);
+    const double rs = F_RSQRT(d);  // (d is clamped to B2_MINVAL above: positive, normal)
     double l = 0;
     if (act && lane == col) dinv[col] = rs;
     if (act && lane > col) { l = A[lane][col] * rs; A[lane][col] = l; }
@@ -847,7 +858,7 @@ __device__ inline double fr3_line_search(const Fr3Model* __restrict__ m, Fr3Work
   }
   fwsum2(g1, g2);
   fwsum2(sn, gs);
-  const double snorm = sqrt(sn);
+  const double snorm = F_SQRT(sn);
   // derivatives at alpha = 0 without touching the rows: d1(0) = grad . search and, for the Newton direction, d2(0) = -d1(0)
   double d1 = gs, d2 = -d1, lo = 0, hi = -1, alpha;
   if (snorm < B2_MINVAL) return 0;
@@ -861,7 +872,7 @@ __device__ inline double fr3_line_search(const Fr3Model* __restrict__ m, Fr3Work
     fr3_ls_eval(L, alpha, g1, g2, &d1, &d2);
     if (fabs(d1) < gtol) return alpha;
     if (d1 < 0) lo = alpha; else hi = alpha;
-    double next = d2 > 0 ? alpha - d1 / d2 : -1;
+    double next = d2 > 0 ? alpha - d1 * F_RCP(fmax(d2, 1e-200)) : -1;
     if (hi < 0) { if (!(next > lo)) next = 2 * alpha + B2_MINVAL; }
     else if (!(next > lo && next < hi && fabs(next - alpha) < 0.5 * prev_step)) next = 0.5 * (lo + hi);
     if (next == alpha) return alpha;
@@ -903,7 +914,7 @@ __device__ inline void fr3_fwd_constraint(const Fr3Model* __restrict__ m, Fr3Wor
     if (done) continue;
     double gn = lane < FR_NV ? W->grad[lane] * W->grad[lane] : 0.0;
     gn = fwsum(gn);
-    if (scale * sqrt(gn) < m->tolerance) { done = true; continue; }
+    if (scale * F_SQRT(gn) < m->tolerance) { done = true; continue; }
     long long t1 = FPROF_T();
     fr3_newton_direction(m, W, lane);
     FPROF_ADD(8, t1); t1 = FPROF_T();
