@@ -375,6 +375,10 @@ class Controller:
         self.all_traces_rollout_size = self.sensor_rollout_size * self.num_trace_sensors
         self.num_trace_elites = min(self.max_num_traces, self.optimizer_cfg.num_rollouts)
         ne, nts, size = self.num_trace_elites, self.num_trace_sensors, self.sensor_rollout_size
+        if ne == 0 or nts == 0:  # max_num_traces = 0 (or a task without trace sensors): no segments, as the reference's empty gather
+            self.elite_indices = np.zeros(0, dtype=np.int64)
+            self.traces = np.zeros((0, 2, 3))
+            return
         if getattr(self, "_fast_traces", None) is not None:  # the fast path's C call already assembled the segments
             self.elite_indices = np.asarray(self._elite[:ne])
             self.traces = self._fast_traces

@@ -59,15 +59,28 @@ struct b200mpc_handle {
   // peer exchange (multi-GPU fused MPPI): local buffer + peers' buffers opened through CUDA IPC
   void* xchg = nullptr; void* xchg_peer[8] = {nullptr}; int xchg_world = 0, xchg_rank = 0; unsigned long long xchg_epoch = 0, xchg_align_epoch = 0; bool xchg_local = false;
   unsigned long long* d_stamps = nullptr;  // %globaltimer stamps of the last finalize=2 step (b200mpc_exchange_stamps)
-  double t_stage = 0, t_launch = 0, t_sync = 0, t_out = 0, t_spec = 0; long long t_calls = 0; bool timing = false;  // B200MPC_TIMING=1
+  double t_stage = 0, t_launch = 0, t_sync = 0, t_out = 0, t_spec = 0, t_gpu = 0; long long t_calls = 0; bool timing = false;  // B200MPC_TIMING=1
+  cudaEvent_t tev0 = nullptr, tev1 = nullptr;  // (timing mode: GPU-side duration of a controller step, H2D to kernel end)
   // b200mpc_controller_step: normals of the current block, captured positions (N, H, nq) for the in-kernel elite traces, and where the
   // last step's candidates sit in the pinned staging buffer
   std::vector<double> zbuf, qtimes; bool step_sampled = false, step_tail_pending = false;
   void* d_traceq = nullptr; size_t d_traceq_bytes = 0;
   size_t cand_off = 0; int cand_N = 0, cand_K = 0;
+  bool allow_resident = false;  // set by b200mpc_controller_step around its sampling stage (the device group assembles on the host)
   std::vector<double> trace_tmp;
   // speculative sampling: the next block of normals, the generator state it was drawn from and the state after it
-  std::vector<double> znext; size_t znext_n = 0; bool znext_valid = false;
+  size_t znext_n = 0; bool znext_valid = false;
+  // The speculated block lives in one of two PINNED host slots and is uploaded to the matching device slot by the helper thread as soon
+  // as it is drawn.  A step whose whole block was speculated then launches with the normals already resident: the kernel assembles
+  // clip(nominal + sigma * z) itself (sampling.cuh, enabled == 2) and neither the host assembly nor the (N, K, nu) upload are on the
+  // step's critical path.  Slots alternate, so the block a running kernel reads is never the one being refilled.
+  double* h_z[2] = {nullptr, nullptr}; size_t h_z_bytes[2] = {0, 0};
+  double* d_z[2] = {nullptr, nullptr}; size_t d_z_bytes[2] = {0, 0};
+  cudaStream_t z_stream = nullptr; cudaEvent_t z_ev[2] = {nullptr, nullptr};
+  bool z_uploaded[2] = {false, false}; int z_slot = 0 /* slot of znext */, z_cur = -1 /* slot this step's kernel reads, -1: none */;
+  bool z_resident = false, z_resident_ok = true;
+  // candidates of a device-assembled step are rebuilt on the host only if somebody asks (b200mpc_last_candidates)
+  bool cand_lazy = false; const double* cand_z = nullptr; std::vector<double> cand_par;
   uint32_t snap_key[624]; int snap_pos = 0; uint32_t adv_key[624]; int adv_pos = 0;
   // the speculative block is drawn by a helper thread while the GPU runs AND while the caller goes on (copy-out, Python glue, the next
   // call's staging): at C2 drawing 16 K normals takes twice as long as the GPU step.  Readers of znext / adv_* join first (spec_join).
@@ -142,6 +155,7 @@ extern "C" int b200mpc_create(b200mpc_handle** out, int task_id, const double* c
   } else return bad("unknown task id");
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bad("cudaStreamCreate failed");
   if (const char* z = getenv("B200MPC_ZEROCOPY")) h->zero_copy = atoi(z);
+  if (const char* z = getenv("B200MPC_Z_RESIDENT")) h->z_resident_ok = atoi(z) != 0;
   h->timing = getenv("B200MPC_TIMING") != nullptr;
   *out = h;
   return 0;
@@ -154,11 +168,14 @@ extern "C" void b200mpc_destroy(b200mpc_handle* h) {
   if (h->timing && h->t_calls)
     fprintf(stderr, "b200mpc host timing over %lld calls (us) [plan_step: stage|launch|wait|copy-out; controller_step: sample|assemble|h2d+launch|wait (+ speculative sampling before the wait)]: %.1f %.1f %.1f %.1f (+ %.1f)\n", h->t_calls,
             h->t_stage / h->t_calls, h->t_launch / h->t_calls, h->t_sync / h->t_calls, h->t_out / h->t_calls, h->t_spec / h->t_calls);
+  if (h->timing && h->t_calls && h->t_gpu > 0) fprintf(stderr, "b200mpc controller_step GPU side (H2D .. kernel end, CUDA events): %.1f us\n", h->t_gpu / h->t_calls);
   spec_stop(h);
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int g = 0; g < 8; g++) if (h->xchg_peer[g] && h->xchg_peer[g] != h->xchg && !h->xchg_local) cudaIpcCloseMemHandle(h->xchg_peer[g]);
   cudaFree(h->xchg); cudaFree(h->d_stamps);
+  for (int i = 0; i < 2; i++) { cudaFreeHost(h->h_z[i]); cudaFree(h->d_z[i]); if (h->z_ev[i]) cudaEventDestroy(h->z_ev[i]); }
+  if (h->z_stream) cudaStreamDestroy(h->z_stream);
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_big); cudaFree(h->d_part); cudaFree(h->d_work); cudaFree(h->d_trace); cudaFree(h->d_traceq);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out);
 #ifdef B200MPC_WITH_LEAP
@@ -930,6 +947,12 @@ extern "C" int b200mpc_last_candidates(b200mpc_handle* h, double* knots_out, int
   if (!h) return 1;
   if (!knots_out || !h->h_in || h->cand_N == 0) return fail(h, "no candidates: run b200mpc_controller_step first");
   if (N != h->cand_N || K != h->cand_K) return fail(h, "N / K do not match the last b200mpc_controller_step");
+  if (h->cand_lazy) {  // the step assembled its candidates on the device: same arithmetic, here, from the same normals
+    const int nu = h->dims.nu, KNU = K * nu;
+    const double* par = h->cand_par.data();
+    b2host::assemble_candidates(h->cand_z, par, par + KNU, par + 2 * KNU, par + 2 * KNU + nu, N, K, nu, knots_out);
+    return 0;
+  }
   memcpy(knots_out, (const char*)h->h_in + h->cand_off, (size_t)N * K * h->dims.nu * 8);
   return 0;
 }
@@ -942,9 +965,14 @@ static void spec_worker(b200mpc_handle* h) {
     h->spec_pending = false;
     const size_t cnt = h->spec_cnt;
     lk.unlock();
-    h->znext.resize(cnt);
-    b2host::mt19937_normals(h->adv_key, &h->adv_pos, h->znext.data(), cnt);  // (adv_* / znext belong to the worker until spec_busy drops)
+    const int slot = h->z_slot;
+    b2host::mt19937_normals(h->adv_key, &h->adv_pos, h->h_z[slot], cnt);  // (adv_* / the slot belong to the worker until spec_busy drops)
+    bool up = false;
+    if (h->z_resident_ok && h->d_z[slot] && h->z_stream && cudaSetDevice(h->device) == cudaSuccess)
+      up = cudaMemcpyAsync(h->d_z[slot], h->h_z[slot], cnt * sizeof(double), cudaMemcpyHostToDevice, h->z_stream) == cudaSuccess &&
+           cudaEventRecord(h->z_ev[slot], h->z_stream) == cudaSuccess;
     lk.lock();
+    h->z_uploaded[slot] = up;
     h->znext_n = cnt;
     h->znext_valid = true;
     h->spec_busy = false;
@@ -974,7 +1002,9 @@ extern "C" int b200mpc_controller_speculation(b200mpc_handle* h, const unsigned 
 // The sampling stage of b200mpc_controller_step (shared with the multi-GPU group): fills h->zbuf with the n normals of this step's
 // block.  Returns 0 when the block is complete, 2 after a phase-1 call (the caller still owes the tail), 1 on error.
 static int step_sample(b200mpc_handle* h, b200mpc_step_request* rq, size_t n) {
+  h->z_resident = false;
   if (rq->phase != 2) {
+    h->z_cur = -1;
     h->zbuf.resize(n + 2);
     double* z = h->zbuf.data();
     for (int i = 0; i < rq->n_head; i++) z[i] = rq->head[i];
@@ -983,7 +1013,13 @@ static int step_sample(b200mpc_handle* h, b200mpc_step_request* rq, size_t n) {
     if (rq->use_speculated) {
       // the `gen` normals that follow the head values were drawn during the previous step's GPU time (step_speculate)
       if (!gen || !b200mpc_controller_speculation(h, rq->mt_key, rq->mt_pos, gen)) return fail(h, "the speculated block does not match the generator state");
-      memcpy(z + rq->n_head, h->znext.data(), gen * sizeof(double));
+      const bool warp_task = h->task == B200MPC_TASK_LEAP_CUBE || h->task == B200MPC_TASK_FR3_PICK;
+      if (rq->n_head == 0 && gen == n && rq->phase == 0 && h->z_uploaded[h->z_slot] && h->z_resident_ok && !warp_task && h->allow_resident) {
+        h->z_resident = true;   // the whole block is already on the device: no host copy, no host assembly (b200mpc_controller_step)
+        h->z_cur = h->z_slot;
+      } else {
+        memcpy(z + rq->n_head, h->h_z[h->z_slot], gen * sizeof(double));
+      }
       memcpy(rq->mt_key, h->adv_key, sizeof(h->adv_key));  // the generator now stands where drawing them would have left it
       *rq->mt_pos = h->adv_pos;
     } else if (gen) {
@@ -1020,6 +1056,15 @@ static void step_speculate(b200mpc_handle* h, const b200mpc_step_request* rq, si
     h->snap_pos = *rq->mt_pos;
     memcpy(h->adv_key, h->snap_key, sizeof(h->adv_key));
     h->adv_pos = h->snap_pos;
+    const int slot = h->z_cur == 0 ? 1 : 0;  // never the slot the running kernel reads
+    bool ok = grow(h, (void**)&h->h_z[slot], &h->h_z_bytes[slot], cnt * sizeof(double), true) == 0;
+    if (ok && h->z_resident_ok) {
+      if (!h->z_stream) ok = cudaStreamCreateWithFlags(&h->z_stream, cudaStreamNonBlocking) == cudaSuccess;
+      for (int i = 0; ok && i < 2; i++) if (!h->z_ev[i]) ok = cudaEventCreateWithFlags(&h->z_ev[i], cudaEventDisableTiming) == cudaSuccess;
+      if (ok) ok = grow(h, (void**)&h->d_z[slot], &h->d_z_bytes[slot], cnt * sizeof(double), false) == 0;
+    }
+    if (!ok) return;  // (no speculation this step: the next one samples in the call)
+    h->z_slot = slot; h->z_uploaded[slot] = false;
     if (!h->spec_thread.joinable()) h->spec_thread = std::thread(spec_worker, h);
     { std::lock_guard<std::mutex> lk(h->spec_mu); h->spec_cnt = cnt; h->spec_pending = true; h->spec_busy = true; }
     h->spec_cv.notify_all();  // the block is drawn while the GPU runs and the caller carries on; whoever reads it joins first
@@ -1052,19 +1097,24 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
 
   // ---- phase 0 / 1: draw the block of normals (head values first, then an even number straight from the generator state)
   {
+    h->allow_resident = !rq->knots_out;
     const int rc = step_sample(h, rq, n);
+    h->allow_resident = false;
     if (rc == 2) return 0;   // phase 1: sampled, waiting for the caller's tail normal
     if (rc) return 1;
   }
   auto T1 = std::chrono::steady_clock::now();
+  const bool resident = h->z_resident;  // this step's normals are already on the device (drawn and uploaded during the previous step)
 
   // ---- stage [x0 | basis | params | knots] in pinned memory: the basis and the candidates are produced in place
   size_t o = 0;
   const size_t ox0 = o; o += al16((size_t)nx * 8);
   const size_t ob = o; o += al16((size_t)H * K * 8);
   const size_t op = o; o += al16((size_t)np * 8);
-  const size_t ok = o; o += (size_t)N * KNU * 8;
-  if (grow(h, &h->h_in, &h->h_in_bytes, o, true) || grow(h, &h->d_in, &h->d_in_bytes, o, false)) return 1;
+  // resident: [nominal | sigma | lo | hi] instead of the candidates
+  const size_t ok = o; o += resident ? al16((size_t)(2 * KNU + 2 * nu) * 8) : (size_t)N * KNU * 8;
+  if (grow(h, &h->h_in, &h->h_in_bytes, al16(o), true) || grow(h, &h->d_in, &h->d_in_bytes, al16(o), false)) return 1;
+  if (resident && grow(h, &h->d_big, &h->d_big_bytes, (size_t)N * KNU * 8, false)) return 1;
   char* hp = (char*)h->h_in;
   memcpy(hp + ox0, rq->x0, (size_t)nx * 8);
   memcpy(hp + op, rq->cost_params, (size_t)np * 8);
@@ -1072,11 +1122,26 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
   for (int i = 0; i < H; i++) h->qtimes[i] = rq->time + rq->dt * (double)i;  // self.time + task.dt * arange(H) (controller.py:261)
   if (b2host::spline_basis(rq->spline_order, rq->knot_times, K, h->qtimes.data(), H, (double*)(hp + ob))) return fail(h, "bad spline request (order / number of knots)");
   if (rq->basis_out) memcpy(rq->basis_out, hp + ob, (size_t)H * K * 8);
-  b2host::assemble_candidates(h->zbuf.data(), rq->nominal, rq->sigma, rq->lo, rq->hi, N, K, nu, (double*)(hp + ok));
+  SampleSpec smp{};
+  if (resident) {
+    double* par = (double*)(hp + ok);
+    memcpy(par, rq->nominal, (size_t)KNU * 8); memcpy(par + KNU, rq->sigma, (size_t)KNU * 8);
+    memcpy(par + 2 * KNU, rq->lo, (size_t)nu * 8); memcpy(par + 2 * KNU + nu, rq->hi, (size_t)nu * 8);
+    h->cand_par.assign(par, par + 2 * KNU + 2 * nu);
+    h->cand_lazy = true; h->cand_z = h->h_z[h->z_cur];
+    const double* dpar = (const double*)((char*)h->d_in + ok);
+    smp.enabled = 2; smp.z = h->d_z[h->z_cur]; smp.nominal = dpar; smp.sigma = dpar + KNU; smp.lo = dpar + 2 * KNU; smp.hi = dpar + 2 * KNU + nu;
+    smp.knots_out = (double*)h->d_big;
+  } else {
+    b2host::assemble_candidates(h->zbuf.data(), rq->nominal, rq->sigma, rq->lo, rq->hi, N, K, nu, (double*)(hp + ok));
+    h->cand_lazy = false;
+    if (rq->knots_out) memcpy(rq->knots_out, hp + ok, (size_t)N * KNU * 8);
+  }
   h->cand_off = ok; h->cand_N = N; h->cand_K = K;
-  if (rq->knots_out) memcpy(rq->knots_out, hp + ok, (size_t)N * KNU * 8);
   auto T2 = std::chrono::steady_clock::now();
+  if (h->timing) { if (!h->tev0) { cudaEventCreate(&h->tev0); cudaEventCreate(&h->tev1); } cudaEventRecord(h->tev0, h->stream); }
   CK(cudaMemcpyAsync(h->d_in, h->h_in, o, cudaMemcpyHostToDevice, h->stream));
+  if (resident) CK(cudaStreamWaitEvent(h->stream, h->z_ev[h->z_cur], 0));  // the upload of the block (finished long ago)
 
   // ---- outputs, written by the kernels straight into pinned host memory: [nominal | sigma | elite idx | elite sensors | reward]
   const bool kernel_traces = nts > 0 && ne > 0 && !warp_task;
@@ -1088,10 +1153,11 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
   void* dout_v = nullptr;
   CK(cudaHostGetDevicePointer(&dout_v, h->h_out, 0));
   char* din = (char*)h->d_in; char* dout = (char*)dout_v;
-  if (plan_step_impl(h, (double*)(din + ox0), (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), optimizer, rq->opt_params,
-                     /*finalize=*/1, /*index_offset=*/0, ne, nullptr, (double*)(dout + o_rw), (double*)(dout + o_nom), (double*)(dout + o_sig),
-                     (double*)(dout + o_el), nullptr, nullptr, SampleSpec{}, h->stream, kernel_traces ? (double*)h->d_traceq : nullptr,
+  if (plan_step_impl(h, (double*)(din + ox0), resident ? (double*)h->d_big : (double*)(din + ok), N, K, (double*)(din + ob), H, (double*)(din + op), optimizer,
+                     rq->opt_params, /*finalize=*/1, /*index_offset=*/0, ne, nullptr, (double*)(dout + o_rw), (double*)(dout + o_nom), (double*)(dout + o_sig),
+                     (double*)(dout + o_el), nullptr, nullptr, smp, h->stream, kernel_traces ? (double*)h->d_traceq : nullptr,
                      kernel_traces ? (double*)(dout + o_es) : nullptr)) return 1;
+  if (h->timing) cudaEventRecord(h->tev1, h->stream);
   auto T3 = std::chrono::steady_clock::now();
   step_speculate(h, rq, n);   // while the GPU works: the next step's normals, from a copy of the generator state
   auto T3b = std::chrono::steady_clock::now();
@@ -1100,6 +1166,7 @@ extern "C" int b200mpc_controller_step(b200mpc_handle* h, b200mpc_step_request* 
     auto T4 = std::chrono::steady_clock::now();
     auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
     h->t_stage += us(T0, T1); h->t_launch += us(T1, T2); h->t_sync += us(T2, T3); h->t_out += us(T3b, T4); h->t_spec += us(T3, T3b); h->t_calls++;
+    float gms = 0; if (cudaEventElapsedTime(&gms, h->tev0, h->tev1) == cudaSuccess) h->t_gpu += gms * 1e3;
   }
   const char* ho = (const char*)h->h_out;
   memcpy(rq->nominal_out, ho + o_nom, (size_t)KNU * 8);

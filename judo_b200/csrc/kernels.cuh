@@ -66,13 +66,19 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
         // on-device sampling: Philox keyed by the GLOBAL rollout index -> identical candidates however N is sharded
         const long long gn = (long long)n + ep.index_offset;
         const int KNU = K * NU;
+        if (smp.enabled == 2) {  // host-drawn normals, uploaded ahead of the step: assemble this rollout's candidate from its row
+          const double* zr = smp.z + (size_t)(gn > 0 ? gn - 1 : 0) * KNU;
 #pragma unroll
-        for (int p2 = 0; p2 < (MAXK * NU + 1) / 2; p2++) {
-          if (2 * p2 < KNU) {
-            double z0, z1;
-            normal_pair(smp, gn, p2, &z0, &z1);
-            kn[2 * p2] = sample_element(smp, gn, 2 * p2, NU, z0);
-            if (2 * p2 + 1 < MAXK * NU && 2 * p2 + 1 < KNU) kn[2 * p2 + 1] = sample_element(smp, gn, 2 * p2 + 1, NU, z1);
+          for (int e = 0; e < MAXK * NU; e++) if (e < KNU) kn[e] = sample_element_hostz(smp, gn, e, NU, gn > 0 ? __ldg(zr + e) : 0.0);
+        } else {
+#pragma unroll
+          for (int p2 = 0; p2 < (MAXK * NU + 1) / 2; p2++) {
+            if (2 * p2 < KNU) {
+              double z0, z1;
+              normal_pair(smp, gn, p2, &z0, &z1);
+              kn[2 * p2] = sample_element(smp, gn, 2 * p2, NU, z0);
+              if (2 * p2 + 1 < MAXK * NU && 2 * p2 + 1 < KNU) kn[2 * p2 + 1] = sample_element(smp, gn, 2 * p2 + 1, NU, z1);
+            }
           }
         }
 #pragma unroll
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
         const double ct = Task::step_cost(c, s, u, cp);
         if (ep.trace_q) {  // positions after step t: the elites' trace sensors are evaluated from them by the last warp (below)
 #pragma unroll
-          for (int j = 0; j < Task::NQ; j++) ep.trace_q[((size_t)n * H + t) * Task::NQ + j] = s.q[j];
+          for (int j = 0; j < Task::NQ; j++) ep.trace_q[((size_t)t * N + n) * Task::NQ + j] = s.q[j];  // time-major: a warp's stores coalesce
         }
         total += ct;
         if (cost_NH) sC[(size_t)tid * (H + 1) + t] = (float)ct;
@@ -119,17 +125,33 @@ __global__ void __launch_bounds__(128) rollout_kernel(const typename Task::Const
         // (Every rollout's trace_q stores precede its warp's ticket (threadfence + atomic), so they are visible here; __ldcg reads L2.)
         const int lane = tid & 31;
         const int nt = min(ne, ep.n_trace);
-        for (int idx = lane; idx < nt * H; idx += 32) {
-          const int e = idx / H, t = idx - e * H;
-          long long r = el[0];
+        // four (elite, step) items per lane and round, their L2 loads issued together: the stage is one warp deep, so a round costs one
+        // L2 round trip whatever it carries (one item per round made this tail ~15 us at 5 elites x 64 steps)
+        for (int base = 0; base < nt * H; base += 128) {
+          double q[4][Task::NQ];
 #pragma unroll
-          for (int i = 1; i < EP_MAXK; i++) if (i == e) r = el[i];
-          double q[Task::NQ], sens[NS];
+          for (int u = 0; u < 4; u++) {
+            const int idx = base + 32 * u + lane;
+            if (idx < nt * H) {
+              const int e = idx / H, t = idx - e * H;
+              long long r = el[0];
 #pragma unroll
-          for (int j = 0; j < Task::NQ; j++) q[j] = t == 0 ? x0[j] : __ldcg(ep.trace_q + ((size_t)r * H + (t - 1)) * Task::NQ + j);
-          Task::sensors(c, q, sens);
+              for (int i = 1; i < EP_MAXK; i++) if (i == e) r = el[i];
 #pragma unroll
-          for (int j = 0; j < NS; j++) ep.elite_sens[((size_t)e * H + t) * NS + j] = sens[j];
+              for (int j = 0; j < Task::NQ; j++) q[u][j] = t == 0 ? x0[j] : __ldcg(ep.trace_q + ((size_t)(t - 1) * N + r) * Task::NQ + j);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int idx = base + 32 * u + lane;
+            if (idx < nt * H) {
+              const int e = idx / H, t = idx - e * H;
+              double sens[NS];
+              Task::sensors(c, q[u], sens);
+#pragma unroll
+              for (int j = 0; j < NS; j++) ep.elite_sens[((size_t)e * H + t) * NS + j] = sens[j];
+            }
+          }
         }
       }
     }

@@ -19,6 +19,9 @@ struct SampleSpec {
   const double* lo;                  // (nu) clip range (may hold -inf / +inf)
   const double* hi;                  // (nu)
   double* knots_out;                 // (N, K*nu) the generated candidates (read back by the epilogue and, on request, the host)
+  // enabled == 2: the normals are the HOST's (NumPy's legacy stream, drawn and uploaded ahead of the step): ((N-1), K*nu) in the
+  // reference's draw order; the kernel only assembles clip(nominal + sigma * z) — seed parity without the candidates crossing PCIe
+  const double* z;
 };
 
 __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned (&out)[4]) {
@@ -51,6 +54,23 @@ __device__ __forceinline__ double sample_element(const SampleSpec& s, long long 
   const double v = s.nominal[e] + (n == 0 ? 0.0 : s.sigma[e] * z);
   const int j = e % nu;
   return fmin(fmax(v, s.lo[j]), s.hi[j]);
+}
+
+// the same element from a host-drawn normal, rounded exactly as NumPy rounds `nominal + sigma * noise` (two roundings, no fused
+// multiply-add) and clipped as np.clip does (compare + select: NaN stays NaN)
+__device__ __forceinline__ double sample_element_hostz(const SampleSpec& s, long long n, int e, int nu, double z) {
+#ifdef B2_HOST_SIM
+  double v = z * s.sigma[e];
+  v = v + s.nominal[e];
+#else
+  double v = __dadd_rn(__dmul_rn(z, s.sigma[e]), s.nominal[e]);
+#endif
+  if (n == 0) v = s.nominal[e];
+  const int j = e % nu;
+  const double l = s.lo[j], h = s.hi[j];
+  v = v < l ? l : v;
+  v = v > h ? h : v;
+  return v;
 }
 
 }  // namespace b2
