@@ -165,3 +165,36 @@ def test_c_abi_library_exports_every_declared_symbol():
         c = task_consts("cartpole")
         rc = lib.b200mpc_create(ctypes.byref(h), 0, c.ctypes.data, c.size, 0, 8)
         assert rc != 0 and b"CUDA" in lib.b200mpc_last_error(None)
+
+
+def test_leap_pair_list_is_mujocos_static_filter_in_mj_collision_order():
+    """The leap_cube collision pairs the oracle and the kernel share: every geom pair MuJoCo's static filters leave (same body, parent-child
+    unless one side is welded to the world, the 18 <exclude>s of leap_components/params_and_default.xml:76-101, contype/conaffinity), the
+    cube's 71 pairs first, then the hand-hand pairs body pair by body pair."""
+    from judo_b200.tasks.leap_cube import LEAP_MAXHH, leap_consts, reduced_collision_model
+    from oracle.mjc import load_table
+
+    tb = load_table("leap_cube")
+    geoms, pairs = reduced_collision_model(tb)
+    names = [b["name"] for b in tb["bodies"]]
+    body = lambda g: names[geoms[g]["body"]]  # noqa: E731
+    cube = next(i for i, g in enumerate(geoms) if g["name"] == "cube")
+    assert len(pairs) == 1692 and all(cube in p for p in pairs[:71]) and not any(cube in p for p in pairs[71:])
+    hh = pairs[71:]
+    assert len(hh) == 1621 <= LEAP_MAXHH and len({tuple(p) for p in hh}) == len(hh)
+    keys = [(geoms[a]["body"], geoms[b]["body"], a, b) for a, b in hh]
+    assert keys == sorted(keys)                                    # body-pair major, geoms of the first body outermost
+    bp = {(body(a), body(b)) for a, b in hh}
+    assert len(bp) == 106
+    excluded = [("palm", "if_bs"), ("palm", "if_px"), ("palm", "if_md"), ("palm", "th_px"), ("if_bs", "mf_bs"), ("th_mp", "rf_bs")]
+    for a, b in excluded:
+        assert (a, b) not in bp and (b, a) not in bp
+    for a, b in [("if_bs", "if_px"), ("mf_md", "mf_ds"), ("palm", "palm")]:   # parent-child (neither welded to the world) / same body
+        assert (a, b) not in bp and (b, a) not in bp
+    for a, b in [("palm", "if_ds"), ("if_bs", "if_md"), ("if_md", "mf_md"), ("rf_ds", "th_ds")]:  # fingertip-palm, grandparent, neighbours
+        assert (a, b) in bp
+    assert {g["type"] for g in geoms} == {"box", "sphere"}          # the four fingertip meshes are the only substitution
+    c = leap_consts(tb)
+    codes = c[-LEAP_MAXHH // 4:].view(np.uint16)
+    hidx = {gi: k for k, gi in enumerate(i for i in range(len(geoms)) if i != cube)}
+    assert [int(x) for x in codes[:len(hh)]] == [hidx[a] * 256 + hidx[b] for a, b in hh] and not codes[len(hh):].any()

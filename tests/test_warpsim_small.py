@@ -100,3 +100,36 @@ def test_fused_epilogue_on_emulator_matches_reference_update_rules(sim, opt, opt
     else:
         np.testing.assert_array_equal(nom, op.ps_update(knots, rew))
     np.testing.assert_allclose(np.sort(rew[elite])[::-1], np.sort(rew)[::-1][:4])
+
+
+@pytest.mark.parametrize("task,N,K", [("cartpole", 70, 4), ("cylinder_push", 45, 6)])
+def test_candidates_assembled_in_the_kernel_from_host_normals_are_bit_identical(sim, task, N, K):
+    """SampleSpec.enabled == 2 (what b200mpc_controller_step launches when the step's block of normals was drawn and uploaded ahead of it):
+    the kernel's clip(nominal + sigma * z) must equal NumPy's, bit for bit (two roundings, np.clip), row 0 the un-noised nominal, and the
+    fused step must be the step over those candidates."""
+    from judo_b200.tasks import get_registered_tasks
+
+    t = get_registered_tasks()[task][0]()
+    nu = t.nu
+    rng = np.random.default_rng(3)
+    H = 12
+    nominal = 0.4 * rng.normal(size=(K, nu))
+    sigma = 0.05 + rng.random((K, nu))
+    z = rng.normal(size=(N - 1, K, nu))
+    lo, hi = np.ascontiguousarray(t.actuator_ctrlrange[:, 0] * 0.2), np.ascontiguousarray(t.actuator_ctrlrange[:, 1] * 0.2)  # tight: clipping happens
+    ref = np.concatenate([nominal[None], nominal + sigma * z])
+    ref = np.clip(ref, lo, hi)
+    assert (ref == lo).any() and (ref == hi).any()
+    x0 = np.concatenate([t.data.qpos, t.data.qvel])
+    basis = np.ascontiguousarray(rng.random((H, K)))
+    basis /= basis.sum(1, keepdims=True)
+    params = np.ascontiguousarray(t.cost_params(), dtype=np.float64)
+    consts = np.ascontiguousarray(task_consts(task))
+    rew, nom, kout = np.zeros(N), np.zeros((K, nu)), np.zeros((N, K, nu))
+    sim.sim_plan_step_hostz.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 7 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                                               ctypes.c_double, ctypes.c_int] + [ctypes.c_void_p] * 3
+    sim.sim_plan_step_hostz(TASK[task], P(consts), P(np.ascontiguousarray(x0)), P(np.ascontiguousarray(z)), P(np.ascontiguousarray(nominal)),
+                            P(np.ascontiguousarray(sigma)), P(lo), P(hi), N, K, P(basis), H, P(params), 0.05, 32, P(rew), P(nom), P(kout))
+    assert np.array_equal(kout, ref)
+    rew2, nom2, _, _, _ = _plan_step(sim, task, x0, ref, basis, params, "mppi", [0.05], n_elite=0, want_cost=False)
+    assert np.array_equal(rew, rew2) and np.array_equal(nom, nom2)

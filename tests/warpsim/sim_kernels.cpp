@@ -105,6 +105,38 @@ static int sim_small_plan_step(const double* consts, const double* x0, const dou
   return 0;
 }
 
+// The same fused launch with the candidates assembled IN the kernel from host-drawn normals (SampleSpec.enabled == 2: what
+// b200mpc_controller_step launches when the step's block of normals was speculated and uploaded ahead of it).  z: ((N-1), K*nu).
+template <class Task>
+static int sim_small_plan_step_hostz(const double* consts, const double* x0, const double* z, const double* nominal_in, const double* sigma_in,
+                                     const double* lo, const double* hi, int N, int K, const double* basis, int H, const double* params,
+                                     double temperature, int threads, double* reward_N, double* nominal, double* knots_out) {
+  typename Task::Consts c;
+  memcpy(&c, consts, sizeof(c));
+  const int KNU = K * Task::NU, grid = (N + threads - 1) / threads, nw = grid * (threads / 32);
+  PlanEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.optimizer = EP_MPPI; ep.finalize = 1; ep.temperature = temperature;
+  std::vector<double> wm((size_t)nw * (2 + KNU) + 1), wt((size_t)nw * 2 + 1);
+  unsigned int ticket = 0;
+  ep.warp_mppi = wm.data(); ep.warp_topk = wt.data(); ep.ticket = &ticket; ep.nominal = nominal;
+  SampleSpec smp{};
+  smp.enabled = 2; smp.z = z; smp.nominal = nominal_in; smp.sigma = sigma_in; smp.lo = lo; smp.hi = hi; smp.knots_out = knots_out;
+  const size_t smem = rollout_cost_smem<Task>(threads, H, K, false);
+  wsim::set_reverse(false);
+  wsim::launch(grid, threads, smem, [&] {
+    if (K <= 4) rollout_kernel<Task, true, 4>(c, x0, 0, knots_out, N, H, K, basis, params, nullptr, nullptr, nullptr, reward_N, ep, smp);
+    else rollout_kernel<Task, true, 8>(c, x0, 0, knots_out, N, H, K, basis, params, nullptr, nullptr, nullptr, reward_N, ep, smp);
+  });
+  return 0;
+}
+extern "C" int sim_plan_step_hostz(int task, const double* consts, const double* x0, const double* z, const double* nominal_in,
+                                   const double* sigma_in, const double* lo, const double* hi, int N, int K, const double* basis, int H,
+                                   const double* params, double temperature, int threads, double* reward_N, double* nominal, double* knots_out) {
+  if (task == 0) return sim_small_plan_step_hostz<CartpoleTask>(consts, x0, z, nominal_in, sigma_in, lo, hi, N, K, basis, H, params, temperature, threads, reward_N, nominal, knots_out);
+  return sim_small_plan_step_hostz<CylinderPushTask>(consts, x0, z, nominal_in, sigma_in, lo, hi, N, K, basis, H, params, temperature, threads, reward_N, nominal, knots_out);
+}
+
 // task: 0 cartpole, 1 cylinder_push; optimizer: 0 mppi, 1 cem, 2 ps; one launch = rollout + cost + fused optimizer update
 extern "C" int sim_plan_step(int task, const double* consts, const double* x0, const double* knots, int N, int K, const double* basis, int H,
                              const double* params, int optimizer, const double* opt_params, int n_elite, int threads, float* cost_NH,
